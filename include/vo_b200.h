@@ -1,0 +1,250 @@
+/*
+ * vo_b200.h -- C ABI of libvo_b200.so, the B200-native visual-odometry front-end.
+ *
+ * Drop-in boundary for the per-frame hot path of Gautham-JS/ROS_Stereo_SLAM.  The
+ * reference has no FFI/plugin interface: the path sits behind C++ member functions
+ * of `class visualSLAM` (reference include/visualSLAM.h:152-169), called only from
+ * visualSLAM::initSequence (reference src/VisualSLAM.cpp:31,64,112,123).  Each entry
+ * point below cites the reference member function (file:line in the reference tree)
+ * it replaces; INTEGRATION.md shows the ~30-line C++ shim that converts cv::Mat /
+ * std::vector to these raw pointers inside the ROS node.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no C++/torch types.  Every function returns
+ *     VO_OK (0) or a negative VO_ERR_*; nothing throws or aborts.
+ *   - all pointers are HOST pointers owned by the caller unless the name ends in
+ *     `_dev` / the doc says "device"; outputs have caller-provided capacity and the
+ *     number written is returned through an int*.
+ *   - 2-D points are interleaved float32 (x,y) = cv::Point2f; 3-D points are
+ *     interleaved float32 (x,y,z) = cv::Point3f; images are 8-bit, 1 channel,
+ *     row-major with `stride` bytes per row (cv::Mat::step).
+ *   - results are complete (stream-synchronised) on return.
+ *   - one vo_ctx per host thread / per GPU; calls on one ctx are serialised by the
+ *     caller (the reference is single-threaded on this path).
+ *   - there is NO CPU fallback: without a CUDA device vo_create fails with
+ *     VO_ERR_NO_DEVICE.
+ */
+#ifndef VO_B200_H
+#define VO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VO_B200_ABI_VERSION 1
+
+enum {
+  VO_OK = 0,
+  VO_ERR_INVALID_ARG = -1,
+  VO_ERR_NO_DEVICE = -2,      /* no CUDA device / driver: the library never computes on the CPU */
+  VO_ERR_CUDA = -3,           /* a CUDA call failed; see vo_last_error() */
+  VO_ERR_CAPACITY = -4,       /* caller buffer or ctx max_points / max_hypotheses too small */
+  VO_ERR_TOO_FEW_POINTS = -5, /* fewer correspondences than the minimal solver needs */
+  VO_ERR_NO_MODEL = -6,       /* RANSAC never found a model with enough inliers */
+  VO_ERR_LOW_INLIERS = -7,    /* both PnP attempts gave < pnp_min_inliers: the reference's
+                                 SHUTDOWN_FLAG (src/keyFrameManagement.cpp:89-92) */
+  VO_ERR_NOT_IMPLEMENTED = -8
+};
+
+/* minimal solvers for vo_pnp_ransac */
+enum { VO_PNP_EPNP5 = 0, VO_PNP_P3P4 = 1 };
+
+typedef struct vo_ctx vo_ctx;
+
+/* Parameters.  vo_default_params() fills the reference's compile-time constants. */
+typedef struct vo_params {
+  double fx, fy, cx, cy;      /* 718.856, 718.856, 607.1928, 185.2157  (include/visualSLAM.h:82-87) */
+  double baseline;            /* 0.54                                   (include/visualSLAM.h:68)    */
+  int width, height;          /* 1241, 376 */
+  int channels;               /* 1 (3 = the reference's BGR input; not implemented yet) */
+  int lk_win;                 /* 21   cv::calcOpticalFlowPyrLK defaults (src/tracking.cpp:18,52) */
+  int lk_max_level;           /* 3  */
+  int lk_max_iters;           /* 30 */
+  double lk_eps;              /* 0.01 */
+  double lk_min_eig;          /* 1e-4 */
+  int grid_step;              /* 30   (src/triangulation.cpp:89) */
+  double f_thr_stereo;        /* 3.0  (src/tracking.cpp:34) */
+  double f_thr_temporal;      /* 1.0  (src/tracking.cpp:75) */
+  double f_conf;              /* 0.99 */
+  int f_max_iters;            /* 1000 (cv::findFundamentalMat default maxIters) */
+  int pnp_iters;              /* 100  (src/keyFrameManagement.cpp:84) */
+  double pnp_thr;             /* 1.0  */
+  double pnp_conf;            /* 0.99 */
+  int pnp_retry_iters;        /* 100  (src/keyFrameManagement.cpp:88) */
+  double pnp_retry_thr;       /* 8.0  */
+  double pnp_retry_conf;      /* 0.98 */
+  int pnp_min_inliers;        /* 10   (src/keyFrameManagement.cpp:85,89) */
+  int kf_min_inliers;         /* 200  keyframe rule (src/VisualSLAM.cpp:120), used by vo_seq_* only */
+  int ransac_exhaustive;      /* 0: score only the hypotheses OpenCV's adaptive stop would reach.
+                                 1: solve and score all `iters` hypotheses (the BASELINE workload);
+                                 results are identical either way (early-exit semantics kept). */
+  int max_points;             /* capacity: keypoints per call (default 131072) */
+  int max_hypotheses;         /* capacity: RANSAC samples per call (default 4096) */
+  int device;                 /* CUDA device ordinal */
+} vo_params;
+
+void vo_default_params(vo_params* p);
+int vo_abi_version(void);
+const char* vo_last_error(void);         /* thread-local message of the last failure */
+const char* vo_strerror(int code);
+
+int vo_create(const vo_params* p, vo_ctx** out);
+int vo_destroy(vo_ctx* ctx);
+
+/* ---- a-1  visualSLAM::denseKeypointExtractor(img, step)      src/tracking.cpp:4-12 ----
+ * Raster grid (y-major, x fastest) over a rows x cols image; xy receives up to cap points. */
+int vo_grid_keypoints(vo_ctx* ctx, int rows, int cols, int step, float* xy, int cap, int* n);
+
+/* ---- a-2  adaptiveNonMaximalSuppresion(keypoints, numToKeep) src/ANMS.cpp:18-67 ----
+ * keep_idx receives the indices (into the input) of the kept keypoints in canonical
+ * order (response desc, index asc).  n < num_keep keeps everything (ANMS.cpp:21);
+ * n == num_keep is rejected (the reference reads out of bounds, ANMS.cpp:59). */
+int vo_anms(vo_ctx* ctx, const float* xy, const float* response, int n, int num_keep,
+            int32_t* keep_idx, int cap, int* n_keep);
+
+/* ---- a-3  cv::calcOpticalFlowPyrLK(prev, next, prevPts, nextPts, status, err) with all
+ * defaults, as called at src/tracking.cpp:18 and :52.  Raw outputs (no compaction);
+ * err may be NULL. */
+int vo_lk_track(vo_ctx* ctx, const uint8_t* prev, const uint8_t* next, int stride,
+                const float* prev_xy, int n, float* next_xy, uint8_t* status, float* err);
+
+/* buildOpticalFlowPyramid intermediates, for parity tests: level `level` of the pyramid
+ * of `img` (tight, w x h bytes) and its Scharr derivative (w x h x 2 int16); either
+ * output may be NULL.  w/h receive the level size. */
+int vo_debug_pyramid_level(vo_ctx* ctx, const uint8_t* img, int stride, int level,
+                           uint8_t* out_level, int16_t* out_deriv, int* w, int* h);
+
+/* ---- a-5  cv::findFundamentalMat(pts1, pts2, FM_RANSAC, thr, conf, mask)
+ * src/tracking.cpp:34 (thr 3.0) and :75 (thr 1.0).
+ * samples7: NULL -> OpenCV's RNG stream (seed 0xFFFFFFFFFFFFFFFF) incl. the collinearity
+ * subset check; else an n_samples x 7 replay list of accepted subsets.  mask receives n
+ * bytes (0/1); F (row-major 3x3) and n_inliers may be NULL.  Requires n >= 15 (below that
+ * OpenCV switches estimator; VO_ERR_TOO_FEW_POINTS). */
+int vo_fmat_ransac(vo_ctx* ctx, const float* xy1, const float* xy2, int n, double thr, double conf,
+                   const int32_t* samples7, int n_samples, uint8_t* mask, double F[9], int* n_inliers);
+
+/* ---- a-6  cv::triangulatePoints(P1, P2, pt1, pt2) + float dehomogenisation
+ * src/triangulation.cpp:152-160.  P1, P2 row-major 3x4. */
+int vo_triangulate(vo_ctx* ctx, const double P1[12], const double P2[12],
+                   const float* xy1, const float* xy2, int n, float* xyz);
+
+/* ---- a-7  cv::solvePnPRansac(p3d, p2d, K, 0, rvec, tvec, false, iters, thr, conf, inliers)
+ * src/keyFrameManagement.cpp:84,88.  K comes from the ctx params.  samples: NULL -> OpenCV's
+ * RNG stream; else n_samples x 5 (EPNP5) or x 4 (P3P4) replay list.  inliers receives up to
+ * cap ascending indices of the best model's inliers (before refinement, as OpenCV);
+ * rvec/tvec are the LM-refined pose. */
+int vo_pnp_ransac(vo_ctx* ctx, const float* xyz, const float* xy, int n, int iters, double thr, double conf,
+                  int min_solver, const int32_t* samples, int n_samples,
+                  double rvec[3], double tvec[3], int32_t* inliers, int cap, int* n_inl);
+
+/* Per-hypothesis view of the last vo_pnp_ransac / vo_fmat_ransac call, for parity tests:
+ * PnP: models = n_h x 6 (rvec,tvec), counts = n_h inlier counts (-1 = solver failed).
+ * F:   models = n_h x 3 x 9, counts = n_h x 3 (-1 = no such root).  Any pointer may be NULL. */
+int vo_debug_last_pnp(vo_ctx* ctx, double* models, int32_t* counts, int cap_h, int* n_h, int* best, int* n_iters);
+int vo_debug_last_fmat(vo_ctx* ctx, double* models, int32_t* counts, int cap_h, int* n_h, int* best_sample,
+                       int* best_model, int* n_iters);
+
+/* ---- a-9  visualSLAM::update3dtransformation(pts, pose3x4)  src/keyFrameManagement.cpp:33-46
+ * (same loop as insertKeyFrames :20-30).  M row-major 3x4 double. */
+int vo_transform_points(vo_ctx* ctx, const double M[12], const float* xyz_in, int n, float* xyz_out);
+
+/* ---- a-8  Rodrigues + inversion, src/VisualSLAM.cpp:70-74,93-97: pose3x4 = [R^T | -R^T tvec]. */
+int vo_pose_from_pnp(const double rvec[3], const double tvec[3], double pose3x4[12]);
+
+/* ================= fused stage entry points = the reference's method boundaries ================= */
+
+/* visualSLAM::denseLKtracking  src/tracking.cpp:14-28: LK + status==1 compaction.
+ * ref_xy (n points) is read; ref_out/trk_out receive the m survivors in order. */
+int vo_dense_lk_tracking(vo_ctx* ctx, const uint8_t* ref_img, const uint8_t* cur_img, int stride,
+                         const float* ref_xy, int n, float* ref_out, float* trk_out, int* m);
+
+/* visualSLAM::FmatThresholding  src/tracking.cpp:30-43 (thr = params.f_thr_stereo). */
+int vo_fmat_thresholding(vo_ctx* ctx, const float* ref_xy, const float* trk_xy, int n,
+                         float* ref_out, float* trk_out, int* m);
+
+/* visualSLAM::stereoTriangulate  src/triangulation.cpp:73-166 (DENSE_FLAG branch):
+ * grid(params.grid_step) -> LK left->right -> status compaction -> F-RANSAC(f_thr_stereo)
+ * -> compaction -> triangulate with P1=K[I|0], P2=K[I|-b e1].  xyz is in the LEFT CAMERA
+ * frame.  A NULL image returns VO_ERR_INVALID_ARG (the reference prints and returns). */
+int vo_stereo_triangulate(vo_ctx* ctx, const uint8_t* left, const uint8_t* right, int stride,
+                          float* xyz, float* xy_left, int cap, int* n);
+
+/* visualSLAM::insertKeyFrames  src/keyFrameManagement.cpp:9-31: stereoTriangulate + transform
+ * by pose3x4 (camera->world).  xyz_cam (the reference's `untransformed`) may be NULL. */
+int vo_insert_keyframe(vo_ctx* ctx, const uint8_t* left, const uint8_t* right, int stride,
+                       const double pose3x4[12], float* xyz_world, float* xy_left, float* xyz_cam,
+                       int cap, int* n);
+
+/* visualSLAM::PyrLKtrackFrame2Frame  src/tracking.cpp:46-91: LK ref->cur, status compaction,
+ * F-RANSAC(f_thr_temporal), mask compaction (loop bound fixed to inIdx.size()).
+ * Outputs: tracked 2-D, their 3-D points, and the surviving REFERENCE 2-D points
+ * (inlierReferencePyrLKPts, tracking.cpp:90; may be NULL). */
+int vo_track_frame(vo_ctx* ctx, const uint8_t* ref_img, const uint8_t* cur_img, int stride,
+                   const float* ref_xy, const float* ref_xyz, int n,
+                   float* trk_xy, float* trk_xyz, float* ref_xy_inl, int* n_out);
+
+/* visualSLAM::PerspectiveNpointEstimation  src/keyFrameManagement.cpp:73-94:
+ * vo_track_frame + solvePnPRansac(pnp_iters, pnp_thr, pnp_conf); if < pnp_min_inliers retry
+ * with (pnp_retry_*); still < pnp_min_inliers -> VO_ERR_LOW_INLIERS (outputs still written).
+ * attempt_used = 1 or 2. */
+int vo_pnp_frame(vo_ctx* ctx, const uint8_t* ref_img, const uint8_t* cur_img, int stride,
+                 const float* ref_xy, const float* ref_xyz, int n,
+                 float* trk_xy, float* trk_xyz, float* ref_xy_inl, int* n_trk,
+                 double rvec[3], double tvec[3], int32_t* inliers, int cap_inl, int* n_inl, int* attempt_used);
+
+/* ================= device-resident sequence driver ================================================
+ * The hot-path part of the per-frame loop of visualSLAM::initSequence (src/VisualSLAM.cpp:31,
+ * 58-64,70-74,93-97,120-151) with all state (reference image pyramid, reference 2-D/3-D points)
+ * kept in HBM between frames; only the pose and the counters cross PCIe per frame.  Images may
+ * be host pointers (copied H2D inside the call) or device pointers (is_device != 0). */
+typedef struct vo_frame_result {
+  double rvec[3], tvec[3];   /* solvePnPRansac output (world -> camera)        */
+  double pose3x4[12];        /* [R|t] camera -> world, src/VisualSLAM.cpp:70-97 */
+  int n_lk_in;               /* keypoints that entered the temporal LK          */
+  int n_tracked;             /* after status + F-RANSAC compaction              */
+  int n_inliers;             /* PnP inliers                                     */
+  int attempt_used;          /* 1 or 2                                          */
+  int keyframe;              /* 1 if a keyframe was inserted on this frame      */
+  int n_kf_points;           /* points of the new keyframe (if keyframe)        */
+  int n_lk_in_stereo;        /* keypoints that entered the stereo LK (if keyframe) */
+} vo_frame_result;
+
+int vo_seq_init(vo_ctx* ctx, const uint8_t* left, const uint8_t* right, int stride, int is_device, int* n_points);
+int vo_seq_track(vo_ctx* ctx, const uint8_t* left, const uint8_t* right, int stride, int is_device,
+                 int force_keyframe, vo_frame_result* out);
+/* current reference set (after the last vo_seq_* call); any pointer may be NULL */
+int vo_seq_get_reference(vo_ctx* ctx, float* xy, float* xyz, int cap, int* n);
+
+/* ================= harness / measurement helpers ================================================= */
+void* vo_cuda_stream(vo_ctx* ctx);   /* cudaStream_t every kernel of this ctx is launched on */
+int vo_sync(vo_ctx* ctx);
+/* per-kernel device timing: when enabled, every launch of the named kernel families is bracketed
+ * by CUDA events on the ctx stream; vo_profile_read returns launches and summed milliseconds. */
+enum { VO_K_PYRAMID = 0, VO_K_LK = 1, VO_K_COMPACT = 2, VO_K_FMAT_SOLVE = 3, VO_K_FMAT_SCORE = 4,
+       VO_K_TRIANGULATE = 5, VO_K_PNP_SOLVE = 6, VO_K_PNP_SCORE = 7, VO_K_PNP_REFINE = 8,
+       VO_K_SELECT = 9, VO_K_MISC = 10, VO_K_COUNT = 11 };
+int vo_profile_enable(vo_ctx* ctx, int on);
+int vo_profile_read(vo_ctx* ctx, int kernel, int64_t* launches, double* ms, int reset);
+int64_t vo_launch_count(vo_ctx* ctx);          /* kernels launched by this ctx since creation */
+/* LK work counters of the last LK launch: point-levels processed and LK iterations executed
+ * (the units of the LK roofline in DESIGN.md). */
+int vo_lk_work(vo_ctx* ctx, int64_t* point_levels, int64_t* iterations);
+/* FP32 issue-rate microbenchmark (dependent FFMA chains on every SM): TFLOP/s achieved. */
+int vo_measure_fp32_peak(vo_ctx* ctx, double* tflops);
+/* synthetic scene renderer (harness only; same scene as oracle/synth.py): renders frame
+ * `frame` of scene `seed` into a DEVICE buffer of width*height bytes.  eye 0 = left, 1 = right. */
+int vo_synth_render_dev(vo_ctx* ctx, int seed, int frame, int eye, uint8_t* out_dev);
+/* pinned host memory + plain device memory for the harness */
+int vo_alloc_host(void** p, uint64_t bytes);
+int vo_free_host(void* p);
+int vo_alloc_dev(vo_ctx* ctx, void** p, uint64_t bytes);
+int vo_free_dev(vo_ctx* ctx, void* p);
+int vo_memcpy_d2h(vo_ctx* ctx, void* dst_host, const void* src_dev, uint64_t bytes);
+int vo_memcpy_h2d(vo_ctx* ctx, void* dst_dev, const void* src_host, uint64_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VO_B200_H */

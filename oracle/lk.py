@@ -1,0 +1,261 @@
+"""Scalar restatement of OpenCV's pyramidal Lucas-Kanade.  TEST INFRASTRUCTURE ONLY.
+
+Restates what cv::calcOpticalFlowPyrLK does when the reference calls it with
+all defaults (src/tracking.cpp:18,52 of the reference tree: winSize 21x21,
+maxLevel 3, criteria (COUNT+EPS, 30, 0.01), flags 0, minEigThreshold 1e-4):
+buildOpticalFlowPyramid (pyrDown 5-tap [1 4 6 4 1], REFLECT_101), the Scharr
+derivative of the previous image, and the per-level iteration in 14-bit
+fixed-point bilinear arithmetic.  The integer window sums are accumulated
+exactly here (OpenCV accumulates them in float lanes), so positions agree with
+cv2 to ~1e-5 px, not bit-exactly; pyramids and derivatives are bit-exact.
+tests/test_oracle_lk.py pins all of this against cv2.
+
+It also counts the iterations actually executed per (point, level), which is
+the figure the LK roofline in DESIGN.md is computed from.
+"""
+import numpy as np
+
+try:
+    import numba
+    _njit = numba.njit(cache=True)
+except Exception:  # pragma: no cover
+    def _njit(f):
+        return f
+
+W_BITS = 14
+FLT_SCALE = np.float32(1.0 / (1 << 20))
+FLT_EPSILON = np.float32(1.1920929e-07)
+
+
+def reflect101(i, n):
+    i = np.asarray(i)
+    i = np.where(i < 0, -i, i)
+    i = np.where(i >= n, 2 * (n - 1) - i, i)
+    return i
+
+
+def pyr_down(img):
+    """cv::pyrDown for u8, 1 channel: separable [1 4 6 4 1], (sum + 128) >> 8,
+    BORDER_REFLECT_101, output ((w+1)/2, (h+1)/2)."""
+    h, w = img.shape
+    oh, ow = (h + 1) // 2, (w + 1) // 2
+    src = img.astype(np.int32)
+    k = (1, 4, 6, 4, 1)
+    # horizontal on every source row, at even columns
+    cols = [reflect101(2 * np.arange(ow) + d, w) for d in (-2, -1, 0, 1, 2)]
+    hor = sum(kk * src[:, c] for kk, c in zip(k, cols))
+    rows = [reflect101(2 * np.arange(oh) + d, h) for d in (-2, -1, 0, 1, 2)]
+    ver = sum(kk * hor[r, :] for kk, r in zip(k, rows))
+    return ((ver + 128) >> 8).astype(np.uint8)
+
+
+def build_pyramid(img, max_level=3, win=21):
+    """Levels 0..L of buildOpticalFlowPyramid (unpadded); stops early when the
+    next level would not be larger than the window."""
+    levels = [np.ascontiguousarray(img)]
+    for _ in range(max_level):
+        nxt = pyr_down(levels[-1])
+        if nxt.shape[1] <= win or nxt.shape[0] <= win:
+            break
+        levels.append(nxt)
+    return levels
+
+
+def scharr_deriv(img):
+    """calcSharrDeriv: int16 (h, w, 2) = (dx, dy), REFLECT_101 1-px border, gain 32."""
+    h, w = img.shape
+    s = img.astype(np.int32)
+    up = s[reflect101(np.arange(h) - 1, h), :]
+    dn = s[reflect101(np.arange(h) + 1, h), :]
+    smooth = (up + dn) * 3 + s * 10      # vertical smoothing
+    diff = dn - up                        # vertical derivative
+    xl = reflect101(np.arange(w) - 1, w)
+    xr = reflect101(np.arange(w) + 1, w)
+    dx = smooth[:, xr] - smooth[:, xl]
+    dy = (diff[:, xl] + diff[:, xr]) * 3 + diff * 10
+    return np.stack([dx, dy], -1).astype(np.int16)
+
+
+def pad_reflect101(img, b):
+    return np.pad(img, ((b, b), (b, b)), mode="reflect")
+
+
+def pad_zero(d, b):
+    return np.pad(d, ((b, b), (b, b), (0, 0)), mode="constant")
+
+
+@_njit
+def _cv_round_f32(v):
+    # cvRound(float): round half to even
+    return int(np.rint(v))
+
+
+@_njit
+def _weights(a, b):
+    one = np.float32(1.0)
+    s = np.float32(1 << 14)
+    iw00 = _cv_round_f32((one - a) * (one - b) * s)
+    iw01 = _cv_round_f32(a * (one - b) * s)
+    iw10 = _cv_round_f32((one - a) * b * s)
+    iw11 = (1 << 14) - iw00 - iw01 - iw10
+    return iw00, iw01, iw10, iw11
+
+
+@_njit
+def _track_level(Ipad, Dpad, Jpad, rows, cols, level, max_level, win, max_count, eps, min_eig_thr,
+                 prev_pts, next_pts, status, err, iters_out):
+    """One pyramid level of LKTrackerInvoker for every point.  Ipad/Jpad are the
+    REFLECT_101-padded (by win) levels, Dpad the zero-padded derivative."""
+    n = prev_pts.shape[0]
+    half = np.float32((win - 1) * 0.5)
+    scale = np.float32(1.0 / (1 << level))
+    Iw = np.zeros((win, win), np.int32)
+    Ix = np.zeros((win, win), np.int32)
+    Iy = np.zeros((win, win), np.int32)
+    flt_scale = np.float32(1.0 / (1 << 20))
+    for p in range(n):
+        px = np.float32(prev_pts[p, 0] * scale)
+        py = np.float32(prev_pts[p, 1] * scale)
+        if level == max_level:
+            nx = px
+            ny = py
+        else:
+            nx = np.float32(next_pts[p, 0] * np.float32(2.0))
+            ny = np.float32(next_pts[p, 1] * np.float32(2.0))
+        next_pts[p, 0] = nx
+        next_pts[p, 1] = ny
+        px = np.float32(px - half)
+        py = np.float32(py - half)
+        ipx = int(np.floor(px))
+        ipy = int(np.floor(py))
+        if ipx < -win or ipx >= cols or ipy < -win or ipy >= rows:
+            if level == 0:
+                status[p] = 0
+                err[p] = 0
+            continue
+        a = np.float32(px - np.float32(ipx))
+        b = np.float32(py - np.float32(ipy))
+        iw00, iw01, iw10, iw11 = _weights(a, b)
+        sA11 = 0
+        sA12 = 0
+        sA22 = 0
+        for y in range(win):
+            for x in range(win):
+                yy = y + ipy + win
+                xx = x + ipx + win
+                ival = (int(Ipad[yy, xx]) * iw00 + int(Ipad[yy, xx + 1]) * iw01
+                        + int(Ipad[yy + 1, xx]) * iw10 + int(Ipad[yy + 1, xx + 1]) * iw11 + (1 << 8)) >> 9
+                ixv = (int(Dpad[yy, xx, 0]) * iw00 + int(Dpad[yy, xx + 1, 0]) * iw01
+                       + int(Dpad[yy + 1, xx, 0]) * iw10 + int(Dpad[yy + 1, xx + 1, 0]) * iw11 + (1 << 13)) >> 14
+                iyv = (int(Dpad[yy, xx, 1]) * iw00 + int(Dpad[yy, xx + 1, 1]) * iw01
+                       + int(Dpad[yy + 1, xx, 1]) * iw10 + int(Dpad[yy + 1, xx + 1, 1]) * iw11 + (1 << 13)) >> 14
+                Iw[y, x] = ival
+                Ix[y, x] = ixv
+                Iy[y, x] = iyv
+                sA11 += ixv * ixv
+                sA12 += ixv * iyv
+                sA22 += iyv * iyv
+        A11 = np.float32(np.float32(sA11) * flt_scale)
+        A12 = np.float32(np.float32(sA12) * flt_scale)
+        A22 = np.float32(np.float32(sA22) * flt_scale)
+        D = np.float32(np.float32(A11 * A22) - np.float32(A12 * A12))
+        dd = np.float32(A11 - A22)
+        q = np.float32(np.float32(dd * dd) + np.float32(np.float32(np.float32(4.0) * A12) * A12))
+        min_eig = np.float32(np.float32(np.float32(A22 + A11) - np.float32(np.sqrt(q))) / np.float32(2 * win * win))
+        if min_eig < min_eig_thr or D < np.float32(1.1920929e-07):
+            if level == 0:
+                status[p] = 0
+            continue
+        D = np.float32(np.float32(1.0) / D)
+        nx = np.float32(nx - half)
+        ny = np.float32(ny - half)
+        pdx = np.float32(0.0)
+        pdy = np.float32(0.0)
+        j = 0
+        while j < max_count:
+            inx = int(np.floor(nx))
+            iny = int(np.floor(ny))
+            if inx < -win or inx >= cols or iny < -win or iny >= rows:
+                if level == 0:
+                    status[p] = 0
+                break
+            a = np.float32(nx - np.float32(inx))
+            b = np.float32(ny - np.float32(iny))
+            iw00, iw01, iw10, iw11 = _weights(a, b)
+            sb1 = 0
+            sb2 = 0
+            for y in range(win):
+                for x in range(win):
+                    yy = y + iny + win
+                    xx = x + inx + win
+                    jv = (int(Jpad[yy, xx]) * iw00 + int(Jpad[yy, xx + 1]) * iw01
+                          + int(Jpad[yy + 1, xx]) * iw10 + int(Jpad[yy + 1, xx + 1]) * iw11 + (1 << 8)) >> 9
+                    diff = jv - Iw[y, x]
+                    sb1 += diff * Ix[y, x]
+                    sb2 += diff * Iy[y, x]
+            iters_out[p] += 1
+            b1 = np.float32(np.float32(sb1) * flt_scale)
+            b2 = np.float32(np.float32(sb2) * flt_scale)
+            dx = np.float32(np.float32(np.float32(A12 * b2) - np.float32(A22 * b1)) * D)
+            dy = np.float32(np.float32(np.float32(A12 * b1) - np.float32(A11 * b2)) * D)
+            nx = np.float32(nx + dx)
+            ny = np.float32(ny + dy)
+            next_pts[p, 0] = np.float32(nx + half)
+            next_pts[p, 1] = np.float32(ny + half)
+            if float(dx) * float(dx) + float(dy) * float(dy) <= eps:
+                break
+            if j > 0 and abs(float(np.float32(dx + pdx))) < 0.01 and abs(float(np.float32(dy + pdy))) < 0.01:
+                next_pts[p, 0] = np.float32(next_pts[p, 0] - np.float32(dx * np.float32(0.5)))
+                next_pts[p, 1] = np.float32(next_pts[p, 1] - np.float32(dy * np.float32(0.5)))
+                break
+            pdx = dx
+            pdy = dy
+            j += 1
+        if status[p] != 0 and level == 0:
+            fx = np.float32(next_pts[p, 0] - half)
+            fy = np.float32(next_pts[p, 1] - half)
+            inx = int(np.floor(fx))
+            iny = int(np.floor(fy))
+            if inx < -win or inx >= cols or iny < -win or iny >= rows:
+                status[p] = 0
+                continue
+            a = np.float32(fx - np.float32(inx))
+            b = np.float32(fy - np.float32(iny))
+            iw00, iw01, iw10, iw11 = _weights(a, b)
+            e = 0
+            for y in range(win):
+                for x in range(win):
+                    yy = y + iny + win
+                    xx = x + inx + win
+                    jv = (int(Jpad[yy, xx]) * iw00 + int(Jpad[yy, xx + 1]) * iw01
+                          + int(Jpad[yy + 1, xx]) * iw10 + int(Jpad[yy + 1, xx + 1]) * iw11 + (1 << 8)) >> 9
+                    e += abs(jv - Iw[y, x])
+            err[p] = np.float32(np.float32(e) * np.float32(1.0 / (32 * win * win)))
+
+
+def calc_optical_flow_pyr_lk(prev_img, next_img, prev_pts, win=21, max_level=3, max_count=30, eps=0.01,
+                             min_eig_thr=1e-4, return_iters=False):
+    """Restated cv2.calcOpticalFlowPyrLK(prev, next, pts, None) for 1-channel u8.
+    Returns (next_pts (N,2) f32, status (N,) u8, err (N,) f32[, iters (levels,N)])."""
+    prev_pts = np.ascontiguousarray(prev_pts, np.float32).reshape(-1, 2)
+    n = len(prev_pts)
+    max_count = min(max(max_count, 0), 100)
+    eps = min(max(eps, 0.0), 10.0)
+    eps = eps * eps
+    lp = build_pyramid(prev_img, max_level, win)
+    ln = build_pyramid(next_img, max_level, win)
+    L = len(lp) - 1
+    next_pts = np.zeros((n, 2), np.float32)
+    status = np.ones(n, np.uint8)
+    err = np.zeros(n, np.float32)
+    iters = np.zeros((L + 1, n), np.int32)
+    for level in range(L, -1, -1):
+        I = lp[level]
+        Ipad = pad_reflect101(I, win)
+        Dpad = pad_zero(scharr_deriv(I), win)
+        Jpad = pad_reflect101(ln[level], win)
+        _track_level(Ipad, Dpad, Jpad, I.shape[0], I.shape[1], level, L, win, max_count, eps,
+                     np.float32(min_eig_thr), prev_pts, next_pts, status, err, iters[level])
+    if return_iters:
+        return next_pts, status, err, iters
+    return next_pts, status, err

@@ -1,0 +1,39 @@
+// Host build of ros_stereo_slam_b200/csrc/cvmath.cuh for CPU-side unit tests.
+// TEST TOOL ONLY: it lets tests/test_hostmath.py pin the device numerics against cv2
+// in a container without a GPU.  libvo_b200.so never links or calls this.
+#include "../../ros_stereo_slam_b200/csrc/cvmath.cuh"
+#include "../../ros_stereo_slam_b200/csrc/fmat7.cuh"
+#include <string.h>
+using namespace vo;
+extern "C" {
+void hm_svd(const double* A, int n, double* w, double* u, double* vt) {
+  switch (n) {
+    case 3: svd_square<3>(A, w, u, vt); break;
+    case 4: svd_square<4>(A, w, u, vt); break;
+    case 12: svd_square<12>(A, w, u, vt); break;
+  }
+}
+void hm_solve(const double* A, const double* b, int n, double* x) {
+  if (n == 3) solve_svd<6, 3>(A, b, x);
+  if (n == 4) solve_svd<6, 4>(A, b, x);
+  if (n == 5) solve_svd<6, 5>(A, b, x);
+}
+void hm_invert3(const double* A, double* inv) { invert3_svd(A, inv); }
+void hm_mtm12(const double* M, int rows, int fma_, double* out) {
+  if (fma_) mul_transposed<12, true>(M, rows, out); else mul_transposed<12, false>(M, rows, out);
+}
+void hm_epnp5(const float* obj, const float* img, const double* K4, int fma_, double* rvec, double* tvec, double* R) {
+  Intrinsics K{K4[0], K4[1], K4[2], K4[3]};
+  double t[3];
+  if (fma_) epnp5<true>(obj, img, K, R, t); else epnp5<false>(obj, img, K, R, t);
+  rodrigues_mat2vec(R, rvec);
+  for (int i = 0; i < 3; i++) tvec[i] = t[i];
+}
+void hm_rodrigues_v2m(const double* r, double* R) { rodrigues_vec2mat(r, R); }
+void hm_triangulate(const double* P1, const double* P2, const float* xy1, const float* xy2, int n, float* xyz, float* h4) {
+  for (int i = 0; i < n; i++)
+    triangulate_dlt(P1, P2, xy1[2 * i], xy1[2 * i + 1], xy2[2 * i], xy2[2 * i + 1], xyz + 3 * i, h4 ? h4 + 4 * i : nullptr);
+}
+int hm_fmat7(const float* m1, const float* m2, double* F) { return fmat_7point(m1, m2, F); }
+int hm_solve_cubic(const double* c, double* r) { return solve_cubic(c, r); }
+}

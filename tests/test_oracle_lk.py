@@ -1,0 +1,41 @@
+"""Pins oracle.lk (scalar restatement) against cv2: pyramids and Scharr
+derivatives bit-exact, tracks within 1e-4 px, status identical."""
+import numpy as np
+import cv2
+import pytest
+
+from oracle import lk, synth, glue
+
+
+@pytest.fixture(scope="module")
+def frames():
+    sc = synth.Scene(0)
+    return sc.render(0, "L"), sc.render(1, "L"), sc.render(0, "R")
+
+
+def test_pyramid_and_scharr_bit_exact(frames):
+    L0, _, _ = frames
+    n, pyr = cv2.buildOpticalFlowPyramid(L0, (21, 21), 3, withDerivatives=True)
+    assert n == 3
+    mine = lk.build_pyramid(L0, 3, 21)
+    assert [m.shape for m in mine] == [(376, 1241), (188, 621), (94, 311), (47, 156)]
+    for l in range(4):
+        assert np.array_equal(pyr[2 * l], mine[l])
+        assert np.array_equal(pyr[2 * l + 1], lk.scharr_deriv(mine[l]))
+
+
+@pytest.mark.parametrize("pair", ["temporal", "stereo"])
+def test_lk_tracks_match_cv2(frames, pair):
+    L0, L1, R0 = frames
+    nxt = L1 if pair == "temporal" else R0
+    pts = glue.dense_keypoint_extractor(376, 1241, 30)
+    extra = np.array([[5, 5], [1236, 371], [0.4, 200.7], [1240.2, 3.3], [620.5, 375.9]], np.float32)
+    pts = np.concatenate([pts, extra])
+    p1, st1, err1 = cv2.calcOpticalFlowPyrLK(L0, nxt, pts.reshape(-1, 1, 2), None)
+    p2, st2, err2, iters = lk.calc_optical_flow_pyr_lk(L0, nxt, pts, return_iters=True)
+    assert np.array_equal(st1.ravel(), st2)
+    d = np.abs(p1.reshape(-1, 2) - p2).max(1)
+    assert d[st2 == 1].max() < 1e-4
+    assert np.median(d) < 1e-6
+    assert np.abs(err1.ravel() - err2)[st2 == 1].max() < 1e-3
+    assert iters.sum() > 0
