@@ -32,6 +32,9 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
 
 #define VO_B200_ABI_VERSION 1
 
@@ -244,6 +247,9 @@ int vo_free_dev(vo_ctx* ctx, void* p);
 int vo_memcpy_d2h(vo_ctx* ctx, void* dst_host, const void* src_dev, uint64_t bytes);
 int vo_memcpy_h2d(vo_ctx* ctx, void* dst_dev, const void* src_host, uint64_t bytes);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

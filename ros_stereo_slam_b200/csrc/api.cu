@@ -1,0 +1,1003 @@
+// api.cu -- the C ABI of include/vo_b200.h: context, host-side orchestration of the stages
+// (the reference's method boundaries, include/visualSLAM.h:152-169 of the reference tree),
+// OpenCV-compatible RANSAC sample generation, and the device-resident sequence driver.
+// No CPU compute path exists: every stage launches the CUDA kernels of this library.
+#include <math.h>
+#include <stdarg.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "cvmath.cuh"
+
+using namespace vo;
+
+// ------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+
+namespace vo {
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+LaunchScope::LaunchScope(vo_ctx* ctx, int k) : c(ctx), kind(k) {
+  c->launch_count++;
+  if (c->prof.on) {
+    auto get = [&]() {
+      cudaEvent_t e;
+      if (!c->prof.pool.empty()) {
+        e = c->prof.pool.back();
+        c->prof.pool.pop_back();
+      } else {
+        cudaEventCreate(&e);
+      }
+      return e;
+    };
+    a = get();
+    b = get();
+    cudaEventRecord(a, c->stream);
+  }
+}
+LaunchScope::~LaunchScope() {
+  if (a) {
+    cudaEventRecord(b, c->stream);
+    c->prof.pending.push_back({kind, a, b});
+  }
+}
+}  // namespace vo
+
+static void prof_drain(vo_ctx* c) {
+  for (auto& p : c->prof.pending) {
+    float ms = 0;
+    cudaEventSynchronize(p.b);
+    if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+      c->prof.launches[p.kind]++;
+      c->prof.ms[p.kind] += ms;
+    }
+    c->prof.pool.push_back(p.a);
+    c->prof.pool.push_back(p.b);
+  }
+  c->prof.pending.clear();
+}
+
+extern "C" {
+
+const char* vo_last_error(void) { return g_err; }
+int vo_abi_version(void) { return VO_B200_ABI_VERSION; }
+
+const char* vo_strerror(int code) {
+  switch (code) {
+    case VO_OK: return "ok";
+    case VO_ERR_INVALID_ARG: return "invalid argument";
+    case VO_ERR_NO_DEVICE: return "no CUDA device (this library has no CPU path)";
+    case VO_ERR_CUDA: return "CUDA error";
+    case VO_ERR_CAPACITY: return "capacity exceeded";
+    case VO_ERR_TOO_FEW_POINTS: return "too few points";
+    case VO_ERR_NO_MODEL: return "RANSAC found no model";
+    case VO_ERR_LOW_INLIERS: return "low inlier count after retry (reference SHUTDOWN_FLAG)";
+    case VO_ERR_NOT_IMPLEMENTED: return "not implemented";
+  }
+  return "unknown";
+}
+
+void vo_default_params(vo_params* p) {
+  memset(p, 0, sizeof(*p));
+  p->fx = 7.188560000000e+02;
+  p->fy = 7.188560000000e+02;
+  p->cx = 6.071928000000e+02;
+  p->cy = 1.852157000000e+02;
+  p->baseline = 0.54;
+  p->width = 1241;
+  p->height = 376;
+  p->channels = 1;
+  p->lk_win = 21;
+  p->lk_max_level = 3;
+  p->lk_max_iters = 30;
+  p->lk_eps = 0.01;
+  p->lk_min_eig = 1e-4;
+  p->grid_step = 30;
+  p->f_thr_stereo = 3.0;
+  p->f_thr_temporal = 1.0;
+  p->f_conf = 0.99;
+  p->f_max_iters = 1000;
+  p->pnp_iters = 100;
+  p->pnp_thr = 1.0;
+  p->pnp_conf = 0.99;
+  p->pnp_retry_iters = 100;
+  p->pnp_retry_thr = 8.0;
+  p->pnp_retry_conf = 0.98;
+  p->pnp_min_inliers = 10;
+  p->kf_min_inliers = 200;
+  p->ransac_exhaustive = 0;
+  p->max_points = 131072;
+  p->max_hypotheses = 4096;
+  p->device = 0;
+}
+
+// ------------------------------------------------------------------------------------ ctx
+int vo_create(const vo_params* p, vo_ctx** out) {
+  if (!p || !out) return VO_ERR_INVALID_ARG;
+  *out = nullptr;
+  if (p->channels != 1) {
+    set_error("channels=%d: only 1-channel images are implemented (BGR is a 'next' row, SURVEY 8f)", p->channels);
+    return VO_ERR_NOT_IMPLEMENTED;
+  }
+  if (p->lk_win != LK_WIN) {
+    set_error("lk_win=%d: the LK kernel is specialised for the reference's 21x21 window", p->lk_win);
+    return VO_ERR_NOT_IMPLEMENTED;
+  }
+  if (p->width < 64 || p->height < 64 || p->max_points < 32 || p->max_hypotheses < 1 || p->lk_max_level < 0) {
+    set_error("bad geometry/capacity");
+    return VO_ERR_INVALID_ARG;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+    set_error("no CUDA device visible; libvo_b200 has no CPU fallback");
+    return VO_ERR_NO_DEVICE;
+  }
+  if (p->device < 0 || p->device >= ndev) {
+    set_error("device %d out of range (%d devices)", p->device, ndev);
+    return VO_ERR_INVALID_ARG;
+  }
+  VO_CUDA(cudaSetDevice(p->device));
+  vo_ctx* c = new vo_ctx();
+  c->p = *p;
+  c->device = p->device;
+  cudaDeviceProp prop;
+  VO_CUDA(cudaGetDeviceProperties(&prop, p->device));
+  c->sm_count = prop.multiProcessorCount;
+  VO_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  const size_t img_bytes = (size_t)p->width * p->height;
+  for (int s = 0; s < 3; s++) {
+    VO_CUDA(cudaMalloc(&c->d_raw[s], img_bytes));
+    VO_TRY(pyr_alloc(c, c->pyr[s]));
+    VO_CUDA(cudaMallocHost(&c->h_img[s], img_bytes));
+  }
+  const int cap = p->max_points;
+  c->cap = cap;
+  VO_CUDA(cudaMalloc(&c->d_xy_in, cap * sizeof(float2)));
+  VO_CUDA(cudaMalloc(&c->d_xy_trk, cap * sizeof(float2)));
+  VO_CUDA(cudaMalloc(&c->d_status, cap));
+  VO_CUDA(cudaMalloc(&c->d_err, cap * sizeof(float)));
+  VO_CUDA(cudaMalloc(&c->d_xyz_in, cap * sizeof(float3)));
+  VO_CUDA(cudaMalloc(&c->d_c_ref, cap * sizeof(float2)));
+  VO_CUDA(cudaMalloc(&c->d_c_trk, cap * sizeof(float2)));
+  VO_CUDA(cudaMalloc(&c->d_c_xyz, cap * sizeof(float3)));
+  VO_CUDA(cudaMalloc(&c->d_f_ref, cap * sizeof(float2)));
+  VO_CUDA(cudaMalloc(&c->d_f_trk, cap * sizeof(float2)));
+  VO_CUDA(cudaMalloc(&c->d_f_xyz, cap * sizeof(float3)));
+  VO_CUDA(cudaMalloc(&c->d_xyz_tmp, cap * sizeof(float3)));
+  VO_CUDA(cudaMalloc(&c->d_mask, cap));
+  VO_CUDA(cudaMalloc(&c->d_idx, cap * sizeof(int32_t)));
+  VO_CUDA(cudaMalloc(&c->d_seq_xy, cap * sizeof(float2)));
+  VO_CUDA(cudaMalloc(&c->d_seq_xyz, cap * sizeof(float3)));
+  VO_CUDA(cudaMalloc(&c->d_count, 16 * sizeof(int)));
+  VO_CUDA(cudaMallocHost(&c->h_count, 16 * sizeof(int)));
+  VO_CUDA(cudaMallocHost(&c->h_pts, (size_t)cap * 8 * sizeof(float)));
+  const int ch = p->max_hypotheses;
+  c->cap_h = ch;
+  VO_CUDA(cudaMalloc(&c->d_samples, (size_t)ch * 7 * sizeof(int32_t)));
+  VO_CUDA(cudaMallocHost(&c->h_samples, (size_t)ch * 7 * sizeof(int32_t)));
+  VO_CUDA(cudaMalloc(&c->d_models, (size_t)ch * 27 * sizeof(double)));
+  VO_CUDA(cudaMalloc(&c->d_counts, (size_t)ch * 3 * sizeof(int32_t)));
+  VO_CUDA(cudaMalloc(&c->d_sel, 8 * sizeof(int)));
+  VO_CUDA(cudaMallocHost(&c->h_sel, 8 * sizeof(int)));
+  VO_CUDA(cudaMalloc(&c->d_pose, 16 * sizeof(double)));
+  VO_CUDA(cudaMallocHost(&c->h_pose, 16 * sizeof(double)));
+  VO_CUDA(cudaMalloc(&c->d_cam, 48 * sizeof(double)));
+  VO_CUDA(cudaMalloc(&c->d_lk_work, 2 * sizeof(unsigned long long)));
+  VO_CUDA(cudaMallocHost(&c->h_lk_work, 2 * sizeof(unsigned long long)));
+  VO_CUDA(cudaMemsetAsync(c->d_lk_work, 0, 2 * sizeof(unsigned long long), c->stream));
+  VO_CUDA(cudaStreamSynchronize(c->stream));
+  *out = c;
+  return VO_OK;
+}
+
+int vo_destroy(vo_ctx* c) {
+  if (!c) return VO_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  prof_drain(c);
+  for (auto e : c->prof.pool) cudaEventDestroy(e);
+  for (int s = 0; s < 3; s++) {
+    cudaFree(c->d_raw[s]);
+    pyr_free(c->pyr[s]);
+    cudaFreeHost(c->h_img[s]);
+  }
+  void* dev[] = {c->d_xy_in, c->d_xy_trk, c->d_status, c->d_err, c->d_xyz_in, c->d_c_ref, c->d_c_trk, c->d_c_xyz,
+                 c->d_f_ref, c->d_f_trk, c->d_f_xyz, c->d_xyz_tmp, c->d_mask, c->d_idx, c->d_seq_xy, c->d_seq_xyz,
+                 c->d_count, c->d_samples, c->d_models, c->d_counts, c->d_sel, c->d_pose, c->d_cam, c->d_lk_work};
+  for (void* p : dev) cudaFree(p);
+  void* host[] = {c->h_count, c->h_pts, c->h_samples, c->h_sel, c->h_pose, c->h_lk_work};
+  for (void* p : host) cudaFreeHost(p);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return VO_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------ helpers
+#define CHECK_CTX(c)                        \
+  if (!(c)) return VO_ERR_INVALID_ARG;      \
+  VO_CUDA(cudaSetDevice((c)->device))
+
+static int sync_stream(vo_ctx* c) {
+  VO_CUDA(cudaStreamSynchronize(c->stream));
+  return VO_OK;
+}
+
+// image -> padded level 0 of `slot` (H2D or D2D straight into place), then the pyramid
+static int load_image(vo_ctx* c, int slot, const uint8_t* img, int stride, int is_device, bool with_deriv) {
+  if (!img) return VO_ERR_INVALID_ARG;
+  if (stride < c->p.width) {
+    set_error("stride %d < width %d", stride, c->p.width);
+    return VO_ERR_INVALID_ARG;
+  }
+  PyrLevel& L0 = c->pyr[slot].lv[0];
+  VO_CUDA(cudaMemcpy2DAsync(L0.img + (size_t)PAD_Y * L0.pitch + PAD_L, L0.pitch, img, stride, L0.w, L0.h,
+                            is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+  return pyr_build(c, slot, nullptr, with_deriv);
+}
+
+static int read_counts(vo_ctx* c) {
+  VO_CUDA(cudaMemcpyAsync(c->h_count, c->d_count, 16 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  return sync_stream(c);
+}
+
+// --- OpenCV-compatible minimal-sample generation (RANSACPointSetRegistrator::getSubset) ---
+static inline void draw_indices(CvRng& rng, int count, int m, int32_t* idx) {
+  for (int i = 0; i < m; i++) {
+    int v;
+    for (;;) {
+      v = rng.uniform(0, count);
+      bool dup = false;
+      for (int k = 0; k < i; k++) dup |= (idx[k] == v);
+      if (!dup) break;
+    }
+    idx[i] = v;
+  }
+}
+
+static bool have_collinear(const float* pts /*xy interleaved, full set*/, const int32_t* idx, int count) {
+  const int i = count - 1;
+  const double xi = pts[2 * idx[i]], yi = pts[2 * idx[i] + 1];
+  for (int j = 0; j < i; j++) {
+    const double dx1 = (double)pts[2 * idx[j]] - xi, dy1 = (double)pts[2 * idx[j] + 1] - yi;
+    for (int k = 0; k < j; k++) {
+      const double dx2 = (double)pts[2 * idx[k]] - xi, dy2 = (double)pts[2 * idx[k] + 1] - yi;
+      if (fabs(dx2 * dy1 - dy2 * dx1) <= FLT_EPSILON * (fabs(dx1) + fabs(dy1) + fabs(dx2) + fabs(dy2))) return true;
+    }
+  }
+  return false;
+}
+
+// Draw accepted 7-subsets into out[k*7..]; returns how many were produced (< want only if
+// 10000 attempts failed for one sample, like OpenCV's getSubset).
+static int draw_fmat_samples(CvRng& rng, const float* m1, const float* m2, int n, int want, int32_t* out) {
+  for (int s = 0; s < want; s++) {
+    bool found = false;
+    for (int att = 0; att < 10000; att++) {
+      int32_t* idx = out + (size_t)s * 7;
+      draw_indices(rng, n, 7, idx);
+      if (!have_collinear(m1, idx, 7) && !have_collinear(m2, idx, 7)) {
+        found = true;
+        break;
+      }
+    }
+    if (!found) return s;
+  }
+  return want;
+}
+
+// ------------------------------------------------------------------------------------ F-RANSAC
+// Device inputs m1, m2 (n points).  h_m1/h_m2: host copies for the collinearity check (unused
+// with a replay list).  On return d_sel holds (best, niters, best_count, records), d_mask the
+// best model's inlier mask.
+static int run_fmat(vo_ctx* c, const float2* m1, const float2* m2, int n, double thr, double conf,
+                    const int32_t* replay, int n_replay, const float* h_m1, const float* h_m2) {
+  if (n < 15) {
+    set_error("findFundamentalMat(FM_RANSAC) with %d < 15 points switches estimator in OpenCV; not supported", n);
+    return VO_ERR_TOO_FEW_POINTS;
+  }
+  const int max_iters = std::max(c->p.f_max_iters, 1);
+  const int H = replay ? n_replay : max_iters;
+  if (H > c->cap_h) {
+    set_error("%d samples exceed max_hypotheses %d", H, c->cap_h);
+    return VO_ERR_CAPACITY;
+  }
+  const float thr2 = (float)(thr * thr);
+  CvRng rng(0xffffffffffffffffULL);
+  int done = 0;
+  int target = (c->p.ransac_exhaustive || replay) ? H : std::min(H, 48);
+  for (;;) {
+    int k = target - done;
+    if (k > 0) {
+      int32_t* hs = c->h_samples + (size_t)done * 7;
+      if (replay) {
+        memcpy(hs, replay + (size_t)done * 7, (size_t)k * 7 * sizeof(int32_t));
+        for (int i = 0; i < k * 7; i++)
+          if (hs[i] < 0 || hs[i] >= n) {
+            set_error("replay sample index out of range");
+            return VO_ERR_INVALID_ARG;
+          }
+      } else {
+        int got = draw_fmat_samples(rng, h_m1, h_m2, n, k, hs);
+        if (got < k) {  // OpenCV: getSubset failed -> the loop ends here
+          k = got;
+          target = done + k;
+        }
+      }
+      if (k > 0) {
+        VO_CUDA(cudaMemcpyAsync(c->d_samples + (size_t)done * 7, hs, (size_t)k * 7 * sizeof(int32_t),
+                                cudaMemcpyHostToDevice, c->stream));
+        VO_TRY(fmat_solve_launch(c, m1, m2, c->d_samples + (size_t)done * 7, k, c->d_models + (size_t)done * 27,
+                                 c->d_counts + (size_t)done * 3));
+        VO_TRY(fmat_score_launch(c, m1, m2, n, c->d_models + (size_t)done * 27, c->d_counts + (size_t)done * 3, k,
+                                 thr2));
+        done += k;
+      }
+    }
+    VO_TRY(select_launch(c, c->d_counts, done, 3, 7, n, conf, max_iters, c->d_sel));
+    VO_CUDA(cudaMemcpyAsync(c->h_sel, c->d_sel, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    VO_TRY(sync_stream(c));
+    const int niters = c->h_sel[1];
+    if (done >= std::min(niters, H) || k <= 0) break;
+    target = std::min(niters, H);
+  }
+  c->last_f_h = done;
+  VO_TRY(fmat_mask_launch(c, m1, m2, n, c->d_models, c->d_sel, thr2, c->d_mask));
+  return VO_OK;
+}
+
+// ------------------------------------------------------------------------------------ PnP-RANSAC
+static int run_pnp(vo_ctx* c, const float3* xyz, const float2* xy, int n, int iters, double thr, double conf,
+                   int min_solver, const int32_t* replay, int n_replay, int* n_inl_out) {
+  *n_inl_out = 0;
+  if (min_solver != VO_PNP_EPNP5) {
+    set_error("P3P minimal solver (only used by OpenCV when N == 4) is not implemented");
+    return VO_ERR_NOT_IMPLEMENTED;
+  }
+  if (n <= 5) {
+    set_error("solvePnPRansac with %d <= 5 points takes OpenCV's non-RANSAC path; not supported", n);
+    return VO_ERR_TOO_FEW_POINTS;
+  }
+  const int max_iters = std::max(iters, 1);
+  const int H = replay ? n_replay : max_iters;
+  if (H > c->cap_h) {
+    set_error("%d samples exceed max_hypotheses %d", H, c->cap_h);
+    return VO_ERR_CAPACITY;
+  }
+  const float thr2 = (float)(thr * thr);
+  CvRng rng(0xffffffffffffffffULL);
+  int done = 0;
+  int target = (c->p.ransac_exhaustive || replay) ? H : std::min(H, 32);
+  for (;;) {
+    int k = target - done;
+    if (k > 0) {
+      int32_t* hs = c->h_samples + (size_t)done * 5;
+      if (replay) {
+        memcpy(hs, replay + (size_t)done * 5, (size_t)k * 5 * sizeof(int32_t));
+        for (int i = 0; i < k * 5; i++)
+          if (hs[i] < 0 || hs[i] >= n) {
+            set_error("replay sample index out of range");
+            return VO_ERR_INVALID_ARG;
+          }
+      } else {
+        for (int s = 0; s < k; s++) draw_indices(rng, n, 5, hs + (size_t)s * 5);
+      }
+      VO_CUDA(cudaMemcpyAsync(c->d_samples + (size_t)done * 5, hs, (size_t)k * 5 * sizeof(int32_t),
+                              cudaMemcpyHostToDevice, c->stream));
+      VO_TRY(pnp_solve_launch(c, xyz, xy, c->d_samples + (size_t)done * 5, k, c->d_models + (size_t)done * 16,
+                              c->d_counts + done));
+      VO_TRY(pnp_score_launch(c, xyz, xy, n, c->d_models + (size_t)done * 16, c->d_counts + done, k, thr2));
+      done += k;
+    }
+    VO_TRY(select_launch(c, c->d_counts, done, 1, 5, n, conf, max_iters, c->d_sel));
+    VO_CUDA(cudaMemcpyAsync(c->h_sel, c->d_sel, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    VO_TRY(sync_stream(c));
+    const int niters = c->h_sel[1];
+    if (done >= std::min(niters, H) || k <= 0) break;
+    target = std::min(niters, H);
+  }
+  c->last_pnp_h = done;
+  if (c->h_sel[0] < 0) {
+    set_error("solvePnPRansac: no hypothesis reached 5 inliers");
+    return VO_ERR_NO_MODEL;
+  }
+  VO_TRY(pnp_mask_launch(c, xyz, xy, n, c->d_models, c->d_sel, thr2, c->d_mask));
+  VO_TRY(compact_launch(c, c->d_mask, n, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, c->d_idx, 4));
+  VO_TRY(pnp_refine_launch(c, xyz, xy, c->d_idx, c->d_count + 4, c->d_models, c->d_sel, c->d_pose));
+  VO_CUDA(cudaMemcpyAsync(c->h_pose, c->d_pose, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  VO_TRY(read_counts(c));
+  *n_inl_out = c->h_count[4];
+  return VO_OK;
+}
+
+// ------------------------------------------------------------------------------------ stage pipelines (device)
+// LK slot_a -> slot_b of d_in (n points) + status compaction.  Optional xyz carried along.
+// Leaves survivors in d_c_ref / d_c_trk / d_c_xyz; *m = count (host, synchronised).
+static int lk_and_compact(vo_ctx* c, int slot_a, int slot_b, const float2* d_in, const float3* d_in_xyz, int n, int* m) {
+  *m = 0;
+  if (n <= 0) return VO_OK;
+  VO_TRY(lk_launch(c, slot_a, slot_b, d_in, n, c->d_xy_trk, c->d_status, c->d_err));
+  VO_TRY(compact_launch(c, c->d_status, n, d_in, c->d_c_ref, c->d_xy_trk, c->d_c_trk, d_in_xyz, c->d_c_xyz, nullptr, 0));
+  VO_TRY(read_counts(c));
+  *m = c->h_count[0];
+  return VO_OK;
+}
+
+// F-RANSAC on d_c_* (m points) + mask compaction into d_f_*; *k = survivors.
+static int fmat_and_compact(vo_ctx* c, int m, double thr, bool with_xyz, int* k) {
+  *k = 0;
+  if (m <= 0) return VO_OK;
+  // host copies of the correspondences for the subset (collinearity) check
+  float* h1 = c->h_pts;
+  float* h2 = c->h_pts + (size_t)2 * c->cap;
+  VO_CUDA(cudaMemcpyAsync(h1, c->d_c_ref, (size_t)m * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
+  VO_CUDA(cudaMemcpyAsync(h2, c->d_c_trk, (size_t)m * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
+  VO_TRY(sync_stream(c));
+  int r = run_fmat(c, c->d_c_ref, c->d_c_trk, m, thr, c->p.f_conf, nullptr, 0, h1, h2);
+  if (r == VO_ERR_TOO_FEW_POINTS) return r;
+  VO_TRY(r);
+  VO_TRY(compact_launch(c, c->d_mask, m, c->d_c_ref, c->d_f_ref, c->d_c_trk, c->d_f_trk, with_xyz ? c->d_c_xyz : nullptr,
+                        c->d_f_xyz, nullptr, 1));
+  VO_TRY(read_counts(c));
+  *k = c->h_count[1];
+  return VO_OK;
+}
+
+static void make_projections(const vo_params& p, double* P /*24*/) {
+  // P1 = K [I|0], P2 = K [I | (-b,0,0)^T]   (reference src/triangulation.cpp:142-149)
+  const double K[9] = {p.fx, 0, p.cx, 0, p.fy, p.cy, 0, 0, 1};
+  double E1[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+  double E2[12] = {1, 0, 0, -p.baseline, 0, 1, 0, 0, 0, 0, 1, 0};
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 4; j++) {
+      double s1 = 0, s2 = 0;
+      for (int k = 0; k < 3; k++) {
+        s1 += K[i * 3 + k] * E1[k * 4 + j];
+        s2 += K[i * 3 + k] * E2[k * 4 + j];
+      }
+      P[i * 4 + j] = s1;
+      P[12 + i * 4 + j] = s2;
+    }
+}
+
+// stereoTriangulate on pyramids slot_l / slot_r (already built).  Result: d_f_ref (2-D left),
+// d_xyz_tmp (camera frame) and, when pose != NULL, d_f_xyz <- pose * xyz (world frame).
+static int stereo_pipeline(vo_ctx* c, int slot_l, int slot_r, const double* pose3x4, int* n_out, int* n_grid_out) {
+  int ng = 0;
+  VO_TRY(grid_launch(c, c->p.height, c->p.width, c->p.grid_step, c->d_xy_in, &ng));
+  if (n_grid_out) *n_grid_out = ng;
+  int m = 0, k = 0;
+  VO_TRY(lk_and_compact(c, slot_l, slot_r, c->d_xy_in, nullptr, ng, &m));
+  VO_TRY(fmat_and_compact(c, m, c->p.f_thr_stereo, false, &k));
+  double P[36];
+  make_projections(c->p, P);
+  if (pose3x4) memcpy(P + 24, pose3x4, 12 * sizeof(double));
+  VO_CUDA(cudaMemcpyAsync(c->d_cam, P, (pose3x4 ? 36 : 24) * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  VO_TRY(triangulate_launch(c, c->d_cam, c->d_f_ref, c->d_f_trk, k, c->d_xyz_tmp, pose3x4 ? c->d_cam + 24 : nullptr,
+                            c->d_f_xyz));
+  *n_out = k;
+  return VO_OK;
+}
+
+// PyrLKtrackFrame2Frame on device data: d_ref_xy/d_ref_xyz (n) -> d_f_trk, d_f_xyz, d_f_ref (k)
+static int track_pipeline(vo_ctx* c, int slot_ref, int slot_cur, const float2* d_ref_xy, const float3* d_ref_xyz, int n,
+                          int* k) {
+  int m = 0;
+  VO_TRY(lk_and_compact(c, slot_ref, slot_cur, d_ref_xy, d_ref_xyz, n, &m));
+  return fmat_and_compact(c, m, c->p.f_thr_temporal, true, k);
+}
+
+// two-attempt PnP on d_f_xyz / d_f_trk (k points); pose in h_pose, inliers in d_idx
+static int pnp_two_attempts(vo_ctx* c, int k, int* n_inl, int* attempt) {
+  *attempt = 1;
+  int r = run_pnp(c, c->d_f_xyz, c->d_f_trk, k, c->p.pnp_iters, c->p.pnp_thr, c->p.pnp_conf, VO_PNP_EPNP5, nullptr, 0,
+                  n_inl);
+  if (r != VO_OK && r != VO_ERR_NO_MODEL && r != VO_ERR_TOO_FEW_POINTS) return r;
+  if (*n_inl < c->p.pnp_min_inliers) {
+    *attempt = 2;
+    double keep[6];
+    const bool had = (r == VO_OK);
+    if (had) memcpy(keep, c->h_pose, sizeof(keep));
+    r = run_pnp(c, c->d_f_xyz, c->d_f_trk, k, c->p.pnp_retry_iters, c->p.pnp_retry_thr, c->p.pnp_retry_conf,
+                VO_PNP_EPNP5, nullptr, 0, n_inl);
+    if (r != VO_OK && r != VO_ERR_NO_MODEL && r != VO_ERR_TOO_FEW_POINTS) return r;
+    if (r != VO_OK && had) memcpy(c->h_pose, keep, sizeof(keep));
+    if (*n_inl < c->p.pnp_min_inliers) return VO_ERR_LOW_INLIERS;
+  }
+  return VO_OK;
+}
+
+static void pose_from_pnp(const double rvec[3], const double tvec[3], double pose[12]) {
+  double R[9];
+  rodrigues_vec2mat(rvec, R);
+  // R <- R^T ; t <- -R^T tvec   (reference src/VisualSLAM.cpp:70-74), pose = [R|t] (:93-97)
+  for (int i = 0; i < 3; i++) {
+    for (int j = 0; j < 3; j++) pose[i * 4 + j] = R[j * 3 + i];
+    double s = 0;
+    for (int k = 0; k < 3; k++) s += (-R[k * 3 + i]) * tvec[k];
+    pose[i * 4 + 3] = s;
+  }
+}
+
+extern "C" {
+
+// ------------------------------------------------------------------------------------ stage API
+int vo_grid_keypoints(vo_ctx* c, int rows, int cols, int step, float* xy, int cap, int* n) {
+  CHECK_CTX(c);
+  if (!n || step <= 0) return VO_ERR_INVALID_ARG;
+  int ng = 0;
+  VO_TRY(grid_launch(c, rows, cols, step, c->d_xy_in, &ng));
+  *n = ng;
+  if (ng > cap) return VO_ERR_CAPACITY;
+  if (ng && xy) VO_CUDA(cudaMemcpyAsync(xy, c->d_xy_in, (size_t)ng * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
+  return sync_stream(c);
+}
+
+int vo_anms(vo_ctx* c, const float* xy, const float* response, int n, int num_keep, int32_t* keep_idx, int cap,
+            int* n_keep) {
+  CHECK_CTX(c);
+  if (!xy || !response || !keep_idx || !n_keep || n < 0) return VO_ERR_INVALID_ARG;
+  return anms_launch(c, xy, response, n, num_keep, keep_idx, cap, n_keep);
+}
+
+int vo_lk_track(vo_ctx* c, const uint8_t* prev, const uint8_t* next, int stride, const float* prev_xy, int n,
+                float* next_xy, uint8_t* status, float* err) {
+  CHECK_CTX(c);
+  if (!prev || !next || !prev_xy || !next_xy || !status || n < 0) return VO_ERR_INVALID_ARG;
+  if (n > c->cap) return VO_ERR_CAPACITY;
+  if (n == 0) return VO_OK;
+  VO_TRY(load_image(c, 0, prev, stride, 0, true));
+  VO_TRY(load_image(c, 1, next, stride, 0, false));
+  VO_CUDA(cudaMemcpyAsync(c->d_xy_in, prev_xy, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+  VO_TRY(lk_launch(c, 0, 1, c->d_xy_in, n, c->d_xy_trk, c->d_status, c->d_err));
+  VO_CUDA(cudaMemcpyAsync(next_xy, c->d_xy_trk, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
+  VO_CUDA(cudaMemcpyAsync(status, c->d_status, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  if (err) VO_CUDA(cudaMemcpyAsync(err, c->d_err, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  return sync_stream(c);
+}
+
+int vo_debug_pyramid_level(vo_ctx* c, const uint8_t* img, int stride, int level, uint8_t* out_level, int16_t* out_deriv,
+                           int* w, int* h) {
+  CHECK_CTX(c);
+  if (!img) return VO_ERR_INVALID_ARG;
+  VO_TRY(load_image(c, 0, img, stride, 0, true));
+  Pyramid& p = c->pyr[0];
+  if (level < 0 || level >= p.nlevels) return VO_ERR_INVALID_ARG;
+  PyrLevel& L = p.lv[level];
+  if (w) *w = L.w;
+  if (h) *h = L.h;
+  if (out_level)
+    VO_CUDA(cudaMemcpy2DAsync(out_level, L.w, L.img + (size_t)PAD_Y * L.pitch + PAD_L, L.pitch, L.w, L.h,
+                              cudaMemcpyDeviceToHost, c->stream));
+  if (out_deriv)
+    VO_CUDA(cudaMemcpy2DAsync(out_deriv, (size_t)L.w * 4, L.deriv + (size_t)PAD_Y * L.pitch + PAD_L,
+                              (size_t)L.pitch * 4, (size_t)L.w * 4, L.h, cudaMemcpyDeviceToHost, c->stream));
+  return sync_stream(c);
+}
+
+int vo_fmat_ransac(vo_ctx* c, const float* xy1, const float* xy2, int n, double thr, double conf,
+                   const int32_t* samples7, int n_samples, uint8_t* mask, double F[9], int* n_inliers) {
+  CHECK_CTX(c);
+  if (!xy1 || !xy2 || !mask || n < 0) return VO_ERR_INVALID_ARG;
+  if (n > c->cap) return VO_ERR_CAPACITY;
+  VO_CUDA(cudaMemcpyAsync(c->d_c_ref, xy1, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+  VO_CUDA(cudaMemcpyAsync(c->d_c_trk, xy2, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+  VO_TRY(run_fmat(c, c->d_c_ref, c->d_c_trk, n, thr, conf, samples7, samples7 ? n_samples : 0, xy1, xy2));
+  VO_CUDA(cudaMemcpyAsync(mask, c->d_mask, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  VO_TRY(sync_stream(c));
+  const int best = c->h_sel[0];
+  if (n_inliers) *n_inliers = best >= 0 ? c->h_sel[2] : 0;
+  if (best < 0) {
+    set_error("findFundamentalMat: no model with more than 6 inliers");
+    return VO_ERR_NO_MODEL;
+  }
+  if (F) {
+    VO_CUDA(cudaMemcpyAsync(F, c->d_models + (size_t)best * 9, 9 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    VO_TRY(sync_stream(c));
+  }
+  return VO_OK;
+}
+
+int vo_triangulate(vo_ctx* c, const double P1[12], const double P2[12], const float* xy1, const float* xy2, int n,
+                   float* xyz) {
+  CHECK_CTX(c);
+  if (!P1 || !P2 || !xy1 || !xy2 || !xyz || n < 0) return VO_ERR_INVALID_ARG;
+  if (n > c->cap) return VO_ERR_CAPACITY;
+  if (n == 0) return VO_OK;
+  double P[24];
+  memcpy(P, P1, 96);
+  memcpy(P + 12, P2, 96);
+  VO_CUDA(cudaMemcpyAsync(c->d_cam, P, sizeof(P), cudaMemcpyHostToDevice, c->stream));
+  VO_CUDA(cudaMemcpyAsync(c->d_f_ref, xy1, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+  VO_CUDA(cudaMemcpyAsync(c->d_f_trk, xy2, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+  VO_TRY(triangulate_launch(c, c->d_cam, c->d_f_ref, c->d_f_trk, n, c->d_xyz_tmp, nullptr, nullptr));
+  VO_CUDA(cudaMemcpyAsync(xyz, c->d_xyz_tmp, (size_t)n * sizeof(float3), cudaMemcpyDeviceToHost, c->stream));
+  return sync_stream(c);
+}
+
+int vo_pnp_ransac(vo_ctx* c, const float* xyz, const float* xy, int n, int iters, double thr, double conf,
+                  int min_solver, const int32_t* samples, int n_samples, double rvec[3], double tvec[3],
+                  int32_t* inliers, int cap, int* n_inl) {
+  CHECK_CTX(c);
+  if (!xyz || !xy || !rvec || !tvec || n < 0) return VO_ERR_INVALID_ARG;
+  if (n > c->cap) return VO_ERR_CAPACITY;
+  VO_CUDA(cudaMemcpyAsync(c->d_f_xyz, xyz, (size_t)n * sizeof(float3), cudaMemcpyHostToDevice, c->stream));
+  VO_CUDA(cudaMemcpyAsync(c->d_f_trk, xy, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+  int ni = 0;
+  int r = run_pnp(c, c->d_f_xyz, c->d_f_trk, n, iters, thr, conf, min_solver, samples, samples ? n_samples : 0, &ni);
+  if (n_inl) *n_inl = ni;
+  VO_TRY(r);
+  for (int i = 0; i < 3; i++) {
+    rvec[i] = c->h_pose[i];
+    tvec[i] = c->h_pose[3 + i];
+  }
+  if (inliers) {
+    if (ni > cap) return VO_ERR_CAPACITY;
+    VO_CUDA(cudaMemcpyAsync(inliers, c->d_idx, (size_t)ni * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    VO_TRY(sync_stream(c));
+  }
+  return VO_OK;
+}
+
+int vo_debug_last_pnp(vo_ctx* c, double* models, int32_t* counts, int cap_h, int* n_h, int* best, int* n_iters) {
+  CHECK_CTX(c);
+  const int h = c->last_pnp_h;
+  if (n_h) *n_h = h;
+  if (best) *best = c->h_sel[0];
+  if (n_iters) *n_iters = c->h_sel[1];
+  if (h > cap_h && (models || counts)) return VO_ERR_CAPACITY;
+  std::vector<double> tmp((size_t)h * 16);
+  if (models && h) {
+    VO_CUDA(cudaMemcpyAsync(tmp.data(), c->d_models, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    VO_TRY(sync_stream(c));
+    for (int i = 0; i < h; i++)
+      for (int k = 0; k < 6; k++) models[i * 6 + k] = tmp[(size_t)i * 16 + k];
+  }
+  if (counts && h) {
+    VO_CUDA(cudaMemcpyAsync(counts, c->d_counts, (size_t)h * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    VO_TRY(sync_stream(c));
+  }
+  return VO_OK;
+}
+
+int vo_debug_last_fmat(vo_ctx* c, double* models, int32_t* counts, int cap_h, int* n_h, int* best_sample,
+                       int* best_model, int* n_iters) {
+  CHECK_CTX(c);
+  const int h = c->last_f_h;
+  if (n_h) *n_h = h;
+  if (best_sample) *best_sample = c->h_sel[0] >= 0 ? c->h_sel[0] / 3 : -1;
+  if (best_model) *best_model = c->h_sel[0] >= 0 ? c->h_sel[0] % 3 : -1;
+  if (n_iters) *n_iters = c->h_sel[1];
+  if (h > cap_h && (models || counts)) return VO_ERR_CAPACITY;
+  if (models && h)
+    VO_CUDA(cudaMemcpyAsync(models, c->d_models, (size_t)h * 27 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (counts && h)
+    VO_CUDA(cudaMemcpyAsync(counts, c->d_counts, (size_t)h * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  return sync_stream(c);
+}
+
+int vo_transform_points(vo_ctx* c, const double M[12], const float* xyz_in, int n, float* xyz_out) {
+  CHECK_CTX(c);
+  if (!M || !xyz_in || !xyz_out || n < 0) return VO_ERR_INVALID_ARG;
+  if (n > c->cap) return VO_ERR_CAPACITY;
+  if (n == 0) return VO_OK;
+  VO_CUDA(cudaMemcpyAsync(c->d_cam + 24, M, 96, cudaMemcpyHostToDevice, c->stream));
+  VO_CUDA(cudaMemcpyAsync(c->d_xyz_in, xyz_in, (size_t)n * sizeof(float3), cudaMemcpyHostToDevice, c->stream));
+  VO_TRY(transform_launch(c, c->d_cam + 24, c->d_xyz_in, n, c->d_xyz_tmp));
+  VO_CUDA(cudaMemcpyAsync(xyz_out, c->d_xyz_tmp, (size_t)n * sizeof(float3), cudaMemcpyDeviceToHost, c->stream));
+  return sync_stream(c);
+}
+
+int vo_pose_from_pnp(const double rvec[3], const double tvec[3], double pose3x4[12]) {
+  if (!rvec || !tvec || !pose3x4) return VO_ERR_INVALID_ARG;
+  pose_from_pnp(rvec, tvec, pose3x4);
+  return VO_OK;
+}
+
+// ------------------------------------------------------------------------------------ fused stage entry points
+int vo_dense_lk_tracking(vo_ctx* c, const uint8_t* ref_img, const uint8_t* cur_img, int stride, const float* ref_xy,
+                         int n, float* ref_out, float* trk_out, int* m) {
+  CHECK_CTX(c);
+  if (!ref_img || !cur_img || !ref_xy || !ref_out || !trk_out || !m || n < 0) return VO_ERR_INVALID_ARG;
+  if (n > c->cap) return VO_ERR_CAPACITY;
+  *m = 0;
+  if (n == 0) return VO_OK;
+  VO_TRY(load_image(c, 0, ref_img, stride, 0, true));
+  VO_TRY(load_image(c, 1, cur_img, stride, 0, false));
+  VO_CUDA(cudaMemcpyAsync(c->d_xy_in, ref_xy, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+  int k = 0;
+  VO_TRY(lk_and_compact(c, 0, 1, c->d_xy_in, nullptr, n, &k));
+  *m = k;
+  if (k) {
+    VO_CUDA(cudaMemcpyAsync(ref_out, c->d_c_ref, (size_t)k * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
+    VO_CUDA(cudaMemcpyAsync(trk_out, c->d_c_trk, (size_t)k * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
+  }
+  return sync_stream(c);
+}
+
+int vo_fmat_thresholding(vo_ctx* c, const float* ref_xy, const float* trk_xy, int n, float* ref_out, float* trk_out,
+                         int* m) {
+  CHECK_CTX(c);
+  if (!ref_xy || !trk_xy || !ref_out || !trk_out || !m || n < 0) return VO_ERR_INVALID_ARG;
+  if (n > c->cap) return VO_ERR_CAPACITY;
+  *m = 0;
+  VO_CUDA(cudaMemcpyAsync(c->d_c_ref, ref_xy, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+  VO_CUDA(cudaMemcpyAsync(c->d_c_trk, trk_xy, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+  int k = 0;
+  VO_TRY(fmat_and_compact(c, n, c->p.f_thr_stereo, false, &k));
+  *m = k;
+  if (k) {
+    VO_CUDA(cudaMemcpyAsync(ref_out, c->d_f_ref, (size_t)k * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
+    VO_CUDA(cudaMemcpyAsync(trk_out, c->d_f_trk, (size_t)k * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
+  }
+  return sync_stream(c);
+}
+
+static int stereo_host(vo_ctx* c, const uint8_t* left, const uint8_t* right, int stride, const double* pose,
+                       float* xyz_a, float* xy_left, float* xyz_b, int cap, int* n) {
+  if (!left || !right || !n) {
+    set_error("NULL IMG");  // the reference prints this and returns (src/triangulation.cpp:81-84)
+    return VO_ERR_INVALID_ARG;
+  }
+  *n = 0;
+  VO_TRY(load_image(c, 0, left, stride, 0, true));
+  VO_TRY(load_image(c, 2, right, stride, 0, false));
+  int k = 0;
+  VO_TRY(stereo_pipeline(c, 0, 2, pose, &k, nullptr));
+  *n = k;
+  if (k > cap) return VO_ERR_CAPACITY;
+  if (k) {
+    // xyz_a: primary 3-D output (world if pose given, else camera); xyz_b: camera-frame copy
+    if (xyz_a)
+      VO_CUDA(cudaMemcpyAsync(xyz_a, pose ? c->d_f_xyz : c->d_xyz_tmp, (size_t)k * sizeof(float3), cudaMemcpyDeviceToHost,
+                              c->stream));
+    if (xyz_b) VO_CUDA(cudaMemcpyAsync(xyz_b, c->d_xyz_tmp, (size_t)k * sizeof(float3), cudaMemcpyDeviceToHost, c->stream));
+    if (xy_left) VO_CUDA(cudaMemcpyAsync(xy_left, c->d_f_ref, (size_t)k * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
+  }
+  return sync_stream(c);
+}
+
+int vo_stereo_triangulate(vo_ctx* c, const uint8_t* left, const uint8_t* right, int stride, float* xyz, float* xy_left,
+                          int cap, int* n) {
+  CHECK_CTX(c);
+  return stereo_host(c, left, right, stride, nullptr, xyz, xy_left, nullptr, cap, n);
+}
+
+int vo_insert_keyframe(vo_ctx* c, const uint8_t* left, const uint8_t* right, int stride, const double pose3x4[12],
+                       float* xyz_world, float* xy_left, float* xyz_cam, int cap, int* n) {
+  CHECK_CTX(c);
+  if (!pose3x4) return VO_ERR_INVALID_ARG;
+  return stereo_host(c, left, right, stride, pose3x4, xyz_world, xy_left, xyz_cam, cap, n);
+}
+
+static int track_host(vo_ctx* c, const uint8_t* ref_img, const uint8_t* cur_img, int stride, const float* ref_xy,
+                      const float* ref_xyz, int n, int* k) {
+  if (!ref_img || !cur_img || !ref_xy || !ref_xyz || n < 0) return VO_ERR_INVALID_ARG;
+  if (n > c->cap) return VO_ERR_CAPACITY;
+  *k = 0;
+  if (n == 0) return VO_OK;
+  VO_TRY(load_image(c, 0, ref_img, stride, 0, true));
+  VO_TRY(load_image(c, 1, cur_img, stride, 0, false));
+  VO_CUDA(cudaMemcpyAsync(c->d_xy_in, ref_xy, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+  VO_CUDA(cudaMemcpyAsync(c->d_xyz_in, ref_xyz, (size_t)n * sizeof(float3), cudaMemcpyHostToDevice, c->stream));
+  return track_pipeline(c, 0, 1, c->d_xy_in, c->d_xyz_in, n, k);
+}
+
+static int copy_track_outputs(vo_ctx* c, int k, float* trk_xy, float* trk_xyz, float* ref_xy_inl) {
+  if (k) {
+    if (trk_xy) VO_CUDA(cudaMemcpyAsync(trk_xy, c->d_f_trk, (size_t)k * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
+    if (trk_xyz) VO_CUDA(cudaMemcpyAsync(trk_xyz, c->d_f_xyz, (size_t)k * sizeof(float3), cudaMemcpyDeviceToHost, c->stream));
+    if (ref_xy_inl)
+      VO_CUDA(cudaMemcpyAsync(ref_xy_inl, c->d_f_ref, (size_t)k * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
+  }
+  return sync_stream(c);
+}
+
+int vo_track_frame(vo_ctx* c, const uint8_t* ref_img, const uint8_t* cur_img, int stride, const float* ref_xy,
+                   const float* ref_xyz, int n, float* trk_xy, float* trk_xyz, float* ref_xy_inl, int* n_out) {
+  CHECK_CTX(c);
+  if (!n_out) return VO_ERR_INVALID_ARG;
+  int k = 0;
+  VO_TRY(track_host(c, ref_img, cur_img, stride, ref_xy, ref_xyz, n, &k));
+  *n_out = k;
+  return copy_track_outputs(c, k, trk_xy, trk_xyz, ref_xy_inl);
+}
+
+int vo_pnp_frame(vo_ctx* c, const uint8_t* ref_img, const uint8_t* cur_img, int stride, const float* ref_xy,
+                 const float* ref_xyz, int n, float* trk_xy, float* trk_xyz, float* ref_xy_inl, int* n_trk,
+                 double rvec[3], double tvec[3], int32_t* inliers, int cap_inl, int* n_inl, int* attempt_used) {
+  CHECK_CTX(c);
+  if (!n_trk || !rvec || !tvec || !n_inl) return VO_ERR_INVALID_ARG;
+  int k = 0;
+  *n_inl = 0;
+  VO_TRY(track_host(c, ref_img, cur_img, stride, ref_xy, ref_xyz, n, &k));
+  *n_trk = k;
+  VO_TRY(copy_track_outputs(c, k, trk_xy, trk_xyz, ref_xy_inl));
+  int ni = 0, att = 1;
+  int r = pnp_two_attempts(c, k, &ni, &att);
+  if (attempt_used) *attempt_used = att;
+  *n_inl = ni;
+  if (r != VO_OK && r != VO_ERR_LOW_INLIERS) return r;
+  for (int i = 0; i < 3; i++) {
+    rvec[i] = c->h_pose[i];
+    tvec[i] = c->h_pose[3 + i];
+  }
+  if (inliers && ni) {
+    if (ni > cap_inl) return VO_ERR_CAPACITY;
+    VO_CUDA(cudaMemcpyAsync(inliers, c->d_idx, (size_t)ni * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    VO_TRY(sync_stream(c));
+  }
+  return r;
+}
+
+// ------------------------------------------------------------------------------------ sequence driver
+int vo_seq_init(vo_ctx* c, const uint8_t* left, const uint8_t* right, int stride, int is_device, int* n_points) {
+  CHECK_CTX(c);
+  if (!left || !right) return VO_ERR_INVALID_ARG;
+  VO_TRY(load_image(c, 0, left, stride, is_device, true));
+  VO_TRY(load_image(c, 2, right, stride, is_device, false));
+  int k = 0;
+  VO_TRY(stereo_pipeline(c, 0, 2, nullptr, &k, nullptr));
+  if (k) {
+    VO_CUDA(cudaMemcpyAsync(c->d_seq_xy, c->d_f_ref, (size_t)k * sizeof(float2), cudaMemcpyDeviceToDevice, c->stream));
+    VO_CUDA(cudaMemcpyAsync(c->d_seq_xyz, c->d_xyz_tmp, (size_t)k * sizeof(float3), cudaMemcpyDeviceToDevice, c->stream));
+  }
+  c->seq_n = k;
+  c->seq_ref_slot = 0;
+  if (n_points) *n_points = k;
+  return sync_stream(c);
+}
+
+int vo_seq_track(vo_ctx* c, const uint8_t* left, const uint8_t* right, int stride, int is_device, int force_keyframe,
+                 vo_frame_result* out) {
+  CHECK_CTX(c);
+  if (!left || !out || c->seq_ref_slot < 0) return VO_ERR_INVALID_ARG;
+  memset(out, 0, sizeof(*out));
+  const int ref = c->seq_ref_slot, cur = 1 - ref;
+  VO_TRY(load_image(c, cur, left, stride, is_device, false));
+  out->n_lk_in = c->seq_n;
+  int k = 0;
+  VO_TRY(track_pipeline(c, ref, cur, c->d_seq_xy, c->d_seq_xyz, c->seq_n, &k));
+  out->n_tracked = k;
+  int ni = 0, att = 1;
+  int r = pnp_two_attempts(c, k, &ni, &att);
+  out->n_inliers = ni;
+  out->attempt_used = att;
+  if (r != VO_OK) return r;  // incl. VO_ERR_LOW_INLIERS: the reference breaks out of its loop here
+  for (int i = 0; i < 3; i++) {
+    out->rvec[i] = c->h_pose[i];
+    out->tvec[i] = c->h_pose[3 + i];
+  }
+  pose_from_pnp(out->rvec, out->tvec, out->pose3x4);
+  if (ni < c->p.kf_min_inliers || force_keyframe) {
+    // keyframe: src/VisualSLAM.cpp:120-137 -> insertKeyFrames (src/keyFrameManagement.cpp:9-31)
+    if (!right) {
+      set_error("keyframe required (inliers %d < %d) but no right image was supplied", ni, c->p.kf_min_inliers);
+      return VO_ERR_INVALID_ARG;
+    }
+    VO_TRY(load_image(c, 2, right, stride, is_device, false));
+    int kk = 0, ng = 0;
+    VO_TRY(stereo_pipeline(c, cur, 2, out->pose3x4, &kk, &ng));
+    if (kk) {
+      VO_CUDA(cudaMemcpyAsync(c->d_seq_xy, c->d_f_ref, (size_t)kk * sizeof(float2), cudaMemcpyDeviceToDevice, c->stream));
+      VO_CUDA(cudaMemcpyAsync(c->d_seq_xyz, c->d_f_xyz, (size_t)kk * sizeof(float3), cudaMemcpyDeviceToDevice, c->stream));
+    }
+    c->seq_n = kk;
+    out->keyframe = 1;
+    out->n_kf_points = kk;
+    out->n_lk_in_stereo = ng;
+  } else {
+    // ref3dCoords = trked3dCoords; ref2dFeatures = trked2dPts   (src/VisualSLAM.cpp:143-146)
+    if (k) {
+      VO_CUDA(cudaMemcpyAsync(c->d_seq_xy, c->d_f_trk, (size_t)k * sizeof(float2), cudaMemcpyDeviceToDevice, c->stream));
+      VO_CUDA(cudaMemcpyAsync(c->d_seq_xyz, c->d_f_xyz, (size_t)k * sizeof(float3), cudaMemcpyDeviceToDevice, c->stream));
+    }
+    c->seq_n = k;
+  }
+  c->seq_ref_slot = cur;  // referenceImg = currentImage (src/VisualSLAM.cpp:151)
+  return sync_stream(c);
+}
+
+int vo_seq_get_reference(vo_ctx* c, float* xy, float* xyz, int cap, int* n) {
+  CHECK_CTX(c);
+  if (n) *n = c->seq_n;
+  if (c->seq_n > cap && (xy || xyz)) return VO_ERR_CAPACITY;
+  if (c->seq_n) {
+    if (xy) VO_CUDA(cudaMemcpyAsync(xy, c->d_seq_xy, (size_t)c->seq_n * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
+    if (xyz) VO_CUDA(cudaMemcpyAsync(xyz, c->d_seq_xyz, (size_t)c->seq_n * sizeof(float3), cudaMemcpyDeviceToHost, c->stream));
+  }
+  return sync_stream(c);
+}
+
+// ------------------------------------------------------------------------------------ harness helpers
+void* vo_cuda_stream(vo_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int vo_sync(vo_ctx* c) {
+  CHECK_CTX(c);
+  return sync_stream(c);
+}
+
+int vo_profile_enable(vo_ctx* c, int on) {
+  CHECK_CTX(c);
+  VO_TRY(sync_stream(c));
+  prof_drain(c);
+  c->prof.on = on != 0;
+  return VO_OK;
+}
+
+int vo_profile_read(vo_ctx* c, int kernel, int64_t* launches, double* ms, int reset) {
+  CHECK_CTX(c);
+  if (kernel < 0 || kernel >= VO_K_COUNT) return VO_ERR_INVALID_ARG;
+  VO_TRY(sync_stream(c));
+  prof_drain(c);
+  if (launches) *launches = c->prof.launches[kernel];
+  if (ms) *ms = c->prof.ms[kernel];
+  if (reset) {
+    c->prof.launches[kernel] = 0;
+    c->prof.ms[kernel] = 0;
+  }
+  return VO_OK;
+}
+
+int64_t vo_launch_count(vo_ctx* c) { return c ? c->launch_count : 0; }
+
+int vo_lk_work(vo_ctx* c, int64_t* point_levels, int64_t* iterations) {
+  CHECK_CTX(c);
+  VO_CUDA(cudaMemcpyAsync(c->h_lk_work, c->d_lk_work, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  VO_TRY(sync_stream(c));
+  if (point_levels) *point_levels = (int64_t)c->h_lk_work[0];
+  if (iterations) *iterations = (int64_t)c->h_lk_work[1];
+  return VO_OK;
+}
+
+int vo_measure_fp32_peak(vo_ctx* c, double* tflops) {
+  CHECK_CTX(c);
+  if (!tflops) return VO_ERR_INVALID_ARG;
+  return fp32_peak_launch(c, tflops);
+}
+
+int vo_synth_render_dev(vo_ctx* c, int seed, int frame, int eye, uint8_t* out_dev) {
+  CHECK_CTX(c);
+  if (!out_dev) return VO_ERR_INVALID_ARG;
+  return synth_launch(c, seed, frame, eye, out_dev);
+}
+
+int vo_alloc_host(void** p, uint64_t bytes) {
+  if (!p) return VO_ERR_INVALID_ARG;
+  VO_CUDA(cudaMallocHost(p, bytes));
+  return VO_OK;
+}
+int vo_free_host(void* p) {
+  VO_CUDA(cudaFreeHost(p));
+  return VO_OK;
+}
+int vo_alloc_dev(vo_ctx* c, void** p, uint64_t bytes) {
+  CHECK_CTX(c);
+  if (!p) return VO_ERR_INVALID_ARG;
+  VO_CUDA(cudaMalloc(p, bytes));
+  return VO_OK;
+}
+int vo_free_dev(vo_ctx* c, void* p) {
+  CHECK_CTX(c);
+  VO_CUDA(cudaFree(p));
+  return VO_OK;
+}
+int vo_memcpy_d2h(vo_ctx* c, void* dst, const void* src, uint64_t bytes) {
+  CHECK_CTX(c);
+  VO_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+  return sync_stream(c);
+}
+int vo_memcpy_h2d(vo_ctx* c, void* dst, const void* src, uint64_t bytes) {
+  CHECK_CTX(c);
+  VO_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  return sync_stream(c);
+}
+
+}  // extern "C"

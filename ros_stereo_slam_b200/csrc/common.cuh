@@ -1,0 +1,192 @@
+// common.cuh -- context, device buffers and launch helpers shared by the kernels of
+// libvo_b200.so.  Host side of the drop-in boundary declared in include/vo_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/vo_b200.h"
+
+namespace vo {
+
+// ------------------------------------------------------------------------------------
+// HBM layout of one pyramid level.  Images are stored PADDED so that the LK window and
+// the pyrDown taps never need bounds logic: border PAD_Y rows above/below and PAD_L /
+// >= PAD_R columns left/right, filled with BORDER_REFLECT_101 (image) or zeros
+// (derivative), exactly the borders cv::buildOpticalFlowPyramid creates with
+// winSize = 21.  PAD_L = 32 keeps interior rows 32-byte aligned (pitch % 128 == 0).
+constexpr int LK_WIN = 21;
+constexpr int PAD_Y = 21;
+constexpr int PAD_L = 32;
+constexpr int PAD_R = 32;
+constexpr int MAX_LEVELS = 4;
+
+struct PyrLevel {
+  int w, h;          // interior size
+  int pitch;         // bytes per padded image row (multiple of 128)
+  uint8_t* img;      // padded buffer base; pixel (x,y) at img[(y+PAD_Y)*pitch + x + PAD_L]
+  short2* deriv;     // padded (dx,dy) buffer, same geometry, element pitch = pitch
+};
+
+struct Pyramid {
+  PyrLevel lv[MAX_LEVELS];
+  int nlevels = 0;
+  bool has_deriv = false;
+  uint64_t stamp = 0;  // content tag (0 = empty)
+};
+
+struct PyrLevelView {  // what kernels see
+  const uint8_t* img;
+  const short2* deriv;
+  int w, h, pitch;
+};
+
+struct PyrView {
+  PyrLevelView lv[MAX_LEVELS];
+  int nlevels;
+};
+
+struct Profile {
+  bool on = false;
+  int64_t launches[VO_K_COUNT] = {0};
+  double ms[VO_K_COUNT] = {0};
+  struct Pending { int kind; cudaEvent_t a, b; };
+  std::vector<Pending> pending;
+  std::vector<cudaEvent_t> pool;
+};
+
+}  // namespace vo
+
+struct vo_ctx {
+  vo_params p;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  int64_t launch_count = 0;
+  vo::Profile prof;
+
+  // image staging + pyramids: slot 0/1 ping-pong left images (reference <-> current), slot 2 right
+  uint8_t* d_raw[3] = {nullptr, nullptr, nullptr};
+  vo::Pyramid pyr[3];
+  uint64_t stamp_counter = 0;
+
+  // point buffers (capacity max_points)
+  int cap = 0;
+  float2 *d_xy_in = nullptr, *d_xy_trk = nullptr;        // LK input / output
+  uint8_t* d_status = nullptr;
+  float* d_err = nullptr;
+  float3* d_xyz_in = nullptr;
+  float2 *d_c_ref = nullptr, *d_c_trk = nullptr;         // after status compaction
+  float3* d_c_xyz = nullptr;
+  float2 *d_f_ref = nullptr, *d_f_trk = nullptr;         // after F-mask compaction
+  float3* d_f_xyz = nullptr;
+  float3* d_xyz_tmp = nullptr;                           // triangulation / transform output
+  uint8_t* d_mask = nullptr;
+  int32_t* d_idx = nullptr;                              // inlier indices
+  int* d_count = nullptr;                                // small int scratch (16 ints)
+  int* h_count = nullptr;                                // pinned mirror
+
+  // sequence state (vo_seq_*): reference set resident in HBM
+  float2* d_seq_xy = nullptr;
+  float3* d_seq_xyz = nullptr;
+  int seq_n = 0;
+  int seq_ref_slot = -1;
+
+  // RANSAC buffers (capacity max_hypotheses)
+  int cap_h = 0;
+  int32_t* d_samples = nullptr;   // H x 7
+  int32_t* h_samples = nullptr;   // pinned
+  double* d_models = nullptr;     // F: H x 3 x 9 ; PnP: H x 18 (rvec, tvec, R'(9), pad)
+  int32_t* d_counts = nullptr;    // F: H x 3 ; PnP: H
+  int* d_sel = nullptr;           // [0]=best flat index, [1]=n_iters, [2]=best count, [3]=n_records
+  int* h_sel = nullptr;           // pinned
+  double* d_pose = nullptr;       // 16 doubles: refined rvec,tvec + diagnostics
+  double* h_pose = nullptr;       // pinned
+  double* d_cam = nullptr;        // P1 (12), P2 (12), M (12) scratch
+  // last-call debug views
+  int last_pnp_h = 0, last_f_h = 0;
+
+  // pinned host staging for images and point outputs
+  uint8_t* h_img[3] = {nullptr, nullptr, nullptr};
+  float* h_pts = nullptr;         // cap * 8 floats
+
+  // LK work counters
+  unsigned long long* d_lk_work = nullptr;  // [0]=point-levels, [1]=iterations
+  unsigned long long* h_lk_work = nullptr;
+};
+
+namespace vo {
+
+void set_error(const char* fmt, ...);
+
+#define VO_CUDA(call)                                                                      \
+  do {                                                                                     \
+    cudaError_t _e = (call);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      vo::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e));  \
+      return VO_ERR_CUDA;                                                                  \
+    }                                                                                      \
+  } while (0)
+
+#define VO_TRY(expr)            \
+  do {                          \
+    int _r = (expr);            \
+    if (_r != VO_OK) return _r; \
+  } while (0)
+
+// Launch bracket: counts launches, optionally records events around the launch.
+struct LaunchScope {
+  vo_ctx* c;
+  int kind;
+  cudaEvent_t a = nullptr, b = nullptr;
+  LaunchScope(vo_ctx* ctx, int k);
+  ~LaunchScope();
+};
+
+static inline int div_up(int a, int b) { return (a + b - 1) / b; }
+
+// stage launchers (each returns VO_OK / VO_ERR_CUDA) -------------------------------------
+int pyr_alloc(vo_ctx* c, Pyramid& p);
+void pyr_free(Pyramid& p);
+int pyr_build(vo_ctx* c, int slot, const uint8_t* d_tight /*w*h device*/, bool with_deriv);
+int pyr_ensure_deriv(vo_ctx* c, int slot);
+PyrView pyr_view(const Pyramid& p);
+
+int lk_launch(vo_ctx* c, int slot_prev, int slot_next, const float2* d_prev, int n, float2* d_next, uint8_t* d_status,
+              float* d_err);
+
+int grid_launch(vo_ctx* c, int rows, int cols, int step, float2* d_xy, int* n_out);
+// order-preserving compaction of up to three parallel arrays by flag==1; count -> d_count[slot]
+int compact_launch(vo_ctx* c, const uint8_t* d_flags, int n, const float2* a_in, float2* a_out, const float2* b_in,
+                   float2* b_out, const float3* c_in, float3* c_out, int32_t* idx_out, int count_slot);
+int triangulate_launch(vo_ctx* c, const double* d_P1P2, const float2* a, const float2* b, int n, float3* out,
+                       const double* d_M /*nullable: fused rigid transform -> out2*/, float3* out2);
+int transform_launch(vo_ctx* c, const double* d_M, const float3* in, int n, float3* out);
+
+int fmat_solve_launch(vo_ctx* c, const float2* m1, const float2* m2, const int32_t* d_samples, int h, double* d_models,
+                      int32_t* d_counts);
+int fmat_score_launch(vo_ctx* c, const float2* m1, const float2* m2, int n, const double* d_models, int32_t* d_counts,
+                      int h, float thr2);
+int fmat_mask_launch(vo_ctx* c, const float2* m1, const float2* m2, int n, const double* d_models, const int* d_sel,
+                     float thr2, uint8_t* d_mask);
+int pnp_solve_launch(vo_ctx* c, const float3* xyz, const float2* xy, const int32_t* d_samples, int h, double* d_models,
+                     int32_t* d_counts);
+int pnp_score_launch(vo_ctx* c, const float3* xyz, const float2* xy, int n, const double* d_models, int32_t* d_counts,
+                     int h, float thr2);
+int pnp_mask_launch(vo_ctx* c, const float3* xyz, const float2* xy, int n, const double* d_models, const int* d_sel,
+                    float thr2, uint8_t* d_mask);
+// RANSAC record-setter scan: counts[n_models] (flattened, models_per_sample each) -> d_sel
+int select_launch(vo_ctx* c, const int32_t* d_counts, int n_samples, int models_per_sample, int model_points, int n_points,
+                  double conf, int max_iters, int* d_sel);
+int pnp_refine_launch(vo_ctx* c, const float3* xyz, const float2* xy, const int32_t* d_idx, const int* d_n_inl,
+                      const double* d_models, const int* d_sel, double* d_pose);
+
+int anms_launch(vo_ctx* c, const float* h_xy, const float* h_resp, int n, int num_keep, int32_t* keep_idx, int cap,
+                int* n_keep);
+int synth_launch(vo_ctx* c, int seed, int frame, int eye, uint8_t* d_out);
+int fp32_peak_launch(vo_ctx* c, double* tflops);
+
+}  // namespace vo

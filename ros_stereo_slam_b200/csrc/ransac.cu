@@ -1,0 +1,396 @@
+// ransac.cu -- K4/K6/K7: the two RANSAC estimators of the hot path, restructured for a GPU:
+// every minimal-sample hypothesis is solved in parallel, every (hypothesis, point) pair is
+// scored in parallel, and OpenCV's *sequential* acceptance rule (a hypothesis is accepted iff
+// its inlier count beats every earlier one and lies before the adaptively shrinking iteration
+// limit) is replayed afterwards by a prefix-max scan -- so the result is the one the serial
+// loop of cv::RANSACPointSetRegistrator::run would return for the same sample list.
+//
+//   F-matrix : cv::findFundamentalMat(FM_RANSAC)  reference src/tracking.cpp:34,75
+//   PnP      : cv::solvePnPRansac (EPnP-5)         reference src/keyFrameManagement.cpp:84,88
+//
+// All geometry is FP64 in OpenCV's operation order (cvmath.cuh / fmat7.cuh, --fmad=false);
+// the residual is rounded to float and compared with (float)(thr*thr) like OpenCV does.
+#include "common.cuh"
+#include "cvmath.cuh"
+#include "fmat7.cuh"
+
+namespace vo {
+
+constexpr int PNP_STRIDE = 16;  // doubles per PnP model: rvec(3) tvec(3) R(9) pad
+constexpr int F_STRIDE = 9;     // doubles per F model (3 per sample)
+
+// ================================================================ hypothesis generation
+// One thread per minimal sample; one-thread warps would waste lanes, so samples are packed
+// SOLVE_TPB per CTA: the solvers are long dependent FP64 chains (Jacobi sweeps), i.e.
+// latency-bound, and small CTAs spread them over all SMs.
+constexpr int SOLVE_TPB = 8;
+
+__global__ void __launch_bounds__(SOLVE_TPB)
+fmat_solve_kernel(const float2* __restrict__ m1, const float2* __restrict__ m2, const int32_t* __restrict__ samples,
+                  int h, double* __restrict__ models, int32_t* __restrict__ counts) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= h) return;
+  float a[14], b[14];
+#pragma unroll
+  for (int i = 0; i < 7; i++) {
+    const int idx = samples[s * 7 + i];
+    const float2 p = m1[idx], q = m2[idx];
+    a[2 * i] = p.x; a[2 * i + 1] = p.y;
+    b[2 * i] = q.x; b[2 * i + 1] = q.y;
+  }
+  double F[27];
+  int n = fmat_7point(a, b, F);
+  if (n < 0 || n > 3) n = 0;
+  for (int k = 0; k < 3; k++) {
+    counts[s * 3 + k] = k < n ? 0 : -1;
+    if (k < n)
+      for (int i = 0; i < 9; i++) models[(size_t)(s * 3 + k) * F_STRIDE + i] = F[k * 9 + i];
+  }
+}
+
+__global__ void __launch_bounds__(SOLVE_TPB)
+pnp_solve_kernel(const float3* __restrict__ xyz, const float2* __restrict__ xy, const int32_t* __restrict__ samples,
+                 int h, Intrinsics K, double* __restrict__ models, int32_t* __restrict__ counts) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= h) return;
+  float obj[15], img[10];
+#pragma unroll
+  for (int i = 0; i < 5; i++) {
+    const int idx = samples[s * 5 + i];
+    const float3 p = xyz[idx];
+    const float2 q = xy[idx];
+    obj[3 * i] = p.x; obj[3 * i + 1] = p.y; obj[3 * i + 2] = p.z;
+    img[2 * i] = q.x; img[2 * i + 1] = q.y;
+  }
+  double R[9], t[3], rvec[3], R2[9];
+  epnp5<false>(obj, img, K, R, t);
+  rodrigues_mat2vec(R, rvec);       // the RANSAC model is (rvec, tvec) ...
+  rodrigues_vec2mat(rvec, R2);      // ... and projectPoints converts it back
+  double* m = models + (size_t)s * PNP_STRIDE;
+  for (int i = 0; i < 3; i++) {
+    m[i] = rvec[i];
+    m[3 + i] = t[i];
+  }
+  for (int i = 0; i < 9; i++) m[6 + i] = R2[i];
+  m[15] = 0;
+  counts[s] = 0;
+}
+
+// ================================================================ scoring
+__device__ __forceinline__ float fmat_err(const double* F, float2 p1, float2 p2) {
+  const double x1 = p1.x, y1 = p1.y, x2 = p2.x, y2 = p2.y;
+  double a = F[0] * x1 + F[1] * y1 + F[2];
+  double b = F[3] * x1 + F[4] * y1 + F[5];
+  double c = F[6] * x1 + F[7] * y1 + F[8];
+  const double s2 = 1. / (a * a + b * b);
+  const double d2 = x2 * a + y2 * b + c;
+  a = F[0] * x2 + F[3] * y2 + F[6];
+  b = F[1] * x2 + F[4] * y2 + F[7];
+  c = F[2] * x2 + F[5] * y2 + F[8];
+  const double s1 = 1. / (a * a + b * b);
+  const double d1 = x1 * a + y1 * b + c;
+  const double e1 = d1 * d1 * s1, e2 = d2 * d2 * s2;
+  return (float)((e1 < e2) ? e2 : e1);  // std::max(e1, e2)
+}
+
+__device__ __forceinline__ float pnp_err(const double* m /*PNP_STRIDE*/, const Intrinsics& K, float3 P, float2 q) {
+  const double* R = m + 6;
+  const double* t = m + 3;
+  const double X = P.x, Y = P.y, Z = P.z;
+  double x = R[0] * X + R[1] * Y + R[2] * Z + t[0];
+  double y = R[3] * X + R[4] * Y + R[5] * Z + t[1];
+  double z = R[6] * X + R[7] * Y + R[8] * Z + t[2];
+  z = z ? 1. / z : 1;
+  x *= z;
+  y *= z;
+  const float u = (float)(x * K.fx + K.cx);
+  const float v = (float)(y * K.fy + K.cy);
+  const float dx = __fsub_rn(q.x, u), dy = __fsub_rn(q.y, v);
+  return __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+}
+
+constexpr int SCORE_TPB = 256;
+constexpr int SCORE_HB = 16;  // hypotheses per CTA (staged in shared memory)
+
+// grid.x = point tiles, grid.y = hypothesis batches.  Each thread keeps its correspondence in
+// registers and walks the batch; per-hypothesis counts are reduced warp (ballot) -> CTA
+// (shared atomics) -> global (one atomic per CTA and hypothesis).
+__global__ void __launch_bounds__(SCORE_TPB)
+fmat_score_kernel(const float2* __restrict__ m1, const float2* __restrict__ m2, int n, const double* __restrict__ models,
+                  int32_t* __restrict__ counts, int n_models, float thr2, const int* __restrict__ limit) {
+  __shared__ double sF[SCORE_HB * F_STRIDE];
+  __shared__ int sCnt[SCORE_HB];
+  __shared__ int sValid[SCORE_HB];
+  const int m0 = blockIdx.y * SCORE_HB;
+  if (limit && m0 >= *limit * 3) return;
+  for (int i = threadIdx.x; i < SCORE_HB * F_STRIDE; i += blockDim.x) {
+    const int m = m0 + i / F_STRIDE;
+    sF[i] = m < n_models ? models[(size_t)m0 * F_STRIDE + i] : 0.;
+  }
+  if (threadIdx.x < SCORE_HB) {
+    const int m = m0 + threadIdx.x;
+    sCnt[threadIdx.x] = 0;
+    sValid[threadIdx.x] = (m < n_models) && counts[m] >= 0;
+  }
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool act = i < n;
+  float2 p1 = make_float2(0, 0), p2 = make_float2(0, 0);
+  if (act) {
+    p1 = m1[i];
+    p2 = m2[i];
+  }
+#pragma unroll 1
+  for (int k = 0; k < SCORE_HB; k++) {
+    if (!sValid[k]) continue;
+    const bool in = act && (fmat_err(sF + k * F_STRIDE, p1, p2) <= thr2);
+    const unsigned b = __ballot_sync(0xffffffffu, in);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(&sCnt[k], __popc(b));
+  }
+  __syncthreads();
+  if (threadIdx.x < SCORE_HB && sValid[threadIdx.x] && sCnt[threadIdx.x])
+    atomicAdd(&counts[m0 + threadIdx.x], sCnt[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(SCORE_TPB)
+pnp_score_kernel(const float3* __restrict__ xyz, const float2* __restrict__ xy, int n, const double* __restrict__ models,
+                 int32_t* __restrict__ counts, int n_models, Intrinsics K, float thr2, const int* __restrict__ limit) {
+  __shared__ double sM[SCORE_HB * PNP_STRIDE];
+  __shared__ int sCnt[SCORE_HB];
+  const int m0 = blockIdx.y * SCORE_HB;
+  if (limit && m0 >= *limit) return;
+  for (int i = threadIdx.x; i < SCORE_HB * PNP_STRIDE; i += blockDim.x) {
+    const int m = m0 + i / PNP_STRIDE;
+    sM[i] = m < n_models ? models[(size_t)m0 * PNP_STRIDE + i] : 0.;
+  }
+  if (threadIdx.x < SCORE_HB) sCnt[threadIdx.x] = 0;
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool act = i < n;
+  float3 P = make_float3(0, 0, 1);
+  float2 q = make_float2(0, 0);
+  if (act) {
+    P = xyz[i];
+    q = xy[i];
+  }
+  const int kmax = min(SCORE_HB, n_models - m0);
+#pragma unroll 1
+  for (int k = 0; k < kmax; k++) {
+    const bool in = act && (pnp_err(sM + k * PNP_STRIDE, K, P, q) <= thr2);
+    const unsigned b = __ballot_sync(0xffffffffu, in);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(&sCnt[k], __popc(b));
+  }
+  __syncthreads();
+  if (threadIdx.x < kmax && sCnt[threadIdx.x]) atomicAdd(&counts[m0 + threadIdx.x], sCnt[threadIdx.x]);
+}
+
+// ================================================================ best-model inlier mask
+__global__ void fmat_mask_kernel(const float2* __restrict__ m1, const float2* __restrict__ m2, int n,
+                                 const double* __restrict__ models, const int* __restrict__ sel, float thr2,
+                                 uint8_t* __restrict__ mask) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int best = sel[0];
+  uint8_t v = 0;
+  if (best >= 0) v = fmat_err(models + (size_t)best * F_STRIDE, m1[i], m2[i]) <= thr2;
+  mask[i] = v;
+}
+
+__global__ void pnp_mask_kernel(const float3* __restrict__ xyz, const float2* __restrict__ xy, int n,
+                                const double* __restrict__ models, const int* __restrict__ sel, Intrinsics K,
+                                float thr2, uint8_t* __restrict__ mask) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int best = sel[0];
+  uint8_t v = 0;
+  if (best >= 0) v = pnp_err(models + (size_t)best * PNP_STRIDE, K, xyz[i], xy[i]) <= thr2;
+  mask[i] = v;
+}
+
+// ================================================================ sequential acceptance replay
+// cv::RANSACUpdateNumIters
+__device__ int ransac_update_num_iters(double p, double ep, int model_points, int max_iters) {
+  p = fmax(p, 0.);
+  p = fmin(p, 1.);
+  ep = fmax(ep, 0.);
+  ep = fmin(ep, 1.);
+  double num = fmax(1. - p, DBL_MIN);
+  double denom = 1. - pow(1. - ep, (double)model_points);
+  if (denom < DBL_MIN) return 0;
+  num = log(num);
+  denom = log(denom);
+  return denom >= 0 || -num >= max_iters * (-denom) ? max_iters : (int)rint(num / denom);
+}
+
+constexpr int SEL_THREADS = 1024;
+
+// counts: flattened [sample][model] inlier counts (-1 = no such model).  One CTA.
+// A model is a *candidate* iff its count exceeds every earlier count and modelPoints-1
+// (prefix max); candidates are then replayed in order with the adaptive iteration limit.
+__global__ void __launch_bounds__(SEL_THREADS)
+select_kernel(const int32_t* __restrict__ counts, int n_samples, int mps, int model_points, int n_points, double conf,
+              int max_iters, int* __restrict__ sel) {
+  __shared__ int s_excl[SEL_THREADS];
+  __shared__ int s_warp[32];
+  __shared__ unsigned s_cand[32];
+  const int t = threadIdx.x;
+  const int total = n_samples * mps;
+  const int chunk = (total + SEL_THREADS - 1) / SEL_THREADS;
+  const int beg = t * chunk, end = min(beg + chunk, total);
+  int mx = -1;
+  for (int i = beg; i < end; i++) mx = max(mx, counts[i]);
+  // inclusive prefix max over threads
+  int incl = mx;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int v = __shfl_up_sync(0xffffffffu, incl, d);
+    if ((t & 31) >= d) incl = max(incl, v);
+  }
+  if ((t & 31) == 31) s_warp[t >> 5] = incl;
+  __syncthreads();
+  if (t < 32) {
+    int w = s_warp[t];
+    int wi = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int v = __shfl_up_sync(0xffffffffu, wi, d);
+      if (t >= d) wi = max(wi, v);
+    }
+    // exclusive over warps
+    int ex = __shfl_up_sync(0xffffffffu, wi, 1);
+    s_warp[t] = t == 0 ? -1 : ex;
+  }
+  __syncthreads();
+  int ex_lane = __shfl_up_sync(0xffffffffu, incl, 1);
+  if ((t & 31) == 0) ex_lane = -1;
+  const int floor0 = model_points - 1;
+  const int excl = max(max(s_warp[t >> 5], ex_lane), floor0);
+  s_excl[t] = excl;
+  const unsigned cand = __ballot_sync(0xffffffffu, mx > excl);
+  if ((t & 31) == 0) s_cand[t >> 5] = cand;
+  __syncthreads();
+  if (t == 0) {
+    int niters = max(max_iters, 1);
+    int best = -1, best_count = 0, n_rec = 0;
+    int open_sample = -1;  // OpenCV tests `iter < niters` once per sample: all models of an
+                           // admitted sample are scored even if the first one shrinks niters
+    bool stop = false;
+    for (int w = 0; w < 32 && !stop; w++) {
+      unsigned bits = s_cand[w];
+      while (bits && !stop) {
+        const int l = __ffs(bits) - 1;
+        bits &= bits - 1;
+        const int th = w * 32 + l;
+        int run = s_excl[th];
+        const int b2 = th * chunk, e2 = min(b2 + chunk, total);
+        for (int i = b2; i < e2; i++) {
+          const int g = counts[i];
+          if (g > run) {
+            const int smp = i / mps;
+            if (smp != open_sample) {
+              if (smp >= niters) {
+                stop = true;
+                break;
+              }
+              open_sample = smp;
+            }
+            run = g;
+            best = i;
+            best_count = g;
+            n_rec++;
+            niters = ransac_update_num_iters(conf, (double)(n_points - g) / n_points, model_points, niters);
+          }
+        }
+      }
+    }
+    sel[0] = best;
+    sel[1] = niters;
+    sel[2] = best_count;
+    sel[3] = n_rec;
+  }
+}
+
+// ================================================================ launchers
+static Intrinsics intr(const vo_ctx* c) { return Intrinsics{c->p.fx, c->p.fy, c->p.cx, c->p.cy}; }
+
+int fmat_solve_launch(vo_ctx* c, const float2* m1, const float2* m2, const int32_t* d_samples, int h, double* d_models,
+                      int32_t* d_counts) {
+  if (h <= 0) return VO_OK;
+  {
+    LaunchScope ls(c, VO_K_FMAT_SOLVE);
+    fmat_solve_kernel<<<div_up(h, SOLVE_TPB), SOLVE_TPB, 0, c->stream>>>(m1, m2, d_samples, h, d_models, d_counts);
+  }
+  VO_CUDA(cudaGetLastError());
+  return VO_OK;
+}
+
+int fmat_score_launch(vo_ctx* c, const float2* m1, const float2* m2, int n, const double* d_models, int32_t* d_counts,
+                      int h, float thr2) {
+  if (h <= 0 || n <= 0) return VO_OK;
+  dim3 g(div_up(n, SCORE_TPB), div_up(h * 3, SCORE_HB));
+  {
+    LaunchScope ls(c, VO_K_FMAT_SCORE);
+    fmat_score_kernel<<<g, SCORE_TPB, 0, c->stream>>>(m1, m2, n, d_models, d_counts, h * 3, thr2, nullptr);
+  }
+  VO_CUDA(cudaGetLastError());
+  return VO_OK;
+}
+
+int fmat_mask_launch(vo_ctx* c, const float2* m1, const float2* m2, int n, const double* d_models, const int* d_sel,
+                     float thr2, uint8_t* d_mask) {
+  if (n <= 0) return VO_OK;
+  {
+    LaunchScope ls(c, VO_K_FMAT_SCORE);
+    fmat_mask_kernel<<<div_up(n, 256), 256, 0, c->stream>>>(m1, m2, n, d_models, d_sel, thr2, d_mask);
+  }
+  VO_CUDA(cudaGetLastError());
+  return VO_OK;
+}
+
+int pnp_solve_launch(vo_ctx* c, const float3* xyz, const float2* xy, const int32_t* d_samples, int h, double* d_models,
+                     int32_t* d_counts) {
+  if (h <= 0) return VO_OK;
+  {
+    LaunchScope ls(c, VO_K_PNP_SOLVE);
+    pnp_solve_kernel<<<div_up(h, SOLVE_TPB), SOLVE_TPB, 0, c->stream>>>(xyz, xy, d_samples, h, intr(c), d_models,
+                                                                       d_counts);
+  }
+  VO_CUDA(cudaGetLastError());
+  return VO_OK;
+}
+
+int pnp_score_launch(vo_ctx* c, const float3* xyz, const float2* xy, int n, const double* d_models, int32_t* d_counts,
+                     int h, float thr2) {
+  if (h <= 0 || n <= 0) return VO_OK;
+  dim3 g(div_up(n, SCORE_TPB), div_up(h, SCORE_HB));
+  {
+    LaunchScope ls(c, VO_K_PNP_SCORE);
+    pnp_score_kernel<<<g, SCORE_TPB, 0, c->stream>>>(xyz, xy, n, d_models, d_counts, h, intr(c), thr2, nullptr);
+  }
+  VO_CUDA(cudaGetLastError());
+  return VO_OK;
+}
+
+int pnp_mask_launch(vo_ctx* c, const float3* xyz, const float2* xy, int n, const double* d_models, const int* d_sel,
+                    float thr2, uint8_t* d_mask) {
+  if (n <= 0) return VO_OK;
+  {
+    LaunchScope ls(c, VO_K_PNP_SCORE);
+    pnp_mask_kernel<<<div_up(n, 256), 256, 0, c->stream>>>(xyz, xy, n, d_models, d_sel, intr(c), thr2, d_mask);
+  }
+  VO_CUDA(cudaGetLastError());
+  return VO_OK;
+}
+
+int select_launch(vo_ctx* c, const int32_t* d_counts, int n_samples, int models_per_sample, int model_points,
+                  int n_points, double conf, int max_iters, int* d_sel) {
+  {
+    LaunchScope ls(c, VO_K_SELECT);
+    select_kernel<<<1, SEL_THREADS, 0, c->stream>>>(d_counts, n_samples, models_per_sample, model_points, n_points,
+                                                    conf, max_iters, d_sel);
+  }
+  VO_CUDA(cudaGetLastError());
+  return VO_OK;
+}
+
+}  // namespace vo

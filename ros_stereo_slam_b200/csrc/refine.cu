@@ -1,0 +1,224 @@
+// refine.cu -- K8: Levenberg-Marquardt pose refinement on the RANSAC inliers, i.e. the final
+// solvePnP(SOLVEPNP_ITERATIVE, useExtrinsicGuess = best RANSAC model) inside
+// cv::solvePnPRansac (reference call site src/keyFrameManagement.cpp:84,88).
+//
+// Restates OpenCV's CvLevMarq state machine (6 parameters, criteria 20 iterations /
+// FLT_EPSILON relative step, lambda = 10^k starting at k=-3, damped normal equations solved
+// by SVD) over the pixel reprojection error of cvProjectPoints2 with analytic Jacobians.
+// One CTA: the residual/Jacobian pass is data-parallel over the inliers with an FP64 tree
+// reduction; the 6x6 solve and the state machine run on thread 0.  Parallel summation
+// reorders OpenCV's sequential sums (relative 1e-13), far inside the 1e-4 rad / 1e-3 m
+// pose tolerance.
+#include "common.cuh"
+#include "cvmath.cuh"
+
+namespace vo {
+
+constexpr int REF_THREADS = 1024;
+constexpr int NACC = 28;  // 21 (JtJ upper) + 6 (JtErr) + 1 (|err|^2)
+
+struct PoseJac {
+  double R[9];
+  double dRdr[27];  // dR_k/dr_i at [i*9+k]
+};
+
+__device__ void rodrigues_with_jacobian(const double r_[3], PoseJac& o) {
+  double rx = r_[0], ry = r_[1], rz = r_[2];
+  const double theta = sqrt(rx * rx + ry * ry + rz * rz);
+  if (theta < DBL_EPSILON) {
+    for (int i = 0; i < 9; i++) o.R[i] = (i % 4 == 0) ? 1. : 0.;
+    for (int i = 0; i < 27; i++) o.dRdr[i] = 0;
+    o.dRdr[5] = o.dRdr[15] = o.dRdr[19] = -1;
+    o.dRdr[7] = o.dRdr[11] = o.dRdr[21] = 1;
+    return;
+  }
+  const double c = cos(theta), s = sin(theta), c1 = 1. - c, itheta = 1. / theta;
+  rx *= itheta; ry *= itheta; rz *= itheta;
+  const double rrt[9] = {rx * rx, rx * ry, rx * rz, rx * ry, ry * ry, ry * rz, rx * rz, ry * rz, rz * rz};
+  const double r_x[9] = {0, -rz, ry, rz, 0, -rx, -ry, rx, 0};
+  const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  for (int k = 0; k < 9; k++) o.R[k] = c * I[k] + c1 * rrt[k] + s * r_x[k];
+  const double drrt[27] = {rx + rx, ry, rz, ry, 0, 0, rz, 0, 0, 0, rx, 0, rx, ry + ry, rz, 0, rz, 0,
+                           0, 0, rx, 0, 0, ry, rx, ry, rz + rz};
+  const double d_r_x_[27] = {0, 0, 0, 0, 0, -1, 0, 1, 0, 0, 0, 1, 0, 0, 0, -1, 0, 0, 0, -1, 0, 1, 0, 0, 0, 0, 0};
+  for (int i = 0; i < 3; i++) {
+    const double ri = i == 0 ? rx : i == 1 ? ry : rz;
+    const double a0 = -s * ri, a1 = (s - 2 * c1 * itheta) * ri, a2 = c1 * itheta;
+    const double a3 = (c - s * itheta) * ri, a4 = s * itheta;
+    for (int k = 0; k < 9; k++)
+      o.dRdr[i * 9 + k] = a0 * I[k] + a1 * rrt[k] + a2 * drrt[i * 9 + k] + a3 * r_x[k] + a4 * d_r_x_[i * 9 + k];
+  }
+}
+
+// block-wide sum of NACC doubles per thread -> s_out[NACC] (valid for all threads after return)
+__device__ void block_reduce(double* acc, double* s_part /*32*NACC*/, double* s_out /*NACC*/) {
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+#pragma unroll
+  for (int k = 0; k < NACC; k++) {
+    double v = acc[k];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if (lane == 0) s_part[w * NACC + k] = v;
+  }
+  __syncthreads();
+  if (t < NACC) {
+    double v = 0;
+    for (int ww = 0; ww < REF_THREADS / 32; ww++) v += s_part[ww * NACC + t];
+    s_out[t] = v;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(REF_THREADS)
+pnp_refine_kernel(const float3* __restrict__ xyz, const float2* __restrict__ xy, const int32_t* __restrict__ idx,
+                  const int* __restrict__ n_inl_p, const double* __restrict__ models, const int* __restrict__ sel,
+                  Intrinsics K, double* __restrict__ pose_out) {
+  __shared__ double s_part[32 * NACC];
+  __shared__ double s_sum[NACC];
+  __shared__ PoseJac s_pj;
+  __shared__ double s_param[6];
+  __shared__ int s_state;  // 0 = need J+err at s_param, 1 = need err only, 2 = done
+  const int t = threadIdx.x;
+  const int n = *n_inl_p;
+  const int best = sel[0];
+  if (best < 0 || n < 3) {
+    if (t == 0) pose_out[6] = -1;
+    return;
+  }
+  // thread-0 state (CvLevMarq)
+  double param[6], prev_param[6], JtJ[36], JtErr[6];
+  double prev_err_norm = DBL_MAX, err_norm = 0;
+  int lambda_lg10 = -3, iters = 0;
+  const int max_iter = 20;
+  const double epsilon = (double)FLT_EPSILON;
+  if (t == 0) {
+    const double* m = models + (size_t)best * 16;
+    for (int i = 0; i < 6; i++) {
+      param[i] = m[i];
+      prev_param[i] = m[i];
+      s_param[i] = m[i];
+    }
+    s_state = 0;
+  }
+  __syncthreads();
+
+  for (int guard = 0; guard < 1000; guard++) {
+    const int state = s_state;
+    if (state == 2) break;
+    if (t == 0) rodrigues_with_jacobian(s_param, s_pj);
+    __syncthreads();
+    const bool need_j = state == 0;
+    double acc[NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; k++) acc[k] = 0;
+    const double* R = s_pj.R;
+    const double* dR = s_pj.dRdr;
+    const double t0 = s_param[3], t1 = s_param[4], t2 = s_param[5];
+    for (int i = t; i < n; i += REF_THREADS) {
+      const int id = idx[i];
+      const float3 P = xyz[id];
+      const float2 q = xy[id];
+      const double X = P.x, Y = P.y, Z = P.z;
+      double x = R[0] * X + R[1] * Y + R[2] * Z + t0;
+      double y = R[3] * X + R[4] * Y + R[5] * Z + t1;
+      double z = R[6] * X + R[7] * Y + R[8] * Z + t2;
+      z = z ? 1. / z : 1;
+      x *= z;
+      y *= z;
+      const double ex = (x * K.fx + K.cx) - (double)q.x;
+      const double ey = (y * K.fy + K.cy) - (double)q.y;
+      acc[27] += ex * ex + ey * ey;
+      if (need_j) {
+        double jx[6], jy[6];
+        for (int j = 0; j < 3; j++) {
+          const double dx0 = X * dR[j * 9 + 0] + Y * dR[j * 9 + 1] + Z * dR[j * 9 + 2];
+          const double dy0 = X * dR[j * 9 + 3] + Y * dR[j * 9 + 4] + Z * dR[j * 9 + 5];
+          const double dz0 = X * dR[j * 9 + 6] + Y * dR[j * 9 + 7] + Z * dR[j * 9 + 8];
+          jx[j] = K.fx * (z * (dx0 - x * dz0));
+          jy[j] = K.fy * (z * (dy0 - y * dz0));
+        }
+        jx[3] = K.fx * z; jx[4] = 0; jx[5] = K.fx * (-x * z);
+        jy[3] = 0; jy[4] = K.fy * z; jy[5] = K.fy * (-y * z);
+        int k = 0;
+#pragma unroll
+        for (int a = 0; a < 6; a++)
+#pragma unroll
+          for (int b = a; b < 6; b++) acc[k++] += jx[a] * jx[b] + jy[a] * jy[b];
+#pragma unroll
+        for (int a = 0; a < 6; a++) acc[21 + a] += jx[a] * ex + jy[a] * ey;
+      }
+    }
+    block_reduce(acc, s_part, s_sum);
+
+    if (t == 0) {
+      // LM step from prev_param with the current JtJ/JtErr and lambda
+      auto lm_step = [&]() {
+        const double lambda = exp(lambda_lg10 * log(10.));
+        double A[36], x[6];
+        for (int i = 0; i < 36; i++) A[i] = JtJ[i];
+        for (int i = 0; i < 6; i++) A[i * 6 + i] *= 1. + lambda;
+        solve_svd<6, 6>(A, JtErr, x);
+        for (int i = 0; i < 6; i++) param[i] = prev_param[i] - x[i];
+      };
+      if (state == 0) {
+        // CALC_J: JtJ, JtErr at param; step
+        int k = 0;
+        for (int a = 0; a < 6; a++)
+          for (int b = a; b < 6; b++) {
+            JtJ[a * 6 + b] = s_sum[k];
+            JtJ[b * 6 + a] = s_sum[k];
+            k++;
+          }
+        for (int a = 0; a < 6; a++) JtErr[a] = s_sum[21 + a];
+        for (int i = 0; i < 6; i++) prev_param[i] = param[i];
+        lm_step();
+        if (iters == 0) prev_err_norm = sqrt(s_sum[27]);
+        s_state = 1;
+      } else {
+        // CHECK_ERR
+        err_norm = sqrt(s_sum[27]);
+        bool retry = false;
+        if (err_norm > prev_err_norm) {
+          if (++lambda_lg10 <= 16) {
+            lm_step();
+            retry = true;
+          }
+        }
+        if (!retry) {
+          lambda_lg10 = lambda_lg10 - 1 > -16 ? lambda_lg10 - 1 : -16;
+          double dn = 0, pn = 0;
+          for (int i = 0; i < 6; i++) {
+            dn += (param[i] - prev_param[i]) * (param[i] - prev_param[i]);
+            pn += prev_param[i] * prev_param[i];
+          }
+          if (++iters >= max_iter || sqrt(dn) / sqrt(pn) < epsilon) {
+            s_state = 2;
+          } else {
+            prev_err_norm = err_norm;
+            s_state = 0;
+          }
+        }
+      }
+      for (int i = 0; i < 6; i++) s_param[i] = param[i];
+    }
+    __syncthreads();
+  }
+  if (t == 0) {
+    for (int i = 0; i < 6; i++) pose_out[i] = s_param[i];
+    pose_out[6] = (double)iters;
+    pose_out[7] = err_norm;
+  }
+}
+
+int pnp_refine_launch(vo_ctx* c, const float3* xyz, const float2* xy, const int32_t* d_idx, const int* d_n_inl,
+                      const double* d_models, const int* d_sel, double* d_pose) {
+  Intrinsics K{c->p.fx, c->p.fy, c->p.cx, c->p.cy};
+  {
+    LaunchScope ls(c, VO_K_PNP_REFINE);
+    pnp_refine_kernel<<<1, REF_THREADS, 0, c->stream>>>(xyz, xy, d_idx, d_n_inl, d_models, d_sel, K, d_pose);
+  }
+  VO_CUDA(cudaGetLastError());
+  return VO_OK;
+}
+
+}  // namespace vo

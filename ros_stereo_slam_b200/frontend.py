@@ -1,0 +1,326 @@
+"""Host-side mirror of the reference's hot-path interface over the C ABI.
+
+`VisualFrontEnd` exposes the member functions of the reference's `class visualSLAM` that make
+up the VO front-end (reference include/visualSLAM.h:152-169) under the same names and argument
+meaning, with numpy arrays standing in for cv::Mat / std::vector<Point2f|Point3f>.  Every call
+goes through libvo_b200.so (hand-written CUDA for sm_100a); nothing is computed on the CPU.
+The C++ equivalent for the ROS node is include/vo_b200.hpp.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import VoError, VoFrameResult, check
+
+
+def _f32(a, cols):
+    a = np.ascontiguousarray(a, np.float32)
+    if a.size == 0:
+        return a.reshape(0, cols)
+    return a.reshape(-1, cols)
+
+
+def _u8img(img):
+    if img is None:
+        return None
+    img = np.asarray(img)
+    if img.dtype != np.uint8 or img.ndim != 2:
+        raise ValueError("images must be 2-D uint8 (1 channel)")
+    if img.strides[1] != 1:
+        img = np.ascontiguousarray(img)
+    return img
+
+
+def _p(a, t=None):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class VisualFrontEnd:
+    def __init__(self, **params):
+        self.lib = _lib.load()
+        self.params = _lib.default_params(**params)
+        h = C.c_void_p()
+        check(self.lib.vo_create(C.byref(self.params), C.byref(h)))
+        self.h = h
+        self.cap = self.params.max_points
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.vo_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ intrinsics helpers
+    @property
+    def K(self):
+        p = self.params
+        return np.array([[p.fx, 0, p.cx], [0, p.fy, p.cy], [0, 0, 1]], np.float64)
+
+    # ------------------------------------------------------------------ a-1 .. a-9 raw stages
+    def denseKeypointExtractor(self, img, stepSize):
+        """visualSLAM::denseKeypointExtractor (src/tracking.cpp:4-12) -> (N,2) float32."""
+        rows, cols = img.shape[:2]
+        out = np.empty((self.cap, 2), np.float32)
+        n = C.c_int()
+        check(self.lib.vo_grid_keypoints(self.h, rows, cols, int(stepSize), _p(out), self.cap, C.byref(n)))
+        return out[:n.value].copy()
+
+    def adaptiveNonMaximalSuppresion(self, xy, response, numToKeep):
+        """adaptiveNonMaximalSuppresion (src/ANMS.cpp:18-67) -> kept indices, canonical order."""
+        xy = _f32(xy, 2)
+        resp = np.ascontiguousarray(response, np.float32)
+        keep = np.empty(max(len(xy), 1), np.int32)
+        n = C.c_int()
+        check(self.lib.vo_anms(self.h, _p(xy), _p(resp), len(xy), int(numToKeep), _p(keep), len(keep), C.byref(n)))
+        return keep[:n.value].copy()
+
+    def calcOpticalFlowPyrLK(self, prevImg, nextImg, prevPts):
+        """cv::calcOpticalFlowPyrLK with the reference's defaults -> (nextPts, status, err)."""
+        a, b = _u8img(prevImg), _u8img(nextImg)
+        pts = _f32(prevPts, 2)
+        n = len(pts)
+        nxt = np.zeros((n, 2), np.float32)
+        st = np.zeros(n, np.uint8)
+        err = np.zeros(n, np.float32)
+        if a.strides[0] != b.strides[0]:
+            b = np.ascontiguousarray(b)
+            a = np.ascontiguousarray(a)
+        check(self.lib.vo_lk_track(self.h, _p(a), _p(b), a.strides[0], _p(pts), n, _p(nxt), _p(st), _p(err)))
+        return nxt, st, err
+
+    def pyramid_level(self, img, level):
+        a = _u8img(img)
+        w, h = C.c_int(), C.c_int()
+        check(self.lib.vo_debug_pyramid_level(self.h, _p(a), a.strides[0], level, None, None, C.byref(w), C.byref(h)))
+        lv = np.zeros((h.value, w.value), np.uint8)
+        dv = np.zeros((h.value, w.value, 2), np.int16)
+        check(self.lib.vo_debug_pyramid_level(self.h, _p(a), a.strides[0], level, _p(lv), _p(dv), C.byref(w), C.byref(h)))
+        return lv, dv
+
+    def findFundamentalMat(self, pts1, pts2, thr, conf=0.99, samples=None):
+        """cv::findFundamentalMat(FM_RANSAC) -> (F 3x3 or None, mask (N,) u8, n_inliers)."""
+        a, b = _f32(pts1, 2), _f32(pts2, 2)
+        n = len(a)
+        mask = np.zeros(n, np.uint8)
+        F = np.zeros(9, np.float64)
+        ni = C.c_int()
+        s = None if samples is None else np.ascontiguousarray(samples, np.int32).reshape(-1, 7)
+        r = self.lib.vo_fmat_ransac(self.h, _p(a), _p(b), n, C.c_double(thr), C.c_double(conf),
+                                    _p(s), 0 if s is None else len(s), _p(mask), _p(F), C.byref(ni))
+        check(r, (_lib.VO_OK, _lib.VO_ERR_NO_MODEL))
+        return (F.reshape(3, 3) if r == _lib.VO_OK else None), mask, ni.value
+
+    def last_fmat(self):
+        cap = self.params.max_hypotheses
+        models = np.zeros((cap, 3, 9), np.float64)
+        counts = np.zeros((cap, 3), np.int32)
+        nh, bs, bm, nit = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        check(self.lib.vo_debug_last_fmat(self.h, _p(models), _p(counts), cap, C.byref(nh), C.byref(bs), C.byref(bm),
+                                          C.byref(nit)))
+        return dict(models=models[:nh.value], counts=counts[:nh.value], best=(bs.value, bm.value), n_iters=nit.value)
+
+    def triangulatePoints(self, P1, P2, pts1, pts2):
+        """cv::triangulatePoints + float dehomogenisation (src/triangulation.cpp:152-160)."""
+        a, b = _f32(pts1, 2), _f32(pts2, 2)
+        P1 = np.ascontiguousarray(P1, np.float64)
+        P2 = np.ascontiguousarray(P2, np.float64)
+        out = np.zeros((len(a), 3), np.float32)
+        check(self.lib.vo_triangulate(self.h, _p(P1), _p(P2), _p(a), _p(b), len(a), _p(out)))
+        return out
+
+    def solvePnPRansac(self, pts3d, pts2d, iters=100, thr=1.0, conf=0.99, samples=None):
+        """cv::solvePnPRansac(..., false, iters, thr, conf, inliers) -> dict(ok, rvec, tvec, inliers)."""
+        X, x = _f32(pts3d, 3), _f32(pts2d, 2)
+        n = len(X)
+        rvec = np.zeros(3)
+        tvec = np.zeros(3)
+        inl = np.zeros(max(n, 1), np.int32)
+        ni = C.c_int()
+        s = None if samples is None else np.ascontiguousarray(samples, np.int32).reshape(-1, 5)
+        r = self.lib.vo_pnp_ransac(self.h, _p(X), _p(x), n, int(iters), C.c_double(thr), C.c_double(conf),
+                                   _lib.VO_PNP_EPNP5, _p(s), 0 if s is None else len(s),
+                                   _p(rvec), _p(tvec), _p(inl), len(inl), C.byref(ni))
+        check(r, (_lib.VO_OK, _lib.VO_ERR_NO_MODEL))
+        return dict(ok=r == _lib.VO_OK, rvec=rvec, tvec=tvec, inliers=inl[:ni.value].copy())
+
+    def last_pnp(self):
+        cap = self.params.max_hypotheses
+        models = np.zeros((cap, 6), np.float64)
+        counts = np.zeros(cap, np.int32)
+        nh, best, nit = C.c_int(), C.c_int(), C.c_int()
+        check(self.lib.vo_debug_last_pnp(self.h, _p(models), _p(counts), cap, C.byref(nh), C.byref(best), C.byref(nit)))
+        return dict(models=models[:nh.value], counts=counts[:nh.value], best=best.value, n_iters=nit.value)
+
+    def update3dtransformation(self, pts3d, pose3x4):
+        """visualSLAM::update3dtransformation (src/keyFrameManagement.cpp:33-46)."""
+        X = _f32(pts3d, 3)
+        M = np.ascontiguousarray(pose3x4, np.float64).reshape(3, 4)
+        out = np.zeros_like(X)
+        check(self.lib.vo_transform_points(self.h, _p(M), _p(X), len(X), _p(out)))
+        return out
+
+    def pose_from_pnp(self, rvec, tvec):
+        """src/VisualSLAM.cpp:70-74,93-97 -> 3x4 [R|t] camera->world."""
+        r = np.ascontiguousarray(rvec, np.float64).ravel()
+        t = np.ascontiguousarray(tvec, np.float64).ravel()
+        M = np.zeros(12)
+        check(self.lib.vo_pose_from_pnp(_p(r), _p(t), _p(M)))
+        return M.reshape(3, 4)
+
+    # ------------------------------------------------------------------ the reference's method boundaries
+    def denseLKtracking(self, refImg, curImg, refPts):
+        """visualSLAM::denseLKtracking (src/tracking.cpp:14-28) -> (refPts_kept, trackPts_kept)."""
+        a, b = _u8img(refImg), _u8img(curImg)
+        pts = _f32(refPts, 2)
+        n = len(pts)
+        r = np.zeros((n, 2), np.float32)
+        t = np.zeros((n, 2), np.float32)
+        m = C.c_int()
+        check(self.lib.vo_dense_lk_tracking(self.h, _p(a), _p(b), a.strides[0], _p(pts), n, _p(r), _p(t), C.byref(m)))
+        return r[:m.value].copy(), t[:m.value].copy()
+
+    def FmatThresholding(self, refPts, trkPts):
+        """visualSLAM::FmatThresholding (src/tracking.cpp:30-43)."""
+        a, b = _f32(refPts, 2), _f32(trkPts, 2)
+        n = len(a)
+        r = np.zeros((n, 2), np.float32)
+        t = np.zeros((n, 2), np.float32)
+        m = C.c_int()
+        check(self.lib.vo_fmat_thresholding(self.h, _p(a), _p(b), n, _p(r), _p(t), C.byref(m)))
+        return r[:m.value].copy(), t[:m.value].copy()
+
+    def stereoTriangulate(self, im1, im2):
+        """visualSLAM::stereoTriangulate (src/triangulation.cpp:73-166) -> (ref3dPts, ref2dPts)."""
+        a, b = _u8img(im1), _u8img(im2)
+        if a is None or b is None:
+            print("NULL IMG")
+            return None
+        xyz = np.zeros((self.cap, 3), np.float32)
+        xy = np.zeros((self.cap, 2), np.float32)
+        n = C.c_int()
+        check(self.lib.vo_stereo_triangulate(self.h, _p(a), _p(b), a.strides[0], _p(xyz), _p(xy), self.cap, C.byref(n)))
+        return xyz[:n.value].copy(), xy[:n.value].copy()
+
+    def insertKeyFrames(self, imL, imR, pose4dTransform):
+        """visualSLAM::insertKeyFrames (src/keyFrameManagement.cpp:9-31)
+        -> (ref3dCoords world, ftrPts, untransformed)."""
+        a, b = _u8img(imL), _u8img(imR)
+        M = np.ascontiguousarray(pose4dTransform, np.float64).reshape(3, 4)
+        xyz = np.zeros((self.cap, 3), np.float32)
+        cam = np.zeros((self.cap, 3), np.float32)
+        xy = np.zeros((self.cap, 2), np.float32)
+        n = C.c_int()
+        check(self.lib.vo_insert_keyframe(self.h, _p(a), _p(b), a.strides[0], _p(M), _p(xyz), _p(xy), _p(cam), self.cap,
+                                          C.byref(n)))
+        return xyz[:n.value].copy(), xy[:n.value].copy(), cam[:n.value].copy()
+
+    def PyrLKtrackFrame2Frame(self, refimg, curImg, refPts, ref3dpts):
+        """visualSLAM::PyrLKtrackFrame2Frame (src/tracking.cpp:46-91)
+        -> (refRetpts = tracked 2-D, ref3dretPts, inlierReferencePyrLKPts)."""
+        a, b = _u8img(refimg), _u8img(curImg)
+        p2, p3 = _f32(refPts, 2), _f32(ref3dpts, 3)
+        n = len(p2)
+        t2 = np.zeros((n, 2), np.float32)
+        t3 = np.zeros((n, 3), np.float32)
+        r2 = np.zeros((n, 2), np.float32)
+        m = C.c_int()
+        check(self.lib.vo_track_frame(self.h, _p(a), _p(b), a.strides[0], _p(p2), _p(p3), n, _p(t2), _p(t3), _p(r2),
+                                      C.byref(m)))
+        return t2[:m.value].copy(), t3[:m.value].copy(), r2[:m.value].copy()
+
+    def PerspectiveNpointEstimation(self, prevImg, curImg, ref2dPoints, ref3dPoints):
+        """visualSLAM::PerspectiveNpointEstimation (src/keyFrameManagement.cpp:73-94)
+        -> dict(trk2d, trk3d, ref2d_inl, rvec, tvec, inliers, attempt, shutdown)."""
+        a, b = _u8img(prevImg), _u8img(curImg)
+        p2, p3 = _f32(ref2dPoints, 2), _f32(ref3dPoints, 3)
+        n = len(p2)
+        t2 = np.zeros((n, 2), np.float32)
+        t3 = np.zeros((n, 3), np.float32)
+        r2 = np.zeros((n, 2), np.float32)
+        rvec, tvec = np.zeros(3), np.zeros(3)
+        inl = np.zeros(max(n, 1), np.int32)
+        m, ni, att = C.c_int(), C.c_int(), C.c_int()
+        r = self.lib.vo_pnp_frame(self.h, _p(a), _p(b), a.strides[0], _p(p2), _p(p3), n, _p(t2), _p(t3), _p(r2),
+                                  C.byref(m), _p(rvec), _p(tvec), _p(inl), len(inl), C.byref(ni), C.byref(att))
+        check(r, (_lib.VO_OK, _lib.VO_ERR_LOW_INLIERS))
+        return dict(trk2d=t2[:m.value].copy(), trk3d=t3[:m.value].copy(), ref2d_inl=r2[:m.value].copy(), rvec=rvec,
+                    tvec=tvec, inliers=inl[:ni.value].copy(), attempt=att.value,
+                    shutdown=(r == _lib.VO_ERR_LOW_INLIERS))
+
+    # ------------------------------------------------------------------ device-resident sequence driver
+    def seq_init(self, left, right, is_device=False, stride=None):
+        n = C.c_int()
+        if is_device:
+            check(self.lib.vo_seq_init(self.h, C.c_void_p(left), C.c_void_p(right), stride or self.params.width, 1,
+                                       C.byref(n)))
+        else:
+            a, b = _u8img(left), _u8img(right)
+            check(self.lib.vo_seq_init(self.h, _p(a), _p(b), a.strides[0], 0, C.byref(n)))
+        return n.value
+
+    def seq_track(self, left, right=None, is_device=False, stride=None, force_keyframe=False):
+        res = VoFrameResult()
+        if is_device:
+            r = self.lib.vo_seq_track(self.h, C.c_void_p(left), C.c_void_p(right) if right else None,
+                                      stride or self.params.width, 1, int(force_keyframe), C.byref(res))
+        else:
+            a, b = _u8img(left), _u8img(right)
+            r = self.lib.vo_seq_track(self.h, _p(a), _p(b), a.strides[0], 0, int(force_keyframe), C.byref(res))
+        check(r, (_lib.VO_OK, _lib.VO_ERR_LOW_INLIERS))
+        return res, r
+
+    def seq_reference(self):
+        xy = np.zeros((self.cap, 2), np.float32)
+        xyz = np.zeros((self.cap, 3), np.float32)
+        n = C.c_int()
+        check(self.lib.vo_seq_get_reference(self.h, _p(xy), _p(xyz), self.cap, C.byref(n)))
+        return xy[:n.value].copy(), xyz[:n.value].copy()
+
+    # ------------------------------------------------------------------ measurement helpers
+    def sync(self):
+        check(self.lib.vo_sync(self.h))
+
+    def profile_enable(self, on=True):
+        check(self.lib.vo_profile_enable(self.h, int(on)))
+
+    def profile_read(self, reset=False):
+        out = {}
+        for i, name in enumerate(_lib.KERNELS):
+            l, ms = C.c_int64(), C.c_double()
+            check(self.lib.vo_profile_read(self.h, i, C.byref(l), C.byref(ms), int(reset)))
+            out[name] = (l.value, ms.value)
+        return out
+
+    def launch_count(self):
+        return self.lib.vo_launch_count(self.h)
+
+    def lk_work(self):
+        a, b = C.c_int64(), C.c_int64()
+        check(self.lib.vo_lk_work(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def measure_fp32_peak(self):
+        t = C.c_double()
+        check(self.lib.vo_measure_fp32_peak(self.h, C.byref(t)))
+        return t.value
+
+    def synth_render(self, seed, frame, eye):
+        """Harness: render one synthetic frame on the GPU and return it as a numpy array."""
+        w, h = self.params.width, self.params.height
+        d = C.c_void_p()
+        check(self.lib.vo_alloc_dev(self.h, C.byref(d), w * h))
+        try:
+            check(self.lib.vo_synth_render_dev(self.h, seed, frame, eye, d))
+            out = np.zeros((h, w), np.uint8)
+            check(self.lib.vo_memcpy_d2h(self.h, _p(out), d, w * h))
+        finally:
+            self.lib.vo_free_dev(self.h, d)
+        return out

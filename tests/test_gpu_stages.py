@@ -1,0 +1,264 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (ctypes), against the
+oracle (cv2 call-through + replay loops) on the same inputs, and against the committed golden
+vectors.  Tolerances are the ones BASELINE.json's north_star states:
+  keypoint sets / inlier index sets: bit-exact;  tracks: 0.01 px;  3-D points: 1e-4 relative;
+  pose: 1e-4 rad, 1e-3 m.
+"""
+import cv2
+import numpy as np
+import pytest
+
+from oracle import glue, lk as olk, replay, synth, cvrng
+from gpu_common import golden, make_frontend
+
+pytestmark = pytest.mark.gpu
+
+TOL_PX = 0.01
+TOL_REL3D = 1e-4
+TOL_RAD = 1e-4
+TOL_M = 1e-3
+
+
+@pytest.fixture(scope="module")
+def G():
+    return golden()
+
+
+@pytest.fixture(scope="module")
+def fe():
+    f = make_frontend()
+    yield f
+    f.close()
+
+
+@pytest.fixture(scope="module")
+def fe9():
+    f = make_frontend(grid_step=9)
+    yield f
+    f.close()
+
+
+def test_grid_keypoints_bit_exact(fe):
+    img = np.zeros((376, 1241), np.uint8)
+    for step in (30, 10, 9, 5, 2):
+        a = fe.denseKeypointExtractor(img, step)
+        b = glue.dense_keypoint_extractor(376, 1241, step)
+        assert a.shape == b.shape and np.array_equal(a, b)
+    assert len(fe.denseKeypointExtractor(np.zeros((40, 50), np.uint8), 30)) == 0
+
+
+def test_pyramid_and_scharr_bit_exact(fe, G):
+    L0 = G["L0"]
+    n, pyr = cv2.buildOpticalFlowPyramid(L0, (21, 21), 3, withDerivatives=True)
+    for l in range(4):
+        lv, dv = fe.pyramid_level(L0, l)
+        assert np.array_equal(lv, pyr[2 * l])
+        assert np.array_equal(dv, pyr[2 * l + 1])
+        assert int(lv.astype(np.int64).sum()) == int(G["pyr_sums"][l])
+        assert int(np.abs(dv.astype(np.int64)).sum()) == int(G["deriv_abs_sums"][l])
+
+
+@pytest.mark.parametrize("pair", ["temporal", "stereo"])
+@pytest.mark.parametrize("step", [30, 9])
+def test_lk_matches_opencv(fe, G, pair, step):
+    L0 = G["L0"]
+    nxt = G["L1"] if pair == "temporal" else G["R0"]
+    pts = glue.dense_keypoint_extractor(376, 1241, step)
+    extra = np.array([[5, 5], [1236, 371], [0.4, 200.7], [1240.2, 3.3], [620.5, 375.9]], np.float32)
+    pts_x = np.concatenate([pts, extra])
+    p, st, err = fe.calcOpticalFlowPyrLK(L0, nxt, pts_x)
+    # (1) live cv2
+    p0, st0, err0 = cv2.calcOpticalFlowPyrLK(L0, nxt, pts_x.reshape(-1, 1, 2), None)
+    p0 = p0.reshape(-1, 2); st0 = st0.ravel(); err0 = err0.ravel()
+    assert np.array_equal(st, st0)
+    d = np.abs(p - p0).max(1)
+    ok = st0 == 1
+    assert d[ok].max() <= TOL_PX, d[ok].max()
+    assert np.mean(d[ok] == 0) > 0.9          # the vast majority is bit-identical
+    assert np.abs(err - err0)[ok].max() < 5e-3
+    # (2) committed golden vectors (grid part)
+    assert np.array_equal(st[:len(pts)], G[f"lk_{pair}_{step}_status"])
+    assert np.abs(p[:len(pts)] - G[f"lk_{pair}_{step}_pts"]).max(1)[st[:len(pts)] == 1].max() <= TOL_PX
+    # (3) the scalar restatement with exact integer sums is the kernel's bit-exact twin
+    if step == 30:
+        p1, st1, err1 = olk.calc_optical_flow_pyr_lk(L0, nxt, pts_x)
+        assert np.array_equal(st, st1)
+        assert np.array_equal(p[st1 == 1], p1[st1 == 1])
+        assert np.array_equal(err[st1 == 1], err1[st1 == 1])
+
+
+def test_lk_empty_and_out_of_image(fe, G):
+    L0, L1 = G["L0"], G["L1"]
+    p, st, err = fe.calcOpticalFlowPyrLK(L0, L1, np.zeros((0, 2), np.float32))
+    assert len(p) == 0
+    pts = np.array([[-50, -50], [2000, 100], [100, 900], [600, 180]], np.float32)
+    p, st, err = fe.calcOpticalFlowPyrLK(L0, L1, pts)
+    p0, st0, _ = cv2.calcOpticalFlowPyrLK(L0, L1, pts.reshape(-1, 1, 2), None)
+    assert np.array_equal(st, st0.ravel())
+
+
+def test_triangulate_bit_exact(fe):
+    P1, P2 = glue.projection_matrices()
+    rng = np.random.default_rng(0)
+    n = 20000
+    z = rng.uniform(3, 80, n)
+    x1 = np.stack([rng.uniform(0, 1241, n), rng.uniform(0, 376, n)], 1)
+    x2 = x1.copy(); x2[:, 0] -= glue.FX * 0.54 / z
+    x1 = (x1 + rng.normal(0, 0.1, (n, 2))).astype(np.float32)
+    x2 = (x2 + rng.normal(0, 0.1, (n, 2))).astype(np.float32)
+    a = fe.triangulatePoints(P1, P2, x1, x2)
+    b = glue.triangulate(P1, P2, x1, x2)
+    rel = np.abs(a - b).max(1) / np.maximum(np.abs(b).max(1), 1e-9)
+    assert rel.max() <= TOL_REL3D
+    assert np.array_equal(a, b)          # in fact bit-identical (same Jacobi SVD op order)
+    assert len(fe.triangulatePoints(P1, P2, x1[:0], x2[:0])) == 0
+
+
+def test_transform_points_bit_exact(fe):
+    rng = np.random.default_rng(1)
+    X = rng.uniform(-50, 50, (5000, 3)).astype(np.float32)
+    pose = glue.camera_pose_from_pnp([0.01, -0.3, 0.02], [0.5, -0.1, 12.0])
+    assert np.array_equal(fe.update3dtransformation(X, pose), glue.update_3d_transformation(X, pose))
+    assert np.allclose(fe.pose_from_pnp([0.01, -0.3, 0.02], [0.5, -0.1, 12.0]), pose, rtol=0, atol=1e-15)
+
+
+def _flow_case(n, seed, outlier_frac=0.2, grid=False):
+    import test_oracle_ransac as t
+    return t._flow_case(n, seed, outlier_frac, grid)
+
+
+@pytest.mark.parametrize("n,seed,thr,grid", [(350, 0, 1.0, True), (350, 1, 3.0, True), (2000, 2, 1.0, False),
+                                             (5000, 3, 3.0, False), (18000, 6, 1.0, False), (15, 5, 3.0, False)])
+def test_fmat_ransac_mask_bit_exact(fe, n, seed, thr, grid):
+    m1, m2 = _flow_case(n, seed, grid=grid)
+    F0, mask0 = cv2.findFundamentalMat(m1, m2, cv2.FM_RANSAC, thr, 0.99)
+    F, mask, ni = fe.findFundamentalMat(m1, m2, thr, 0.99)
+    assert np.array_equal(mask, mask0.ravel())
+    assert ni == int(mask0.sum())
+    assert np.allclose(F, F0, rtol=1e-7, atol=1e-9)
+    # replay: same minimal-sample index list on both sides
+    r = replay.fmat_ransac(m1, m2, thr, 0.99)
+    F2, mask2, _ = fe.findFundamentalMat(m1, m2, thr, 0.99, samples=r["samples"])
+    assert np.array_equal(mask2, r["mask"])
+    last = fe.last_fmat()
+    assert last["best"] == r["best"]
+    got = {(s, m): int(last["counts"][s, m]) for s in range(len(last["counts"])) for m in range(3) if last["counts"][s, m] >= 0}
+    want = {(s, m): g for s, m, g in r["counts"]}
+    assert got == want                      # every hypothesis has the same inlier count
+
+
+def test_fmat_too_few_points(fe):
+    m1, m2 = _flow_case(14, 0)
+    from ros_stereo_slam_b200 import VoError
+    with pytest.raises(VoError):
+        fe.findFundamentalMat(m1, m2, 1.0)
+
+
+@pytest.mark.parametrize("n,frac,iters,thr,conf", [(500, 0.1, 100, 1.0, 0.99), (5000, 0.3, 100, 1.0, 0.99),
+                                                  (20000, 0.5, 100, 1.0, 0.99), (3000, 0.5, 400, 8.0, 0.98)])
+def test_pnp_ransac_matches_opencv(fe, n, frac, iters, thr, conf):
+    X, xy, _, _, _ = synth.pnp_stress_case(n, frac, 0.3, seed=3)
+    ok, rvec, tvec, inl = cv2.solvePnPRansac(X.reshape(-1, 1, 3), xy.reshape(-1, 1, 2), glue.K, np.zeros((4, 1)),
+                                             None, None, False, iters, thr, conf)
+    r = fe.solvePnPRansac(X, xy, iters, thr, conf)
+    assert r["ok"]
+    assert np.array_equal(r["inliers"], inl.ravel())             # inlier index set bit-exact
+    assert np.abs(r["rvec"] - rvec.ravel()).max() <= TOL_RAD
+    assert np.abs(r["tvec"] - tvec.ravel()).max() <= TOL_M
+    assert np.abs(r["rvec"] - rvec.ravel()).max() < 1e-7 and np.abs(r["tvec"] - tvec.ravel()).max() < 1e-6
+
+
+def test_pnp_hypotheses_and_counts_replay(G):
+    """Golden replay list: every hypothesis and every inlier count must match OpenCV's."""
+    fe = make_frontend(ransac_exhaustive=1)
+    X, xy = G["stress_X"], G["stress_xy"]
+    S = G["stress_samples"]
+    r = fe.solvePnPRansac(X, xy, 200, 1.0, 0.99, samples=S)
+    last = fe.last_pnp()
+    assert len(last["counts"]) == len(S)
+    assert np.array_equal(last["counts"], G["stress_counts"])
+    assert np.abs(last["models"] - G["stress_hyp"]).max() < 1e-9
+    assert last["best"] == int(G["stress_best"]) and last["n_iters"] == int(G["stress_niters"])
+    assert np.array_equal(r["inliers"], G["stress_inliers"])
+    assert np.abs(r["rvec"] - G["stress_rvec"]).max() < 1e-7 and np.abs(r["tvec"] - G["stress_tvec"]).max() < 1e-6
+    # exhaustive and early-exit evaluation give the same answer
+    fe2 = make_frontend(ransac_exhaustive=0)
+    r2 = fe2.solvePnPRansac(X, xy, 200, 1.0, 0.99)
+    assert np.array_equal(r2["inliers"], r["inliers"]) and np.array_equal(r2["rvec"], r["rvec"])
+    fe.close(); fe2.close()
+
+
+def test_pnp_default_sample_stream(fe):
+    X, xy, _, _, _ = synth.pnp_stress_case(500, 0.1, 0.3, seed=3)
+    fe.solvePnPRansac(X, xy, 100, 1.0, 0.99)
+    # first sample drawn for N=500
+    assert list(cvrng.sample_list(500, 5, 1)[0]) == [105, 4, 440, 173, 331]
+
+
+@pytest.mark.parametrize("step", [30, 9])
+def test_stage_boundaries_match_reference_glue(G, step):
+    fe = make_frontend(grid_step=step)
+    L0, R0, L1, R1 = G["L0"], G["R0"], G["L1"], G["R1"]
+    # stereoTriangulate
+    xyz, ref2d = fe.stereoTriangulate(L0, R0)
+    xyz0, ref0 = glue.stereo_triangulate(L0, R0, step)
+    assert np.array_equal(ref2d, ref0)                       # sampled keypoint set bit-exact
+    assert np.array_equal(ref2d, G[f"stereo_{step}_ref2d"])
+    rel = np.abs(xyz - xyz0).max(1) / np.abs(xyz0).max(1)
+    assert rel.max() <= TOL_REL3D
+    # PerspectiveNpointEstimation on the reference's own inputs
+    res = fe.PerspectiveNpointEstimation(L0, L1, ref0, xyz0)
+    ref = glue.perspective_n_point_estimation(L0, L1, ref0, xyz0, iters=100)
+    assert res["trk2d"].shape == ref["trk2d"].shape
+    assert np.abs(res["trk2d"] - ref["trk2d"]).max() <= TOL_PX
+    assert np.array_equal(res["trk3d"], ref["trk3d"])
+    assert np.array_equal(res["ref2d_inl"], ref["ref2d_inl"])
+    assert res["attempt"] == ref["attempt"] and res["shutdown"] == ref["shutdown"]
+    assert np.array_equal(res["inliers"], ref["inliers"])
+    assert np.abs(res["rvec"] - ref["rvec"]).max() <= TOL_RAD
+    assert np.abs(res["tvec"] - ref["tvec"]).max() <= TOL_M
+    assert np.array_equal(res["inliers"], G[f"pnp_{step}_inliers"])
+    # insertKeyFrames
+    pose = glue.camera_pose_from_pnp(ref["rvec"], ref["tvec"])
+    w3, w2, cam = fe.insertKeyFrames(L1, R1, pose)
+    w3r, w2r, camr = glue.insert_key_frames(L1, R1, pose, step)
+    assert np.array_equal(w2, w2r)
+    assert (np.abs(w3 - w3r).max(1) / np.abs(w3r).max(1)).max() <= TOL_REL3D
+    fe.close()
+
+
+def test_anms_set_bit_exact(fe):
+    rng = np.random.default_rng(5)
+    n = 3000
+    xy = np.stack([rng.uniform(0, 1241, n), rng.uniform(0, 376, n)], 1).astype(np.float32)
+    resp = rng.uniform(0, 1, n).astype(np.float32)
+    for keep in (100, 1000, 2999):
+        a = fe.adaptiveNonMaximalSuppresion(xy, resp, keep)
+        b = glue.anms(xy, resp, keep)
+        assert np.array_equal(a, b)
+    # grid keypoints have response 0 -> everything is kept
+    g = glue.dense_keypoint_extractor(376, 1241, 30)
+    a = fe.adaptiveNonMaximalSuppresion(g, np.zeros(len(g), np.float32), 100)
+    assert np.array_equal(np.sort(a), np.arange(len(g)))
+    # fewer than numToKeep: returned unchanged
+    assert np.array_equal(fe.adaptiveNonMaximalSuppresion(xy[:50], resp[:50], 100), np.arange(50))
+
+
+def test_sequence_driver_matches_reference_loop():
+    """Device-resident sequence driver vs the reference frame loop restated over cv2."""
+    sc = synth.Scene(1)
+    n = 4
+    Ls = [sc.render(i, "L") for i in range(n)]
+    Rs = [sc.render(i, "R") for i in range(n)]
+    for kf in (200, 10 ** 9):
+        fe = make_frontend(kf_min_inliers=min(kf, 2 ** 31 - 1))
+        ref = glue.run_sequence(Ls, Rs, step=30, pnp_iters=100, kf_min_inliers=kf)
+        n0 = fe.seq_init(Ls[0], Rs[0])
+        for i in range(1, n):
+            res, code = fe.seq_track(Ls[i], Rs[i])
+            want = ref[i - 1]
+            assert res.n_lk_in == want["n_lk_in"] and res.n_tracked == want["n_tracked"]
+            assert res.n_inliers == want["n_inliers"] and bool(res.keyframe) == want["keyframe"]
+            assert np.abs(np.array(res.rvec) - want["rvec"]).max() <= TOL_RAD
+            assert np.abs(np.array(res.tvec) - want["tvec"]).max() <= TOL_M
+        fe.close()
