@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s of the VO front-end hot path on synthetic KITTI-shaped stereo sequences.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1], made concrete in SURVEY.md section 8d): 1241x376 u8 stereo
+sequence, grid step 5 -> 18,278 keypoints entering the stereo LK of every frame, 1024 PnP
+hypotheses, keyframe inserted on every frame so that each step does KLT (temporal + stereo),
+F-matrix RANSAC (x2), triangulation and PnP-RANSAC + refinement -- the metric's
+"KLT + triangulate + PnP-RANSAC" per frame.  One step = one frame.
+
+  value : frames/s with the frames already resident in HBM (device pointers), CUDA events on
+          the library's stream, max over ranks.
+  e2e   : the same through the C ABI with HOST buffers: every step copies that step's left and
+          right image from pinned host memory (H2D inside the timed region) and reads the pose
+          and counters back (D2H).
+  N > 1 : replicas only: one independent sequence per GPU, no data-path
+          collective; torch.distributed (NCCL) is used for the barrier and the max/sum of the
+          timings only.
+  --impl reference : the reference's own CPU implementation of the path (the oracle's cv2
+          call-through of the reference glue, all host threads) on a bounded sample of the same
+          workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WIDTH, HEIGHT = 1241, 376
+GRID_STEP = 5
+PNP_ITERS = 1024
+WORKLOAD = "kitti00_synth_1241x376_grid5_18278kp_pnp1024_keyframe_every_frame"
+INT_MAX = 2 ** 31 - 1
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-frames", type=int, default=8, help="frames of the bounded cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--seed", type=int, default=0)
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- helpers
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for l in self.proc.stdout:
+            self.lines.append(l.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def aggregate(elapsed_ms, frames, keypoints, world, backend=None):
+    """Max elapsed time over ranks, sum of units over ranks.  Host-side logic of the N>1 path
+    (tested with gloo, world_size 2, in tests/test_bench_dist.py)."""
+    if world == 1:
+        return elapsed_ms, frames, keypoints
+    import torch
+    import torch.distributed as dist
+    dev = "cuda" if (backend or dist.get_backend()) == "nccl" else "cpu"
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    u = torch.tensor([float(frames), float(keypoints)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(u, op=dist.ReduceOp.SUM)
+    return float(t.item()), int(u[0].item()), int(u[1].item())
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d.get("hbm_gbs", 6650.0)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    from ros_stereo_slam_b200 import VisualFrontEnd, _lib
+    rank, world, local = dist_env()
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = local if world > 1 else 0
+    torch.cuda.set_device(dev)
+    K, W = args.steps, max(args.warmup, 3)
+    nf = K + W + 1
+    fe = VisualFrontEnd(device=dev, grid_step=GRID_STEP, pnp_iters=PNP_ITERS, kf_min_inliers=INT_MAX,
+                        ransac_exhaustive=1)
+    lib = fe.lib
+    img_bytes = WIDTH * HEIGHT
+    seed = args.seed + rank            # one independent sequence per GPU
+    # ---- render the sequence on the GPU (harness kernel), keep a pinned host copy for e2e
+    d_frames = C.c_void_p()
+    _lib.check(lib.vo_alloc_dev(fe.h, C.byref(d_frames), C.c_uint64(2 * nf * img_bytes)))
+    h_frames = C.c_void_p()
+    _lib.check(lib.vo_alloc_host(C.byref(h_frames), C.c_uint64(2 * nf * img_bytes)))
+
+    def dptr(i, eye):
+        return d_frames.value + (2 * i + eye) * img_bytes
+
+    def hptr(i, eye):
+        return h_frames.value + (2 * i + eye) * img_bytes
+
+    for i in range(nf):
+        for eye in (0, 1):
+            _lib.check(lib.vo_synth_render_dev(fe.h, seed, i, eye, C.c_void_p(dptr(i, eye))))
+    _lib.check(lib.vo_memcpy_d2h(fe.h, h_frames, d_frames, C.c_uint64(2 * nf * img_bytes)))
+
+    stream = torch.cuda.ExternalStream(lib.vo_cuda_stream(fe.h), device=torch.device("cuda", dev))
+    res = _lib.VoFrameResult()
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run_pass(first, count, device_resident, record):
+        kp = 0
+        for i in range(first, first + count):
+            if device_resident:
+                r = lib.vo_seq_track(fe.h, C.c_void_p(dptr(i, 0)), C.c_void_p(dptr(i, 1)), WIDTH, 1, 0, C.byref(res))
+            else:
+                r = lib.vo_seq_track(fe.h, C.c_void_p(hptr(i, 0)), C.c_void_p(hptr(i, 1)), WIDTH, 0, 0, C.byref(res))
+            _lib.check(r)
+            kp += res.n_lk_in + res.n_lk_in_stereo
+            if record is not None:
+                record.append((res.n_lk_in, res.n_tracked, res.n_inliers, res.n_kf_points,
+                               tuple(res.rvec), tuple(res.tvec)))
+        return kp
+
+    def timed(device_resident):
+        n0 = C.c_int()
+        _lib.check(lib.vo_seq_init(fe.h, C.c_void_p(dptr(0, 0) if device_resident else hptr(0, 0)),
+                                   C.c_void_p(dptr(0, 1) if device_resident else hptr(0, 1)), WIDTH,
+                                   1 if device_resident else 0, C.byref(n0)))
+        run_pass(1, W, device_resident, None)                      # warm-up
+        fe.profile_enable(["lk"])                                  # events around the LK launches only
+        fe.profile_read(reset=True)
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        sampler = ClockSampler(dev)
+        sampler.start()
+        barrier()
+        l0 = fe.launch_count()
+        t0 = time.perf_counter()
+        w0 = fe.lk_work()
+        e0.record(stream)
+        rec = []
+        kp = run_pass(1 + W, K, device_resident, rec)
+        e1.record(stream)
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        launches = fe.launch_count() - l0
+        clocks = sampler.stop()
+        ms = e0.elapsed_time(e1)
+        prof = fe.profile_read(reset=True)
+        fe.profile_enable(None)
+        w1 = fe.lk_work()
+        return dict(ms=ms, wall_ms=wall_ms, kp=kp, launches=launches, clocks=clocks, lk=prof["lk"], rec=rec,
+                    lk_work=(w1[0] - w0[0], w1[1] - w0[1]))
+
+    dev_run = timed(True)
+    host_run = timed(False)
+
+    # ---- per-stage breakdown (separate, untimed pass with every kernel family bracketed)
+    fe.profile_enable("all")
+    fe.profile_read(reset=True)
+    n0 = C.c_int()
+    _lib.check(lib.vo_seq_init(fe.h, C.c_void_p(dptr(0, 0)), C.c_void_p(dptr(0, 1)), WIDTH, 1, C.byref(n0)))
+    nb = min(20, K)
+    lkw_pl = lkw_it = 0
+    for i in range(1, 1 + nb):
+        _lib.check(lib.vo_seq_track(fe.h, C.c_void_p(dptr(i, 0)), C.c_void_p(dptr(i, 1)), WIDTH, 1, 0, C.byref(res)))
+    breakdown = {k: {"launches": v[0] / nb, "ms_per_frame": v[1] / nb} for k, v in fe.profile_read(reset=True).items()}
+    fe.profile_enable(None)
+
+    grid = fe.denseKeypointExtractor(np.zeros((HEIGHT, WIDTH), np.uint8), GRID_STEP)
+    fp32_peak = fe.measure_fp32_peak()
+
+    e_ms, frames, kps = aggregate(dev_run["ms"], K, dev_run["kp"], world)
+    h_ms, frames_h, kps_h = aggregate(host_run["ms"], K, host_run["kp"], world)
+
+    out = None
+    if rank == 0:
+        hbm_peak, hbm_src = load_peaks()
+        fps = frames / (e_ms * 1e-3)
+        fps_e2e = frames_h / (h_ms * 1e-3)
+        lk_launches, lk_ms = dev_run["lk"]
+        lk_avg_ms = lk_ms / max(lk_launches, 1)
+        # algorithmic work: 441*(30 + 13*iters) ops per (point, level), with the
+        # (point, level) pairs and iterations counted by the kernel over the timed region;
+        # bytes per launch = both u8 pyramids + the int16x2 derivative pyramid + 21 B/point
+        pl, it = dev_run["lk_work"]
+        ops_per_launch = 441.0 * (30.0 * pl + 13.0 * it) / max(lk_launches, 1)
+        kp_per_launch = dev_run["kp"] / max(lk_launches, 1)
+        lk_bytes = 2 * 619930 + 4 * 619930 + 21.0 * kp_per_launch
+        achieved_tops = ops_per_launch / (lk_avg_ms * 1e-3) / 1e12
+        roofline = {
+            "kernel": "lk_kernel (pyramidal LK, warp per keypoint)",
+            "bound": "fp32_issue",
+            "achieved": round(achieved_tops, 3), "peak": round(fp32_peak, 2), "unit": "TFLOP/s",
+            "frac": round(achieved_tops / fp32_peak, 4),
+            "peak_source": "FFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP32 figure)",
+            "avg_launch_ms": round(lk_avg_ms, 4), "launches_timed": lk_launches,
+            "ops_per_launch": ops_per_launch, "keypoints_per_launch": round(kp_per_launch, 1),
+            "iterations_per_point_level": round(it / max(pl, 1), 2),
+            "ops_model": "441*(30*point_levels + 13*iterations), counted by the kernel",
+            "hbm": {"achieved": round(lk_bytes / (lk_avg_ms * 1e-3) / 1e9, 2), "peak": hbm_peak, "unit": "GB/s",
+                    "frac": round(lk_bytes / (lk_avg_ms * 1e-3) / 1e9 / hbm_peak, 5), "peak_source": hbm_src,
+                    "note": "working set (~5 MB of pyramids) is L2-resident; HBM is not the bound"},
+            "traffic": None,
+        }
+        out = {
+            "metric": "frames/sec for KLT+triangulate+PnP-RANSAC at 1241x376; Mkeypoints/s tracked",
+            "value": round(fps, 2), "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": round(e_ms / K, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8/int32 fixed-point (LK) + f64 (RANSAC solvers)", "data": "synthetic",
+            "mkeypoints_per_s": round(kps / (e_ms * 1e-3) / 1e6, 3),
+            "keypoints_per_frame": round(kps / frames, 1),
+            "config": {"workload": WORKLOAD, "image": "1241x376 u8 c1", "grid_step": GRID_STEP,
+                       "grid_keypoints": int(len(grid)), "pnp_hypotheses": PNP_ITERS, "ransac_exhaustive": 1,
+                       "frames": K, "keyframe_rule": "every frame (kf_min_inliers=INT_MAX)",
+                       "parallelism": "replicas x%d (one sequence per GPU, no collective)" % world,
+                       "l2": "every step reads two frames not touched before; the %d-frame set is %.0f MB"
+                             % (nf, 2 * nf * img_bytes / 1e6),
+                       "timing": "CUDA events on the library stream, barrier+synchronize both sides, max over ranks"},
+            "e2e": {"value": round(fps_e2e, 2), "unit": "frames/s", "ms_per_step": round(h_ms / K, 4),
+                    "h2d_bytes_per_step": 2 * img_bytes, "d2h_bytes_per_step": C.sizeof(_lib.VoFrameResult),
+                    "api": "vo_seq_track(host left, host right) -> vo_frame_result"},
+            "gpu_launches": int(dev_run["launches"]),
+            "gpu_launches_per_step": round(dev_run["launches"] / K, 1),
+            "clocks": dev_run["clocks"],
+            "wall_ms_per_step": round(dev_run["wall_ms"] / K, 4),
+            "roofline": roofline,
+            "stage_ms_per_frame": {k: round(v["ms_per_frame"], 4) for k, v in breakdown.items()},
+            "last_frame": {"n_lk_in": dev_run["rec"][-1][0], "n_tracked": dev_run["rec"][-1][1],
+                           "n_inliers": dev_run["rec"][-1][2], "n_kf_points": dev_run["rec"][-1][3]},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            frames_np = []
+            ncpu = args.cpu_frames + 1
+            buf = (C.c_uint8 * (2 * ncpu * img_bytes)).from_address(h_frames.value)
+            arr = np.frombuffer(buf, np.uint8).reshape(ncpu, 2, HEIGHT, WIDTH)
+            out["cpu_baseline"] = cpu_reference([arr[i, 0] for i in range(ncpu)], [arr[i, 1] for i in range(ncpu)],
+                                                args.cpu_frames)
+    lib.vo_free_dev(fe.h, d_frames)
+    lib.vo_free_host(h_frames)
+    fe.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+    if out is not None:
+        print(json.dumps(out))
+
+
+# ----------------------------------------------------------------------------- CPU reference
+def cpu_reference(Ls, Rs, n_frames, warm=1):
+    """The reference's CPU path (oracle.glue: the reference glue over OpenCV) on a bounded sample
+    of the same workload: grid step 5, PnP 1024 iterations, keyframe every frame."""
+    import cv2
+    from oracle import glue
+    cores = len(os.sched_getaffinity(0))
+    cv2.setNumThreads(cores)
+    t_first = None
+    recs = glue.run_sequence(Ls[:warm + 1], Rs[:warm + 1], step=GRID_STEP, pnp_iters=PNP_ITERS, kf_min_inliers=10 ** 9)
+    t0 = time.perf_counter()
+    recs = glue.run_sequence(Ls[:n_frames + 1], Rs[:n_frames + 1], step=GRID_STEP, pnp_iters=PNP_ITERS,
+                             kf_min_inliers=10 ** 9)
+    dt = time.perf_counter() - t0
+    # run_sequence also performs the initial stereoTriangulate of frame 0; count per-frame time only
+    per_frame = [r["ms"] for r in recs if "ms" in r]
+    fps = 1e3 / (sum(per_frame) / max(len(per_frame), 1)) if per_frame else 0.0
+    kp = sum(r["n_lk_in"] for r in recs) + len(per_frame) * 18278
+    return {"value": round(fps, 3), "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": "first %d frames of the same sequence (oracle.glue = reference glue restated over cv2 %s, "
+                      "cv2.setNumThreads(%d)); wall %.1f s" % (len(per_frame), cv2.__version__, cores, dt),
+            "ms_per_frame": round(sum(per_frame) / max(len(per_frame), 1), 2),
+            "mkeypoints_per_s": round(kp / (sum(per_frame) * 1e-3) / 1e6, 4) if per_frame else 0.0}
+
+
+def run_reference(args):
+    rank, world, local = dist_env()
+    if rank != 0:
+        return
+    n = max(1, min(args.steps, 24))
+    warm = 1
+    # inputs: the same synthetic sequence; rendered with the library's harness kernel when a GPU is
+    # present (identical frames to our arm), else with the numpy renderer of the oracle
+    Ls, Rs = [], []
+    try:
+        from ros_stereo_slam_b200 import VisualFrontEnd
+        fe = VisualFrontEnd()
+        for i in range(n + 1):
+            Ls.append(fe.synth_render(args.seed, i, 0))
+            Rs.append(fe.synth_render(args.seed, i, 1))
+        fe.close()
+        src = "GPU harness renderer"
+    except Exception:
+        from oracle import synth
+        sc = synth.Scene(args.seed)
+        for i in range(n + 1):
+            Ls.append(sc.render(i, "L"))
+            Rs.append(sc.render(i, "R"))
+        src = "numpy renderer"
+    cb = cpu_reference(Ls, Rs, n, warm)
+    out = {
+        "impl": "reference",
+        "metric": "frames/sec for KLT+triangulate+PnP-RANSAC at 1241x376; Mkeypoints/s tracked",
+        "value": cb["value"], "unit": "frames/s", "n_gpus": args.gpus, "steps": n, "warmup": warm,
+        "ms_per_step": cb["ms_per_frame"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8/int16 fixed-point (LK) + f64 (RANSAC solvers)", "data": "synthetic (" + src + ")",
+        "mkeypoints_per_s": cb["mkeypoints_per_s"],
+        "config": {"workload": WORKLOAD, "grid_step": GRID_STEP, "pnp_hypotheses": PNP_ITERS,
+                   "keyframe_rule": "every frame", "frames": n,
+                   "note": "bounded sample: %d of the requested %d steps" % (n, args.steps)},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

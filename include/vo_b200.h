@@ -48,7 +48,8 @@ enum {
   VO_ERR_NO_MODEL = -6,       /* RANSAC never found a model with enough inliers */
   VO_ERR_LOW_INLIERS = -7,    /* both PnP attempts gave < pnp_min_inliers: the reference's
                                  SHUTDOWN_FLAG (src/keyFrameManagement.cpp:89-92) */
-  VO_ERR_NOT_IMPLEMENTED = -8
+  VO_ERR_NOT_IMPLEMENTED = -8,
+  VO_ERR_SELF_CHECK = -9      /* device numerics differ from the IEEE host evaluation of the same code */
 };
 
 /* minimal solvers for vo_pnp_ransac */
@@ -95,6 +96,8 @@ const char* vo_strerror(int code);
 
 int vo_create(const vo_params* p, vo_ctx** out);
 int vo_destroy(vo_ctx* ctx);
+/* Device-vs-host bit comparison of the FP64 solvers on canned inputs (run by vo_create). */
+int vo_self_check(vo_ctx* ctx);
 
 /* ---- a-1  visualSLAM::denseKeypointExtractor(img, step)      src/tracking.cpp:4-12 ----
  * Raster grid (y-major, x fastest) over a rows x cols image; xy receives up to cap points. */
@@ -148,6 +151,9 @@ int vo_pnp_ransac(vo_ctx* ctx, const float* xyz, const float* xy, int n, int ite
 int vo_debug_last_pnp(vo_ctx* ctx, double* models, int32_t* counts, int cap_h, int* n_h, int* best, int* n_iters);
 int vo_debug_last_fmat(vo_ctx* ctx, double* models, int32_t* counts, int cap_h, int* n_h, int* best_sample,
                        int* best_model, int* n_iters);
+
+/* one EPnP-5 solve on the device with its intermediates (432 doubles), for parity debugging */
+int vo_debug_epnp(vo_ctx* ctx, const float* obj15, const float* img10, double* dbg432);
 
 /* ---- a-9  visualSLAM::update3dtransformation(pts, pose3x4)  src/keyFrameManagement.cpp:33-46
  * (same loop as insertKeyFrames :20-30).  M row-major 3x4 double. */
@@ -223,16 +229,17 @@ int vo_seq_get_reference(vo_ctx* ctx, float* xy, float* xyz, int cap, int* n);
 /* ================= harness / measurement helpers ================================================= */
 void* vo_cuda_stream(vo_ctx* ctx);   /* cudaStream_t every kernel of this ctx is launched on */
 int vo_sync(vo_ctx* ctx);
-/* per-kernel device timing: when enabled, every launch of the named kernel families is bracketed
- * by CUDA events on the ctx stream; vo_profile_read returns launches and summed milliseconds. */
+/* per-kernel device timing: `mask` is a bit set of kernel families (bit k = VO_K_*; 0 = off,
+ * -1 = all).  Every launch of a selected family is bracketed by CUDA events on the ctx stream;
+ * vo_profile_read returns launches and summed milliseconds. */
 enum { VO_K_PYRAMID = 0, VO_K_LK = 1, VO_K_COMPACT = 2, VO_K_FMAT_SOLVE = 3, VO_K_FMAT_SCORE = 4,
        VO_K_TRIANGULATE = 5, VO_K_PNP_SOLVE = 6, VO_K_PNP_SCORE = 7, VO_K_PNP_REFINE = 8,
        VO_K_SELECT = 9, VO_K_MISC = 10, VO_K_COUNT = 11 };
-int vo_profile_enable(vo_ctx* ctx, int on);
+int vo_profile_enable(vo_ctx* ctx, int mask);
 int vo_profile_read(vo_ctx* ctx, int kernel, int64_t* launches, double* ms, int reset);
 int64_t vo_launch_count(vo_ctx* ctx);          /* kernels launched by this ctx since creation */
-/* LK work counters of the last LK launch: point-levels processed and LK iterations executed
- * (the units of the LK roofline in DESIGN.md). */
+/* Cumulative LK work counters since vo_create: (point, level) pairs processed and LK iterations
+ * executed -- the units of the LK roofline in DESIGN.md.  Take differences around a region. */
 int vo_lk_work(vo_ctx* ctx, int64_t* point_levels, int64_t* iterations);
 /* FP32 issue-rate microbenchmark (dependent FFMA chains on every SM): TFLOP/s achieved. */
 int vo_measure_fp32_peak(vo_ctx* ctx, double* tflops);

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libvo_b200.so")
+LIB_PATH = os.path.join(HERE, os.environ.get("VO_B200_LIB", "libvo_b200.so"))
 
 VO_OK = 0
 VO_ERR_INVALID_ARG = -1
@@ -18,6 +18,7 @@ VO_ERR_TOO_FEW_POINTS = -5
 VO_ERR_NO_MODEL = -6
 VO_ERR_LOW_INLIERS = -7
 VO_ERR_NOT_IMPLEMENTED = -8
+VO_ERR_SELF_CHECK = -9
 
 VO_PNP_EPNP5 = 0
 VO_PNP_P3P4 = 1
@@ -61,9 +62,9 @@ _lib = None
 
 # every symbol include/vo_b200.h declares (tests/test_abi.py checks the list against the header)
 SYMBOLS = [
-    "vo_default_params", "vo_abi_version", "vo_last_error", "vo_strerror", "vo_create", "vo_destroy",
+    "vo_default_params", "vo_abi_version", "vo_last_error", "vo_strerror", "vo_create", "vo_destroy", "vo_self_check",
     "vo_grid_keypoints", "vo_anms", "vo_lk_track", "vo_debug_pyramid_level", "vo_fmat_ransac", "vo_triangulate",
-    "vo_pnp_ransac", "vo_debug_last_pnp", "vo_debug_last_fmat", "vo_transform_points", "vo_pose_from_pnp",
+    "vo_pnp_ransac", "vo_debug_last_pnp", "vo_debug_last_fmat", "vo_debug_epnp", "vo_transform_points", "vo_pose_from_pnp",
     "vo_dense_lk_tracking", "vo_fmat_thresholding", "vo_stereo_triangulate", "vo_insert_keyframe",
     "vo_track_frame", "vo_pnp_frame", "vo_seq_init", "vo_seq_track", "vo_seq_get_reference", "vo_cuda_stream",
     "vo_sync", "vo_profile_enable", "vo_profile_read", "vo_launch_count", "vo_lk_work", "vo_measure_fp32_peak",

@@ -17,7 +17,9 @@ OUT = os.path.join(HERE, "libvo_b200.so")
 OBJ = os.path.join(HERE, "build")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
+# VO_HELPERS_NOINLINE: keep the solver helpers as separate device functions (small, robust
+# compile units; see selfcheck.cu for why the code shape matters).
+COMMON = ["-O3", "-lineinfo", "-std=c++17", "-DVO_HELPERS_NOINLINE", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
           "-Xcompiler", "-O2", "--expt-relaxed-constexpr"]
 # FP64 solver files follow OpenCV's operation order: no FMA contraction anywhere in them.
 SOURCES = {
@@ -27,6 +29,7 @@ SOURCES = {
     "points.cu": ["--fmad=false"],
     "ransac.cu": ["--fmad=false"],
     "refine.cu": ["--fmad=false"],
+    "selfcheck.cu": ["--fmad=false"],
     "aux.cu": [],
 }
 HEADERS = ["common.cuh", "cvmath.cuh", "fmat7.cuh", os.path.join("..", "..", "include", "vo_b200.h")]

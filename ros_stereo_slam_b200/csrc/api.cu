@@ -25,7 +25,7 @@ void set_error(const char* fmt, ...) {
 
 LaunchScope::LaunchScope(vo_ctx* ctx, int k) : c(ctx), kind(k) {
   c->launch_count++;
-  if (c->prof.on) {
+  if (c->prof.mask & (1u << k)) {
     auto get = [&]() {
       cudaEvent_t e;
       if (!c->prof.pool.empty()) {
@@ -79,6 +79,7 @@ const char* vo_strerror(int code) {
     case VO_ERR_NO_MODEL: return "RANSAC found no model";
     case VO_ERR_LOW_INLIERS: return "low inlier count after retry (reference SHUTDOWN_FLAG)";
     case VO_ERR_NOT_IMPLEMENTED: return "not implemented";
+    case VO_ERR_SELF_CHECK: return "numerics self-check failed";
   }
   return "unknown";
 }
@@ -192,8 +193,21 @@ int vo_create(const vo_params* p, vo_ctx** out) {
   VO_CUDA(cudaMallocHost(&c->h_lk_work, 2 * sizeof(unsigned long long)));
   VO_CUDA(cudaMemsetAsync(c->d_lk_work, 0, 2 * sizeof(unsigned long long), c->stream));
   VO_CUDA(cudaStreamSynchronize(c->stream));
+  {
+    const int r = selfcheck_run(c);
+    if (r != VO_OK) {
+      vo_destroy(c);
+      return r;
+    }
+  }
   *out = c;
   return VO_OK;
+}
+
+int vo_self_check(vo_ctx* c) {
+  if (!c) return VO_ERR_INVALID_ARG;
+  VO_CUDA(cudaSetDevice(c->device));
+  return selfcheck_run(c);
 }
 
 int vo_destroy(vo_ctx* c) {
@@ -683,6 +697,17 @@ int vo_debug_last_fmat(vo_ctx* c, double* models, int32_t* counts, int cap_h, in
   return sync_stream(c);
 }
 
+int vo_debug_epnp(vo_ctx* c, const float* obj15, const float* img10, double* dbg432) {
+  CHECK_CTX(c);
+  float* d_in = (float*)c->d_xyz_in;
+  double* d_dbg = c->d_models;
+  VO_CUDA(cudaMemcpyAsync(d_in, obj15, 15 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  VO_CUDA(cudaMemcpyAsync(d_in + 16, img10, 10 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  VO_TRY(epnp_debug_launch(c, d_in, d_in + 16, d_dbg));
+  VO_CUDA(cudaMemcpyAsync(dbg432, d_dbg, 432 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  return sync_stream(c);
+}
+
 int vo_transform_points(vo_ctx* c, const double M[12], const float* xyz_in, int n, float* xyz_out) {
   CHECK_CTX(c);
   if (!M || !xyz_in || !xyz_out || n < 0) return VO_ERR_INVALID_ARG;
@@ -924,11 +949,11 @@ int vo_sync(vo_ctx* c) {
   return sync_stream(c);
 }
 
-int vo_profile_enable(vo_ctx* c, int on) {
+int vo_profile_enable(vo_ctx* c, int mask) {
   CHECK_CTX(c);
   VO_TRY(sync_stream(c));
   prof_drain(c);
-  c->prof.on = on != 0;
+  c->prof.mask = (unsigned)mask;
   return VO_OK;
 }
 

@@ -50,7 +50,7 @@ struct PyrView {
 };
 
 struct Profile {
-  bool on = false;
+  unsigned mask = 0;  // bit k: bracket launches of kind k with events
   int64_t launches[VO_K_COUNT] = {0};
   double ms[VO_K_COUNT] = {0};
   struct Pending { int kind; cudaEvent_t a, b; };
@@ -184,6 +184,8 @@ int select_launch(vo_ctx* c, const int32_t* d_counts, int n_samples, int models_
 int pnp_refine_launch(vo_ctx* c, const float3* xyz, const float2* xy, const int32_t* d_idx, const int* d_n_inl,
                       const double* d_models, const int* d_sel, double* d_pose);
 
+int selfcheck_run(vo_ctx* c);
+int epnp_debug_launch(vo_ctx* c, const float* d_obj, const float* d_img, double* d_dbg);
 int anms_launch(vo_ctx* c, const float* h_xy, const float* h_resp, int n, int num_keep, int32_t* keep_idx, int cap,
                 int* n_keep);
 int synth_launch(vo_ctx* c, int seed, int frame, int eye, uint8_t* d_out);

@@ -21,9 +21,15 @@
 
 #if defined(__CUDACC__)
 #define VO_HD __host__ __device__ __forceinline__
-#define VO_HDN __host__ __device__ __noinline__
+#define VO_HDN static __host__ __device__ __noinline__
 #define VO_HDM __host__ __device__ __forceinline__
+#ifdef VO_HELPERS_NOINLINE
+#define VO_HDF static __host__ __device__ __noinline__
 #else
+#define VO_HDF __host__ __device__ __forceinline__
+#endif
+#else
+#define VO_HDF static inline
 #define VO_HD static inline
 #define VO_HDN static
 #define VO_HDM inline
@@ -203,7 +209,7 @@ VO_HDN void jacobi_svd(double* At, int astep, double* _W, double* Vt, int vstep,
 // cv::SVD::compute(A) for a SQUARE N x N matrix A (row-major): w (N), u (N x N, columns
 // = left vectors), vt (N x N).  Mirrors _SVDcompute: temp_a = A^T, Jacobi on its rows.
 template <int N>
-VO_HD void svd_square(const double* A, double* w, double* u, double* vt) {
+VO_HDF void svd_square(const double* A, double* w, double* u, double* vt) {
   double at[N * N];
   for (int i = 0; i < N; i++)
     for (int j = 0; j < N; j++) at[i * N + j] = A[j * N + i];
@@ -215,7 +221,7 @@ VO_HD void svd_square(const double* A, double* w, double* u, double* vt) {
 
 // Same, but returns U^T (rows = left singular vectors) -- the CV_SVD_U_T form EPnP uses.
 template <int N>
-VO_HD void svd_square_ut(const double* A, double* w, double* ut, double* vt) {
+VO_HDF void svd_square_ut(const double* A, double* w, double* ut, double* vt) {
   for (int i = 0; i < N; i++)
     for (int j = 0; j < N; j++) ut[i * N + j] = A[j * N + i];
   jacobi_svd<N>(ut, N, w, vt, N, N, N, N);
@@ -223,7 +229,7 @@ VO_HD void svd_square_ut(const double* A, double* w, double* ut, double* vt) {
 
 // cv::solve(A (M x N, M >= N), b (M), x (N), DECOMP_SVD): Jacobi SVD of A^T's rows + SVBkSb.
 template <int M, int N>
-VO_HD void solve_svd(const double* A, const double* b, double* x) {
+VO_HDF void solve_svd(const double* A, const double* b, double* x) {
   double at[N * M], w[N], v[N * N];
   for (int i = 0; i < N; i++)
     for (int j = 0; j < M; j++) at[i * M + j] = A[j * N + i];
@@ -247,7 +253,7 @@ VO_HD void solve_svd(const double* A, const double* b, double* x) {
 }
 
 // cv::invert(A 3x3, DECOMP_SVD) = SVD::compute + SVD::backSubst(w, u, vt, Mat(), dst).
-VO_HD void invert3_svd(const double* A, double* inv) {
+VO_HDF void invert3_svd(const double* A, double* inv) {
   double w[3], u[9], vt[9];
   svd_square<3>(A, w, u, vt);
   double threshold = 0;
@@ -272,7 +278,7 @@ VO_HD void invert3_svd(const double* A, double* inv) {
 // FMA=true reproduces the AVX2/AVX-512 dispatch of OpenCV's matmul kernel, where the
 // compiler contracts `s += a*b`.
 template <int COLS, bool FMA>
-VO_HD void mul_transposed(const double* src, int rows, double* dst) {
+VO_HDF void mul_transposed(const double* src, int rows, double* dst) {
   for (int i = 0; i < COLS; i++) {
     for (int j = i; j < COLS; j++) {
       double s0 = 0;
@@ -291,7 +297,7 @@ VO_HD void mul_transposed(const double* src, int rows, double* dst) {
 
 // ---------------------------------------------------------------------------------------
 // cv::Rodrigues, both directions (smooth; ulp-level libm differences are harmless).
-VO_HD void rodrigues_vec2mat(const double r_[3], double R[9]) {
+VO_HDF void rodrigues_vec2mat(const double r_[3], double R[9]) {
   double rx = r_[0], ry = r_[1], rz = r_[2];
   double theta = sqrt(rx * rx + ry * ry + rz * rz);
   if (theta < DBL_EPSILON) {
@@ -308,7 +314,7 @@ VO_HD void rodrigues_vec2mat(const double r_[3], double R[9]) {
   R[6] = c1 * rx * rz - s * ry; R[7] = c1 * ry * rz + s * rx; R[8] = c + c1 * rz * rz;
 }
 
-VO_HD void rodrigues_mat2vec(const double Rin[9], double r[3]) {
+VO_HDF void rodrigues_mat2vec(const double Rin[9], double r[3]) {
   double w[3], u[9], vt[9], R[9];
   svd_square<3>(Rin, w, u, vt);
   for (int i = 0; i < 3; i++)
@@ -361,7 +367,7 @@ VO_HD double epnp_dist2(const double* p1, const double* p2) {
   return (p1[0] - p2[0]) * (p1[0] - p2[0]) + (p1[1] - p2[1]) * (p1[1] - p2[1]) + (p1[2] - p2[2]) * (p1[2] - p2[2]);
 }
 
-VO_HD void epnp_qr_solve_6x4(double* pA, double* pb, double* pX) {
+VO_HDF void epnp_qr_solve_6x4(double* pA, double* pb, double* pX) {
   const int nr = 6, nc = 4;
   double A1[6], A2[6];
   double* ppAkk = pA;
@@ -436,7 +442,7 @@ VO_HD void epnp_qr_solve_6x4(double* pA, double* pb, double* pX) {
   }
 }
 
-VO_HD void epnp_gauss_newton(const double* l_6x10, const double* rho, double betas[4]) {
+VO_HDF void epnp_gauss_newton(const double* l_6x10, const double* rho, double betas[4]) {
   for (int it = 0; it < 5; it++) {
     double a[24], b[6], x[4] = {0, 0, 0, 0};
     for (int i = 0; i < 6; i++) {
@@ -456,7 +462,7 @@ VO_HD void epnp_gauss_newton(const double* l_6x10, const double* rho, double bet
   }
 }
 
-VO_HD void epnp_estimate_R_and_t(EpnpWork& w, double R[3][3], double t[3]) {
+VO_HDF void epnp_estimate_R_and_t(EpnpWork& w, double R[3][3], double t[3]) {
   const int n = 5;
   double pc0[3] = {0, 0, 0}, pw0[3] = {0, 0, 0};
   for (int i = 0; i < n; i++)
@@ -497,7 +503,7 @@ VO_HD void epnp_estimate_R_and_t(EpnpWork& w, double R[3][3], double t[3]) {
   t[2] = pc0[2] - epnp_dot3(R[2], pw0);
 }
 
-VO_HD double epnp_compute_R_and_t(EpnpWork& w, const Intrinsics& K, const double* ut, const double* betas,
+VO_HDF double epnp_compute_R_and_t(EpnpWork& w, const Intrinsics& K, const double* ut, const double* betas,
                                   double R[3][3], double t[3]) {
   const int n = 5;
   // compute_ccs
@@ -541,7 +547,13 @@ VO_HD double epnp_compute_R_and_t(EpnpWork& w, const Intrinsics& K, const double
 
 // FMA_MTM: see mul_transposed.  Returns R (row-major) and t.
 template <bool FMA_MTM>
+#ifdef VO_NO_EPNP_DBG
 VO_HDN void epnp5(const float* obj /*15*/, const float* img /*10*/, const Intrinsics& K, double Rout[9], double tout[3]) {
+  double* dbg = nullptr;
+#else
+VO_HDN void epnp5(const float* obj /*15*/, const float* img /*10*/, const Intrinsics& K, double Rout[9], double tout[3],
+                  double* dbg = nullptr /*>= 420 doubles: intermediates for parity debugging*/) {
+#endif
   const int n = 5;
   EpnpWork w;
   // solvePnP: undistortPoints (float in, float out, zero distortion) then epnp::init_points
@@ -605,7 +617,17 @@ VO_HDN void epnp5(const float* obj /*15*/, const float* img /*10*/, const Intrin
       }
     }
     mul_transposed<12, FMA_MTM>(M, 2 * n, mtm);
+    if (dbg) {
+      for (int i = 0; i < 10; i++) dbg[i] = w.us[i];
+      for (int i = 0; i < 12; i++) dbg[10 + i] = w.cws[i / 3][i % 3];
+      for (int i = 0; i < 20; i++) dbg[22 + i] = w.alphas[i];
+      for (int i = 0; i < 144; i++) dbg[42 + i] = mtm[i];
+    }
     svd_square_ut<12>(mtm, d, ut, vt_unused);
+    if (dbg) {
+      for (int i = 0; i < 144; i++) dbg[186 + i] = ut[i];
+      for (int i = 0; i < 12; i++) dbg[330 + i] = d[i];
+    }
   }
   // compute_L_6x10, compute_rho
   double l_6x10[60], rho[6];
@@ -717,6 +739,13 @@ VO_HDN void epnp5(const float* obj /*15*/, const float* img /*10*/, const Intrin
   epnp_gauss_newton(l_6x10, rho, Betas[3]);
   rep_errors[3] = epnp_compute_R_and_t(w, K, ut, Betas[3], Rs[3], ts[3]);
 
+  if (dbg) {
+    for (int i = 0; i < 60; i++) dbg[342 + i] = l_6x10[i];
+    for (int i = 0; i < 6; i++) dbg[402 + i] = rho[i];
+    for (int i = 0; i < 3; i++) dbg[408 + i] = rep_errors[1 + i];
+    for (int i = 0; i < 4; i++) dbg[411 + i] = Betas[1][i];
+    for (int i = 0; i < 4; i++) dbg[415 + i] = Betas[2][i];
+  }
   int N = 1;
   if (rep_errors[2] < rep_errors[1]) N = 2;
   if (rep_errors[3] < rep_errors[N]) N = 3;

@@ -221,7 +221,6 @@ int lk_launch(vo_ctx* c, int slot_prev, int slot_next, const float2* d_prev, int
   int max_iters = c->p.lk_max_iters < 0 ? 0 : (c->p.lk_max_iters > 100 ? 100 : c->p.lk_max_iters);
   double eps = c->p.lk_eps < 0 ? 0 : (c->p.lk_eps > 10 ? 10 : c->p.lk_eps);
   eps *= eps;
-  VO_CUDA(cudaMemsetAsync(c->d_lk_work, 0, 2 * sizeof(unsigned long long), c->stream));
   const int threads = 128;
   const int blocks = div_up(n * 32, threads);
   {

@@ -76,6 +76,25 @@ pnp_solve_kernel(const float3* __restrict__ xyz, const float2* __restrict__ xy, 
   counts[s] = 0;
 }
 
+// debug: one EPnP on the device with intermediates (parity investigations only)
+__global__ void epnp_debug_kernel(const float* obj, const float* img, Intrinsics K, double* dbg) {
+  double R[9], t[3];
+#ifdef VO_NO_EPNP_DBG
+  epnp5<false>(obj, img, K, R, t);
+#else
+  epnp5<false>(obj, img, K, R, t, dbg);
+#endif
+  for (int i = 0; i < 9; i++) dbg[420 + i] = R[i];
+  for (int i = 0; i < 3; i++) dbg[429 + i] = t[i];
+}
+
+int epnp_debug_launch(vo_ctx* c, const float* d_obj, const float* d_img, double* d_dbg) {
+  Intrinsics K{c->p.fx, c->p.fy, c->p.cx, c->p.cy};
+  epnp_debug_kernel<<<1, 1, 0, c->stream>>>(d_obj, d_img, K, d_dbg);
+  VO_CUDA(cudaGetLastError());
+  return VO_OK;
+}
+
 // ================================================================ scoring
 __device__ __forceinline__ float fmat_err(const double* F, float2 p1, float2 p2) {
   const double x1 = p1.x, y1 = p1.y, x2 = p2.x, y2 = p2.y;

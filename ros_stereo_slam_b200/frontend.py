@@ -288,8 +288,17 @@ class VisualFrontEnd:
     def sync(self):
         check(self.lib.vo_sync(self.h))
 
-    def profile_enable(self, on=True):
-        check(self.lib.vo_profile_enable(self.h, int(on)))
+    def profile_enable(self, kinds="all"):
+        """kinds: "all", None/False (off) or an iterable of names from _lib.KERNELS."""
+        if kinds in (None, False, 0):
+            mask = 0
+        elif kinds == "all" or kinds is True:
+            mask = -1
+        else:
+            mask = 0
+            for k in kinds:
+                mask |= 1 << _lib.KERNELS.index(k)
+        check(self.lib.vo_profile_enable(self.h, C.c_int(mask)))
 
     def profile_read(self, reset=False):
         out = {}

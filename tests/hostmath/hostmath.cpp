@@ -34,6 +34,13 @@ void hm_triangulate(const double* P1, const double* P2, const float* xy1, const 
   for (int i = 0; i < n; i++)
     triangulate_dlt(P1, P2, xy1[2 * i], xy1[2 * i + 1], xy2[2 * i], xy2[2 * i + 1], xyz + 3 * i, h4 ? h4 + 4 * i : nullptr);
 }
+void hm_epnp5_dbg(const float* obj, const float* img, const double* K4, double* dbg) {
+  Intrinsics K{K4[0], K4[1], K4[2], K4[3]};
+  double R[9], t[3];
+  epnp5<false>(obj, img, K, R, t, dbg);
+  for (int i = 0; i < 9; i++) dbg[420 + i] = R[i];
+  for (int i = 0; i < 3; i++) dbg[429 + i] = t[i];
+}
 int hm_fmat7(const float* m1, const float* m2, double* F) { return fmat_7point(m1, m2, F); }
 int hm_solve_cubic(const double* c, double* r) { return solve_cubic(c, r); }
 }
