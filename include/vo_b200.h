@@ -81,9 +81,11 @@ typedef struct vo_params {
   double pnp_retry_conf;      /* 0.98 */
   int pnp_min_inliers;        /* 10   (src/keyFrameManagement.cpp:85,89) */
   int kf_min_inliers;         /* 200  keyframe rule (src/VisualSLAM.cpp:120), used by vo_seq_* only */
-  int ransac_exhaustive;      /* 0: score only the hypotheses OpenCV's adaptive stop would reach.
-                                 1: solve and score all `iters` hypotheses (the BASELINE workload);
-                                 results are identical either way (early-exit semantics kept). */
+  int ransac_exhaustive;      /* PnP-RANSAC. 0: solve/score only the hypotheses OpenCV's adaptive stop would
+                                 reach.  1: solve and score all `iters` hypotheses (the BASELINE workload,
+                                 "1024 hypotheses per frame"); results are identical either way because the
+                                 acceptance replay keeps the early-exit semantics. */
+  int f_exhaustive;           /* same switch for the F-matrix RANSAC (f_max_iters samples); default 0 */
   int max_points;             /* capacity: keypoints per call (default 131072) */
   int max_hypotheses;         /* capacity: RANSAC samples per call (default 4096) */
   int device;                 /* CUDA device ordinal */

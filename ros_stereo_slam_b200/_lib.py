@@ -39,7 +39,7 @@ class VoParams(C.Structure):
         ("f_max_iters", C.c_int),
         ("pnp_iters", C.c_int), ("pnp_thr", C.c_double), ("pnp_conf", C.c_double),
         ("pnp_retry_iters", C.c_int), ("pnp_retry_thr", C.c_double), ("pnp_retry_conf", C.c_double),
-        ("pnp_min_inliers", C.c_int), ("kf_min_inliers", C.c_int), ("ransac_exhaustive", C.c_int),
+        ("pnp_min_inliers", C.c_int), ("kf_min_inliers", C.c_int), ("ransac_exhaustive", C.c_int), ("f_exhaustive", C.c_int),
         ("max_points", C.c_int), ("max_hypotheses", C.c_int), ("device", C.c_int),
     ]
 

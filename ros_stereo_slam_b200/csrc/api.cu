@@ -113,6 +113,7 @@ void vo_default_params(vo_params* p) {
   p->pnp_min_inliers = 10;
   p->kf_min_inliers = 200;
   p->ransac_exhaustive = 0;
+  p->f_exhaustive = 0;
   p->max_points = 131072;
   p->max_hypotheses = 4096;
   p->device = 0;
@@ -177,6 +178,8 @@ int vo_create(const vo_params* p, vo_ctx** out) {
   VO_CUDA(cudaMalloc(&c->d_seq_xyz, cap * sizeof(float3)));
   VO_CUDA(cudaMalloc(&c->d_count, 16 * sizeof(int)));
   VO_CUDA(cudaMallocHost(&c->h_count, 16 * sizeof(int)));
+  VO_CUDA(cudaMalloc(&c->d_tile_state, 256 * sizeof(unsigned long long)));
+  VO_CUDA(cudaMemsetAsync(c->d_tile_state, 0, 256 * sizeof(unsigned long long), c->stream));
   VO_CUDA(cudaMallocHost(&c->h_pts, (size_t)cap * 8 * sizeof(float)));
   const int ch = p->max_hypotheses;
   c->cap_h = ch;
@@ -223,7 +226,7 @@ int vo_destroy(vo_ctx* c) {
   }
   void* dev[] = {c->d_xy_in, c->d_xy_trk, c->d_status, c->d_err, c->d_xyz_in, c->d_c_ref, c->d_c_trk, c->d_c_xyz,
                  c->d_f_ref, c->d_f_trk, c->d_f_xyz, c->d_xyz_tmp, c->d_mask, c->d_idx, c->d_seq_xy, c->d_seq_xyz,
-                 c->d_count, c->d_samples, c->d_models, c->d_counts, c->d_sel, c->d_pose, c->d_cam, c->d_lk_work};
+                 c->d_count, c->d_tile_state, c->d_samples, c->d_models, c->d_counts, c->d_sel, c->d_pose, c->d_cam, c->d_lk_work};
   for (void* p : dev) cudaFree(p);
   void* host[] = {c->h_count, c->h_pts, c->h_samples, c->h_sel, c->h_pose, c->h_lk_work};
   for (void* p : host) cudaFreeHost(p);
@@ -326,7 +329,7 @@ static int run_fmat(vo_ctx* c, const float2* m1, const float2* m2, int n, double
   const float thr2 = (float)(thr * thr);
   CvRng rng(0xffffffffffffffffULL);
   int done = 0;
-  int target = (c->p.ransac_exhaustive || replay) ? H : std::min(H, 48);
+  int target = (c->p.f_exhaustive || replay) ? H : std::min(H, 48);
   for (;;) {
     int k = target - done;
     if (k > 0) {

@@ -88,6 +88,8 @@ struct vo_ctx {
   int32_t* d_idx = nullptr;                              // inlier indices
   int* d_count = nullptr;                                // small int scratch (16 ints)
   int* h_count = nullptr;                                // pinned mirror
+  unsigned long long* d_tile_state = nullptr;            // compaction look-back (epoch<<32 | tile total)
+  unsigned compact_epoch = 0;
 
   // sequence state (vo_seq_*): reference set resident in HBM
   float2* d_seq_xy = nullptr;

@@ -70,20 +70,31 @@ struct CvRng {
 // u_i.  Vt: n x n (stride vstep), W: n singular values, descending.  Rows n..n1-1 of At
 // (zero singular values when n1 > n, or exactly-zero ones) are completed with OpenCV's
 // deterministic pseudo-random Gram-Schmidt vectors (RNG 0x12345678).
-template <int MAXN>
-VO_HDN void jacobi_svd(double* At, int astep, double* _W, double* Vt, int vstep, int m, int n, int n1) {
-  double W[MAXN];
+// Compile-time shapes (M = row length, N = rows, N1 = rows to complete) let the compiler
+// unroll the length-M inner loops and keep a row pair in registers across dot product,
+// rotation and norm update; the arithmetic and its order are unchanged.
+// WITH_V=false skips the accumulation of V (its rotations never feed back into At/W, so U
+// and W are bit-identical); callers that only consume U^T (EPnP's 12x12 and 3x3 PCA) use it
+// and pass any non-null pointer as Vt (OpenCV's code keys the row normalisation on Vt != 0).
+template <int M, int N, int N1, bool WITH_V = true>
+VO_HDN void jacobi_svd(double* At, double* _W, double* Vt) {
+  constexpr int astep = M, vstep = N, m = M, n = N, n1 = N1;
+  double W[N];
   const double minval = DBL_MIN, eps = DBL_EPSILON * 10;
-  int i, j, k, iter, max_iter = m > 30 ? m : 30;
+  int i, j, k, iter;
+  constexpr int max_iter = m > 30 ? m : 30;
   double c, s, sd;
 
   for (i = 0; i < n; i++) {
-    for (k = 0, sd = 0; k < m; k++) {
+    sd = 0;
+#pragma unroll
+    for (k = 0; k < m; k++) {
       double t = At[i * astep + k];
       sd += t * t;
     }
     W[i] = sd;
-    if (Vt) {
+    if (WITH_V && Vt) {
+#pragma unroll
       for (k = 0; k < n; k++) Vt[i * vstep + k] = 0;
       Vt[i * vstep + i] = 1;
     }
@@ -95,7 +106,14 @@ VO_HDN void jacobi_svd(double* At, int astep, double* _W, double* Vt, int vstep,
       for (j = i + 1; j < n; j++) {
         double *Ai = At + i * astep, *Aj = At + j * astep;
         double a = W[i], p = 0, b = W[j];
-        for (k = 0; k < m; k++) p += Ai[k] * Aj[k];
+        double ri[M], rj[M];
+#pragma unroll
+        for (k = 0; k < m; k++) {
+          ri[k] = Ai[k];
+          rj[k] = Aj[k];
+        }
+#pragma unroll
+        for (k = 0; k < m; k++) p += ri[k] * rj[k];
         if (fabs(p) <= eps * sqrt(a * b)) continue;
 
         p *= 2;
@@ -110,9 +128,10 @@ VO_HDN void jacobi_svd(double* At, int astep, double* _W, double* Vt, int vstep,
         }
 
         a = b = 0;
+#pragma unroll
         for (k = 0; k < m; k++) {
-          double t0 = c * Ai[k] + s * Aj[k];
-          double t1 = -s * Ai[k] + c * Aj[k];
+          double t0 = c * ri[k] + s * rj[k];
+          double t1 = -s * ri[k] + c * rj[k];
           Ai[k] = t0;
           Aj[k] = t1;
           a += t0 * t0;
@@ -122,8 +141,9 @@ VO_HDN void jacobi_svd(double* At, int astep, double* _W, double* Vt, int vstep,
         W[j] = b;
         changed = true;
 
-        if (Vt) {
+        if (WITH_V && Vt) {
           double *Vi = Vt + i * vstep, *Vj = Vt + j * vstep;
+#pragma unroll
           for (k = 0; k < n; k++) {
             double t0 = c * Vi[k] + s * Vj[k];
             double t1 = -s * Vi[k] + c * Vj[k];
@@ -136,7 +156,9 @@ VO_HDN void jacobi_svd(double* At, int astep, double* _W, double* Vt, int vstep,
   }
 
   for (i = 0; i < n; i++) {
-    for (k = 0, sd = 0; k < m; k++) {
+    sd = 0;
+#pragma unroll
+    for (k = 0; k < m; k++) {
       double t = At[i * astep + k];
       sd += t * t;
     }
@@ -157,11 +179,12 @@ VO_HDN void jacobi_svd(double* At, int astep, double* _W, double* Vt, int vstep,
           At[i * astep + k] = At[j * astep + k];
           At[j * astep + k] = t;
         }
-        for (k = 0; k < n; k++) {
-          t = Vt[i * vstep + k];
-          Vt[i * vstep + k] = Vt[j * vstep + k];
-          Vt[j * vstep + k] = t;
-        }
+        if (WITH_V)
+          for (k = 0; k < n; k++) {
+            t = Vt[i * vstep + k];
+            Vt[i * vstep + k] = Vt[j * vstep + k];
+            Vt[j * vstep + k] = t;
+          }
       }
     }
   }
@@ -213,7 +236,7 @@ VO_HDF void svd_square(const double* A, double* w, double* u, double* vt) {
   double at[N * N];
   for (int i = 0; i < N; i++)
     for (int j = 0; j < N; j++) at[i * N + j] = A[j * N + i];
-  jacobi_svd<N>(at, N, w, vt, N, N, N, N);
+  jacobi_svd<N, N, N>(at, w, vt);
   if (u)
     for (int i = 0; i < N; i++)
       for (int j = 0; j < N; j++) u[i * N + j] = at[j * N + i];
@@ -224,7 +247,16 @@ template <int N>
 VO_HDF void svd_square_ut(const double* A, double* w, double* ut, double* vt) {
   for (int i = 0; i < N; i++)
     for (int j = 0; j < N; j++) ut[i * N + j] = A[j * N + i];
-  jacobi_svd<N>(ut, N, w, vt, N, N, N, N);
+  jacobi_svd<N, N, N>(ut, w, vt);
+}
+
+// U^T and W only (V not accumulated; `ut` doubles as the non-null marker OpenCV's code needs
+// to run its normalisation / zero-singular-value completion of the rows).
+template <int N>
+VO_HDF void svd_square_ut_only(const double* A, double* w, double* ut) {
+  for (int i = 0; i < N; i++)
+    for (int j = 0; j < N; j++) ut[i * N + j] = A[j * N + i];
+  jacobi_svd<N, N, N, false>(ut, w, ut);
 }
 
 // cv::solve(A (M x N, M >= N), b (M), x (N), DECOMP_SVD): Jacobi SVD of A^T's rows + SVBkSb.
@@ -233,7 +265,7 @@ VO_HDF void solve_svd(const double* A, const double* b, double* x) {
   double at[N * M], w[N], v[N * N];
   for (int i = 0; i < N; i++)
     for (int j = 0; j < M; j++) at[i * M + j] = A[j * N + i];
-  jacobi_svd<N>(at, M, w, v, N, M, N, N);
+  jacobi_svd<M, N, N>(at, w, v);
   // SVBkSbImpl_ with nb == 1, u = at (uT), v (vT), eps = 2*DBL_EPSILON
   double threshold = 0;
   for (int i = 0; i < N; i++) {
@@ -573,11 +605,11 @@ VO_HDN void epnp5(const float* obj /*15*/, const float* img /*10*/, const Intrin
     for (int j = 0; j < 3; j++) w.cws[0][j] += w.pws[3 * i + j];
   for (int j = 0; j < 3; j++) w.cws[0][j] /= n;
   {
-    double pw0[15], pw0tpw0[9], dc[3], uct[9], vt_unused[9];
+    double pw0[15], pw0tpw0[9], dc[3], uct[9];
     for (int i = 0; i < n; i++)
       for (int j = 0; j < 3; j++) pw0[3 * i + j] = w.pws[3 * i + j] - w.cws[0][j];
     mul_transposed<3, FMA_MTM>(pw0, n, pw0tpw0);
-    svd_square_ut<3>(pw0tpw0, dc, uct, vt_unused);
+    svd_square_ut_only<3>(pw0tpw0, dc, uct);
     for (int i = 1; i < 4; i++) {
       double k = sqrt(dc[i - 1] / n);
       for (int j = 0; j < 3; j++) w.cws[i][j] = w.cws[0][j] + k * uct[3 * (i - 1) + j];
@@ -601,7 +633,7 @@ VO_HDN void epnp5(const float* obj /*15*/, const float* img /*10*/, const Intrin
   // M (10 x 12), MtM, SVD
   double ut[144];
   {
-    double M[120], mtm[144], d[12], vt_unused[144];
+    double M[120], mtm[144], d[12];
     for (int i = 0; i < n; i++) {
       const double* as = &w.alphas[4 * i];
       double u = w.us[2 * i], v = w.us[2 * i + 1];
@@ -623,7 +655,7 @@ VO_HDN void epnp5(const float* obj /*15*/, const float* img /*10*/, const Intrin
       for (int i = 0; i < 20; i++) dbg[22 + i] = w.alphas[i];
       for (int i = 0; i < 144; i++) dbg[42 + i] = mtm[i];
     }
-    svd_square_ut<12>(mtm, d, ut, vt_unused);
+    svd_square_ut_only<12>(mtm, d, ut);
     if (dbg) {
       for (int i = 0; i < 144; i++) dbg[186 + i] = ut[i];
       for (int i = 0; i < 12; i++) dbg[330 + i] = d[i];

@@ -136,7 +136,7 @@ VO_HDN int fmat_7point(const float* m1 /*14*/, const float* m2 /*14*/, double* f
     double vv[7 * 7];
     for (i = 0; i < 63; i++) v[i] = a[i];
     for (i = 63; i < 81; i++) v[i] = 0;
-    jacobi_svd<7>(v, 9, w, vv, 7, 9, 7, 9);
+    jacobi_svd<9, 7, 9>(v, w, vv);
   }
   f1 = v + 7 * 9;
   f2 = v + 8 * 9;

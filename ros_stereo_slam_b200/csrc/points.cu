@@ -39,47 +39,78 @@ int grid_launch(vo_ctx* c, int rows, int cols, int step, float2* d_xy, int* n_ou
 }
 
 // ---------------------------------------------------------------------------- compaction
-// Single CTA, 1024 threads: each thread owns a contiguous chunk (order preserving), block
-// exclusive scan of the chunk counts, then the ordered scatter.  N <= 131072 -> <= 128
-// flags per thread; the arrays are L2-resident (<= 1.5 MB) so this is latency-, not
-// bandwidth-bound.
-constexpr int COMPACT_THREADS = 1024;
+// Order-preserving stream compaction of up to three parallel arrays (+ the index list), single
+// pass with decoupled look-back: every CTA owns a tile of CP_TILE flags (8 per thread, one
+// 64-bit load), scans it, publishes its tile total tagged with the launch epoch, and sums the
+// totals of the lower-indexed tiles (at most 64 tiles, all co-resident, so the wait is short
+// and cannot deadlock).  The arrays are L2-resident (<= 1.5 MB): latency-, not bandwidth-bound.
+constexpr int CP_THREADS = 256;
+constexpr int CP_ITEMS = 8;
+constexpr int CP_TILE = CP_THREADS * CP_ITEMS;
 
-__global__ void __launch_bounds__(COMPACT_THREADS)
+__global__ void __launch_bounds__(CP_THREADS)
 compact_kernel(const uint8_t* __restrict__ flags, int n, const float2* __restrict__ a_in, float2* __restrict__ a_out,
                const float2* __restrict__ b_in, float2* __restrict__ b_out, const float3* __restrict__ c_in,
-               float3* __restrict__ c_out, int32_t* __restrict__ idx_out, int* __restrict__ count_out) {
-  __shared__ int warp_tot[32];
-  const int t = threadIdx.x;
-  const int chunk = (n + COMPACT_THREADS - 1) / COMPACT_THREADS;
-  const int beg = t * chunk;
-  const int end = min(beg + chunk, n);
+               float3* __restrict__ c_out, int32_t* __restrict__ idx_out, int* __restrict__ count_out,
+               volatile unsigned long long* tile_state, unsigned epoch) {
+  __shared__ int warp_tot[CP_THREADS / 32];
+  __shared__ int s_base;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const int beg = blockIdx.x * CP_TILE + t * CP_ITEMS;
+  unsigned long long bits = 0;  // byte k = flag of element beg+k
+  if (beg + CP_ITEMS <= n) {
+    bits = *reinterpret_cast<const unsigned long long*>(flags + beg);
+  } else {
+    for (int k = 0; k < CP_ITEMS; k++)
+      if (beg + k < n) bits |= (unsigned long long)flags[beg + k] << (8 * k);
+  }
   int cnt = 0;
-  for (int i = beg; i < end; i++) cnt += (flags[i] == 1);
-  // block exclusive scan
+#pragma unroll
+  for (int k = 0; k < CP_ITEMS; k++) cnt += ((bits >> (8 * k)) & 0xff) == 1;
   int incl = cnt;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
-    int v = __shfl_up_sync(0xffffffffu, incl, d);
-    if ((t & 31) >= d) incl += v;
+    const int v = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += v;
   }
-  if ((t & 31) == 31) warp_tot[t >> 5] = incl;
+  if (lane == 31) warp_tot[w] = incl;
   __syncthreads();
-  if (t < 32) {
-    int w = warp_tot[t];
-    int wi = w;
+  if (w == 0) {
+    // exclusive scan of the 8 warp totals, publish the tile total, look back
+    int wt = lane < CP_THREADS / 32 ? warp_tot[lane] : 0;
+    int wi = wt;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      int v = __shfl_up_sync(0xffffffffu, wi, d);
-      if (t >= d) wi += v;
+    for (int d = 1; d < 8; d <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, wi, d);
+      if (lane >= d) wi += v;
     }
-    warp_tot[t] = wi - w;  // exclusive
-    if (t == 31) *count_out = wi;
+    const int tile_total = __shfl_sync(0xffffffffu, wi, CP_THREADS / 32 - 1);
+    if (lane < CP_THREADS / 32) warp_tot[lane] = wi - wt;
+    if (lane == 0) {
+      tile_state[blockIdx.x] = ((unsigned long long)epoch << 32) | (unsigned)tile_total;
+      __threadfence();
+    }
+    int base = 0;
+    for (int j = lane; j < (int)blockIdx.x; j += 32) {
+      unsigned long long v;
+      do {
+        v = tile_state[j];
+      } while ((unsigned)(v >> 32) != epoch);
+      base += (int)(unsigned)v;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) base += __shfl_xor_sync(0xffffffffu, base, d);
+    if (lane == 0) {
+      s_base = base;
+      if (blockIdx.x == gridDim.x - 1) *count_out = base + tile_total;
+    }
   }
   __syncthreads();
-  int pos = warp_tot[t >> 5] + incl - cnt;
-  for (int i = beg; i < end; i++) {
-    if (flags[i] == 1) {
+  int pos = s_base + warp_tot[w] + incl - cnt;
+#pragma unroll
+  for (int k = 0; k < CP_ITEMS; k++) {
+    if (((bits >> (8 * k)) & 0xff) == 1) {
+      const int i = beg + k;
       if (a_in) a_out[pos] = a_in[i];
       if (b_in) b_out[pos] = b_in[i];
       if (c_in) c_out[pos] = c_in[i];
@@ -97,8 +128,9 @@ int compact_launch(vo_ctx* c, const uint8_t* d_flags, int n, const float2* a_in,
   }
   {
     LaunchScope ls(c, VO_K_COMPACT);
-    compact_kernel<<<1, COMPACT_THREADS, 0, c->stream>>>(d_flags, n, a_in, a_out, b_in, b_out, c_in, c_out, idx_out,
-                                                         c->d_count + count_slot);
+    compact_kernel<<<div_up(n, CP_TILE), CP_THREADS, 0, c->stream>>>(d_flags, n, a_in, a_out, b_in, b_out, c_in, c_out,
+                                                                     idx_out, c->d_count + count_slot, c->d_tile_state,
+                                                                     ++c->compact_epoch);
   }
   VO_CUDA(cudaGetLastError());
   return VO_OK;

@@ -10,6 +10,8 @@
 //
 // All geometry is FP64 in OpenCV's operation order (cvmath.cuh / fmat7.cuh, --fmad=false);
 // the residual is rounded to float and compared with (float)(thr*thr) like OpenCV does.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "cvmath.cuh"
 #include "fmat7.cuh"
@@ -20,12 +22,24 @@ constexpr int PNP_STRIDE = 16;  // doubles per PnP model: rvec(3) tvec(3) R(9) p
 constexpr int F_STRIDE = 9;     // doubles per F model (3 per sample)
 
 // ================================================================ hypothesis generation
-// One thread per minimal sample; one-thread warps would waste lanes, so samples are packed
-// SOLVE_TPB per CTA: the solvers are long dependent FP64 chains (Jacobi sweeps), i.e.
-// latency-bound, and small CTAs spread them over all SMs.
-constexpr int SOLVE_TPB = 8;
+// One thread per minimal sample, SOLVE_TPB samples per CTA (one partially filled warp).  The
+// solvers are long dependent FP64 chains (Jacobi sweeps) over ~5 KB of per-thread local
+// arrays, i.e. latency-bound: small CTAs spread them over all SMs.  Measured on B200: one
+// sample per warp (lane 0 only) is 3x SLOWER than 8 per warp, because local memory is
+// lane-interleaved and a lone lane uses 4 of every 32-byte sector, so the stacks of the
+// co-resident warps no longer fit L1.
+constexpr int SOLVE_TPB_MAX = 32;
+static int solve_tpb() {
+  static int v = 0;
+  if (!v) {
+    const char* e = getenv("VO_SOLVE_TPB");
+    v = e ? atoi(e) : 8;
+    if (v < 1 || v > SOLVE_TPB_MAX) v = 8;
+  }
+  return v;
+}
 
-__global__ void __launch_bounds__(SOLVE_TPB)
+__global__ void __launch_bounds__(SOLVE_TPB_MAX)
 fmat_solve_kernel(const float2* __restrict__ m1, const float2* __restrict__ m2, const int32_t* __restrict__ samples,
                   int h, double* __restrict__ models, int32_t* __restrict__ counts) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -48,7 +62,7 @@ fmat_solve_kernel(const float2* __restrict__ m1, const float2* __restrict__ m2, 
   }
 }
 
-__global__ void __launch_bounds__(SOLVE_TPB)
+__global__ void __launch_bounds__(SOLVE_TPB_MAX)
 pnp_solve_kernel(const float3* __restrict__ xyz, const float2* __restrict__ xy, const int32_t* __restrict__ samples,
                  int h, Intrinsics K, double* __restrict__ models, int32_t* __restrict__ counts) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -337,7 +351,7 @@ int fmat_solve_launch(vo_ctx* c, const float2* m1, const float2* m2, const int32
   if (h <= 0) return VO_OK;
   {
     LaunchScope ls(c, VO_K_FMAT_SOLVE);
-    fmat_solve_kernel<<<div_up(h, SOLVE_TPB), SOLVE_TPB, 0, c->stream>>>(m1, m2, d_samples, h, d_models, d_counts);
+    fmat_solve_kernel<<<div_up(h, solve_tpb()), solve_tpb(), 0, c->stream>>>(m1, m2, d_samples, h, d_models, d_counts);
   }
   VO_CUDA(cudaGetLastError());
   return VO_OK;
@@ -371,7 +385,7 @@ int pnp_solve_launch(vo_ctx* c, const float3* xyz, const float2* xy, const int32
   if (h <= 0) return VO_OK;
   {
     LaunchScope ls(c, VO_K_PNP_SOLVE);
-    pnp_solve_kernel<<<div_up(h, SOLVE_TPB), SOLVE_TPB, 0, c->stream>>>(xyz, xy, d_samples, h, intr(c), d_models,
+    pnp_solve_kernel<<<div_up(h, solve_tpb()), solve_tpb(), 0, c->stream>>>(xyz, xy, d_samples, h, intr(c), d_models,
                                                                        d_counts);
   }
   VO_CUDA(cudaGetLastError());
