@@ -12,16 +12,27 @@
 // once; OpenCV accumulates them in float SIMD lanes, which is the only source of
 // difference (~1e-5 px typical).  oracle/lk.py is the bit-exact twin.
 //
-// Mapping: lane l owns window pixels k = l, l+32, ... (<441), i.e. 14 per lane; I-patch,
-// Ix, Iy stay in registers across iterations; J is read through the read-only path from
-// the padded level (no bounds logic, see common.cuh).
+// Mapping: the 21x21 window is cut into 63 horizontal segments of 7 pixels; lane l owns
+// segments l and l+32 (14 pixels, lane 31 has 7).  I / Ix / Iy patches stay in registers
+// across iterations.  Every bilinear sample is two DP2A instructions (signed 16-bit weight pair
+// x unsigned 8-bit pixel pair) with the rounding constant folded into the accumulator.
+//
+// Memory path (what ncu said about the first two versions: l1tex 73 % then 92 % busy, issue only
+// 37-66 %): a warp-wide load whose lanes sit in 11 different image rows costs 11+ L1 wavefronts,
+// whatever its width.  So the 22x22-byte source patch is first STAGED into a warp-private
+// shared-memory tile with row-coalesced loads (lane -> (row = 4i + lane/8, word = lane%8): 6
+// loads of 4 rows each, ~30 wavefronts instead of ~130), then every lane reads its segments from
+// shared memory (3 words per row, realigned with a funnel shift).  The derivative patch
+// (22x22 short2) is staged the same way once per level.  Levels live padded in HBM/L2
+// (common.cuh), so none of this carries bounds logic.
 #include "common.cuh"
 
 namespace vo {
 
 constexpr int WIN = LK_WIN;
-constexpr int NPIX = WIN * WIN;            // 441
-constexpr int PER_LANE = (NPIX + 31) / 32;  // 14
+constexpr int SEG = 7;                      // pixels per segment
+constexpr int SEGS_PER_ROW = WIN / SEG;     // 3
+constexpr int NSEG = WIN * SEGS_PER_ROW;    // 63
 constexpr int W_BITS = 14;
 
 __device__ __forceinline__ long long warp_sum_exact(int v) {
@@ -33,32 +44,90 @@ __device__ __forceinline__ long long warp_sum_exact(int v) {
   return (long long)shi * 4096 + (long long)slo;
 }
 
-__device__ __forceinline__ void lk_weights(float a, float b, int& iw00, int& iw01, int& iw10, int& iw11) {
+__device__ __forceinline__ void lk_weights(float a, float b, unsigned& wt, unsigned& wb, int& iw00, int& iw01,
+                                           int& iw10, int& iw11) {
   const float s = (float)(1 << W_BITS);
   const float oma = __fsub_rn(1.f, a), omb = __fsub_rn(1.f, b);
   iw00 = __float2int_rn(__fmul_rn(__fmul_rn(oma, omb), s));
   iw01 = __float2int_rn(__fmul_rn(__fmul_rn(a, omb), s));
   iw10 = __float2int_rn(__fmul_rn(__fmul_rn(oma, b), s));
   iw11 = (1 << W_BITS) - iw00 - iw01 - iw10;
+  wt = ((unsigned)iw00 & 0xffffu) | ((unsigned)iw01 << 16);   // weights are in [-1, 2^14]: two s16 per register
+  wb = ((unsigned)iw10 & 0xffffu) | ((unsigned)iw11 << 16);
+}
+
+// d = c + a.s16[0]*b.u8[0] + a.s16[1]*b.u8[1]  (signed 16-bit weights: iw11 = 2^14 - the other
+// three can be -1; unsigned 8-bit pixels).  Plain (non-volatile) asm so that ptxas may schedule it.
+__device__ __forceinline__ int dp2a_w(unsigned w, unsigned px, int c) {
+  int d;
+  asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(px), "r"(c));
+  return d;
+}
+
+constexpr int PROWS = WIN + 1;   // 22 source rows
+constexpr int PS = 9;            // tile row stride in 32-bit words (7 used)
+constexpr int DS = 23;           // derivative tile row stride in short2 (22 used)
+constexpr int TILE_WORDS = PROWS * PS;          // 198
+constexpr int DTILE_WORDS = PROWS * DS;         // 506
+constexpr int WARP_SMEM_WORDS = TILE_WORDS + DTILE_WORDS;
+constexpr int LK_WARPS = 4;
+
+// Stage the 22 x 28-byte patch whose (unaligned) origin is `a0` into `tile`; returns the byte
+// offset (0..3) of the origin inside the first staged word.
+__device__ __forceinline__ unsigned stage_patch(const uint8_t* a0, int pitch, unsigned* tile, int lane) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(a0);
+  const unsigned* w = reinterpret_cast<const unsigned*>(a & ~uintptr_t(3));
+  const int wcol = lane & 7, r0 = lane >> 3, pw = pitch >> 2;
+  __syncwarp();   // everyone is done reading the previous tile
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    const int r = 4 * i + r0;
+    if (r < PROWS && wcol < 7) tile[r * PS + wcol] = __ldg(w + (size_t)r * pw + wcol);
+  }
+  __syncwarp();
+  return (unsigned)(a & 3);
+}
+
+// bilinear samples (x = 0..6) of the segment at (row, byte offset bo) of a staged tile
+__device__ __forceinline__ void seg_bilinear(const unsigned* tile, int row, unsigned bo, unsigned wt, unsigned wb,
+                                             int out[SEG]) {
+  const unsigned* p = tile + row * PS + (bo >> 2);
+  const unsigned sh = (bo & 3) * 8;
+  const unsigned t0 = __funnelshift_r(p[0], p[1], sh), t1 = __funnelshift_r(p[1], p[2], sh);
+  const unsigned b0 = __funnelshift_r(p[PS], p[PS + 1], sh), b1 = __funnelshift_r(p[PS + 1], p[PS + 2], sh);
+  const unsigned tp[SEG] = {t0, t0 >> 8, t0 >> 16, __funnelshift_r(t0, t1, 24), t1, t1 >> 8, t1 >> 16};
+  const unsigned bp[SEG] = {b0, b0 >> 8, b0 >> 16, __funnelshift_r(b0, b1, 24), b1, b1 >> 8, b1 >> 16};
+#pragma unroll
+  for (int x = 0; x < SEG; x++)
+    out[x] = dp2a_w(wb, bp[x], dp2a_w(wt, tp[x], 1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
 }
 
 __global__ void __launch_bounds__(128)
 lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n, float2* __restrict__ next_pts,
           uint8_t* __restrict__ status, float* __restrict__ err, int max_iters, double eps_sq, float min_eig_thr,
           unsigned long long* __restrict__ work) {
+  __shared__ unsigned smem[LK_WARPS * WARP_SMEM_WORDS];
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= n) return;
+  unsigned* tile = smem + (threadIdx.x >> 5) * WARP_SMEM_WORDS;
+  unsigned* dtile = tile + TILE_WORDS;
   const float2 pt = prev_pts[warp];
   const float half_win = (WIN - 1) * 0.5f;
   const float FLT_SCALE = 1.f / (1 << 20);
+
+  // this lane's two segments (fixed for the whole kernel)
+  const int rowA = lane / SEGS_PER_ROW, colA = (lane - rowA * SEGS_PER_ROW) * SEG;
+  const int sB = lane + 32;
+  const bool hasB = sB < NSEG;
+  const int rowB = hasB ? sB / SEGS_PER_ROW : 0, colB = hasB ? (sB - rowB * SEGS_PER_ROW) * SEG : 0;
 
   float outx = 0.f, outy = 0.f;  // nextPts[ptidx] as OpenCV keeps it between levels
   bool st = true;
   float errv = 0.f;
   unsigned int n_levels_done = 0, n_iters_done = 0;
 
-  int Iw[PER_LANE], Ix[PER_LANE], Iy[PER_LANE], off[PER_LANE];
+  int Iw[2 * SEG], Ix[2 * SEG], Iy[2 * SEG];
 
   const int top = prev.nlevels - 1;
   for (int level = top; level >= 0; level--) {
@@ -89,31 +158,53 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
       continue;
     }
     int iw00, iw01, iw10, iw11;
-    lk_weights(__fsub_rn(px, (float)ipx), __fsub_rn(py, (float)ipy), iw00, iw01, iw10, iw11);
+    unsigned wt, wb;
+    lk_weights(__fsub_rn(px, (float)ipx), __fsub_rn(py, (float)ipy), wt, wb, iw00, iw01, iw10, iw11);
 
     // ---- window extraction from the previous image + its Scharr derivative
     int sA11 = 0, sA12 = 0, sA22 = 0;
     {
-      const uint8_t* ibase = I.img + (size_t)(ipy + PAD_Y) * pitch + (ipx + PAD_L);
-      const short2* dbase = I.deriv + (size_t)(ipy + PAD_Y) * pitch + (ipx + PAD_L);
+      const size_t o0 = (size_t)(ipy + PAD_Y) * pitch + (ipx + PAD_L);
+      const unsigned sh = stage_patch(I.img + o0, pitch, tile, lane);
+      // derivative patch: 484 short2, row-coalesced (lane -> consecutive elements)
+      {
+        const unsigned* dsrc = reinterpret_cast<const unsigned*>(I.deriv + o0);
+        int r = 0, x = lane;
+        if (x >= PROWS) { x -= PROWS; r = 1; }
 #pragma unroll
-      for (int i = 0; i < PER_LANE; i++) {
-        const int k = lane + 32 * i;
-        Iw[i] = 0; Ix[i] = 0; Iy[i] = 0; off[i] = 0;
-        if (k < NPIX) {
-          const int y = k / WIN, x = k - y * WIN;
-          const int o = y * pitch + x;
-          off[i] = o;
-          const uint8_t* s = ibase + o;
-          const int ival = ((int)__ldg(s) * iw00 + (int)__ldg(s + 1) * iw01 + (int)__ldg(s + pitch) * iw10 +
-                            (int)__ldg(s + pitch + 1) * iw11 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
-          const short2 d00 = __ldg(dbase + o), d01 = __ldg(dbase + o + 1);
-          const short2 d10 = __ldg(dbase + o + pitch), d11 = __ldg(dbase + o + pitch + 1);
-          const int ixv = ((int)d00.x * iw00 + (int)d01.x * iw01 + (int)d10.x * iw10 + (int)d11.x * iw11 +
+        for (int i = 0; i < 16; i++) {
+          if (r < PROWS) dtile[r * DS + x] = __ldg(dsrc + (size_t)r * pitch + x);
+          x += 32 - PROWS; r += 1;                       // advance by 32 elements of 22-wide rows
+          if (x >= PROWS) { x -= PROWS; r += 1; }
+        }
+        __syncwarp();
+      }
+      seg_bilinear(tile, rowA, colA + sh, wt, wb, Iw);
+      if (hasB) seg_bilinear(tile, rowB, colB + sh, wt, wb, Iw + SEG);
+#pragma unroll
+      for (int sgi = 0; sgi < 2; sgi++) {
+        if (sgi == 1 && !hasB) {
+#pragma unroll
+          for (int x = 0; x < SEG; x++) { Iw[SEG + x] = 0; Ix[SEG + x] = 0; Iy[SEG + x] = 0; }
+          break;
+        }
+        const unsigned* d = dtile + (sgi ? rowB : rowA) * DS + (sgi ? colB : colA);
+        unsigned top_[SEG + 1], bot_[SEG + 1];
+#pragma unroll
+        for (int x = 0; x <= SEG; x++) {
+          top_[x] = d[x];
+          bot_[x] = d[DS + x];
+        }
+#pragma unroll
+        for (int x = 0; x < SEG; x++) {
+          // short2 packed in a word: .x = low half (dx), .y = high half (dy)
+          const int ixv = ((int)(short)(top_[x] & 0xffff) * iw00 + (int)(short)(top_[x + 1] & 0xffff) * iw01 +
+                           (int)(short)(bot_[x] & 0xffff) * iw10 + (int)(short)(bot_[x + 1] & 0xffff) * iw11 +
                            (1 << (W_BITS - 1))) >> W_BITS;
-          const int iyv = ((int)d00.y * iw00 + (int)d01.y * iw01 + (int)d10.y * iw10 + (int)d11.y * iw11 +
-                           (1 << (W_BITS - 1))) >> W_BITS;
-          Iw[i] = ival; Ix[i] = ixv; Iy[i] = iyv;
+          const int iyv = (((int)top_[x] >> 16) * iw00 + ((int)top_[x + 1] >> 16) * iw01 + ((int)bot_[x] >> 16) * iw10 +
+                           ((int)bot_[x + 1] >> 16) * iw11 + (1 << (W_BITS - 1))) >> W_BITS;
+          Ix[sgi * SEG + x] = ixv;
+          Iy[sgi * SEG + x] = iyv;
           sA11 += ixv * ixv;
           sA12 += ixv * iyv;
           sA22 += iyv * iyv;
@@ -143,19 +234,26 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
         if (level == 0) st = false;
         break;
       }
-      lk_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), iw00, iw01, iw10, iw11);
-      const uint8_t* jbase = J.img + (size_t)(iny + PAD_Y) * pitch + (inx + PAD_L);
+      lk_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), wt, wb, iw00, iw01, iw10, iw11);
+      const unsigned sh = stage_patch(J.img + (size_t)(iny + PAD_Y) * pitch + (inx + PAD_L), pitch, tile, lane);
       int sb1 = 0, sb2 = 0;
+      {
+        int jv[SEG];
+        seg_bilinear(tile, rowA, colA + sh, wt, wb, jv);
 #pragma unroll
-      for (int i = 0; i < PER_LANE; i++) {
-        const int k = lane + 32 * i;
-        if (k < NPIX) {
-          const uint8_t* s = jbase + off[i];
-          const int jv = ((int)__ldg(s) * iw00 + (int)__ldg(s + 1) * iw01 + (int)__ldg(s + pitch) * iw10 +
-                          (int)__ldg(s + pitch + 1) * iw11 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
-          const int diff = jv - Iw[i];
-          sb1 += diff * Ix[i];
-          sb2 += diff * Iy[i];
+        for (int x = 0; x < SEG; x++) {
+          const int diff = jv[x] - Iw[x];
+          sb1 += diff * Ix[x];
+          sb2 += diff * Iy[x];
+        }
+        if (hasB) {
+          seg_bilinear(tile, rowB, colB + sh, wt, wb, jv);
+#pragma unroll
+          for (int x = 0; x < SEG; x++) {
+            const int diff = jv[x] - Iw[SEG + x];
+            sb1 += diff * Ix[SEG + x];
+            sb2 += diff * Iy[SEG + x];
+          }
         }
       }
       n_iters_done++;
@@ -184,18 +282,17 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
       if (inx < -WIN || inx >= J.w || iny < -WIN || iny >= J.h) {
         st = false;
       } else {
-        lk_weights(__fsub_rn(fx, (float)inx), __fsub_rn(fy, (float)iny), iw00, iw01, iw10, iw11);
-        const uint8_t* jbase = J.img + (size_t)(iny + PAD_Y) * pitch + (inx + PAD_L);
+        lk_weights(__fsub_rn(fx, (float)inx), __fsub_rn(fy, (float)iny), wt, wb, iw00, iw01, iw10, iw11);
+        const unsigned sh = stage_patch(J.img + (size_t)(iny + PAD_Y) * pitch + (inx + PAD_L), pitch, tile, lane);
         int se = 0;
+        int jv[SEG];
+        seg_bilinear(tile, rowA, colA + sh, wt, wb, jv);
 #pragma unroll
-        for (int i = 0; i < PER_LANE; i++) {
-          const int k = lane + 32 * i;
-          if (k < NPIX) {
-            const uint8_t* s = jbase + off[i];
-            const int jv = ((int)__ldg(s) * iw00 + (int)__ldg(s + 1) * iw01 + (int)__ldg(s + pitch) * iw10 +
-                            (int)__ldg(s + pitch + 1) * iw11 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
-            se += abs(jv - Iw[i]);
-          }
+        for (int x = 0; x < SEG; x++) se += abs(jv[x] - Iw[x]);
+        if (hasB) {
+          seg_bilinear(tile, rowB, colB + sh, wt, wb, jv);
+#pragma unroll
+          for (int x = 0; x < SEG; x++) se += abs(jv[x] - Iw[SEG + x]);
         }
         const int tot = __reduce_add_sync(0xffffffffu, se);  // <= 441*8160 fits int32
         errv = __fmul_rn((float)tot, 1.f / (32 * WIN * WIN));
