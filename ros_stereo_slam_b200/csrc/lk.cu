@@ -63,10 +63,25 @@ __device__ __forceinline__ int dp2a_w(unsigned w, unsigned px, int c) {
   asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(px), "r"(c));
   return d;
 }
+// same with bytes 2,3 of px
+__device__ __forceinline__ int dp2a_w_hi(unsigned w, unsigned px, int c) {
+  int d;
+  asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(px), "r"(c));
+  return d;
+}
 
 constexpr int PROWS = WIN + 1;   // 22 source rows
-constexpr int PS = 9;            // tile row stride in 32-bit words (7 used)
-constexpr int DS = 23;           // derivative tile row stride in short2 (22 used)
+#ifndef LK_OPT_HI
+#define LK_OPT_HI 1
+#endif
+#ifndef LK_OPT_DENSE
+#define LK_OPT_DENSE 1
+#endif
+#ifndef LK_OPT_HOIST
+#define LK_OPT_HOIST 1
+#endif
+constexpr int PS = LK_OPT_DENSE ? 7 : 9;            // tile row stride in 32-bit words (dense: conflict-free stores, 2-way loads)
+constexpr int DS = LK_OPT_DENSE ? 22 : 23;           // derivative tile row stride in short2 (dense, same reasoning)
 constexpr int TILE_WORDS = PROWS * PS;          // 198
 constexpr int DTILE_WORDS = PROWS * DS;         // 506
 constexpr int WARP_SMEM_WORDS = TILE_WORDS + DTILE_WORDS;
@@ -95,13 +110,31 @@ __device__ __forceinline__ void seg_bilinear(const unsigned* tile, int row, unsi
   const unsigned sh = (bo & 3) * 8;
   const unsigned t0 = __funnelshift_r(p[0], p[1], sh), t1 = __funnelshift_r(p[1], p[2], sh);
   const unsigned b0 = __funnelshift_r(p[PS], p[PS + 1], sh), b1 = __funnelshift_r(p[PS + 1], p[PS + 2], sh);
+#if !LK_OPT_HI
   const unsigned tp[SEG] = {t0, t0 >> 8, t0 >> 16, __funnelshift_r(t0, t1, 24), t1, t1 >> 8, t1 >> 16};
   const unsigned bp[SEG] = {b0, b0 >> 8, b0 >> 16, __funnelshift_r(b0, b1, 24), b1, b1 >> 8, b1 >> 16};
 #pragma unroll
   for (int x = 0; x < SEG; x++)
     out[x] = dp2a_w(wb, bp[x], dp2a_w(wt, tp[x], 1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
+#else
+  // pixel pairs (x, x+1): bytes (0,1),(2,3) of t0 / t1 via dp2a.lo/.hi; the odd ones from the
+  // registers shifted by one byte -- 2 extra shifts per row instead of 5
+  const unsigned tu = __funnelshift_r(t0, t1, 8), tv = t1 >> 8;
+  const unsigned bu = __funnelshift_r(b0, b1, 8), bv = b1 >> 8;
+  const int rc = 1 << (W_BITS - 5 - 1);
+  out[0] = dp2a_w(wb, b0, dp2a_w(wt, t0, rc)) >> (W_BITS - 5);
+  out[1] = dp2a_w(wb, bu, dp2a_w(wt, tu, rc)) >> (W_BITS - 5);
+  out[2] = dp2a_w_hi(wb, b0, dp2a_w_hi(wt, t0, rc)) >> (W_BITS - 5);
+  out[3] = dp2a_w_hi(wb, bu, dp2a_w_hi(wt, tu, rc)) >> (W_BITS - 5);
+  out[4] = dp2a_w(wb, b1, dp2a_w(wt, t1, rc)) >> (W_BITS - 5);
+  out[5] = dp2a_w(wb, bv, dp2a_w(wt, tv, rc)) >> (W_BITS - 5);
+  out[6] = dp2a_w_hi(wb, b1, dp2a_w_hi(wt, t1, rc)) >> (W_BITS - 5);
+#endif
 }
 
+#ifndef LK_MINBLOCKS
+#define LK_MINBLOCKS 4
+#endif
 __global__ void __launch_bounds__(128)
 lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n, float2* __restrict__ next_pts,
           uint8_t* __restrict__ status, float* __restrict__ err, int max_iters, double eps_sq, float min_eig_thr,
@@ -162,7 +195,7 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
     lk_weights(__fsub_rn(px, (float)ipx), __fsub_rn(py, (float)ipy), wt, wb, iw00, iw01, iw10, iw11);
 
     // ---- window extraction from the previous image + its Scharr derivative
-    int sA11 = 0, sA12 = 0, sA22 = 0;
+    int sA11 = 0, sA12 = 0, sA22 = 0, sC1 = 0, sC2 = 0;
     {
       const size_t o0 = (size_t)(ipy + PAD_Y) * pitch + (ipx + PAD_L);
       const unsigned sh = stage_patch(I.img + o0, pitch, tile, lane);
@@ -208,12 +241,16 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
           sA11 += ixv * ixv;
           sA12 += ixv * iyv;
           sA22 += iyv * iyv;
+          sC1 += Iw[sgi * SEG + x] * ixv;
+          sC2 += Iw[sgi * SEG + x] * iyv;
         }
       }
     }
     const float A11 = __fmul_rn(__ll2float_rn(warp_sum_exact(sA11)), FLT_SCALE);
     const float A12 = __fmul_rn(__ll2float_rn(warp_sum_exact(sA12)), FLT_SCALE);
     const float A22 = __fmul_rn(__ll2float_rn(warp_sum_exact(sA22)), FLT_SCALE);
+    // sum(diff*Ix) = sum(J*Ix) - sum(I*Ix): the second term is constant over the iterations
+    const long long C1 = LK_OPT_HOIST ? warp_sum_exact(sC1) : 0, C2 = LK_OPT_HOIST ? warp_sum_exact(sC2) : 0;
     float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
     const float dd = __fsub_rn(A11, A22);
     const float q = __fadd_rn(__fmul_rn(dd, dd), __fmul_rn(__fmul_rn(4.f, A12), A12));
@@ -242,23 +279,23 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
         seg_bilinear(tile, rowA, colA + sh, wt, wb, jv);
 #pragma unroll
         for (int x = 0; x < SEG; x++) {
-          const int diff = jv[x] - Iw[x];
-          sb1 += diff * Ix[x];
-          sb2 += diff * Iy[x];
+          const int dj = LK_OPT_HOIST ? jv[x] : jv[x] - Iw[x];
+          sb1 += dj * Ix[x];
+          sb2 += dj * Iy[x];
         }
         if (hasB) {
           seg_bilinear(tile, rowB, colB + sh, wt, wb, jv);
 #pragma unroll
           for (int x = 0; x < SEG; x++) {
-            const int diff = jv[x] - Iw[SEG + x];
-            sb1 += diff * Ix[SEG + x];
-            sb2 += diff * Iy[SEG + x];
+            const int dj = LK_OPT_HOIST ? jv[x] : jv[x] - Iw[SEG + x];
+            sb1 += dj * Ix[SEG + x];
+            sb2 += dj * Iy[SEG + x];
           }
         }
       }
       n_iters_done++;
-      const float b1 = __fmul_rn(__ll2float_rn(warp_sum_exact(sb1)), FLT_SCALE);
-      const float b2 = __fmul_rn(__ll2float_rn(warp_sum_exact(sb2)), FLT_SCALE);
+      const float b1 = __fmul_rn(__ll2float_rn(warp_sum_exact(sb1) - C1), FLT_SCALE);
+      const float b2 = __fmul_rn(__ll2float_rn(warp_sum_exact(sb2) - C2), FLT_SCALE);
       const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
       const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
       nx = __fadd_rn(nx, dx);
