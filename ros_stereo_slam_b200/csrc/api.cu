@@ -63,6 +63,106 @@ static void prof_drain(vo_ctx* c) {
   c->prof.pending.clear();
 }
 
+static int alloc_chain(vo_ctx* c) {
+  const vo_params* p = &c->p;
+  VO_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  const int cap = p->max_points;
+  c->cap = cap;
+  VO_CUDA(cudaMalloc(&c->d_xy_in, cap * sizeof(float2)));
+  VO_CUDA(cudaMalloc(&c->d_xy_trk, cap * sizeof(float2)));
+  VO_CUDA(cudaMalloc(&c->d_status, cap));
+  VO_CUDA(cudaMalloc(&c->d_err, cap * sizeof(float)));
+  VO_CUDA(cudaMalloc(&c->d_xyz_in, cap * sizeof(float3)));
+  VO_CUDA(cudaMalloc(&c->d_c_ref, cap * sizeof(float2)));
+  VO_CUDA(cudaMalloc(&c->d_c_trk, cap * sizeof(float2)));
+  VO_CUDA(cudaMalloc(&c->d_c_xyz, cap * sizeof(float3)));
+  VO_CUDA(cudaMalloc(&c->d_f_ref, cap * sizeof(float2)));
+  VO_CUDA(cudaMalloc(&c->d_f_trk, cap * sizeof(float2)));
+  VO_CUDA(cudaMalloc(&c->d_f_xyz, cap * sizeof(float3)));
+  VO_CUDA(cudaMalloc(&c->d_xyz_tmp, cap * sizeof(float3)));
+  VO_CUDA(cudaMalloc(&c->d_mask, cap));
+  VO_CUDA(cudaMalloc(&c->d_idx, cap * sizeof(int32_t)));
+  if (!c->is_aux) {
+    VO_CUDA(cudaMalloc(&c->d_seq_xy, cap * sizeof(float2)));
+    VO_CUDA(cudaMalloc(&c->d_seq_xyz, cap * sizeof(float3)));
+  }
+  VO_CUDA(cudaMalloc(&c->d_count, 16 * sizeof(int)));
+  VO_CUDA(cudaMallocHost(&c->h_count, 16 * sizeof(int)));
+  VO_CUDA(cudaMalloc(&c->d_tile_state, 256 * sizeof(unsigned long long)));
+  VO_CUDA(cudaMemsetAsync(c->d_tile_state, 0, 256 * sizeof(unsigned long long), c->stream));
+  VO_CUDA(cudaMallocHost(&c->h_pts, (size_t)cap * 8 * sizeof(float)));
+  const int ch = p->max_hypotheses;
+  c->cap_h = ch;
+  VO_CUDA(cudaMalloc(&c->d_samples, (size_t)ch * 7 * sizeof(int32_t)));
+  VO_CUDA(cudaMallocHost(&c->h_samples, (size_t)ch * 7 * sizeof(int32_t)));
+  VO_CUDA(cudaMalloc(&c->d_models, (size_t)ch * 27 * sizeof(double)));
+  VO_CUDA(cudaMalloc(&c->d_counts, (size_t)ch * 3 * sizeof(int32_t)));
+  VO_CUDA(cudaMalloc(&c->d_sel, 8 * sizeof(int)));
+  VO_CUDA(cudaMallocHost(&c->h_sel, 8 * sizeof(int)));
+  VO_CUDA(cudaMalloc(&c->d_pose, 16 * sizeof(double)));
+  VO_CUDA(cudaMallocHost(&c->h_pose, 16 * sizeof(double)));
+  VO_CUDA(cudaMalloc(&c->d_cam, 48 * sizeof(double)));
+  VO_CUDA(cudaMalloc(&c->d_lk_work, 2 * sizeof(unsigned long long)));
+  VO_CUDA(cudaMallocHost(&c->h_lk_work, 2 * sizeof(unsigned long long)));
+  VO_CUDA(cudaMemsetAsync(c->d_lk_work, 0, 2 * sizeof(unsigned long long), c->stream));
+  VO_CUDA(cudaStreamSynchronize(c->stream));
+  return VO_OK;
+}
+
+static void free_chain(vo_ctx* c) {
+  if (!c) return;
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  void* dev[] = {c->d_xy_in, c->d_xy_trk, c->d_status, c->d_err, c->d_xyz_in, c->d_c_ref, c->d_c_trk, c->d_c_xyz,
+                 c->d_f_ref, c->d_f_trk, c->d_f_xyz, c->d_xyz_tmp, c->d_mask, c->d_idx, c->d_seq_xy, c->d_seq_xyz,
+                 c->d_count, c->d_tile_state, c->d_samples, c->d_models, c->d_counts, c->d_sel, c->d_pose, c->d_cam,
+                 c->d_lk_work};
+  for (void* p : dev) cudaFree(p);
+  void* host[] = {c->h_count, c->h_pts, c->h_samples, c->h_sel, c->h_pose, c->h_lk_work};
+  for (void* p : host) cudaFreeHost(p);
+  for (auto& pe : c->prof.pending) {
+    cudaEventDestroy(pe.a);
+    cudaEventDestroy(pe.b);
+  }
+  for (auto e : c->prof.pool) cudaEventDestroy(e);
+  if (c->stream) cudaStreamDestroy(c->stream);
+}
+
+// host worker of the auxiliary chain: runs one posted task at a time
+static void worker_main(vo_ctx* c) {
+  cudaSetDevice(c->device);
+  std::unique_lock<std::mutex> lk(c->mtx);
+  for (;;) {
+    c->cv.wait(lk, [&] { return c->task_pending || c->quit; });
+    if (c->quit) return;
+    std::function<int()> f = c->task;
+    c->task_pending = false;
+    lk.unlock();
+    const int r = f();
+    const std::string err = r != VO_OK ? std::string(g_err) : std::string();
+    lk.lock();
+    c->task_result = r;
+    c->task_error = err;
+    c->task_done = true;
+    c->cv.notify_all();
+  }
+}
+
+static void post_task(vo_ctx* c, std::function<int()> f) {
+  std::lock_guard<std::mutex> g(c->mtx);
+  c->task = std::move(f);
+  c->task_pending = true;
+  c->task_done = false;
+  c->cv.notify_all();
+}
+
+static int wait_task(vo_ctx* c) {
+  std::unique_lock<std::mutex> lk(c->mtx);
+  c->cv.wait(lk, [&] { return c->task_done; });
+  c->task_done = false;
+  if (c->task_result != VO_OK) set_error("%s", c->task_error.c_str());
+  return c->task_result;
+}
+
 extern "C" {
 
 const char* vo_last_error(void) { return g_err; }
@@ -151,58 +251,35 @@ int vo_create(const vo_params* p, vo_ctx** out) {
   cudaDeviceProp prop;
   VO_CUDA(cudaGetDeviceProperties(&prop, p->device));
   c->sm_count = prop.multiProcessorCount;
-  VO_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  const size_t img_bytes = (size_t)p->width * p->height;
-  for (int s = 0; s < 3; s++) {
-    VO_CUDA(cudaMalloc(&c->d_raw[s], img_bytes));
-    VO_TRY(pyr_alloc(c, c->pyr[s]));
-    VO_CUDA(cudaMallocHost(&c->h_img[s], img_bytes));
+  c->pyr = new Pyramid[3];
+  int r = alloc_chain(c);
+  if (r == VO_OK) {
+    for (int s = 0; s < 3 && r == VO_OK; s++) r = pyr_alloc(c, c->pyr[s]);
   }
-  const int cap = p->max_points;
-  c->cap = cap;
-  VO_CUDA(cudaMalloc(&c->d_xy_in, cap * sizeof(float2)));
-  VO_CUDA(cudaMalloc(&c->d_xy_trk, cap * sizeof(float2)));
-  VO_CUDA(cudaMalloc(&c->d_status, cap));
-  VO_CUDA(cudaMalloc(&c->d_err, cap * sizeof(float)));
-  VO_CUDA(cudaMalloc(&c->d_xyz_in, cap * sizeof(float3)));
-  VO_CUDA(cudaMalloc(&c->d_c_ref, cap * sizeof(float2)));
-  VO_CUDA(cudaMalloc(&c->d_c_trk, cap * sizeof(float2)));
-  VO_CUDA(cudaMalloc(&c->d_c_xyz, cap * sizeof(float3)));
-  VO_CUDA(cudaMalloc(&c->d_f_ref, cap * sizeof(float2)));
-  VO_CUDA(cudaMalloc(&c->d_f_trk, cap * sizeof(float2)));
-  VO_CUDA(cudaMalloc(&c->d_f_xyz, cap * sizeof(float3)));
-  VO_CUDA(cudaMalloc(&c->d_xyz_tmp, cap * sizeof(float3)));
-  VO_CUDA(cudaMalloc(&c->d_mask, cap));
-  VO_CUDA(cudaMalloc(&c->d_idx, cap * sizeof(int32_t)));
-  VO_CUDA(cudaMalloc(&c->d_seq_xy, cap * sizeof(float2)));
-  VO_CUDA(cudaMalloc(&c->d_seq_xyz, cap * sizeof(float3)));
-  VO_CUDA(cudaMalloc(&c->d_count, 16 * sizeof(int)));
-  VO_CUDA(cudaMallocHost(&c->h_count, 16 * sizeof(int)));
-  VO_CUDA(cudaMalloc(&c->d_tile_state, 256 * sizeof(unsigned long long)));
-  VO_CUDA(cudaMemsetAsync(c->d_tile_state, 0, 256 * sizeof(unsigned long long), c->stream));
-  VO_CUDA(cudaMallocHost(&c->h_pts, (size_t)cap * 8 * sizeof(float)));
-  const int ch = p->max_hypotheses;
-  c->cap_h = ch;
-  VO_CUDA(cudaMalloc(&c->d_samples, (size_t)ch * 7 * sizeof(int32_t)));
-  VO_CUDA(cudaMallocHost(&c->h_samples, (size_t)ch * 7 * sizeof(int32_t)));
-  VO_CUDA(cudaMalloc(&c->d_models, (size_t)ch * 27 * sizeof(double)));
-  VO_CUDA(cudaMalloc(&c->d_counts, (size_t)ch * 3 * sizeof(int32_t)));
-  VO_CUDA(cudaMalloc(&c->d_sel, 8 * sizeof(int)));
-  VO_CUDA(cudaMallocHost(&c->h_sel, 8 * sizeof(int)));
-  VO_CUDA(cudaMalloc(&c->d_pose, 16 * sizeof(double)));
-  VO_CUDA(cudaMallocHost(&c->h_pose, 16 * sizeof(double)));
-  VO_CUDA(cudaMalloc(&c->d_cam, 48 * sizeof(double)));
-  VO_CUDA(cudaMalloc(&c->d_lk_work, 2 * sizeof(unsigned long long)));
-  VO_CUDA(cudaMallocHost(&c->h_lk_work, 2 * sizeof(unsigned long long)));
-  VO_CUDA(cudaMemsetAsync(c->d_lk_work, 0, 2 * sizeof(unsigned long long), c->stream));
-  VO_CUDA(cudaStreamSynchronize(c->stream));
-  {
-    const int r = selfcheck_run(c);
-    if (r != VO_OK) {
-      vo_destroy(c);
-      return r;
+  if (r == VO_OK) {
+    vo_ctx* a = new vo_ctx();
+    a->p = *p;
+    a->device = p->device;
+    a->sm_count = c->sm_count;
+    a->is_aux = true;
+    a->pyr = c->pyr;
+    c->aux = a;
+    r = alloc_chain(a);
+  }
+  if (r == VO_OK) {
+    if (cudaEventCreateWithFlags(&c->ev_left, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_stereo, cudaEventDisableTiming) != cudaSuccess) {
+      set_error("cudaEventCreate failed");
+      r = VO_ERR_CUDA;
     }
   }
+  if (r == VO_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) r = VO_ERR_CUDA;
+  if (r == VO_OK) r = selfcheck_run(c);
+  if (r != VO_OK) {
+    vo_destroy(c);
+    return r;
+  }
+  c->worker = std::thread(worker_main, c);
   *out = c;
   return VO_OK;
 }
@@ -216,21 +293,26 @@ int vo_self_check(vo_ctx* c) {
 int vo_destroy(vo_ctx* c) {
   if (!c) return VO_OK;
   cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream);
-  prof_drain(c);
-  for (auto e : c->prof.pool) cudaEventDestroy(e);
-  for (int s = 0; s < 3; s++) {
-    cudaFree(c->d_raw[s]);
-    pyr_free(c->pyr[s]);
-    cudaFreeHost(c->h_img[s]);
+  if (c->worker.joinable()) {
+    {
+      std::lock_guard<std::mutex> g(c->mtx);
+      c->quit = true;
+      c->cv.notify_all();
+    }
+    c->worker.join();
   }
-  void* dev[] = {c->d_xy_in, c->d_xy_trk, c->d_status, c->d_err, c->d_xyz_in, c->d_c_ref, c->d_c_trk, c->d_c_xyz,
-                 c->d_f_ref, c->d_f_trk, c->d_f_xyz, c->d_xyz_tmp, c->d_mask, c->d_idx, c->d_seq_xy, c->d_seq_xyz,
-                 c->d_count, c->d_tile_state, c->d_samples, c->d_models, c->d_counts, c->d_sel, c->d_pose, c->d_cam, c->d_lk_work};
-  for (void* p : dev) cudaFree(p);
-  void* host[] = {c->h_count, c->h_pts, c->h_samples, c->h_sel, c->h_pose, c->h_lk_work};
-  for (void* p : host) cudaFreeHost(p);
-  cudaStreamDestroy(c->stream);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->aux) {
+    free_chain(c->aux);
+    delete c->aux;
+  }
+  if (c->pyr) {
+    for (int s = 0; s < 3; s++) pyr_free(c->pyr[s]);
+    delete[] c->pyr;
+  }
+  if (c->ev_left) cudaEventDestroy(c->ev_left);
+  if (c->ev_stereo) cudaEventDestroy(c->ev_stereo);
+  free_chain(c);
   delete c;
   return VO_OK;
 }
@@ -891,27 +973,61 @@ int vo_seq_track(vo_ctx* c, const uint8_t* left, const uint8_t* right, int strid
   const int ref = c->seq_ref_slot, cur = 1 - ref;
   VO_TRY(load_image(c, cur, left, stride, is_device, false));
   out->n_lk_in = c->seq_n;
-  int k = 0;
-  VO_TRY(track_pipeline(c, ref, cur, c->d_seq_xy, c->d_seq_xyz, c->seq_n, &k));
-  out->n_tracked = k;
-  int ni = 0, att = 1;
-  int r = pnp_two_attempts(c, k, &ni, &att);
-  out->n_inliers = ni;
-  out->attempt_used = att;
+
+  // A keyframe that is known before PnP (caller forces it, or the policy fires on every frame
+  // because no inlier count can reach kf_min_inliers) does not depend on this frame's tracking:
+  // run the stereo pipeline on the auxiliary chain concurrently with tracking + PnP.
+  const bool kf_known = right && (force_keyframe || c->p.kf_min_inliers > c->p.max_points);
+  vo_ctx* a = c->aux;
+  int kk = 0, ng = 0;
+  if (kf_known) {
+    VO_CUDA(cudaEventRecord(c->ev_left, c->stream));           // cur-left pyramid is complete
+    VO_CUDA(cudaStreamWaitEvent(a->stream, c->ev_left, 0));
+    post_task(c, [=, &kk, &ng]() -> int {
+      VO_TRY(load_image(a, 2, right, stride, is_device, false));
+      VO_TRY(stereo_pipeline(a, cur, 2, nullptr, &kk, &ng));   // camera-frame xyz in a->d_xyz_tmp
+      VO_CUDA(cudaEventRecord(c->ev_stereo, a->stream));
+      return VO_OK;
+    });
+  }
+
+  int k = 0, ni = 0, att = 1;
+  int r = track_pipeline(c, ref, cur, c->d_seq_xy, c->d_seq_xyz, c->seq_n, &k);
+  if (r == VO_OK) {
+    out->n_tracked = k;
+    r = pnp_two_attempts(c, k, &ni, &att);
+    out->n_inliers = ni;
+    out->attempt_used = att;
+  }
+  if (kf_known) {
+    const int rs = wait_task(c);     // always join: the auxiliary chain must be idle on return
+    if (r == VO_OK) r = rs;
+  }
   if (r != VO_OK) return r;  // incl. VO_ERR_LOW_INLIERS: the reference breaks out of its loop here
   for (int i = 0; i < 3; i++) {
     out->rvec[i] = c->h_pose[i];
     out->tvec[i] = c->h_pose[3 + i];
   }
   pose_from_pnp(out->rvec, out->tvec, out->pose3x4);
-  if (ni < c->p.kf_min_inliers || force_keyframe) {
+  if (kf_known) {
+    // insertKeyFrames epilogue: world points = pose * camera points (src/keyFrameManagement.cpp:20-30)
+    VO_CUDA(cudaStreamWaitEvent(c->stream, c->ev_stereo, 0));
+    VO_CUDA(cudaMemcpyAsync(c->d_cam + 24, out->pose3x4, 12 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (kk) {
+      VO_TRY(transform_launch(c, c->d_cam + 24, a->d_xyz_tmp, kk, c->d_seq_xyz));
+      VO_CUDA(cudaMemcpyAsync(c->d_seq_xy, a->d_f_ref, (size_t)kk * sizeof(float2), cudaMemcpyDeviceToDevice, c->stream));
+    }
+    c->seq_n = kk;
+    out->keyframe = 1;
+    out->n_kf_points = kk;
+    out->n_lk_in_stereo = ng;
+  } else if (ni < c->p.kf_min_inliers || force_keyframe) {
     // keyframe: src/VisualSLAM.cpp:120-137 -> insertKeyFrames (src/keyFrameManagement.cpp:9-31)
     if (!right) {
       set_error("keyframe required (inliers %d < %d) but no right image was supplied", ni, c->p.kf_min_inliers);
       return VO_ERR_INVALID_ARG;
     }
     VO_TRY(load_image(c, 2, right, stride, is_device, false));
-    int kk = 0, ng = 0;
     VO_TRY(stereo_pipeline(c, cur, 2, out->pose3x4, &kk, &ng));
     if (kk) {
       VO_CUDA(cudaMemcpyAsync(c->d_seq_xy, c->d_f_ref, (size_t)kk * sizeof(float2), cudaMemcpyDeviceToDevice, c->stream));
@@ -955,8 +1071,11 @@ int vo_sync(vo_ctx* c) {
 int vo_profile_enable(vo_ctx* c, int mask) {
   CHECK_CTX(c);
   VO_TRY(sync_stream(c));
+  VO_TRY(sync_stream(c->aux));
   prof_drain(c);
+  prof_drain(c->aux);
   c->prof.mask = (unsigned)mask;
+  c->aux->prof.mask = (unsigned)mask;
   return VO_OK;
 }
 
@@ -964,24 +1083,31 @@ int vo_profile_read(vo_ctx* c, int kernel, int64_t* launches, double* ms, int re
   CHECK_CTX(c);
   if (kernel < 0 || kernel >= VO_K_COUNT) return VO_ERR_INVALID_ARG;
   VO_TRY(sync_stream(c));
+  VO_TRY(sync_stream(c->aux));
   prof_drain(c);
-  if (launches) *launches = c->prof.launches[kernel];
-  if (ms) *ms = c->prof.ms[kernel];
+  prof_drain(c->aux);
+  if (launches) *launches = c->prof.launches[kernel] + c->aux->prof.launches[kernel];
+  if (ms) *ms = c->prof.ms[kernel] + c->aux->prof.ms[kernel];
   if (reset) {
-    c->prof.launches[kernel] = 0;
-    c->prof.ms[kernel] = 0;
+    c->prof.launches[kernel] = c->aux->prof.launches[kernel] = 0;
+    c->prof.ms[kernel] = c->aux->prof.ms[kernel] = 0;
   }
   return VO_OK;
 }
 
-int64_t vo_launch_count(vo_ctx* c) { return c ? c->launch_count : 0; }
+int64_t vo_launch_count(vo_ctx* c) { return c ? c->launch_count + (c->aux ? c->aux->launch_count : 0) : 0; }
 
 int vo_lk_work(vo_ctx* c, int64_t* point_levels, int64_t* iterations) {
   CHECK_CTX(c);
-  VO_CUDA(cudaMemcpyAsync(c->h_lk_work, c->d_lk_work, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
-  VO_TRY(sync_stream(c));
-  if (point_levels) *point_levels = (int64_t)c->h_lk_work[0];
-  if (iterations) *iterations = (int64_t)c->h_lk_work[1];
+  int64_t pl = 0, it = 0;
+  for (vo_ctx* k : {c, c->aux}) {
+    VO_CUDA(cudaMemcpyAsync(k->h_lk_work, k->d_lk_work, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, k->stream));
+    VO_TRY(sync_stream(k));
+    pl += (int64_t)k->h_lk_work[0];
+    it += (int64_t)k->h_lk_work[1];
+  }
+  if (point_levels) *point_levels = pl;
+  if (iterations) *iterations = it;
   return VO_OK;
 }
 

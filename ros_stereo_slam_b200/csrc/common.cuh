@@ -5,7 +5,11 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/vo_b200.h"
@@ -68,9 +72,25 @@ struct vo_ctx {
   int64_t launch_count = 0;
   vo::Profile prof;
 
+  // A context is one CHAIN of scratch buffers + one stream.  The public context owns a second,
+  // auxiliary chain (`aux`) that shares the pyramids: when a keyframe is known in advance
+  // (force_keyframe, or a keyframe policy that fires on every frame) the stereo pipeline runs on
+  // the auxiliary chain (own stream, own host worker thread) concurrently with temporal
+  // tracking + PnP, whose long latency-bound solver kernels leave the SMs mostly idle.
+  vo_ctx* aux = nullptr;
+  bool is_aux = false;
+  std::thread worker;
+  std::mutex mtx;
+  std::condition_variable cv;
+  std::function<int()> task;
+  bool task_pending = false, task_done = false, quit = false;
+  int task_result = 0;
+  std::string task_error;
+  cudaEvent_t ev_left = nullptr, ev_stereo = nullptr;
+
   // image staging + pyramids: slot 0/1 ping-pong left images (reference <-> current), slot 2 right
   uint8_t* d_raw[3] = {nullptr, nullptr, nullptr};
-  vo::Pyramid pyr[3];
+  vo::Pyramid* pyr = nullptr;   // 3 slots, owned by the primary chain, shared with aux
   uint64_t stamp_counter = 0;
 
   // point buffers (capacity max_points)
