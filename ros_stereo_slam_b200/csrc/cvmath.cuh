@@ -76,7 +76,9 @@ struct CvRng {
 // WITH_V=false skips the accumulation of V (its rotations never feed back into At/W, so U
 // and W are bit-identical); callers that only consume U^T (EPnP's 12x12 and 3x3 PCA) use it
 // and pass any non-null pointer as Vt (OpenCV's code keys the row normalisation on Vt != 0).
-template <int M, int N, int N1, bool WITH_V = true>
+// SKIP_SWEEPS=true: the rows of At were already orthogonalised (by jacobi_sweeps_warp on the
+// device); only the norms, the ordering and the completion of the rows are done here.
+template <int M, int N, int N1, bool WITH_V = true, bool SKIP_SWEEPS = false>
 VO_HDN void jacobi_svd(double* At, double* _W, double* Vt) {
   constexpr int astep = M, vstep = N, m = M, n = N, n1 = N1;
   double W[N];
@@ -100,7 +102,7 @@ VO_HDN void jacobi_svd(double* At, double* _W, double* Vt) {
     }
   }
 
-  for (iter = 0; iter < max_iter; iter++) {
+  for (iter = 0; iter < (SKIP_SWEEPS ? 0 : max_iter); iter++) {
     bool changed = false;
     for (i = 0; i < n - 1; i++)
       for (j = i + 1; j < n; j++) {
@@ -284,6 +286,151 @@ VO_HDF void solve_svd(const double* A, const double* b, double* x) {
   }
 }
 
+// Runtime-size variant of jacobi_svd (n1 = n, V accumulated) and of cv::solve(DECOMP_SVD): same
+// operations in the same order as the compile-time versions.  EPnP's three beta initialisations
+// solve 6x4, 6x3 and 6x5 systems; on the device they run on three lanes of one warp, and sharing
+// ONE instruction stream (instead of three template instantiations) keeps those lanes converged.
+VO_HDN void jacobi_svd_rt(double* At, int astep, double* _W, double* Vt, int vstep, int m, int n) {
+  double W[8];
+  const double minval = DBL_MIN, eps = DBL_EPSILON * 10;
+  int i, j, k, iter, max_iter = m > 30 ? m : 30;
+  double c, s, sd;
+  for (i = 0; i < n; i++) {
+    for (k = 0, sd = 0; k < m; k++) {
+      double t = At[i * astep + k];
+      sd += t * t;
+    }
+    W[i] = sd;
+    for (k = 0; k < n; k++) Vt[i * vstep + k] = 0;
+    Vt[i * vstep + i] = 1;
+  }
+  for (iter = 0; iter < max_iter; iter++) {
+    bool changed = false;
+    for (i = 0; i < n - 1; i++)
+      for (j = i + 1; j < n; j++) {
+        double *Ai = At + i * astep, *Aj = At + j * astep;
+        double a = W[i], p = 0, b = W[j];
+        for (k = 0; k < m; k++) p += Ai[k] * Aj[k];
+        if (fabs(p) <= eps * sqrt(a * b)) continue;
+        p *= 2;
+        double beta = a - b, gamma = cv_hypot(p, beta);
+        if (beta < 0) {
+          double delta = (gamma - beta) * 0.5;
+          s = sqrt(delta / gamma);
+          c = p / (gamma * s * 2);
+        } else {
+          c = sqrt((gamma + beta) / (gamma * 2));
+          s = p / (gamma * c * 2);
+        }
+        a = b = 0;
+        for (k = 0; k < m; k++) {
+          double t0 = c * Ai[k] + s * Aj[k];
+          double t1 = -s * Ai[k] + c * Aj[k];
+          Ai[k] = t0;
+          Aj[k] = t1;
+          a += t0 * t0;
+          b += t1 * t1;
+        }
+        W[i] = a;
+        W[j] = b;
+        changed = true;
+        double *Vi = Vt + i * vstep, *Vj = Vt + j * vstep;
+        for (k = 0; k < n; k++) {
+          double t0 = c * Vi[k] + s * Vj[k];
+          double t1 = -s * Vi[k] + c * Vj[k];
+          Vi[k] = t0;
+          Vj[k] = t1;
+        }
+      }
+    if (!changed) break;
+  }
+  for (i = 0; i < n; i++) {
+    for (k = 0, sd = 0; k < m; k++) {
+      double t = At[i * astep + k];
+      sd += t * t;
+    }
+    W[i] = sqrt(sd);
+  }
+  for (i = 0; i < n - 1; i++) {
+    j = i;
+    for (k = i + 1; k < n; k++)
+      if (W[j] < W[k]) j = k;
+    if (i != j) {
+      double t = W[i];
+      W[i] = W[j];
+      W[j] = t;
+      for (k = 0; k < m; k++) {
+        t = At[i * astep + k];
+        At[i * astep + k] = At[j * astep + k];
+        At[j * astep + k] = t;
+      }
+      for (k = 0; k < n; k++) {
+        t = Vt[i * vstep + k];
+        Vt[i * vstep + k] = Vt[j * vstep + k];
+        Vt[j * vstep + k] = t;
+      }
+    }
+  }
+  for (i = 0; i < n; i++) _W[i] = W[i];
+  CvRng rng(0x12345678);
+  for (i = 0; i < n; i++) {
+    sd = W[i];
+    for (int ii = 0; ii < 100 && sd <= minval; ii++) {
+      const double val0 = 1. / m;
+      for (k = 0; k < m; k++) {
+        double val = (rng.next() & 256) != 0 ? val0 : -val0;
+        At[i * astep + k] = val;
+      }
+      for (iter = 0; iter < 2; iter++) {
+        for (j = 0; j < i; j++) {
+          sd = 0;
+          for (k = 0; k < m; k++) sd += At[i * astep + k] * At[j * astep + k];
+          double asum = 0;
+          for (k = 0; k < m; k++) {
+            double t = At[i * astep + k] - sd * At[j * astep + k];
+            At[i * astep + k] = t;
+            asum += fabs(t);
+          }
+          asum = asum > eps * 100 ? 1 / asum : 0;
+          for (k = 0; k < m; k++) At[i * astep + k] *= asum;
+        }
+      }
+      sd = 0;
+      for (k = 0; k < m; k++) {
+        double t = At[i * astep + k];
+        sd += t * t;
+      }
+      sd = sqrt(sd);
+    }
+    s = sd > minval ? 1 / sd : 0.;
+    for (k = 0; k < m; k++) At[i * astep + k] *= s;
+  }
+}
+
+// cv::solve(A (6 x n), b (6), x (n), DECOMP_SVD) for n <= 5
+VO_HDN void solve_svd_6xn(const double* A, const double* b, double* x, int n) {
+  const int m = 6;
+  double at[30], w[5], v[25];
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < m; j++) at[i * m + j] = A[j * n + i];
+  jacobi_svd_rt(at, m, w, v, n, m, n);
+  double threshold = 0;
+  for (int i = 0; i < n; i++) {
+    x[i] = 0;
+    threshold += w[i];
+  }
+  threshold *= DBL_EPSILON * 2;
+  for (int i = 0; i < n; i++) {
+    double wi = w[i];
+    if (fabs(wi) <= threshold) continue;
+    wi = 1 / wi;
+    double s = 0;
+    for (int j = 0; j < m; j++) s += at[i * m + j] * b[j];
+    s *= wi;
+    for (int j = 0; j < n; j++) x[j] = x[j] + s * v[i * n + j];
+  }
+}
+
 // cv::invert(A 3x3, DECOMP_SVD) = SVD::compute + SVD::backSubst(w, u, vt, Mat(), dst).
 VO_HDF void invert3_svd(const double* A, double* inv) {
   double w[3], u[9], vt[9];
@@ -389,9 +536,9 @@ struct Intrinsics {
   double fx, fy, cx, cy;
 };
 
-struct EpnpWork {
-  double pws[15], us[10], alphas[20], pcs[15];
-  double cws[4][3], ccs[4][3];
+struct EpnpWork {   // read-only after epnp5_front
+  double pws[15], us[10], alphas[20];
+  double cws[4][3];
 };
 
 VO_HD double epnp_dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
@@ -494,12 +641,12 @@ VO_HDF void epnp_gauss_newton(const double* l_6x10, const double* rho, double be
   }
 }
 
-VO_HDF void epnp_estimate_R_and_t(EpnpWork& w, double R[3][3], double t[3]) {
+VO_HDF void epnp_estimate_R_and_t(const EpnpWork& w, const double* pcs, double R[3][3], double t[3]) {
   const int n = 5;
   double pc0[3] = {0, 0, 0}, pw0[3] = {0, 0, 0};
   for (int i = 0; i < n; i++)
     for (int j = 0; j < 3; j++) {
-      pc0[j] += w.pcs[3 * i + j];
+      pc0[j] += pcs[3 * i + j];
       pw0[j] += w.pws[3 * i + j];
     }
   for (int j = 0; j < 3; j++) {
@@ -508,7 +655,7 @@ VO_HDF void epnp_estimate_R_and_t(EpnpWork& w, double R[3][3], double t[3]) {
   }
   double abt[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, abt_d[3], abt_u[9], abt_vt[9];
   for (int i = 0; i < n; i++) {
-    const double* pc = &w.pcs[3 * i];
+    const double* pc = &pcs[3 * i];
     const double* pw = &w.pws[3 * i];
     for (int j = 0; j < 3; j++) {
       abt[3 * j] += (pc[j] - pc0[j]) * (pw[0] - pw0[0]);
@@ -535,33 +682,34 @@ VO_HDF void epnp_estimate_R_and_t(EpnpWork& w, double R[3][3], double t[3]) {
   t[2] = pc0[2] - epnp_dot3(R[2], pw0);
 }
 
-VO_HDF double epnp_compute_R_and_t(EpnpWork& w, const Intrinsics& K, const double* ut, const double* betas,
+VO_HDF double epnp_compute_R_and_t(const EpnpWork& w, const Intrinsics& K, const double* ut, const double* betas,
                                   double R[3][3], double t[3]) {
   const int n = 5;
+  double ccs[4][3], pcs[15];
   // compute_ccs
-  for (int i = 0; i < 4; i++) w.ccs[i][0] = w.ccs[i][1] = w.ccs[i][2] = 0.0;
+  for (int i = 0; i < 4; i++) ccs[i][0] = ccs[i][1] = ccs[i][2] = 0.0;
   for (int i = 0; i < 4; i++) {
     const double* v = ut + 12 * (11 - i);
     for (int j = 0; j < 4; j++)
-      for (int k = 0; k < 3; k++) w.ccs[j][k] += betas[i] * v[3 * j + k];
+      for (int k = 0; k < 3; k++) ccs[j][k] += betas[i] * v[3 * j + k];
   }
   // compute_pcs
   for (int i = 0; i < n; i++) {
     const double* a = &w.alphas[4 * i];
-    double* pc = &w.pcs[3 * i];
-    for (int j = 0; j < 3; j++) pc[j] = a[0] * w.ccs[0][j] + a[1] * w.ccs[1][j] + a[2] * w.ccs[2][j] + a[3] * w.ccs[3][j];
+    double* pc = &pcs[3 * i];
+    for (int j = 0; j < 3; j++) pc[j] = a[0] * ccs[0][j] + a[1] * ccs[1][j] + a[2] * ccs[2][j] + a[3] * ccs[3][j];
   }
   // solve_for_sign
-  if (w.pcs[2] < 0.0) {
+  if (pcs[2] < 0.0) {
     for (int i = 0; i < 4; i++)
-      for (int j = 0; j < 3; j++) w.ccs[i][j] = -w.ccs[i][j];
+      for (int j = 0; j < 3; j++) ccs[i][j] = -ccs[i][j];
     for (int i = 0; i < n; i++) {
-      w.pcs[3 * i] = -w.pcs[3 * i];
-      w.pcs[3 * i + 1] = -w.pcs[3 * i + 1];
-      w.pcs[3 * i + 2] = -w.pcs[3 * i + 2];
+      pcs[3 * i] = -pcs[3 * i];
+      pcs[3 * i + 1] = -pcs[3 * i + 1];
+      pcs[3 * i + 2] = -pcs[3 * i + 2];
     }
   }
-  epnp_estimate_R_and_t(w, R, t);
+  epnp_estimate_R_and_t(w, pcs, R, t);
   // reprojection_error
   double sum2 = 0.0;
   for (int i = 0; i < n; i++) {
@@ -577,17 +725,14 @@ VO_HDF double epnp_compute_R_and_t(EpnpWork& w, const Intrinsics& K, const doubl
   return sum2 / n;
 }
 
-// FMA_MTM: see mul_transposed.  Returns R (row-major) and t.
+// EPnP is split at its 12x12 SVD so that the device can run the Jacobi sweeps of that SVD
+// warp-cooperatively (jacobi_warp.cuh) while everything else stays on one lane.
+// FMA_MTM: see mul_transposed.
+// epnp5_front_M: everything up to the 10x12 matrix M;  MtM = M^T M follows (mul_transposed).
 template <bool FMA_MTM>
-#ifdef VO_NO_EPNP_DBG
-VO_HDN void epnp5(const float* obj /*15*/, const float* img /*10*/, const Intrinsics& K, double Rout[9], double tout[3]) {
-  double* dbg = nullptr;
-#else
-VO_HDN void epnp5(const float* obj /*15*/, const float* img /*10*/, const Intrinsics& K, double Rout[9], double tout[3],
-                  double* dbg = nullptr /*>= 420 doubles: intermediates for parity debugging*/) {
-#endif
+VO_HDN void epnp5_front_M(const float* obj /*15*/, const float* img /*10*/, const Intrinsics& K, EpnpWork& w,
+                          double* M /*120*/) {
   const int n = 5;
-  EpnpWork w;
   // solvePnP: undistortPoints (float in, float out, zero distortion) then epnp::init_points
   const double ifx = 1. / K.fx, ify = 1. / K.fy;
   for (int i = 0; i < n; i++) {
@@ -630,10 +775,8 @@ VO_HDN void epnp5(const float* obj /*15*/, const float* img /*10*/, const Intrin
       a[0] = 1.0f - a[1] - a[2] - a[3];
     }
   }
-  // M (10 x 12), MtM, SVD
-  double ut[144];
+  // M (10 x 12)
   {
-    double M[120], mtm[144], d[12];
     for (int i = 0; i < n; i++) {
       const double* as = &w.alphas[4 * i];
       double u = w.us[2 * i], v = w.us[2 * i + 1];
@@ -648,21 +791,24 @@ VO_HDN void epnp5(const float* obj /*15*/, const float* img /*10*/, const Intrin
         M2[3 * q + 2] = as[q] * (K.cy - v);
       }
     }
-    mul_transposed<12, FMA_MTM>(M, 2 * n, mtm);
-    if (dbg) {
-      for (int i = 0; i < 10; i++) dbg[i] = w.us[i];
-      for (int i = 0; i < 12; i++) dbg[10 + i] = w.cws[i / 3][i % 3];
-      for (int i = 0; i < 20; i++) dbg[22 + i] = w.alphas[i];
-      for (int i = 0; i < 144; i++) dbg[42 + i] = mtm[i];
-    }
-    svd_square_ut_only<12>(mtm, d, ut);
-    if (dbg) {
-      for (int i = 0; i < 144; i++) dbg[186 + i] = ut[i];
-      for (int i = 0; i < 12; i++) dbg[330 + i] = d[i];
-    }
   }
+}
+
+template <bool FMA_MTM>
+VO_HDN void epnp5_front(const float* obj /*15*/, const float* img /*10*/, const Intrinsics& K, EpnpWork& w,
+                        double* mtm /*144*/) {
+  double M[120];
+  epnp5_front_M<FMA_MTM>(obj, img, K, w, M);
+  mul_transposed<12, FMA_MTM>(M, 10, mtm);
+}
+
+// ---- back end: L/rho from the last four left singular vectors, then the three beta
+// initialisations N = 1, 2, 3 (each followed by 5 Gauss-Newton steps and a Horn alignment) and
+// the choice of the smallest reprojection error.  The three variants are independent: the
+// device runs them on three lanes (ransac.cu), the host one after the other.
+// ut: U^T of MtM (rows = left singular vectors, descending singular values)
+VO_HDN void epnp_prepare(const EpnpWork& w, const double* ut, double* l_6x10 /*60*/, double* rho /*6*/) {
   // compute_L_6x10, compute_rho
-  double l_6x10[60], rho[6];
   {
     const double* v[4] = {ut + 12 * 11, ut + 12 * 10, ut + 12 * 9, ut + 12 * 8};
     double dv[4][6][3];
@@ -700,78 +846,60 @@ VO_HDN void epnp5(const float* obj /*15*/, const float* img /*10*/, const Intrin
     rho[5] = epnp_dist2(w.cws[2], w.cws[3]);
   }
 
+}
+
+// variant N in {1,2,3}: betas (4, out), R, t; returns the mean reprojection error.
+// find_betas_approx_1 uses columns [0 1 3 6] of L, _2 columns [0 1 2], _3 columns [0 1 2 3 4].
+VO_HDN double epnp_variant(int N, const EpnpWork& w, const Intrinsics& K, const double* ut, const double* l_6x10,
+                           const double* rho, double* betas, double R[3][3], double t[3]) {
+  const int ncol = N == 1 ? 4 : (N == 2 ? 3 : 5);
+  double l[30], bx[5] = {0, 0, 0, 0, 0};
+  for (int i = 0; i < 6; i++)
+    for (int j = 0; j < ncol; j++) {
+      const int col = N == 1 ? (j == 0 ? 0 : j == 1 ? 1 : j == 2 ? 3 : 6) : j;
+      l[i * ncol + j] = l_6x10[i * 10 + col];
+    }
+  solve_svd_6xn(l, rho, bx, ncol);
+  if (N == 1) {
+    if (bx[0] < 0) {
+      betas[0] = sqrt(-bx[0]);
+      betas[1] = -bx[1] / betas[0];
+      betas[2] = -bx[2] / betas[0];
+      betas[3] = -bx[3] / betas[0];
+    } else {
+      betas[0] = sqrt(bx[0]);
+      betas[1] = bx[1] / betas[0];
+      betas[2] = bx[2] / betas[0];
+      betas[3] = bx[3] / betas[0];
+    }
+  } else {
+    if (bx[0] < 0) {
+      betas[0] = sqrt(-bx[0]);
+      betas[1] = (bx[2] < 0) ? sqrt(-bx[2]) : 0.0;
+    } else {
+      betas[0] = sqrt(bx[0]);
+      betas[1] = (bx[2] > 0) ? sqrt(bx[2]) : 0.0;
+    }
+    if (bx[1] < 0) betas[0] = -betas[0];
+    betas[2] = N == 2 ? 0.0 : bx[3] / betas[0];
+    betas[3] = 0.0;
+  }
+  epnp_gauss_newton(l_6x10, rho, betas);
+  return epnp_compute_R_and_t(w, K, ut, betas, R, t);
+}
+
+VO_HDN void epnp5_back(const EpnpWork& w, const Intrinsics& K, const double* ut, double Rout[9], double tout[3],
+                       double* dbg = nullptr) {
+  double l_6x10[60], rho[6];
+  epnp_prepare(w, ut, l_6x10, rho);
   double Betas[4][4], rep_errors[4];
   double Rs[4][3][3], ts[4][3];
-
-  {  // find_betas_approx_1: betas10 columns [0 1 3 6]
-    double l[24], b4[4];
-    for (int i = 0; i < 6; i++) {
-      l[i * 4 + 0] = l_6x10[i * 10 + 0];
-      l[i * 4 + 1] = l_6x10[i * 10 + 1];
-      l[i * 4 + 2] = l_6x10[i * 10 + 3];
-      l[i * 4 + 3] = l_6x10[i * 10 + 6];
-    }
-    solve_svd<6, 4>(l, rho, b4);
-    double* betas = Betas[1];
-    if (b4[0] < 0) {
-      betas[0] = sqrt(-b4[0]);
-      betas[1] = -b4[1] / betas[0];
-      betas[2] = -b4[2] / betas[0];
-      betas[3] = -b4[3] / betas[0];
-    } else {
-      betas[0] = sqrt(b4[0]);
-      betas[1] = b4[1] / betas[0];
-      betas[2] = b4[2] / betas[0];
-      betas[3] = b4[3] / betas[0];
-    }
-  }
-  epnp_gauss_newton(l_6x10, rho, Betas[1]);
-  rep_errors[1] = epnp_compute_R_and_t(w, K, ut, Betas[1], Rs[1], ts[1]);
-
-  {  // find_betas_approx_2: columns [0 1 2]
-    double l[18], b3[3];
-    for (int i = 0; i < 6; i++) {
-      l[i * 3 + 0] = l_6x10[i * 10 + 0];
-      l[i * 3 + 1] = l_6x10[i * 10 + 1];
-      l[i * 3 + 2] = l_6x10[i * 10 + 2];
-    }
-    solve_svd<6, 3>(l, rho, b3);
-    double* betas = Betas[2];
-    if (b3[0] < 0) {
-      betas[0] = sqrt(-b3[0]);
-      betas[1] = (b3[2] < 0) ? sqrt(-b3[2]) : 0.0;
-    } else {
-      betas[0] = sqrt(b3[0]);
-      betas[1] = (b3[2] > 0) ? sqrt(b3[2]) : 0.0;
-    }
-    if (b3[1] < 0) betas[0] = -betas[0];
-    betas[2] = 0.0;
-    betas[3] = 0.0;
-  }
-  epnp_gauss_newton(l_6x10, rho, Betas[2]);
-  rep_errors[2] = epnp_compute_R_and_t(w, K, ut, Betas[2], Rs[2], ts[2]);
-
-  {  // find_betas_approx_3: columns [0 1 2 3 4]
-    double l[30], b5[5];
-    for (int i = 0; i < 6; i++)
-      for (int j = 0; j < 5; j++) l[i * 5 + j] = l_6x10[i * 10 + j];
-    solve_svd<6, 5>(l, rho, b5);
-    double* betas = Betas[3];
-    if (b5[0] < 0) {
-      betas[0] = sqrt(-b5[0]);
-      betas[1] = (b5[2] < 0) ? sqrt(-b5[2]) : 0.0;
-    } else {
-      betas[0] = sqrt(b5[0]);
-      betas[1] = (b5[2] > 0) ? sqrt(b5[2]) : 0.0;
-    }
-    if (b5[1] < 0) betas[0] = -betas[0];
-    betas[2] = b5[3] / betas[0];
-    betas[3] = 0.0;
-  }
-  epnp_gauss_newton(l_6x10, rho, Betas[3]);
-  rep_errors[3] = epnp_compute_R_and_t(w, K, ut, Betas[3], Rs[3], ts[3]);
-
+  for (int N = 1; N <= 3; N++) rep_errors[N] = epnp_variant(N, w, K, ut, l_6x10, rho, Betas[N], Rs[N], ts[N]);
   if (dbg) {
+    for (int i = 0; i < 10; i++) dbg[i] = w.us[i];
+    for (int i = 0; i < 12; i++) dbg[10 + i] = w.cws[i / 3][i % 3];
+    for (int i = 0; i < 20; i++) dbg[22 + i] = w.alphas[i];
+    for (int i = 0; i < 144; i++) dbg[186 + i] = ut[i];
     for (int i = 0; i < 60; i++) dbg[342 + i] = l_6x10[i];
     for (int i = 0; i < 6; i++) dbg[402 + i] = rho[i];
     for (int i = 0; i < 3; i++) dbg[408 + i] = rep_errors[1 + i];
@@ -785,6 +913,21 @@ VO_HDN void epnp5(const float* obj /*15*/, const float* img /*10*/, const Intrin
     tout[i] = ts[N][i];
     for (int j = 0; j < 3; j++) Rout[i * 3 + j] = Rs[N][i][j];
   }
+}
+
+// Returns R (row-major) and t.  dbg (>= 420 doubles, optional): intermediates for parity debugging.
+template <bool FMA_MTM>
+VO_HDN void epnp5(const float* obj /*15*/, const float* img /*10*/, const Intrinsics& K, double Rout[9], double tout[3],
+                  double* dbg = nullptr) {
+  EpnpWork w;
+  double mtm[144], d[12], ut[144];
+  epnp5_front<FMA_MTM>(obj, img, K, w, mtm);
+  if (dbg)
+    for (int i = 0; i < 144; i++) dbg[42 + i] = mtm[i];
+  svd_square_ut_only<12>(mtm, d, ut);
+  if (dbg)
+    for (int i = 0; i < 12; i++) dbg[330 + i] = d[i];
+  epnp5_back(w, K, ut, Rout, tout, dbg);
 }
 
 // ---------------------------------------------------------------------------------------

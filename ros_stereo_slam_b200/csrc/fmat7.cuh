@@ -85,14 +85,19 @@ VO_HD int solve_cubic(const double* coef, double* r) {
   return n;
 }
 
-// FMEstimatorCallback::run7Point on 7 float correspondences -> up to 3 F (row-major 3x3
-// each, written consecutively).  Returns the number of models.
-VO_HDN int fmat_7point(const float* m1 /*14*/, const float* m2 /*14*/, double* fmatrix /*27*/) {
-  double a[7 * 9], w[7], v[9 * 9], c[4], r[3] = {0, 0, 0};
-  double *f1, *f2;
-  double t0, t1, t2;
-  int i, k, n;
+// FMEstimatorCallback::run7Point, split at its SVD like EPnP (see jacobi_warp.cuh):
+//   front: Hartley normalisation + the 7x9 design matrix written into the 9x9 buffer `v`
+//          (rows 7, 8 zeroed); returns false for a degenerate sample (0 models);
+//   SVD  : SVDecomp(A (7x9), W, U, Vt, MODIFY_A + FULL_UV).  m < n, so OpenCV runs the Jacobi on
+//          the 7 rows of A itself (length 9), completes rows 7 and 8 of the 9x9 with its
+//          pseudo-random Gram-Schmidt vectors, and returns that 9x9 as Vt (U is never used);
+//   back : cubic in the null-space parameter, up to 3 models, de-normalisation.
+struct FmatNorm {
+  double m1cx, m1cy, m2cx, m2cy, scale1, scale2;
+};
 
+VO_HDN bool fmat_7point_front(const float* m1 /*14*/, const float* m2 /*14*/, double* v /*81*/, FmatNorm& nm) {
+  int i;
   // Hartley normalisation of both point sets (centroid to origin, mean distance sqrt(2))
   double m1cx = 0, m1cy = 0, m2cx = 0, m2cy = 0, t, scale1 = 0, scale2 = 0;
   for (i = 0; i < 7; i++) {
@@ -111,33 +116,34 @@ VO_HDN int fmat_7point(const float* m1 /*14*/, const float* m2 /*14*/, double* f
   }
   scale1 *= t;
   scale2 *= t;
-  if (scale1 < FLT_EPSILON || scale2 < FLT_EPSILON) return 0;
+  if (scale1 < FLT_EPSILON || scale2 < FLT_EPSILON) return false;
   scale1 = sqrt(2.) / scale1;
   scale2 = sqrt(2.) / scale2;
+  nm.m1cx = m1cx; nm.m1cy = m1cy; nm.m2cx = m2cx; nm.m2cy = m2cy; nm.scale1 = scale1; nm.scale2 = scale2;
 
   for (i = 0; i < 7; i++) {
     double x0 = (m1[i * 2] - m1cx) * scale1, y0 = (m1[i * 2 + 1] - m1cy) * scale1;
     double x1 = (m2[i * 2] - m2cx) * scale2, y1 = (m2[i * 2 + 1] - m2cy) * scale2;
-    a[i * 9 + 0] = x1 * x0;
-    a[i * 9 + 1] = x1 * y0;
-    a[i * 9 + 2] = x1;
-    a[i * 9 + 3] = y1 * x0;
-    a[i * 9 + 4] = y1 * y0;
-    a[i * 9 + 5] = y1;
-    a[i * 9 + 6] = x0;
-    a[i * 9 + 7] = y0;
-    a[i * 9 + 8] = 1;
+    v[i * 9 + 0] = x1 * x0;
+    v[i * 9 + 1] = x1 * y0;
+    v[i * 9 + 2] = x1;
+    v[i * 9 + 3] = y1 * x0;
+    v[i * 9 + 4] = y1 * y0;
+    v[i * 9 + 5] = y1;
+    v[i * 9 + 6] = x0;
+    v[i * 9 + 7] = y0;
+    v[i * 9 + 8] = 1;
   }
+  for (i = 63; i < 81; i++) v[i] = 0;
+  return true;
+}
 
-  // SVDecomp(A (7x9), W, U, Vt, MODIFY_A + FULL_UV): m < n, so OpenCV runs the Jacobi on the
-  // 7 rows of A itself (length 9), completes rows 7 and 8 of the 9x9 with its pseudo-random
-  // Gram-Schmidt vectors, and returns that 9x9 as Vt.
-  {
-    double vv[7 * 7];
-    for (i = 0; i < 63; i++) v[i] = a[i];
-    for (i = 63; i < 81; i++) v[i] = 0;
-    jacobi_svd<9, 7, 9>(v, w, vv);
-  }
+VO_HDN int fmat_7point_back(double* v /*81: Vt*/, const FmatNorm& nm, double* fmatrix /*27*/) {
+  double c[4], r[3] = {0, 0, 0};
+  double *f1, *f2;
+  double t0, t1, t2;
+  int i, k, n;
+  const double m1cx = nm.m1cx, m1cy = nm.m1cy, m2cx = nm.m2cx, m2cy = nm.m2cy, scale1 = nm.scale1, scale2 = nm.scale2;
   f1 = v + 7 * 9;
   f2 = v + 8 * 9;
 
@@ -202,6 +208,15 @@ VO_HDN int fmat_7point(const float* m1 /*14*/, const float* m2 /*14*/, double* f
     for (i = 0; i < 9; i++) fmatrix[i] = out[i];
   }
   return n;
+}
+
+// up to 3 F (row-major 3x3 each, written consecutively); returns the number of models
+VO_HDN int fmat_7point(const float* m1 /*14*/, const float* m2 /*14*/, double* fmatrix /*27*/) {
+  double v[81], w[7];
+  FmatNorm nm;
+  if (!fmat_7point_front(m1, m2, v, nm)) return 0;
+  jacobi_svd<9, 7, 9, false>(v, w, v);   // U (= V of the transposed problem) is not needed
+  return fmat_7point_back(v, nm, fmatrix);
 }
 
 }  // namespace vo

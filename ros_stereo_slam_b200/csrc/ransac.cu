@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "cvmath.cuh"
 #include "fmat7.cuh"
+#include "jacobi_warp.cuh"
 
 namespace vo {
 
@@ -22,82 +23,172 @@ constexpr int PNP_STRIDE = 16;  // doubles per PnP model: rvec(3) tvec(3) R(9) p
 constexpr int F_STRIDE = 9;     // doubles per F model (3 per sample)
 
 // ================================================================ hypothesis generation
-// One thread per minimal sample, SOLVE_TPB samples per CTA (one partially filled warp).  The
-// solvers are long dependent FP64 chains (Jacobi sweeps) over ~5 KB of per-thread local
-// arrays, i.e. latency-bound: small CTAs spread them over all SMs.  Measured on B200: one
-// sample per warp (lane 0 only) is 3x SLOWER than 8 per warp, because local memory is
-// lane-interleaved and a lone lane uses 4 of every 32-byte sector, so the stacks of the
-// co-resident warps no longer fit L1.
-constexpr int SOLVE_TPB_MAX = 32;
-static int solve_tpb() {
-  static int v = 0;
-  if (!v) {
-    const char* e = getenv("VO_SOLVE_TPB");
-    v = e ? atoi(e) : 8;
-    if (v < 1 || v > SOLVE_TPB_MAX) v = 8;
-  }
-  return v;
-}
+// One WARP per minimal sample.  The solvers are long dependent FP64 chains (each Jacobi rotation
+// carries 3 divides and 3 square roots), i.e. latency-bound: lane 0 runs the scalar parts, and
+// the sweep phase of the big SVD (12x12 for EPnP, 7 rows x 9 for the 7-point solver) -- ~60 % of
+// the chain -- is executed by the whole warp as a wavefront over independent row pairs
+// (jacobi_warp.cuh), with bit-identical results.  The row matrix lives in shared memory.
+constexpr int SOLVE_WARPS = 4;
 
-__global__ void __launch_bounds__(SOLVE_TPB_MAX)
+__global__ void __launch_bounds__(SOLVE_WARPS * 32)
 fmat_solve_kernel(const float2* __restrict__ m1, const float2* __restrict__ m2, const int32_t* __restrict__ samples,
                   int h, double* __restrict__ models, int32_t* __restrict__ counts) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= h) return;
-  float a[14], b[14];
+  __shared__ double s_v[SOLVE_WARPS][81];
+  __shared__ double s_w[SOLVE_WARPS][8];
+  __shared__ int s_ok[SOLVE_WARPS];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int s = blockIdx.x * SOLVE_WARPS + wid;
+  if (s >= h) return;   // warp-uniform
+  double* v = s_v[wid];
+  double* W = s_w[wid];
+  FmatNorm nm;
+  if (lane == 0) {
+    float a[14], b[14];
 #pragma unroll
-  for (int i = 0; i < 7; i++) {
-    const int idx = samples[s * 7 + i];
-    const float2 p = m1[idx], q = m2[idx];
-    a[2 * i] = p.x; a[2 * i + 1] = p.y;
-    b[2 * i] = q.x; b[2 * i + 1] = q.y;
+    for (int i = 0; i < 7; i++) {
+      const int idx = samples[s * 7 + i];
+      const float2 p = m1[idx], q = m2[idx];
+      a[2 * i] = p.x; a[2 * i + 1] = p.y;
+      b[2 * i] = q.x; b[2 * i + 1] = q.y;
+    }
+    const bool ok = fmat_7point_front(a, b, v, nm);
+    s_ok[wid] = ok;
+    if (ok)
+      for (int i = 0; i < 7; i++) {
+        double sd = 0;
+        for (int k = 0; k < 9; k++) {
+          const double t = v[i * 9 + k];
+          sd += t * t;
+        }
+        W[i] = sd;
+      }
   }
-  double F[27];
-  int n = fmat_7point(a, b, F);
-  if (n < 0 || n > 3) n = 0;
-  for (int k = 0; k < 3; k++) {
-    counts[s * 3 + k] = k < n ? 0 : -1;
-    if (k < n)
-      for (int i = 0; i < 9; i++) models[(size_t)(s * 3 + k) * F_STRIDE + i] = F[k * 9 + i];
+  __syncwarp();
+  const bool ok = s_ok[wid] != 0;
+  if (ok) jacobi_sweeps_warp<9, 7>(v, W, lane);
+  if (lane == 0) {
+    double F[27];
+    int n = 0;
+    if (ok) {
+      double w[7];
+      jacobi_svd<9, 7, 9, false, true>(v, w, v);   // norms, ordering, completion of rows 7 and 8
+      n = fmat_7point_back(v, nm, F);
+      if (n < 0 || n > 3) n = 0;
+    }
+    for (int k = 0; k < 3; k++) {
+      counts[s * 3 + k] = k < n ? 0 : -1;
+      if (k < n)
+        for (int i = 0; i < 9; i++) models[(size_t)(s * 3 + k) * F_STRIDE + i] = F[k * 9 + i];
+    }
   }
 }
 
-__global__ void __launch_bounds__(SOLVE_TPB_MAX)
+// EPnP-5 per warp.  Lane roles: lane 0 = scalar parts; all lanes = the 78 entries of MtM
+// (each a sequential 10-term sum, as OpenCV's mulTransposed), the 12 row norms and the
+// wavefront Jacobi sweeps; lanes 0..2 = the three independent beta initialisations N = 1,2,3
+// with their Gauss-Newton polish and Horn alignment (one shared instruction stream).
+struct PnpWarpSmem {
+  double at[144];      // MtM -> U^T
+  double W[12];
+  double M[120];       // 10x12 design matrix; reused for l_6x10 (60) + rho (6) afterwards
+  EpnpWork work;
+  double var[3][13];   // per variant: reprojection error, R (9), t (3)
+};
+
+__global__ void __launch_bounds__(SOLVE_WARPS * 32)
 pnp_solve_kernel(const float3* __restrict__ xyz, const float2* __restrict__ xy, const int32_t* __restrict__ samples,
                  int h, Intrinsics K, double* __restrict__ models, int32_t* __restrict__ counts) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= h) return;
-  float obj[15], img[10];
+  __shared__ PnpWarpSmem sm_all[SOLVE_WARPS];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int s = blockIdx.x * SOLVE_WARPS + wid;
+  if (s >= h) return;   // warp-uniform
+  PnpWarpSmem& sm = sm_all[wid];
+  double* at = sm.at;
+  double* W = sm.W;
+  if (lane == 0) {
+    float obj[15], img[10];
 #pragma unroll
-  for (int i = 0; i < 5; i++) {
-    const int idx = samples[s * 5 + i];
-    const float3 p = xyz[idx];
-    const float2 q = xy[idx];
-    obj[3 * i] = p.x; obj[3 * i + 1] = p.y; obj[3 * i + 2] = p.z;
-    img[2 * i] = q.x; img[2 * i + 1] = q.y;
+    for (int i = 0; i < 5; i++) {
+      const int idx = samples[s * 5 + i];
+      const float3 p = xyz[idx];
+      const float2 q = xy[idx];
+      obj[3 * i] = p.x; obj[3 * i + 1] = p.y; obj[3 * i + 2] = p.z;
+      img[2 * i] = q.x; img[2 * i + 1] = q.y;
+    }
+    epnp5_front_M<false>(obj, img, K, sm.work, sm.M);
   }
-  double R[9], t[3], rvec[3], R2[9];
-  epnp5<false>(obj, img, K, R, t);
-  rodrigues_mat2vec(R, rvec);       // the RANSAC model is (rvec, tvec) ...
-  rodrigues_vec2mat(rvec, R2);      // ... and projectPoints converts it back
-  double* m = models + (size_t)s * PNP_STRIDE;
-  for (int i = 0; i < 3; i++) {
-    m[i] = rvec[i];
-    m[3 + i] = t[i];
+  __syncwarp();
+  // MtM = M^T M: upper triangle, one entry per lane and pass, mirrored (it is its own transpose,
+  // so OpenCV's temp_a = MtM^T is `at` itself)
+  for (int e = lane; e < 78; e += 32) {
+    int i = 0, rem = e;
+    while (rem >= 12 - i) {
+      rem -= 12 - i;
+      i++;
+    }
+    const int j = i + rem;
+    double s0 = 0;
+#pragma unroll
+    for (int k = 0; k < 10; k++) s0 += sm.M[k * 12 + i] * sm.M[k * 12 + j];
+    at[i * 12 + j] = s0;
+    at[j * 12 + i] = s0;
   }
-  for (int i = 0; i < 9; i++) m[6 + i] = R2[i];
-  m[15] = 0;
-  counts[s] = 0;
+  __syncwarp();
+  if (lane < 12) {
+    double sd = 0;
+#pragma unroll
+    for (int k = 0; k < 12; k++) {
+      const double t = at[lane * 12 + k];
+      sd += t * t;
+    }
+    W[lane] = sd;
+  }
+  __syncwarp();
+  jacobi_sweeps_warp<12, 12>(at, W, lane);
+  double* l_6x10 = sm.M;
+  double* rho = sm.M + 60;
+  if (lane == 0) {
+    double d[12];
+    jacobi_svd<12, 12, 12, false, true>(at, d, at);   // norms, ordering, row normalisation -> U^T
+    epnp_prepare(sm.work, at, l_6x10, rho);
+  }
+  __syncwarp();
+  if (lane < 3) {
+    double betas[4], R[3][3], t[3];
+    const double rep = epnp_variant(lane + 1, sm.work, K, at, l_6x10, rho, betas, R, t);
+    double* o = sm.var[lane];
+    o[0] = rep;
+    for (int i = 0; i < 3; i++) {
+      o[10 + i] = t[i];
+      for (int j = 0; j < 3; j++) o[1 + i * 3 + j] = R[i][j];
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    int N = 1;
+    if (sm.var[1][0] < sm.var[0][0]) N = 2;
+    if (sm.var[2][0] < sm.var[N - 1][0]) N = 3;
+    const double* o = sm.var[N - 1];
+    double R[9], t[3], rvec[3], R2[9];
+    for (int i = 0; i < 9; i++) R[i] = o[1 + i];
+    for (int i = 0; i < 3; i++) t[i] = o[10 + i];
+    rodrigues_mat2vec(R, rvec);       // the RANSAC model is (rvec, tvec) ...
+    rodrigues_vec2mat(rvec, R2);      // ... and projectPoints converts it back
+    double* m = models + (size_t)s * PNP_STRIDE;
+    for (int i = 0; i < 3; i++) {
+      m[i] = rvec[i];
+      m[3 + i] = t[i];
+    }
+    for (int i = 0; i < 9; i++) m[6 + i] = R2[i];
+    m[15] = 0;
+    counts[s] = 0;
+  }
 }
 
 // debug: one EPnP on the device with intermediates (parity investigations only)
 __global__ void epnp_debug_kernel(const float* obj, const float* img, Intrinsics K, double* dbg) {
   double R[9], t[3];
-#ifdef VO_NO_EPNP_DBG
-  epnp5<false>(obj, img, K, R, t);
-#else
   epnp5<false>(obj, img, K, R, t, dbg);
-#endif
   for (int i = 0; i < 9; i++) dbg[420 + i] = R[i];
   for (int i = 0; i < 3; i++) dbg[429 + i] = t[i];
 }
@@ -351,7 +442,7 @@ int fmat_solve_launch(vo_ctx* c, const float2* m1, const float2* m2, const int32
   if (h <= 0) return VO_OK;
   {
     LaunchScope ls(c, VO_K_FMAT_SOLVE);
-    fmat_solve_kernel<<<div_up(h, solve_tpb()), solve_tpb(), 0, c->stream>>>(m1, m2, d_samples, h, d_models, d_counts);
+    fmat_solve_kernel<<<div_up(h, SOLVE_WARPS), SOLVE_WARPS * 32, 0, c->stream>>>(m1, m2, d_samples, h, d_models, d_counts);
   }
   VO_CUDA(cudaGetLastError());
   return VO_OK;
@@ -385,7 +476,7 @@ int pnp_solve_launch(vo_ctx* c, const float3* xyz, const float2* xy, const int32
   if (h <= 0) return VO_OK;
   {
     LaunchScope ls(c, VO_K_PNP_SOLVE);
-    pnp_solve_kernel<<<div_up(h, solve_tpb()), solve_tpb(), 0, c->stream>>>(xyz, xy, d_samples, h, intr(c), d_models,
+    pnp_solve_kernel<<<div_up(h, SOLVE_WARPS), SOLVE_WARPS * 32, 0, c->stream>>>(xyz, xy, d_samples, h, intr(c), d_models,
                                                                        d_counts);
   }
   VO_CUDA(cudaGetLastError());

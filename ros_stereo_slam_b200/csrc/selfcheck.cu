@@ -49,6 +49,10 @@ __global__ void selfcheck_kernel(const SelfCase* cases, int n, Intrinsics K, con
 }
 
 int selfcheck_run(vo_ctx* c) {
+#ifdef VO_NO_SELFCHECK   // instrumented debug builds only (tools/); never defined by build.py
+  (void)c;
+  return VO_OK;
+#endif
   const Intrinsics K{c->p.fx, c->p.fy, c->p.cx, c->p.cy};
   double P[24];
   {
@@ -106,6 +110,59 @@ int selfcheck_run(vo_ctx* c) {
   cudaFree(d_cases);
   cudaFree(d_P);
   cudaFree(d_out);
+  // ---- the production RANSAC solve kernels (warp-cooperative Jacobi) on the same cases
+  int bad_prod = 0;
+  double worst_prod_f = 0;
+  {
+    std::vector<float> xyz(SC_N * 15), xy(SC_N * 10), f1(SC_N * 14), f2(SC_N * 14);
+    std::vector<int32_t> s5(SC_N * 5), s7(SC_N * 7);
+    for (int s = 0; s < SC_N; s++) {
+      memcpy(&xyz[s * 15], cases[s].obj, 15 * sizeof(float));
+      memcpy(&xy[s * 10], cases[s].img, 10 * sizeof(float));
+      memcpy(&f1[s * 14], cases[s].m1, 14 * sizeof(float));
+      memcpy(&f2[s * 14], cases[s].m2, 14 * sizeof(float));
+      for (int i = 0; i < 5; i++) s5[s * 5 + i] = s * 5 + i;
+      for (int i = 0; i < 7; i++) s7[s * 7 + i] = s * 7 + i;
+    }
+    VO_CUDA(cudaMemcpyAsync(c->d_f_xyz, xyz.data(), xyz.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    VO_CUDA(cudaMemcpyAsync(c->d_f_trk, xy.data(), xy.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    VO_CUDA(cudaMemcpyAsync(c->d_samples, s5.data(), s5.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    VO_TRY(pnp_solve_launch(c, c->d_f_xyz, c->d_f_trk, c->d_samples, SC_N, c->d_models, c->d_counts));
+    std::vector<double> pm((size_t)SC_N * 16);
+    VO_CUDA(cudaMemcpyAsync(pm.data(), c->d_models, pm.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+    VO_CUDA(cudaStreamSynchronize(c->stream));
+    for (int s = 0; s < SC_N; s++) {
+      // tvec has no libm on its path: bit comparison.  rvec goes through acos/sin/cos.
+      const double* h = host.data() + (size_t)s * SC_STRIDE;
+      if (memcmp(h + 9, &pm[(size_t)s * 16 + 3], 3 * sizeof(double)) != 0) bad_prod++;
+      double rv[3];
+      rodrigues_mat2vec(h, rv);
+      for (int i = 0; i < 3; i++)
+        if (fabs(rv[i] - pm[(size_t)s * 16 + i]) > 1e-12) bad_prod++;
+    }
+    VO_CUDA(cudaMemcpyAsync(c->d_c_ref, f1.data(), f1.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    VO_CUDA(cudaMemcpyAsync(c->d_c_trk, f2.data(), f2.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    VO_CUDA(cudaMemcpyAsync(c->d_samples, s7.data(), s7.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    VO_TRY(fmat_solve_launch(c, c->d_c_ref, c->d_c_trk, c->d_samples, SC_N, c->d_models, c->d_counts));
+    std::vector<double> fm((size_t)SC_N * 27);
+    std::vector<int32_t> fc((size_t)SC_N * 3);
+    VO_CUDA(cudaMemcpyAsync(fm.data(), c->d_models, fm.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+    VO_CUDA(cudaMemcpyAsync(fc.data(), c->d_counts, fc.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+    VO_CUDA(cudaStreamSynchronize(c->stream));
+    for (int s = 0; s < SC_N; s++) {
+      const double* h = host.data() + (size_t)s * SC_STRIDE + SC_EPNP;
+      const int n = (int)h[0];
+      for (int k = 0; k < 3; k++) {
+        if ((fc[s * 3 + k] >= 0) != (k < n)) bad_prod++;
+        if (k < n)
+          for (int i = 0; i < 9; i++) {
+            const double a = h[1 + k * 9 + i], b = fm[(size_t)(s * 3 + k) * 9 + i];
+            const double e = fabs(a - b) / fmax(fabs(a), 1e-12);
+            if (e > worst_prod_f) worst_prod_f = e;
+          }
+      }
+    }
+  }
   int bad_epnp = 0, bad_tri = 0, bad_f = 0;
   double worst_f = 0;
   for (int s = 0; s < SC_N; s++) {
@@ -122,10 +179,11 @@ int selfcheck_run(vo_ctx* c) {
       if (e > worst_f) worst_f = e;
     }
   }
-  if (bad_epnp || bad_tri || bad_f || worst_f > 1e-9) {
+  if (bad_epnp || bad_tri || bad_f || worst_f > 1e-9 || bad_prod || worst_prod_f > 1e-9) {
     set_error("numerics self-check failed: device != host for %d/%d EPnP, %d/%d triangulation, %d/%d 7-point cases "
-              "(F rel err %.3g); this build of libvo_b200 must not be used",
-              bad_epnp, SC_N, bad_tri, SC_N, bad_f, SC_N, worst_f);
+              "(F rel err %.3g), %d mismatches in the production solve kernels (F rel err %.3g); this build of "
+              "libvo_b200 must not be used",
+              bad_epnp, SC_N, bad_tri, SC_N, bad_f, SC_N, worst_f, bad_prod, worst_prod_f);
     return VO_ERR_SELF_CHECK;
   }
   return VO_OK;
