@@ -396,8 +396,13 @@ static int draw_fmat_samples(CvRng& rng, const float* m1, const float* m2, int n
 // Device inputs m1, m2 (n points).  h_m1/h_m2: host copies for the collinearity check (unused
 // with a replay list).  On return d_sel holds (best, niters, best_count, records), d_mask the
 // best model's inlier mask.
+// `tail` (optional) enqueues the consumers of the mask (compaction, count read-back) BEFORE the
+// one host synchronisation of a round: OpenCV's adaptive stop almost always ends inside the first
+// chunk, so the mask of the first selection is final and no second round trip is needed; when it
+// is not, more chunks are evaluated and mask + tail are simply redone.
 static int run_fmat(vo_ctx* c, const float2* m1, const float2* m2, int n, double thr, double conf,
-                    const int32_t* replay, int n_replay, const float* h_m1, const float* h_m2) {
+                    const int32_t* replay, int n_replay, const float* h_m1, const float* h_m2,
+                    const std::function<int()>& tail = nullptr) {
   if (n < 15) {
     set_error("findFundamentalMat(FM_RANSAC) with %d < 15 points switches estimator in OpenCV; not supported", n);
     return VO_ERR_TOO_FEW_POINTS;
@@ -441,6 +446,8 @@ static int run_fmat(vo_ctx* c, const float2* m1, const float2* m2, int n, double
       }
     }
     VO_TRY(select_launch(c, c->d_counts, done, 3, 7, n, conf, max_iters, c->d_sel));
+    VO_TRY(fmat_mask_launch(c, m1, m2, n, c->d_models, c->d_sel, thr2, c->d_mask));
+    if (tail) VO_TRY(tail());
     VO_CUDA(cudaMemcpyAsync(c->h_sel, c->d_sel, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     VO_TRY(sync_stream(c));
     const int niters = c->h_sel[1];
@@ -448,7 +455,6 @@ static int run_fmat(vo_ctx* c, const float2* m1, const float2* m2, int n, double
     target = std::min(niters, H);
   }
   c->last_f_h = done;
-  VO_TRY(fmat_mask_launch(c, m1, m2, n, c->d_models, c->d_sel, thr2, c->d_mask));
   return VO_OK;
 }
 
@@ -496,8 +502,13 @@ static int run_pnp(vo_ctx* c, const float3* xyz, const float2* xy, int n, int it
       done += k;
     }
     VO_TRY(select_launch(c, c->d_counts, done, 1, 5, n, conf, max_iters, c->d_sel));
+    // consumers of the selection, enqueued before the single synchronisation of this round
+    VO_TRY(pnp_mask_launch(c, xyz, xy, n, c->d_models, c->d_sel, thr2, c->d_mask));
+    VO_TRY(compact_launch(c, c->d_mask, n, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, c->d_idx, 4));
+    VO_TRY(pnp_refine_launch(c, xyz, xy, c->d_idx, c->d_count + 4, c->d_models, c->d_sel, c->d_pose));
     VO_CUDA(cudaMemcpyAsync(c->h_sel, c->d_sel, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    VO_TRY(sync_stream(c));
+    VO_CUDA(cudaMemcpyAsync(c->h_pose, c->d_pose, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    VO_TRY(read_counts(c));
     const int niters = c->h_sel[1];
     if (done >= std::min(niters, H) || k <= 0) break;
     target = std::min(niters, H);
@@ -507,11 +518,6 @@ static int run_pnp(vo_ctx* c, const float3* xyz, const float2* xy, int n, int it
     set_error("solvePnPRansac: no hypothesis reached 5 inliers");
     return VO_ERR_NO_MODEL;
   }
-  VO_TRY(pnp_mask_launch(c, xyz, xy, n, c->d_models, c->d_sel, thr2, c->d_mask));
-  VO_TRY(compact_launch(c, c->d_mask, n, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, c->d_idx, 4));
-  VO_TRY(pnp_refine_launch(c, xyz, xy, c->d_idx, c->d_count + 4, c->d_models, c->d_sel, c->d_pose));
-  VO_CUDA(cudaMemcpyAsync(c->h_pose, c->d_pose, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  VO_TRY(read_counts(c));
   *n_inl_out = c->h_count[4];
   return VO_OK;
 }
@@ -519,32 +525,43 @@ static int run_pnp(vo_ctx* c, const float3* xyz, const float2* xy, int n, int it
 // ------------------------------------------------------------------------------------ stage pipelines (device)
 // LK slot_a -> slot_b of d_in (n points) + status compaction.  Optional xyz carried along.
 // Leaves survivors in d_c_ref / d_c_trk / d_c_xyz; *m = count (host, synchronised).
-static int lk_and_compact(vo_ctx* c, int slot_a, int slot_b, const float2* d_in, const float3* d_in_xyz, int n, int* m) {
+// pts_to_host: also bring the (at most n) surviving correspondences to c->h_pts in the same
+// synchronisation -- the F-matrix sampler needs them for OpenCV's collinearity subset check.
+static int lk_and_compact(vo_ctx* c, int slot_a, int slot_b, const float2* d_in, const float3* d_in_xyz, int n, int* m,
+                          bool pts_to_host = false) {
   *m = 0;
   if (n <= 0) return VO_OK;
   VO_TRY(lk_launch(c, slot_a, slot_b, d_in, n, c->d_xy_trk, c->d_status, c->d_err));
   VO_TRY(compact_launch(c, c->d_status, n, d_in, c->d_c_ref, c->d_xy_trk, c->d_c_trk, d_in_xyz, c->d_c_xyz, nullptr, 0));
+  if (pts_to_host) {
+    VO_CUDA(cudaMemcpyAsync(c->h_pts, c->d_c_ref, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
+    VO_CUDA(cudaMemcpyAsync(c->h_pts + (size_t)2 * c->cap, c->d_c_trk, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost,
+                            c->stream));
+  }
   VO_TRY(read_counts(c));
   *m = c->h_count[0];
   return VO_OK;
 }
 
 // F-RANSAC on d_c_* (m points) + mask compaction into d_f_*; *k = survivors.
-static int fmat_and_compact(vo_ctx* c, int m, double thr, bool with_xyz, int* k) {
+// have_host_pts: c->h_pts already holds the correspondences (lk_and_compact(pts_to_host)).
+static int fmat_and_compact(vo_ctx* c, int m, double thr, bool with_xyz, int* k, bool have_host_pts = false) {
   *k = 0;
   if (m <= 0) return VO_OK;
-  // host copies of the correspondences for the subset (collinearity) check
   float* h1 = c->h_pts;
   float* h2 = c->h_pts + (size_t)2 * c->cap;
-  VO_CUDA(cudaMemcpyAsync(h1, c->d_c_ref, (size_t)m * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
-  VO_CUDA(cudaMemcpyAsync(h2, c->d_c_trk, (size_t)m * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
-  VO_TRY(sync_stream(c));
-  int r = run_fmat(c, c->d_c_ref, c->d_c_trk, m, thr, c->p.f_conf, nullptr, 0, h1, h2);
-  if (r == VO_ERR_TOO_FEW_POINTS) return r;
-  VO_TRY(r);
-  VO_TRY(compact_launch(c, c->d_mask, m, c->d_c_ref, c->d_f_ref, c->d_c_trk, c->d_f_trk, with_xyz ? c->d_c_xyz : nullptr,
-                        c->d_f_xyz, nullptr, 1));
-  VO_TRY(read_counts(c));
+  if (!have_host_pts) {
+    VO_CUDA(cudaMemcpyAsync(h1, c->d_c_ref, (size_t)m * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
+    VO_CUDA(cudaMemcpyAsync(h2, c->d_c_trk, (size_t)m * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
+    VO_TRY(sync_stream(c));
+  }
+  auto tail = [&]() -> int {
+    VO_TRY(compact_launch(c, c->d_mask, m, c->d_c_ref, c->d_f_ref, c->d_c_trk, c->d_f_trk,
+                          with_xyz ? c->d_c_xyz : nullptr, c->d_f_xyz, nullptr, 1));
+    VO_CUDA(cudaMemcpyAsync(c->h_count, c->d_count, 16 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    return VO_OK;
+  };
+  VO_TRY(run_fmat(c, c->d_c_ref, c->d_c_trk, m, thr, c->p.f_conf, nullptr, 0, h1, h2, tail));
   *k = c->h_count[1];
   return VO_OK;
 }
@@ -573,8 +590,8 @@ static int stereo_pipeline(vo_ctx* c, int slot_l, int slot_r, const double* pose
   VO_TRY(grid_launch(c, c->p.height, c->p.width, c->p.grid_step, c->d_xy_in, &ng));
   if (n_grid_out) *n_grid_out = ng;
   int m = 0, k = 0;
-  VO_TRY(lk_and_compact(c, slot_l, slot_r, c->d_xy_in, nullptr, ng, &m));
-  VO_TRY(fmat_and_compact(c, m, c->p.f_thr_stereo, false, &k));
+  VO_TRY(lk_and_compact(c, slot_l, slot_r, c->d_xy_in, nullptr, ng, &m, true));
+  VO_TRY(fmat_and_compact(c, m, c->p.f_thr_stereo, false, &k, true));
   double P[36];
   make_projections(c->p, P);
   if (pose3x4) memcpy(P + 24, pose3x4, 12 * sizeof(double));
@@ -589,8 +606,8 @@ static int stereo_pipeline(vo_ctx* c, int slot_l, int slot_r, const double* pose
 static int track_pipeline(vo_ctx* c, int slot_ref, int slot_cur, const float2* d_ref_xy, const float3* d_ref_xyz, int n,
                           int* k) {
   int m = 0;
-  VO_TRY(lk_and_compact(c, slot_ref, slot_cur, d_ref_xy, d_ref_xyz, n, &m));
-  return fmat_and_compact(c, m, c->p.f_thr_temporal, true, k);
+  VO_TRY(lk_and_compact(c, slot_ref, slot_cur, d_ref_xy, d_ref_xyz, n, &m, true));
+  return fmat_and_compact(c, m, c->p.f_thr_temporal, true, k, true);
 }
 
 // two-attempt PnP on d_f_xyz / d_f_trk (k points); pose in h_pose, inliers in d_idx

@@ -144,7 +144,9 @@ pnp_refine_kernel(const float3* __restrict__ xyz, const float2* __restrict__ xy,
     if (state == 2) break;
     if (t == 0) rodrigues_with_jacobian(s_param, s_pj);
     __syncthreads();
-    const bool need_j = state == 0;
+    // J is accumulated on every pass: when a candidate is accepted, the next LM step needs J at
+    // exactly this parameter vector, and recomputing it would cost a second pass over the inliers
+    const bool need_j = true;
     double acc[NACC];
 #pragma unroll
     for (int k = 0; k < NACC; k++) acc[k] = 0;
@@ -219,8 +221,7 @@ pnp_refine_kernel(const float3* __restrict__ xyz, const float2* __restrict__ xy,
         solve6(A, JtErr, x);
         for (int i = 0; i < 6; i++) param[i] = prev_param[i] - x[i];
       };
-      if (state == 0) {
-        // CALC_J: JtJ, JtErr at param; step
+      auto take_normal_equations = [&]() {   // CvLevMarq CALC_J: JtJ, JtErr at `param`, then step
         int k = 0;
         for (int a = 0; a < 6; a++)
           for (int b = a; b < 6; b++) {
@@ -231,15 +232,18 @@ pnp_refine_kernel(const float3* __restrict__ xyz, const float2* __restrict__ xy,
         for (int a = 0; a < 6; a++) JtErr[a] = s_sum[21 + a];
         for (int i = 0; i < 6; i++) prev_param[i] = param[i];
         lm_step();
-        if (iters == 0) prev_err_norm = sqrt(s_sum[27]);
+      };
+      if (state == 0) {
+        take_normal_equations();
+        prev_err_norm = sqrt(s_sum[27]);   // iters == 0
         s_state = 1;
       } else {
-        // CHECK_ERR
+        // CHECK_ERR at the candidate `param`
         err_norm = sqrt(s_sum[27]);
         bool retry = false;
         if (err_norm > prev_err_norm) {
           if (++lambda_lg10 <= 16) {
-            lm_step();
+            lm_step();   // same JtJ / JtErr / prev_param, larger damping
             retry = true;
           }
         }
@@ -254,7 +258,7 @@ pnp_refine_kernel(const float3* __restrict__ xyz, const float2* __restrict__ xy,
             s_state = 2;
           } else {
             prev_err_norm = err_norm;
-            s_state = 0;
+            take_normal_equations();   // the sums of this very pass are J, err at the accepted param
           }
         }
       }
