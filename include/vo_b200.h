@@ -239,6 +239,9 @@ enum { VO_K_PYRAMID = 0, VO_K_LK = 1, VO_K_COMPACT = 2, VO_K_FMAT_SOLVE = 3, VO_
        VO_K_SELECT = 9, VO_K_MISC = 10, VO_K_COUNT = 11 };
 int vo_profile_enable(vo_ctx* ctx, int mask);
 int vo_profile_read(vo_ctx* ctx, int kernel, int64_t* launches, double* ms, int reset);
+/* timeline of the bracketed launches since the last vo_profile_read: rows of 4 floats
+ * (chain 0/1, kernel family, start ms relative to the first launch, duration ms) */
+int vo_debug_timeline(vo_ctx* ctx, float* rows, int cap, int* n);
 int64_t vo_launch_count(vo_ctx* ctx);          /* kernels launched by this ctx since creation */
 /* Cumulative LK work counters since vo_create: (point, level) pairs processed and LK iterations
  * executed -- the units of the LK roofline in DESIGN.md.  Take differences around a region. */

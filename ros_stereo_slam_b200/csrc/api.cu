@@ -65,7 +65,14 @@ static void prof_drain(vo_ctx* c) {
 
 static int alloc_chain(vo_ctx* c) {
   const vo_params* p = &c->p;
-  VO_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  {
+    // The primary chain carries the frame's critical path (tracking -> F -> PnP -> refine), made of
+    // short latency-bound kernels; the auxiliary chain carries the stereo LK that fills every SM.
+    // Without priorities the critical kernels queue behind the 4,570 CTAs of that LK launch.
+    int lo = 0, hi = 0;
+    VO_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    VO_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, c->is_aux ? lo : hi));
+  }
   const int cap = p->max_points;
   c->cap = cap;
   VO_CUDA(cudaMalloc(&c->d_xy_in, cap * sizeof(float2)));
@@ -1108,6 +1115,32 @@ int vo_profile_read(vo_ctx* c, int kernel, int64_t* launches, double* ms, int re
   if (reset) {
     c->prof.launches[kernel] = c->aux->prof.launches[kernel] = 0;
     c->prof.ms[kernel] = c->aux->prof.ms[kernel] = 0;
+  }
+  return VO_OK;
+}
+
+int vo_debug_timeline(vo_ctx* c, float* rows, int cap, int* n) {
+  CHECK_CTX(c);
+  if (!rows || !n) return VO_ERR_INVALID_ARG;
+  VO_TRY(sync_stream(c));
+  VO_TRY(sync_stream(c->aux));
+  *n = 0;
+  cudaEvent_t t0 = nullptr;
+  if (!c->prof.pending.empty()) t0 = c->prof.pending.front().a;
+  if (!t0) return VO_OK;
+  int chain = 0;
+  for (vo_ctx* k : {c, c->aux}) {
+    for (auto& pe : k->prof.pending) {
+      if (*n >= cap) break;
+      float st = 0, du = 0;
+      cudaEventSynchronize(pe.b);
+      cudaEventElapsedTime(&st, t0, pe.a);
+      cudaEventElapsedTime(&du, pe.a, pe.b);
+      float* r = rows + 4 * (*n);
+      r[0] = (float)chain; r[1] = (float)pe.kind; r[2] = st; r[3] = du;
+      (*n)++;
+    }
+    chain++;
   }
   return VO_OK;
 }

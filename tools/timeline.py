@@ -1,0 +1,21 @@
+"""Per-kernel timeline of one frame of the bench workload (both chains)."""
+import sys, os, ctypes as C
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from ros_stereo_slam_b200 import VisualFrontEnd, _lib
+fe = VisualFrontEnd(grid_step=5, pnp_iters=1024, kf_min_inliers=2**31 - 1, ransac_exhaustive=1)
+Ls = [fe.synth_render(0, i, 0) for i in range(8)]
+Rs = [fe.synth_render(0, i, 1) for i in range(8)]
+fe.seq_init(Ls[0], Rs[0])
+for i in range(1, 6):
+    fe.seq_track(Ls[i], Rs[i])
+fe.profile_enable("all"); fe.profile_read(reset=True)
+import time
+t0 = time.perf_counter(); fe.seq_track(Ls[6], Rs[6]); dt = time.perf_counter() - t0
+rows = np.zeros((512, 4), np.float32); n = C.c_int()
+_lib.check(fe.lib.vo_debug_timeline(fe.h, rows.ctypes.data_as(C.c_void_p), 512, C.byref(n)))
+rows = rows[:n.value]
+order = np.argsort(rows[:, 2])
+print("wall ms (with event overhead)", dt * 1e3)
+for r in rows[order]:
+    print("chain %d  %-12s start %7.3f  dur %6.3f  end %7.3f" % (int(r[0]), _lib.KERNELS[int(r[1])], r[2], r[3], r[2] + r[3]))
