@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-frames", type=int, default=8, help="frames of the bounded cpu_baseline sample")
+    ap.add_argument("--cpu-frames", type=int, default=100, help="frames of the bounded cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
     return ap.parse_args()
@@ -275,7 +275,10 @@ def run_ours(args):
             "hbm": {"achieved": round(lk_bytes / (lk_avg_ms * 1e-3) / 1e9, 2), "peak": hbm_peak, "unit": "GB/s",
                     "frac": round(lk_bytes / (lk_avg_ms * 1e-3) / 1e9 / hbm_peak, 5), "peak_source": hbm_src,
                     "note": "working set (~5 MB of pyramids) is L2-resident; HBM is not the bound"},
-            "traffic": None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of one lk_kernel launch (18,278 points) from the
+            # ncu --set full capture in profiles/r01_lk_kernel_final_ncu.txt; algorithmic bytes are 4.07 MB
+            "traffic": 4413184,
+            "algorithmic_bytes_per_launch": round(lk_bytes),
         }
         out = {
             "metric": "frames/sec for KLT+triangulate+PnP-RANSAC at 1241x376; Mkeypoints/s tracked",
@@ -305,11 +308,11 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             frames_np = []
-            ncpu = args.cpu_frames + 1
+            ncpu = min(args.cpu_frames, nf - 1) + 1
             buf = (C.c_uint8 * (2 * ncpu * img_bytes)).from_address(h_frames.value)
             arr = np.frombuffer(buf, np.uint8).reshape(ncpu, 2, HEIGHT, WIDTH)
             out["cpu_baseline"] = cpu_reference([arr[i, 0] for i in range(ncpu)], [arr[i, 1] for i in range(ncpu)],
-                                                args.cpu_frames)
+                                                ncpu - 1)
     lib.vo_free_dev(fe.h, d_frames)
     lib.vo_free_host(h_frames)
     fe.close()
@@ -388,9 +391,40 @@ def run_reference(args):
     print(json.dumps(out))
 
 
+class StdoutGuard:
+    """Everything libraries print to fd 1 during the run (e.g. NCCL's version banner) is sent to
+    stderr, so that the ONE JSON line is the only thing on stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
 if __name__ == "__main__":
     a = parse()
-    if a.impl == "reference":
-        run_reference(a)
-    else:
-        run_ours(a)
+    result = []
+    _print = print
+
+    def capture(line):
+        result.append(line)
+
+    import builtins
+    with StdoutGuard():
+        builtins.print = capture
+        try:
+            if a.impl == "reference":
+                run_reference(a)
+            else:
+                run_ours(a)
+        finally:
+            builtins.print = _print
+    for line in result:
+        _print(line, flush=True)
