@@ -88,17 +88,23 @@ constexpr int WARP_SMEM_WORDS = TILE_WORDS + DTILE_WORDS;
 constexpr int LK_WARPS = 4;
 
 // Stage the 22 x 28-byte patch whose (unaligned) origin is `a0` into `tile`; returns the byte
-// offset (0..3) of the origin inside the first staged word.
-__device__ __forceinline__ unsigned stage_patch(const uint8_t* a0, int pitch, unsigned* tile, int lane) {
+// offset (0..3) of the origin inside the first staged word.  lane_off = (lane/8)*(pitch/4) +
+// lane%8 and step = 4*(pitch/4) are per-level constants, so each load is one 64-bit pointer bump.
+__device__ __forceinline__ unsigned stage_patch(const uint8_t* a0, int lane_off, int step, unsigned* tile_lane,
+                                                bool col_ok, bool last_ok) {
   const uintptr_t a = reinterpret_cast<uintptr_t>(a0);
-  const unsigned* w = reinterpret_cast<const unsigned*>(a & ~uintptr_t(3));
-  const int wcol = lane & 7, r0 = lane >> 3, pw = pitch >> 2;
+  const unsigned* w = reinterpret_cast<const unsigned*>(a & ~uintptr_t(3)) + lane_off;
   __syncwarp();   // everyone is done reading the previous tile
+  unsigned v[6];
 #pragma unroll
   for (int i = 0; i < 6; i++) {
-    const int r = 4 * i + r0;
-    if (r < PROWS && wcol < 7) tile[r * PS + wcol] = __ldg(w + (size_t)r * pw + wcol);
+    v[i] = 0;
+    if (col_ok && (i < 5 || last_ok)) v[i] = __ldg(w);
+    w += step;
   }
+#pragma unroll
+  for (int i = 0; i < 6; i++)
+    if (col_ok && (i < 5 || last_ok)) tile_lane[i * 4 * PS] = v[i];
   __syncwarp();
   return (unsigned)(a & 3);
 }
@@ -145,9 +151,13 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
   if (warp >= n) return;
   unsigned* tile = smem + (threadIdx.x >> 5) * WARP_SMEM_WORDS;
   unsigned* dtile = tile + TILE_WORDS;
+  // staging role of this lane: row (lane/8) + 4i, word lane%8 (< 7) of the 22 x 7-word tile
+  unsigned* tile_lane = tile + (lane >> 3) * PS + (lane & 7);
+  const bool st_col_ok = (lane & 7) < 7, st_last_ok = (lane >> 3) < PROWS - 20;
   const float2 pt = prev_pts[warp];
   const float half_win = (WIN - 1) * 0.5f;
   const float FLT_SCALE = 1.f / (1 << 20);
+  const float eps_lo = (float)(eps_sq * (1.0 - 1e-5)), eps_hi = (float)(eps_sq * (1.0 + 1e-5));
 
   // this lane's two segments (fixed for the whole kernel)
   const int rowA = lane / SEGS_PER_ROW, colA = (lane - rowA * SEGS_PER_ROW) * SEG;
@@ -167,6 +177,8 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
     const PyrLevelView I = prev.lv[level];
     const PyrLevelView J = next.lv[level];
     const int pitch = I.pitch;
+    const int st_step = pitch;                              // 4 rows, in words: 4 * (pitch / 4)
+    const int st_off = (lane >> 3) * (pitch >> 2) + (lane & 7);
     const float scale = 1.f / (float)(1 << level);
     float px = __fmul_rn(pt.x, scale), py = __fmul_rn(pt.y, scale);
     float nx, ny;
@@ -198,7 +210,7 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
     int sA11 = 0, sA12 = 0, sA22 = 0, sC1 = 0, sC2 = 0;
     {
       const size_t o0 = (size_t)(ipy + PAD_Y) * pitch + (ipx + PAD_L);
-      const unsigned sh = stage_patch(I.img + o0, pitch, tile, lane);
+      const unsigned sh = stage_patch(I.img + o0, st_off, st_step, tile_lane, st_col_ok, st_last_ok);
       // derivative patch: 484 short2, row-coalesced (lane -> consecutive elements)
       {
         const unsigned* dsrc = reinterpret_cast<const unsigned*>(I.deriv + o0);
@@ -272,7 +284,8 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
         break;
       }
       lk_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), wt, wb, iw00, iw01, iw10, iw11);
-      const unsigned sh = stage_patch(J.img + (size_t)(iny + PAD_Y) * pitch + (inx + PAD_L), pitch, tile, lane);
+      const unsigned sh = stage_patch(J.img + ((iny + PAD_Y) * pitch + (inx + PAD_L)), st_off, st_step, tile_lane,
+                                      st_col_ok, st_last_ok);
       int sb1 = 0, sb2 = 0;
       {
         int jv[SEG];
@@ -302,7 +315,16 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
       ny = __fadd_rn(ny, dy);
       outx = __fadd_rn(nx, half_win);
       outy = __fadd_rn(ny, half_win);
-      if (__dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)) <= eps_sq) break;
+      {
+        // OpenCV tests (double)dx*dx + (double)dy*dy <= eps^2.  The float value of that sum is within
+        // 3 ulp of it, so the double evaluation is only needed inside a narrow band around eps^2.
+        const float s2 = fmaf(dx, dx, dy * dy);
+        bool conv;
+        if (s2 < eps_lo) conv = true;
+        else if (s2 > eps_hi) conv = false;
+        else conv = __dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)) <= eps_sq;
+        if (conv) break;
+      }
       if (j > 0 && (double)fabsf(__fadd_rn(dx, pdx)) < 0.01 && (double)fabsf(__fadd_rn(dy, pdy)) < 0.01) {
         outx = __fsub_rn(outx, __fmul_rn(dx, 0.5f));
         outy = __fsub_rn(outy, __fmul_rn(dy, 0.5f));
@@ -320,7 +342,8 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
         st = false;
       } else {
         lk_weights(__fsub_rn(fx, (float)inx), __fsub_rn(fy, (float)iny), wt, wb, iw00, iw01, iw10, iw11);
-        const unsigned sh = stage_patch(J.img + (size_t)(iny + PAD_Y) * pitch + (inx + PAD_L), pitch, tile, lane);
+        const unsigned sh = stage_patch(J.img + ((iny + PAD_Y) * pitch + (inx + PAD_L)), st_off, st_step, tile_lane,
+                                      st_col_ok, st_last_ok);
         int se = 0;
         int jv[SEG];
         seg_bilinear(tile, rowA, colA + sh, wt, wb, jv);
