@@ -109,6 +109,16 @@ static int alloc_chain(vo_ctx* c) {
   VO_CUDA(cudaMalloc(&c->d_pose, 16 * sizeof(double)));
   VO_CUDA(cudaMallocHost(&c->h_pose, 16 * sizeof(double)));
   VO_CUDA(cudaMalloc(&c->d_cam, 48 * sizeof(double)));
+  {
+    std::vector<uint32_t> raw(RNG_LEN);
+    CvRng rng(0xffffffffffffffffULL);
+    for (int i = 0; i < RNG_LEN; i++) raw[i] = rng.next();
+    VO_CUDA(cudaMalloc(&c->d_rng, RNG_LEN * sizeof(uint32_t)));
+    VO_CUDA(cudaMemcpy(c->d_rng, raw.data(), RNG_LEN * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    VO_CUDA(cudaMalloc(&c->d_flags, 8 * sizeof(int)));
+    VO_CUDA(cudaMemset(c->d_flags, 0, 8 * sizeof(int)));
+    VO_CUDA(cudaMallocHost(&c->h_flags, 8 * sizeof(int)));
+  }
   VO_CUDA(cudaMalloc(&c->d_lk_work, 2 * sizeof(unsigned long long)));
   VO_CUDA(cudaMallocHost(&c->h_lk_work, 2 * sizeof(unsigned long long)));
   VO_CUDA(cudaMemsetAsync(c->d_lk_work, 0, 2 * sizeof(unsigned long long), c->stream));
@@ -122,9 +132,9 @@ static void free_chain(vo_ctx* c) {
   void* dev[] = {c->d_xy_in, c->d_xy_trk, c->d_status, c->d_err, c->d_xyz_in, c->d_c_ref, c->d_c_trk, c->d_c_xyz,
                  c->d_f_ref, c->d_f_trk, c->d_f_xyz, c->d_xyz_tmp, c->d_mask, c->d_idx, c->d_seq_xy, c->d_seq_xyz,
                  c->d_count, c->d_tile_state, c->d_samples, c->d_models, c->d_counts, c->d_sel, c->d_pose, c->d_cam,
-                 c->d_lk_work};
+                 c->d_lk_work, c->d_rng, c->d_flags};
   for (void* p : dev) cudaFree(p);
-  void* host[] = {c->h_count, c->h_pts, c->h_samples, c->h_sel, c->h_pose, c->h_lk_work};
+  void* host[] = {c->h_count, c->h_pts, c->h_samples, c->h_sel, c->h_pose, c->h_lk_work, c->h_flags};
   for (void* p : host) cudaFreeHost(p);
   for (auto& pe : c->prof.pending) {
     cudaEventDestroy(pe.a);
@@ -327,6 +337,32 @@ int vo_destroy(vo_ctx* c) {
 }  // extern "C"
 
 // ------------------------------------------------------------------------------------ helpers
+#include <chrono>
+struct HostTrace {
+  bool on = getenv("VO_B200_TRACE_HOST") != nullptr;
+  double acc[8] = {0};
+  long n[8] = {0};
+  ~HostTrace() {
+    if (!on) return;
+    const char* names[8] = {"pnp_sample_gen", "pnp_enqueue", "pnp_sync_wait", "f_sample_gen", "f_enqueue", "f_sync_wait",
+                            "lk_sync_wait", "other"};
+    for (int i = 0; i < 8; i++)
+      if (n[i]) fprintf(stderr, "[vo trace] %-16s calls %6ld  avg %8.2f us\n", names[i], n[i], acc[i] / n[i]);
+  }
+};
+static HostTrace g_trace;
+struct TraceScope {
+  int k;
+  std::chrono::steady_clock::time_point t0;
+  explicit TraceScope(int kk) : k(kk) { if (g_trace.on) t0 = std::chrono::steady_clock::now(); }
+  ~TraceScope() {
+    if (g_trace.on) {
+      g_trace.acc[k] += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+      g_trace.n[k]++;
+    }
+  }
+};
+
 #define CHECK_CTX(c)                        \
   if (!(c)) return VO_ERR_INVALID_ARG;      \
   VO_CUDA(cudaSetDevice((c)->device))
@@ -436,6 +472,7 @@ static int run_fmat(vo_ctx* c, const float2* m1, const float2* m2, int n, double
             return VO_ERR_INVALID_ARG;
           }
       } else {
+        TraceScope ts(3);
         int got = draw_fmat_samples(rng, h_m1, h_m2, n, k, hs);
         if (got < k) {  // OpenCV: getSubset failed -> the loop ends here
           k = got;
@@ -456,7 +493,10 @@ static int run_fmat(vo_ctx* c, const float2* m1, const float2* m2, int n, double
     VO_TRY(fmat_mask_launch(c, m1, m2, n, c->d_models, c->d_sel, thr2, c->d_mask));
     if (tail) VO_TRY(tail());
     VO_CUDA(cudaMemcpyAsync(c->h_sel, c->d_sel, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    VO_TRY(sync_stream(c));
+    {
+      TraceScope tw(5);
+      VO_TRY(sync_stream(c));
+    }
     const int niters = c->h_sel[1];
     if (done >= std::min(niters, H) || k <= 0) break;
     target = std::min(niters, H);
@@ -499,8 +539,10 @@ static int run_pnp(vo_ctx* c, const float3* xyz, const float2* xy, int n, int it
             return VO_ERR_INVALID_ARG;
           }
       } else {
+        TraceScope ts(0);
         for (int s = 0; s < k; s++) draw_indices(rng, n, 5, hs + (size_t)s * 5);
       }
+      TraceScope te(1);
       VO_CUDA(cudaMemcpyAsync(c->d_samples + (size_t)done * 5, hs, (size_t)k * 5 * sizeof(int32_t),
                               cudaMemcpyHostToDevice, c->stream));
       VO_TRY(pnp_solve_launch(c, xyz, xy, c->d_samples + (size_t)done * 5, k, c->d_models + (size_t)done * 16,
@@ -515,7 +557,10 @@ static int run_pnp(vo_ctx* c, const float3* xyz, const float2* xy, int n, int it
     VO_TRY(pnp_refine_launch(c, xyz, xy, c->d_idx, c->d_count + 4, c->d_models, c->d_sel, c->d_pose));
     VO_CUDA(cudaMemcpyAsync(c->h_sel, c->d_sel, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     VO_CUDA(cudaMemcpyAsync(c->h_pose, c->d_pose, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    VO_TRY(read_counts(c));
+    {
+      TraceScope tw(2);
+      VO_TRY(read_counts(c));
+    }
     const int niters = c->h_sel[1];
     if (done >= std::min(niters, H) || k <= 0) break;
     target = std::min(niters, H);
@@ -545,7 +590,10 @@ static int lk_and_compact(vo_ctx* c, int slot_a, int slot_b, const float2* d_in,
     VO_CUDA(cudaMemcpyAsync(c->h_pts + (size_t)2 * c->cap, c->d_c_trk, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost,
                             c->stream));
   }
-  VO_TRY(read_counts(c));
+  {
+    TraceScope tw(6);
+    VO_TRY(read_counts(c));
+  }
   *m = c->h_count[0];
   return VO_OK;
 }
@@ -635,6 +683,179 @@ static int pnp_two_attempts(vo_ctx* c, int k, int* n_inl, int* attempt) {
     if (*n_inl < c->p.pnp_min_inliers) return VO_ERR_LOW_INLIERS;
   }
   return VO_OK;
+}
+
+// ------------------------------------------------------------------------------------ fused chains
+// The same stages as track_pipeline + pnp_two_attempts / stereo_pipeline, but enqueued back to back
+// with every element count read from device memory and the RANSAC samples drawn on the device, so
+// the chain needs ONE host synchronisation at its end instead of one per stage.  Anything outside
+// the common case (adaptive stop not reached inside the first chunk, too few points, low inlier
+// count -> second PnP attempt, sampler overflow) is detected after that synchronisation and the
+// stage is redone on the host-driven path above, which handles every case.
+constexpr int F_CHUNK = 48, PNP_CHUNK = 32;
+
+struct FusedStatus {
+  int m = 0, k = 0, n_inl = 0;
+  bool f_ok = false, pnp_ok = false;
+};
+
+// F-RANSAC part of a fused chain on d_c_* (count in d_count[0], upper bound n_max):
+// sampling, solve, score, select (-> d_sel + 4), mask, compaction into d_f_* (count d_count[1]).
+static int enqueue_fmat_fused(vo_ctx* c, int n_max, double thr, bool with_xyz) {
+  const int H = c->p.f_exhaustive ? std::min(std::max(c->p.f_max_iters, 1), 1024) : F_CHUNK;
+  const float thr2 = (float)(thr * thr);
+  c->n_dev = c->d_count + 0;
+  VO_TRY(sample_launch(c, 7, c->d_c_ref, c->d_c_trk, n_max, H, c->d_samples, c->d_flags + 0));
+  VO_TRY(fmat_solve_launch(c, c->d_c_ref, c->d_c_trk, c->d_samples, H, c->d_models, c->d_counts));
+  VO_TRY(fmat_score_launch(c, c->d_c_ref, c->d_c_trk, n_max, c->d_models, c->d_counts, H, thr2));
+  VO_TRY(select_launch(c, c->d_counts, H, 3, 7, n_max, c->p.f_conf, std::max(c->p.f_max_iters, 1), c->d_sel + 4));
+  VO_TRY(fmat_mask_launch(c, c->d_c_ref, c->d_c_trk, n_max, c->d_models, c->d_sel + 4, thr2, c->d_mask));
+  VO_TRY(compact_launch(c, c->d_mask, n_max, c->d_c_ref, c->d_f_ref, c->d_c_trk, c->d_f_trk,
+                        with_xyz ? c->d_c_xyz : nullptr, c->d_f_xyz, nullptr, 1));
+  c->n_dev = nullptr;
+  c->last_f_h = H;
+  return VO_OK;
+}
+
+static bool fmat_fused_valid(const vo_ctx* c, int m, int H) {
+  // h_sel[4..7] = F selection; the first chunk is final iff OpenCV's niters ended inside it
+  return c->h_flags[0] == 0 && m >= 15 && c->h_sel[4] >= 0 && c->h_sel[5] <= H;
+}
+
+static int track_pnp_fused_enqueue(vo_ctx* c, int slot_ref, int slot_cur, const float2* d_ref_xy,
+                                   const float3* d_ref_xyz, int n) {
+  const int iters = std::max(c->p.pnp_iters, 1);
+  const int Hp = c->p.ransac_exhaustive ? iters : std::min(iters, PNP_CHUNK);
+  const float thr2 = (float)(c->p.pnp_thr * c->p.pnp_thr);
+  VO_TRY(lk_launch(c, slot_ref, slot_cur, d_ref_xy, n, c->d_xy_trk, c->d_status, c->d_err));
+  VO_TRY(compact_launch(c, c->d_status, n, d_ref_xy, c->d_c_ref, c->d_xy_trk, c->d_c_trk, d_ref_xyz, c->d_c_xyz, nullptr, 0));
+  VO_TRY(enqueue_fmat_fused(c, n, c->p.f_thr_temporal, true));
+  // PnP on d_f_* (count in d_count[1])
+  c->n_dev = c->d_count + 1;
+  VO_TRY(sample_launch(c, 5, nullptr, nullptr, n, Hp, c->d_samples, c->d_flags + 1));
+  VO_TRY(pnp_solve_launch(c, c->d_f_xyz, c->d_f_trk, c->d_samples, Hp, c->d_models, c->d_counts));
+  VO_TRY(pnp_score_launch(c, c->d_f_xyz, c->d_f_trk, n, c->d_models, c->d_counts, Hp, thr2));
+  VO_TRY(select_launch(c, c->d_counts, Hp, 1, 5, n, c->p.pnp_conf, iters, c->d_sel));
+  VO_TRY(pnp_mask_launch(c, c->d_f_xyz, c->d_f_trk, n, c->d_models, c->d_sel, thr2, c->d_mask));
+  VO_TRY(compact_launch(c, c->d_mask, n, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, c->d_idx, 4));
+  c->n_dev = nullptr;
+  VO_TRY(pnp_refine_launch(c, c->d_f_xyz, c->d_f_trk, c->d_idx, c->d_count + 4, c->d_models, c->d_sel, c->d_pose));
+  c->last_pnp_h = Hp;
+  VO_CUDA(cudaMemcpyAsync(c->h_sel, c->d_sel, 8 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  VO_CUDA(cudaMemcpyAsync(c->h_flags, c->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  VO_CUDA(cudaMemcpyAsync(c->h_pose, c->d_pose, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  VO_CUDA(cudaMemcpyAsync(c->h_count, c->d_count, 16 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  return VO_OK;
+}
+
+static int track_pnp_fused_finish(vo_ctx* c, FusedStatus* st) {
+  const int Hf = c->p.f_exhaustive ? std::min(std::max(c->p.f_max_iters, 1), 1024) : F_CHUNK;
+  const int iters = std::max(c->p.pnp_iters, 1);
+  const int Hp = c->p.ransac_exhaustive ? iters : std::min(iters, PNP_CHUNK);
+  VO_TRY(sync_stream(c));
+  st->m = c->h_count[0];
+  st->k = c->h_count[1];
+  st->n_inl = c->h_count[4];
+  st->f_ok = fmat_fused_valid(c, st->m, Hf);
+  st->pnp_ok = st->f_ok && c->h_flags[1] == 0 && st->k > 5 && c->h_sel[0] >= 0 && c->h_sel[1] <= Hp &&
+               st->n_inl >= c->p.pnp_min_inliers;
+  return VO_OK;
+}
+
+// stereoTriangulate as one fused chain.  Same outputs as stereo_pipeline (pose == NULL variant).
+static int stereo_fused_enqueue(vo_ctx* c, int slot_l, int slot_r, int* n_grid_out) {
+  int ng = 0;
+  VO_TRY(grid_launch(c, c->p.height, c->p.width, c->p.grid_step, c->d_xy_in, &ng));
+  if (n_grid_out) *n_grid_out = ng;
+  if (ng <= 0) {
+    VO_CUDA(cudaMemsetAsync(c->d_count, 0, 16 * sizeof(int), c->stream));
+    VO_CUDA(cudaMemcpyAsync(c->h_count, c->d_count, 16 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    return VO_OK;
+  }
+  VO_TRY(lk_launch(c, slot_l, slot_r, c->d_xy_in, ng, c->d_xy_trk, c->d_status, c->d_err));
+  VO_TRY(compact_launch(c, c->d_status, ng, c->d_xy_in, c->d_c_ref, c->d_xy_trk, c->d_c_trk, nullptr, nullptr, nullptr, 0));
+  VO_TRY(enqueue_fmat_fused(c, ng, c->p.f_thr_stereo, false));
+  double P[24];
+  make_projections(c->p, P);
+  VO_CUDA(cudaMemcpyAsync(c->d_cam, P, sizeof(P), cudaMemcpyHostToDevice, c->stream));
+  c->n_dev = c->d_count + 1;
+  VO_TRY(triangulate_launch(c, c->d_cam, c->d_f_ref, c->d_f_trk, ng, c->d_xyz_tmp, nullptr, nullptr));
+  c->n_dev = nullptr;
+  VO_CUDA(cudaMemcpyAsync(c->h_sel, c->d_sel, 8 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  VO_CUDA(cudaMemcpyAsync(c->h_flags, c->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  VO_CUDA(cudaMemcpyAsync(c->h_count, c->d_count, 16 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  return VO_OK;
+}
+
+// Synchronise a stereo chain enqueued by stereo_fused_enqueue; when its fused result is not final,
+// redo F-RANSAC + triangulation on the host-driven path.
+// Result: d_f_ref (left 2-D), d_xyz_tmp (camera frame), *n_out points.
+static int stereo_fused_finish(vo_ctx* c, int* n_out) {
+  const int Hf = c->p.f_exhaustive ? std::min(std::max(c->p.f_max_iters, 1), 1024) : F_CHUNK;
+  VO_TRY(sync_stream(c));
+  *n_out = c->h_count[1];
+  if (c->h_count[0] == 0) {
+    *n_out = 0;
+    return VO_OK;
+  }
+  if (fmat_fused_valid(c, c->h_count[0], Hf)) return VO_OK;
+  int k = 0;
+  VO_TRY(fmat_and_compact(c, c->h_count[0], c->p.f_thr_stereo, false, &k));   // d_c_* still hold the LK survivors
+  double P[24];
+  make_projections(c->p, P);
+  VO_CUDA(cudaMemcpyAsync(c->d_cam, P, sizeof(P), cudaMemcpyHostToDevice, c->stream));
+  VO_TRY(triangulate_launch(c, c->d_cam, c->d_f_ref, c->d_f_trk, k, c->d_xyz_tmp, nullptr, nullptr));
+  *n_out = k;
+  return VO_OK;
+}
+
+static int stereo_any(vo_ctx* c, int slot_l, int slot_r, int* n_out, int* n_grid_out) {
+  VO_TRY(stereo_fused_enqueue(c, slot_l, slot_r, n_grid_out));
+  return stereo_fused_finish(c, n_out);
+}
+
+static int temporal_finish(vo_ctx* c, int* k, int* n_inl, int* attempt);
+static bool temporal_fusable(const vo_ctx* c) {
+  const int iters = std::max(c->p.pnp_iters, 1);
+  return (c->p.ransac_exhaustive ? iters : std::min(iters, PNP_CHUNK)) <= 1024;
+}
+
+// PerspectiveNpointEstimation on device data: fused chain first, host-driven completion otherwise.
+// Returns VO_OK or VO_ERR_LOW_INLIERS like pnp_two_attempts; *k tracked points in d_f_*, pose in h_pose.
+static int temporal_any(vo_ctx* c, int slot_ref, int slot_cur, const float2* d_ref_xy, const float3* d_ref_xyz, int n,
+                        int* k, int* n_inl, int* attempt) {
+  *k = 0;
+  *n_inl = 0;
+  *attempt = 1;
+  if (n <= 0) return pnp_two_attempts(c, 0, n_inl, attempt);
+  const int iters = std::max(c->p.pnp_iters, 1);
+  if ((c->p.ransac_exhaustive ? iters : std::min(iters, PNP_CHUNK)) > 1024) {   // beyond the device sampler
+    VO_TRY(track_pipeline(c, slot_ref, slot_cur, d_ref_xy, d_ref_xyz, n, k));
+    return pnp_two_attempts(c, *k, n_inl, attempt);
+  }
+  VO_TRY(track_pnp_fused_enqueue(c, slot_ref, slot_cur, d_ref_xy, d_ref_xyz, n));
+  return temporal_finish(c, k, n_inl, attempt);
+}
+
+// second half of temporal_any: synchronise the fused chain and complete it on the host path if needed
+static int temporal_finish(vo_ctx* c, int* k, int* n_inl, int* attempt) {
+  *k = 0;
+  *n_inl = 0;
+  *attempt = 1;
+  FusedStatus st;
+  VO_TRY(track_pnp_fused_finish(c, &st));
+  if (st.pnp_ok) {
+    *k = st.k;
+    *n_inl = st.n_inl;
+    return VO_OK;
+  }
+  if (st.f_ok) {
+    *k = st.k;
+  } else {
+    int r = fmat_and_compact(c, st.m, c->p.f_thr_temporal, true, k);   // d_c_* still hold the LK survivors
+    if (r != VO_OK && r != VO_ERR_TOO_FEW_POINTS) return r;
+  }
+  return pnp_two_attempts(c, *k, n_inl, attempt);
 }
 
 static void pose_from_pnp(const double rvec[3], const double tvec[3], double pose[12]) {
@@ -884,7 +1105,11 @@ static int stereo_host(vo_ctx* c, const uint8_t* left, const uint8_t* right, int
   VO_TRY(load_image(c, 0, left, stride, 0, true));
   VO_TRY(load_image(c, 2, right, stride, 0, false));
   int k = 0;
-  VO_TRY(stereo_pipeline(c, 0, 2, pose, &k, nullptr));
+  VO_TRY(stereo_any(c, 0, 2, &k, nullptr));
+  if (pose && k) {
+    VO_CUDA(cudaMemcpyAsync(c->d_cam + 24, pose, 12 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    VO_TRY(transform_launch(c, c->d_cam + 24, c->d_xyz_tmp, k, c->d_f_xyz));
+  }
   *n = k;
   if (k > cap) return VO_ERR_CAPACITY;
   if (k) {
@@ -951,11 +1176,22 @@ int vo_pnp_frame(vo_ctx* c, const uint8_t* ref_img, const uint8_t* cur_img, int 
   if (!n_trk || !rvec || !tvec || !n_inl) return VO_ERR_INVALID_ARG;
   int k = 0;
   *n_inl = 0;
-  VO_TRY(track_host(c, ref_img, cur_img, stride, ref_xy, ref_xyz, n, &k));
-  *n_trk = k;
-  VO_TRY(copy_track_outputs(c, k, trk_xy, trk_xyz, ref_xy_inl));
+  if (!ref_img || !cur_img || !ref_xy || !ref_xyz || n < 0) return VO_ERR_INVALID_ARG;
+  if (n > c->cap) return VO_ERR_CAPACITY;
   int ni = 0, att = 1;
-  int r = pnp_two_attempts(c, k, &ni, &att);
+  int r;
+  if (n == 0) {
+    r = pnp_two_attempts(c, 0, &ni, &att);
+  } else {
+    VO_TRY(load_image(c, 0, ref_img, stride, 0, true));
+    VO_TRY(load_image(c, 1, cur_img, stride, 0, false));
+    VO_CUDA(cudaMemcpyAsync(c->d_xy_in, ref_xy, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
+    VO_CUDA(cudaMemcpyAsync(c->d_xyz_in, ref_xyz, (size_t)n * sizeof(float3), cudaMemcpyHostToDevice, c->stream));
+    r = temporal_any(c, 0, 1, c->d_xy_in, c->d_xyz_in, n, &k, &ni, &att);
+  }
+  *n_trk = k;
+  if (r != VO_OK && r != VO_ERR_LOW_INLIERS) return r;
+  VO_TRY(copy_track_outputs(c, k, trk_xy, trk_xyz, ref_xy_inl));
   if (attempt_used) *attempt_used = att;
   *n_inl = ni;
   if (r != VO_OK && r != VO_ERR_LOW_INLIERS) return r;
@@ -978,7 +1214,7 @@ int vo_seq_init(vo_ctx* c, const uint8_t* left, const uint8_t* right, int stride
   VO_TRY(load_image(c, 0, left, stride, is_device, true));
   VO_TRY(load_image(c, 2, right, stride, is_device, false));
   int k = 0;
-  VO_TRY(stereo_pipeline(c, 0, 2, nullptr, &k, nullptr));
+  VO_TRY(stereo_any(c, 0, 2, &k, nullptr));
   if (k) {
     VO_CUDA(cudaMemcpyAsync(c->d_seq_xy, c->d_f_ref, (size_t)k * sizeof(float2), cudaMemcpyDeviceToDevice, c->stream));
     VO_CUDA(cudaMemcpyAsync(c->d_seq_xyz, c->d_xyz_tmp, (size_t)k * sizeof(float3), cudaMemcpyDeviceToDevice, c->stream));
@@ -1004,29 +1240,49 @@ int vo_seq_track(vo_ctx* c, const uint8_t* left, const uint8_t* right, int strid
   const bool kf_known = right && (force_keyframe || c->p.kf_min_inliers > c->p.max_points);
   vo_ctx* a = c->aux;
   int kk = 0, ng = 0;
-  if (kf_known) {
-    VO_CUDA(cudaEventRecord(c->ev_left, c->stream));           // cur-left pyramid is complete
-    VO_CUDA(cudaStreamWaitEvent(a->stream, c->ev_left, 0));
-    post_task(c, [=, &kk, &ng]() -> int {
-      VO_TRY(load_image(a, 2, right, stride, is_device, false));
-      VO_TRY(stereo_pipeline(a, cur, 2, nullptr, &kk, &ng));   // camera-frame xyz in a->d_xyz_tmp
-      VO_CUDA(cudaEventRecord(c->ev_stereo, a->stream));
-      return VO_OK;
-    });
-  }
-
   int k = 0, ni = 0, att = 1;
-  int r = track_pipeline(c, ref, cur, c->d_seq_xy, c->d_seq_xyz, c->seq_n, &k);
-  if (r == VO_OK) {
-    out->n_tracked = k;
-    r = pnp_two_attempts(c, k, &ni, &att);
-    out->n_inliers = ni;
-    out->attempt_used = att;
-  }
-  if (kf_known) {
-    const int rs = wait_task(c);     // always join: the auxiliary chain must be idle on return
+  int r;
+  if (kf_known && c->seq_n > 0 && temporal_fusable(c)) {
+    // both chains are enqueued by this thread, the critical one (tracking + PnP, high-priority
+    // stream) first; one synchronisation per chain at the end
+    VO_CUDA(cudaEventRecord(c->ev_left, c->stream));           // cur-left pyramid is complete
+    int rs = VO_OK;
+    if (getenv("VO_B200_STEREO_FIRST")) {
+      VO_CUDA(cudaStreamWaitEvent(a->stream, c->ev_left, 0));
+      rs = load_image(a, 2, right, stride, is_device, false);
+      if (rs == VO_OK) rs = stereo_fused_enqueue(a, cur, 2, &ng);
+      VO_TRY(track_pnp_fused_enqueue(c, ref, cur, c->d_seq_xy, c->d_seq_xyz, c->seq_n));
+    } else {
+      VO_TRY(track_pnp_fused_enqueue(c, ref, cur, c->d_seq_xy, c->d_seq_xyz, c->seq_n));
+      VO_CUDA(cudaStreamWaitEvent(a->stream, c->ev_left, 0));
+      rs = load_image(a, 2, right, stride, is_device, false);
+      if (rs == VO_OK) rs = stereo_fused_enqueue(a, cur, 2, &ng);
+    }
+    r = temporal_finish(c, &k, &ni, &att);
+    if (rs == VO_OK) rs = stereo_fused_finish(a, &kk);
+    else cudaStreamSynchronize(a->stream);
+    VO_CUDA(cudaEventRecord(c->ev_stereo, a->stream));
     if (r == VO_OK) r = rs;
+  } else {
+    if (kf_known) {
+      VO_CUDA(cudaEventRecord(c->ev_left, c->stream));
+      VO_CUDA(cudaStreamWaitEvent(a->stream, c->ev_left, 0));
+      post_task(c, [=, &kk, &ng]() -> int {
+        VO_TRY(load_image(a, 2, right, stride, is_device, false));
+        VO_TRY(stereo_any(a, cur, 2, &kk, &ng));                  // camera-frame xyz in a->d_xyz_tmp
+        VO_CUDA(cudaEventRecord(c->ev_stereo, a->stream));
+        return VO_OK;
+      });
+    }
+    r = temporal_any(c, ref, cur, c->d_seq_xy, c->d_seq_xyz, c->seq_n, &k, &ni, &att);
+    if (kf_known) {
+      const int rs = wait_task(c);     // always join: the auxiliary chain must be idle on return
+      if (r == VO_OK) r = rs;
+    }
   }
+  out->n_tracked = k;
+  out->n_inliers = ni;
+  out->attempt_used = att;
   if (r != VO_OK) return r;  // incl. VO_ERR_LOW_INLIERS: the reference breaks out of its loop here
   for (int i = 0; i < 3; i++) {
     out->rvec[i] = c->h_pose[i];
@@ -1052,10 +1308,11 @@ int vo_seq_track(vo_ctx* c, const uint8_t* left, const uint8_t* right, int strid
       return VO_ERR_INVALID_ARG;
     }
     VO_TRY(load_image(c, 2, right, stride, is_device, false));
-    VO_TRY(stereo_pipeline(c, cur, 2, out->pose3x4, &kk, &ng));
+    VO_TRY(stereo_any(c, cur, 2, &kk, &ng));
+    VO_CUDA(cudaMemcpyAsync(c->d_cam + 24, out->pose3x4, 12 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     if (kk) {
+      VO_TRY(transform_launch(c, c->d_cam + 24, c->d_xyz_tmp, kk, c->d_seq_xyz));
       VO_CUDA(cudaMemcpyAsync(c->d_seq_xy, c->d_f_ref, (size_t)kk * sizeof(float2), cudaMemcpyDeviceToDevice, c->stream));
-      VO_CUDA(cudaMemcpyAsync(c->d_seq_xyz, c->d_f_xyz, (size_t)kk * sizeof(float3), cudaMemcpyDeviceToDevice, c->stream));
     }
     c->seq_n = kk;
     out->keyframe = 1;

@@ -110,6 +110,12 @@ struct vo_ctx {
   int* h_count = nullptr;                                // pinned mirror
   unsigned long long* d_tile_state = nullptr;            // compaction look-back (epoch<<32 | tile total)
   unsigned compact_epoch = 0;
+  // When set, kernels take their element count from this device pointer (clamped to the host-side
+  // upper bound they were launched with): lets a whole chain run without a host round trip.
+  const int* n_dev = nullptr;
+  uint32_t* d_rng = nullptr;     // OpenCV's RNG output stream for seed 2^64-1 (fixed), RNG_LEN values
+  int* d_flags = nullptr;        // sampler status words (0 = ok)
+  int* h_flags = nullptr;
 
   // sequence state (vo_seq_*): reference set resident in HBM
   float2* d_seq_xy = nullptr;
@@ -201,6 +207,10 @@ int pnp_score_launch(vo_ctx* c, const float3* xyz, const float2* xy, int n, cons
 int pnp_mask_launch(vo_ctx* c, const float3* xyz, const float2* xy, int n, const double* d_models, const int* d_sel,
                     float thr2, uint8_t* d_mask);
 // RANSAC record-setter scan: counts[n_models] (flattened, models_per_sample each) -> d_sel
+constexpr int RNG_LEN = 1 << 17;
+// device-side minimal-sample generation (OpenCV getSubset semantics); M = 7 checks collinearity
+int sample_launch(vo_ctx* c, int model_points, const float2* m1, const float2* m2, int n_max, int h, int32_t* d_samples,
+                  int* d_flag);
 int select_launch(vo_ctx* c, const int32_t* d_counts, int n_samples, int models_per_sample, int model_points, int n_points,
                   double conf, int max_iters, int* d_sel);
 int pnp_refine_launch(vo_ctx* c, const float3* xyz, const float2* xy, const int32_t* d_idx, const int* d_n_inl,

@@ -52,7 +52,8 @@ __global__ void __launch_bounds__(CP_THREADS)
 compact_kernel(const uint8_t* __restrict__ flags, int n, const float2* __restrict__ a_in, float2* __restrict__ a_out,
                const float2* __restrict__ b_in, float2* __restrict__ b_out, const float3* __restrict__ c_in,
                float3* __restrict__ c_out, int32_t* __restrict__ idx_out, int* __restrict__ count_out,
-               volatile unsigned long long* tile_state, unsigned epoch) {
+               volatile unsigned long long* tile_state, unsigned epoch, const int* __restrict__ n_dev) {
+  if (n_dev) n = min(n, *n_dev);
   __shared__ int warp_tot[CP_THREADS / 32];
   __shared__ int s_base;
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
@@ -130,7 +131,7 @@ int compact_launch(vo_ctx* c, const uint8_t* d_flags, int n, const float2* a_in,
     LaunchScope ls(c, VO_K_COMPACT);
     compact_kernel<<<div_up(n, CP_TILE), CP_THREADS, 0, c->stream>>>(d_flags, n, a_in, a_out, b_in, b_out, c_in, c_out,
                                                                      idx_out, c->d_count + count_slot, c->d_tile_state,
-                                                                     ++c->compact_epoch);
+                                                                     ++c->compact_epoch, c->n_dev);
   }
   VO_CUDA(cudaGetLastError());
   return VO_OK;
@@ -151,7 +152,9 @@ __device__ __forceinline__ float3 rigid_apply(const double* M, float3 p) {
 
 __global__ void __launch_bounds__(128)
 triangulate_kernel(const double* __restrict__ P, const float2* __restrict__ a, const float2* __restrict__ b, int n,
-                   float3* __restrict__ out, const double* __restrict__ M, float3* __restrict__ out2) {
+                   float3* __restrict__ out, const double* __restrict__ M, float3* __restrict__ out2,
+                   const int* __restrict__ n_dev) {
+  if (n_dev) n = min(n, *n_dev);
   __shared__ double sP[24], sM[12];
   if (threadIdx.x < 24) sP[threadIdx.x] = P[threadIdx.x];
   if (M && threadIdx.x < 12) sM[threadIdx.x] = M[threadIdx.x];
@@ -171,14 +174,15 @@ int triangulate_launch(vo_ctx* c, const double* d_P1P2, const float2* a, const f
   if (n <= 0) return VO_OK;
   {
     LaunchScope ls(c, VO_K_TRIANGULATE);
-    triangulate_kernel<<<div_up(n, 128), 128, 0, c->stream>>>(d_P1P2, a, b, n, out, d_M, out2);
+    triangulate_kernel<<<div_up(n, 128), 128, 0, c->stream>>>(d_P1P2, a, b, n, out, d_M, out2, c->n_dev);
   }
   VO_CUDA(cudaGetLastError());
   return VO_OK;
 }
 
 __global__ void transform_kernel(const double* __restrict__ M, const float3* __restrict__ in, int n,
-                                 float3* __restrict__ out) {
+                                 float3* __restrict__ out, const int* __restrict__ n_dev) {
+  if (n_dev) n = min(n, *n_dev);
   __shared__ double sM[12];
   if (threadIdx.x < 12) sM[threadIdx.x] = M[threadIdx.x];
   __syncthreads();
@@ -191,7 +195,7 @@ int transform_launch(vo_ctx* c, const double* d_M, const float3* in, int n, floa
   if (n <= 0) return VO_OK;
   {
     LaunchScope ls(c, VO_K_MISC);
-    transform_kernel<<<div_up(n, 256), 256, 0, c->stream>>>(d_M, in, n, out);
+    transform_kernel<<<div_up(n, 256), 256, 0, c->stream>>>(d_M, in, n, out, c->n_dev);
   }
   VO_CUDA(cudaGetLastError());
   return VO_OK;

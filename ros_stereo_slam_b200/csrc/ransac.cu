@@ -241,7 +241,9 @@ constexpr int SCORE_HB = 16;  // hypotheses per CTA (staged in shared memory)
 // (shared atomics) -> global (one atomic per CTA and hypothesis).
 __global__ void __launch_bounds__(SCORE_TPB)
 fmat_score_kernel(const float2* __restrict__ m1, const float2* __restrict__ m2, int n, const double* __restrict__ models,
-                  int32_t* __restrict__ counts, int n_models, float thr2, const int* __restrict__ limit) {
+                  int32_t* __restrict__ counts, int n_models, float thr2, const int* __restrict__ limit,
+                  const int* __restrict__ n_dev) {
+  if (n_dev) n = min(n, *n_dev);
   __shared__ double sF[SCORE_HB * F_STRIDE];
   __shared__ int sCnt[SCORE_HB];
   __shared__ int sValid[SCORE_HB];
@@ -278,7 +280,9 @@ fmat_score_kernel(const float2* __restrict__ m1, const float2* __restrict__ m2, 
 
 __global__ void __launch_bounds__(SCORE_TPB)
 pnp_score_kernel(const float3* __restrict__ xyz, const float2* __restrict__ xy, int n, const double* __restrict__ models,
-                 int32_t* __restrict__ counts, int n_models, Intrinsics K, float thr2, const int* __restrict__ limit) {
+                 int32_t* __restrict__ counts, int n_models, Intrinsics K, float thr2, const int* __restrict__ limit,
+                 const int* __restrict__ n_dev) {
+  if (n_dev) n = min(n, *n_dev);
   __shared__ double sM[SCORE_HB * PNP_STRIDE];
   __shared__ int sCnt[SCORE_HB];
   const int m0 = blockIdx.y * SCORE_HB;
@@ -311,7 +315,8 @@ pnp_score_kernel(const float3* __restrict__ xyz, const float2* __restrict__ xy, 
 // ================================================================ best-model inlier mask
 __global__ void fmat_mask_kernel(const float2* __restrict__ m1, const float2* __restrict__ m2, int n,
                                  const double* __restrict__ models, const int* __restrict__ sel, float thr2,
-                                 uint8_t* __restrict__ mask) {
+                                 uint8_t* __restrict__ mask, const int* __restrict__ n_dev) {
+  if (n_dev) n = min(n, *n_dev);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int best = sel[0];
@@ -322,7 +327,8 @@ __global__ void fmat_mask_kernel(const float2* __restrict__ m1, const float2* __
 
 __global__ void pnp_mask_kernel(const float3* __restrict__ xyz, const float2* __restrict__ xy, int n,
                                 const double* __restrict__ models, const int* __restrict__ sel, Intrinsics K,
-                                float thr2, uint8_t* __restrict__ mask) {
+                                float thr2, uint8_t* __restrict__ mask, const int* __restrict__ n_dev) {
+  if (n_dev) n = min(n, *n_dev);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int best = sel[0];
@@ -353,7 +359,8 @@ constexpr int SEL_THREADS = 1024;
 // (prefix max); candidates are then replayed in order with the adaptive iteration limit.
 __global__ void __launch_bounds__(SEL_THREADS)
 select_kernel(const int32_t* __restrict__ counts, int n_samples, int mps, int model_points, int n_points, double conf,
-              int max_iters, int* __restrict__ sel) {
+              int max_iters, int* __restrict__ sel, const int* __restrict__ n_dev) {
+  if (n_dev) n_points = min(n_points, *n_dev);
   __shared__ int s_excl[SEL_THREADS];
   __shared__ int s_warp[32];
   __shared__ unsigned s_cand[32];
@@ -434,6 +441,120 @@ select_kernel(const int32_t* __restrict__ counts, int n_samples, int mps, int mo
   }
 }
 
+// ================================================================ device-side sampling
+// RANSACPointSetRegistrator::getSubset for all H samples of a chunk at once.  OpenCV consumes ONE
+// random stream sequentially: sample s starts where sample s-1 stopped, a duplicate index costs one
+// extra draw, a subset rejected by the collinearity check (F-matrix only) costs a whole new subset.
+// The stream itself is fixed (seed 2^64-1) and precomputed in `raw`.  Every thread owns one sample,
+// speculates that all earlier samples consumed exactly M values, computes its own consumption from
+// that start, and a block prefix sum yields the true start positions; threads whose start moved
+// recompute.  Each round fixes at least the first wrong start, and exceptions are rare (a few per
+// thousand samples; a few per 48 on integer grids), so this converges in a handful of rounds.
+template <int M, bool CHECK>
+__global__ void __launch_bounds__(1024)
+sample_kernel(const uint32_t* __restrict__ raw, int raw_len, const int* __restrict__ n_dev, int n_max,
+              const float2* __restrict__ m1, const float2* __restrict__ m2, int H, int32_t* __restrict__ out,
+              int* __restrict__ flag) {
+  __shared__ int s_warp[32];
+  __shared__ int s_bad;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  int n = n_max;
+  if (n_dev) n = min(n, *n_dev);
+  if (t == 0) s_bad = 0;
+  __syncthreads();
+  if (n < M + 1) {   // too few points for this estimator's RANSAC path (host decides what to do)
+    if (t == 0) *flag = 2;
+    return;
+  }
+  const bool active = t < H;
+  int pos = M * t, used = M, idx[M];
+  bool dirty = true;
+  for (int round = 0; round <= H + 1; round++) {
+    if (active && dirty) {
+      int p = pos;
+      bool ok = false;
+      for (int attempt = 0; attempt < 10000 && !ok; attempt++) {
+        for (int i = 0; i < M; i++) {
+          int v;
+          for (;;) {
+            if (p >= raw_len) { s_bad = 1; v = 0; break; }
+            v = (int)(raw[p++] % (unsigned)n);
+            bool dup = false;
+            for (int k = 0; k < i; k++) dup |= (idx[k] == v);
+            if (!dup) break;
+          }
+          idx[i] = v;
+        }
+        ok = true;
+        if (CHECK && !s_bad) {
+          // haveCollinearPoints(ms1) || haveCollinearPoints(ms2): last point vs every earlier pair
+          for (int set = 0; set < 2 && ok; set++) {
+            const float2* pts = set ? m2 : m1;
+            const float2 pi = pts[idx[M - 1]];
+            for (int j = 0; j < M - 1 && ok; j++) {
+              const float2 pj = pts[idx[j]];
+              const double dx1 = (double)pj.x - (double)pi.x, dy1 = (double)pj.y - (double)pi.y;
+              for (int k = 0; k < j; k++) {
+                const float2 pk = pts[idx[k]];
+                const double dx2 = (double)pk.x - (double)pi.x, dy2 = (double)pk.y - (double)pi.y;
+                if (fabs(dx2 * dy1 - dy2 * dx1) <= (double)FLT_EPSILON * (fabs(dx1) + fabs(dy1) + fabs(dx2) + fabs(dy2))) {
+                  ok = false;
+                  break;
+                }
+              }
+            }
+          }
+        }
+        if (s_bad) break;
+      }
+      if (!ok) s_bad = 1;
+      used = p - pos;
+    }
+    // exclusive prefix sum of `used` over the block -> true start positions
+    int incl = active ? used : 0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += v;
+    }
+    if (lane == 31) s_warp[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+      int x = s_warp[lane], xi = x;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, xi, d);
+        if (lane >= d) xi += v;
+      }
+      s_warp[lane] = xi - x;
+    }
+    __syncthreads();
+    const int newpos = s_warp[w] + incl - (active ? used : 0);
+    dirty = active && newpos != pos;
+    pos = newpos;
+    const int any = __syncthreads_or(dirty ? 1 : 0);
+    if (!any || s_bad) break;
+  }
+  if (active)
+    for (int i = 0; i < M; i++) out[t * M + i] = idx[i];
+  if (t == 0) *flag = s_bad ? 1 : 0;
+}
+
+int sample_launch(vo_ctx* c, int model_points, const float2* m1, const float2* m2, int n_max, int h, int32_t* d_samples,
+                  int* d_flag) {
+  if (h <= 0 || h > 1024) return VO_ERR_INVALID_ARG;
+  {
+    LaunchScope ls(c, VO_K_SELECT);
+    if (model_points == 7)
+      sample_kernel<7, true><<<1, 1024, 0, c->stream>>>(c->d_rng, RNG_LEN, c->n_dev, n_max, m1, m2, h, d_samples, d_flag);
+    else
+      sample_kernel<5, false><<<1, 1024, 0, c->stream>>>(c->d_rng, RNG_LEN, c->n_dev, n_max, nullptr, nullptr, h, d_samples,
+                                                       d_flag);
+  }
+  VO_CUDA(cudaGetLastError());
+  return VO_OK;
+}
+
 // ================================================================ launchers
 static Intrinsics intr(const vo_ctx* c) { return Intrinsics{c->p.fx, c->p.fy, c->p.cx, c->p.cy}; }
 
@@ -454,7 +575,7 @@ int fmat_score_launch(vo_ctx* c, const float2* m1, const float2* m2, int n, cons
   dim3 g(div_up(n, SCORE_TPB), div_up(h * 3, SCORE_HB));
   {
     LaunchScope ls(c, VO_K_FMAT_SCORE);
-    fmat_score_kernel<<<g, SCORE_TPB, 0, c->stream>>>(m1, m2, n, d_models, d_counts, h * 3, thr2, nullptr);
+    fmat_score_kernel<<<g, SCORE_TPB, 0, c->stream>>>(m1, m2, n, d_models, d_counts, h * 3, thr2, nullptr, c->n_dev);
   }
   VO_CUDA(cudaGetLastError());
   return VO_OK;
@@ -465,7 +586,7 @@ int fmat_mask_launch(vo_ctx* c, const float2* m1, const float2* m2, int n, const
   if (n <= 0) return VO_OK;
   {
     LaunchScope ls(c, VO_K_FMAT_SCORE);
-    fmat_mask_kernel<<<div_up(n, 256), 256, 0, c->stream>>>(m1, m2, n, d_models, d_sel, thr2, d_mask);
+    fmat_mask_kernel<<<div_up(n, 256), 256, 0, c->stream>>>(m1, m2, n, d_models, d_sel, thr2, d_mask, c->n_dev);
   }
   VO_CUDA(cudaGetLastError());
   return VO_OK;
@@ -489,7 +610,7 @@ int pnp_score_launch(vo_ctx* c, const float3* xyz, const float2* xy, int n, cons
   dim3 g(div_up(n, SCORE_TPB), div_up(h, SCORE_HB));
   {
     LaunchScope ls(c, VO_K_PNP_SCORE);
-    pnp_score_kernel<<<g, SCORE_TPB, 0, c->stream>>>(xyz, xy, n, d_models, d_counts, h, intr(c), thr2, nullptr);
+    pnp_score_kernel<<<g, SCORE_TPB, 0, c->stream>>>(xyz, xy, n, d_models, d_counts, h, intr(c), thr2, nullptr, c->n_dev);
   }
   VO_CUDA(cudaGetLastError());
   return VO_OK;
@@ -500,7 +621,7 @@ int pnp_mask_launch(vo_ctx* c, const float3* xyz, const float2* xy, int n, const
   if (n <= 0) return VO_OK;
   {
     LaunchScope ls(c, VO_K_PNP_SCORE);
-    pnp_mask_kernel<<<div_up(n, 256), 256, 0, c->stream>>>(xyz, xy, n, d_models, d_sel, intr(c), thr2, d_mask);
+    pnp_mask_kernel<<<div_up(n, 256), 256, 0, c->stream>>>(xyz, xy, n, d_models, d_sel, intr(c), thr2, d_mask, c->n_dev);
   }
   VO_CUDA(cudaGetLastError());
   return VO_OK;
@@ -511,7 +632,7 @@ int select_launch(vo_ctx* c, const int32_t* d_counts, int n_samples, int models_
   {
     LaunchScope ls(c, VO_K_SELECT);
     select_kernel<<<1, SEL_THREADS, 0, c->stream>>>(d_counts, n_samples, models_per_sample, model_points, n_points,
-                                                    conf, max_iters, d_sel);
+                                                    conf, max_iters, d_sel, c->n_dev);
   }
   VO_CUDA(cudaGetLastError());
   return VO_OK;

@@ -4,14 +4,20 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from ros_stereo_slam_b200 import VisualFrontEnd, _lib
 fe = VisualFrontEnd(grid_step=5, pnp_iters=1024, kf_min_inliers=2**31 - 1, ransac_exhaustive=1)
-Ls = [fe.synth_render(0, i, 0) for i in range(8)]
-Rs = [fe.synth_render(0, i, 1) for i in range(8)]
-fe.seq_init(Ls[0], Rs[0])
+W, H = 1241, 376
+d = C.c_void_p()
+_lib.check(fe.lib.vo_alloc_dev(fe.h, C.byref(d), C.c_uint64(16 * W * H)))
+for i in range(8):
+    for eye in (0, 1):
+        _lib.check(fe.lib.vo_synth_render_dev(fe.h, 0, i, eye, C.c_void_p(d.value + (2 * i + eye) * W * H)))
+Ls = [d.value + (2 * i) * W * H for i in range(8)]
+Rs = [d.value + (2 * i + 1) * W * H for i in range(8)]
+fe.seq_init(Ls[0], Rs[0], is_device=True)
 for i in range(1, 6):
-    fe.seq_track(Ls[i], Rs[i])
+    fe.seq_track(Ls[i], Rs[i], is_device=True)
 fe.profile_enable("all"); fe.profile_read(reset=True)
 import time
-t0 = time.perf_counter(); fe.seq_track(Ls[6], Rs[6]); dt = time.perf_counter() - t0
+t0 = time.perf_counter(); fe.seq_track(Ls[6], Rs[6], is_device=True); dt = time.perf_counter() - t0
 rows = np.zeros((512, 4), np.float32); n = C.c_int()
 _lib.check(fe.lib.vo_debug_timeline(fe.h, rows.ctypes.data_as(C.c_void_p), 512, C.byref(n)))
 rows = rows[:n.value]
