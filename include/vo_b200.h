@@ -123,6 +123,11 @@ int vo_lk_track(vo_ctx* ctx, const uint8_t* prev, const uint8_t* next, int strid
  * output may be NULL.  w/h receive the level size. */
 int vo_debug_pyramid_level(vo_ctx* ctx, const uint8_t* img, int stride, int level,
                            uint8_t* out_level, int16_t* out_deriv, int* w, int* h);
+/* Same, including `pad` (<= 21) border pixels on every side as the LK window sees them:
+ * out_level is (h+2*pad) x (w+2*pad) u8 (BORDER_REFLECT_101), out_deriv (h+2*pad) x (w+2*pad)
+ * x 2 int16 (zero border) -- the padded layout cv::buildOpticalFlowPyramid produces. */
+int vo_debug_pyramid_padded(vo_ctx* ctx, const uint8_t* img, int stride, int level, int pad,
+                            uint8_t* out_level, int16_t* out_deriv);
 
 /* ---- a-5  cv::findFundamentalMat(pts1, pts2, FM_RANSAC, thr, conf, mask)
  * src/tracking.cpp:34 (thr 3.0) and :75 (thr 1.0).

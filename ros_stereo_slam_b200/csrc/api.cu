@@ -24,6 +24,10 @@ void set_error(const char* fmt, ...) {
 }
 
 LaunchScope::LaunchScope(vo_ctx* ctx, int k) : c(ctx), kind(k) {
+  if (c->capturing) {
+    c->captured_launches++;
+    return;
+  }
   c->launch_count++;
   if (c->prof.mask & (1u << k)) {
     auto get = [&]() {
@@ -63,6 +67,8 @@ static void prof_drain(vo_ctx* c) {
   c->prof.pending.clear();
 }
 
+static void make_projections(const vo_params& p, double* P /*24*/);
+
 static int alloc_chain(vo_ctx* c) {
   const vo_params* p = &c->p;
   {
@@ -96,6 +102,17 @@ static int alloc_chain(vo_ctx* c) {
   VO_CUDA(cudaMalloc(&c->d_count, 16 * sizeof(int)));
   VO_CUDA(cudaMallocHost(&c->h_count, 16 * sizeof(int)));
   VO_CUDA(cudaMalloc(&c->d_tile_state, 256 * sizeof(unsigned long long)));
+  {
+    const unsigned one = 1;
+    VO_CUDA(cudaMalloc(&c->d_epoch, sizeof(unsigned)));
+    VO_CUDA(cudaMemcpy(c->d_epoch, &one, sizeof(one), cudaMemcpyHostToDevice));
+    VO_CUDA(cudaMalloc(&c->d_seq_n, sizeof(int)));
+    VO_CUDA(cudaMallocHost(&c->h_seq_n, sizeof(int)));
+    double P[24];
+    make_projections(c->p, P);
+    VO_CUDA(cudaMalloc(&c->d_Pst, sizeof(P)));
+    VO_CUDA(cudaMemcpy(c->d_Pst, P, sizeof(P), cudaMemcpyHostToDevice));
+  }
   VO_CUDA(cudaMemsetAsync(c->d_tile_state, 0, 256 * sizeof(unsigned long long), c->stream));
   VO_CUDA(cudaMallocHost(&c->h_pts, (size_t)cap * 8 * sizeof(float)));
   const int ch = p->max_hypotheses;
@@ -132,9 +149,11 @@ static void free_chain(vo_ctx* c) {
   void* dev[] = {c->d_xy_in, c->d_xy_trk, c->d_status, c->d_err, c->d_xyz_in, c->d_c_ref, c->d_c_trk, c->d_c_xyz,
                  c->d_f_ref, c->d_f_trk, c->d_f_xyz, c->d_xyz_tmp, c->d_mask, c->d_idx, c->d_seq_xy, c->d_seq_xyz,
                  c->d_count, c->d_tile_state, c->d_samples, c->d_models, c->d_counts, c->d_sel, c->d_pose, c->d_cam,
-                 c->d_lk_work, c->d_rng, c->d_flags};
+                 c->d_lk_work, c->d_rng, c->d_flags, c->d_epoch, c->d_seq_n, c->d_Pst};
   for (void* p : dev) cudaFree(p);
-  void* host[] = {c->h_count, c->h_pts, c->h_samples, c->h_sel, c->h_pose, c->h_lk_work, c->h_flags};
+  void* host[] = {c->h_count, c->h_pts, c->h_samples, c->h_sel, c->h_pose, c->h_lk_work, c->h_flags, c->h_seq_n};
+  for (int i = 0; i < 2; i++)
+    if (c->frame_graph[i]) cudaGraphExecDestroy(c->frame_graph[i]);
   for (void* p : host) cudaFreeHost(p);
   for (auto& pe : c->prof.pending) {
     cudaEventDestroy(pe.a);
@@ -722,13 +741,17 @@ static bool fmat_fused_valid(const vo_ctx* c, int m, int H) {
   return c->h_flags[0] == 0 && m >= 15 && c->h_sel[4] >= 0 && c->h_sel[5] <= H;
 }
 
+// d_n (optional): device-resident number of reference points (n is then only the upper bound the
+// grids are sized with) -- what a CUDA-graph replay needs.
 static int track_pnp_fused_enqueue(vo_ctx* c, int slot_ref, int slot_cur, const float2* d_ref_xy,
-                                   const float3* d_ref_xyz, int n) {
+                                   const float3* d_ref_xyz, int n, const int* d_n = nullptr) {
   const int iters = std::max(c->p.pnp_iters, 1);
   const int Hp = c->p.ransac_exhaustive ? iters : std::min(iters, PNP_CHUNK);
   const float thr2 = (float)(c->p.pnp_thr * c->p.pnp_thr);
+  c->n_dev = d_n;
   VO_TRY(lk_launch(c, slot_ref, slot_cur, d_ref_xy, n, c->d_xy_trk, c->d_status, c->d_err));
   VO_TRY(compact_launch(c, c->d_status, n, d_ref_xy, c->d_c_ref, c->d_xy_trk, c->d_c_trk, d_ref_xyz, c->d_c_xyz, nullptr, 0));
+  c->n_dev = nullptr;
   VO_TRY(enqueue_fmat_fused(c, n, c->p.f_thr_temporal, true));
   // PnP on d_f_* (count in d_count[1])
   c->n_dev = c->d_count + 1;
@@ -775,11 +798,8 @@ static int stereo_fused_enqueue(vo_ctx* c, int slot_l, int slot_r, int* n_grid_o
   VO_TRY(lk_launch(c, slot_l, slot_r, c->d_xy_in, ng, c->d_xy_trk, c->d_status, c->d_err));
   VO_TRY(compact_launch(c, c->d_status, ng, c->d_xy_in, c->d_c_ref, c->d_xy_trk, c->d_c_trk, nullptr, nullptr, nullptr, 0));
   VO_TRY(enqueue_fmat_fused(c, ng, c->p.f_thr_stereo, false));
-  double P[24];
-  make_projections(c->p, P);
-  VO_CUDA(cudaMemcpyAsync(c->d_cam, P, sizeof(P), cudaMemcpyHostToDevice, c->stream));
   c->n_dev = c->d_count + 1;
-  VO_TRY(triangulate_launch(c, c->d_cam, c->d_f_ref, c->d_f_trk, ng, c->d_xyz_tmp, nullptr, nullptr));
+  VO_TRY(triangulate_launch(c, c->d_Pst, c->d_f_ref, c->d_f_trk, ng, c->d_xyz_tmp, nullptr, nullptr));
   c->n_dev = nullptr;
   VO_CUDA(cudaMemcpyAsync(c->h_sel, c->d_sel, 8 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   VO_CUDA(cudaMemcpyAsync(c->h_flags, c->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -923,6 +943,24 @@ int vo_debug_pyramid_level(vo_ctx* c, const uint8_t* img, int stride, int level,
   if (out_deriv)
     VO_CUDA(cudaMemcpy2DAsync(out_deriv, (size_t)L.w * 4, L.deriv + (size_t)PAD_Y * L.pitch + PAD_L,
                               (size_t)L.pitch * 4, (size_t)L.w * 4, L.h, cudaMemcpyDeviceToHost, c->stream));
+  return sync_stream(c);
+}
+
+int vo_debug_pyramid_padded(vo_ctx* c, const uint8_t* img, int stride, int level, int pad, uint8_t* out_level,
+                            int16_t* out_deriv) {
+  CHECK_CTX(c);
+  if (!img || pad < 0 || pad > PAD_Y) return VO_ERR_INVALID_ARG;
+  VO_TRY(load_image(c, 0, img, stride, 0, true));
+  Pyramid& p = c->pyr[0];
+  if (level < 0 || level >= p.nlevels) return VO_ERR_INVALID_ARG;
+  PyrLevel& L = p.lv[level];
+  const size_t off = (size_t)(PAD_Y - pad) * L.pitch + (PAD_L - pad);
+  const int pw = L.w + 2 * pad, ph = L.h + 2 * pad;
+  if (out_level)
+    VO_CUDA(cudaMemcpy2DAsync(out_level, pw, L.img + off, L.pitch, pw, ph, cudaMemcpyDeviceToHost, c->stream));
+  if (out_deriv)
+    VO_CUDA(cudaMemcpy2DAsync(out_deriv, (size_t)pw * 4, L.deriv + off, (size_t)L.pitch * 4, (size_t)pw * 4, ph,
+                              cudaMemcpyDeviceToHost, c->stream));
   return sync_stream(c);
 }
 
@@ -1231,7 +1269,9 @@ int vo_seq_track(vo_ctx* c, const uint8_t* left, const uint8_t* right, int strid
   if (!left || !out || c->seq_ref_slot < 0) return VO_ERR_INVALID_ARG;
   memset(out, 0, sizeof(*out));
   const int ref = c->seq_ref_slot, cur = 1 - ref;
-  VO_TRY(load_image(c, cur, left, stride, is_device, false));
+  // with derivatives: this left image is the previous image of this frame's stereo LK and of the
+  // next frame's temporal LK (one fused launch builds levels, borders and Scharr planes)
+  VO_TRY(load_image(c, cur, left, stride, is_device, true));
   out->n_lk_in = c->seq_n;
 
   // A keyframe that is known before PnP (caller forces it, or the policy fires on every frame

@@ -40,6 +40,8 @@ struct Pyramid {
   int nlevels = 0;
   bool has_deriv = false;
   uint64_t stamp = 0;  // content tag (0 = empty)
+  // CUtensorMap (TMA descriptor) of the level-0 interior: u8, dims (w, h), row stride = pitch
+  alignas(64) unsigned char tmap0[128] = {0};
 };
 
 struct PyrLevelView {  // what kernels see
@@ -109,7 +111,14 @@ struct vo_ctx {
   int* d_count = nullptr;                                // small int scratch (16 ints)
   int* h_count = nullptr;                                // pinned mirror
   unsigned long long* d_tile_state = nullptr;            // compaction look-back (epoch<<32 | tile total)
-  unsigned compact_epoch = 0;
+  unsigned* d_epoch = nullptr;                           // device-side launch epoch of the compaction
+  bool capturing = false;                                // launches are being recorded into a CUDA graph
+  int64_t captured_launches = 0;
+  cudaGraphExec_t frame_graph[2] = {nullptr, nullptr};   // per `cur` slot (primary chain only)
+  int64_t frame_graph_launches[2] = {0, 0};
+  int* d_seq_n = nullptr;                                // device copy of seq_n for graph replays
+  int* h_seq_n = nullptr;
+  double* d_Pst = nullptr;                               // P1 | P2 of the stereo rig (constant)
   // When set, kernels take their element count from this device pointer (clamped to the host-side
   // upper bound they were launched with): lets a whole chain run without a host round trip.
   const int* n_dev = nullptr;

@@ -144,7 +144,8 @@ __device__ __forceinline__ void seg_bilinear(const unsigned* tile, int row, unsi
 __global__ void __launch_bounds__(128)
 lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n, float2* __restrict__ next_pts,
           uint8_t* __restrict__ status, float* __restrict__ err, int max_iters, double eps_sq, float min_eig_thr,
-          unsigned long long* __restrict__ work) {
+          unsigned long long* __restrict__ work, const int* __restrict__ n_dev) {
+  if (n_dev) n = min(n, *n_dev);
   __shared__ unsigned smem[LK_WARPS * WARP_SMEM_WORDS];
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -384,7 +385,7 @@ int lk_launch(vo_ctx* c, int slot_prev, int slot_next, const float2* d_prev, int
     LaunchScope ls(c, VO_K_LK);
     lk_kernel<<<blocks, threads, 0, c->stream>>>(pyr_view(c->pyr[slot_prev]), pyr_view(c->pyr[slot_next]), d_prev, n,
                                                  d_next, d_status, d_err, max_iters, eps, (float)c->p.lk_min_eig,
-                                                 c->d_lk_work);
+                                                 c->d_lk_work, c->n_dev);
   }
   VO_CUDA(cudaGetLastError());
   return VO_OK;

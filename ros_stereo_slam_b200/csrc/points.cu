@@ -52,8 +52,11 @@ __global__ void __launch_bounds__(CP_THREADS)
 compact_kernel(const uint8_t* __restrict__ flags, int n, const float2* __restrict__ a_in, float2* __restrict__ a_out,
                const float2* __restrict__ b_in, float2* __restrict__ b_out, const float3* __restrict__ c_in,
                float3* __restrict__ c_out, int32_t* __restrict__ idx_out, int* __restrict__ count_out,
-               volatile unsigned long long* tile_state, unsigned epoch, const int* __restrict__ n_dev) {
+               volatile unsigned long long* tile_state, unsigned* epoch_ctr, const int* __restrict__ n_dev) {
   if (n_dev) n = min(n, *n_dev);
+  // launch epoch from a device counter (graph-replay safe): every CTA reads it before publishing its
+  // tile total, and the last CTA -- whose look-back has then seen every publication -- bumps it
+  const unsigned epoch = *reinterpret_cast<volatile unsigned*>(epoch_ctr);
   __shared__ int warp_tot[CP_THREADS / 32];
   __shared__ int s_base;
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
@@ -103,7 +106,10 @@ compact_kernel(const uint8_t* __restrict__ flags, int n, const float2* __restric
     for (int d = 16; d > 0; d >>= 1) base += __shfl_xor_sync(0xffffffffu, base, d);
     if (lane == 0) {
       s_base = base;
-      if (blockIdx.x == gridDim.x - 1) *count_out = base + tile_total;
+      if (blockIdx.x == gridDim.x - 1) {
+        *count_out = base + tile_total;
+        *epoch_ctr = epoch + 1;
+      }
     }
   }
   __syncthreads();
@@ -131,7 +137,7 @@ int compact_launch(vo_ctx* c, const uint8_t* d_flags, int n, const float2* a_in,
     LaunchScope ls(c, VO_K_COMPACT);
     compact_kernel<<<div_up(n, CP_TILE), CP_THREADS, 0, c->stream>>>(d_flags, n, a_in, a_out, b_in, b_out, c_in, c_out,
                                                                      idx_out, c->d_count + count_slot, c->d_tile_state,
-                                                                     ++c->compact_epoch, c->n_dev);
+                                                                     c->d_epoch, c->n_dev);
   }
   VO_CUDA(cudaGetLastError());
   return VO_OK;

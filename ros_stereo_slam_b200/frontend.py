@@ -105,6 +105,16 @@ class VisualFrontEnd:
         check(self.lib.vo_debug_pyramid_level(self.h, _p(a), a.strides[0], level, _p(lv), _p(dv), C.byref(w), C.byref(h)))
         return lv, dv
 
+    def pyramid_padded(self, img, level, pad=21):
+        """Level `level` and its derivative with `pad` border pixels, as the LK window sees them."""
+        a = _u8img(img)
+        w, h = C.c_int(), C.c_int()
+        check(self.lib.vo_debug_pyramid_level(self.h, _p(a), a.strides[0], level, None, None, C.byref(w), C.byref(h)))
+        lv = np.zeros((h.value + 2 * pad, w.value + 2 * pad), np.uint8)
+        dv = np.zeros((h.value + 2 * pad, w.value + 2 * pad, 2), np.int16)
+        check(self.lib.vo_debug_pyramid_padded(self.h, _p(a), a.strides[0], level, pad, _p(lv), _p(dv)))
+        return lv, dv
+
     def findFundamentalMat(self, pts1, pts2, thr, conf=0.99, samples=None):
         """cv::findFundamentalMat(FM_RANSAC) -> (F 3x3 or None, mask (N,) u8, n_inliers)."""
         a, b = _f32(pts1, 2), _f32(pts2, 2)

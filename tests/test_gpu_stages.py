@@ -58,6 +58,47 @@ def test_pyramid_and_scharr_bit_exact(fe, G):
         assert int(np.abs(dv.astype(np.int64)).sum()) == int(G["deriv_abs_sums"][l])
 
 
+def _padded_ref(img, levels, pad):
+    n, pyr = cv2.buildOpticalFlowPyramid(img, (21, 21), levels, withDerivatives=True)
+    out = []
+    for l in range(n + 1):
+        lv = cv2.copyMakeBorder(pyr[2 * l], pad, pad, pad, pad, cv2.BORDER_REFLECT_101)
+        dv = cv2.copyMakeBorder(pyr[2 * l + 1], pad, pad, pad, pad, cv2.BORDER_CONSTANT, value=0)
+        out.append((lv, dv))
+    return out
+
+
+def test_fused_pyramid_padded_borders_bit_exact(fe, G):
+    """The one-launch TMA pyramid kernel writes every level, its REFLECT_101 border (21 px, what the
+    LK window can reach) and the zero-bordered Scharr planes exactly as buildOpticalFlowPyramid does."""
+    ref = _padded_ref(G["L0"], 3, 21)
+    assert len(ref) == 4
+    for l, (lv0, dv0) in enumerate(ref):
+        lv, dv = fe.pyramid_padded(G["L0"], l, 21)
+        assert np.array_equal(lv, lv0), "level %d" % l
+        assert np.array_equal(dv, dv0), "deriv %d" % l
+
+
+@pytest.mark.parametrize("size", [(333, 190), (64, 64), (257, 129), (1000, 64), (640, 480), (100, 70)])
+def test_fused_pyramid_other_sizes(size):
+    """Odd sizes, sizes below one CTA block, early stop of the level chain (next level <= winSize)."""
+    w, h = size
+    rng = np.random.default_rng(w * 1000 + h)
+    img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    img = cv2.GaussianBlur(img, (5, 5), 0)
+    f = make_frontend(width=w, height=h)
+    try:
+        ref = _padded_ref(img, 3, 21)
+        for l, (lv0, dv0) in enumerate(ref):
+            lv, dv = f.pyramid_padded(img, l, 21)
+            assert np.array_equal(lv, lv0), "level %d of %dx%d" % (l, w, h)
+            assert np.array_equal(dv, dv0), "deriv %d of %dx%d" % (l, w, h)
+        with pytest.raises(Exception):
+            f.pyramid_padded(img, len(ref), 21)       # no such level: the chain stopped where OpenCV's does
+    finally:
+        f.close()
+
+
 @pytest.mark.parametrize("pair", ["temporal", "stereo"])
 @pytest.mark.parametrize("step", [30, 9])
 def test_lk_matches_opencv(fe, G, pair, step):
