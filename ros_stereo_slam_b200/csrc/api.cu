@@ -24,10 +24,6 @@ void set_error(const char* fmt, ...) {
 }
 
 LaunchScope::LaunchScope(vo_ctx* ctx, int k) : c(ctx), kind(k) {
-  if (c->capturing) {
-    c->captured_launches++;
-    return;
-  }
   c->launch_count++;
   if (c->prof.mask & (1u << k)) {
     auto get = [&]() {
@@ -106,8 +102,6 @@ static int alloc_chain(vo_ctx* c) {
     const unsigned one = 1;
     VO_CUDA(cudaMalloc(&c->d_epoch, sizeof(unsigned)));
     VO_CUDA(cudaMemcpy(c->d_epoch, &one, sizeof(one), cudaMemcpyHostToDevice));
-    VO_CUDA(cudaMalloc(&c->d_seq_n, sizeof(int)));
-    VO_CUDA(cudaMallocHost(&c->h_seq_n, sizeof(int)));
     double P[24];
     make_projections(c->p, P);
     VO_CUDA(cudaMalloc(&c->d_Pst, sizeof(P)));
@@ -149,11 +143,9 @@ static void free_chain(vo_ctx* c) {
   void* dev[] = {c->d_xy_in, c->d_xy_trk, c->d_status, c->d_err, c->d_xyz_in, c->d_c_ref, c->d_c_trk, c->d_c_xyz,
                  c->d_f_ref, c->d_f_trk, c->d_f_xyz, c->d_xyz_tmp, c->d_mask, c->d_idx, c->d_seq_xy, c->d_seq_xyz,
                  c->d_count, c->d_tile_state, c->d_samples, c->d_models, c->d_counts, c->d_sel, c->d_pose, c->d_cam,
-                 c->d_lk_work, c->d_rng, c->d_flags, c->d_epoch, c->d_seq_n, c->d_Pst};
+                 c->d_lk_work, c->d_rng, c->d_flags, c->d_epoch, c->d_Pst};
   for (void* p : dev) cudaFree(p);
-  void* host[] = {c->h_count, c->h_pts, c->h_samples, c->h_sel, c->h_pose, c->h_lk_work, c->h_flags, c->h_seq_n};
-  for (int i = 0; i < 2; i++)
-    if (c->frame_graph[i]) cudaGraphExecDestroy(c->frame_graph[i]);
+  void* host[] = {c->h_count, c->h_pts, c->h_samples, c->h_sel, c->h_pose, c->h_lk_work, c->h_flags};
   for (void* p : host) cudaFreeHost(p);
   for (auto& pe : c->prof.pending) {
     cudaEventDestroy(pe.a);
@@ -304,6 +296,7 @@ int vo_create(const vo_params* p, vo_ctx** out) {
   }
   if (r == VO_OK) {
     if (cudaEventCreateWithFlags(&c->ev_left, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_lk, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_stereo, cudaEventDisableTiming) != cudaSuccess) {
       set_error("cudaEventCreate failed");
       r = VO_ERR_CUDA;
@@ -348,6 +341,7 @@ int vo_destroy(vo_ctx* c) {
   }
   if (c->ev_left) cudaEventDestroy(c->ev_left);
   if (c->ev_stereo) cudaEventDestroy(c->ev_stereo);
+  if (c->ev_lk) cudaEventDestroy(c->ev_lk);
   free_chain(c);
   delete c;
   return VO_OK;
@@ -712,6 +706,16 @@ static int pnp_two_attempts(vo_ctx* c, int k, int* n_inl, int* attempt) {
 // count -> second PnP attempt, sampler overflow) is detected after that synchronisation and the
 // stage is redone on the host-driven path above, which handles every case.
 constexpr int F_CHUNK = 48, PNP_CHUNK = 32;
+// First-chunk size of the fused F-RANSAC.  OpenCV stops after niters = log(1-conf)/log(1-w^7) samples
+// (w = inlier ratio of the best model so far): 48 samples cover w >= 0.71, which the stereo pairs
+// (threshold 3 px) always reach; the temporal pairs (threshold 1 px) sit at w = 0.60..0.70 on ~13 % of
+// the bench frames (niters 49..143), and every miss costs a host-driven redo of F + PnP (~1 ms).
+// 96 samples cover w >= 0.64 for +14 us of scoring.
+constexpr int F_CHUNK_TEMPORAL = 96;
+static int fused_f_chunk(const vo_ctx* c, bool temporal) {
+  if (c->p.f_exhaustive) return std::min(std::max(c->p.f_max_iters, 1), 1024);
+  return std::min(temporal ? F_CHUNK_TEMPORAL : F_CHUNK, std::max(c->p.f_max_iters, 1));
+}
 
 struct FusedStatus {
   int m = 0, k = 0, n_inl = 0;
@@ -721,7 +725,7 @@ struct FusedStatus {
 // F-RANSAC part of a fused chain on d_c_* (count in d_count[0], upper bound n_max):
 // sampling, solve, score, select (-> d_sel + 4), mask, compaction into d_f_* (count d_count[1]).
 static int enqueue_fmat_fused(vo_ctx* c, int n_max, double thr, bool with_xyz) {
-  const int H = c->p.f_exhaustive ? std::min(std::max(c->p.f_max_iters, 1), 1024) : F_CHUNK;
+  const int H = fused_f_chunk(c, with_xyz);   // with_xyz <=> temporal pair
   const float thr2 = (float)(thr * thr);
   c->n_dev = c->d_count + 0;
   VO_TRY(sample_launch(c, 7, c->d_c_ref, c->d_c_trk, n_max, H, c->d_samples, c->d_flags + 0));
@@ -738,7 +742,12 @@ static int enqueue_fmat_fused(vo_ctx* c, int n_max, double thr, bool with_xyz) {
 
 static bool fmat_fused_valid(const vo_ctx* c, int m, int H) {
   // h_sel[4..7] = F selection; the first chunk is final iff OpenCV's niters ended inside it
-  return c->h_flags[0] == 0 && m >= 15 && c->h_sel[4] >= 0 && c->h_sel[5] <= H;
+  const bool ok = c->h_flags[0] == 0 && m >= 15 && c->h_sel[4] >= 0 && c->h_sel[5] <= H;
+  static const bool dbg = getenv("VO_B200_DEBUG_FALLBACK") != nullptr;
+  if (dbg && !ok)
+    fprintf(stderr, "[vo fallback] F chain %d: flag %d m %d best %d niters %d count %d (H %d)\n", c->is_aux ? 1 : 0, c->h_flags[0],
+            m, c->h_sel[4], c->h_sel[5], c->h_sel[6], H);
+  return ok;
 }
 
 // d_n (optional): device-resident number of reference points (n is then only the upper bound the
@@ -750,6 +759,7 @@ static int track_pnp_fused_enqueue(vo_ctx* c, int slot_ref, int slot_cur, const 
   const float thr2 = (float)(c->p.pnp_thr * c->p.pnp_thr);
   c->n_dev = d_n;
   VO_TRY(lk_launch(c, slot_ref, slot_cur, d_ref_xy, n, c->d_xy_trk, c->d_status, c->d_err));
+  if (c->ev_lk_done) VO_CUDA(cudaEventRecord(c->ev_lk_done, c->stream));
   VO_TRY(compact_launch(c, c->d_status, n, d_ref_xy, c->d_c_ref, c->d_xy_trk, c->d_c_trk, d_ref_xyz, c->d_c_xyz, nullptr, 0));
   c->n_dev = nullptr;
   VO_TRY(enqueue_fmat_fused(c, n, c->p.f_thr_temporal, true));
@@ -772,7 +782,7 @@ static int track_pnp_fused_enqueue(vo_ctx* c, int slot_ref, int slot_cur, const 
 }
 
 static int track_pnp_fused_finish(vo_ctx* c, FusedStatus* st) {
-  const int Hf = c->p.f_exhaustive ? std::min(std::max(c->p.f_max_iters, 1), 1024) : F_CHUNK;
+  const int Hf = fused_f_chunk(c, true);
   const int iters = std::max(c->p.pnp_iters, 1);
   const int Hp = c->p.ransac_exhaustive ? iters : std::min(iters, PNP_CHUNK);
   VO_TRY(sync_stream(c));
@@ -782,11 +792,15 @@ static int track_pnp_fused_finish(vo_ctx* c, FusedStatus* st) {
   st->f_ok = fmat_fused_valid(c, st->m, Hf);
   st->pnp_ok = st->f_ok && c->h_flags[1] == 0 && st->k > 5 && c->h_sel[0] >= 0 && c->h_sel[1] <= Hp &&
                st->n_inl >= c->p.pnp_min_inliers;
+  static const bool dbg = getenv("VO_B200_DEBUG_FALLBACK") != nullptr;
+  if (dbg && st->f_ok && !st->pnp_ok)
+    fprintf(stderr, "[vo fallback] PnP: flag %d k %d best %d niters %d n_inl %d (H %d)\n", c->h_flags[1], st->k, c->h_sel[0],
+            c->h_sel[1], st->n_inl, Hp);
   return VO_OK;
 }
 
 // stereoTriangulate as one fused chain.  Same outputs as stereo_pipeline (pose == NULL variant).
-static int stereo_fused_enqueue(vo_ctx* c, int slot_l, int slot_r, int* n_grid_out) {
+static int stereo_fused_enqueue(vo_ctx* c, int slot_l, int slot_r, int* n_grid_out, cudaEvent_t lk_after = nullptr) {
   int ng = 0;
   VO_TRY(grid_launch(c, c->p.height, c->p.width, c->p.grid_step, c->d_xy_in, &ng));
   if (n_grid_out) *n_grid_out = ng;
@@ -795,6 +809,9 @@ static int stereo_fused_enqueue(vo_ctx* c, int slot_l, int slot_r, int* n_grid_o
     VO_CUDA(cudaMemcpyAsync(c->h_count, c->d_count, 16 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     return VO_OK;
   }
+  // lk_after: the other chain's LK launch.  Either LK fills every SM; side by side they only slow each
+  // other down, back to back this one overlaps the other chain's latency-bound RANSAC solvers instead.
+  if (lk_after) VO_CUDA(cudaStreamWaitEvent(c->stream, lk_after, 0));
   VO_TRY(lk_launch(c, slot_l, slot_r, c->d_xy_in, ng, c->d_xy_trk, c->d_status, c->d_err));
   VO_TRY(compact_launch(c, c->d_status, ng, c->d_xy_in, c->d_c_ref, c->d_xy_trk, c->d_c_trk, nullptr, nullptr, nullptr, 0));
   VO_TRY(enqueue_fmat_fused(c, ng, c->p.f_thr_stereo, false));
@@ -811,7 +828,7 @@ static int stereo_fused_enqueue(vo_ctx* c, int slot_l, int slot_r, int* n_grid_o
 // redo F-RANSAC + triangulation on the host-driven path.
 // Result: d_f_ref (left 2-D), d_xyz_tmp (camera frame), *n_out points.
 static int stereo_fused_finish(vo_ctx* c, int* n_out) {
-  const int Hf = c->p.f_exhaustive ? std::min(std::max(c->p.f_max_iters, 1), 1024) : F_CHUNK;
+  const int Hf = fused_f_chunk(c, false);
   VO_TRY(sync_stream(c));
   *n_out = c->h_count[1];
   if (c->h_count[0] == 0) {
@@ -1282,7 +1299,14 @@ int vo_seq_track(vo_ctx* c, const uint8_t* left, const uint8_t* right, int strid
   int kk = 0, ng = 0;
   int k = 0, ni = 0, att = 1;
   int r;
-  if (kf_known && c->seq_n > 0 && temporal_fusable(c)) {
+  // Two drivers for the dual-chain frame.  Measured on the bench workload (B200, 200 frames):
+  //   host-driven chains, stereo chain on the worker thread (2-3 synchronisations per chain)  956 frames/s, e2e 910
+  //   fused single-sync chains enqueued by this thread (device-side sampling)                  919 frames/s, e2e 874
+  // The fused chains are what the single-chain entry points use (one synchronisation per call); with two
+  // chains in flight the host-driven form still wins, so it is the default here.  VO_B200_SEQ_FUSED=1 selects
+  // the other one.
+  static const bool host_driven = getenv("VO_B200_SEQ_FUSED") == nullptr;
+  if (kf_known && c->seq_n > 0 && temporal_fusable(c) && !getenv("VO_B200_SEQ_WORKER") && !host_driven) {
     // both chains are enqueued by this thread, the critical one (tracking + PnP, high-priority
     // stream) first; one synchronisation per chain at the end
     VO_CUDA(cudaEventRecord(c->ev_left, c->stream));           // cur-left pyramid is complete
@@ -1293,10 +1317,14 @@ int vo_seq_track(vo_ctx* c, const uint8_t* left, const uint8_t* right, int strid
       if (rs == VO_OK) rs = stereo_fused_enqueue(a, cur, 2, &ng);
       VO_TRY(track_pnp_fused_enqueue(c, ref, cur, c->d_seq_xy, c->d_seq_xyz, c->seq_n));
     } else {
-      VO_TRY(track_pnp_fused_enqueue(c, ref, cur, c->d_seq_xy, c->d_seq_xyz, c->seq_n));
+      static const bool lk_order = getenv("VO_B200_LK_ORDER") != nullptr;   // measured: slower (835 vs 853 frames/s)
+      c->ev_lk_done = lk_order ? c->ev_lk : nullptr;
+      const int rt = track_pnp_fused_enqueue(c, ref, cur, c->d_seq_xy, c->d_seq_xyz, c->seq_n);
+      c->ev_lk_done = nullptr;
+      VO_TRY(rt);
       VO_CUDA(cudaStreamWaitEvent(a->stream, c->ev_left, 0));
       rs = load_image(a, 2, right, stride, is_device, false);
-      if (rs == VO_OK) rs = stereo_fused_enqueue(a, cur, 2, &ng);
+      if (rs == VO_OK) rs = stereo_fused_enqueue(a, cur, 2, &ng, lk_order ? c->ev_lk : nullptr);
     }
     r = temporal_finish(c, &k, &ni, &att);
     if (rs == VO_OK) rs = stereo_fused_finish(a, &kk);
@@ -1309,12 +1337,18 @@ int vo_seq_track(vo_ctx* c, const uint8_t* left, const uint8_t* right, int strid
       VO_CUDA(cudaStreamWaitEvent(a->stream, c->ev_left, 0));
       post_task(c, [=, &kk, &ng]() -> int {
         VO_TRY(load_image(a, 2, right, stride, is_device, false));
-        VO_TRY(stereo_any(a, cur, 2, &kk, &ng));                  // camera-frame xyz in a->d_xyz_tmp
+        if (host_driven) VO_TRY(stereo_pipeline(a, cur, 2, nullptr, &kk, &ng));
+        else VO_TRY(stereo_any(a, cur, 2, &kk, &ng));             // camera-frame xyz in a->d_xyz_tmp
         VO_CUDA(cudaEventRecord(c->ev_stereo, a->stream));
         return VO_OK;
       });
     }
-    r = temporal_any(c, ref, cur, c->d_seq_xy, c->d_seq_xyz, c->seq_n, &k, &ni, &att);
+    if (host_driven) {
+      r = track_pipeline(c, ref, cur, c->d_seq_xy, c->d_seq_xyz, c->seq_n, &k);
+      if (r == VO_OK) r = pnp_two_attempts(c, k, &ni, &att);
+    } else {
+      r = temporal_any(c, ref, cur, c->d_seq_xy, c->d_seq_xyz, c->seq_n, &k, &ni, &att);
+    }
     if (kf_known) {
       const int rs = wait_task(c);     // always join: the auxiliary chain must be idle on return
       if (r == VO_OK) r = rs;

@@ -88,7 +88,8 @@ struct vo_ctx {
   bool task_pending = false, task_done = false, quit = false;
   int task_result = 0;
   std::string task_error;
-  cudaEvent_t ev_left = nullptr, ev_stereo = nullptr;
+  cudaEvent_t ev_left = nullptr, ev_stereo = nullptr, ev_lk = nullptr;
+  cudaEvent_t ev_lk_done = nullptr;    // when set, track_pnp_fused_enqueue records it right after its LK launch
 
   // image staging + pyramids: slot 0/1 ping-pong left images (reference <-> current), slot 2 right
   uint8_t* d_raw[3] = {nullptr, nullptr, nullptr};
@@ -112,12 +113,6 @@ struct vo_ctx {
   int* h_count = nullptr;                                // pinned mirror
   unsigned long long* d_tile_state = nullptr;            // compaction look-back (epoch<<32 | tile total)
   unsigned* d_epoch = nullptr;                           // device-side launch epoch of the compaction
-  bool capturing = false;                                // launches are being recorded into a CUDA graph
-  int64_t captured_launches = 0;
-  cudaGraphExec_t frame_graph[2] = {nullptr, nullptr};   // per `cur` slot (primary chain only)
-  int64_t frame_graph_launches[2] = {0, 0};
-  int* d_seq_n = nullptr;                                // device copy of seq_n for graph replays
-  int* h_seq_n = nullptr;
   double* d_Pst = nullptr;                               // P1 | P2 of the stereo rig (constant)
   // When set, kernels take their element count from this device pointer (clamped to the host-side
   // upper bound they were launched with): lets a whole chain run without a host round trip.

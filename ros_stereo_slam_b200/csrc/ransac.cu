@@ -450,16 +450,25 @@ select_kernel(const int32_t* __restrict__ counts, int n_samples, int mps, int mo
 // that start, and a block prefix sum yields the true start positions; threads whose start moved
 // recompute.  Each round fixes at least the first wrong start, and exceptions are rare (a few per
 // thousand samples; a few per 48 on integer grids), so this converges in a handful of rounds.
+// Latency: the random stream window the block will consume (M*H values + slack) is staged into
+// shared memory with coalesced loads, so the draws of a subset are shared-memory reads instead of a
+// chain of dependent global loads, and the 2 x M points of the collinearity check are fetched with
+// independent loads before the 21 pair tests run out of registers.
+constexpr int SAMPLE_SLACK = 256;
+
 template <int M, bool CHECK>
 __global__ void __launch_bounds__(1024)
 sample_kernel(const uint32_t* __restrict__ raw, int raw_len, const int* __restrict__ n_dev, int n_max,
               const float2* __restrict__ m1, const float2* __restrict__ m2, int H, int32_t* __restrict__ out,
               int* __restrict__ flag) {
+  extern __shared__ uint32_t s_raw[];   // M*H + SAMPLE_SLACK values of the stream
   __shared__ int s_warp[32];
   __shared__ int s_bad;
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
   int n = n_max;
   if (n_dev) n = min(n, *n_dev);
+  const int staged = min(M * H + SAMPLE_SLACK, raw_len);
+  for (int i = t; i < staged; i += blockDim.x) s_raw[i] = raw[i];
   if (t == 0) s_bad = 0;
   __syncthreads();
   if (n < M + 1) {   // too few points for this estimator's RANSAC path (host decides what to do)
@@ -474,13 +483,17 @@ sample_kernel(const uint32_t* __restrict__ raw, int raw_len, const int* __restri
       int p = pos;
       bool ok = false;
       for (int attempt = 0; attempt < 10000 && !ok; attempt++) {
+#pragma unroll
         for (int i = 0; i < M; i++) {
           int v;
           for (;;) {
             if (p >= raw_len) { s_bad = 1; v = 0; break; }
-            v = (int)(raw[p++] % (unsigned)n);
+            const uint32_t rv = p < staged ? s_raw[p] : raw[p];
+            p++;
+            v = (int)(rv % (unsigned)n);
             bool dup = false;
-            for (int k = 0; k < i; k++) dup |= (idx[k] == v);
+#pragma unroll
+            for (int k = 0; k < M; k++) dup |= (k < i && idx[k] == v);
             if (!dup) break;
           }
           idx[i] = v;
@@ -488,21 +501,25 @@ sample_kernel(const uint32_t* __restrict__ raw, int raw_len, const int* __restri
         ok = true;
         if (CHECK && !s_bad) {
           // haveCollinearPoints(ms1) || haveCollinearPoints(ms2): last point vs every earlier pair
-          for (int set = 0; set < 2 && ok; set++) {
+#pragma unroll
+          for (int set = 0; set < 2; set++) {
             const float2* pts = set ? m2 : m1;
-            const float2 pi = pts[idx[M - 1]];
-            for (int j = 0; j < M - 1 && ok; j++) {
-              const float2 pj = pts[idx[j]];
-              const double dx1 = (double)pj.x - (double)pi.x, dy1 = (double)pj.y - (double)pi.y;
-              for (int k = 0; k < j; k++) {
-                const float2 pk = pts[idx[k]];
-                const double dx2 = (double)pk.x - (double)pi.x, dy2 = (double)pk.y - (double)pi.y;
-                if (fabs(dx2 * dy1 - dy2 * dx1) <= (double)FLT_EPSILON * (fabs(dx1) + fabs(dy1) + fabs(dx2) + fabs(dy2))) {
-                  ok = false;
-                  break;
-                }
+            float2 q[M];
+#pragma unroll
+            for (int i = 0; i < M; i++) q[i] = pts[idx[i]];
+            const float2 pi = q[M - 1];
+            bool col = false;
+#pragma unroll
+            for (int j = 0; j < M - 1; j++) {
+              const double dx1 = (double)q[j].x - (double)pi.x, dy1 = (double)q[j].y - (double)pi.y;
+#pragma unroll
+              for (int k = 0; k < M - 1; k++) {
+                if (k >= j) continue;
+                const double dx2 = (double)q[k].x - (double)pi.x, dy2 = (double)q[k].y - (double)pi.y;
+                col |= fabs(dx2 * dy1 - dy2 * dx1) <= (double)FLT_EPSILON * (fabs(dx1) + fabs(dy1) + fabs(dx2) + fabs(dy2));
               }
             }
+            if (col) ok = false;
           }
         }
         if (s_bad) break;
@@ -545,11 +562,14 @@ int sample_launch(vo_ctx* c, int model_points, const float2* m1, const float2* m
   if (h <= 0 || h > 1024) return VO_ERR_INVALID_ARG;
   {
     LaunchScope ls(c, VO_K_SELECT);
+    // threads: one per sample, rounded up to whole warps (the block-wide scans assume full warps)
+    const int threads = std::min(1024, std::max(64, div_up(h, 32) * 32));
+    const size_t smem = (size_t)(model_points * h + SAMPLE_SLACK) * sizeof(uint32_t);
     if (model_points == 7)
-      sample_kernel<7, true><<<1, 1024, 0, c->stream>>>(c->d_rng, RNG_LEN, c->n_dev, n_max, m1, m2, h, d_samples, d_flag);
+      sample_kernel<7, true><<<1, threads, smem, c->stream>>>(c->d_rng, RNG_LEN, c->n_dev, n_max, m1, m2, h, d_samples, d_flag);
     else
-      sample_kernel<5, false><<<1, 1024, 0, c->stream>>>(c->d_rng, RNG_LEN, c->n_dev, n_max, nullptr, nullptr, h, d_samples,
-                                                       d_flag);
+      sample_kernel<5, false><<<1, threads, smem, c->stream>>>(c->d_rng, RNG_LEN, c->n_dev, n_max, nullptr, nullptr, h,
+                                                             d_samples, d_flag);
   }
   VO_CUDA(cudaGetLastError());
   return VO_OK;
