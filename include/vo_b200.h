@@ -62,7 +62,9 @@ typedef struct vo_params {
   double fx, fy, cx, cy;      /* 718.856, 718.856, 607.1928, 185.2157  (include/visualSLAM.h:82-87) */
   double baseline;            /* 0.54                                   (include/visualSLAM.h:68)    */
   int width, height;          /* 1241, 376 */
-  int channels;               /* 1 (3 = the reference's BGR input; not implemented yet) */
+  int channels;               /* 1 = gray; 3 = interleaved BGR as cv::imread returns it (what the reference
+                               * feeds calcOpticalFlowPyrLK, src/keyFrameManagement.cpp:52,64): every image
+                               * argument is then H x W x 3 with stride >= 3*width bytes */
   int lk_win;                 /* 21   cv::calcOpticalFlowPyrLK defaults (src/tracking.cpp:18,52) */
   int lk_max_level;           /* 3  */
   int lk_max_iters;           /* 30 */

@@ -2,7 +2,10 @@
 
 Restates what cv::calcOpticalFlowPyrLK does when the reference calls it with
 all defaults (src/tracking.cpp:18,52 of the reference tree: winSize 21x21,
-maxLevel 3, criteria (COUNT+EPS, 30, 0.01), flags 0, minEigThreshold 1e-4):
+maxLevel 3, criteria (COUNT+EPS, 30, 0.01), flags 0, minEigThreshold 1e-4),
+for 1-channel images and for the 3-channel BGR images the reference really
+passes (imread default, src/keyFrameManagement.cpp:52,64; every window sum then
+runs over the channels, minEig is normalised by the window area, err by area*cn):
 buildOpticalFlowPyramid (pyrDown 5-tap [1 4 6 4 1], REFLECT_101), the Scharr
 derivative of the previous image, and the per-level iteration in 14-bit
 fixed-point bilinear arithmetic.  The integer window sums are accumulated
@@ -104,14 +107,15 @@ def _weights(a, b):
 @_njit
 def _track_level(Ipad, Dpad, Jpad, rows, cols, level, max_level, win, max_count, eps, min_eig_thr,
                  prev_pts, next_pts, status, err, iters_out):
-    """One pyramid level of LKTrackerInvoker for every point.  Ipad/Jpad are the
-    REFLECT_101-padded (by win) levels, Dpad the zero-padded derivative."""
+    """One pyramid level of LKTrackerInvoker for every point.  Ipad/Jpad (cn, H, W) are the
+    REFLECT_101-padded (by win) levels, Dpad (cn, H, W, 2) the zero-padded derivative."""
     n = prev_pts.shape[0]
+    cn = Ipad.shape[0]
     half = np.float32((win - 1) * 0.5)
     scale = np.float32(1.0 / (1 << level))
-    Iw = np.zeros((win, win), np.int32)
-    Ix = np.zeros((win, win), np.int32)
-    Iy = np.zeros((win, win), np.int32)
+    Iw = np.zeros((cn, win, win), np.int32)
+    Ix = np.zeros((cn, win, win), np.int32)
+    Iy = np.zeros((cn, win, win), np.int32)
     flt_scale = np.float32(1.0 / (1 << 20))
     for p in range(n):
         px = np.float32(prev_pts[p, 0] * scale)
@@ -139,22 +143,23 @@ def _track_level(Ipad, Dpad, Jpad, rows, cols, level, max_level, win, max_count,
         sA11 = 0
         sA12 = 0
         sA22 = 0
-        for y in range(win):
-            for x in range(win):
-                yy = y + ipy + win
-                xx = x + ipx + win
-                ival = (int(Ipad[yy, xx]) * iw00 + int(Ipad[yy, xx + 1]) * iw01
-                        + int(Ipad[yy + 1, xx]) * iw10 + int(Ipad[yy + 1, xx + 1]) * iw11 + (1 << 8)) >> 9
-                ixv = (int(Dpad[yy, xx, 0]) * iw00 + int(Dpad[yy, xx + 1, 0]) * iw01
-                       + int(Dpad[yy + 1, xx, 0]) * iw10 + int(Dpad[yy + 1, xx + 1, 0]) * iw11 + (1 << 13)) >> 14
-                iyv = (int(Dpad[yy, xx, 1]) * iw00 + int(Dpad[yy, xx + 1, 1]) * iw01
-                       + int(Dpad[yy + 1, xx, 1]) * iw10 + int(Dpad[yy + 1, xx + 1, 1]) * iw11 + (1 << 13)) >> 14
-                Iw[y, x] = ival
-                Ix[y, x] = ixv
-                Iy[y, x] = iyv
-                sA11 += ixv * ixv
-                sA12 += ixv * iyv
-                sA22 += iyv * iyv
+        for c in range(cn):
+            for y in range(win):
+                for x in range(win):
+                    yy = y + ipy + win
+                    xx = x + ipx + win
+                    ival = (int(Ipad[c, yy, xx]) * iw00 + int(Ipad[c, yy, xx + 1]) * iw01
+                            + int(Ipad[c, yy + 1, xx]) * iw10 + int(Ipad[c, yy + 1, xx + 1]) * iw11 + (1 << 8)) >> 9
+                    ixv = (int(Dpad[c, yy, xx, 0]) * iw00 + int(Dpad[c, yy, xx + 1, 0]) * iw01
+                           + int(Dpad[c, yy + 1, xx, 0]) * iw10 + int(Dpad[c, yy + 1, xx + 1, 0]) * iw11 + (1 << 13)) >> 14
+                    iyv = (int(Dpad[c, yy, xx, 1]) * iw00 + int(Dpad[c, yy, xx + 1, 1]) * iw01
+                           + int(Dpad[c, yy + 1, xx, 1]) * iw10 + int(Dpad[c, yy + 1, xx + 1, 1]) * iw11 + (1 << 13)) >> 14
+                    Iw[c, y, x] = ival
+                    Ix[c, y, x] = ixv
+                    Iy[c, y, x] = iyv
+                    sA11 += ixv * ixv
+                    sA12 += ixv * iyv
+                    sA22 += iyv * iyv
         A11 = np.float32(np.float32(sA11) * flt_scale)
         A12 = np.float32(np.float32(sA12) * flt_scale)
         A22 = np.float32(np.float32(sA22) * flt_scale)
@@ -184,15 +189,16 @@ def _track_level(Ipad, Dpad, Jpad, rows, cols, level, max_level, win, max_count,
             iw00, iw01, iw10, iw11 = _weights(a, b)
             sb1 = 0
             sb2 = 0
-            for y in range(win):
-                for x in range(win):
-                    yy = y + iny + win
-                    xx = x + inx + win
-                    jv = (int(Jpad[yy, xx]) * iw00 + int(Jpad[yy, xx + 1]) * iw01
-                          + int(Jpad[yy + 1, xx]) * iw10 + int(Jpad[yy + 1, xx + 1]) * iw11 + (1 << 8)) >> 9
-                    diff = jv - Iw[y, x]
-                    sb1 += diff * Ix[y, x]
-                    sb2 += diff * Iy[y, x]
+            for c in range(cn):
+                for y in range(win):
+                    for x in range(win):
+                        yy = y + iny + win
+                        xx = x + inx + win
+                        jv = (int(Jpad[c, yy, xx]) * iw00 + int(Jpad[c, yy, xx + 1]) * iw01
+                              + int(Jpad[c, yy + 1, xx]) * iw10 + int(Jpad[c, yy + 1, xx + 1]) * iw11 + (1 << 8)) >> 9
+                        diff = jv - Iw[c, y, x]
+                        sb1 += diff * Ix[c, y, x]
+                        sb2 += diff * Iy[c, y, x]
             iters_out[p] += 1
             b1 = np.float32(np.float32(sb1) * flt_scale)
             b2 = np.float32(np.float32(sb2) * flt_scale)
@@ -223,37 +229,43 @@ def _track_level(Ipad, Dpad, Jpad, rows, cols, level, max_level, win, max_count,
             b = np.float32(fy - np.float32(iny))
             iw00, iw01, iw10, iw11 = _weights(a, b)
             e = 0
-            for y in range(win):
-                for x in range(win):
-                    yy = y + iny + win
-                    xx = x + inx + win
-                    jv = (int(Jpad[yy, xx]) * iw00 + int(Jpad[yy, xx + 1]) * iw01
-                          + int(Jpad[yy + 1, xx]) * iw10 + int(Jpad[yy + 1, xx + 1]) * iw11 + (1 << 8)) >> 9
-                    e += abs(jv - Iw[y, x])
-            err[p] = np.float32(np.float32(e) * np.float32(1.0 / (32 * win * win)))
+            for c in range(cn):
+                for y in range(win):
+                    for x in range(win):
+                        yy = y + iny + win
+                        xx = x + inx + win
+                        jv = (int(Jpad[c, yy, xx]) * iw00 + int(Jpad[c, yy, xx + 1]) * iw01
+                              + int(Jpad[c, yy + 1, xx]) * iw10 + int(Jpad[c, yy + 1, xx + 1]) * iw11 + (1 << 8)) >> 9
+                        e += abs(jv - Iw[c, y, x])
+            err[p] = np.float32(np.float32(e) * np.float32(1.0 / (32 * win * cn * win)))
 
 
 def calc_optical_flow_pyr_lk(prev_img, next_img, prev_pts, win=21, max_level=3, max_count=30, eps=0.01,
                              min_eig_thr=1e-4, return_iters=False):
-    """Restated cv2.calcOpticalFlowPyrLK(prev, next, pts, None) for 1-channel u8.
+    """Restated cv2.calcOpticalFlowPyrLK(prev, next, pts, None) for u8 images, H x W or H x W x cn
+    (channels are processed as planes: pyrDown, Scharr and the bilinear samples are per channel).
     Returns (next_pts (N,2) f32, status (N,) u8, err (N,) f32[, iters (levels,N)])."""
+    prev_img = np.asarray(prev_img)
+    next_img = np.asarray(next_img)
+    planes_p = [prev_img] if prev_img.ndim == 2 else [np.ascontiguousarray(prev_img[:, :, c]) for c in range(prev_img.shape[2])]
+    planes_n = [next_img] if next_img.ndim == 2 else [np.ascontiguousarray(next_img[:, :, c]) for c in range(next_img.shape[2])]
     prev_pts = np.ascontiguousarray(prev_pts, np.float32).reshape(-1, 2)
     n = len(prev_pts)
     max_count = min(max(max_count, 0), 100)
     eps = min(max(eps, 0.0), 10.0)
     eps = eps * eps
-    lp = build_pyramid(prev_img, max_level, win)
-    ln = build_pyramid(next_img, max_level, win)
-    L = len(lp) - 1
+    lps = [build_pyramid(pl, max_level, win) for pl in planes_p]
+    lns = [build_pyramid(pl, max_level, win) for pl in planes_n]
+    L = len(lps[0]) - 1
     next_pts = np.zeros((n, 2), np.float32)
     status = np.ones(n, np.uint8)
     err = np.zeros(n, np.float32)
     iters = np.zeros((L + 1, n), np.int32)
     for level in range(L, -1, -1):
-        I = lp[level]
-        Ipad = pad_reflect101(I, win)
-        Dpad = pad_zero(scharr_deriv(I), win)
-        Jpad = pad_reflect101(ln[level], win)
+        I = lps[0][level]
+        Ipad = np.stack([pad_reflect101(lp[level], win) for lp in lps])
+        Dpad = np.stack([pad_zero(scharr_deriv(lp[level]), win) for lp in lps])
+        Jpad = np.stack([pad_reflect101(ln[level], win) for ln in lns])
         _track_level(Ipad, Dpad, Jpad, I.shape[0], I.shape[1], level, L, win, max_count, eps,
                      np.float32(min_eig_thr), prev_pts, next_pts, status, err, iters[level])
     if return_iters:

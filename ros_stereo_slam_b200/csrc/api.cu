@@ -130,6 +130,7 @@ static int alloc_chain(vo_ctx* c) {
     VO_CUDA(cudaMemset(c->d_flags, 0, 8 * sizeof(int)));
     VO_CUDA(cudaMallocHost(&c->h_flags, 8 * sizeof(int)));
   }
+  if (p->channels == 3) VO_CUDA(cudaMalloc(&c->d_bgr, (size_t)3 * p->width * p->height));
   VO_CUDA(cudaMalloc(&c->d_lk_work, 2 * sizeof(unsigned long long)));
   VO_CUDA(cudaMallocHost(&c->h_lk_work, 2 * sizeof(unsigned long long)));
   VO_CUDA(cudaMemsetAsync(c->d_lk_work, 0, 2 * sizeof(unsigned long long), c->stream));
@@ -143,7 +144,7 @@ static void free_chain(vo_ctx* c) {
   void* dev[] = {c->d_xy_in, c->d_xy_trk, c->d_status, c->d_err, c->d_xyz_in, c->d_c_ref, c->d_c_trk, c->d_c_xyz,
                  c->d_f_ref, c->d_f_trk, c->d_f_xyz, c->d_xyz_tmp, c->d_mask, c->d_idx, c->d_seq_xy, c->d_seq_xyz,
                  c->d_count, c->d_tile_state, c->d_samples, c->d_models, c->d_counts, c->d_sel, c->d_pose, c->d_cam,
-                 c->d_lk_work, c->d_rng, c->d_flags, c->d_epoch, c->d_Pst};
+                 c->d_lk_work, c->d_rng, c->d_flags, c->d_epoch, c->d_Pst, c->d_bgr};
   for (void* p : dev) cudaFree(p);
   void* host[] = {c->h_count, c->h_pts, c->h_samples, c->h_sel, c->h_pose, c->h_lk_work, c->h_flags};
   for (void* p : host) cudaFreeHost(p);
@@ -251,9 +252,10 @@ void vo_default_params(vo_params* p) {
 int vo_create(const vo_params* p, vo_ctx** out) {
   if (!p || !out) return VO_ERR_INVALID_ARG;
   *out = nullptr;
-  if (p->channels != 1) {
-    set_error("channels=%d: only 1-channel images are implemented (BGR is a 'next' row, SURVEY 8f)", p->channels);
-    return VO_ERR_NOT_IMPLEMENTED;
+  if (p->channels != 1 && p->channels != 3) {
+    set_error("channels=%d: images are 1-channel (gray) or 3-channel (BGR, what the reference's imread returns)",
+              p->channels);
+    return VO_ERR_INVALID_ARG;
   }
   if (p->lk_win != LK_WIN) {
     set_error("lk_win=%d: the LK kernel is specialised for the reference's 21x21 window", p->lk_win);
@@ -388,11 +390,23 @@ static int sync_stream(vo_ctx* c) {
 // image -> padded level 0 of `slot` (H2D or D2D straight into place), then the pyramid
 static int load_image(vo_ctx* c, int slot, const uint8_t* img, int stride, int is_device, bool with_deriv) {
   if (!img) return VO_ERR_INVALID_ARG;
-  if (stride < c->p.width) {
-    set_error("stride %d < width %d", stride, c->p.width);
+  const int row_bytes = c->p.width * c->p.channels;
+  if (stride < row_bytes) {
+    set_error("stride %d < %d bytes per image row", stride, row_bytes);
     return VO_ERR_INVALID_ARG;
   }
   PyrLevel& L0 = c->pyr[slot].lv[0];
+  if (c->p.channels == 3) {
+    // interleaved BGR: tight staging copy (skipped for tight device images), de-interleave into the planes
+    const uint8_t* src = img;
+    if (!is_device || stride != row_bytes) {
+      VO_CUDA(cudaMemcpy2DAsync(c->d_bgr, row_bytes, img, stride, row_bytes, L0.h,
+                                is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+      src = c->d_bgr;
+    }
+    VO_TRY(pyr_split_bgr(c, slot, src));
+    return pyr_build(c, slot, nullptr, with_deriv);
+  }
   VO_CUDA(cudaMemcpy2DAsync(L0.img + (size_t)PAD_Y * L0.pitch + PAD_L, L0.pitch, img, stride, L0.w, L0.h,
                             is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
   return pyr_build(c, slot, nullptr, with_deriv);
@@ -944,6 +958,40 @@ int vo_lk_track(vo_ctx* c, const uint8_t* prev, const uint8_t* next, int stride,
   return sync_stream(c);
 }
 
+// copy a (w+2*pad) x (h+2*pad) window of level L (all planes) to the host in OpenCV's interleaved layout
+static int fetch_level(vo_ctx* c, const PyrLevel& L, int cn, int pad, uint8_t* out_level, int16_t* out_deriv) {
+  const size_t off = (size_t)(PAD_Y - pad) * L.pitch + (PAD_L - pad);
+  const int pw = L.w + 2 * pad, ph = L.h + 2 * pad;
+  if (cn == 1) {
+    if (out_level)
+      VO_CUDA(cudaMemcpy2DAsync(out_level, pw, L.img + off, L.pitch, pw, ph, cudaMemcpyDeviceToHost, c->stream));
+    if (out_deriv)
+      VO_CUDA(cudaMemcpy2DAsync(out_deriv, (size_t)pw * 4, L.deriv + off, (size_t)L.pitch * 4, (size_t)pw * 4, ph,
+                                cudaMemcpyDeviceToHost, c->stream));
+    return sync_stream(c);
+  }
+  std::vector<uint8_t> hi((size_t)pw * ph);
+  std::vector<int16_t> hd((size_t)pw * ph * 2);
+  for (int k = 0; k < cn; k++) {
+    if (out_level) {
+      VO_CUDA(cudaMemcpy2DAsync(hi.data(), pw, L.img + k * L.plane + off, L.pitch, pw, ph, cudaMemcpyDeviceToHost, c->stream));
+      VO_TRY(sync_stream(c));
+      for (size_t i = 0; i < hi.size(); i++) out_level[i * cn + k] = hi[i];
+    }
+    if (out_deriv) {
+      VO_CUDA(cudaMemcpy2DAsync(hd.data(), (size_t)pw * 4, L.deriv + k * L.plane + off, (size_t)L.pitch * 4, (size_t)pw * 4, ph,
+                                cudaMemcpyDeviceToHost, c->stream));
+      VO_TRY(sync_stream(c));
+      // cv::calcSharrDeriv: sample x*cn+k of a row -> (dx, dy) at [2*(x*cn+k)], [2*(x*cn+k)+1]
+      for (size_t i = 0; i < (size_t)pw * ph; i++) {
+        out_deriv[(i * cn + k) * 2] = hd[2 * i];
+        out_deriv[(i * cn + k) * 2 + 1] = hd[2 * i + 1];
+      }
+    }
+  }
+  return VO_OK;
+}
+
 int vo_debug_pyramid_level(vo_ctx* c, const uint8_t* img, int stride, int level, uint8_t* out_level, int16_t* out_deriv,
                            int* w, int* h) {
   CHECK_CTX(c);
@@ -954,13 +1002,7 @@ int vo_debug_pyramid_level(vo_ctx* c, const uint8_t* img, int stride, int level,
   PyrLevel& L = p.lv[level];
   if (w) *w = L.w;
   if (h) *h = L.h;
-  if (out_level)
-    VO_CUDA(cudaMemcpy2DAsync(out_level, L.w, L.img + (size_t)PAD_Y * L.pitch + PAD_L, L.pitch, L.w, L.h,
-                              cudaMemcpyDeviceToHost, c->stream));
-  if (out_deriv)
-    VO_CUDA(cudaMemcpy2DAsync(out_deriv, (size_t)L.w * 4, L.deriv + (size_t)PAD_Y * L.pitch + PAD_L,
-                              (size_t)L.pitch * 4, (size_t)L.w * 4, L.h, cudaMemcpyDeviceToHost, c->stream));
-  return sync_stream(c);
+  return fetch_level(c, L, p.cn, 0, out_level, out_deriv);
 }
 
 int vo_debug_pyramid_padded(vo_ctx* c, const uint8_t* img, int stride, int level, int pad, uint8_t* out_level,
@@ -970,15 +1012,7 @@ int vo_debug_pyramid_padded(vo_ctx* c, const uint8_t* img, int stride, int level
   VO_TRY(load_image(c, 0, img, stride, 0, true));
   Pyramid& p = c->pyr[0];
   if (level < 0 || level >= p.nlevels) return VO_ERR_INVALID_ARG;
-  PyrLevel& L = p.lv[level];
-  const size_t off = (size_t)(PAD_Y - pad) * L.pitch + (PAD_L - pad);
-  const int pw = L.w + 2 * pad, ph = L.h + 2 * pad;
-  if (out_level)
-    VO_CUDA(cudaMemcpy2DAsync(out_level, pw, L.img + off, L.pitch, pw, ph, cudaMemcpyDeviceToHost, c->stream));
-  if (out_deriv)
-    VO_CUDA(cudaMemcpy2DAsync(out_deriv, (size_t)pw * 4, L.deriv + off, (size_t)L.pitch * 4, (size_t)pw * 4, ph,
-                              cudaMemcpyDeviceToHost, c->stream));
-  return sync_stream(c);
+  return fetch_level(c, p.lv[level], p.cn, pad, out_level, out_deriv);
 }
 
 int vo_fmat_ransac(vo_ctx* c, const float* xy1, const float* xy2, int n, double thr, double conf,

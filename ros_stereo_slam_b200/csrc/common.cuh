@@ -28,26 +28,35 @@ constexpr int PAD_L = 32;
 constexpr int PAD_R = 32;
 constexpr int MAX_LEVELS = 4;
 
+// 3-channel (BGR) images are stored PLANAR: `cn` planes per level, each with the 1-channel geometry,
+// plane k at img + k*plane / deriv + k*plane.  pyrDown, Scharr and the bilinear window samples are
+// per-channel operations and the LK sums run over all channels of the window, so planes give the
+// same numbers as OpenCV's interleaved layout while every kernel keeps its 1-channel access pattern.
+constexpr int MAX_CN = 3;
+
 struct PyrLevel {
   int w, h;          // interior size
   int pitch;         // bytes per padded image row (multiple of 128)
-  uint8_t* img;      // padded buffer base; pixel (x,y) at img[(y+PAD_Y)*pitch + x + PAD_L]
+  size_t plane;      // elements (bytes of img, short2 of deriv) per plane = (h + 2*PAD_Y) * pitch
+  uint8_t* img;      // padded buffer base; pixel (x,y) of plane k at img[k*plane + (y+PAD_Y)*pitch + x + PAD_L]
   short2* deriv;     // padded (dx,dy) buffer, same geometry, element pitch = pitch
 };
 
 struct Pyramid {
   PyrLevel lv[MAX_LEVELS];
   int nlevels = 0;
+  int cn = 1;
   bool has_deriv = false;
   uint64_t stamp = 0;  // content tag (0 = empty)
-  // CUtensorMap (TMA descriptor) of the level-0 interior: u8, dims (w, h), row stride = pitch
-  alignas(64) unsigned char tmap0[128] = {0};
+  // CUtensorMap (TMA descriptor) of the level-0 interior of each plane: u8, dims (w, h), row stride = pitch
+  alignas(64) unsigned char tmap0[MAX_CN][128] = {{0}};
 };
 
 struct PyrLevelView {  // what kernels see
   const uint8_t* img;
   const short2* deriv;
   int w, h, pitch;
+  unsigned plane;    // elements per plane
 };
 
 struct PyrView {
@@ -141,8 +150,8 @@ struct vo_ctx {
   // last-call debug views
   int last_pnp_h = 0, last_f_h = 0;
 
-  // pinned host staging for images and point outputs
-  uint8_t* h_img[3] = {nullptr, nullptr, nullptr};
+  // interleaved BGR staging (channels == 3): the image lands here, split_planes_kernel de-interleaves it
+  uint8_t* d_bgr = nullptr;
   float* h_pts = nullptr;         // cap * 8 floats
 
   // LK work counters
@@ -185,6 +194,7 @@ int pyr_alloc(vo_ctx* c, Pyramid& p);
 void pyr_free(Pyramid& p);
 int pyr_build(vo_ctx* c, int slot, const uint8_t* d_tight /*w*h device*/, bool with_deriv);
 int pyr_ensure_deriv(vo_ctx* c, int slot);
+int pyr_split_bgr(vo_ctx* c, int slot, const uint8_t* d_bgr /*tight h x 3w*/);
 PyrView pyr_view(const Pyramid& p);
 
 int lk_launch(vo_ctx* c, int slot_prev, int slot_next, const float2* d_prev, int n, float2* d_next, uint8_t* d_status,

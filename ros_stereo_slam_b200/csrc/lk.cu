@@ -372,6 +372,252 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
   }
 }
 
+// ------------------------------------------------------------------------------------ 3-channel (BGR) LK
+// cv::calcOpticalFlowPyrLK on 3-channel images -- what the reference actually feeds it (imread's default
+// BGR output, reference src/keyFrameManagement.cpp:52,64).  OpenCV walks the window as 21 rows x 63
+// interleaved samples (neighbour = +cn): every sum runs over the three channels of the window, the
+// bilinear samples and derivatives are per channel.  With planar storage (common.cuh) that is the
+// 1-channel computation repeated per plane with ONE set of sums: same segment mapping, same staging,
+// same DP2A samples.  Ix/Iy of the 3 x 14 samples a lane owns are kept packed (s16 | s16 << 16) in 42
+// registers; I is not kept (the sum of I*Ix is hoisted) and is re-sampled once for the err pass.
+// minEig is normalised by the window AREA (no channel factor) and err by area * cn, as in OpenCV.
+__device__ __forceinline__ void lk_deriv_seg(const unsigned* dtile, int row, int col, int iw00, int iw01, int iw10, int iw11,
+                                             const int* Iw, unsigned* ixy, int& sA11, int& sA12, int& sA22, int& sC1,
+                                             int& sC2) {
+  const unsigned* d = dtile + row * DS + col;
+  unsigned top_[SEG + 1], bot_[SEG + 1];
+#pragma unroll
+  for (int x = 0; x <= SEG; x++) {
+    top_[x] = d[x];
+    bot_[x] = d[DS + x];
+  }
+#pragma unroll
+  for (int x = 0; x < SEG; x++) {
+    const int ixv = ((int)(short)(top_[x] & 0xffff) * iw00 + (int)(short)(top_[x + 1] & 0xffff) * iw01 +
+                     (int)(short)(bot_[x] & 0xffff) * iw10 + (int)(short)(bot_[x + 1] & 0xffff) * iw11 + (1 << (W_BITS - 1))) >>
+                    W_BITS;
+    const int iyv = (((int)top_[x] >> 16) * iw00 + ((int)top_[x + 1] >> 16) * iw01 + ((int)bot_[x] >> 16) * iw10 +
+                     ((int)bot_[x + 1] >> 16) * iw11 + (1 << (W_BITS - 1))) >>
+                    W_BITS;
+    ixy[x] = ((unsigned)ixv & 0xffffu) | ((unsigned)iyv << 16);
+    sA11 += ixv * ixv;
+    sA12 += ixv * iyv;
+    sA22 += iyv * iyv;
+    sC1 += Iw[x] * ixv;
+    sC2 += Iw[x] * iyv;
+  }
+}
+
+__global__ void __launch_bounds__(128)
+lk_kernel_c3(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n, float2* __restrict__ next_pts,
+             uint8_t* __restrict__ status, float* __restrict__ err, int max_iters, double eps_sq, float min_eig_thr,
+             unsigned long long* __restrict__ work, const int* __restrict__ n_dev) {
+  constexpr int CN = 3;
+  if (n_dev) n = min(n, *n_dev);
+  __shared__ unsigned smem[LK_WARPS * WARP_SMEM_WORDS];
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= n) return;
+  unsigned* tile = smem + (threadIdx.x >> 5) * WARP_SMEM_WORDS;
+  unsigned* dtile = tile + TILE_WORDS;
+  unsigned* tile_lane = tile + (lane >> 3) * PS + (lane & 7);
+  const bool st_col_ok = (lane & 7) < 7, st_last_ok = (lane >> 3) < PROWS - 20;
+  const float2 pt = prev_pts[warp];
+  const float half_win = (WIN - 1) * 0.5f;
+  const float FLT_SCALE = 1.f / (1 << 20);
+  const float eps_lo = (float)(eps_sq * (1.0 - 1e-5)), eps_hi = (float)(eps_sq * (1.0 + 1e-5));
+
+  const int rowA = lane / SEGS_PER_ROW, colA = (lane - rowA * SEGS_PER_ROW) * SEG;
+  const int sB = lane + 32;
+  const bool hasB = sB < NSEG;
+  const int rowB = hasB ? sB / SEGS_PER_ROW : 0, colB = hasB ? (sB - rowB * SEGS_PER_ROW) * SEG : 0;
+
+  float outx = 0.f, outy = 0.f;
+  bool st = true;
+  float errv = 0.f;
+  unsigned int n_levels_done = 0, n_iters_done = 0;
+
+  unsigned ixy[CN][2 * SEG];   // packed (Ix, Iy) of this lane's samples, per plane
+
+  const int top = prev.nlevels - 1;
+  for (int level = top; level >= 0; level--) {
+    const PyrLevelView I = prev.lv[level];
+    const PyrLevelView J = next.lv[level];
+    const int pitch = I.pitch;
+    const int st_step = pitch;
+    const int st_off = (lane >> 3) * (pitch >> 2) + (lane & 7);
+    const float scale = 1.f / (float)(1 << level);
+    float px = __fmul_rn(pt.x, scale), py = __fmul_rn(pt.y, scale);
+    float nx, ny;
+    if (level == top) {
+      nx = px;
+      ny = py;
+    } else {
+      nx = __fmul_rn(outx, 2.f);
+      ny = __fmul_rn(outy, 2.f);
+    }
+    outx = nx;
+    outy = ny;
+
+    px = __fsub_rn(px, half_win);
+    py = __fsub_rn(py, half_win);
+    const int ipx = (int)floorf(px), ipy = (int)floorf(py);
+    if (ipx < -WIN || ipx >= I.w || ipy < -WIN || ipy >= I.h) {
+      if (level == 0) {
+        st = false;
+        errv = 0.f;
+      }
+      continue;
+    }
+    int iw00, iw01, iw10, iw11;
+    unsigned wt, wb;
+    lk_weights(__fsub_rn(px, (float)ipx), __fsub_rn(py, (float)ipy), wt, wb, iw00, iw01, iw10, iw11);
+    const unsigned wtI = wt, wbI = wb;
+    const size_t o0 = (size_t)(ipy + PAD_Y) * pitch + (ipx + PAD_L);
+
+    // ---- window extraction from the previous image + its Scharr derivative, all planes
+    int sA11 = 0, sA12 = 0, sA22 = 0, sC1 = 0, sC2 = 0;
+#pragma unroll
+    for (int ch = 0; ch < CN; ch++) {
+      const unsigned sh = stage_patch(I.img + (size_t)ch * I.plane + o0, st_off, st_step, tile_lane, st_col_ok, st_last_ok);
+      {
+        const unsigned* dsrc = reinterpret_cast<const unsigned*>(I.deriv + (size_t)ch * I.plane + o0);
+        int r = 0, x = lane;
+        if (x >= PROWS) { x -= PROWS; r = 1; }
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+          if (r < PROWS) dtile[r * DS + x] = __ldg(dsrc + (size_t)r * pitch + x);
+          x += 32 - PROWS; r += 1;
+          if (x >= PROWS) { x -= PROWS; r += 1; }
+        }
+        __syncwarp();
+      }
+      int Iw[SEG];
+      seg_bilinear(tile, rowA, colA + sh, wt, wb, Iw);
+      lk_deriv_seg(dtile, rowA, colA, iw00, iw01, iw10, iw11, Iw, ixy[ch], sA11, sA12, sA22, sC1, sC2);
+      if (hasB) {
+        seg_bilinear(tile, rowB, colB + sh, wt, wb, Iw);
+        lk_deriv_seg(dtile, rowB, colB, iw00, iw01, iw10, iw11, Iw, ixy[ch] + SEG, sA11, sA12, sA22, sC1, sC2);
+      } else {
+#pragma unroll
+        for (int x = 0; x < SEG; x++) ixy[ch][SEG + x] = 0;
+      }
+    }
+    const float A11 = __fmul_rn(__ll2float_rn(warp_sum_exact(sA11)), FLT_SCALE);
+    const float A12 = __fmul_rn(__ll2float_rn(warp_sum_exact(sA12)), FLT_SCALE);
+    const float A22 = __fmul_rn(__ll2float_rn(warp_sum_exact(sA22)), FLT_SCALE);
+    const long long C1 = warp_sum_exact(sC1), C2 = warp_sum_exact(sC2);
+    float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+    const float dd = __fsub_rn(A11, A22);
+    const float q = __fadd_rn(__fmul_rn(dd, dd), __fmul_rn(__fmul_rn(4.f, A12), A12));
+    const float min_eig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), __fsqrt_rn(q)), (float)(2 * WIN * WIN));
+    n_levels_done++;
+    if (min_eig < min_eig_thr || D < 1.1920929e-07f) {
+      if (level == 0) st = false;
+      continue;
+    }
+    D = __fdiv_rn(1.f, D);
+
+    nx = __fsub_rn(nx, half_win);
+    ny = __fsub_rn(ny, half_win);
+    float pdx = 0.f, pdy = 0.f;
+    for (int j = 0; j < max_iters; j++) {
+      const int inx = (int)floorf(nx), iny = (int)floorf(ny);
+      if (inx < -WIN || inx >= J.w || iny < -WIN || iny >= J.h) {
+        if (level == 0) st = false;
+        break;
+      }
+      lk_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), wt, wb, iw00, iw01, iw10, iw11);
+      const size_t oj = (size_t)(iny + PAD_Y) * pitch + (inx + PAD_L);
+      int sb1 = 0, sb2 = 0;
+#pragma unroll
+      for (int ch = 0; ch < CN; ch++) {
+        const unsigned sh = stage_patch(J.img + (size_t)ch * J.plane + oj, st_off, st_step, tile_lane, st_col_ok, st_last_ok);
+        int jv[SEG];
+        seg_bilinear(tile, rowA, colA + sh, wt, wb, jv);
+#pragma unroll
+        for (int x = 0; x < SEG; x++) {
+          sb1 += jv[x] * (int)(short)(ixy[ch][x] & 0xffff);
+          sb2 += jv[x] * ((int)ixy[ch][x] >> 16);
+        }
+        if (hasB) {
+          seg_bilinear(tile, rowB, colB + sh, wt, wb, jv);
+#pragma unroll
+          for (int x = 0; x < SEG; x++) {
+            sb1 += jv[x] * (int)(short)(ixy[ch][SEG + x] & 0xffff);
+            sb2 += jv[x] * ((int)ixy[ch][SEG + x] >> 16);
+          }
+        }
+      }
+      n_iters_done++;
+      const float b1 = __fmul_rn(__ll2float_rn(warp_sum_exact(sb1) - C1), FLT_SCALE);
+      const float b2 = __fmul_rn(__ll2float_rn(warp_sum_exact(sb2) - C2), FLT_SCALE);
+      const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
+      const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
+      nx = __fadd_rn(nx, dx);
+      ny = __fadd_rn(ny, dy);
+      outx = __fadd_rn(nx, half_win);
+      outy = __fadd_rn(ny, half_win);
+      {
+        const float s2 = fmaf(dx, dx, dy * dy);
+        bool conv;
+        if (s2 < eps_lo) conv = true;
+        else if (s2 > eps_hi) conv = false;
+        else conv = __dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)) <= eps_sq;
+        if (conv) break;
+      }
+      if (j > 0 && (double)fabsf(__fadd_rn(dx, pdx)) < 0.01 && (double)fabsf(__fadd_rn(dy, pdy)) < 0.01) {
+        outx = __fsub_rn(outx, __fmul_rn(dx, 0.5f));
+        outy = __fsub_rn(outy, __fmul_rn(dy, 0.5f));
+        break;
+      }
+      pdx = dx;
+      pdy = dy;
+    }
+
+    // ---- err pass: mean |J - I| / 32 over the window and the channels at the final position
+    if (st && level == 0) {
+      const float fx = __fsub_rn(outx, half_win), fy = __fsub_rn(outy, half_win);
+      const int inx = (int)floorf(fx), iny = (int)floorf(fy);
+      if (inx < -WIN || inx >= J.w || iny < -WIN || iny >= J.h) {
+        st = false;
+      } else {
+        lk_weights(__fsub_rn(fx, (float)inx), __fsub_rn(fy, (float)iny), wt, wb, iw00, iw01, iw10, iw11);
+        const size_t oj = (size_t)(iny + PAD_Y) * pitch + (inx + PAD_L);
+        int se = 0;
+#pragma unroll
+        for (int ch = 0; ch < CN; ch++) {
+          int iv[2 * SEG], jv[SEG];
+          const unsigned shI = stage_patch(I.img + (size_t)ch * I.plane + o0, st_off, st_step, tile_lane, st_col_ok, st_last_ok);
+          seg_bilinear(tile, rowA, colA + shI, wtI, wbI, iv);
+          if (hasB) seg_bilinear(tile, rowB, colB + shI, wtI, wbI, iv + SEG);
+          const unsigned sh = stage_patch(J.img + (size_t)ch * J.plane + oj, st_off, st_step, tile_lane, st_col_ok, st_last_ok);
+          seg_bilinear(tile, rowA, colA + sh, wt, wb, jv);
+#pragma unroll
+          for (int x = 0; x < SEG; x++) se += abs(jv[x] - iv[x]);
+          if (hasB) {
+            seg_bilinear(tile, rowB, colB + sh, wt, wb, jv);
+#pragma unroll
+            for (int x = 0; x < SEG; x++) se += abs(jv[x] - iv[SEG + x]);
+          }
+        }
+        const int tot = __reduce_add_sync(0xffffffffu, se);  // <= 3*441*8160 fits int32
+        errv = __fmul_rn((float)tot, 1.f / (32 * WIN * CN * WIN));
+      }
+    }
+  }
+
+  if (lane == 0) {
+    next_pts[warp] = make_float2(outx, outy);
+    status[warp] = st ? 1 : 0;
+    if (err) err[warp] = errv;
+    if (work) {
+      atomicAdd(&work[0], (unsigned long long)n_levels_done);
+      atomicAdd(&work[1], (unsigned long long)n_iters_done);
+    }
+  }
+}
+
 int lk_launch(vo_ctx* c, int slot_prev, int slot_next, const float2* d_prev, int n, float2* d_next, uint8_t* d_status,
               float* d_err) {
   if (n <= 0) return VO_OK;
@@ -383,9 +629,14 @@ int lk_launch(vo_ctx* c, int slot_prev, int slot_next, const float2* d_prev, int
   const int blocks = div_up(n * 32, threads);
   {
     LaunchScope ls(c, VO_K_LK);
-    lk_kernel<<<blocks, threads, 0, c->stream>>>(pyr_view(c->pyr[slot_prev]), pyr_view(c->pyr[slot_next]), d_prev, n,
-                                                 d_next, d_status, d_err, max_iters, eps, (float)c->p.lk_min_eig,
-                                                 c->d_lk_work, c->n_dev);
+    if (c->p.channels == 3)
+      lk_kernel_c3<<<blocks, threads, 0, c->stream>>>(pyr_view(c->pyr[slot_prev]), pyr_view(c->pyr[slot_next]), d_prev, n,
+                                                      d_next, d_status, d_err, max_iters, eps, (float)c->p.lk_min_eig,
+                                                      c->d_lk_work, c->n_dev);
+    else
+      lk_kernel<<<blocks, threads, 0, c->stream>>>(pyr_view(c->pyr[slot_prev]), pyr_view(c->pyr[slot_next]), d_prev, n,
+                                                   d_next, d_status, d_err, max_iters, eps, (float)c->p.lk_min_eig,
+                                                   c->d_lk_work, c->n_dev);
   }
   VO_CUDA(cudaGetLastError());
   return VO_OK;

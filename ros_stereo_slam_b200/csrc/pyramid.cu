@@ -66,9 +66,13 @@ struct K1Level {
   int w, h, pitch;
 };
 struct K1Args {
-  K1Level lv[MAX_LEVELS];
+  K1Level lv[MAX_LEVELS];       // plane 0; plane z at img + z*plane[l], deriv + z*plane[l]
+  size_t plane[MAX_LEVELS];
   int nlevels;
   int with_deriv;
+};
+struct K1Maps {
+  CUtensorMap m[MAX_CN];        // level-0 interior of each plane
 };
 
 struct Range {
@@ -186,7 +190,7 @@ __device__ __forceinline__ void k1_emit_level(const uint8_t* __restrict__ tile, 
 }
 
 __global__ void __launch_bounds__(K1_THREADS)
-pyr_fused_kernel(const __grid_constant__ CUtensorMap tmap0, const K1Args a) {
+pyr_fused_kernel(const __grid_constant__ K1Maps maps, const K1Args a) {
   __shared__ alignas(128) uint8_t t0[K1_BOXW * K1_BOXH];
   __shared__ uint8_t t1[K1_TW1 * K1_TH1], t2[K1_TW2 * K1_TH2], t3[K1_TW3 * K1_TH3];
   __shared__ alignas(8) unsigned long long bar;
@@ -227,7 +231,7 @@ pyr_fused_kernel(const __grid_constant__ CUtensorMap tmap0, const K1Args a) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
             smem_addr(t0)),
-        "l"(reinterpret_cast<uint64_t>(&tmap0)), "r"(t0x), "r"(ny[0].lo), "r"(bar_a)
+        "l"(reinterpret_cast<uint64_t>(&maps.m[blockIdx.z])), "r"(t0x), "r"(ny[0].lo), "r"(bar_a)
         : "memory");
   }
   asm volatile(
@@ -256,14 +260,41 @@ pyr_fused_kernel(const __grid_constant__ CUtensorMap tmap0, const K1Args a) {
 #pragma unroll
   for (int l = 0; l < MAX_LEVELS; l++) {
     if (l >= nl) break;
-    k1_emit_level(tiles[l], l == 0 ? t0x : nx[l].lo, ny[l].lo, strides[l], a.lv[l], ox[l], oy[l], l > 0, a.with_deriv != 0);
+    K1Level L = a.lv[l];
+    L.img += blockIdx.z * a.plane[l];
+    L.deriv += blockIdx.z * a.plane[l];
+    k1_emit_level(tiles[l], l == 0 ? t0x : nx[l].lo, ny[l].lo, strides[l], L, ox[l], oy[l], l > 0, a.with_deriv != 0);
+  }
+}
+
+// Interleaved BGR (tight rows of 3*w bytes) -> the level-0 interiors of the three planes.
+// 4 pixels per thread: twelve byte loads (rows of 3*w bytes are not word aligned), three uchar4 stores.
+__global__ void split_planes_kernel(const uint8_t* __restrict__ bgr, int w, int h, uint8_t* __restrict__ img, int pitch,
+                                    size_t plane) {
+  const int x = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+  const int y = blockIdx.y;
+  if (x >= w) return;
+  const uint8_t* s = bgr + (size_t)y * (3 * w) + 3 * x;
+  uint8_t* d = img + (size_t)(y + PAD_Y) * pitch + PAD_L + x;
+  if (x + 4 <= w) {
+    uint8_t v[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) v[k] = __ldg(s + k);
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+      *reinterpret_cast<uchar4*>(d + c * plane) = make_uchar4(v[c], v[3 + c], v[6 + c], v[9 + c]);
+  } else {
+    for (int k = 0; x + k < w; k++)
+      for (int c = 0; c < 3; c++) d[c * plane + k] = s[3 * k + c];
   }
 }
 
 // ------------------------------------------------------------------------------------
 int pyr_alloc(vo_ctx* c, Pyramid& p) {
   int w = c->p.width, h = c->p.height;
+  const int cn = c->p.channels;
   p.nlevels = 0;
+  p.cn = cn;
   for (int l = 0; l <= c->p.lk_max_level && l < MAX_LEVELS; l++) {
     if (l > 0) {
       int nw = (w + 1) / 2, nh = (h + 1) / 2;
@@ -275,16 +306,16 @@ int pyr_alloc(vo_ctx* c, Pyramid& p) {
     L.w = w;
     L.h = h;
     L.pitch = ((w + PAD_L + PAD_R + 127) / 128) * 128;
-    size_t rows = (size_t)h + 2 * PAD_Y;
-    VO_CUDA(cudaMalloc(&L.img, rows * L.pitch));
-    VO_CUDA(cudaMalloc(&L.deriv, rows * L.pitch * sizeof(short2)));
-    VO_CUDA(cudaMemsetAsync(L.img, 0, rows * L.pitch, c->stream));
-    VO_CUDA(cudaMemsetAsync(L.deriv, 0, rows * L.pitch * sizeof(short2), c->stream));
+    L.plane = ((size_t)h + 2 * PAD_Y) * L.pitch;
+    VO_CUDA(cudaMalloc(&L.img, cn * L.plane));
+    VO_CUDA(cudaMalloc(&L.deriv, cn * L.plane * sizeof(short2)));
+    VO_CUDA(cudaMemsetAsync(L.img, 0, cn * L.plane, c->stream));
+    VO_CUDA(cudaMemsetAsync(L.deriv, 0, cn * L.plane * sizeof(short2), c->stream));
     p.nlevels = l + 1;
   }
   p.has_deriv = false;
   p.stamp = 0;
-  // TMA descriptor of the level-0 interior (the driver entry point is resolved through the
+  // TMA descriptors of the level-0 interiors (the driver entry point is resolved through the
   // runtime, so the library does not link libcuda)
   {
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -298,20 +329,23 @@ int pyr_alloc(vo_ctx* c, Pyramid& p) {
       return VO_ERR_CUDA;
     }
     PyrLevel& L0 = p.lv[0];
-    CUtensorMap tm;
     const cuuint64_t gdim[2] = {(cuuint64_t)L0.w, (cuuint64_t)L0.h};
     const cuuint64_t gstride[1] = {(cuuint64_t)L0.pitch};
     const cuuint32_t box[2] = {(cuuint32_t)K1_BOXW, (cuuint32_t)K1_BOXH};
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = ((EncodeFn)fn)(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, L0.img + (size_t)PAD_Y * L0.pitch + PAD_L, gdim,
-                                      gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                      CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-      set_error("cuTensorMapEncodeTiled failed (%d) for %d x %d, pitch %d", (int)r, L0.w, L0.h, L0.pitch);
-      return VO_ERR_CUDA;
+    static_assert(sizeof(CUtensorMap) == sizeof(p.tmap0[0]), "CUtensorMap size");
+    for (int k = 0; k < cn; k++) {
+      CUtensorMap tm;
+      const CUresult r = ((EncodeFn)fn)(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2,
+                                        L0.img + k * L0.plane + (size_t)PAD_Y * L0.pitch + PAD_L, gdim, gstride, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                        CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) for %d x %d, pitch %d", (int)r, L0.w, L0.h, L0.pitch);
+        return VO_ERR_CUDA;
+      }
+      memcpy(p.tmap0[k], &tm, sizeof(tm));
     }
-    static_assert(sizeof(CUtensorMap) == sizeof(p.tmap0), "CUtensorMap size");
-    memcpy(p.tmap0, &tm, sizeof(tm));
   }
   return VO_OK;
 }
@@ -336,8 +370,9 @@ PyrView pyr_view(const Pyramid& p) {
       v.lv[l].w = p.lv[l].w;
       v.lv[l].h = p.lv[l].h;
       v.lv[l].pitch = p.lv[l].pitch;
+      v.lv[l].plane = (unsigned)p.lv[l].plane;
     } else {
-      v.lv[l] = PyrLevelView{nullptr, nullptr, 0, 0, 0};
+      v.lv[l] = PyrLevelView{nullptr, nullptr, 0, 0, 0, 0};
     }
   }
   return v;
@@ -347,15 +382,18 @@ static int scharr_all(vo_ctx* c, Pyramid& p) {
   for (int l = 0; l < p.nlevels; l++) {
     PyrLevel& L = p.lv[l];
     dim3 b(32, 8), g(div_up(L.w + PAD_L + PAD_R, 32), div_up(L.h + 2 * PAD_Y, 8));
-    LaunchScope ls(c, VO_K_PYRAMID);
-    scharr_kernel<<<g, b, 0, c->stream>>>(L.img, L.deriv, L.w, L.h, L.pitch);
+    for (int k = 0; k < p.cn; k++) {
+      LaunchScope ls(c, VO_K_PYRAMID);
+      scharr_kernel<<<g, b, 0, c->stream>>>(L.img + k * L.plane, L.deriv + k * L.plane, L.w, L.h, L.pitch);
+    }
   }
   VO_CUDA(cudaGetLastError());
   p.has_deriv = true;
   return VO_OK;
 }
 
-// Level 0 interior must already be in place (memcpy2D straight into the padded buffer).
+// Level 0 interior(s) must already be in place (memcpy2D straight into the padded buffer, or
+// pyr_split_bgr for 3-channel images).
 int pyr_build(vo_ctx* c, int slot, const uint8_t* d_tight, bool with_deriv) {
   Pyramid& p = c->pyr[slot];
   PyrLevel& L0 = p.lv[0];
@@ -367,19 +405,36 @@ int pyr_build(vo_ctx* c, int slot, const uint8_t* d_tight, bool with_deriv) {
   a.nlevels = p.nlevels;
   a.with_deriv = with_deriv ? 1 : 0;
   for (int l = 0; l < MAX_LEVELS; l++) {
-    if (l < p.nlevels) a.lv[l] = K1Level{p.lv[l].img, p.lv[l].deriv, p.lv[l].w, p.lv[l].h, p.lv[l].pitch};
-    else a.lv[l] = K1Level{nullptr, nullptr, 0, 0, 0};
+    if (l < p.nlevels) {
+      a.lv[l] = K1Level{p.lv[l].img, p.lv[l].deriv, p.lv[l].w, p.lv[l].h, p.lv[l].pitch};
+      a.plane[l] = p.lv[l].plane;
+    } else {
+      a.lv[l] = K1Level{nullptr, nullptr, 0, 0, 0};
+      a.plane[l] = 0;
+    }
   }
-  CUtensorMap tm;
-  memcpy(&tm, p.tmap0, sizeof(tm));
+  K1Maps maps;
+  for (int k = 0; k < MAX_CN; k++) memcpy(&maps.m[k], p.tmap0[k < p.cn ? k : 0], sizeof(CUtensorMap));
   {
-    dim3 g(div_up(L0.w, K1_T0W), div_up(L0.h, K1_T0H));
+    dim3 g(div_up(L0.w, K1_T0W), div_up(L0.h, K1_T0H), p.cn);
     LaunchScope ls(c, VO_K_PYRAMID);
-    pyr_fused_kernel<<<g, K1_THREADS, 0, c->stream>>>(tm, a);
+    pyr_fused_kernel<<<g, K1_THREADS, 0, c->stream>>>(maps, a);
   }
   VO_CUDA(cudaGetLastError());
   p.has_deriv = with_deriv;
   p.stamp = ++c->stamp_counter;
+  return VO_OK;
+}
+
+// 3-channel input: de-interleave the tight BGR image in d_bgr into the level-0 planes of `slot`.
+int pyr_split_bgr(vo_ctx* c, int slot, const uint8_t* d_bgr) {
+  PyrLevel& L0 = c->pyr[slot].lv[0];
+  dim3 b(128), g(div_up(div_up(L0.w, 4), 128), L0.h);
+  {
+    LaunchScope ls(c, VO_K_PYRAMID);
+    split_planes_kernel<<<g, b, 0, c->stream>>>(d_bgr, L0.w, L0.h, L0.img, L0.pitch, L0.plane);
+  }
+  VO_CUDA(cudaGetLastError());
   return VO_OK;
 }
 

@@ -25,9 +25,11 @@ def _u8img(img):
     if img is None:
         return None
     img = np.asarray(img)
-    if img.dtype != np.uint8 or img.ndim != 2:
-        raise ValueError("images must be 2-D uint8 (1 channel)")
-    if img.strides[1] != 1:
+    if img.dtype != np.uint8 or img.ndim not in (2, 3) or (img.ndim == 3 and img.shape[2] != 3):
+        raise ValueError("images must be uint8, H x W (gray) or H x W x 3 (BGR)")
+    if img.ndim == 2 and img.strides[1] != 1:
+        img = np.ascontiguousarray(img)
+    if img.ndim == 3 and (img.strides[2] != 1 or img.strides[1] != 3):
         img = np.ascontiguousarray(img)
     return img
 
@@ -100,8 +102,9 @@ class VisualFrontEnd:
         a = _u8img(img)
         w, h = C.c_int(), C.c_int()
         check(self.lib.vo_debug_pyramid_level(self.h, _p(a), a.strides[0], level, None, None, C.byref(w), C.byref(h)))
-        lv = np.zeros((h.value, w.value), np.uint8)
-        dv = np.zeros((h.value, w.value, 2), np.int16)
+        cn = self.params.channels
+        lv = np.zeros((h.value, w.value) if cn == 1 else (h.value, w.value, cn), np.uint8)
+        dv = np.zeros((h.value, w.value, 2 * cn), np.int16)
         check(self.lib.vo_debug_pyramid_level(self.h, _p(a), a.strides[0], level, _p(lv), _p(dv), C.byref(w), C.byref(h)))
         return lv, dv
 
@@ -110,8 +113,9 @@ class VisualFrontEnd:
         a = _u8img(img)
         w, h = C.c_int(), C.c_int()
         check(self.lib.vo_debug_pyramid_level(self.h, _p(a), a.strides[0], level, None, None, C.byref(w), C.byref(h)))
-        lv = np.zeros((h.value + 2 * pad, w.value + 2 * pad), np.uint8)
-        dv = np.zeros((h.value + 2 * pad, w.value + 2 * pad, 2), np.int16)
+        cn = self.params.channels
+        lv = np.zeros((h.value + 2 * pad, w.value + 2 * pad) if cn == 1 else (h.value + 2 * pad, w.value + 2 * pad, cn), np.uint8)
+        dv = np.zeros((h.value + 2 * pad, w.value + 2 * pad, 2 * cn), np.int16)
         check(self.lib.vo_debug_pyramid_padded(self.h, _p(a), a.strides[0], level, pad, _p(lv), _p(dv)))
         return lv, dv
 

@@ -305,6 +305,110 @@ def test_sequence_driver_matches_reference_loop():
         fe.close()
 
 
+# ---------------------------------------------------------------------------- 3-channel (BGR) input, SURVEY 8(f)-1
+def _colorize(img, k):
+    """A BGR image whose channels really differ (gain / inversion / gamma of the gray frame)."""
+    f = img.astype(np.float32)
+    b = f
+    g = 255.0 - 0.8 * f
+    r = 255.0 * (f / 255.0) ** (0.7 + 0.1 * k)
+    return np.stack([b, g, r], -1).round().clip(0, 255).astype(np.uint8)
+
+
+@pytest.fixture(scope="module")
+def fe3():
+    f = make_frontend(channels=3)
+    yield f
+    f.close()
+
+
+@pytest.mark.parametrize("kind", ["replicated_gray", "color"])
+def test_bgr_pyramid_and_scharr_bit_exact(fe3, G, kind):
+    """channels=3: levels, REFLECT_101 borders and the 6-channel Scharr planes equal
+    cv::buildOpticalFlowPyramid on the interleaved BGR image (imread's output, reference
+    src/keyFrameManagement.cpp:52)."""
+    img = cv2.cvtColor(G["L0"], cv2.COLOR_GRAY2BGR) if kind == "replicated_gray" else _colorize(G["L0"], 0)
+    ref = _padded_ref(img, 3, 21)
+    assert len(ref) == 4
+    for l, (lv0, dv0) in enumerate(ref):
+        lv, dv = fe3.pyramid_padded(img, l, 21)
+        assert lv.shape == lv0.shape and dv.shape == dv0.shape
+        assert np.array_equal(lv, lv0), "level %d" % l
+        assert np.array_equal(dv, dv0), "deriv %d" % l
+
+
+@pytest.mark.parametrize("kind", ["replicated_gray", "color"])
+@pytest.mark.parametrize("pair", ["temporal", "stereo"])
+def test_bgr_lk_matches_opencv(fe3, G, kind, pair):
+    """3-channel LK against cv2.calcOpticalFlowPyrLK on the same BGR images: status identical,
+    positions within 0.01 px (>= 99.9 %, the integer-vs-float-lane summation note of DESIGN.md applies)."""
+    a, b = G["L0"], (G["L1"] if pair == "temporal" else G["R0"])
+    if kind == "replicated_gray":
+        A, B = cv2.cvtColor(a, cv2.COLOR_GRAY2BGR), cv2.cvtColor(b, cv2.COLOR_GRAY2BGR)
+    else:
+        A, B = _colorize(a, 0), _colorize(b, 0)
+    pts = glue.dense_keypoint_extractor(376, 1241, 9)
+    extra = np.array([[5, 5], [1236, 371], [0.4, 200.7], [1240.2, 3.3], [620.5, 375.9]], np.float32)
+    pts = np.concatenate([pts, extra])
+    p, st, err = fe3.calcOpticalFlowPyrLK(A, B, pts)
+    p0, st0, err0 = cv2.calcOpticalFlowPyrLK(A, B, pts.reshape(-1, 1, 2), None)
+    p0 = p0.reshape(-1, 2); st0 = st0.ravel(); err0 = err0.ravel()
+    assert np.array_equal(st, st0)
+    ok = st0 == 1
+    d = np.abs(p - p0).max(1)[ok]
+    # >= 99.9 % within 0.01 px; the rest are tracks whose stopping test flips on the last bits of a window sum
+    # (OpenCV: float lanes; here: exact integers) and then end an iteration apart
+    assert np.mean(d <= TOL_PX) >= 0.999, (np.mean(d <= TOL_PX), d.max())
+    assert np.mean(d == 0) > 0.6        # 3x more terms in OpenCV's float-lane sums than with 1 channel (there: > 0.9)
+    # the scalar restatement with exact integer sums (oracle/lk.py, pinned against cv2 for 3 channels in
+    # tests/test_oracle_lk.py) is the kernel's bit-exact twin: positions, status and err
+    sub = np.r_[0:len(pts):7, len(pts) - 5:len(pts)]
+    p1, st1, err1 = olk.calc_optical_flow_pyr_lk(A, B, pts[sub])
+    assert np.array_equal(st[sub], st1)
+    assert np.array_equal(p[sub][st1 == 1], p1[st1 == 1])
+    assert np.array_equal(err[sub][st1 == 1], err1[st1 == 1])
+    close = ok & (np.abs(p - p0).max(1) <= TOL_PX)
+    assert np.abs(err[close] - err0[close]).max() < 2e-2  # err follows the final position; identical positions give identical err
+    same = ok & (np.abs(p - p0).max(1) == 0)
+    assert np.abs(err[same] - err0[same]).max() < 1e-5
+    # the 3-channel result is NOT the 1-channel one (SURVEY F8): the path really uses all channels
+    if kind == "color":
+        f1 = make_frontend()
+        p1, st1, _ = f1.calcOpticalFlowPyrLK(a, b, pts)
+        f1.close()
+        both = (st1 == 1) & ok
+        assert np.abs(p1[both] - p[both]).max() > 1e-3
+
+
+def test_bgr_stage_entry_points_and_sequence(G):
+    """stereoTriangulate / PerspectiveNpointEstimation / sequence driver on BGR frames vs the oracle glue
+    (the reference's own data flow: imread -> LK on 3 channels)."""
+    L0, R0, L1 = [cv2.cvtColor(G[k], cv2.COLOR_GRAY2BGR) for k in ("L0", "R0", "L1")]
+    fe = make_frontend(channels=3)
+    xyz, ref2d = fe.stereoTriangulate(L0, R0)
+    xyz0, ref0 = glue.stereo_triangulate(L0, R0, 30)
+    assert np.array_equal(ref2d, ref0)
+    assert (np.abs(xyz - xyz0).max(1) / np.abs(xyz0).max(1)).max() <= TOL_REL3D
+    res = fe.PerspectiveNpointEstimation(L0, L1, ref0, xyz0)
+    ref = glue.perspective_n_point_estimation(L0, L1, ref0, xyz0, iters=100)
+    assert np.array_equal(res["inliers"], ref["inliers"])
+    assert np.abs(res["rvec"] - ref["rvec"]).max() <= TOL_RAD and np.abs(res["tvec"] - ref["tvec"]).max() <= TOL_M
+    fe.close()
+    sc = synth.Scene(1)
+    Ls = [cv2.cvtColor(sc.render(i, "L"), cv2.COLOR_GRAY2BGR) for i in range(4)]
+    Rs = [cv2.cvtColor(sc.render(i, "R"), cv2.COLOR_GRAY2BGR) for i in range(4)]
+    fe = make_frontend(channels=3, kf_min_inliers=2 ** 31 - 1)
+    want = glue.run_sequence(Ls, Rs, step=30, pnp_iters=100, kf_min_inliers=10 ** 9)
+    fe.seq_init(Ls[0], Rs[0])
+    for i in range(1, 4):
+        res, code = fe.seq_track(Ls[i], Rs[i])
+        w = want[i - 1]
+        assert res.n_lk_in == w["n_lk_in"] and res.n_tracked == w["n_tracked"] and res.n_inliers == w["n_inliers"]
+        assert np.abs(np.array(res.rvec) - w["rvec"]).max() <= TOL_RAD
+        assert np.abs(np.array(res.tvec) - w["tvec"]).max() <= TOL_M
+    fe.close()
+
+
 # ---------------------------------------------------------------------------- full-size cases
 def test_full_size_config2_lk_and_stages(G):
     """BASELINE config 2 sizes: grid step 5 (18,278 keypoints), 1024 PnP hypotheses."""

@@ -41,3 +41,35 @@ def test_lk_tracks_match_cv2(frames, pair):
     assert np.mean(d[st2 == 1] == 0) > 0.9
     assert np.abs(err1.ravel() - err2)[st2 == 1].max() < 1e-3
     assert iters.sum() > 0
+
+
+def _colorize(img):
+    f = img.astype(np.float32)
+    return np.stack([f, 255.0 - 0.8 * f, 255.0 * (f / 255.0) ** 0.7], -1).round().clip(0, 255).astype(np.uint8)
+
+
+@pytest.mark.parametrize("kind", ["replicated_gray", "color"])
+def test_lk_tracks_match_cv2_bgr(frames, kind):
+    """3-channel images (what the reference passes, imread default): the restatement processes the
+    channels as planes with one set of window sums; pinned against cv2 on the interleaved image."""
+    L0, L1, _ = frames
+    if kind == "replicated_gray":
+        A, B = cv2.cvtColor(L0, cv2.COLOR_GRAY2BGR), cv2.cvtColor(L1, cv2.COLOR_GRAY2BGR)
+    else:
+        A, B = _colorize(L0), _colorize(L1)
+    n, pyr = cv2.buildOpticalFlowPyramid(A, (21, 21), 3, withDerivatives=True)
+    for c in range(3):
+        mine = lk.build_pyramid(np.ascontiguousarray(A[:, :, c]), 3, 21)
+        for l in range(4):
+            assert np.array_equal(pyr[2 * l][:, :, c], mine[l])
+            assert np.array_equal(pyr[2 * l + 1][:, :, 2 * c:2 * c + 2], lk.scharr_deriv(mine[l]))
+    pts = glue.dense_keypoint_extractor(376, 1241, 30)
+    extra = np.array([[5, 5], [1236, 371], [0.4, 200.7], [1240.2, 3.3], [620.5, 375.9]], np.float32)
+    pts = np.concatenate([pts, extra])
+    p1, st1, err1 = cv2.calcOpticalFlowPyrLK(A, B, pts.reshape(-1, 1, 2), None)
+    p2, st2, err2 = lk.calc_optical_flow_pyr_lk(A, B, pts)
+    assert np.array_equal(st1.ravel(), st2)
+    d = np.abs(p1.reshape(-1, 2) - p2).max(1)[st2 == 1]
+    assert np.mean(d <= 0.01) >= 0.995 and np.mean(d == 0) > 0.6, (np.mean(d <= 0.01), np.mean(d == 0), d.max())
+    same = (st2 == 1) & (np.abs(p1.reshape(-1, 2) - p2).max(1) == 0)
+    assert np.abs(err1.ravel() - err2)[same].max() < 1e-4
