@@ -299,6 +299,7 @@ int vo_create(const vo_params* p, vo_ctx** out) {
   if (r == VO_OK) {
     if (cudaEventCreateWithFlags(&c->ev_left, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_lk, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_xform, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_stereo, cudaEventDisableTiming) != cudaSuccess) {
       set_error("cudaEventCreate failed");
       r = VO_ERR_CUDA;
@@ -344,6 +345,7 @@ int vo_destroy(vo_ctx* c) {
   if (c->ev_left) cudaEventDestroy(c->ev_left);
   if (c->ev_stereo) cudaEventDestroy(c->ev_stereo);
   if (c->ev_lk) cudaEventDestroy(c->ev_lk);
+  if (c->ev_xform) cudaEventDestroy(c->ev_xform);
   free_chain(c);
   delete c;
   return VO_OK;
@@ -1333,6 +1335,10 @@ int vo_seq_track(vo_ctx* c, const uint8_t* left, const uint8_t* right, int strid
   int kk = 0, ng = 0;
   int k = 0, ni = 0, att = 1;
   int r;
+  if (c->xform_pending) {   // previous frame's world transform still reads the stereo chain's outputs
+    VO_CUDA(cudaStreamWaitEvent(a->stream, c->ev_xform, 0));
+    c->xform_pending = false;
+  }
   // Two drivers for the dual-chain frame.  Measured on the bench workload (B200, 200 frames):
   //   host-driven chains, stereo chain on the worker thread (2-3 synchronisations per chain)  956 frames/s, e2e 910
   //   fused single-sync chains enqueued by this thread (device-side sampling)                  919 frames/s, e2e 874
@@ -1409,6 +1415,13 @@ int vo_seq_track(vo_ctx* c, const uint8_t* left, const uint8_t* right, int strid
     out->keyframe = 1;
     out->n_kf_points = kk;
     out->n_lk_in_stereo = ng;
+    // Everything the caller receives is already on the host; the world transform of the new keyframe
+    // points only feeds the NEXT frame's PnP (stream order), so the call does not wait for it.  The
+    // stereo chain must not overwrite its outputs before this has read them: ev_xform.
+    VO_CUDA(cudaEventRecord(c->ev_xform, c->stream));
+    c->xform_pending = true;
+    c->seq_ref_slot = cur;
+    return VO_OK;
   } else if (ni < c->p.kf_min_inliers || force_keyframe) {
     // keyframe: src/VisualSLAM.cpp:120-137 -> insertKeyFrames (src/keyFrameManagement.cpp:9-31)
     if (!right) {

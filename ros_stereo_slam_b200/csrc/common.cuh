@@ -97,7 +97,8 @@ struct vo_ctx {
   bool task_pending = false, task_done = false, quit = false;
   int task_result = 0;
   std::string task_error;
-  cudaEvent_t ev_left = nullptr, ev_stereo = nullptr, ev_lk = nullptr;
+  cudaEvent_t ev_left = nullptr, ev_stereo = nullptr, ev_lk = nullptr, ev_xform = nullptr;
+  bool xform_pending = false;          // the last keyframe transform was enqueued without a final synchronisation
   cudaEvent_t ev_lk_done = nullptr;    // when set, track_pnp_fused_enqueue records it right after its LK launch
 
   // image staging + pyramids: slot 0/1 ping-pong left images (reference <-> current), slot 2 right

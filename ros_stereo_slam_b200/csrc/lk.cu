@@ -289,23 +289,28 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
                                       st_col_ok, st_last_ok);
       int sb1 = 0, sb2 = 0;
       {
+        // four independent accumulators per sum (ncu: 29 % of the stalls were `wait`, i.e. the 14-deep
+        // dependent IMAD chains of a single accumulator with only 3 warps per scheduler to hide them)
+        int p1[4] = {0, 0, 0, 0}, p2[4] = {0, 0, 0, 0};
         int jv[SEG];
         seg_bilinear(tile, rowA, colA + sh, wt, wb, jv);
 #pragma unroll
         for (int x = 0; x < SEG; x++) {
           const int dj = LK_OPT_HOIST ? jv[x] : jv[x] - Iw[x];
-          sb1 += dj * Ix[x];
-          sb2 += dj * Iy[x];
+          p1[x & 1] += dj * Ix[x];
+          p2[x & 1] += dj * Iy[x];
         }
         if (hasB) {
           seg_bilinear(tile, rowB, colB + sh, wt, wb, jv);
 #pragma unroll
           for (int x = 0; x < SEG; x++) {
             const int dj = LK_OPT_HOIST ? jv[x] : jv[x] - Iw[SEG + x];
-            sb1 += dj * Ix[SEG + x];
-            sb2 += dj * Iy[SEG + x];
+            p1[2 + (x & 1)] += dj * Ix[SEG + x];
+            p2[2 + (x & 1)] += dj * Iy[SEG + x];
           }
         }
+        sb1 = (p1[0] + p1[1]) + (p1[2] + p1[3]);
+        sb2 = (p2[0] + p2[1]) + (p2[2] + p2[3]);
       }
       n_iters_done++;
       const float b1 = __fmul_rn(__ll2float_rn(warp_sum_exact(sb1) - C1), FLT_SCALE);
