@@ -168,6 +168,12 @@ int vo_debug_epnp(vo_ctx* ctx, const float* obj15, const float* img10, double* d
  * (same loop as insertKeyFrames :20-30).  M row-major 3x4 double. */
 int vo_transform_points(vo_ctx* ctx, const double M[12], const float* xyz_in, int n, float* xyz_out);
 
+/* ---- cv::cvtColor(bgr, gray, CV_BGR2GRAY) for 8-bit images (src/StereoCV.cpp:35-36; the commented-out
+ * conversion of src/keyFrameManagement.cpp:53,65): bit-exact with OpenCV's fixed-point formula.  For callers
+ * that hold imread's BGR frames but run the 1-channel pipeline (channels = 1).  bgr: h x w x 3, stride >= 3*w
+ * bytes; gray: h x w, gray_stride >= w; both host pointers (is_device = 0) or both device pointers (1). */
+int vo_bgr_to_gray(vo_ctx* ctx, const uint8_t* bgr, int stride, int is_device, uint8_t* gray, int gray_stride);
+
 /* ---- a-8  Rodrigues + inversion, src/VisualSLAM.cpp:70-74,93-97: pose3x4 = [R^T | -R^T tvec]. */
 int vo_pose_from_pnp(const double rvec[3], const double tvec[3], double pose3x4[12]);
 

@@ -237,3 +237,15 @@ def run_sequence(frames_l, frames_r, step=30, pnp_iters=100, kf_min_inliers=200,
         rec["ms"] = (time.perf_counter() - t0) * 1e3
         out.append(rec)
     return out
+
+
+def bgr_to_gray(bgr):
+    """cv::cvtColor(im, gray, CV_BGR2GRAY) as the reference calls it (src/StereoCV.cpp:35-36)."""
+    return cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY)
+
+
+def bgr_to_gray_restated(bgr):
+    """The arithmetic behind it for 8-bit images: 15-bit fixed point, round to nearest
+    (pinned against cv2 in tests/test_oracle_misc.py)."""
+    b, g, r = (bgr[..., i].astype(np.int32) for i in range(3))
+    return ((b * 3735 + g * 19235 + r * 9798 + (1 << 14)) >> 15).astype(np.uint8)

@@ -144,7 +144,7 @@ static void free_chain(vo_ctx* c) {
   void* dev[] = {c->d_xy_in, c->d_xy_trk, c->d_status, c->d_err, c->d_xyz_in, c->d_c_ref, c->d_c_trk, c->d_c_xyz,
                  c->d_f_ref, c->d_f_trk, c->d_f_xyz, c->d_xyz_tmp, c->d_mask, c->d_idx, c->d_seq_xy, c->d_seq_xyz,
                  c->d_count, c->d_tile_state, c->d_samples, c->d_models, c->d_counts, c->d_sel, c->d_pose, c->d_cam,
-                 c->d_lk_work, c->d_rng, c->d_flags, c->d_epoch, c->d_Pst, c->d_bgr};
+                 c->d_lk_work, c->d_rng, c->d_flags, c->d_epoch, c->d_Pst, c->d_bgr, c->d_gray};
   for (void* p : dev) cudaFree(p);
   void* host[] = {c->h_count, c->h_pts, c->h_samples, c->h_sel, c->h_pose, c->h_lk_work, c->h_flags};
   for (void* p : host) cudaFreeHost(p);
@@ -1138,6 +1138,22 @@ int vo_transform_points(vo_ctx* c, const double M[12], const float* xyz_in, int 
   VO_CUDA(cudaMemcpyAsync(c->d_xyz_in, xyz_in, (size_t)n * sizeof(float3), cudaMemcpyHostToDevice, c->stream));
   VO_TRY(transform_launch(c, c->d_cam + 24, c->d_xyz_in, n, c->d_xyz_tmp));
   VO_CUDA(cudaMemcpyAsync(xyz_out, c->d_xyz_tmp, (size_t)n * sizeof(float3), cudaMemcpyDeviceToHost, c->stream));
+  return sync_stream(c);
+}
+
+int vo_bgr_to_gray(vo_ctx* c, const uint8_t* bgr, int stride, int is_device, uint8_t* gray, int gray_stride) {
+  CHECK_CTX(c);
+  const int w = c->p.width, h = c->p.height;
+  if (!bgr || !gray || stride < 3 * w || gray_stride < w) return VO_ERR_INVALID_ARG;
+  if (is_device) {
+    VO_TRY(bgr2gray_launch(c, bgr, stride, gray, gray_stride));
+    return sync_stream(c);
+  }
+  if (!c->d_bgr) VO_CUDA(cudaMalloc(&c->d_bgr, (size_t)3 * w * h));
+  if (!c->d_gray) VO_CUDA(cudaMalloc(&c->d_gray, (size_t)w * h));
+  VO_CUDA(cudaMemcpy2DAsync(c->d_bgr, 3 * w, bgr, stride, 3 * w, h, cudaMemcpyHostToDevice, c->stream));
+  VO_TRY(bgr2gray_launch(c, c->d_bgr, 3 * w, c->d_gray, w));
+  VO_CUDA(cudaMemcpy2DAsync(gray, gray_stride, c->d_gray, w, w, h, cudaMemcpyDeviceToHost, c->stream));
   return sync_stream(c);
 }
 

@@ -153,6 +153,7 @@ struct vo_ctx {
 
   // interleaved BGR staging (channels == 3): the image lands here, split_planes_kernel de-interleaves it
   uint8_t* d_bgr = nullptr;
+  uint8_t* d_gray = nullptr;      // vo_bgr_to_gray staging (lazily allocated)
   float* h_pts = nullptr;         // cap * 8 floats
 
   // LK work counters
@@ -196,6 +197,7 @@ void pyr_free(Pyramid& p);
 int pyr_build(vo_ctx* c, int slot, const uint8_t* d_tight /*w*h device*/, bool with_deriv);
 int pyr_ensure_deriv(vo_ctx* c, int slot);
 int pyr_split_bgr(vo_ctx* c, int slot, const uint8_t* d_bgr /*tight h x 3w*/);
+int bgr2gray_launch(vo_ctx* c, const uint8_t* d_bgr, int src_pitch, uint8_t* d_gray, int dst_pitch);
 PyrView pyr_view(const Pyramid& p);
 
 int lk_launch(vo_ctx* c, int slot_prev, int slot_next, const float2* d_prev, int n, float2* d_next, uint8_t* d_status,

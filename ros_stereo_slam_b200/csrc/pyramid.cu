@@ -289,6 +289,43 @@ __global__ void split_planes_kernel(const uint8_t* __restrict__ bgr, int w, int 
   }
 }
 
+// cv::cvtColor(BGR2GRAY) for 8-bit images (reference src/StereoCV.cpp:35-36): OpenCV's 15-bit fixed point
+// gray = (B*3735 + G*19235 + R*9798 + 2^14) >> 15.  4 pixels per thread, one uchar4 store.
+__global__ void bgr2gray_kernel(const uint8_t* __restrict__ bgr, int w, int h, int src_pitch, uint8_t* __restrict__ gray,
+                                int dst_pitch) {
+  const int x = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+  const int y = blockIdx.y;
+  if (x >= w) return;
+  const uint8_t* s = bgr + (size_t)y * src_pitch + 3 * x;
+  uint8_t* d = gray + (size_t)y * dst_pitch + x;
+  uint8_t o[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    if (x + k < w) {
+      const int b = __ldg(s + 3 * k), g = __ldg(s + 3 * k + 1), r = __ldg(s + 3 * k + 2);
+      o[k] = (uint8_t)((b * 3735 + g * 19235 + r * 9798 + (1 << 14)) >> 15);
+    } else {
+      o[k] = 0;
+    }
+  }
+  if (x + 4 <= w && ((reinterpret_cast<uintptr_t>(d) & 3) == 0)) {
+    *reinterpret_cast<uchar4*>(d) = make_uchar4(o[0], o[1], o[2], o[3]);
+  } else {
+    for (int k = 0; k < 4 && x + k < w; k++) d[k] = o[k];
+  }
+}
+
+int bgr2gray_launch(vo_ctx* c, const uint8_t* d_bgr, int src_pitch, uint8_t* d_gray, int dst_pitch) {
+  const int w = c->p.width, h = c->p.height;
+  dim3 b(128), g(div_up(div_up(w, 4), 128), h);
+  {
+    LaunchScope ls(c, VO_K_PYRAMID);
+    bgr2gray_kernel<<<g, b, 0, c->stream>>>(d_bgr, w, h, src_pitch, d_gray, dst_pitch);
+  }
+  VO_CUDA(cudaGetLastError());
+  return VO_OK;
+}
+
 // ------------------------------------------------------------------------------------
 int pyr_alloc(vo_ctx* c, Pyramid& p) {
   int w = c->p.width, h = c->p.height;

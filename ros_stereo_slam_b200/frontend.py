@@ -108,6 +108,15 @@ class VisualFrontEnd:
         check(self.lib.vo_debug_pyramid_level(self.h, _p(a), a.strides[0], level, _p(lv), _p(dv), C.byref(w), C.byref(h)))
         return lv, dv
 
+    def cvtColorBGR2GRAY(self, bgr):
+        """cv::cvtColor(bgr, CV_BGR2GRAY) on the device (bit-exact with OpenCV's 15-bit fixed point)."""
+        a = np.ascontiguousarray(bgr)
+        if a.dtype != np.uint8 or a.ndim != 3 or a.shape[2] != 3:
+            raise ValueError("expected an H x W x 3 uint8 image")
+        out = np.zeros(a.shape[:2], np.uint8)
+        check(self.lib.vo_bgr_to_gray(self.h, _p(a), a.strides[0], 0, _p(out), out.strides[0]))
+        return out
+
     def pyramid_padded(self, img, level, pad=21):
         """Level `level` and its derivative with `pad` border pixels, as the LK window sees them."""
         a = _u8img(img)

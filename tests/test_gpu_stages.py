@@ -380,6 +380,16 @@ def test_bgr_lk_matches_opencv(fe3, G, kind, pair):
         assert np.abs(p1[both] - p[both]).max() > 1e-3
 
 
+def test_bgr_to_gray_bit_exact(fe, G):
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, (376, 1241, 3), dtype=np.uint8)
+    assert np.array_equal(fe.cvtColorBGR2GRAY(img), cv2.cvtColor(img, cv2.COLOR_BGR2GRAY))
+    col = _colorize(G["L0"], 1)
+    assert np.array_equal(fe.cvtColorBGR2GRAY(col), glue.bgr_to_gray(col))
+    # replicated gray comes back unchanged (3735 + 19235 + 9798 = 2^15)
+    assert np.array_equal(fe.cvtColorBGR2GRAY(cv2.cvtColor(G["L0"], cv2.COLOR_GRAY2BGR)), G["L0"])
+
+
 def test_bgr_stage_entry_points_and_sequence(G):
     """stereoTriangulate / PerspectiveNpointEstimation / sequence driver on BGR frames vs the oracle glue
     (the reference's own data flow: imread -> LK on 3 channels)."""
