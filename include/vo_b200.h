@@ -174,6 +174,17 @@ int vo_transform_points(vo_ctx* ctx, const double M[12], const float* xyz_in, in
  * bytes; gray: h x w, gray_stride >= w; both host pointers (is_device = 0) or both device pointers (1). */
 int vo_bgr_to_gray(vo_ctx* ctx, const uint8_t* bgr, int stride, int is_device, uint8_t* gray, int gray_stride);
 
+/* ---- SURVEY 8(f)-3  visualSLAM::SORcloud(ref3d, colorMap)  src/rosFuncs.cpp:9-39 (every frame at
+ * src/VisualSLAM.cpp:154, on keyframes at :128): points with -z > 500 are dropped, then
+ * pcl::StatisticalOutlierRemoval(meanK = mean_k, stddevMulThresh = stddev_mul; the reference uses 200 and
+ * 0.01) keeps the points whose mean distance to their mean_k nearest neighbours is <= mean + mul * stddev
+ * of those means.  keep_idx receives the input indices of the kept points in input order (apply it to the
+ * colour vector on the caller's side); mean_dist (nullable, n floats) the per-point mean neighbour
+ * distance (-1 for points that never entered the cloud).  PCL is not vendored by the reference and not
+ * present in the build image: parity is against the restatement in oracle/sor.py. */
+int vo_sor_cloud(vo_ctx* ctx, const float* xyz, int n, int mean_k, double stddev_mul,
+                 int32_t* keep_idx, int cap, int* n_keep, float* mean_dist);
+
 /* ---- a-8  Rodrigues + inversion, src/VisualSLAM.cpp:70-74,93-97: pose3x4 = [R^T | -R^T tvec]. */
 int vo_pose_from_pnp(const double rvec[3], const double tvec[3], double pose3x4[12]);
 

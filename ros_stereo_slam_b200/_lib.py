@@ -64,7 +64,7 @@ _lib = None
 SYMBOLS = [
     "vo_default_params", "vo_abi_version", "vo_last_error", "vo_strerror", "vo_create", "vo_destroy", "vo_self_check",
     "vo_grid_keypoints", "vo_anms", "vo_lk_track", "vo_debug_pyramid_level", "vo_debug_pyramid_padded", "vo_fmat_ransac", "vo_triangulate",
-    "vo_pnp_ransac", "vo_debug_last_pnp", "vo_debug_last_fmat", "vo_debug_epnp", "vo_transform_points", "vo_bgr_to_gray", "vo_pose_from_pnp",
+    "vo_pnp_ransac", "vo_debug_last_pnp", "vo_debug_last_fmat", "vo_debug_epnp", "vo_transform_points", "vo_bgr_to_gray", "vo_sor_cloud", "vo_pose_from_pnp",
     "vo_dense_lk_tracking", "vo_fmat_thresholding", "vo_stereo_triangulate", "vo_insert_keyframe",
     "vo_track_frame", "vo_pnp_frame", "vo_seq_init", "vo_seq_track", "vo_seq_get_reference", "vo_cuda_stream",
     "vo_sync", "vo_profile_enable", "vo_profile_read", "vo_debug_timeline", "vo_launch_count", "vo_lk_work", "vo_measure_fp32_peak",

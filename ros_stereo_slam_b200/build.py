@@ -30,6 +30,7 @@ SOURCES = {
     "ransac.cu": ["--fmad=false"],
     "refine.cu": ["--fmad=false"],
     "selfcheck.cu": ["--fmad=false"],
+    "sor.cu": ["--fmad=false"],
     "aux.cu": [],
 }
 HEADERS = ["common.cuh", "cvmath.cuh", "fmat7.cuh", os.path.join("..", "..", "include", "vo_b200.h")]

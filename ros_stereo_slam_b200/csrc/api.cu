@@ -1157,6 +1157,68 @@ int vo_bgr_to_gray(vo_ctx* c, const uint8_t* bgr, int stride, int is_device, uin
   return sync_stream(c);
 }
 
+int vo_sor_cloud(vo_ctx* c, const float* xyz, int n, int mean_k, double stddev_mul, int32_t* keep_idx, int cap,
+                 int* n_keep, float* mean_dist) {
+  CHECK_CTX(c);
+  if (!xyz || !keep_idx || !n_keep || n < 0 || mean_k < 1) return VO_ERR_INVALID_ARG;
+  *n_keep = 0;
+  // visualSLAM::SORcloud, src/rosFuncs.cpp:11-19: points with -z > 500 never enter the cloud
+  std::vector<int32_t> cloud;       // input index of every cloud point
+  std::vector<int32_t> finite;      // cloud positions of the finite points (PCL skips the others)
+  std::vector<float> pts;
+  cloud.reserve(n);
+  pts.reserve((size_t)3 * n);
+  for (int i = 0; i < n; i++) {
+    const float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+    if (-1 * z > 500) continue;
+    if (std::isfinite(x) && std::isfinite(y) && std::isfinite(z)) {
+      finite.push_back((int32_t)cloud.size());
+      pts.push_back(x);
+      pts.push_back(y);
+      pts.push_back(z);
+    }
+    cloud.push_back(i);
+  }
+  const int m = (int)cloud.size(), mf = (int)finite.size();
+  if (mf > c->cap) return VO_ERR_CAPACITY;
+  std::vector<float> dist(m, 0.f);
+  int valid = 0;
+  // pcl::StatisticalOutlierRemoval::applyFilterIndices, first pass: a query whose k+1 neighbours cannot be
+  // found keeps distance 0 and is not counted
+  if (mf > mean_k) {
+    VO_CUDA(cudaMemcpyAsync(c->d_xyz_in, pts.data(), (size_t)mf * sizeof(float3), cudaMemcpyHostToDevice, c->stream));
+    VO_TRY(sor_mean_knn_launch(c, c->d_xyz_in, mf, mean_k, c->d_err));
+    std::vector<float> dv(mf);
+    VO_CUDA(cudaMemcpyAsync(dv.data(), c->d_err, (size_t)mf * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    VO_TRY(sync_stream(c));
+    for (int j = 0; j < mf; j++) dist[finite[j]] = dv[j];
+    valid = mf;
+  }
+  // second pass: mean and standard deviation of the mean distances, in double, in cloud order
+  double sum = 0, sq_sum = 0;
+  for (int j = 0; j < m; j++) {
+    const float d = dist[j];
+    sum += d;
+    sq_sum += d * d;           // float product, as in PCL
+  }
+  const double mean = sum / (double)valid;
+  const double variance = (sq_sum - sum * sum / (double)valid) / ((double)valid - 1);
+  const double stddev = sqrt(variance);
+  const double thr = mean + stddev_mul * stddev;
+  int k = 0;
+  for (int j = 0; j < m; j++) {
+    if (dist[j] > thr) continue;   // NaN threshold (no valid distance) keeps everything, like PCL
+    if (k < cap) keep_idx[k] = cloud[j];
+    k++;
+  }
+  *n_keep = k;
+  if (mean_dist) {
+    for (int i = 0; i < n; i++) mean_dist[i] = -1.f;   // -1: not part of the cloud
+    for (int j = 0; j < m; j++) mean_dist[cloud[j]] = dist[j];
+  }
+  return k > cap ? VO_ERR_CAPACITY : VO_OK;
+}
+
 int vo_pose_from_pnp(const double rvec[3], const double tvec[3], double pose3x4[12]) {
   if (!rvec || !tvec || !pose3x4) return VO_ERR_INVALID_ARG;
   pose_from_pnp(rvec, tvec, pose3x4);

@@ -233,6 +233,7 @@ int select_launch(vo_ctx* c, const int32_t* d_counts, int n_samples, int models_
 int pnp_refine_launch(vo_ctx* c, const float3* xyz, const float2* xy, const int32_t* d_idx, const int* d_n_inl,
                       const double* d_models, const int* d_sel, double* d_pose);
 
+int sor_mean_knn_launch(vo_ctx* c, const float3* d_pts, int n, int mean_k, float* d_mean);
 int selfcheck_run(vo_ctx* c);
 int epnp_debug_launch(vo_ctx* c, const float* d_obj, const float* d_img, double* d_dbg);
 int anms_launch(vo_ctx* c, const float* h_xy, const float* h_resp, int n, int num_keep, int32_t* keep_idx, int cap,

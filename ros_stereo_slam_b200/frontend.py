@@ -108,6 +108,21 @@ class VisualFrontEnd:
         check(self.lib.vo_debug_pyramid_level(self.h, _p(a), a.strides[0], level, _p(lv), _p(dv), C.byref(w), C.byref(h)))
         return lv, dv
 
+    def SORcloud(self, ref3d, colorMap=None, mean_k=200, stddev_mul=0.01, return_distances=False):
+        """visualSLAM::SORcloud (reference src/rosFuncs.cpp:9-39): returns the filtered points (and colours);
+        with return_distances also the kept indices and the per-point mean neighbour distances."""
+        pts = _f32(ref3d, 3)
+        n = len(pts)
+        keep = np.zeros(max(n, 1), np.int32)
+        nk = C.c_int()
+        md = np.zeros(max(n, 1), np.float32)
+        check(self.lib.vo_sor_cloud(self.h, _p(pts), n, int(mean_k), C.c_double(stddev_mul), _p(keep), n, C.byref(nk), _p(md)))
+        idx = keep[:nk.value].copy()
+        out = (pts[idx], None if colorMap is None else np.asarray(colorMap)[idx])
+        if return_distances:
+            return out + (idx, md[:n].copy())
+        return out
+
     def cvtColorBGR2GRAY(self, bgr):
         """cv::cvtColor(bgr, CV_BGR2GRAY) on the device (bit-exact with OpenCV's 15-bit fixed point)."""
         a = np.ascontiguousarray(bgr)

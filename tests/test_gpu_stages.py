@@ -419,6 +419,41 @@ def test_bgr_stage_entry_points_and_sequence(G):
     fe.close()
 
 
+# ---------------------------------------------------------------------------- SORcloud, SURVEY 8(f)-3
+def test_sor_cloud_matches_restatement(fe, G):
+    """visualSLAM::SORcloud on real keyframe clouds (stereoTriangulate at grid step 9 and 5) and on a synthetic
+    one with far outliers, duplicates and a -z > 500 point: kept index set identical to oracle/sor.py, per-point
+    mean neighbour distances bit-identical."""
+    from oracle import sor as osor
+    clouds = []
+    for step in (9, 5):
+        f = make_frontend(grid_step=step)
+        xyz, _ = f.stereoTriangulate(G["L0"], G["R0"])
+        f.close()
+        clouds.append(xyz)
+    rng = np.random.default_rng(11)
+    syn = np.c_[rng.uniform(-10, 10, 4000), rng.normal(1.65, 0.05, 4000), rng.uniform(4, 60, 4000)].astype(np.float32)
+    syn[100:120] = syn[99]                       # duplicates: several zero distances
+    syn[7] = (1, 2, -700)                        # never enters the cloud
+    syn[3000:3050] += rng.uniform(50, 90, (50, 3)).astype(np.float32)
+    clouds.append(syn)
+    for xyz in clouds:
+        assert len(xyz) > 1000
+        pts, _c, idx, md = fe.SORcloud(xyz, None, 200, 0.01, return_distances=True)
+        keep0, dist0, thr0 = osor.sor_cloud(xyz, 200, 0.01, return_all=True)
+        assert np.array_equal(md, dist0)
+        assert np.array_equal(idx, keep0)
+        assert np.array_equal(pts, xyz[keep0])
+        assert 0 < len(idx) < len(xyz)
+    # colours follow the points; fewer points than meanK + 1 keeps everything that enters the cloud
+    small = clouds[0][:150]
+    col = np.arange(450, dtype=np.float32).reshape(150, 3)
+    pts, c2 = fe.SORcloud(small, col)
+    assert np.array_equal(pts, small) and np.array_equal(c2, col)
+    pts, _ = fe.SORcloud(np.zeros((0, 3), np.float32))
+    assert len(pts) == 0
+
+
 # ---------------------------------------------------------------------------- full-size cases
 def test_full_size_config2_lk_and_stages(G):
     """BASELINE config 2 sizes: grid step 5 (18,278 keypoints), 1024 PnP hypotheses."""
