@@ -249,6 +249,12 @@ typedef struct vo_frame_result {
 int vo_seq_init(vo_ctx* ctx, const uint8_t* left, const uint8_t* right, int stride, int is_device, int* n_points);
 int vo_seq_track(vo_ctx* ctx, const uint8_t* left, const uint8_t* right, int stride, int is_device,
                  int force_keyframe, vo_frame_result* out);
+/* Optional: announce the NEXT frame's host images (pinned memory for a truly asynchronous copy) before
+ * calling vo_seq_track for the current one.  That call enqueues their copy to device staging on a separate
+ * copy stream as soon as its own first kernels are in flight; the vo_seq_track call that later passes the
+ * same pointers and stride skips its own copy.  The buffers must stay unchanged until that later call has
+ * returned.  Purely a transfer overlap: results are the same with or without it. */
+int vo_seq_prefetch(vo_ctx* ctx, const uint8_t* left, const uint8_t* right, int stride);
 /* current reference set (after the last vo_seq_* call); any pointer may be NULL */
 int vo_seq_get_reference(vo_ctx* ctx, float* xy, float* xyz, int cap, int* n);
 

@@ -346,6 +346,15 @@ int vo_destroy(vo_ctx* c) {
   if (c->ev_stereo) cudaEventDestroy(c->ev_stereo);
   if (c->ev_lk) cudaEventDestroy(c->ev_lk);
   if (c->ev_xform) cudaEventDestroy(c->ev_xform);
+  if (c->copy_stream) {
+    cudaStreamSynchronize(c->copy_stream);
+    cudaStreamDestroy(c->copy_stream);
+  }
+  for (int i = 0; i < 2; i++) {
+    if (c->ev_prefetch[i]) cudaEventDestroy(c->ev_prefetch[i]);
+    cudaFree(c->d_stage[i][0]);
+    cudaFree(c->d_stage[i][1]);
+  }
   free_chain(c);
   delete c;
   return VO_OK;
@@ -409,8 +418,12 @@ static int load_image(vo_ctx* c, int slot, const uint8_t* img, int stride, int i
     VO_TRY(pyr_split_bgr(c, slot, src));
     return pyr_build(c, slot, nullptr, with_deriv);
   }
-  VO_CUDA(cudaMemcpy2DAsync(L0.img + (size_t)PAD_Y * L0.pitch + PAD_L, L0.pitch, img, stride, L0.w, L0.h,
-                            is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+  if (is_device) {
+    VO_TRY(pyr_unpack_rows(c, slot, img, stride));
+  } else {
+    VO_CUDA(cudaMemcpy2DAsync(L0.img + (size_t)PAD_Y * L0.pitch + PAD_L, L0.pitch, img, stride, L0.w, L0.h,
+                              cudaMemcpyHostToDevice, c->stream));
+  }
   return pyr_build(c, slot, nullptr, with_deriv);
 }
 
@@ -603,6 +616,25 @@ static int run_pnp(vo_ctx* c, const float3* xyz, const float2* xy, int n, int it
   return VO_OK;
 }
 
+// Enqueue the host->device copies of the frame announced by vo_seq_prefetch (copy stream, tight staging).
+static int prefetch_issue(vo_ctx* c) {
+  if (!c->pf_wait_left) return VO_OK;
+  const int row_bytes = c->p.width * c->p.channels;
+  const int s = c->pf_next;
+  VO_CUDA(cudaMemcpy2DAsync(c->d_stage[s][0], row_bytes, c->pf_wait_left, c->pf_wait_stride, row_bytes, c->p.height,
+                            cudaMemcpyHostToDevice, c->copy_stream));
+  if (c->pf_wait_right)
+    VO_CUDA(cudaMemcpy2DAsync(c->d_stage[s][1], row_bytes, c->pf_wait_right, c->pf_wait_stride, row_bytes, c->p.height,
+                              cudaMemcpyHostToDevice, c->copy_stream));
+  VO_CUDA(cudaEventRecord(c->ev_prefetch[s], c->copy_stream));
+  c->pf_left[s] = c->pf_wait_left;
+  c->pf_right[s] = c->pf_wait_right;
+  c->pf_stride[s] = c->pf_wait_stride;
+  c->pf_next = 1 - s;
+  c->pf_wait_left = nullptr;
+  return VO_OK;
+}
+
 // ------------------------------------------------------------------------------------ stage pipelines (device)
 // LK slot_a -> slot_b of d_in (n points) + status compaction.  Optional xyz carried along.
 // Leaves survivors in d_c_ref / d_c_trk / d_c_xyz; *m = count (host, synchronised).
@@ -619,6 +651,7 @@ static int lk_and_compact(vo_ctx* c, int slot_a, int slot_b, const float2* d_in,
     VO_CUDA(cudaMemcpyAsync(c->h_pts + (size_t)2 * c->cap, c->d_c_trk, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost,
                             c->stream));
   }
+  if (!c->is_aux) VO_TRY(prefetch_issue(c));   // the next frame's H2D copies go out while this LK runs
   {
     TraceScope tw(6);
     VO_TRY(read_counts(c));
@@ -798,6 +831,7 @@ static int track_pnp_fused_enqueue(vo_ctx* c, int slot_ref, int slot_cur, const 
 }
 
 static int track_pnp_fused_finish(vo_ctx* c, FusedStatus* st) {
+  if (!c->is_aux) VO_TRY(prefetch_issue(c));
   const int Hf = fused_f_chunk(c, true);
   const int iters = std::max(c->p.pnp_iters, 1);
   const int Hp = c->p.ransac_exhaustive ? iters : std::min(iters, PNP_CHUNK);
@@ -1394,11 +1428,47 @@ int vo_seq_init(vo_ctx* c, const uint8_t* left, const uint8_t* right, int stride
   return sync_stream(c);
 }
 
+int vo_seq_prefetch(vo_ctx* c, const uint8_t* left, const uint8_t* right, int stride) {
+  CHECK_CTX(c);
+  const int row_bytes = c->p.width * c->p.channels;
+  if (!left || stride < row_bytes) return VO_ERR_INVALID_ARG;
+  if (!c->copy_stream) {
+    VO_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+      VO_CUDA(cudaEventCreateWithFlags(&c->ev_prefetch[i], cudaEventDisableTiming));
+      for (int e = 0; e < 2; e++) VO_CUDA(cudaMalloc(&c->d_stage[i][e], (size_t)row_bytes * c->p.height));
+    }
+  }
+  // Only noted here.  The copies are enqueued by the next vo_seq_track call once its own first kernels are in
+  // flight (prefetch_issue), so that their host-side cost hides behind GPU work; a frame announced while no
+  // vo_seq_track call follows is copied by vo_seq_track itself when it arrives.
+  c->pf_wait_left = left;
+  c->pf_wait_right = right;
+  c->pf_wait_stride = stride;
+  return VO_OK;
+}
+
 int vo_seq_track(vo_ctx* c, const uint8_t* left, const uint8_t* right, int stride, int is_device, int force_keyframe,
                  vo_frame_result* out) {
   CHECK_CTX(c);
   if (!left || !out || c->seq_ref_slot < 0) return VO_ERR_INVALID_ARG;
   memset(out, 0, sizeof(*out));
+  if (!is_device && c->pf_wait_left == left) c->pf_wait_left = nullptr;   // announced but never issued: copy it now
+  if (!is_device) {
+    // images announced by vo_seq_prefetch are already (being) copied: use the device staging instead
+    for (int s = 0; s < 2; s++) {
+      if (c->pf_left[s] == left && c->pf_stride[s] == stride && (!right || c->pf_right[s] == right)) {
+        VO_CUDA(cudaStreamWaitEvent(c->stream, c->ev_prefetch[s], 0));
+        VO_CUDA(cudaStreamWaitEvent(c->aux->stream, c->ev_prefetch[s], 0));
+        left = c->d_stage[s][0];
+        if (right) right = c->d_stage[s][1];
+        stride = c->p.width * c->p.channels;
+        is_device = 1;
+        c->pf_left[s] = nullptr;
+        break;
+      }
+    }
+  }
   const int ref = c->seq_ref_slot, cur = 1 - ref;
   // with derivatives: this left image is the previous image of this frame's stereo LK and of the
   // next frame's temporal LK (one fused launch builds levels, borders and Scharr planes)

@@ -131,6 +131,19 @@ struct vo_ctx {
   int* d_flags = nullptr;        // sampler status words (0 = ok)
   int* h_flags = nullptr;
 
+  // vo_seq_prefetch: the next frame's images are copied to tight device staging (two sets, alternating) on a
+  // copy stream while the current frame is being processed
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_prefetch[2] = {nullptr, nullptr};
+  uint8_t* d_stage[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [set][left/right]
+  const uint8_t* pf_left[2] = {nullptr, nullptr};
+  const uint8_t* pf_right[2] = {nullptr, nullptr};
+  int pf_stride[2] = {0, 0};
+  int pf_next = 0;
+  const uint8_t* pf_wait_left = nullptr;   // announced, copies not enqueued yet
+  const uint8_t* pf_wait_right = nullptr;
+  int pf_wait_stride = 0;
+
   // sequence state (vo_seq_*): reference set resident in HBM
   float2* d_seq_xy = nullptr;
   float3* d_seq_xyz = nullptr;
@@ -197,6 +210,7 @@ void pyr_free(Pyramid& p);
 int pyr_build(vo_ctx* c, int slot, const uint8_t* d_tight /*w*h device*/, bool with_deriv);
 int pyr_ensure_deriv(vo_ctx* c, int slot);
 int pyr_split_bgr(vo_ctx* c, int slot, const uint8_t* d_bgr /*tight h x 3w*/);
+int pyr_unpack_rows(vo_ctx* c, int slot, const uint8_t* d_src, int src_pitch);
 int bgr2gray_launch(vo_ctx* c, const uint8_t* d_bgr, int src_pitch, uint8_t* d_gray, int dst_pitch);
 PyrView pyr_view(const Pyramid& p);
 

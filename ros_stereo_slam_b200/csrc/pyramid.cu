@@ -289,6 +289,34 @@ __global__ void split_planes_kernel(const uint8_t* __restrict__ bgr, int w, int 
   }
 }
 
+// Device image with an arbitrary row stride -> level-0 interior of a padded plane.  An SM copy instead of
+// cudaMemcpy2DAsync(DeviceToDevice): the copy engines stay free for the host<->device transfers that run
+// beside the frame (vo_seq_prefetch), and 1241-byte rows are 376 separate DMA rows for them.
+__global__ void unpack_rows_kernel(const uint8_t* __restrict__ src, int w, int h, int src_pitch, uint8_t* __restrict__ img,
+                                   int pitch) {
+  const int x = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+  const int y = blockIdx.y;
+  if (x >= w) return;
+  const uint8_t* s = src + (size_t)y * src_pitch + x;
+  uint8_t* d = img + (size_t)(y + PAD_Y) * pitch + PAD_L + x;
+  if (x + 4 <= w) {
+    *reinterpret_cast<uchar4*>(d) = make_uchar4(__ldg(s), __ldg(s + 1), __ldg(s + 2), __ldg(s + 3));
+  } else {
+    for (int k = 0; x + k < w; k++) d[k] = s[k];
+  }
+}
+
+int pyr_unpack_rows(vo_ctx* c, int slot, const uint8_t* d_src, int src_pitch) {
+  PyrLevel& L0 = c->pyr[slot].lv[0];
+  dim3 b(128), g(div_up(div_up(L0.w, 4), 128), L0.h);
+  {
+    LaunchScope ls(c, VO_K_PYRAMID);
+    unpack_rows_kernel<<<g, b, 0, c->stream>>>(d_src, L0.w, L0.h, src_pitch, L0.img, L0.pitch);
+  }
+  VO_CUDA(cudaGetLastError());
+  return VO_OK;
+}
+
 // cv::cvtColor(BGR2GRAY) for 8-bit images (reference src/StereoCV.cpp:35-36): OpenCV's 15-bit fixed point
 // gray = (B*3735 + G*19235 + R*9798 + 2^14) >> 15.  4 pixels per thread, one uchar4 store.
 __global__ void bgr2gray_kernel(const uint8_t* __restrict__ bgr, int w, int h, int src_pitch, uint8_t* __restrict__ gray,

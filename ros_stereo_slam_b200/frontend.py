@@ -304,6 +304,12 @@ class VisualFrontEnd:
             check(self.lib.vo_seq_init(self.h, _p(a), _p(b), a.strides[0], 0, C.byref(n)))
         return n.value
 
+    def seq_prefetch(self, left, right=None):
+        """Announce the next frame's host images (vo_seq_prefetch); pass the SAME arrays to seq_track later."""
+        a, b = _u8img(left), _u8img(right)
+        self._prefetched = (a, b)            # keep them alive until they are consumed
+        check(self.lib.vo_seq_prefetch(self.h, _p(a), _p(b), a.strides[0]))
+
     def seq_track(self, left, right=None, is_device=False, stride=None, force_keyframe=False):
         res = VoFrameResult()
         if is_device:

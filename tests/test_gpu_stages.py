@@ -454,6 +454,38 @@ def test_sor_cloud_matches_restatement(fe, G):
     assert len(pts) == 0
 
 
+def test_sequence_prefetch_is_a_pure_transfer_overlap():
+    """vo_seq_prefetch only moves the H2D copy of the next frame under the current frame's processing:
+    every field of every frame result is identical with and without it."""
+    sc = synth.Scene(4)
+    n = 4
+    Ls = [np.ascontiguousarray(sc.render(i, "L")) for i in range(n)]
+    Rs = [np.ascontiguousarray(sc.render(i, "R")) for i in range(n)]
+
+    def fields(res):
+        return (res.n_lk_in, res.n_tracked, res.n_inliers, res.attempt_used, res.keyframe, res.n_kf_points,
+                res.n_lk_in_stereo, tuple(res.rvec), tuple(res.tvec), tuple(res.pose3x4))
+
+    for kf in (200, 2 ** 31 - 1):
+        out = []
+        for use_prefetch in (False, True):
+            fe = make_frontend(kf_min_inliers=kf)
+            fe.seq_init(Ls[0], Rs[0])
+            rows = []
+            if use_prefetch:
+                fe.seq_prefetch(Ls[1], Rs[1])
+            for i in range(1, n):
+                if use_prefetch and i + 1 < n:
+                    fe.seq_prefetch(Ls[i + 1], Rs[i + 1])
+                res, code = fe.seq_track(Ls[i], Rs[i])
+                assert code == 0
+                rows.append(fields(res))
+            out.append((rows, fe.seq_reference()))
+            fe.close()
+        assert out[0][0] == out[1][0]
+        assert np.array_equal(out[0][1][0], out[1][1][0]) and np.array_equal(out[0][1][1], out[1][1][1])
+
+
 # ---------------------------------------------------------------------------- full-size cases
 def test_full_size_config2_lk_and_stages(G):
     """BASELINE config 2 sizes: grid step 5 (18,278 keypoints), 1024 PnP hypotheses."""
