@@ -1490,11 +1490,13 @@ int vo_seq_track(vo_ctx* c, const uint8_t* left, const uint8_t* right, int strid
   // Two drivers for the dual-chain frame.  Measured on the bench workload (B200, 200 frames):
   //   host-driven chains, stereo chain on the worker thread (2-3 synchronisations per chain)  956 frames/s, e2e 910
   //   fused single-sync chains enqueued by this thread (device-side sampling)                  919 frames/s, e2e 874
-  // The fused chains are what the single-chain entry points use (one synchronisation per call); with two
-  // chains in flight the host-driven form still wins, so it is the default here.  VO_B200_SEQ_FUSED=1 selects
-  // the other one.
+  // The fused chain is what the single-chain entry points use (one synchronisation per call; vo_pnp_frame is
+  // 47 us faster with it).  With two chains in flight it loses: without the host gaps between its stages the
+  // tracking chain reaches pnp_solve_kernel ~90 us earlier, while the stereo chain's LK launch (low priority,
+  // dispatched after the tracking LK) is still running -- and that latency-bound kernel slows down by more
+  // (0.30 -> 0.40 ms) than the gaps were worth.  VO_B200_SEQ_FUSED=1 selects the fused form.
   static const bool host_driven = getenv("VO_B200_SEQ_FUSED") == nullptr;
-  if (kf_known && c->seq_n > 0 && temporal_fusable(c) && !getenv("VO_B200_SEQ_WORKER") && !host_driven) {
+  if (kf_known && c->seq_n > 0 && temporal_fusable(c) && !host_driven) {
     // both chains are enqueued by this thread, the critical one (tracking + PnP, high-priority
     // stream) first; one synchronisation per chain at the end
     VO_CUDA(cudaEventRecord(c->ev_left, c->stream));           // cur-left pyramid is complete
