@@ -437,6 +437,8 @@ def test_sor_cloud_matches_restatement(fe, G):
     syn[7] = (1, 2, -700)                        # never enters the cloud
     syn[3000:3050] += rng.uniform(50, 90, (50, 3)).astype(np.float32)
     clouds.append(syn)
+    # point order must not matter for the per-point distances
+    clouds.append(clouds[0][rng.permutation(len(clouds[0]))])
     for xyz in clouds:
         assert len(xyz) > 1000
         pts, _c, idx, md = fe.SORcloud(xyz, None, 200, 0.01, return_distances=True)
@@ -452,6 +454,11 @@ def test_sor_cloud_matches_restatement(fe, G):
     assert np.array_equal(pts, small) and np.array_equal(c2, col)
     pts, _ = fe.SORcloud(np.zeros((0, 3), np.float32))
     assert len(pts) == 0
+    # other meanK values
+    for k in (600, 20):
+        _p, _c, idx, md = fe.SORcloud(clouds[0], None, k, 0.5, return_distances=True)
+        keep0, dist0, _t = osor.sor_cloud(clouds[0], k, 0.5, return_all=True)
+        assert np.array_equal(md, dist0) and np.array_equal(idx, keep0)
 
 
 def test_sequence_prefetch_is_a_pure_transfer_overlap():
