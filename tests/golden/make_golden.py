@@ -3,7 +3,7 @@ container.  The reference ships no golden vectors; these p
 OpenCV behaviour the parity tests compare against, so that the GPU box (which has no
 /root/reference) checks against committed numbers as well as against live cv2.
 
-    python tools/make_golden.py
+    python tests/golden/make_golden.py
 """
 import os
 import sys
@@ -11,7 +11,7 @@ import sys
 import cv2
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import glue, replay, synth  # noqa: E402
 

@@ -2,7 +2,7 @@
 pyramids (live cv2 4.13.0), SORcloud (oracle/sor.py; PCL is not available, see its header) and BGR2GRAY.
 Inputs are derived from the frames stored in vo_golden_v1.npz, so only outputs are stored.
 
-    python tools/make_golden_v2.py
+    python tests/golden/make_golden_v2.py
 """
 import os
 import sys
@@ -10,7 +10,7 @@ import sys
 import cv2
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import glue, sor  # noqa: E402
 

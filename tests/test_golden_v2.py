@@ -1,4 +1,4 @@
-"""Committed vectors for the rows added after v1 (tools/make_golden_v2.py): 3-channel LK / pyramids
+"""Committed vectors for the rows added after v1 (tests/golden/make_golden_v2.py): 3-channel LK / pyramids
 (cv2 4.13.0), SORcloud (oracle/sor.py, parity unpinned) and BGR2GRAY.  CPU: the oracle reproduces them.
 GPU: the CUDA path reproduces them through the C ABI."""
 import os
