@@ -90,9 +90,17 @@ constexpr int LK_WARPS = 4;
 // Stage the 22 x 28-byte patch whose (unaligned) origin is `a0` into `tile`; returns the byte
 // offset (0..3) of the origin inside the first staged word.  lane_off = (lane/8)*(pitch/4) +
 // lane%8 and step = 4*(pitch/4) are per-level constants, so each load is one 64-bit pointer bump.
+// `staged` (optional, warp-uniform) remembers the word-aligned origin that is in the tile: an LK iteration
+// usually moves the window by a fraction of a pixel, so the next iteration's patch is the one already staged
+// (same rows, same first word, only the byte offset and the bilinear weights change) and the six loads, six
+// stores and the exposed L2 latency of re-staging it are skipped.
 __device__ __forceinline__ unsigned stage_patch(const uint8_t* a0, int lane_off, int step, unsigned* tile_lane,
-                                                bool col_ok, bool last_ok) {
+                                                bool col_ok, bool last_ok, uintptr_t* staged = nullptr) {
   const uintptr_t a = reinterpret_cast<uintptr_t>(a0);
+  if (staged) {
+    if (*staged == (a & ~uintptr_t(3))) return (unsigned)(a & 3);
+    *staged = a & ~uintptr_t(3);
+  }
   const unsigned* w = reinterpret_cast<const unsigned*>(a & ~uintptr_t(3)) + lane_off;
   __syncwarp();   // everyone is done reading the previous tile
   unsigned v[6];
@@ -209,6 +217,7 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
 
     // ---- window extraction from the previous image + its Scharr derivative
     int sA11 = 0, sA12 = 0, sA22 = 0, sC1 = 0, sC2 = 0;
+    uintptr_t staged = 0;     // the I patch below goes through the tile unconditionally; J patches are cached
     {
       const size_t o0 = (size_t)(ipy + PAD_Y) * pitch + (ipx + PAD_L);
       const unsigned sh = stage_patch(I.img + o0, st_off, st_step, tile_lane, st_col_ok, st_last_ok);
@@ -286,7 +295,7 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
       }
       lk_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), wt, wb, iw00, iw01, iw10, iw11);
       const unsigned sh = stage_patch(J.img + ((iny + PAD_Y) * pitch + (inx + PAD_L)), st_off, st_step, tile_lane,
-                                      st_col_ok, st_last_ok);
+                                      st_col_ok, st_last_ok, &staged);
       int sb1 = 0, sb2 = 0;
       {
         // four independent accumulators per sum (ncu: 29 % of the stalls were `wait`, i.e. the 14-deep
@@ -349,7 +358,7 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
       } else {
         lk_weights(__fsub_rn(fx, (float)inx), __fsub_rn(fy, (float)iny), wt, wb, iw00, iw01, iw10, iw11);
         const unsigned sh = stage_patch(J.img + ((iny + PAD_Y) * pitch + (inx + PAD_L)), st_off, st_step, tile_lane,
-                                      st_col_ok, st_last_ok);
+                                      st_col_ok, st_last_ok, &staged);
         int se = 0;
         int jv[SEG];
         seg_bilinear(tile, rowA, colA + sh, wt, wb, jv);
