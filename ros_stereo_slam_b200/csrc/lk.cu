@@ -428,13 +428,16 @@ lk_kernel_c3(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, in
              unsigned long long* __restrict__ work, const int* __restrict__ n_dev) {
   constexpr int CN = 3;
   if (n_dev) n = min(n, *n_dev);
-  __shared__ unsigned smem[LK_WARPS * WARP_SMEM_WORDS];
+  // one image tile per channel (so that the J patches of an iteration can stay staged, see stage_patch)
+  // + one derivative tile
+  constexpr int WARP_WORDS_C3 = CN * TILE_WORDS + DTILE_WORDS;
+  __shared__ unsigned smem[LK_WARPS * WARP_WORDS_C3];
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= n) return;
-  unsigned* tile = smem + (threadIdx.x >> 5) * WARP_SMEM_WORDS;
-  unsigned* dtile = tile + TILE_WORDS;
-  unsigned* tile_lane = tile + (lane >> 3) * PS + (lane & 7);
+  unsigned* tile0 = smem + (threadIdx.x >> 5) * WARP_WORDS_C3;
+  unsigned* dtile = tile0 + CN * TILE_WORDS;
+  unsigned* tile_lane0 = tile0 + (lane >> 3) * PS + (lane & 7);
   const bool st_col_ok = (lane & 7) < 7, st_last_ok = (lane >> 3) < PROWS - 20;
   const float2 pt = prev_pts[warp];
   const float half_win = (WIN - 1) * 0.5f;
@@ -491,8 +494,11 @@ lk_kernel_c3(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, in
 
     // ---- window extraction from the previous image + its Scharr derivative, all planes
     int sA11 = 0, sA12 = 0, sA22 = 0, sC1 = 0, sC2 = 0;
+    uintptr_t staged[CN] = {0, 0, 0};
 #pragma unroll
     for (int ch = 0; ch < CN; ch++) {
+      unsigned* tile = tile0 + ch * TILE_WORDS;
+      unsigned* tile_lane = tile_lane0 + ch * TILE_WORDS;
       const unsigned sh = stage_patch(I.img + (size_t)ch * I.plane + o0, st_off, st_step, tile_lane, st_col_ok, st_last_ok);
       {
         const unsigned* dsrc = reinterpret_cast<const unsigned*>(I.deriv + (size_t)ch * I.plane + o0);
@@ -546,7 +552,9 @@ lk_kernel_c3(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, in
       int sb1 = 0, sb2 = 0;
 #pragma unroll
       for (int ch = 0; ch < CN; ch++) {
-        const unsigned sh = stage_patch(J.img + (size_t)ch * J.plane + oj, st_off, st_step, tile_lane, st_col_ok, st_last_ok);
+        unsigned* tile = tile0 + ch * TILE_WORDS;
+        const unsigned sh = stage_patch(J.img + (size_t)ch * J.plane + oj, st_off, st_step, tile_lane0 + ch * TILE_WORDS,
+                                        st_col_ok, st_last_ok, &staged[ch]);
         int jv[SEG];
         seg_bilinear(tile, rowA, colA + sh, wt, wb, jv);
 #pragma unroll
@@ -602,6 +610,8 @@ lk_kernel_c3(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, in
 #pragma unroll
         for (int ch = 0; ch < CN; ch++) {
           int iv[2 * SEG], jv[SEG];
+          unsigned* tile = tile0 + ch * TILE_WORDS;
+          unsigned* tile_lane = tile_lane0 + ch * TILE_WORDS;
           const unsigned shI = stage_patch(I.img + (size_t)ch * I.plane + o0, st_off, st_step, tile_lane, st_col_ok, st_last_ok);
           seg_bilinear(tile, rowA, colA + shI, wtI, wbI, iv);
           if (hasB) seg_bilinear(tile, rowB, colB + shI, wtI, wbI, iv + SEG);
