@@ -13,7 +13,8 @@ F-matrix RANSAC (x2), triangulation and PnP-RANSAC + refinement -- the metric's
           the library's stream, max over ranks.
   e2e   : the same through the C ABI with HOST buffers: every step copies that step's left and
           right image from pinned host memory (H2D inside the timed region) and reads the pose
-          and counters back (D2H).
+          and counters back (D2H).  The caller announces frame n+1 with vo_seq_prefetch before
+          it calls vo_seq_track for frame n, so that copy runs under frame n's processing.
   N > 1 : replicas only: one independent sequence per GPU, no data-path
           collective; torch.distributed (NCCL) is used for the barrier and the max/sum of the
           timings only.
