@@ -116,7 +116,8 @@ int vo_anms(vo_ctx* ctx, const float* xy, const float* response, int n, int num_
 
 /* ---- a-3  cv::calcOpticalFlowPyrLK(prev, next, prevPts, nextPts, status, err) with all
  * defaults, as called at src/tracking.cpp:18 and :52.  Raw outputs (no compaction);
- * err may be NULL. */
+ * err may be NULL: the sum is then skipped, but status still behaves as if err had been requested (the
+ * reference always passes it, and OpenCV's err pass can clear status at level 0). */
 int vo_lk_track(vo_ctx* ctx, const uint8_t* prev, const uint8_t* next, int stride,
                 const float* prev_xy, int n, float* next_xy, uint8_t* status, float* err);
 

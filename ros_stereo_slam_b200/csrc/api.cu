@@ -644,7 +644,7 @@ static int lk_and_compact(vo_ctx* c, int slot_a, int slot_b, const float2* d_in,
                           bool pts_to_host = false) {
   *m = 0;
   if (n <= 0) return VO_OK;
-  VO_TRY(lk_launch(c, slot_a, slot_b, d_in, n, c->d_xy_trk, c->d_status, c->d_err));
+  VO_TRY(lk_launch(c, slot_a, slot_b, d_in, n, c->d_xy_trk, c->d_status, nullptr));   // err is not consumed: test only
   VO_TRY(compact_launch(c, c->d_status, n, d_in, c->d_c_ref, c->d_xy_trk, c->d_c_trk, d_in_xyz, c->d_c_xyz, nullptr, 0));
   if (pts_to_host) {
     VO_CUDA(cudaMemcpyAsync(c->h_pts, c->d_c_ref, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
@@ -807,7 +807,7 @@ static int track_pnp_fused_enqueue(vo_ctx* c, int slot_ref, int slot_cur, const 
   const int Hp = c->p.ransac_exhaustive ? iters : std::min(iters, PNP_CHUNK);
   const float thr2 = (float)(c->p.pnp_thr * c->p.pnp_thr);
   c->n_dev = d_n;
-  VO_TRY(lk_launch(c, slot_ref, slot_cur, d_ref_xy, n, c->d_xy_trk, c->d_status, c->d_err));
+  VO_TRY(lk_launch(c, slot_ref, slot_cur, d_ref_xy, n, c->d_xy_trk, c->d_status, nullptr));
   if (c->ev_lk_done) VO_CUDA(cudaEventRecord(c->ev_lk_done, c->stream));
   VO_TRY(compact_launch(c, c->d_status, n, d_ref_xy, c->d_c_ref, c->d_xy_trk, c->d_c_trk, d_ref_xyz, c->d_c_xyz, nullptr, 0));
   c->n_dev = nullptr;
@@ -862,7 +862,7 @@ static int stereo_fused_enqueue(vo_ctx* c, int slot_l, int slot_r, int* n_grid_o
   // lk_after: the other chain's LK launch.  Either LK fills every SM; side by side they only slow each
   // other down, back to back this one overlaps the other chain's latency-bound RANSAC solvers instead.
   if (lk_after) VO_CUDA(cudaStreamWaitEvent(c->stream, lk_after, 0));
-  VO_TRY(lk_launch(c, slot_l, slot_r, c->d_xy_in, ng, c->d_xy_trk, c->d_status, c->d_err));
+  VO_TRY(lk_launch(c, slot_l, slot_r, c->d_xy_in, ng, c->d_xy_trk, c->d_status, nullptr));
   VO_TRY(compact_launch(c, c->d_status, ng, c->d_xy_in, c->d_c_ref, c->d_xy_trk, c->d_c_trk, nullptr, nullptr, nullptr, 0));
   VO_TRY(enqueue_fmat_fused(c, ng, c->p.f_thr_stereo, false));
   c->n_dev = c->d_count + 1;
@@ -987,7 +987,7 @@ int vo_lk_track(vo_ctx* c, const uint8_t* prev, const uint8_t* next, int stride,
   VO_TRY(load_image(c, 0, prev, stride, 0, true));
   VO_TRY(load_image(c, 1, next, stride, 0, false));
   VO_CUDA(cudaMemcpyAsync(c->d_xy_in, prev_xy, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
-  VO_TRY(lk_launch(c, 0, 1, c->d_xy_in, n, c->d_xy_trk, c->d_status, c->d_err));
+  VO_TRY(lk_launch(c, 0, 1, c->d_xy_in, n, c->d_xy_trk, c->d_status, err ? c->d_err : nullptr));
   VO_CUDA(cudaMemcpyAsync(next_xy, c->d_xy_trk, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
   VO_CUDA(cudaMemcpyAsync(status, c->d_status, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
   if (err) VO_CUDA(cudaMemcpyAsync(err, c->d_err, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));

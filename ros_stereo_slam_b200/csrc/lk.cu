@@ -355,7 +355,7 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
       const int inx = (int)floorf(fx), iny = (int)floorf(fy);
       if (inx < -WIN || inx >= J.w || iny < -WIN || iny >= J.h) {
         st = false;
-      } else {
+      } else if (err) {   // callers that do not read err (the reference never does) skip the sum, not the test above
         lk_weights(__fsub_rn(fx, (float)inx), __fsub_rn(fy, (float)iny), wt, wb, iw00, iw01, iw10, iw11);
         const unsigned sh = stage_patch(J.img + ((iny + PAD_Y) * pitch + (inx + PAD_L)), st_off, st_step, tile_lane,
                                       st_col_ok, st_last_ok, &staged);
@@ -603,7 +603,7 @@ lk_kernel_c3(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, in
       const int inx = (int)floorf(fx), iny = (int)floorf(fy);
       if (inx < -WIN || inx >= J.w || iny < -WIN || iny >= J.h) {
         st = false;
-      } else {
+      } else if (err) {
         lk_weights(__fsub_rn(fx, (float)inx), __fsub_rn(fy, (float)iny), wt, wb, iw00, iw01, iw10, iw11);
         const size_t oj = (size_t)(iny + PAD_Y) * pitch + (inx + PAD_L);
         int se = 0;
