@@ -1414,6 +1414,9 @@ int vo_pnp_frame(vo_ctx* c, const uint8_t* ref_img, const uint8_t* cur_img, int 
 int vo_seq_init(vo_ctx* c, const uint8_t* left, const uint8_t* right, int stride, int is_device, int* n_points) {
   CHECK_CTX(c);
   if (!left || !right) return VO_ERR_INVALID_ARG;
+  // a new sequence: forget announced frames (their copies, if any, are left to finish)
+  c->pf_left[0] = c->pf_left[1] = c->pf_wait_left = nullptr;
+  if (c->copy_stream) VO_CUDA(cudaStreamSynchronize(c->copy_stream));
   VO_TRY(load_image(c, 0, left, stride, is_device, true));
   VO_TRY(load_image(c, 2, right, stride, is_device, false));
   int k = 0;
