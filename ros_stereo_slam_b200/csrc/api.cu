@@ -144,7 +144,7 @@ static void free_chain(vo_ctx* c) {
   void* dev[] = {c->d_xy_in, c->d_xy_trk, c->d_status, c->d_err, c->d_xyz_in, c->d_c_ref, c->d_c_trk, c->d_c_xyz,
                  c->d_f_ref, c->d_f_trk, c->d_f_xyz, c->d_xyz_tmp, c->d_mask, c->d_idx, c->d_seq_xy, c->d_seq_xyz,
                  c->d_count, c->d_tile_state, c->d_samples, c->d_models, c->d_counts, c->d_sel, c->d_pose, c->d_cam,
-                 c->d_lk_work, c->d_rng, c->d_flags, c->d_epoch, c->d_Pst, c->d_bgr, c->d_gray};
+                 c->d_lk_work, c->d_rng, c->d_flags, c->d_epoch, c->d_Pst, c->d_bgr, c->d_gray, c->d_sor};
   for (void* p : dev) cudaFree(p);
   void* host[] = {c->h_count, c->h_pts, c->h_samples, c->h_sel, c->h_pose, c->h_lk_work, c->h_flags};
   for (void* p : host) cudaFreeHost(p);

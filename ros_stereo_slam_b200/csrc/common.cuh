@@ -167,6 +167,8 @@ struct vo_ctx {
   // interleaved BGR staging (channels == 3): the image lands here, split_planes_kernel de-interleaves it
   uint8_t* d_bgr = nullptr;
   uint8_t* d_gray = nullptr;      // vo_bgr_to_gray staging (lazily allocated)
+  void* d_sor = nullptr;          // SORcloud scratch: sort keys / order / sorted points / CUB temp (lazily allocated)
+  size_t sor_tmp_bytes = 0;
   float* h_pts = nullptr;         // cap * 8 floats
 
   // LK work counters
