@@ -279,8 +279,12 @@ def run_ours(args):
                     "frac": round(lk_bytes / (lk_avg_ms * 1e-3) / 1e9 / hbm_peak, 5), "peak_source": hbm_src,
                     "note": "working set (~5 MB of pyramids) is L2-resident; HBM is not the bound"},
             # dram__bytes_read.sum + dram__bytes_write.sum of one lk_kernel launch (18,278 points) from the
-            # ncu --set full capture in profiles/r01_lk_kernel_s2_ncu.txt (4,413,440 B; r01_lk_kernel_final_ncu.txt: 4,413,184 B); algorithmic bytes are 4.07 MB
-            "traffic": 4413440,
+            # ncu --set full capture in profiles/r01_lk_kernel_final_s2_ncu.txt (4,414,208 B; r01_lk_kernel_final_ncu.txt: 4,413,184 B); algorithmic bytes are 4.07 MB
+            # the kernel is integer/issue bound (DP2A, IMAD, shifts): what ncu says about the issue slots of the same
+            # kernel on the same 18,278-point input (static figure from the committed capture, not measured here)
+            "issue_slots_ncu": {"issue_active_pct": 62.1, "warp_instructions_per_launch": 147460166,
+                                "source": "profiles/r01_lk_kernel_final_s2_ncu.txt (smsp__issue_active, smsp__inst_executed)"},
+            "traffic": 4414208,
             "algorithmic_bytes_per_launch": round(lk_bytes),
         }
         out = {
