@@ -186,6 +186,52 @@ int vo_bgr_to_gray(vo_ctx* ctx, const uint8_t* bgr, int stride, int is_device, u
 int vo_sor_cloud(vo_ctx* ctx, const float* xyz, int n, int mean_k, double stddev_mul,
                  int32_t* keep_idx, int cap, int* n_keep, float* mean_dist);
 
+/* ---- a-11 / SURVEY 8(f)-4  dense stereo: StereoProcess::stereoMatch  src/StereoCV.cpp:21-62 and
+ * StereoProcess::reprojectDisparity  src/StereoCV.cpp:221-250.
+ * vo_sgbm_params mirrors the arguments of cv::StereoSGBM::create (mode = MODE_SGBM, the default the reference
+ * uses); vo_sgbm_default_params fills the reference's values (1, 96, 7, 24, 96, 0, 60, 0, 3000, 5;
+ * src/StereoCV.cpp:39-50).  Supported range: numDisparities a multiple of 16 up to 256, odd blockSize up to 11,
+ * preFilterCap up to 126, and blockSize^2 * (2 * ftzero + 63) + P2 <= 32767 (OpenCV's int16 cost range); other
+ * values, and images with width - (minDisparity + numDisparities) <= blockSize / 2 (where cv2 throws), return
+ * VO_ERR_INVALID_ARG.  Image size is per call: the reference runs this on its own executable's frames. */
+typedef struct vo_sgbm_params {
+  int min_disparity;        /* 1    */
+  int num_disparities;      /* 96   */
+  int block_size;           /* 7    */
+  int p1;                   /* 24   */
+  int p2;                   /* 96   */
+  int disp12_max_diff;      /* 0 (OpenCV treats <= 0 as 1) */
+  int pre_filter_cap;       /* 60   */
+  int uniqueness_ratio;     /* 0    */
+  int speckle_window_size;  /* 3000 */
+  int speckle_range;        /* 5    */
+} vo_sgbm_params;
+void vo_sgbm_default_params(vo_sgbm_params* p);
+/* matcher->compute(grayL, grayR, disp): 8-bit 1-channel images (stride bytes per row) -> int16 disparity, 16x
+ * fixed point, invalid = (minDisparity - 1) * 16, disp_stride bytes per row; bit-identical to cv2 4.13.0.  disp
+ * may be NULL: the result then stays on the device for vo_reproject_disparity. */
+int vo_sgbm_compute(vo_ctx* ctx, const uint8_t* left, const uint8_t* right, int stride, int width, int height,
+                    const vo_sgbm_params* p, int16_t* disp, int disp_stride);
+/* StereoProcess::stereoMatch: the same on imread's BGR frames (stride >= 3 * width), cvtColor(BGR2GRAY) on the
+ * device first (src/StereoCV.cpp:35-36). */
+int vo_stereo_match(vo_ctx* ctx, const uint8_t* left_bgr, const uint8_t* right_bgr, int stride, int width, int height,
+                    const vo_sgbm_params* p, int16_t* disp, int disp_stride);
+/* StereoProcess::reprojectDisparity: disp.convertTo(CV_32F) (the raw 16x values, as the reference does),
+ * reprojectImageTo3D with Q (row-major 4x4, from the caller's stereoRectify, src/StereoCV.cpp:229), points with
+ * z > 5 or z <= 0.01 skipped, y negated, raster order.  disp = NULL uses the device-resident result of the last
+ * vo_sgbm_compute / vo_stereo_match of the same size.  xyz receives the points, pix_idx (nullable) their
+ * y * width + x for the caller's colour lookup (lImg.at<Vec3b>(i, j), src/StereoCV.cpp:238); *n is the number of
+ * points that passed (VO_ERR_CAPACITY when it exceeds cap; the first cap are written). */
+int vo_reproject_disparity(vo_ctx* ctx, const int16_t* disp, int disp_stride, int width, int height, const double Q[16],
+                           float* xyz, int32_t* pix_idx, int cap, int* n);
+/* device milliseconds of the last SGBM call: upload (+ gray conversion), prefilter, cost volume (BT + box sums),
+ * horizontal paths, diagonal paths, vertical paths + winner-take-all, left-right check + median, speckle filter,
+ * download */
+int vo_sgbm_timing(vo_ctx* ctx, float ms[9]);
+/* intermediate stages of the last SGBM call, for parity debugging: 0 = C (int16 [h][W1][D]), 1 = disparity after
+ * winner-take-all, 2 = after the left-right check (both int16 [h][w]), 3 = prefilter planes (uchar4 [4][h][w]) */
+int vo_debug_sgbm_stage(vo_ctx* ctx, int stage, void* out, uint64_t bytes);
+
 /* ---- a-8  Rodrigues + inversion, src/VisualSLAM.cpp:70-74,93-97: pose3x4 = [R^T | -R^T tvec]. */
 int vo_pose_from_pnp(const double rvec[3], const double tvec[3], double pose3x4[12]);
 

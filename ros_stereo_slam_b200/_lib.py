@@ -44,6 +44,11 @@ class VoParams(C.Structure):
     ]
 
 
+class VoSgbmParams(C.Structure):
+    _fields_ = [(k, C.c_int) for k in ("min_disparity", "num_disparities", "block_size", "p1", "p2", "disp12_max_diff",
+                                       "pre_filter_cap", "uniqueness_ratio", "speckle_window_size", "speckle_range")]
+
+
 class VoFrameResult(C.Structure):
     _fields_ = [
         ("rvec", C.c_double * 3), ("tvec", C.c_double * 3), ("pose3x4", C.c_double * 12),
@@ -70,6 +75,8 @@ SYMBOLS = [
     "vo_sync", "vo_profile_enable", "vo_profile_read", "vo_debug_timeline", "vo_launch_count", "vo_lk_work", "vo_measure_fp32_peak",
     "vo_synth_render_dev", "vo_alloc_host", "vo_free_host", "vo_alloc_dev", "vo_free_dev", "vo_memcpy_d2h",
     "vo_memcpy_h2d",
+    "vo_sgbm_default_params", "vo_sgbm_compute", "vo_stereo_match", "vo_reproject_disparity", "vo_sgbm_timing",
+    "vo_debug_sgbm_stage",
 ]
 
 
@@ -96,6 +103,8 @@ def load():
     lib.vo_destroy.argtypes = [C.c_void_p]
     lib.vo_default_params.argtypes = [C.POINTER(VoParams)]
     lib.vo_default_params.restype = None
+    lib.vo_sgbm_default_params.argtypes = [C.POINTER(VoSgbmParams)]
+    lib.vo_sgbm_default_params.restype = None
     _lib = lib
     return lib
 

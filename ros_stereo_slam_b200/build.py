@@ -31,6 +31,7 @@ SOURCES = {
     "refine.cu": ["--fmad=false"],
     "selfcheck.cu": ["--fmad=false"],
     "sor.cu": ["--fmad=false"],
+    "sgbm.cu": ["--fmad=false"],
     "aux.cu": [],
 }
 HEADERS = ["common.cuh", "cvmath.cuh", "fmat7.cuh", os.path.join("..", "..", "include", "vo_b200.h")]

@@ -344,7 +344,10 @@ __global__ void bgr2gray_kernel(const uint8_t* __restrict__ bgr, int w, int h, i
 }
 
 int bgr2gray_launch(vo_ctx* c, const uint8_t* d_bgr, int src_pitch, uint8_t* d_gray, int dst_pitch) {
-  const int w = c->p.width, h = c->p.height;
+  return bgr2gray_launch_wh(c, d_bgr, src_pitch, d_gray, dst_pitch, c->p.width, c->p.height);
+}
+
+int bgr2gray_launch_wh(vo_ctx* c, const uint8_t* d_bgr, int src_pitch, uint8_t* d_gray, int dst_pitch, int w, int h) {
   dim3 b(128), g(div_up(div_up(w, 4), 128), h);
   {
     LaunchScope ls(c, VO_K_PYRAMID);

@@ -1,0 +1,862 @@
+// sgbm.cu -- dense stereo: StereoProcess::stereoMatch (reference src/StereoCV.cpp:21-62) =
+// cvtColor(BGR2GRAY) x2 + StereoSGBM::create(1, 96, 7, 24, 96, 0, 60, 0, 3000, 5)->compute, and
+// StereoProcess::reprojectDisparity (src/StereoCV.cpp:221-250) = reprojectImageTo3D + depth gate.
+// SURVEY.md section 8 rows a-11 / (f)-4.  All integer; bit-identical to cv2 4.13.0 (oracle/sgbm.py is the
+// stage-by-stage restatement these kernels are compared with).
+//
+// Stages and HBM layout (W1 = number of columns that get a disparity = width - maxD for minD >= 0, D = numDisparities):
+//   K_pre    x-Sobel prefilter + the Birchfield-Tomasi half-pixel min/max of both planes (filtered, raw) of both
+//            images -> uchar4 (v, lo, hi, -) per pixel and plane                         [2][H][W] uchar4 x 2
+//   K_hsum   a CTA owns a strip of one row: BT pixel costs of the strip + halo for all D are computed into shared
+//            memory (the row-wise search over shared-memory strips of the right image), summed over the block
+//            width -> hsum[y][x][d] u16                                                  H*W1*D*2 bytes
+//   K_vsum   running sum over the block height (rows replicated at the border) -> C[y][x][d] s16
+//   K_path   one WARP per path, the D disparities of a pixel spread over the lanes (4 or 8 per lane, one 8/16-byte
+//            load per step), predecessor costs in registers, neighbours d-1/d+1 by two shuffles, min over d by one
+//            REDUX; C and S reads are prefetched 8 steps ahead so that the only latency on the chain is the
+//            recurrence itself.  Launches: both horizontal directions at once (S = L0, S2 = L4, write only), the
+//            two diagonals (read-modify-write of S), the vertical direction last, fused with winner-take-all,
+//            uniqueness test, sub-pixel step and the right-view disparity (one atomicMin on a packed
+//            (cost, 65535 - x) key replaces OpenCV's descending-x first-come rule).  Every L is >= 0, so OpenCV's two
+//            saturating adds collapse into S = min(32767, sum of the five L): the order of the directions is free.
+//   K_lr     left-right check, K_median 3x3, K_speckle: union-find connected components over |difference| <=
+//            16*speckleRange edges, components of <= speckleWindowSize pixels are cleared (cv::filterSpeckles).
+//   K_reproj reprojectImageTo3D on the float-converted 16x disparity + the reference's gate 0.01 < z <= 5 and y flip,
+//            then an order-preserving compaction (CUB DeviceSelect) -> points + their pixel indices for the
+//            caller's colour lookup.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace vo {
+
+constexpr int SG_MAX_COST = 32767;
+constexpr int SG_TX = 32;          // columns per K_hsum CTA
+constexpr int SG_MAX_D = 256;
+constexpr int SG_MAX_R = 5;        // block size <= 11
+constexpr int SG_PF = 8;           // prefetch distance of the path kernel (steps)
+constexpr unsigned SG_KEY_INIT = 0xFFFFFFFFu;
+
+struct Sgbm {
+  int w = 0, h = 0, D = 0;                  // allocation is for w*h pixels and (w - ...)*D costs
+  size_t cost_elems = 0;
+  uint8_t* img[2] = {nullptr, nullptr};     // tight gray images
+  uint8_t* bgr[2] = {nullptr, nullptr};     // tight BGR staging (vo_stereo_match)
+  uchar4* pl = nullptr;                     // [2 images][2 planes][h][w]
+  uint16_t* hsum = nullptr;                 // also reused as S2
+  int16_t* C = nullptr;
+  int16_t* S = nullptr;
+  unsigned* key2 = nullptr;                 // right-view (cost, x) keys
+  int16_t* disp[3] = {nullptr, nullptr, nullptr};   // raw WTA, after LR check, after median (+ speckle in place)
+  int* label = nullptr;
+  int* count = nullptr;
+  float3* xyz = nullptr;                    // reprojection, per pixel
+  uint8_t* keep = nullptr;
+  float3* xyz_out = nullptr;
+  int* idx_out = nullptr;
+  int* d_n = nullptr;
+  double* dQ = nullptr;
+  void* cub_tmp = nullptr;
+  size_t cub_bytes = 0;
+  bool have_disp = false;
+  int last_w = 0, last_h = 0;
+  cudaEvent_t ev[10] = {nullptr};
+  float ms[9] = {0};
+};
+
+void sgbm_free(vo_ctx* c) {
+  Sgbm* s = reinterpret_cast<Sgbm*>(c->sgbm);
+  if (!s) return;
+  void* dev[] = {s->img[0], s->img[1], s->bgr[0], s->bgr[1], s->pl, s->hsum, s->C, s->S, s->key2, s->disp[0], s->disp[1],
+                 s->disp[2], s->label, s->count, s->xyz, s->keep, s->xyz_out, s->idx_out, s->d_n, s->dQ, s->cub_tmp};
+  for (void* p : dev) cudaFree(p);
+  for (auto e : s->ev)
+    if (e) cudaEventDestroy(e);
+  delete s;
+  c->sgbm = nullptr;
+}
+
+static void sgbm_release_buffers(Sgbm* s) {
+  void** dev[] = {(void**)&s->img[0], (void**)&s->img[1], (void**)&s->bgr[0], (void**)&s->bgr[1], (void**)&s->pl,
+                  (void**)&s->hsum, (void**)&s->C, (void**)&s->S, (void**)&s->key2, (void**)&s->disp[0],
+                  (void**)&s->disp[1], (void**)&s->disp[2], (void**)&s->label, (void**)&s->count, (void**)&s->xyz,
+                  (void**)&s->keep, (void**)&s->xyz_out, (void**)&s->idx_out, (void**)&s->cub_tmp};
+  for (void** p : dev) {
+    cudaFree(*p);
+    *p = nullptr;
+  }
+}
+
+// ------------------------------------------------------------------------------------ K_pre
+// calcPixelCostBT, first half: the clipped x-Sobel plane and the raw plane of one image row; OpenCV writes tab[0]
+// (= ftzero) into both row ends of both planes.
+__device__ __forceinline__ int sg_plane_value(const uint8_t* __restrict__ r0, const uint8_t* __restrict__ rn,
+                                              const uint8_t* __restrict__ rs, int x, int w, int ftzero, int plane) {
+  if (x <= 0 || x >= w - 1) return ftzero;
+  if (plane) return r0[x];
+  int s = ((int)r0[x + 1] - (int)r0[x - 1]) * 2 + (int)rn[x + 1] - (int)rn[x - 1] + (int)rs[x + 1] - (int)rs[x - 1];
+  s = min(max(s, -ftzero), ftzero);
+  return s + ftzero;
+}
+
+__global__ void sgbm_prefilter_kernel(const uint8_t* __restrict__ imgL, const uint8_t* __restrict__ imgR, int w, int h,
+                                      int ftzero, uchar4* __restrict__ out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  const int im = blockIdx.z;
+  if (x >= w) return;
+  const uint8_t* img = im ? imgR : imgL;
+  const uint8_t* r0 = img + (size_t)y * w;
+  const uint8_t* rn = y > 0 ? r0 - w : r0;
+  const uint8_t* rs = y < h - 1 ? r0 + w : r0;
+#pragma unroll
+  for (int plane = 0; plane < 2; plane++) {
+    const int v = sg_plane_value(r0, rn, rs, x, w, ftzero, plane);
+    const int vl = x > 0 ? (v + sg_plane_value(r0, rn, rs, x - 1, w, ftzero, plane)) / 2 : v;
+    const int vr = x < w - 1 ? (v + sg_plane_value(r0, rn, rs, x + 1, w, ftzero, plane)) / 2 : v;
+    const int lo = min(min(vl, vr), v), hi = max(max(vl, vr), v);
+    out[(((size_t)im * 2 + plane) * h + y) * w + x] = make_uchar4((unsigned char)v, (unsigned char)lo, (unsigned char)hi, 0);
+  }
+}
+
+// ------------------------------------------------------------------------------------ K_hsum
+// pixel cost of calcPixelCostBT for (x1 = column in the left image, d): both planes, the raw one >> 2
+__device__ __forceinline__ int sg_bt(uchar4 u, uchar4 v, int shift) {
+  const int c0 = max(max(0, (int)u.x - (int)v.z), (int)v.y - (int)u.x);
+  const int c1 = max(max(0, (int)v.x - (int)u.z), (int)u.y - (int)v.x);
+  return min(c0, c1) >> shift;
+}
+
+__global__ void __launch_bounds__(256)
+sgbm_hsum_kernel(const uchar4* __restrict__ pl, int w, int h, int W1, int D, int minD, int minX1, int R,
+                 uint16_t* __restrict__ hsum) {
+  extern __shared__ uint16_t sg_pix[];   // [(SG_TX + 2R)][D]
+  const int y = blockIdx.y;
+  const int x0 = blockIdx.x * SG_TX;
+  const int ncol = SG_TX + 2 * R;
+  const uchar4* L0 = pl + ((size_t)0 * h + y) * w;   // left filtered
+  const uchar4* L1 = pl + ((size_t)1 * h + y) * w;   // left raw
+  const uchar4* R0 = pl + ((size_t)2 * h + y) * w;   // right filtered
+  const uchar4* R1 = pl + ((size_t)3 * h + y) * w;   // right raw
+  for (int e = threadIdx.x; e < ncol * D; e += blockDim.x) {
+    const int xi = e / D, dd = e - xi * D;
+    const int xw = min(max(x0 - R + xi, 0), W1 - 1);   // columns replicate at the border of the computed range
+    const int x1 = xw + minX1;
+    const int x2 = x1 - (dd + minD);
+    const int cst = sg_bt(__ldg(L0 + x1), __ldg(R0 + x2), 0) + sg_bt(__ldg(L1 + x1), __ldg(R1 + x2), 2);
+    sg_pix[e] = (uint16_t)cst;
+  }
+  __syncthreads();
+  const int nb = 2 * R + 1;
+  for (int e = threadIdx.x; e < SG_TX * D; e += blockDim.x) {
+    const int xo = e / D, dd = e - xo * D;
+    if (x0 + xo >= W1) break;
+    int s = 0;
+    for (int k = 0; k < nb; k++) s += sg_pix[(xo + k) * D + dd];
+    hsum[((size_t)y * W1 + x0 + xo) * D + dd] = (uint16_t)s;
+  }
+}
+
+// ------------------------------------------------------------------------------------ K_vsum
+__global__ void __launch_bounds__(256)
+sgbm_vsum_kernel(const uint16_t* __restrict__ hsum, int h, size_t row_elems, int R, int rows_per_strip,
+                 int16_t* __restrict__ C) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= row_elems) return;
+  const int ya = blockIdx.y * rows_per_strip;
+  const int yb = min(ya + rows_per_strip, h);
+  if (ya >= yb) return;
+  int s = 0;
+  for (int k = -R; k <= R; k++) s += hsum[(size_t)min(max(ya + k, 0), h - 1) * row_elems + e];
+  for (int y = ya; y < yb; y++) {
+    C[(size_t)y * row_elems + e] = (int16_t)s;
+    s += (int)hsum[(size_t)min(y + R + 1, h - 1) * row_elems + e] - (int)hsum[(size_t)max(y - R, 0) * row_elems + e];
+  }
+}
+
+// ------------------------------------------------------------------------------------ K_path
+template <int DPL> struct SgVec;
+template <> struct SgVec<4> { using T = uint2; };
+template <> struct SgVec<8> { using T = uint4; };
+
+template <int DPL>
+__device__ __forceinline__ void sg_unpack(const typename SgVec<DPL>::T& v, int* o) {
+  const unsigned* p = reinterpret_cast<const unsigned*>(&v);
+#pragma unroll
+  for (int k = 0; k < DPL / 2; k++) {
+    o[2 * k] = (int)(short)(p[k] & 0xFFFFu);
+    o[2 * k + 1] = (int)(short)(p[k] >> 16);
+  }
+}
+template <int DPL>
+__device__ __forceinline__ typename SgVec<DPL>::T sg_pack(const int* o) {
+  typename SgVec<DPL>::T v;
+  unsigned* p = reinterpret_cast<unsigned*>(&v);
+#pragma unroll
+  for (int k = 0; k < DPL / 2; k++) p[k] = ((unsigned)o[2 * k] & 0xFFFFu) | ((unsigned)o[2 * k + 1] << 16);
+  return v;
+}
+
+struct SgWta {
+  int16_t* disp1;       // [h][w], pre-filled with the invalid value
+  unsigned* key2;       // [h][w], pre-filled with SG_KEY_INIT
+  int w, minD, minX1, uniq;
+};
+
+// MODE 0: S = L (no read).  MODE 1: S = min(32767, S + L).  MODE 2: S = min(32767, S + S2 + L).
+// MODE 3: s = min(32767, S + L) is consumed by the winner-take-all step and not stored.
+// Directions: 0 left-to-right, 4 right-to-left (paths = rows), 1 down-right, 2 down, 3 down-left.
+template <int DPL, int MODE>
+__global__ void __launch_bounds__(128)
+sgbm_path_kernel(const int16_t* __restrict__ C, int16_t* __restrict__ S, int16_t* __restrict__ S_rl,
+                 const int16_t* __restrict__ S2, int W1, int H, int D, int P1, int P2, int dir_a, int dir_b, int npaths,
+                 SgWta wta) {
+  using V = typename SgVec<DPL>::T;
+  const int lane = threadIdx.x & 31;
+  const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (p >= npaths) return;
+  const int dir = blockIdx.y ? dir_b : dir_a;
+  int16_t* Sout = (blockIdx.y && S_rl) ? S_rl : S;
+  int x, y, n, sx, sy;
+  switch (dir) {
+    case 0: x = 0; y = p; n = W1; sx = 1; sy = 0; break;
+    case 4: x = W1 - 1; y = p; n = W1; sx = -1; sy = 0; break;
+    case 2: x = p; y = 0; n = H; sx = 0; sy = 1; break;
+    case 1:
+      if (p < W1) { x = p; y = 0; } else { x = 0; y = p - W1 + 1; }
+      n = min(H - y, W1 - x); sx = 1; sy = 1; break;
+    default:
+      if (p < W1) { x = p; y = 0; } else { x = W1 - 1; y = p - W1 + 1; }
+      n = min(H - y, x + 1); sx = -1; sy = 1; break;
+  }
+  const bool active = DPL * lane < D;
+  const bool last = DPL * (lane + 1) >= D;
+  const long long step = ((long long)sy * W1 + sx) * D;       // elements per step along the path
+  const size_t base = ((size_t)y * W1 + x) * D + (active ? DPL * lane : 0);
+  const int16_t* Cp = C + base;
+  int16_t* Sp = Sout + base;
+  const int16_t* S2p = MODE == 2 ? S2 + base : nullptr;
+
+  V cring[SG_PF], sring[SG_PF], tring[SG_PF];
+#pragma unroll
+  for (int k = 0; k < SG_PF; k++) {
+    if (k < n && active) {
+      cring[k] = __ldg(reinterpret_cast<const V*>(Cp + k * step));
+      if (MODE >= 1) sring[k] = *reinterpret_cast<const V*>(Sp + k * step);
+      if (MODE == 2) tring[k] = __ldg(reinterpret_cast<const V*>(S2p + k * step));
+    }
+  }
+  int Lp[DPL];
+#pragma unroll
+  for (int j = 0; j < DPL; j++) Lp[j] = active ? 0 : SG_MAX_COST;
+  int minp = 0;
+
+  for (int i0 = 0; i0 < n; i0 += SG_PF) {
+#pragma unroll
+    for (int k = 0; k < SG_PF; k++) {
+      const int i = i0 + k;
+      if (i >= n) break;
+      int cv[DPL], sv[DPL], tv[DPL];
+      if (active) {
+        sg_unpack<DPL>(cring[k], cv);
+        if (MODE >= 1) sg_unpack<DPL>(sring[k], sv);
+        if (MODE == 2) sg_unpack<DPL>(tring[k], tv);
+        if (i + SG_PF < n) {
+          cring[k] = __ldg(reinterpret_cast<const V*>(Cp + (long long)(i + SG_PF) * step));
+          if (MODE >= 1) sring[k] = *reinterpret_cast<const V*>(Sp + (long long)(i + SG_PF) * step);
+          if (MODE == 2) tring[k] = __ldg(reinterpret_cast<const V*>(S2p + (long long)(i + SG_PF) * step));
+        }
+      }
+      // formula 13 of the SGM paper as OpenCV evaluates it
+      int left = __shfl_up_sync(0xffffffffu, Lp[DPL - 1], 1);
+      int right = __shfl_down_sync(0xffffffffu, Lp[0], 1);
+      if (lane == 0) left = SG_MAX_COST;
+      if (last) right = SG_MAX_COST;
+      const int delta = minp + P2;
+      int Ln[DPL];
+      int m = 0x7fffffff;
+      if (active) {
+#pragma unroll
+        for (int j = 0; j < DPL; j++) {
+          const int a = Lp[j];
+          const int b = (j ? Lp[j - 1] : left) + P1;
+          const int c = (j < DPL - 1 ? Lp[j + 1] : right) + P1;
+          Ln[j] = cv[j] + min(min(a, b), min(c, delta)) - minp;
+          m = min(m, Ln[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < DPL; j++) Lp[j] = Ln[j];
+      }
+      minp = __reduce_min_sync(0xffffffffu, m);
+
+      int tot[DPL];
+      if (active) {
+#pragma unroll
+        for (int j = 0; j < DPL; j++) {
+          int t = Ln[j];
+          if (MODE >= 1) t += sv[j];
+          if (MODE == 2) t += tv[j];
+          tot[j] = min(t, SG_MAX_COST);
+        }
+        if (MODE != 3) *reinterpret_cast<V*>(Sp + (long long)i * step) = sg_pack<DPL>(tot);
+      }
+      if (MODE == 3) {
+        // winner-take-all over the final S of this pixel: first minimum
+        int key = 0x7fffffff;
+        if (active) {
+#pragma unroll
+          for (int j = 0; j < DPL; j++) key = min(key, (tot[j] << 8) | (DPL * lane + j));
+        }
+        key = __reduce_min_sync(0xffffffffu, key);
+        const int minS = key >> 8, bd = key & 255;
+        bool rej = false;
+        if (wta.uniq > 0) {
+          bool pr = false;
+          if (active) {
+#pragma unroll
+            for (int j = 0; j < DPL; j++)
+              pr |= (tot[j] * (100 - wta.uniq) < minS * 100) && (abs(bd - (DPL * lane + j)) > 1);
+          }
+          rej = __any_sync(0xffffffffu, pr);
+        }
+        const int dm = max(bd - 1, 0), dp = min(bd + 1, D - 1);
+        int vm = 0, vp = 0;
+        if (active) {
+#pragma unroll
+          for (int j = 0; j < DPL; j++) {
+            if ((dm & (DPL - 1)) == j) vm = tot[j];
+            if ((dp & (DPL - 1)) == j) vp = tot[j];
+          }
+        }
+        const int sm = __shfl_sync(0xffffffffu, vm, dm / DPL);
+        const int sp = __shfl_sync(0xffffffffu, vp, dp / DPL);
+        if (lane == 0 && !rej) {
+          const int px = x + i * sx, py = y + i * sy;
+          const int x2 = px + wta.minX1 - bd - wta.minD;
+          if (minS < SG_MAX_COST) atomicMin(wta.key2 + (size_t)py * wta.w + x2, ((unsigned)minS << 16) | (unsigned)(0xFFFF - px));
+          int dv;
+          if (0 < bd && bd < D - 1) {
+            const int denom2 = max(sm + sp - 2 * minS, 1);
+            dv = bd * 16 + ((sm - sp) * 16 + denom2) / (denom2 * 2);
+          } else {
+            dv = bd * 16;
+          }
+          wta.disp1[(size_t)py * wta.w + px + wta.minX1] = (int16_t)(dv + wta.minD * 16);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ K_lr, K_median
+__global__ void sgbm_fill_kernel(int16_t* __restrict__ disp1, unsigned* __restrict__ key2, size_t n, int16_t inv) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  disp1[i] = inv;
+  key2[i] = SG_KEY_INIT;
+}
+
+__device__ __forceinline__ int sg_disp2(const unsigned* __restrict__ krow, int xr, int minX1, int inv) {
+  const unsigned k = krow[xr];
+  if (k == SG_KEY_INIT) return inv;
+  const int xw = 0xFFFF - (int)(k & 0xFFFFu);
+  return xw + minX1 - xr;     // = d + minD of the winning left pixel
+}
+
+__global__ void sgbm_lrcheck_kernel(const int16_t* __restrict__ disp1, const unsigned* __restrict__ key2, int w, int h,
+                                    int minD, int minX1, int maxX1, int d12, int16_t* __restrict__ out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= w) return;
+  const int inv = (minD - 1) * 16;
+  int d1 = disp1[(size_t)y * w + x];
+  if (x >= minX1 && x < maxX1 && d1 != inv) {
+    const unsigned* krow = key2 + (size_t)y * w;
+    const int dlo = d1 >> 4, dhi = (d1 + 15) >> 4;
+    const int xl = x - dlo, xh = x - dhi;
+    bool f1 = false, f2 = false;
+    if (0 <= xl && xl < w) {
+      const int v = sg_disp2(krow, xl, minX1, inv);
+      f1 = v >= minD && abs(v - dlo) > d12;
+    }
+    if (0 <= xh && xh < w) {
+      const int v = sg_disp2(krow, xh, minX1, inv);
+      f2 = v >= minD && abs(v - dhi) > d12;
+    }
+    if (f1 && f2) d1 = inv;
+  }
+  out[(size_t)y * w + x] = (int16_t)d1;
+}
+
+__device__ __forceinline__ void sg_sort2(int& a, int& b) {
+  const int t = min(a, b);
+  b = max(a, b);
+  a = t;
+}
+
+__global__ void sgbm_median3_kernel(const int16_t* __restrict__ in, int w, int h, int16_t* __restrict__ out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= w) return;
+  const int xm = max(x - 1, 0), xp = min(x + 1, w - 1);
+  const int16_t* r0 = in + (size_t)max(y - 1, 0) * w;
+  const int16_t* r1 = in + (size_t)y * w;
+  const int16_t* r2 = in + (size_t)min(y + 1, h - 1) * w;
+  int p0 = r0[xm], p1 = r0[x], p2 = r0[xp], p3 = r1[xm], p4 = r1[x], p5 = r1[xp], p6 = r2[xm], p7 = r2[x], p8 = r2[xp];
+  // median-of-9 exchange network
+  sg_sort2(p1, p2); sg_sort2(p4, p5); sg_sort2(p7, p8); sg_sort2(p0, p1);
+  sg_sort2(p3, p4); sg_sort2(p6, p7); sg_sort2(p1, p2); sg_sort2(p4, p5);
+  sg_sort2(p7, p8); sg_sort2(p0, p3); sg_sort2(p5, p8); sg_sort2(p4, p7);
+  sg_sort2(p3, p6); sg_sort2(p1, p4); sg_sort2(p2, p5); sg_sort2(p4, p7);
+  sg_sort2(p4, p2); sg_sort2(p6, p4); sg_sort2(p4, p2);
+  out[(size_t)y * w + x] = (int16_t)p4;
+}
+
+// ------------------------------------------------------------------------------------ K_speckle (cv::filterSpeckles)
+__device__ __forceinline__ int sg_find(volatile int* lab, int i) {
+  int p = lab[i];
+  while (p != i) {
+    i = p;
+    p = lab[i];
+  }
+  return i;
+}
+
+__device__ __forceinline__ void sg_union(int* lab, int a, int b) {
+  for (;;) {
+    a = sg_find(lab, a);
+    b = sg_find(lab, b);
+    if (a == b) return;
+    if (a > b) {
+      const int t = a;
+      a = b;
+      b = t;
+    }
+    const int old = atomicMin(lab + b, a);     // hook the larger root under the smaller one
+    if (old == b) return;
+    b = old;
+  }
+}
+
+__global__ void sgbm_cc_init_kernel(const int16_t* __restrict__ d, int n, int new_val, int* __restrict__ lab,
+                                    int* __restrict__ cnt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  lab[i] = d[i] != new_val ? i : -1;
+  cnt[i] = 0;
+}
+
+__global__ void sgbm_cc_merge_kernel(const int16_t* __restrict__ d, int w, int h, int new_val, int max_diff,
+                                     int* __restrict__ lab) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= w) return;
+  const int i = y * w + x;
+  const int v = d[i];
+  if (v == new_val) return;
+  if (x + 1 < w) {
+    const int u = d[i + 1];
+    if (u != new_val && abs(v - u) <= max_diff) sg_union(lab, i, i + 1);
+  }
+  if (y + 1 < h) {
+    const int u = d[i + w];
+    if (u != new_val && abs(v - u) <= max_diff) sg_union(lab, i, i + w);
+  }
+}
+
+__global__ void sgbm_cc_count_kernel(int n, int* __restrict__ lab, int* __restrict__ cnt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (lab[i] < 0) return;
+  const int r = sg_find(lab, i);
+  lab[i] = r;                         // a pixel's label always points to an index <= its own: flattening is race-free
+  atomicAdd(cnt + r, 1);
+}
+
+__global__ void sgbm_cc_apply_kernel(int n, const int* __restrict__ lab, const int* __restrict__ cnt, int max_size,
+                                     int new_val, int16_t* __restrict__ d) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int l = lab[i];
+  if (l < 0) return;
+  // lab[i] was flattened to a root by the count pass, or points to a node that was: at most one more hop
+  int r = l;
+  while (lab[r] != r) r = lab[r];
+  if (cnt[r] <= max_size) d[i] = (int16_t)new_val;
+}
+
+// ------------------------------------------------------------------------------------ K_reproj
+__global__ void sgbm_reproject_kernel(const int16_t* __restrict__ disp, int w, int h, const double* __restrict__ Q,
+                                      float3* __restrict__ xyz, uint8_t* __restrict__ keep) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= w) return;
+  const size_t i = (size_t)y * w + x;
+  const double d = (double)(float)disp[i];
+  const double fx = (double)x, fy = (double)y;
+  double hm[4];
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    // Matx product: s = 0; s += a(i,k) * b(k) for k = 0..3, no contraction
+    double s = __dmul_rn(Q[4 * r], fx);
+    s = __dadd_rn(0.0, s);
+    s = __dadd_rn(s, __dmul_rn(Q[4 * r + 1], fy));
+    s = __dadd_rn(s, __dmul_rn(Q[4 * r + 2], d));
+    s = __dadd_rn(s, __dmul_rn(Q[4 * r + 3], 1.0));
+    hm[r] = s;
+  }
+  // the Vec3f destination is assigned first (rounding to float), then divided by the double W
+  const float X = (float)__ddiv_rn((double)(float)hm[0], hm[3]);
+  const float Y = (float)__ddiv_rn((double)(float)hm[1], hm[3]);
+  const float Z = (float)__ddiv_rn((double)(float)hm[2], hm[3]);
+  // StereoCV.cpp:240: skipped when z > 5 or z <= 0.01 (a NaN z is therefore kept, as in the reference)
+  const bool skip = (Z > 5.0f) || (Z <= 0.01f);
+  keep[i] = skip ? 0 : 1;
+  xyz[i] = make_float3(X, __fmul_rn(Y, -1.0f), Z);
+}
+
+}  // namespace vo
+
+// ====================================================================================== C ABI
+using namespace vo;
+
+#define SG_CHECK_CTX(c)                   \
+  if (!(c)) return VO_ERR_INVALID_ARG;    \
+  VO_CUDA(cudaSetDevice((c)->device))
+
+void vo_sgbm_default_params(vo_sgbm_params* p) {
+  if (!p) return;
+  // StereoSGBM::create(1, 96, 7, 8*3, 32*3, 0, 60, 0, 3000, 5), reference src/StereoCV.cpp:39-50
+  p->min_disparity = 1;
+  p->num_disparities = 96;
+  p->block_size = 7;
+  p->p1 = 24;
+  p->p2 = 96;
+  p->disp12_max_diff = 0;
+  p->pre_filter_cap = 60;
+  p->uniqueness_ratio = 0;
+  p->speckle_window_size = 3000;
+  p->speckle_range = 5;
+}
+
+struct SgResolved {
+  int minD, maxD, D, R, P1, P2, uniq, d12, ftzero, minX1, maxX1, W1, inv;
+};
+
+static int sgbm_resolve(const vo_sgbm_params* p, int w, int h, SgResolved& r) {
+  if (!p || w < 3 || h < 1 || w > 16384 || h > 16384) return VO_ERR_INVALID_ARG;
+  r.minD = p->min_disparity;
+  r.D = p->num_disparities;
+  if (r.D <= 0 || r.D % 16 != 0 || r.D > SG_MAX_D) {
+    set_error("numDisparities %d: must be a positive multiple of 16, at most %d", r.D, SG_MAX_D);
+    return VO_ERR_INVALID_ARG;
+  }
+  r.maxD = r.minD + r.D;
+  const int block = p->block_size > 0 ? p->block_size : 5;
+  if (block % 2 == 0 || block > 2 * SG_MAX_R + 1) {
+    set_error("blockSize %d: must be odd and at most %d", block, 2 * SG_MAX_R + 1);
+    return VO_ERR_INVALID_ARG;
+  }
+  r.R = block / 2;
+  r.P1 = p->p1 > 0 ? p->p1 : 2;
+  r.P2 = std::max(p->p2 > 0 ? p->p2 : 5, r.P1 + 1);
+  r.uniq = p->uniqueness_ratio >= 0 ? p->uniqueness_ratio : 10;
+  r.d12 = p->disp12_max_diff > 0 ? p->disp12_max_diff : 1;
+  if (p->pre_filter_cap < 0 || p->pre_filter_cap > 126) return VO_ERR_INVALID_ARG;
+  r.ftzero = std::max(p->pre_filter_cap, 15) | 1;
+  // the int16 cost range OpenCV relies on: block^2 * (largest pixel cost) + P2 must fit
+  if ((long long)block * block * (2 * r.ftzero + 63) + r.P2 > 32767 || r.uniq > 100) {
+    set_error("blockSize / preFilterCap / P2 leave the int16 cost range");
+    return VO_ERR_INVALID_ARG;
+  }
+  if (!(w - r.maxD > r.R)) {
+    // cv2 throws here: "input images are too small for your window size and max disparity" (stereosgbm.cpp:511)
+    set_error("width - (minDisparity + numDisparities) = %d must exceed blockSize / 2 = %d", w - r.maxD, r.R);
+    return VO_ERR_INVALID_ARG;
+  }
+  r.minX1 = std::max(r.maxD, 0);
+  r.maxX1 = w + std::min(r.minD, 0);
+  r.W1 = r.maxX1 - r.minX1;
+  r.inv = (r.minD - 1) * 16;
+  return VO_OK;
+}
+
+static int sgbm_ensure(vo_ctx* c, int w, int h, const SgResolved& r, bool need_bgr) {
+  Sgbm* s = reinterpret_cast<Sgbm*>(c->sgbm);
+  if (!s) {
+    s = new Sgbm();
+    c->sgbm = s;
+    for (auto& e : s->ev) VO_CUDA(cudaEventCreate(&e));
+    VO_CUDA(cudaMalloc(&s->d_n, 4 * sizeof(int)));
+    VO_CUDA(cudaMalloc(&s->dQ, 16 * sizeof(double)));
+  }
+  const size_t npx = (size_t)w * h;
+  const size_t cost = (size_t)std::max(r.W1, 0) * h * r.D;
+  if (npx > (size_t)s->w * s->h || cost > s->cost_elems) {
+    VO_CUDA(cudaStreamSynchronize(c->stream));
+    sgbm_release_buffers(s);
+    s->have_disp = false;
+    s->w = w;
+    s->h = h;
+    s->cost_elems = cost;
+    for (int k = 0; k < 2; k++) VO_CUDA(cudaMalloc(&s->img[k], npx));
+    VO_CUDA(cudaMalloc(&s->pl, 4 * npx * sizeof(uchar4)));
+    VO_CUDA(cudaMalloc(&s->hsum, cost * 2 + 64));
+    VO_CUDA(cudaMalloc(&s->C, cost * 2 + 64));
+    VO_CUDA(cudaMalloc(&s->S, cost * 2 + 64));
+    VO_CUDA(cudaMalloc(&s->key2, npx * sizeof(unsigned)));
+    for (int k = 0; k < 3; k++) VO_CUDA(cudaMalloc(&s->disp[k], npx * sizeof(int16_t)));
+    VO_CUDA(cudaMalloc(&s->label, npx * sizeof(int)));
+    VO_CUDA(cudaMalloc(&s->count, npx * sizeof(int)));
+    VO_CUDA(cudaMalloc(&s->xyz, npx * sizeof(float3)));
+    VO_CUDA(cudaMalloc(&s->keep, npx));
+    VO_CUDA(cudaMalloc(&s->xyz_out, npx * sizeof(float3)));
+    VO_CUDA(cudaMalloc(&s->idx_out, npx * sizeof(int)));
+    size_t t1 = 0, t2 = 0;
+    VO_CUDA(cub::DeviceSelect::Flagged(nullptr, t1, (const float3*)nullptr, (const uint8_t*)nullptr, (float3*)nullptr,
+                                       (int*)nullptr, (int)npx, c->stream));
+    VO_CUDA(cub::DeviceSelect::Flagged(nullptr, t2, cub::CountingInputIterator<int>(0), (const uint8_t*)nullptr,
+                                       (int*)nullptr, (int*)nullptr, (int)npx, c->stream));
+    s->cub_bytes = std::max(t1, t2);
+    VO_CUDA(cudaMalloc(&s->cub_tmp, s->cub_bytes + 256));
+  }
+  if (need_bgr && !s->bgr[0]) {
+    for (int k = 0; k < 2; k++) VO_CUDA(cudaMalloc(&s->bgr[k], 3 * (size_t)s->w * s->h));
+  }
+  return VO_OK;
+}
+
+template <int DPL>
+static int sgbm_paths(vo_ctx* c, Sgbm* s, const SgResolved& r, int h, const SgWta& wta) {
+  const int W1 = r.W1, D = r.D;
+  const int wpb = 4;   // warps per CTA
+  int16_t* S2 = reinterpret_cast<int16_t*>(s->hsum);   // hsum is dead once C exists
+  {
+    LaunchScope ls(c, VO_K_MISC);   // both horizontal directions: S = L0, S2 = L4
+    sgbm_path_kernel<DPL, 0><<<dim3(div_up(h, wpb), 2), wpb * 32, 0, c->stream>>>(s->C, s->S, S2, nullptr, W1, h, D, r.P1,
+                                                                                r.P2, 0, 4, h, wta);
+  }
+  VO_CUDA(cudaEventRecord(s->ev[4], c->stream));
+  const int nd = W1 + h - 1;
+  {
+    LaunchScope ls(c, VO_K_MISC);
+    sgbm_path_kernel<DPL, 2><<<dim3(div_up(nd, wpb), 1), wpb * 32, 0, c->stream>>>(s->C, s->S, nullptr, S2, W1, h, D, r.P1,
+                                                                                 r.P2, 1, 1, nd, wta);
+  }
+  {
+    LaunchScope ls(c, VO_K_MISC);
+    sgbm_path_kernel<DPL, 1><<<dim3(div_up(nd, wpb), 1), wpb * 32, 0, c->stream>>>(s->C, s->S, nullptr, nullptr, W1, h, D,
+                                                                                 r.P1, r.P2, 3, 3, nd, wta);
+  }
+  VO_CUDA(cudaEventRecord(s->ev[5], c->stream));
+  {
+    LaunchScope ls(c, VO_K_MISC);
+    sgbm_path_kernel<DPL, 3><<<dim3(div_up(W1, wpb), 1), wpb * 32, 0, c->stream>>>(s->C, s->S, nullptr, nullptr, W1, h, D,
+                                                                                 r.P1, r.P2, 2, 2, W1, wta);
+  }
+  VO_CUDA(cudaGetLastError());
+  return VO_OK;
+}
+
+// device pipeline on s->img[0..1] (tight gray) -> s->disp[2]
+static int sgbm_run(vo_ctx* c, int w, int h, const vo_sgbm_params* p, const SgResolved& r) {
+  Sgbm* s = reinterpret_cast<Sgbm*>(c->sgbm);
+  const size_t npx = (size_t)w * h;
+  const int n = (int)npx;
+  VO_CUDA(cudaEventRecord(s->ev[1], c->stream));
+  {
+    LaunchScope ls(c, VO_K_MISC);
+    sgbm_fill_kernel<<<div_up(n, 256), 256, 0, c->stream>>>(s->disp[0], s->key2, npx, (int16_t)r.inv);
+  }
+  if (r.W1 > 0) {
+    {
+      LaunchScope ls(c, VO_K_MISC);
+      sgbm_prefilter_kernel<<<dim3(div_up(w, 128), h, 2), 128, 0, c->stream>>>(s->img[0], s->img[1], w, h, r.ftzero, s->pl);
+    }
+    VO_CUDA(cudaEventRecord(s->ev[2], c->stream));
+    {
+      LaunchScope ls(c, VO_K_MISC);
+      const size_t smem = (size_t)(SG_TX + 2 * r.R) * r.D * sizeof(uint16_t);
+      sgbm_hsum_kernel<<<dim3(div_up(r.W1, SG_TX), h), 256, smem, c->stream>>>(s->pl, w, h, r.W1, r.D, r.minD, r.minX1, r.R,
+                                                                             s->hsum);
+    }
+    {
+      LaunchScope ls(c, VO_K_MISC);
+      const size_t row_elems = (size_t)r.W1 * r.D;
+      const int strips = 8, rps = div_up(h, strips);
+      sgbm_vsum_kernel<<<dim3((unsigned)((row_elems + 255) / 256), strips), 256, 0, c->stream>>>(s->hsum, h, row_elems, r.R,
+                                                                                               rps, s->C);
+    }
+    VO_CUDA(cudaEventRecord(s->ev[3], c->stream));
+    SgWta wta{s->disp[0], s->key2, w, r.minD, r.minX1, r.uniq};
+    if (r.D <= 128) VO_TRY(sgbm_paths<4>(c, s, r, h, wta));
+    else VO_TRY(sgbm_paths<8>(c, s, r, h, wta));
+  } else {
+    for (int k = 2; k <= 5; k++) VO_CUDA(cudaEventRecord(s->ev[k], c->stream));
+  }
+  VO_CUDA(cudaEventRecord(s->ev[6], c->stream));
+  {
+    LaunchScope ls(c, VO_K_MISC);
+    sgbm_lrcheck_kernel<<<dim3(div_up(w, 128), h), 128, 0, c->stream>>>(s->disp[0], s->key2, w, h, r.minD, r.minX1, r.maxX1,
+                                                                       r.d12, s->disp[1]);
+  }
+  {
+    LaunchScope ls(c, VO_K_MISC);
+    sgbm_median3_kernel<<<dim3(div_up(w, 128), h), 128, 0, c->stream>>>(s->disp[1], w, h, s->disp[2]);
+  }
+  VO_CUDA(cudaEventRecord(s->ev[7], c->stream));
+  if (p->speckle_window_size > 0) {
+    const int max_diff = 16 * p->speckle_range;
+    {
+      LaunchScope ls(c, VO_K_MISC);
+      sgbm_cc_init_kernel<<<div_up(n, 256), 256, 0, c->stream>>>(s->disp[2], n, r.inv, s->label, s->count);
+    }
+    {
+      LaunchScope ls(c, VO_K_MISC);
+      sgbm_cc_merge_kernel<<<dim3(div_up(w, 128), h), 128, 0, c->stream>>>(s->disp[2], w, h, r.inv, max_diff, s->label);
+    }
+    {
+      LaunchScope ls(c, VO_K_MISC);
+      sgbm_cc_count_kernel<<<div_up(n, 256), 256, 0, c->stream>>>(n, s->label, s->count);
+    }
+    {
+      LaunchScope ls(c, VO_K_MISC);
+      sgbm_cc_apply_kernel<<<div_up(n, 256), 256, 0, c->stream>>>(n, s->label, s->count, p->speckle_window_size, r.inv,
+                                                                 s->disp[2]);
+    }
+  }
+  VO_CUDA(cudaEventRecord(s->ev[8], c->stream));
+  VO_CUDA(cudaGetLastError());
+  s->have_disp = true;
+  s->last_w = w;
+  s->last_h = h;
+  return VO_OK;
+}
+
+static int sgbm_finish(vo_ctx* c, int w, int h, int16_t* disp, int disp_stride) {
+  Sgbm* s = reinterpret_cast<Sgbm*>(c->sgbm);
+  if (disp)
+    VO_CUDA(cudaMemcpy2DAsync(disp, disp_stride, s->disp[2], (size_t)w * 2, (size_t)w * 2, h, cudaMemcpyDeviceToHost,
+                              c->stream));
+  VO_CUDA(cudaEventRecord(s->ev[9], c->stream));
+  VO_CUDA(cudaStreamSynchronize(c->stream));
+  for (int k = 0; k < 9; k++) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, s->ev[k], s->ev[k + 1]) != cudaSuccess) ms = -1.f;
+    s->ms[k] = ms;
+  }
+  return VO_OK;
+}
+
+int vo_sgbm_compute(vo_ctx* c, const uint8_t* left, const uint8_t* right, int stride, int width, int height,
+                    const vo_sgbm_params* p, int16_t* disp, int disp_stride) {
+  SG_CHECK_CTX(c);
+  if (!left || !right || !p || stride < width || (disp && disp_stride < 2 * width)) return VO_ERR_INVALID_ARG;
+  SgResolved r;
+  VO_TRY(sgbm_resolve(p, width, height, r));
+  VO_TRY(sgbm_ensure(c, width, height, r, false));
+  Sgbm* s = reinterpret_cast<Sgbm*>(c->sgbm);
+  VO_CUDA(cudaEventRecord(s->ev[0], c->stream));
+  VO_CUDA(cudaMemcpy2DAsync(s->img[0], width, left, stride, width, height, cudaMemcpyHostToDevice, c->stream));
+  VO_CUDA(cudaMemcpy2DAsync(s->img[1], width, right, stride, width, height, cudaMemcpyHostToDevice, c->stream));
+  VO_TRY(sgbm_run(c, width, height, p, r));
+  return sgbm_finish(c, width, height, disp, disp_stride);
+}
+
+int vo_stereo_match(vo_ctx* c, const uint8_t* left_bgr, const uint8_t* right_bgr, int stride, int width, int height,
+                    const vo_sgbm_params* p, int16_t* disp, int disp_stride) {
+  SG_CHECK_CTX(c);
+  if (!left_bgr || !right_bgr || !p || stride < 3 * width || (disp && disp_stride < 2 * width)) return VO_ERR_INVALID_ARG;
+  SgResolved r;
+  VO_TRY(sgbm_resolve(p, width, height, r));
+  VO_TRY(sgbm_ensure(c, width, height, r, true));
+  Sgbm* s = reinterpret_cast<Sgbm*>(c->sgbm);
+  VO_CUDA(cudaEventRecord(s->ev[0], c->stream));
+  const uint8_t* src[2] = {left_bgr, right_bgr};
+  for (int k = 0; k < 2; k++) {
+    VO_CUDA(cudaMemcpy2DAsync(s->bgr[k], 3 * (size_t)width, src[k], stride, 3 * (size_t)width, height,
+                              cudaMemcpyHostToDevice, c->stream));
+    // cvtColor(BGR2GRAY), src/StereoCV.cpp:35-36
+    VO_TRY(bgr2gray_launch_wh(c, s->bgr[k], 3 * width, s->img[k], width, width, height));
+  }
+  VO_TRY(sgbm_run(c, width, height, p, r));
+  return sgbm_finish(c, width, height, disp, disp_stride);
+}
+
+int vo_sgbm_timing(vo_ctx* c, float ms[9]) {
+  if (!c || !ms || !c->sgbm) return VO_ERR_INVALID_ARG;
+  Sgbm* s = reinterpret_cast<Sgbm*>(c->sgbm);
+  for (int k = 0; k < 9; k++) ms[k] = s->ms[k];
+  return VO_OK;
+}
+
+int vo_debug_sgbm_stage(vo_ctx* c, int stage, void* out, uint64_t bytes) {
+  SG_CHECK_CTX(c);
+  if (!out || !c->sgbm) return VO_ERR_INVALID_ARG;
+  Sgbm* s = reinterpret_cast<Sgbm*>(c->sgbm);
+  if (!s->have_disp) return VO_ERR_INVALID_ARG;
+  const void* src = nullptr;
+  size_t avail = 0;
+  const size_t npx = (size_t)s->last_w * s->last_h;
+  switch (stage) {
+    case 0: src = s->C; avail = s->cost_elems * 2; break;
+    case 1: src = s->disp[0]; avail = npx * 2; break;     // winner-take-all + sub-pixel, before the left-right check
+    case 2: src = s->disp[1]; avail = npx * 2; break;     // after the left-right check
+    case 3: src = s->pl; avail = 4 * npx * 4; break;      // prefilter planes
+    default: return VO_ERR_INVALID_ARG;
+  }
+  if (bytes > avail) return VO_ERR_CAPACITY;
+  VO_CUDA(cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+  VO_CUDA(cudaStreamSynchronize(c->stream));
+  return VO_OK;
+}
+
+int vo_reproject_disparity(vo_ctx* c, const int16_t* disp, int disp_stride, int width, int height, const double Q[16],
+                           float* xyz, int32_t* pix_idx, int cap, int* n_out) {
+  SG_CHECK_CTX(c);
+  if (!Q || !n_out || cap < 0 || width < 1 || height < 1 || (cap > 0 && !xyz)) return VO_ERR_INVALID_ARG;
+  *n_out = 0;
+  Sgbm* s = reinterpret_cast<Sgbm*>(c->sgbm);
+  if (disp) {
+    if (disp_stride < 2 * width) return VO_ERR_INVALID_ARG;
+    SgResolved r{};
+    r.W1 = 0;
+    r.D = 16;
+    VO_TRY(sgbm_ensure(c, width, height, r, false));
+    s = reinterpret_cast<Sgbm*>(c->sgbm);
+    VO_CUDA(cudaMemcpy2DAsync(s->disp[2], (size_t)width * 2, disp, disp_stride, (size_t)width * 2, height,
+                              cudaMemcpyHostToDevice, c->stream));
+    s->have_disp = true;
+    s->last_w = width;
+    s->last_h = height;
+  } else if (!s || !s->have_disp || s->last_w != width || s->last_h != height) {
+    set_error("vo_reproject_disparity: no device-resident disparity of this size (run vo_sgbm_compute first)");
+    return VO_ERR_INVALID_ARG;
+  }
+  const int n = width * height;
+  double* dQ = s->dQ;
+  VO_CUDA(cudaMemcpyAsync(dQ, Q, 16 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  {
+    LaunchScope ls(c, VO_K_MISC);
+    sgbm_reproject_kernel<<<dim3(div_up(width, 128), height), 128, 0, c->stream>>>(s->disp[2], width, height, dQ, s->xyz,
+                                                                                  s->keep);
+  }
+  size_t tb = s->cub_bytes;
+  VO_CUDA(cub::DeviceSelect::Flagged(s->cub_tmp, tb, s->xyz, s->keep, s->xyz_out, s->d_n, n, c->stream));
+  tb = s->cub_bytes;
+  VO_CUDA(cub::DeviceSelect::Flagged(s->cub_tmp, tb, cub::CountingInputIterator<int>(0), s->keep, s->idx_out, s->d_n + 1, n,
+                                     c->stream));
+  c->launch_count += 2;
+  int hn[2] = {0, 0};
+  VO_CUDA(cudaMemcpyAsync(hn, s->d_n, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  VO_CUDA(cudaStreamSynchronize(c->stream));
+  const int m = hn[0];
+  *n_out = m;
+  const int k = std::min(m, cap);
+  if (k > 0) {
+    VO_CUDA(cudaMemcpyAsync(xyz, s->xyz_out, (size_t)k * sizeof(float3), cudaMemcpyDeviceToHost, c->stream));
+    if (pix_idx) VO_CUDA(cudaMemcpyAsync(pix_idx, s->idx_out, (size_t)k * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    VO_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  return m > cap ? VO_ERR_CAPACITY : VO_OK;
+}

@@ -123,6 +123,64 @@ class VisualFrontEnd:
             return out + (idx, md[:n].copy())
         return out
 
+    # ---- dense stereo (reference class StereoProcess, include/stereoCV.h:63-64)
+    def sgbm_params(self, **kw):
+        """vo_sgbm_params with the reference's StereoSGBM::create arguments (src/StereoCV.cpp:39-50)."""
+        p = _lib.VoSgbmParams()
+        self.lib.vo_sgbm_default_params(C.byref(p))
+        for k, v in kw.items():
+            if not hasattr(p, k):
+                raise AttributeError(k)
+            setattr(p, k, int(v))
+        return p
+
+    def stereoMatch(self, imL, imR, download=True, **kw):
+        """StereoProcess::stereoMatch (src/StereoCV.cpp:21-62): BGR frames are converted to gray on the device,
+        gray frames are taken as they are; returns the int16 16x disparity of StereoSGBM::compute.  Keyword
+        arguments override the reference's SGBM parameters (names of vo_sgbm_params)."""
+        a, b = _u8img(imL), _u8img(imR)
+        if a.shape != b.shape:
+            raise ValueError("left / right shapes differ")
+        if a.strides[0] != b.strides[0]:
+            a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+        h, w = a.shape[:2]
+        p = self.sgbm_params(**kw)
+        out = np.zeros((h, w), np.int16) if download else None
+        fn = self.lib.vo_stereo_match if a.ndim == 3 else self.lib.vo_sgbm_compute
+        check(fn(self.h, _p(a), _p(b), a.strides[0], w, h, C.byref(p), _p(out), 2 * w))
+        return out
+
+    def reprojectDisparity(self, disp, Q, shape=None, cap=None):
+        """StereoProcess::reprojectDisparity (src/StereoCV.cpp:221-250): (points (M,3) float32, flat pixel indices
+        (M,)) in raster order.  disp=None reprojects the device-resident result of the last stereoMatch (pass its
+        shape)."""
+        Q = np.ascontiguousarray(Q, np.float64).reshape(4, 4)
+        if disp is not None:
+            disp = np.ascontiguousarray(disp, np.int16)
+            h, w = disp.shape
+        else:
+            h, w = shape
+        cap = h * w if cap is None else int(cap)
+        xyz = np.zeros((max(cap, 1), 3), np.float32)
+        idx = np.zeros(max(cap, 1), np.int32)
+        n = C.c_int()
+        check(self.lib.vo_reproject_disparity(self.h, _p(disp), 2 * w, w, h, _p(Q), _p(xyz), _p(idx), cap, C.byref(n)),
+              ok=(_lib.VO_OK, _lib.VO_ERR_CAPACITY))
+        m = min(n.value, cap)
+        return xyz[:m].copy(), idx[:m].copy()
+
+    def sgbm_timing(self):
+        ms = (C.c_float * 9)()
+        check(self.lib.vo_sgbm_timing(self.h, ms))
+        names = ("upload", "prefilter", "cost_volume", "paths_horizontal", "paths_diagonal", "path_vertical_wta",
+                 "lrcheck_median", "speckle", "download")
+        return dict(zip(names, [float(v) for v in ms]))
+
+    def sgbm_stage(self, stage, shape, dtype):
+        out = np.zeros(shape, dtype)
+        check(self.lib.vo_debug_sgbm_stage(self.h, int(stage), _p(out), C.c_uint64(out.nbytes)))
+        return out
+
     def cvtColorBGR2GRAY(self, bgr):
         """cv::cvtColor(bgr, CV_BGR2GRAY) on the device (bit-exact with OpenCV's 15-bit fixed point)."""
         a = np.ascontiguousarray(bgr)

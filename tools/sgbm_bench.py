@@ -1,0 +1,73 @@
+"""Dense-stereo (SGBM) timing on the GPU box: vo_sgbm_compute on the KITTI-shaped golden pair with the reference's
+parameters (src/StereoCV.cpp:39-50) against cv2.StereoSGBM on the host cores, per-stage device times, and a
+stage-by-stage comparison with oracle/sgbm.py when the end result differs.
+
+    python tools/sgbm_bench.py [reps]
+"""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import cv2
+    from oracle import sgbm
+    from ros_stereo_slam_b200 import VisualFrontEnd
+    reps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+    g = np.load(os.path.join(ROOT, "tests", "golden", "vo_golden_v1.npz"))
+    g3 = np.load(os.path.join(ROOT, "tests", "golden", "vo_golden_v3.npz"))
+    L, R = g["L0"], g["R0"]
+    fe = VisualFrontEnd()
+    out = fe.stereoMatch(L, R)
+    ref = sgbm.sgbm_call_through(L, R)
+    nd = int((out != ref).sum())
+    print("full frame: %d of %d pixels differ from cv2 %s" % (nd, ref.size, cv2.__version__))
+    if nd:
+        crop = (slice(100, 220), slice(300, 700))
+        a, b = L[crop].copy(), R[crop].copy()
+        st = sgbm.sgbm_stages(a, b, num_disp=32)
+        o = fe.stereoMatch(a, b, num_disparities=32)
+        h, w = a.shape
+        f, raw = sgbm.prefilter(a, 61)
+        pl = fe.sgbm_stage(3, (4, h, w, 4), np.uint8)
+        print("  crop: prefilter planes differ:", int((pl[0, :, :, 0] != f).sum()), int((pl[1, :, :, 0] != raw).sum()))
+        C = fe.sgbm_stage(0, st["C"].shape, np.int16)
+        print("  crop: C differs:", int((C != st["C"]).sum()), "of", C.size)
+        print("  crop: after LR check differs:", int((fe.sgbm_stage(2, (h, w), np.int16) != st["raw"]).sum()))
+        print("  crop: final differs:", int((o != st["disp"]).sum()))
+    ts = []
+    for _ in range(reps):
+        t = time.perf_counter()
+        fe.stereoMatch(L, R)
+        ts.append(time.perf_counter() - t)
+    stage = fe.sgbm_timing()
+    print("vo_sgbm_compute (host images in, host disparity out): median %.3f ms, min %.3f ms over %d calls"
+          % (1e3 * np.median(ts), 1e3 * min(ts), reps))
+    print("device stages of the last call (ms):", {k: round(v, 4) for k, v in stage.items()},
+          "sum %.3f" % sum(stage.values()))
+    Q = g3["Q_neg"]
+    t = time.perf_counter()
+    pts, idx = fe.reprojectDisparity(None, Q, shape=L.shape)
+    print("vo_reproject_disparity (device-resident disparity): %.3f ms, %d points" % (1e3 * (time.perf_counter() - t), len(idx)))
+    cv2.setNumThreads(len(os.sched_getaffinity(0)))
+    m = cv2.StereoSGBM_create(1, 96, 7, 24, 96, 0, 60, 0, 3000, 5)
+    tc = []
+    for _ in range(5):
+        t = time.perf_counter()
+        m.compute(L, R)
+        tc.append(time.perf_counter() - t)
+    print("cv2.StereoSGBM.compute on %d host cores: median %.1f ms" % (len(os.sched_getaffinity(0)), 1e3 * np.median(tc)))
+    t = time.perf_counter()
+    with np.errstate(all="ignore"):
+        sgbm.reproject_call_through(ref, Q)
+    print("cv2.reprojectImageTo3D + gate on the host: %.1f ms" % (1e3 * (time.perf_counter() - t)))
+    fe.close()
+
+
+if __name__ == "__main__":
+    main()
