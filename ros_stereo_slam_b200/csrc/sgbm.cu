@@ -438,50 +438,82 @@ __device__ __forceinline__ void sg_union(int* lab, int a, int b) {
   }
 }
 
-__global__ void sgbm_cc_init_kernel(const int16_t* __restrict__ d, int n, int new_val, int* __restrict__ lab,
-                                    int* __restrict__ cnt) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  lab[i] = d[i] != new_val ? i : -1;
-  cnt[i] = 0;
+// Row pass: a CTA per image row labels every valid pixel with the flat index of the first pixel of its horizontal
+// run (inclusive max-scan of the run starts); invalid pixels get -1.  Only run starts ever become tree nodes.
+__global__ void __launch_bounds__(256)
+sgbm_cc_rows_kernel(const int16_t* __restrict__ d, int w, int new_val, int max_diff, int* __restrict__ lab,
+                    int* __restrict__ cnt) {
+  using Scan = cub::BlockScan<int, 256>;
+  __shared__ typename Scan::TempStorage tmp;
+  __shared__ int carry;
+  const int y = blockIdx.x;
+  const int16_t* row = d + (size_t)y * w;
+  if (threadIdx.x == 0) carry = -1;
+  __syncthreads();
+  for (int x0 = 0; x0 < w; x0 += 256) {
+    const int x = x0 + threadIdx.x;
+    int v = new_val, f = -1;
+    if (x < w) {
+      v = row[x];
+      if (v != new_val) {
+        bool conn = false;
+        if (x > 0) {
+          const int l = row[x - 1];
+          conn = l != new_val && abs(v - l) <= max_diff;
+        }
+        f = conn ? -1 : x;
+      }
+    }
+    int r;
+    Scan(tmp).InclusiveScan(f, r, cub::Max());
+    r = max(r, carry);
+    __syncthreads();
+    if (threadIdx.x == 255) carry = r;
+    if (x < w) {
+      lab[(size_t)y * w + x] = v != new_val ? y * w + r : -1;
+      cnt[(size_t)y * w + x] = 0;
+    }
+    __syncthreads();
+  }
 }
 
+// Column pass: unite the runs of vertically connected pixels; a pair is skipped when the pair to its left already
+// joined the same two runs.
 __global__ void sgbm_cc_merge_kernel(const int16_t* __restrict__ d, int w, int h, int new_val, int max_diff,
                                      int* __restrict__ lab) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y;
-  if (x >= w) return;
+  if (x >= w || y + 1 >= h) return;
   const int i = y * w + x;
-  const int v = d[i];
-  if (v == new_val) return;
-  if (x + 1 < w) {
-    const int u = d[i + 1];
-    if (u != new_val && abs(v - u) <= max_diff) sg_union(lab, i, i + 1);
+  const int v = d[i], u = d[i + w];
+  if (v == new_val || u == new_val || abs(v - u) > max_diff) return;
+  if (x > 0) {
+    const int vl = d[i - 1], ul = d[i + w - 1];
+    if (vl != new_val && ul != new_val && abs(v - vl) <= max_diff && abs(u - ul) <= max_diff && abs(vl - ul) <= max_diff)
+      return;
   }
-  if (y + 1 < h) {
-    const int u = d[i + w];
-    if (u != new_val && abs(v - u) <= max_diff) sg_union(lab, i, i + w);
-  }
+  sg_union(lab, lab[i], lab[i + w]);
 }
 
+// Every valid pixel looks up its root; one atomicAdd per distinct root per warp.
 __global__ void sgbm_cc_count_kernel(int n, int* __restrict__ lab, int* __restrict__ cnt) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  if (lab[i] < 0) return;
-  const int r = sg_find(lab, i);
-  lab[i] = r;                         // a pixel's label always points to an index <= its own: flattening is race-free
-  atomicAdd(cnt + r, 1);
+  const int l = i < n ? lab[i] : -1;
+  int r = -1;
+  if (l >= 0) r = sg_find(lab, l);
+  const unsigned m = __match_any_sync(0xffffffffu, r);
+  if (r >= 0) {
+    if ((threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(cnt + r, __popc(m));
+    lab[i] = r;     // roots are the smallest index of their tree: overwriting a label with its root keeps every chain valid
+  }
 }
 
 __global__ void sgbm_cc_apply_kernel(int n, const int* __restrict__ lab, const int* __restrict__ cnt, int max_size,
                                      int new_val, int16_t* __restrict__ d) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int l = lab[i];
-  if (l < 0) return;
-  // lab[i] was flattened to a root by the count pass, or points to a node that was: at most one more hop
-  int r = l;
-  while (lab[r] != r) r = lab[r];
+  const int r = lab[i];
+  if (r < 0) return;
   if (cnt[r] <= max_size) d[i] = (int16_t)new_val;
 }
 
@@ -709,7 +741,7 @@ static int sgbm_run(vo_ctx* c, int w, int h, const vo_sgbm_params* p, const SgRe
     const int max_diff = 16 * p->speckle_range;
     {
       LaunchScope ls(c, VO_K_MISC);
-      sgbm_cc_init_kernel<<<div_up(n, 256), 256, 0, c->stream>>>(s->disp[2], n, r.inv, s->label, s->count);
+      sgbm_cc_rows_kernel<<<h, 256, 0, c->stream>>>(s->disp[2], w, r.inv, max_diff, s->label, s->count);
     }
     {
       LaunchScope ls(c, VO_K_MISC);

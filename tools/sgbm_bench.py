@@ -18,7 +18,7 @@ def main():
     import cv2
     from oracle import sgbm
     from ros_stereo_slam_b200 import VisualFrontEnd
-    reps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+    reps = int(sys.argv[1]) if len(sys.argv) > 1 else 300
     g = np.load(os.path.join(ROOT, "tests", "golden", "vo_golden_v1.npz"))
     g3 = np.load(os.path.join(ROOT, "tests", "golden", "vo_golden_v3.npz"))
     L, R = g["L0"], g["R0"]
@@ -41,19 +41,25 @@ def main():
         print("  crop: after LR check differs:", int((fe.sgbm_stage(2, (h, w), np.int16) != st["raw"]).sum()))
         print("  crop: final differs:", int((o != st["disp"]).sum()))
     ts = []
-    for _ in range(reps):
+    for k in range(reps):      # back to back: the first calls run at idle clocks
         t = time.perf_counter()
         fe.stereoMatch(L, R)
         ts.append(time.perf_counter() - t)
+        if k in (4, 49):
+            print("  after %d calls: %.3f ms, stages" % (k + 1, 1e3 * ts[-1]), {a: round(b, 3) for a, b in fe.sgbm_timing().items()})
+    ts = ts[reps // 2:]
     stage = fe.sgbm_timing()
     print("vo_sgbm_compute (host images in, host disparity out): median %.3f ms, min %.3f ms over %d calls"
           % (1e3 * np.median(ts), 1e3 * min(ts), reps))
     print("device stages of the last call (ms):", {k: round(v, 4) for k, v in stage.items()},
           "sum %.3f" % sum(stage.values()))
     Q = g3["Q_neg"]
-    t = time.perf_counter()
-    pts, idx = fe.reprojectDisparity(None, Q, shape=L.shape)
-    print("vo_reproject_disparity (device-resident disparity): %.3f ms, %d points" % (1e3 * (time.perf_counter() - t), len(idx)))
+    tr = []
+    for _ in range(20):
+        t = time.perf_counter()
+        pts, idx = fe.reprojectDisparity(None, Q, shape=L.shape)
+        tr.append(time.perf_counter() - t)
+    print("vo_reproject_disparity (device-resident disparity): median %.3f ms, %d points" % (1e3 * np.median(tr), len(idx)))
     cv2.setNumThreads(len(os.sched_getaffinity(0)))
     m = cv2.StereoSGBM_create(1, 96, 7, 24, 96, 0, 60, 0, 3000, 5)
     tc = []
