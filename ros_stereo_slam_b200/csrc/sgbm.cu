@@ -31,7 +31,7 @@
 namespace vo {
 
 constexpr int SG_MAX_COST = 32767;
-constexpr int SG_TX = 32;          // columns per K_hsum CTA
+constexpr int SG_TX = 64;          // columns per K_hsum CTA
 constexpr int SG_MAX_D = 256;
 constexpr int SG_MAX_R = 5;        // block size <= 11
 constexpr int SG_PF = 8;           // prefetch distance of the path kernel (steps)
@@ -47,6 +47,7 @@ struct Sgbm {
   int16_t* C = nullptr;
   int16_t* S = nullptr;
   unsigned* key2 = nullptr;                 // right-view (cost, x) keys
+  uint2* rec = nullptr;                     // winner records
   int16_t* disp[3] = {nullptr, nullptr, nullptr};   // raw WTA, after LR check, after median (+ speckle in place)
   int* label = nullptr;
   int* count = nullptr;
@@ -67,7 +68,7 @@ struct Sgbm {
 void sgbm_free(vo_ctx* c) {
   Sgbm* s = reinterpret_cast<Sgbm*>(c->sgbm);
   if (!s) return;
-  void* dev[] = {s->img[0], s->img[1], s->bgr[0], s->bgr[1], s->pl, s->hsum, s->C, s->S, s->key2, s->disp[0], s->disp[1],
+  void* dev[] = {s->img[0], s->img[1], s->bgr[0], s->bgr[1], s->pl, s->hsum, s->C, s->S, s->key2, s->rec, s->disp[0], s->disp[1],
                  s->disp[2], s->label, s->count, s->xyz, s->keep, s->xyz_out, s->idx_out, s->d_n, s->dQ, s->cub_tmp};
   for (void* p : dev) cudaFree(p);
   for (auto e : s->ev)
@@ -78,7 +79,7 @@ void sgbm_free(vo_ctx* c) {
 
 static void sgbm_release_buffers(Sgbm* s) {
   void** dev[] = {(void**)&s->img[0], (void**)&s->img[1], (void**)&s->bgr[0], (void**)&s->bgr[1], (void**)&s->pl,
-                  (void**)&s->hsum, (void**)&s->C, (void**)&s->S, (void**)&s->key2, (void**)&s->disp[0],
+                  (void**)&s->hsum, (void**)&s->C, (void**)&s->S, (void**)&s->key2, (void**)&s->rec, (void**)&s->disp[0],
                   (void**)&s->disp[1], (void**)&s->disp[2], (void**)&s->label, (void**)&s->count, (void**)&s->xyz,
                   (void**)&s->keep, (void**)&s->xyz_out, (void**)&s->idx_out, (void**)&s->cub_tmp};
   for (void** p : dev) {
@@ -134,26 +135,37 @@ sgbm_hsum_kernel(const uchar4* __restrict__ pl, int w, int h, int W1, int D, int
   const int y = blockIdx.y;
   const int x0 = blockIdx.x * SG_TX;
   const int ncol = SG_TX + 2 * R;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const uchar4* L0 = pl + ((size_t)0 * h + y) * w;   // left filtered
   const uchar4* L1 = pl + ((size_t)1 * h + y) * w;   // left raw
   const uchar4* R0 = pl + ((size_t)2 * h + y) * w;   // right filtered
   const uchar4* R1 = pl + ((size_t)3 * h + y) * w;   // right raw
-  for (int e = threadIdx.x; e < ncol * D; e += blockDim.x) {
-    const int xi = e / D, dd = e - xi * D;
+  // pixel costs of the strip + halo: a warp per column, the lanes over the disparities (the right-image reads of a
+  // warp are 32 consecutive pixels)
+  for (int xi = wid; xi < ncol; xi += 8) {
     const int xw = min(max(x0 - R + xi, 0), W1 - 1);   // columns replicate at the border of the computed range
     const int x1 = xw + minX1;
-    const int x2 = x1 - (dd + minD);
-    const int cst = sg_bt(__ldg(L0 + x1), __ldg(R0 + x2), 0) + sg_bt(__ldg(L1 + x1), __ldg(R1 + x2), 2);
-    sg_pix[e] = (uint16_t)cst;
+    const uchar4 u0 = __ldg(L0 + x1), u1 = __ldg(L1 + x1);
+    const uchar4* r0 = R0 + (x1 - minD);
+    const uchar4* r1 = R1 + (x1 - minD);
+    uint16_t* dst = sg_pix + xi * D;
+    for (int dd = lane; dd < D; dd += 32) dst[dd] = (uint16_t)(sg_bt(u0, __ldg(r0 - dd), 0) + sg_bt(u1, __ldg(r1 - dd), 2));
   }
   __syncthreads();
+  // box width: a warp owns SG_TX / 8 consecutive columns and slides the sum along them
+  constexpr int CPW = SG_TX / 8;
   const int nb = 2 * R + 1;
-  for (int e = threadIdx.x; e < SG_TX * D; e += blockDim.x) {
-    const int xo = e / D, dd = e - xo * D;
-    if (x0 + xo >= W1) break;
-    int s = 0;
-    for (int k = 0; k < nb; k++) s += sg_pix[(xo + k) * D + dd];
-    hsum[((size_t)y * W1 + x0 + xo) * D + dd] = (uint16_t)s;
+  const int xo = wid * CPW;
+  for (int dd = lane; dd < D; dd += 32) {
+    const uint16_t* px = sg_pix + xo * D + dd;
+    int sum = 0;
+    for (int k = 0; k < nb; k++) sum += px[k * D];
+#pragma unroll
+    for (int cI = 0; cI < CPW; cI++) {
+      const int x = x0 + xo + cI;
+      if (x < W1) hsum[((size_t)y * W1 + x) * D + dd] = (uint16_t)sum;
+      if (cI + 1 < CPW) sum += (int)px[(cI + nb) * D] - (int)px[cI * D];
+    }
   }
 }
 
@@ -176,16 +188,18 @@ sgbm_vsum_kernel(const uint16_t* __restrict__ hsum, int h, size_t row_elems, int
 
 // ------------------------------------------------------------------------------------ K_path
 template <int DPL> struct SgVec;
-template <> struct SgVec<4> { using T = uint2; };
-template <> struct SgVec<8> { using T = uint4; };
+template <> struct SgVec<4> { using T = uint2; static constexpr int STAGES = 16; };
+template <> struct SgVec<8> { using T = uint4; static constexpr int STAGES = 8; };
+constexpr int SG_WPB = 4;          // warps (paths) per CTA of the path kernel
 
+// costs are non-negative int16: zero-extension is enough
 template <int DPL>
 __device__ __forceinline__ void sg_unpack(const typename SgVec<DPL>::T& v, int* o) {
   const unsigned* p = reinterpret_cast<const unsigned*>(&v);
 #pragma unroll
   for (int k = 0; k < DPL / 2; k++) {
-    o[2 * k] = (int)(short)(p[k] & 0xFFFFu);
-    o[2 * k + 1] = (int)(short)(p[k] >> 16);
+    o[2 * k] = (int)(p[k] & 0xFFFFu);
+    o[2 * k + 1] = (int)(p[k] >> 16);
   }
 }
 template <int DPL>
@@ -193,27 +207,43 @@ __device__ __forceinline__ typename SgVec<DPL>::T sg_pack(const int* o) {
   typename SgVec<DPL>::T v;
   unsigned* p = reinterpret_cast<unsigned*>(&v);
 #pragma unroll
-  for (int k = 0; k < DPL / 2; k++) p[k] = ((unsigned)o[2 * k] & 0xFFFFu) | ((unsigned)o[2 * k + 1] << 16);
+  for (int k = 0; k < DPL / 2; k++) p[k] = __byte_perm((unsigned)o[2 * k], (unsigned)o[2 * k + 1], 0x5410);
   return v;
 }
 
+template <int BYTES>
+__device__ __forceinline__ void sg_cp_async(unsigned dst, const void* src) {
+  if (BYTES == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+  else asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void sg_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void sg_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 struct SgWta {
-  int16_t* disp1;       // [h][w], pre-filled with the invalid value
-  unsigned* key2;       // [h][w], pre-filled with SG_KEY_INIT
+  uint2* rec;           // [h][w] winner records (d | minS << 16, S[d-1] | S[d+1] << 16); x = 0xFFFFFFFF: no disparity
+  unsigned* key2;       // [h][w] right-view (cost << 16 | 65535 - x) keys, pre-filled with SG_KEY_INIT
   int w, minD, minX1, uniq;
 };
 
-// MODE 0: S = L (no read).  MODE 1: S = min(32767, S + L).  MODE 2: S = min(32767, S + S2 + L).
+// One warp per path.  MODE 0: S = L (no read).  MODE 1: S = min(32767, S + L).  MODE 2: S = min(32767, S + S2 + L).
 // MODE 3: s = min(32767, S + L) is consumed by the winner-take-all step and not stored.
 // Directions: 0 left-to-right, 4 right-to-left (paths = rows), 1 down-right, 2 down, 3 down-left.
+// C (and S, S2) of the steps ahead travel through a per-warp shared-memory ring filled by cp.async: completion is
+// tracked per commit group, in order, so a step never waits for a copy younger than its own (register prefetch
+// could not do that: the scoreboards a load waits on are shared with the younger loads in flight).
 template <int DPL, int MODE>
-__global__ void __launch_bounds__(128)
-sgbm_path_kernel(const int16_t* __restrict__ C, int16_t* __restrict__ S, int16_t* __restrict__ S_rl,
-                 const int16_t* __restrict__ S2, int W1, int H, int D, int P1, int P2, int dir_a, int dir_b, int npaths,
-                 SgWta wta) {
+__global__ void __launch_bounds__(SG_WPB * 32)
+sgbm_path_kernel(const int16_t* __restrict__ C, int16_t* S, int16_t* S_rl, const int16_t* S2, int W1, int H, int D, int P1,
+                 int P2, int dir_a, int dir_b, int npaths, SgWta wta) {
   using V = typename SgVec<DPL>::T;
-  const int lane = threadIdx.x & 31;
-  const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  constexpr int NST = SgVec<DPL>::STAGES;
+  constexpr int NARR = MODE == 0 ? 1 : (MODE == 2 ? 3 : 2);
+  constexpr int VB = 2 * DPL;                 // bytes per lane and array
+  constexpr int ARR = 32 * VB, STG = NARR * ARR;
+  extern __shared__ __align__(16) unsigned char sg_ring[];   // [warp][stage][array][lane][VB]
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int p = blockIdx.x * SG_WPB + wib;
   if (p >= npaths) return;
   const int dir = blockIdx.y ? dir_b : dir_a;
   int16_t* Sout = (blockIdx.y && S_rl) ? S_rl : S;
@@ -229,130 +259,132 @@ sgbm_path_kernel(const int16_t* __restrict__ C, int16_t* __restrict__ S, int16_t
       if (p < W1) { x = p; y = 0; } else { x = W1 - 1; y = p - W1 + 1; }
       n = min(H - y, x + 1); sx = -1; sy = 1; break;
   }
-  const bool active = DPL * lane < D;
+  const bool active = DPL * lane < D;          // lanes beyond D work on lane 0's data and never store
   const bool last = DPL * (lane + 1) >= D;
   const long long step = ((long long)sy * W1 + sx) * D;       // elements per step along the path
   const size_t base = ((size_t)y * W1 + x) * D + (active ? DPL * lane : 0);
-  const int16_t* Cp = C + base;
-  int16_t* Sp = Sout + base;
-  const int16_t* S2p = MODE == 2 ? S2 + base : nullptr;
+  const int16_t* gC = C + base;                // issue pointers: the step the next cp.async fetches
+  const int16_t* gS = Sout + base;
+  const int16_t* gT = MODE == 2 ? S2 + base : nullptr;
+  int16_t* wS = Sout + base;                   // store pointer: the current step
+  unsigned char* ring = sg_ring + (size_t)wib * NST * STG + lane * VB;
+  const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
 
-  V cring[SG_PF], sring[SG_PF], tring[SG_PF];
 #pragma unroll
-  for (int k = 0; k < SG_PF; k++) {
-    if (k < n && active) {
-      cring[k] = __ldg(reinterpret_cast<const V*>(Cp + k * step));
-      if (MODE >= 1) sring[k] = *reinterpret_cast<const V*>(Sp + k * step);
-      if (MODE == 2) tring[k] = __ldg(reinterpret_cast<const V*>(S2p + k * step));
+  for (int k = 0; k < NST; k++) {
+    if (k < n) {
+      sg_cp_async<VB>(ring_s + k * STG, gC);
+      if (NARR >= 2) sg_cp_async<VB>(ring_s + k * STG + ARR, gS);
+      if (NARR == 3) sg_cp_async<VB>(ring_s + k * STG + 2 * ARR, gT);
+      gC += step;
+      gS += step;
+      if (MODE == 2) gT += step;
     }
+    sg_cp_commit();
   }
   int Lp[DPL];
 #pragma unroll
-  for (int j = 0; j < DPL; j++) Lp[j] = active ? 0 : SG_MAX_COST;
+  for (int j = 0; j < DPL; j++) Lp[j] = 0;
   int minp = 0;
+  const int PAD = SG_MAX_COST;
+  int px = x, py = y;
 
-  for (int i0 = 0; i0 < n; i0 += SG_PF) {
+  for (int i0 = 0; i0 < n; i0 += NST) {
 #pragma unroll
-    for (int k = 0; k < SG_PF; k++) {
+    for (int k = 0; k < NST; k++) {
       const int i = i0 + k;
       if (i >= n) break;
+      sg_cp_wait<NST - 1>();                  // the group of step i (and every older one) has landed
       int cv[DPL], sv[DPL], tv[DPL];
-      if (active) {
-        sg_unpack<DPL>(cring[k], cv);
-        if (MODE >= 1) sg_unpack<DPL>(sring[k], sv);
-        if (MODE == 2) sg_unpack<DPL>(tring[k], tv);
-        if (i + SG_PF < n) {
-          cring[k] = __ldg(reinterpret_cast<const V*>(Cp + (long long)(i + SG_PF) * step));
-          if (MODE >= 1) sring[k] = *reinterpret_cast<const V*>(Sp + (long long)(i + SG_PF) * step);
-          if (MODE == 2) tring[k] = __ldg(reinterpret_cast<const V*>(S2p + (long long)(i + SG_PF) * step));
-        }
+      sg_unpack<DPL>(*reinterpret_cast<const V*>(ring + k * STG), cv);
+      if (NARR >= 2) sg_unpack<DPL>(*reinterpret_cast<const V*>(ring + k * STG + ARR), sv);
+      if (NARR == 3) sg_unpack<DPL>(*reinterpret_cast<const V*>(ring + k * STG + 2 * ARR), tv);
+      if (i + NST < n) {                      // refill the stage that was just read
+        sg_cp_async<VB>(ring_s + k * STG, gC);
+        if (NARR >= 2) sg_cp_async<VB>(ring_s + k * STG + ARR, gS);
+        if (NARR == 3) sg_cp_async<VB>(ring_s + k * STG + 2 * ARR, gT);
+        gC += step;
+        gS += step;
+        if (MODE == 2) gT += step;
       }
+      sg_cp_commit();
       // formula 13 of the SGM paper as OpenCV evaluates it
       int left = __shfl_up_sync(0xffffffffu, Lp[DPL - 1], 1);
       int right = __shfl_down_sync(0xffffffffu, Lp[0], 1);
-      if (lane == 0) left = SG_MAX_COST;
-      if (last) right = SG_MAX_COST;
+      if (lane == 0) left = PAD;
+      if (last) right = PAD;
       const int delta = minp + P2;
       int Ln[DPL];
-      int m = 0x7fffffff;
-      if (active) {
 #pragma unroll
-        for (int j = 0; j < DPL; j++) {
-          const int a = Lp[j];
-          const int b = (j ? Lp[j - 1] : left) + P1;
-          const int c = (j < DPL - 1 ? Lp[j + 1] : right) + P1;
-          Ln[j] = cv[j] + min(min(a, b), min(c, delta)) - minp;
-          m = min(m, Ln[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < DPL; j++) Lp[j] = Ln[j];
+      for (int j = 0; j < DPL; j++) {
+        const int a = Lp[j];
+        const int b = (j ? Lp[j - 1] : left) + P1;
+        const int c = (j < DPL - 1 ? Lp[j + 1] : right) + P1;
+        Ln[j] = cv[j] + min(min(a, b), min(c, delta)) - minp;
       }
+      int m = Ln[0];
+#pragma unroll
+      for (int j = 1; j < DPL; j++) m = min(m, Ln[j]);
+      if (!active) m = 0x7fffffff;
+#pragma unroll
+      for (int j = 0; j < DPL; j++) Lp[j] = Ln[j];
       minp = __reduce_min_sync(0xffffffffu, m);
 
       int tot[DPL];
-      if (active) {
 #pragma unroll
-        for (int j = 0; j < DPL; j++) {
-          int t = Ln[j];
-          if (MODE >= 1) t += sv[j];
-          if (MODE == 2) t += tv[j];
-          tot[j] = min(t, SG_MAX_COST);
-        }
-        if (MODE != 3) *reinterpret_cast<V*>(Sp + (long long)i * step) = sg_pack<DPL>(tot);
+      for (int j = 0; j < DPL; j++) {
+        int t = Ln[j];
+        if (MODE >= 1) t += sv[j];
+        if (MODE == 2) t += tv[j];
+        tot[j] = MODE >= 1 ? min(t, SG_MAX_COST) : t;
       }
-      if (MODE == 3) {
-        // winner-take-all over the final S of this pixel: first minimum
-        int key = 0x7fffffff;
-        if (active) {
+      if (MODE != 3) {
+        if (active) *reinterpret_cast<V*>(wS) = sg_pack<DPL>(tot);
+        wS += step;
+      } else {
+        // winner-take-all over the final S of this pixel: first minimum; the lane that holds it finishes the pixel
+        int mykey = (tot[0] << 8) | (DPL * lane);
 #pragma unroll
-          for (int j = 0; j < DPL; j++) key = min(key, (tot[j] << 8) | (DPL * lane + j));
-        }
-        key = __reduce_min_sync(0xffffffffu, key);
+        for (int j = 1; j < DPL; j++) mykey = min(mykey, (tot[j] << 8) | (DPL * lane + j));
+        if (!active) mykey = 0x7fffffff;
+        const int key = __reduce_min_sync(0xffffffffu, mykey);
+        const int e_lo = __shfl_up_sync(0xffffffffu, tot[DPL - 1], 1);     // S[d - 1] of this lane's first d
+        const int e_hi = __shfl_down_sync(0xffffffffu, tot[0], 1);         // S[d + 1] of this lane's last d
         const int minS = key >> 8, bd = key & 255;
         bool rej = false;
         if (wta.uniq > 0) {
           bool pr = false;
-          if (active) {
 #pragma unroll
-            for (int j = 0; j < DPL; j++)
-              pr |= (tot[j] * (100 - wta.uniq) < minS * 100) && (abs(bd - (DPL * lane + j)) > 1);
-          }
-          rej = __any_sync(0xffffffffu, pr);
+          for (int j = 0; j < DPL; j++)
+            pr |= (tot[j] * (100 - wta.uniq) < minS * 100) && (abs(bd - (DPL * lane + j)) > 1);
+          rej = __any_sync(0xffffffffu, pr && active);
         }
-        const int dm = max(bd - 1, 0), dp = min(bd + 1, D - 1);
-        int vm = 0, vp = 0;
-        if (active) {
+        if (mykey == key && !rej) {
+          int sm = 0, sp = 0;
 #pragma unroll
           for (int j = 0; j < DPL; j++) {
-            if ((dm & (DPL - 1)) == j) vm = tot[j];
-            if ((dp & (DPL - 1)) == j) vp = tot[j];
+            const bool hit = ((tot[j] << 8) | (DPL * lane + j)) == key;    // exactly one j of this lane
+            sm = hit ? (j > 0 ? tot[j - 1] : e_lo) : sm;
+            sp = hit ? (j < DPL - 1 ? tot[j + 1] : e_hi) : sp;
           }
-        }
-        const int sm = __shfl_sync(0xffffffffu, vm, dm / DPL);
-        const int sp = __shfl_sync(0xffffffffu, vp, dp / DPL);
-        if (lane == 0 && !rej) {
-          const int px = x + i * sx, py = y + i * sy;
           const int x2 = px + wta.minX1 - bd - wta.minD;
-          if (minS < SG_MAX_COST) atomicMin(wta.key2 + (size_t)py * wta.w + x2, ((unsigned)minS << 16) | (unsigned)(0xFFFF - px));
-          int dv;
-          if (0 < bd && bd < D - 1) {
-            const int denom2 = max(sm + sp - 2 * minS, 1);
-            dv = bd * 16 + ((sm - sp) * 16 + denom2) / (denom2 * 2);
-          } else {
-            dv = bd * 16;
-          }
-          wta.disp1[(size_t)py * wta.w + px + wta.minX1] = (int16_t)(dv + wta.minD * 16);
+          if (minS < SG_MAX_COST)
+            atomicMin(wta.key2 + (size_t)py * wta.w + x2, ((unsigned)minS << 16) | (unsigned)(0xFFFF - px));
+          wta.rec[(size_t)py * wta.w + px + wta.minX1] =
+              make_uint2((unsigned)bd | ((unsigned)minS << 16), (unsigned)sm | ((unsigned)sp << 16));
         }
+        px += sx;
+        py += sy;
       }
     }
   }
 }
 
 // ------------------------------------------------------------------------------------ K_lr, K_median
-__global__ void sgbm_fill_kernel(int16_t* __restrict__ disp1, unsigned* __restrict__ key2, size_t n, int16_t inv) {
+__global__ void sgbm_fill_kernel(uint2* __restrict__ rec, unsigned* __restrict__ key2, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  disp1[i] = inv;
+  rec[i] = make_uint2(0xFFFFFFFFu, 0u);
   key2[i] = SG_KEY_INIT;
 }
 
@@ -363,13 +395,28 @@ __device__ __forceinline__ int sg_disp2(const unsigned* __restrict__ krow, int x
   return xw + minX1 - xr;     // = d + minD of the winning left pixel
 }
 
-__global__ void sgbm_lrcheck_kernel(const int16_t* __restrict__ disp1, const unsigned* __restrict__ key2, int w, int h,
-                                    int minD, int minX1, int maxX1, int d12, int16_t* __restrict__ out) {
+// sub-pixel step on the winner record, then the left-right check of computeDisparitySGBM
+__global__ void sgbm_lrcheck_kernel(const uint2* __restrict__ rec, const unsigned* __restrict__ key2, int w, int h, int D,
+                                    int minD, int minX1, int maxX1, int d12, int16_t* __restrict__ out,
+                                    int16_t* __restrict__ out_raw) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y;
   if (x >= w) return;
   const int inv = (minD - 1) * 16;
-  int d1 = disp1[(size_t)y * w + x];
+  int d1 = inv;
+  const uint2 r = rec[(size_t)y * w + x];
+  if (r.x != 0xFFFFFFFFu) {
+    const int bd = (int)(r.x & 0xFFFFu), minS = (int)(r.x >> 16);
+    int dv = bd * 16;
+    if (0 < bd && bd < D - 1) {
+      // parabola through (d-1, S[d-1]), (d, S[d]), (d+1, S[d+1]); C integer division
+      const int sm = (int)(r.y & 0xFFFFu), sp = (int)(r.y >> 16);
+      const int denom2 = max(sm + sp - 2 * minS, 1);
+      dv += ((sm - sp) * 16 + denom2) / (denom2 * 2);
+    }
+    d1 = dv + minD * 16;
+  }
+  if (out_raw) out_raw[(size_t)y * w + x] = (int16_t)d1;
   if (x >= minX1 && x < maxX1 && d1 != inv) {
     const unsigned* krow = key2 + (size_t)y * w;
     const int dlo = d1 >> 4, dhi = (d1 + 15) >> 4;
@@ -637,6 +684,7 @@ static int sgbm_ensure(vo_ctx* c, int w, int h, const SgResolved& r, bool need_b
     VO_CUDA(cudaMalloc(&s->C, cost * 2 + 64));
     VO_CUDA(cudaMalloc(&s->S, cost * 2 + 64));
     VO_CUDA(cudaMalloc(&s->key2, npx * sizeof(unsigned)));
+    VO_CUDA(cudaMalloc(&s->rec, npx * sizeof(uint2)));
     for (int k = 0; k < 3; k++) VO_CUDA(cudaMalloc(&s->disp[k], npx * sizeof(int16_t)));
     VO_CUDA(cudaMalloc(&s->label, npx * sizeof(int)));
     VO_CUDA(cudaMalloc(&s->count, npx * sizeof(int)));
@@ -658,34 +706,33 @@ static int sgbm_ensure(vo_ctx* c, int w, int h, const SgResolved& r, bool need_b
   return VO_OK;
 }
 
+template <int DPL, int MODE>
+static int sgbm_path_launch(vo_ctx* c, const int16_t* C, int16_t* S, int16_t* S_rl, const int16_t* S2, const SgResolved& r, int h,
+                            int dir_a, int dir_b, int ndirs, int npaths, const SgWta& wta) {
+  constexpr int NARR = MODE == 0 ? 1 : (MODE == 2 ? 3 : 2);
+  const size_t smem = (size_t)SG_WPB * SgVec<DPL>::STAGES * NARR * 32 * 2 * DPL;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VO_CUDA(cudaFuncSetAttribute(sgbm_path_kernel<DPL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  LaunchScope ls(c, VO_K_MISC);
+  sgbm_path_kernel<DPL, MODE><<<dim3(div_up(npaths, SG_WPB), ndirs), SG_WPB * 32, smem, c->stream>>>(
+      C, S, S_rl, S2, r.W1, h, r.D, r.P1, r.P2, dir_a, dir_b, npaths, wta);
+  return VO_OK;
+}
+
 template <int DPL>
 static int sgbm_paths(vo_ctx* c, Sgbm* s, const SgResolved& r, int h, const SgWta& wta) {
-  const int W1 = r.W1, D = r.D;
-  const int wpb = 4;   // warps per CTA
   int16_t* S2 = reinterpret_cast<int16_t*>(s->hsum);   // hsum is dead once C exists
-  {
-    LaunchScope ls(c, VO_K_MISC);   // both horizontal directions: S = L0, S2 = L4
-    sgbm_path_kernel<DPL, 0><<<dim3(div_up(h, wpb), 2), wpb * 32, 0, c->stream>>>(s->C, s->S, S2, nullptr, W1, h, D, r.P1,
-                                                                                r.P2, 0, 4, h, wta);
-  }
+  const int nd = r.W1 + h - 1;
+  // both horizontal directions at once: S = L0, S2 = L4
+  VO_TRY((sgbm_path_launch<DPL, 0>(c, s->C, s->S, S2, nullptr, r, h, 0, 4, 2, h, wta)));
   VO_CUDA(cudaEventRecord(s->ev[4], c->stream));
-  const int nd = W1 + h - 1;
-  {
-    LaunchScope ls(c, VO_K_MISC);
-    sgbm_path_kernel<DPL, 2><<<dim3(div_up(nd, wpb), 1), wpb * 32, 0, c->stream>>>(s->C, s->S, nullptr, S2, W1, h, D, r.P1,
-                                                                                 r.P2, 1, 1, nd, wta);
-  }
-  {
-    LaunchScope ls(c, VO_K_MISC);
-    sgbm_path_kernel<DPL, 1><<<dim3(div_up(nd, wpb), 1), wpb * 32, 0, c->stream>>>(s->C, s->S, nullptr, nullptr, W1, h, D,
-                                                                                 r.P1, r.P2, 3, 3, nd, wta);
-  }
+  VO_TRY((sgbm_path_launch<DPL, 2>(c, s->C, s->S, nullptr, S2, r, h, 1, 1, 1, nd, wta)));
+  VO_TRY((sgbm_path_launch<DPL, 1>(c, s->C, s->S, nullptr, nullptr, r, h, 3, 3, 1, nd, wta)));
   VO_CUDA(cudaEventRecord(s->ev[5], c->stream));
-  {
-    LaunchScope ls(c, VO_K_MISC);
-    sgbm_path_kernel<DPL, 3><<<dim3(div_up(W1, wpb), 1), wpb * 32, 0, c->stream>>>(s->C, s->S, nullptr, nullptr, W1, h, D,
-                                                                                 r.P1, r.P2, 2, 2, W1, wta);
-  }
+  VO_TRY((sgbm_path_launch<DPL, 3>(c, s->C, s->S, nullptr, nullptr, r, h, 2, 2, 1, r.W1, wta)));
   VO_CUDA(cudaGetLastError());
   return VO_OK;
 }
@@ -698,7 +745,7 @@ static int sgbm_run(vo_ctx* c, int w, int h, const vo_sgbm_params* p, const SgRe
   VO_CUDA(cudaEventRecord(s->ev[1], c->stream));
   {
     LaunchScope ls(c, VO_K_MISC);
-    sgbm_fill_kernel<<<div_up(n, 256), 256, 0, c->stream>>>(s->disp[0], s->key2, npx, (int16_t)r.inv);
+    sgbm_fill_kernel<<<div_up(n, 256), 256, 0, c->stream>>>(s->rec, s->key2, npx);
   }
   if (r.W1 > 0) {
     {
@@ -720,7 +767,7 @@ static int sgbm_run(vo_ctx* c, int w, int h, const vo_sgbm_params* p, const SgRe
                                                                                                rps, s->C);
     }
     VO_CUDA(cudaEventRecord(s->ev[3], c->stream));
-    SgWta wta{s->disp[0], s->key2, w, r.minD, r.minX1, r.uniq};
+    SgWta wta{s->rec, s->key2, w, r.minD, r.minX1, r.uniq};
     if (r.D <= 128) VO_TRY(sgbm_paths<4>(c, s, r, h, wta));
     else VO_TRY(sgbm_paths<8>(c, s, r, h, wta));
   } else {
@@ -729,8 +776,9 @@ static int sgbm_run(vo_ctx* c, int w, int h, const vo_sgbm_params* p, const SgRe
   VO_CUDA(cudaEventRecord(s->ev[6], c->stream));
   {
     LaunchScope ls(c, VO_K_MISC);
-    sgbm_lrcheck_kernel<<<dim3(div_up(w, 128), h), 128, 0, c->stream>>>(s->disp[0], s->key2, w, h, r.minD, r.minX1, r.maxX1,
-                                                                       r.d12, s->disp[1]);
+    static const bool keep_raw = getenv("VO_B200_SGBM_DEBUG") != nullptr;   // stage 1 of vo_debug_sgbm_stage
+    sgbm_lrcheck_kernel<<<dim3(div_up(w, 128), h), 128, 0, c->stream>>>(s->rec, s->key2, w, h, r.D, r.minD, r.minX1, r.maxX1,
+                                                                       r.d12, s->disp[1], keep_raw ? s->disp[0] : nullptr);
   }
   {
     LaunchScope ls(c, VO_K_MISC);
@@ -833,6 +881,7 @@ int vo_debug_sgbm_stage(vo_ctx* c, int stage, void* out, uint64_t bytes) {
   switch (stage) {
     case 0: src = s->C; avail = s->cost_elems * 2; break;
     case 1: src = s->disp[0]; avail = npx * 2; break;     // winner-take-all + sub-pixel, before the left-right check
+                                                          // (kept only when VO_B200_SGBM_DEBUG is set)
     case 2: src = s->disp[1]; avail = npx * 2; break;     // after the left-right check
     case 3: src = s->pl; avail = 4 * npx * 4; break;      // prefilter planes
     default: return VO_ERR_INVALID_ARG;
