@@ -57,6 +57,9 @@ struct Sgbm {
   int* idx_out = nullptr;
   int* d_n = nullptr;
   double* dQ = nullptr;
+  uint8_t* h_in[2] = {nullptr, nullptr};    // pinned staging for pageable caller memory
+  uint8_t* h_out = nullptr;
+  size_t h_in_bytes = 0, h_out_bytes = 0;
   void* cub_tmp = nullptr;
   size_t cub_bytes = 0;
   bool have_disp = false;
@@ -71,6 +74,9 @@ void sgbm_free(vo_ctx* c) {
   void* dev[] = {s->img[0], s->img[1], s->bgr[0], s->bgr[1], s->pl, s->hsum, s->C, s->S, s->key2, s->rec, s->disp[0], s->disp[1],
                  s->disp[2], s->label, s->count, s->xyz, s->keep, s->xyz_out, s->idx_out, s->d_n, s->dQ, s->cub_tmp};
   for (void* p : dev) cudaFree(p);
+  cudaFreeHost(s->h_in[0]);
+  cudaFreeHost(s->h_in[1]);
+  cudaFreeHost(s->h_out);
   for (auto e : s->ev)
     if (e) cudaEventDestroy(e);
   delete s;
@@ -813,13 +819,72 @@ static int sgbm_run(vo_ctx* c, int w, int h, const vo_sgbm_params* p, const SgRe
   return VO_OK;
 }
 
+
+// Caller buffers are usually pageable (cv::Mat / std::vector memory): a pageable cudaMemcpy runs at a few GB/s, so
+// such buffers go through pinned staging owned by the context (one host memcpy + one DMA); pinned, managed and
+// device pointers are copied directly.
+static bool sg_needs_staging(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return true;
+  }
+  return a.type == cudaMemoryTypeUnregistered;
+}
+
+static int sg_stage_reserve(uint8_t** buf, size_t* have, size_t need) {
+  if (need <= *have) return VO_OK;
+  cudaFreeHost(*buf);
+  *buf = nullptr;
+  *have = 0;
+  VO_CUDA(cudaMallocHost(buf, need));
+  *have = need;
+  return VO_OK;
+}
+
+// host image (row_bytes per row, stride between rows) -> tight device buffer
+static int sg_upload(vo_ctx* c, Sgbm* s, int k, uint8_t* d_dst, const uint8_t* src, int stride, size_t row_bytes, int h) {
+  if (!sg_needs_staging(src)) {
+    VO_CUDA(cudaMemcpy2DAsync(d_dst, row_bytes, src, stride, row_bytes, h, cudaMemcpyDefault, c->stream));
+    return VO_OK;
+  }
+  const size_t bytes = row_bytes * h;
+  if (bytes > s->h_in_bytes) {
+    VO_CUDA(cudaStreamSynchronize(c->stream));
+    size_t have0 = s->h_in_bytes, have1 = s->h_in_bytes;
+    VO_TRY(sg_stage_reserve(&s->h_in[0], &have0, bytes));
+    VO_TRY(sg_stage_reserve(&s->h_in[1], &have1, bytes));
+    s->h_in_bytes = bytes;
+  }
+  if ((size_t)stride == row_bytes) {
+    memcpy(s->h_in[k], src, bytes);
+  } else {
+    for (int y = 0; y < h; y++) memcpy(s->h_in[k] + (size_t)y * row_bytes, src + (size_t)y * stride, row_bytes);
+  }
+  VO_CUDA(cudaMemcpyAsync(d_dst, s->h_in[k], bytes, cudaMemcpyHostToDevice, c->stream));
+  return VO_OK;
+}
+
 static int sgbm_finish(vo_ctx* c, int w, int h, int16_t* disp, int disp_stride) {
   Sgbm* s = reinterpret_cast<Sgbm*>(c->sgbm);
-  if (disp)
-    VO_CUDA(cudaMemcpy2DAsync(disp, disp_stride, s->disp[2], (size_t)w * 2, (size_t)w * 2, h, cudaMemcpyDeviceToHost,
-                              c->stream));
+  const size_t row = (size_t)w * 2;
+  bool staged = false;
+  if (disp) {
+    if (sg_needs_staging(disp)) {
+      VO_TRY(sg_stage_reserve(&s->h_out, &s->h_out_bytes, row * h));
+      VO_CUDA(cudaMemcpyAsync(s->h_out, s->disp[2], row * h, cudaMemcpyDeviceToHost, c->stream));
+      staged = true;
+    } else {
+      VO_CUDA(cudaMemcpy2DAsync(disp, disp_stride, s->disp[2], row, row, h, cudaMemcpyDefault, c->stream));
+    }
+  }
   VO_CUDA(cudaEventRecord(s->ev[9], c->stream));
   VO_CUDA(cudaStreamSynchronize(c->stream));
+  if (staged) {
+    if ((size_t)disp_stride == row) memcpy(disp, s->h_out, row * h);
+    else
+      for (int y = 0; y < h; y++) memcpy((uint8_t*)disp + (size_t)y * disp_stride, s->h_out + (size_t)y * row, row);
+  }
   for (int k = 0; k < 9; k++) {
     float ms = 0;
     if (cudaEventElapsedTime(&ms, s->ev[k], s->ev[k + 1]) != cudaSuccess) ms = -1.f;
@@ -837,8 +902,8 @@ int vo_sgbm_compute(vo_ctx* c, const uint8_t* left, const uint8_t* right, int st
   VO_TRY(sgbm_ensure(c, width, height, r, false));
   Sgbm* s = reinterpret_cast<Sgbm*>(c->sgbm);
   VO_CUDA(cudaEventRecord(s->ev[0], c->stream));
-  VO_CUDA(cudaMemcpy2DAsync(s->img[0], width, left, stride, width, height, cudaMemcpyHostToDevice, c->stream));
-  VO_CUDA(cudaMemcpy2DAsync(s->img[1], width, right, stride, width, height, cudaMemcpyHostToDevice, c->stream));
+  VO_TRY(sg_upload(c, s, 0, s->img[0], left, stride, (size_t)width, height));
+  VO_TRY(sg_upload(c, s, 1, s->img[1], right, stride, (size_t)width, height));
   VO_TRY(sgbm_run(c, width, height, p, r));
   return sgbm_finish(c, width, height, disp, disp_stride);
 }
@@ -854,8 +919,7 @@ int vo_stereo_match(vo_ctx* c, const uint8_t* left_bgr, const uint8_t* right_bgr
   VO_CUDA(cudaEventRecord(s->ev[0], c->stream));
   const uint8_t* src[2] = {left_bgr, right_bgr};
   for (int k = 0; k < 2; k++) {
-    VO_CUDA(cudaMemcpy2DAsync(s->bgr[k], 3 * (size_t)width, src[k], stride, 3 * (size_t)width, height,
-                              cudaMemcpyHostToDevice, c->stream));
+    VO_TRY(sg_upload(c, s, k, s->bgr[k], src[k], stride, 3 * (size_t)width, height));
     // cvtColor(BGR2GRAY), src/StereoCV.cpp:35-36
     VO_TRY(bgr2gray_launch_wh(c, s->bgr[k], 3 * width, s->img[k], width, width, height));
   }
@@ -905,8 +969,8 @@ int vo_reproject_disparity(vo_ctx* c, const int16_t* disp, int disp_stride, int 
     r.D = 16;
     VO_TRY(sgbm_ensure(c, width, height, r, false));
     s = reinterpret_cast<Sgbm*>(c->sgbm);
-    VO_CUDA(cudaMemcpy2DAsync(s->disp[2], (size_t)width * 2, disp, disp_stride, (size_t)width * 2, height,
-                              cudaMemcpyHostToDevice, c->stream));
+    VO_TRY(sg_upload(c, s, 0, reinterpret_cast<uint8_t*>(s->disp[2]), reinterpret_cast<const uint8_t*>(disp), disp_stride,
+                     (size_t)width * 2, height));
     s->have_disp = true;
     s->last_w = width;
     s->last_h = height;
@@ -935,9 +999,19 @@ int vo_reproject_disparity(vo_ctx* c, const int16_t* disp, int disp_stride, int 
   *n_out = m;
   const int k = std::min(m, cap);
   if (k > 0) {
-    VO_CUDA(cudaMemcpyAsync(xyz, s->xyz_out, (size_t)k * sizeof(float3), cudaMemcpyDeviceToHost, c->stream));
-    if (pix_idx) VO_CUDA(cudaMemcpyAsync(pix_idx, s->idx_out, (size_t)k * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    VO_CUDA(cudaStreamSynchronize(c->stream));
+    const size_t bx = (size_t)k * sizeof(float3), bi = pix_idx ? (size_t)k * sizeof(int) : 0;
+    if (sg_needs_staging(xyz) || (pix_idx && sg_needs_staging(pix_idx))) {
+      VO_TRY(sg_stage_reserve(&s->h_out, &s->h_out_bytes, bx + bi));
+      VO_CUDA(cudaMemcpyAsync(s->h_out, s->xyz_out, bx, cudaMemcpyDeviceToHost, c->stream));
+      if (bi) VO_CUDA(cudaMemcpyAsync(s->h_out + bx, s->idx_out, bi, cudaMemcpyDeviceToHost, c->stream));
+      VO_CUDA(cudaStreamSynchronize(c->stream));
+      memcpy(xyz, s->h_out, bx);
+      if (bi) memcpy(pix_idx, s->h_out + bx, bi);
+    } else {
+      VO_CUDA(cudaMemcpyAsync(xyz, s->xyz_out, bx, cudaMemcpyDefault, c->stream));
+      if (bi) VO_CUDA(cudaMemcpyAsync(pix_idx, s->idx_out, bi, cudaMemcpyDefault, c->stream));
+      VO_CUDA(cudaStreamSynchronize(c->stream));
+    }
   }
   return m > cap ? VO_ERR_CAPACITY : VO_OK;
 }
