@@ -46,6 +46,9 @@ struct Sgbm {
   uint16_t* hsum = nullptr;                 // also reused as S2
   int16_t* C = nullptr;
   int16_t* S = nullptr;
+  int16_t* SB = nullptr;                    // right-to-left path costs (left-to-right ones reuse hsum)
+  cudaStream_t stream2 = nullptr;           // the horizontal paths run here, underneath the diagonal ones
+  cudaEvent_t ev_h = nullptr;
   unsigned* key2 = nullptr;                 // right-view (cost, x) keys
   uint2* rec = nullptr;                     // winner records
   int16_t* disp[3] = {nullptr, nullptr, nullptr};   // raw WTA, after LR check, after median (+ speckle in place)
@@ -71,7 +74,7 @@ struct Sgbm {
 void sgbm_free(vo_ctx* c) {
   Sgbm* s = reinterpret_cast<Sgbm*>(c->sgbm);
   if (!s) return;
-  void* dev[] = {s->img[0], s->img[1], s->bgr[0], s->bgr[1], s->pl, s->hsum, s->C, s->S, s->key2, s->rec, s->disp[0], s->disp[1],
+  void* dev[] = {s->img[0], s->img[1], s->bgr[0], s->bgr[1], s->pl, s->hsum, s->C, s->S, s->SB, s->key2, s->rec, s->disp[0], s->disp[1],
                  s->disp[2], s->label, s->count, s->xyz, s->keep, s->xyz_out, s->idx_out, s->d_n, s->dQ, s->cub_tmp};
   for (void* p : dev) cudaFree(p);
   cudaFreeHost(s->h_in[0]);
@@ -79,13 +82,15 @@ void sgbm_free(vo_ctx* c) {
   cudaFreeHost(s->h_out);
   for (auto e : s->ev)
     if (e) cudaEventDestroy(e);
+  if (s->ev_h) cudaEventDestroy(s->ev_h);
+  if (s->stream2) cudaStreamDestroy(s->stream2);
   delete s;
   c->sgbm = nullptr;
 }
 
 static void sgbm_release_buffers(Sgbm* s) {
   void** dev[] = {(void**)&s->img[0], (void**)&s->img[1], (void**)&s->bgr[0], (void**)&s->bgr[1], (void**)&s->pl,
-                  (void**)&s->hsum, (void**)&s->C, (void**)&s->S, (void**)&s->key2, (void**)&s->rec, (void**)&s->disp[0],
+                  (void**)&s->hsum, (void**)&s->C, (void**)&s->S, (void**)&s->SB, (void**)&s->key2, (void**)&s->rec, (void**)&s->disp[0],
                   (void**)&s->disp[1], (void**)&s->disp[2], (void**)&s->label, (void**)&s->count, (void**)&s->xyz,
                   (void**)&s->keep, (void**)&s->xyz_out, (void**)&s->idx_out, (void**)&s->cub_tmp};
   for (void** p : dev) {
@@ -232,19 +237,20 @@ struct SgWta {
   int w, minD, minX1, uniq;
 };
 
-// One warp per path.  MODE 0: S = L (no read).  MODE 1: S = min(32767, S + L).  MODE 2: S = min(32767, S + S2 + L).
-// MODE 3: s = min(32767, S + L) is consumed by the winner-take-all step and not stored.
+// One warp per path.  NIN = number of cost volumes added to this direction's L: 0: out = L (no read); 1: S; 2: S + I1;
+// 3: S + I1 + I2, saturated at 32767.  WTA = false: the sum is stored to S; WTA = true: it is the final S of the pixel
+// and is consumed by the winner-take-all step instead.
 // Directions: 0 left-to-right, 4 right-to-left (paths = rows), 1 down-right, 2 down, 3 down-left.
 // C (and S, S2) of the steps ahead travel through a per-warp shared-memory ring filled by cp.async: completion is
 // tracked per commit group, in order, so a step never waits for a copy younger than its own (register prefetch
 // could not do that: the scoreboards a load waits on are shared with the younger loads in flight).
-template <int DPL, int MODE>
+template <int DPL, int NIN, bool WTA>
 __global__ void __launch_bounds__(SG_WPB * 32)
-sgbm_path_kernel(const int16_t* __restrict__ C, int16_t* S, int16_t* S_rl, const int16_t* S2, int W1, int H, int D, int P1,
-                 int P2, int dir_a, int dir_b, int npaths, SgWta wta) {
+sgbm_path_kernel(const int16_t* __restrict__ C, int16_t* S, int16_t* S_b, const int16_t* I1, const int16_t* I2, int W1, int H,
+                 int D, int P1, int P2, int dir_a, int dir_b, int npaths, SgWta wta) {
   using V = typename SgVec<DPL>::T;
   constexpr int NST = SgVec<DPL>::STAGES;
-  constexpr int NARR = MODE == 0 ? 1 : (MODE == 2 ? 3 : 2);
+  constexpr int NARR = 1 + NIN;
   constexpr int VB = 2 * DPL;                 // bytes per lane and array
   constexpr int ARR = 32 * VB, STG = NARR * ARR;
   extern __shared__ __align__(16) unsigned char sg_ring[];   // [warp][stage][array][lane][VB]
@@ -252,7 +258,7 @@ sgbm_path_kernel(const int16_t* __restrict__ C, int16_t* S, int16_t* S_rl, const
   const int p = blockIdx.x * SG_WPB + wib;
   if (p >= npaths) return;
   const int dir = blockIdx.y ? dir_b : dir_a;
-  int16_t* Sout = (blockIdx.y && S_rl) ? S_rl : S;
+  int16_t* Sout = (blockIdx.y && S_b) ? S_b : S;
   int x, y, n, sx, sy;
   switch (dir) {
     case 0: x = 0; y = p; n = W1; sx = 1; sy = 0; break;
@@ -271,7 +277,8 @@ sgbm_path_kernel(const int16_t* __restrict__ C, int16_t* S, int16_t* S_rl, const
   const size_t base = ((size_t)y * W1 + x) * D + (active ? DPL * lane : 0);
   const int16_t* gC = C + base;                // issue pointers: the step the next cp.async fetches
   const int16_t* gS = Sout + base;
-  const int16_t* gT = MODE == 2 ? S2 + base : nullptr;
+  const int16_t* gT = NIN >= 2 ? I1 + base : nullptr;
+  const int16_t* gU = NIN >= 3 ? I2 + base : nullptr;
   int16_t* wS = Sout + base;                   // store pointer: the current step
   unsigned char* ring = sg_ring + (size_t)wib * NST * STG + lane * VB;
   const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
@@ -280,11 +287,13 @@ sgbm_path_kernel(const int16_t* __restrict__ C, int16_t* S, int16_t* S_rl, const
   for (int k = 0; k < NST; k++) {
     if (k < n) {
       sg_cp_async<VB>(ring_s + k * STG, gC);
-      if (NARR >= 2) sg_cp_async<VB>(ring_s + k * STG + ARR, gS);
-      if (NARR == 3) sg_cp_async<VB>(ring_s + k * STG + 2 * ARR, gT);
+      if (NIN >= 1) sg_cp_async<VB>(ring_s + k * STG + ARR, gS);
+      if (NIN >= 2) sg_cp_async<VB>(ring_s + k * STG + 2 * ARR, gT);
+      if (NIN >= 3) sg_cp_async<VB>(ring_s + k * STG + 3 * ARR, gU);
       gC += step;
       gS += step;
-      if (MODE == 2) gT += step;
+      if (NIN >= 2) gT += step;
+      if (NIN >= 3) gU += step;
     }
     sg_cp_commit();
   }
@@ -301,17 +310,20 @@ sgbm_path_kernel(const int16_t* __restrict__ C, int16_t* S, int16_t* S_rl, const
       const int i = i0 + k;
       if (i >= n) break;
       sg_cp_wait<NST - 1>();                  // the group of step i (and every older one) has landed
-      int cv[DPL], sv[DPL], tv[DPL];
+      int cv[DPL], sv[DPL], tv[DPL], uv[DPL];
       sg_unpack<DPL>(*reinterpret_cast<const V*>(ring + k * STG), cv);
-      if (NARR >= 2) sg_unpack<DPL>(*reinterpret_cast<const V*>(ring + k * STG + ARR), sv);
-      if (NARR == 3) sg_unpack<DPL>(*reinterpret_cast<const V*>(ring + k * STG + 2 * ARR), tv);
+      if (NIN >= 1) sg_unpack<DPL>(*reinterpret_cast<const V*>(ring + k * STG + ARR), sv);
+      if (NIN >= 2) sg_unpack<DPL>(*reinterpret_cast<const V*>(ring + k * STG + 2 * ARR), tv);
+      if (NIN >= 3) sg_unpack<DPL>(*reinterpret_cast<const V*>(ring + k * STG + 3 * ARR), uv);
       if (i + NST < n) {                      // refill the stage that was just read
         sg_cp_async<VB>(ring_s + k * STG, gC);
-        if (NARR >= 2) sg_cp_async<VB>(ring_s + k * STG + ARR, gS);
-        if (NARR == 3) sg_cp_async<VB>(ring_s + k * STG + 2 * ARR, gT);
+        if (NIN >= 1) sg_cp_async<VB>(ring_s + k * STG + ARR, gS);
+        if (NIN >= 2) sg_cp_async<VB>(ring_s + k * STG + 2 * ARR, gT);
+        if (NIN >= 3) sg_cp_async<VB>(ring_s + k * STG + 3 * ARR, gU);
         gC += step;
         gS += step;
-        if (MODE == 2) gT += step;
+        if (NIN >= 2) gT += step;
+        if (NIN >= 3) gU += step;
       }
       sg_cp_commit();
       // formula 13 of the SGM paper as OpenCV evaluates it
@@ -340,11 +352,12 @@ sgbm_path_kernel(const int16_t* __restrict__ C, int16_t* S, int16_t* S_rl, const
 #pragma unroll
       for (int j = 0; j < DPL; j++) {
         int t = Ln[j];
-        if (MODE >= 1) t += sv[j];
-        if (MODE == 2) t += tv[j];
-        tot[j] = MODE >= 1 ? min(t, SG_MAX_COST) : t;
+        if (NIN >= 1) t += sv[j];
+        if (NIN >= 2) t += tv[j];
+        if (NIN >= 3) t += uv[j];
+        tot[j] = NIN >= 1 ? min(t, SG_MAX_COST) : t;
       }
-      if (MODE != 3) {
+      if (!WTA) {
         if (active) *reinterpret_cast<V*>(wS) = sg_pack<DPL>(tot);
         wS += step;
       } else {
@@ -466,11 +479,15 @@ __global__ void sgbm_median3_kernel(const int16_t* __restrict__ in, int w, int h
 }
 
 // ------------------------------------------------------------------------------------ K_speckle (cv::filterSpeckles)
+// labels only ever decrease and always name an ancestor, so shortening a chain (path halving) is safe under
+// concurrent unions
 __device__ __forceinline__ int sg_find(volatile int* lab, int i) {
   int p = lab[i];
   while (p != i) {
+    const int g = lab[p];
+    if (g != p) lab[i] = g;
     i = p;
-    p = lab[i];
+    p = g;
   }
   return i;
 }
@@ -565,8 +582,10 @@ __global__ void sgbm_cc_apply_kernel(int n, const int* __restrict__ lab, const i
                                      int new_val, int16_t* __restrict__ d) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int r = lab[i];
+  int r = lab[i];
   if (r < 0) return;
+  // a concurrent path-halving write of the count pass may have left an ancestor here instead of the root
+  for (int q = lab[r]; q != r; q = lab[r]) r = q;
   if (cnt[r] <= max_size) d[i] = (int16_t)new_val;
 }
 
@@ -672,6 +691,8 @@ static int sgbm_ensure(vo_ctx* c, int w, int h, const SgResolved& r, bool need_b
     s = new Sgbm();
     c->sgbm = s;
     for (auto& e : s->ev) VO_CUDA(cudaEventCreate(&e));
+    VO_CUDA(cudaEventCreateWithFlags(&s->ev_h, cudaEventDisableTiming));
+    VO_CUDA(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
     VO_CUDA(cudaMalloc(&s->d_n, 4 * sizeof(int)));
     VO_CUDA(cudaMalloc(&s->dQ, 16 * sizeof(double)));
   }
@@ -689,6 +710,7 @@ static int sgbm_ensure(vo_ctx* c, int w, int h, const SgResolved& r, bool need_b
     VO_CUDA(cudaMalloc(&s->hsum, cost * 2 + 64));
     VO_CUDA(cudaMalloc(&s->C, cost * 2 + 64));
     VO_CUDA(cudaMalloc(&s->S, cost * 2 + 64));
+    VO_CUDA(cudaMalloc(&s->SB, cost * 2 + 64));
     VO_CUDA(cudaMalloc(&s->key2, npx * sizeof(unsigned)));
     VO_CUDA(cudaMalloc(&s->rec, npx * sizeof(uint2)));
     for (int k = 0; k < 3; k++) VO_CUDA(cudaMalloc(&s->disp[k], npx * sizeof(int16_t)));
@@ -712,33 +734,39 @@ static int sgbm_ensure(vo_ctx* c, int w, int h, const SgResolved& r, bool need_b
   return VO_OK;
 }
 
-template <int DPL, int MODE>
-static int sgbm_path_launch(vo_ctx* c, const int16_t* C, int16_t* S, int16_t* S_rl, const int16_t* S2, const SgResolved& r, int h,
-                            int dir_a, int dir_b, int ndirs, int npaths, const SgWta& wta) {
-  constexpr int NARR = MODE == 0 ? 1 : (MODE == 2 ? 3 : 2);
-  const size_t smem = (size_t)SG_WPB * SgVec<DPL>::STAGES * NARR * 32 * 2 * DPL;
+template <int DPL, int NIN, bool WTA>
+static int sgbm_path_launch(vo_ctx* c, cudaStream_t st, const int16_t* C, int16_t* S, int16_t* S_b, const int16_t* I1,
+                            const int16_t* I2, const SgResolved& r, int h, int dir_a, int dir_b, int ndirs, int npaths,
+                            const SgWta& wta) {
+  const size_t smem = (size_t)SG_WPB * SgVec<DPL>::STAGES * (1 + NIN) * 32 * 2 * DPL;
   static bool attr_set = false;
   if (!attr_set) {
-    VO_CUDA(cudaFuncSetAttribute(sgbm_path_kernel<DPL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VO_CUDA(cudaFuncSetAttribute(sgbm_path_kernel<DPL, NIN, WTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  LaunchScope ls(c, VO_K_MISC);
-  sgbm_path_kernel<DPL, MODE><<<dim3(div_up(npaths, SG_WPB), ndirs), SG_WPB * 32, smem, c->stream>>>(
-      C, S, S_rl, S2, r.W1, h, r.D, r.P1, r.P2, dir_a, dir_b, npaths, wta);
+  c->launch_count++;
+  sgbm_path_kernel<DPL, NIN, WTA><<<dim3(div_up(npaths, SG_WPB), ndirs), SG_WPB * 32, smem, st>>>(
+      C, S, S_b, I1, I2, r.W1, h, r.D, r.P1, r.P2, dir_a, dir_b, npaths, wta);
   return VO_OK;
 }
 
+// The horizontal paths are the long ones (W1 steps, only 2 * h warps): they run on a second stream into their own
+// volumes (SA = L0, SB = L4) underneath the two diagonal launches (S = L1, then S += L3); the vertical launch then
+// adds S + SA + SB to its own L2 and finishes the pixel.
 template <int DPL>
 static int sgbm_paths(vo_ctx* c, Sgbm* s, const SgResolved& r, int h, const SgWta& wta) {
-  int16_t* S2 = reinterpret_cast<int16_t*>(s->hsum);   // hsum is dead once C exists
+  int16_t* SA = reinterpret_cast<int16_t*>(s->hsum);   // hsum is dead once C exists
+  int16_t* SB = s->SB;
   const int nd = r.W1 + h - 1;
-  // both horizontal directions at once: S = L0, S2 = L4
-  VO_TRY((sgbm_path_launch<DPL, 0>(c, s->C, s->S, S2, nullptr, r, h, 0, 4, 2, h, wta)));
+  VO_CUDA(cudaStreamWaitEvent(s->stream2, s->ev[3], 0));
+  VO_TRY((sgbm_path_launch<DPL, 0, false>(c, s->stream2, s->C, SA, SB, nullptr, nullptr, r, h, 0, 4, 2, h, wta)));
+  VO_CUDA(cudaEventRecord(s->ev_h, s->stream2));
+  VO_TRY((sgbm_path_launch<DPL, 0, false>(c, c->stream, s->C, s->S, nullptr, nullptr, nullptr, r, h, 1, 1, 1, nd, wta)));
+  VO_TRY((sgbm_path_launch<DPL, 1, false>(c, c->stream, s->C, s->S, nullptr, nullptr, nullptr, r, h, 3, 3, 1, nd, wta)));
   VO_CUDA(cudaEventRecord(s->ev[4], c->stream));
-  VO_TRY((sgbm_path_launch<DPL, 2>(c, s->C, s->S, nullptr, S2, r, h, 1, 1, 1, nd, wta)));
-  VO_TRY((sgbm_path_launch<DPL, 1>(c, s->C, s->S, nullptr, nullptr, r, h, 3, 3, 1, nd, wta)));
+  VO_CUDA(cudaStreamWaitEvent(c->stream, s->ev_h, 0));
   VO_CUDA(cudaEventRecord(s->ev[5], c->stream));
-  VO_TRY((sgbm_path_launch<DPL, 3>(c, s->C, s->S, nullptr, nullptr, r, h, 2, 2, 1, r.W1, wta)));
+  VO_TRY((sgbm_path_launch<DPL, 3, true>(c, c->stream, s->C, s->S, nullptr, SA, SB, r, h, 2, 2, 1, r.W1, wta)));
   VO_CUDA(cudaGetLastError());
   return VO_OK;
 }
