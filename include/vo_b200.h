@@ -225,8 +225,8 @@ int vo_stereo_match(vo_ctx* ctx, const uint8_t* left_bgr, const uint8_t* right_b
 int vo_reproject_disparity(vo_ctx* ctx, const int16_t* disp, int disp_stride, int width, int height, const double Q[16],
                            float* xyz, int32_t* pix_idx, int cap, int* n);
 /* device milliseconds of the last SGBM call: upload (+ gray conversion), prefilter, cost volume (BT + box sums),
- * diagonal paths (the horizontal ones run underneath on a second stream), what remained of the horizontal paths
- * after that, vertical paths + winner-take-all, left-right check + median, speckle filter, download */
+ * vertical paths (the horizontal and diagonal ones run beside them on two more streams), what remained of those
+ * after that, sum + winner-take-all, left-right check + median, speckle filter, download */
 int vo_sgbm_timing(vo_ctx* ctx, float ms[9]);
 /* intermediate stages of the last SGBM call, for parity debugging: 0 = C (int16 [h][W1][D]), 1 = disparity after
  * winner-take-all, 2 = after the left-right check (both int16 [h][w]), 3 = prefilter planes (uchar4 [4][h][w]) */

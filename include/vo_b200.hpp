@@ -163,4 +163,67 @@ class visualSLAM {
   vo_ctx* ctx_ = nullptr;
 };
 
+// Mirror of the dense-stereo members of the reference's `class StereoProcess` (reference include/stereoCV.h:63-64,
+// src/StereoCV.cpp:21-62,221-250).  The reference reads the frames itself (getImg + imread); here the caller hands
+// over the BGR frames it read, everything after imread runs on the GPU.
+struct BgrImage {            // view of an 8-bit 3-channel image as imread returns it
+  const uint8_t* data = nullptr;
+  int rows = 0, cols = 0, step = 0;
+};
+struct Disparity {           // CV_16S disparity, 16x fixed point (what StereoSGBM::compute returns)
+  std::vector<int16_t> data;
+  int rows = 0, cols = 0;
+};
+
+class StereoProcess {
+ public:
+  double baseline = 0.5707;                                   // reference include/stereoCV.h:39-43
+  double focal_x = 7.188560000000e+02, cx = 6.071928000000e+02;
+  double focal_y = 7.188560000000e+02, cy = 1.852157000000e+02;
+  vo_sgbm_params sgbm;                                        // StereoSGBM::create arguments, src/StereoCV.cpp:39-50
+
+  explicit StereoProcess(vo_ctx* ctx) : ctx_(ctx) { vo_sgbm_default_params(&sgbm); }
+
+  // reference src/StereoCV.cpp:21-62: cvtColor(BGR2GRAY) x 2 + matcher->compute
+  Disparity stereoMatch(const BgrImage& im1, const BgrImage& im2) {
+    lImg_ = im1;
+    Disparity d;
+    d.rows = im1.rows; d.cols = im1.cols;
+    d.data.resize((size_t)im1.rows * im1.cols);
+    check(vo_stereo_match(ctx_, im1.data, im2.data, im1.step, im1.cols, im1.rows, &sgbm, d.data.data(), 2 * im1.cols));
+    return d;
+  }
+
+  // reference src/StereoCV.cpp:221-250.  Q is what stereoRectify(K, 0, K, 0, size, I, (baseline, 0, 0)) returns
+  // there (:224-229); for those arguments (no rotation, equal intrinsics) it has the closed form below -- OpenCV
+  // 4.13.0 rounds the principal point through float, which is reproduced (bit-equal to cv2.stereoRectify).  With
+  // t = +baseline every reprojected z is negative and the gate of :240 drops every point: the reference's behaviour.
+  void reprojectDisparity(const Disparity& disp, std::vector<Point3f>& reproject3dPoints, std::vector<Point3f>& colorMap) {
+    reproject3dPoints.clear(); colorMap.clear();
+    const double Q[16] = {1, 0, 0, -(double)(float)cx, 0, 1, 0, -(double)(float)cy, 0, 0, 0, focal_x,
+                          0, 0, -1.0 / baseline, 0};
+    const int n = disp.rows * disp.cols;
+    std::vector<Point3f> pts(n);
+    std::vector<int32_t> idx(n);
+    int m = 0;
+    check(vo_reproject_disparity(ctx_, disp.data.data(), 2 * disp.cols, disp.cols, disp.rows, Q,
+                                 reinterpret_cast<float*>(pts.data()), idx.data(), n, &m));
+    pts.resize(m);
+    reproject3dPoints.swap(pts);
+    colorMap.resize(m);
+    for (int k = 0; k < m; k++) {       // Vec3b colors = lImg.at<Vec3b>(i, j), src/StereoCV.cpp:238,245
+      const int i = idx[k] / disp.cols, j = idx[k] % disp.cols;
+      const uint8_t* c = lImg_.data ? lImg_.data + (size_t)i * lImg_.step + 3 * j : nullptr;
+      colorMap[k] = c ? Point3f{(float)c[0], (float)c[1], (float)c[2]} : Point3f{0, 0, 0};
+    }
+  }
+
+ private:
+  static void check(int r) {
+    if (r != VO_OK) throw Error(r, std::string(vo_strerror(r)) + ": " + vo_last_error());
+  }
+  vo_ctx* ctx_;
+  BgrImage lImg_;
+};
+
 }  // namespace vo

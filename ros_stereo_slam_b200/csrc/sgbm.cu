@@ -12,13 +12,15 @@
 //            width -> hsum[y][x][d] u16                                                  H*W1*D*2 bytes
 //   K_vsum   running sum over the block height (rows replicated at the border) -> C[y][x][d] s16
 //   K_path   one WARP per path, the D disparities of a pixel spread over the lanes (4 or 8 per lane, one 8/16-byte
-//            load per step), predecessor costs in registers, neighbours d-1/d+1 by two shuffles, min over d by one
-//            REDUX; C and S reads are prefetched 8 steps ahead so that the only latency on the chain is the
-//            recurrence itself.  Launches: both horizontal directions at once (S = L0, S2 = L4, write only), the
-//            two diagonals (read-modify-write of S), the vertical direction last, fused with winner-take-all,
-//            uniqueness test, sub-pixel step and the right-view disparity (one atomicMin on a packed
-//            (cost, 65535 - x) key replaces OpenCV's descending-x first-come rule).  Every L is >= 0, so OpenCV's two
-//            saturating adds collapse into S = min(32767, sum of the five L): the order of the directions is free.
+//            access per step), predecessor costs in registers, neighbours d-1/d+1 by two shuffles, min over d by one
+//            REDUX; C of the next 16 steps is in flight through a per-warp cp.async ring in shared memory, so the only
+//            latency on the chain is the recurrence itself.  A path is one warp and the paths are few (2h horizontal,
+//            2(W1+h-1) diagonal, W1 vertical), so all five directions run at once on three streams, each into its own
+//            volume L_r[y][x][d] s16.
+//   K_wta    warp per pixel: S = min(32767, sum of the five L) (every L is >= 0, so OpenCV's two saturating adds
+//            collapse into this and the order of the directions is free), winner-take-all, uniqueness test, the
+//            neighbours for the sub-pixel step and the right-view disparity (one atomicMin on a packed
+//            (cost, 65535 - x) key replaces OpenCV's descending-x first-come rule).
 //   K_lr     left-right check, K_median 3x3, K_speckle: union-find connected components over |difference| <=
 //            16*speckleRange edges, components of <= speckleWindowSize pixels are cleared (cv::filterSpeckles).
 //   K_reproj reprojectImageTo3D on the float-converted 16x disparity + the reference's gate 0.01 < z <= 5 and y flip,
@@ -46,9 +48,9 @@ struct Sgbm {
   uint16_t* hsum = nullptr;                 // also reused as S2
   int16_t* C = nullptr;
   int16_t* S = nullptr;
-  int16_t* SB = nullptr;                    // right-to-left path costs (left-to-right ones reuse hsum)
-  cudaStream_t stream2 = nullptr;           // the horizontal paths run here, underneath the diagonal ones
-  cudaEvent_t ev_h = nullptr;
+  int16_t* vol[3] = {nullptr, nullptr, nullptr};   // path-cost volumes L4, L1, L3 (L0 reuses hsum, L2 is S)
+  cudaStream_t stream2 = nullptr, stream3 = nullptr;   // horizontal / diagonal paths run beside the vertical ones
+  cudaEvent_t ev_h = nullptr, ev_d = nullptr;
   unsigned* key2 = nullptr;                 // right-view (cost, x) keys
   uint2* rec = nullptr;                     // winner records
   int16_t* disp[3] = {nullptr, nullptr, nullptr};   // raw WTA, after LR check, after median (+ speckle in place)
@@ -74,7 +76,7 @@ struct Sgbm {
 void sgbm_free(vo_ctx* c) {
   Sgbm* s = reinterpret_cast<Sgbm*>(c->sgbm);
   if (!s) return;
-  void* dev[] = {s->img[0], s->img[1], s->bgr[0], s->bgr[1], s->pl, s->hsum, s->C, s->S, s->SB, s->key2, s->rec, s->disp[0], s->disp[1],
+  void* dev[] = {s->img[0], s->img[1], s->bgr[0], s->bgr[1], s->pl, s->hsum, s->C, s->S, s->vol[0], s->vol[1], s->vol[2], s->key2, s->rec, s->disp[0], s->disp[1],
                  s->disp[2], s->label, s->count, s->xyz, s->keep, s->xyz_out, s->idx_out, s->d_n, s->dQ, s->cub_tmp};
   for (void* p : dev) cudaFree(p);
   cudaFreeHost(s->h_in[0]);
@@ -83,14 +85,17 @@ void sgbm_free(vo_ctx* c) {
   for (auto e : s->ev)
     if (e) cudaEventDestroy(e);
   if (s->ev_h) cudaEventDestroy(s->ev_h);
+  if (s->ev_d) cudaEventDestroy(s->ev_d);
   if (s->stream2) cudaStreamDestroy(s->stream2);
+  if (s->stream3) cudaStreamDestroy(s->stream3);
   delete s;
   c->sgbm = nullptr;
 }
 
 static void sgbm_release_buffers(Sgbm* s) {
   void** dev[] = {(void**)&s->img[0], (void**)&s->img[1], (void**)&s->bgr[0], (void**)&s->bgr[1], (void**)&s->pl,
-                  (void**)&s->hsum, (void**)&s->C, (void**)&s->S, (void**)&s->SB, (void**)&s->key2, (void**)&s->rec, (void**)&s->disp[0],
+                  (void**)&s->hsum, (void**)&s->C, (void**)&s->S, (void**)&s->vol[0], (void**)&s->vol[1], (void**)&s->vol[2],
+                  (void**)&s->key2, (void**)&s->rec, (void**)&s->disp[0],
                   (void**)&s->disp[1], (void**)&s->disp[2], (void**)&s->label, (void**)&s->count, (void**)&s->xyz,
                   (void**)&s->keep, (void**)&s->xyz_out, (void**)&s->idx_out, (void**)&s->cub_tmp};
   for (void** p : dev) {
@@ -237,28 +242,26 @@ struct SgWta {
   int w, minD, minX1, uniq;
 };
 
-// One warp per path.  NIN = number of cost volumes added to this direction's L: 0: out = L (no read); 1: S; 2: S + I1;
-// 3: S + I1 + I2, saturated at 32767.  WTA = false: the sum is stored to S; WTA = true: it is the final S of the pixel
-// and is consumed by the winner-take-all step instead.
-// Directions: 0 left-to-right, 4 right-to-left (paths = rows), 1 down-right, 2 down, 3 down-left.
-// C (and S, S2) of the steps ahead travel through a per-warp shared-memory ring filled by cp.async: completion is
-// tracked per commit group, in order, so a step never waits for a copy younger than its own (register prefetch
-// could not do that: the scoreboards a load waits on are shared with the younger loads in flight).
-template <int DPL, int NIN, bool WTA>
+// One warp per path: out(p, d) = L_r(p, d).  Directions: 0 left-to-right, 4 right-to-left (paths = rows), 1 down-right,
+// 2 down, 3 down-left; blockIdx.y selects (dir_a -> out_a) or (dir_b -> out_b), so two directions share a launch.
+// C of the steps ahead travels through a per-warp shared-memory ring filled by cp.async: completion is tracked per
+// commit group, in order, so a step never waits for a copy younger than its own (register prefetch could not do
+// that: the scoreboards a load waits on are shared with the younger loads in flight).
+// NARROW (P2 <= 255): the volume holds L - C, which lies in [0, P2], as one byte per disparity -- half the traffic.
+template <int DPL, bool NARROW>
 __global__ void __launch_bounds__(SG_WPB * 32)
-sgbm_path_kernel(const int16_t* __restrict__ C, int16_t* S, int16_t* S_b, const int16_t* I1, const int16_t* I2, int W1, int H,
-                 int D, int P1, int P2, int dir_a, int dir_b, int npaths, SgWta wta) {
+sgbm_path_kernel(const int16_t* __restrict__ C, void* __restrict__ out_a, void* __restrict__ out_b, int W1, int H,
+                 int D, int P1, int P2, int dir_a, int dir_b, int npaths) {
   using V = typename SgVec<DPL>::T;
   constexpr int NST = SgVec<DPL>::STAGES;
-  constexpr int NARR = 1 + NIN;
-  constexpr int VB = 2 * DPL;                 // bytes per lane and array
-  constexpr int ARR = 32 * VB, STG = NARR * ARR;
-  extern __shared__ __align__(16) unsigned char sg_ring[];   // [warp][stage][array][lane][VB]
+  constexpr int VB = 2 * DPL;                 // bytes per lane
+  constexpr int STG = 32 * VB;
+  extern __shared__ __align__(16) unsigned char sg_ring[];   // [warp][stage][lane][VB]
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int p = blockIdx.x * SG_WPB + wib;
   if (p >= npaths) return;
   const int dir = blockIdx.y ? dir_b : dir_a;
-  int16_t* Sout = (blockIdx.y && S_b) ? S_b : S;
+  void* out = blockIdx.y ? out_b : out_a;
   int x, y, n, sx, sy;
   switch (dir) {
     case 0: x = 0; y = p; n = W1; sx = 1; sy = 0; break;
@@ -271,15 +274,14 @@ sgbm_path_kernel(const int16_t* __restrict__ C, int16_t* S, int16_t* S_b, const 
       if (p < W1) { x = p; y = 0; } else { x = W1 - 1; y = p - W1 + 1; }
       n = min(H - y, x + 1); sx = -1; sy = 1; break;
   }
+  if (dir == 2 && p >= W1) return;             // the vertical direction has fewer paths than its diagonal partner
   const bool active = DPL * lane < D;          // lanes beyond D work on lane 0's data and never store
   const bool last = DPL * (lane + 1) >= D;
   const long long step = ((long long)sy * W1 + sx) * D;       // elements per step along the path
   const size_t base = ((size_t)y * W1 + x) * D + (active ? DPL * lane : 0);
-  const int16_t* gC = C + base;                // issue pointers: the step the next cp.async fetches
-  const int16_t* gS = Sout + base;
-  const int16_t* gT = NIN >= 2 ? I1 + base : nullptr;
-  const int16_t* gU = NIN >= 3 ? I2 + base : nullptr;
-  int16_t* wS = Sout + base;                   // store pointer: the current step
+  const int16_t* gC = C + base;                // the step the next cp.async fetches
+  constexpr int OB = NARROW ? 1 : 2;           // bytes per stored cost
+  unsigned char* wS = reinterpret_cast<unsigned char*>(out) + base * OB;   // the current step
   unsigned char* ring = sg_ring + (size_t)wib * NST * STG + lane * VB;
   const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
 
@@ -287,13 +289,7 @@ sgbm_path_kernel(const int16_t* __restrict__ C, int16_t* S, int16_t* S_b, const 
   for (int k = 0; k < NST; k++) {
     if (k < n) {
       sg_cp_async<VB>(ring_s + k * STG, gC);
-      if (NIN >= 1) sg_cp_async<VB>(ring_s + k * STG + ARR, gS);
-      if (NIN >= 2) sg_cp_async<VB>(ring_s + k * STG + 2 * ARR, gT);
-      if (NIN >= 3) sg_cp_async<VB>(ring_s + k * STG + 3 * ARR, gU);
       gC += step;
-      gS += step;
-      if (NIN >= 2) gT += step;
-      if (NIN >= 3) gU += step;
     }
     sg_cp_commit();
   }
@@ -302,7 +298,6 @@ sgbm_path_kernel(const int16_t* __restrict__ C, int16_t* S, int16_t* S_b, const 
   for (int j = 0; j < DPL; j++) Lp[j] = 0;
   int minp = 0;
   const int PAD = SG_MAX_COST;
-  int px = x, py = y;
 
   for (int i0 = 0; i0 < n; i0 += NST) {
 #pragma unroll
@@ -310,20 +305,11 @@ sgbm_path_kernel(const int16_t* __restrict__ C, int16_t* S, int16_t* S_b, const 
       const int i = i0 + k;
       if (i >= n) break;
       sg_cp_wait<NST - 1>();                  // the group of step i (and every older one) has landed
-      int cv[DPL], sv[DPL], tv[DPL], uv[DPL];
+      int cv[DPL];
       sg_unpack<DPL>(*reinterpret_cast<const V*>(ring + k * STG), cv);
-      if (NIN >= 1) sg_unpack<DPL>(*reinterpret_cast<const V*>(ring + k * STG + ARR), sv);
-      if (NIN >= 2) sg_unpack<DPL>(*reinterpret_cast<const V*>(ring + k * STG + 2 * ARR), tv);
-      if (NIN >= 3) sg_unpack<DPL>(*reinterpret_cast<const V*>(ring + k * STG + 3 * ARR), uv);
       if (i + NST < n) {                      // refill the stage that was just read
         sg_cp_async<VB>(ring_s + k * STG, gC);
-        if (NIN >= 1) sg_cp_async<VB>(ring_s + k * STG + ARR, gS);
-        if (NIN >= 2) sg_cp_async<VB>(ring_s + k * STG + 2 * ARR, gT);
-        if (NIN >= 3) sg_cp_async<VB>(ring_s + k * STG + 3 * ARR, gU);
         gC += step;
-        gS += step;
-        if (NIN >= 2) gT += step;
-        if (NIN >= 3) gU += step;
       }
       sg_cp_commit();
       // formula 13 of the SGM paper as OpenCV evaluates it
@@ -347,54 +333,109 @@ sgbm_path_kernel(const int16_t* __restrict__ C, int16_t* S, int16_t* S_b, const 
 #pragma unroll
       for (int j = 0; j < DPL; j++) Lp[j] = Ln[j];
       minp = __reduce_min_sync(0xffffffffu, m);
+      if (NARROW) {
+        unsigned w[DPL / 4];
+#pragma unroll
+        for (int q = 0; q < DPL / 4; q++) {
+          const unsigned lo = __byte_perm((unsigned)(Ln[4 * q] - cv[4 * q]), (unsigned)(Ln[4 * q + 1] - cv[4 * q + 1]), 0x0040);
+          const unsigned hi = __byte_perm((unsigned)(Ln[4 * q + 2] - cv[4 * q + 2]), (unsigned)(Ln[4 * q + 3] - cv[4 * q + 3]), 0x0040);
+          w[q] = __byte_perm(lo, hi, 0x5410);
+        }
+        if (active) {
+          if (DPL == 4) *reinterpret_cast<unsigned*>(wS) = w[0];
+          else *reinterpret_cast<uint2*>(wS) = make_uint2(w[0], w[DPL / 4 - 1]);
+        }
+      } else {
+        if (active) *reinterpret_cast<V*>(wS) = sg_pack<DPL>(Ln);
+      }
+      wS += step * OB;
+    }
+  }
+}
 
-      int tot[DPL];
+// ------------------------------------------------------------------------------------ K_wta
+// One warp per pixel (grid-stride): S = min(32767, L0 + L1 + L2 + L3 + L4) -- every L is >= 0, so OpenCV's two
+// saturating adds collapse into this -- then winner-take-all (first minimum), uniqueness test, the neighbours of the
+// minimum for the sub-pixel step, and the right-view disparity (atomicMin on (cost << 16 | 65535 - x)).
+template <int DPL, bool NARROW>
+__device__ __forceinline__ void sg_add_volume(const void* __restrict__ vol, size_t off, int* tot) {
+  if (NARROW) {
+    unsigned w[DPL / 4];
+    if (DPL == 4) {
+      w[0] = __ldg(reinterpret_cast<const unsigned*>(reinterpret_cast<const unsigned char*>(vol) + off));
+    } else {
+      const uint2 t = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned char*>(vol) + off));
+      w[0] = t.x;
+      w[DPL / 4 - 1] = t.y;
+    }
+#pragma unroll
+    for (int j = 0; j < DPL; j++) tot[j] += (int)((w[j / 4] >> (8 * (j & 3))) & 0xFFu);
+  } else {
+    int t[DPL];
+    sg_unpack<DPL>(__ldg(reinterpret_cast<const typename SgVec<DPL>::T*>(reinterpret_cast<const int16_t*>(vol) + off)), t);
+#pragma unroll
+    for (int j = 0; j < DPL; j++) tot[j] += t[j];
+  }
+}
+
+template <int DPL, bool NARROW>
+__global__ void __launch_bounds__(256)
+sgbm_wta_kernel(const int16_t* __restrict__ C, const void* __restrict__ v0, const void* __restrict__ v1,
+                const void* __restrict__ v2, const void* __restrict__ v3, const void* __restrict__ v4, int W1, int H, int D,
+                SgWta wta) {
+  using V = typename SgVec<DPL>::T;
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const bool active = DPL * lane < D;
+  const int npix = W1 * H;
+  for (int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < npix; q += warps) {
+    const size_t off = (size_t)q * D + (active ? DPL * lane : 0);
+    int tot[DPL];
+    if (NARROW) {       // the volumes hold L - C: S = 5 C + their sum
+      sg_unpack<DPL>(__ldg(reinterpret_cast<const V*>(C + off)), tot);
+#pragma unroll
+      for (int j = 0; j < DPL; j++) tot[j] *= 5;
+    } else {
+#pragma unroll
+      for (int j = 0; j < DPL; j++) tot[j] = 0;
+    }
+    sg_add_volume<DPL, NARROW>(v0, off, tot);
+    sg_add_volume<DPL, NARROW>(v1, off, tot);
+    sg_add_volume<DPL, NARROW>(v2, off, tot);
+    sg_add_volume<DPL, NARROW>(v3, off, tot);
+    sg_add_volume<DPL, NARROW>(v4, off, tot);
+#pragma unroll
+    for (int j = 0; j < DPL; j++) tot[j] = min(tot[j], SG_MAX_COST);
+    int mykey = (tot[0] << 8) | (DPL * lane);
+#pragma unroll
+    for (int j = 1; j < DPL; j++) mykey = min(mykey, (tot[j] << 8) | (DPL * lane + j));
+    if (!active) mykey = 0x7fffffff;
+    const int key = __reduce_min_sync(0xffffffffu, mykey);
+    const int e_lo = __shfl_up_sync(0xffffffffu, tot[DPL - 1], 1);     // S[d - 1] of this lane's first d
+    const int e_hi = __shfl_down_sync(0xffffffffu, tot[0], 1);         // S[d + 1] of this lane's last d
+    const int minS = key >> 8, bd = key & 255;
+    bool rej = false;
+    if (wta.uniq > 0) {
+      bool pr = false;
+#pragma unroll
+      for (int j = 0; j < DPL; j++)
+        pr |= (tot[j] * (100 - wta.uniq) < minS * 100) && (abs(bd - (DPL * lane + j)) > 1);
+      rej = __any_sync(0xffffffffu, pr && active);
+    }
+    if (mykey == key && !rej) {             // the lane that holds the minimum finishes the pixel
+      int sm = 0, sp = 0;
 #pragma unroll
       for (int j = 0; j < DPL; j++) {
-        int t = Ln[j];
-        if (NIN >= 1) t += sv[j];
-        if (NIN >= 2) t += tv[j];
-        if (NIN >= 3) t += uv[j];
-        tot[j] = NIN >= 1 ? min(t, SG_MAX_COST) : t;
+        const bool hit = ((tot[j] << 8) | (DPL * lane + j)) == key;    // exactly one j of this lane
+        sm = hit ? (j > 0 ? tot[j - 1] : e_lo) : sm;
+        sp = hit ? (j < DPL - 1 ? tot[j + 1] : e_hi) : sp;
       }
-      if (!WTA) {
-        if (active) *reinterpret_cast<V*>(wS) = sg_pack<DPL>(tot);
-        wS += step;
-      } else {
-        // winner-take-all over the final S of this pixel: first minimum; the lane that holds it finishes the pixel
-        int mykey = (tot[0] << 8) | (DPL * lane);
-#pragma unroll
-        for (int j = 1; j < DPL; j++) mykey = min(mykey, (tot[j] << 8) | (DPL * lane + j));
-        if (!active) mykey = 0x7fffffff;
-        const int key = __reduce_min_sync(0xffffffffu, mykey);
-        const int e_lo = __shfl_up_sync(0xffffffffu, tot[DPL - 1], 1);     // S[d - 1] of this lane's first d
-        const int e_hi = __shfl_down_sync(0xffffffffu, tot[0], 1);         // S[d + 1] of this lane's last d
-        const int minS = key >> 8, bd = key & 255;
-        bool rej = false;
-        if (wta.uniq > 0) {
-          bool pr = false;
-#pragma unroll
-          for (int j = 0; j < DPL; j++)
-            pr |= (tot[j] * (100 - wta.uniq) < minS * 100) && (abs(bd - (DPL * lane + j)) > 1);
-          rej = __any_sync(0xffffffffu, pr && active);
-        }
-        if (mykey == key && !rej) {
-          int sm = 0, sp = 0;
-#pragma unroll
-          for (int j = 0; j < DPL; j++) {
-            const bool hit = ((tot[j] << 8) | (DPL * lane + j)) == key;    // exactly one j of this lane
-            sm = hit ? (j > 0 ? tot[j - 1] : e_lo) : sm;
-            sp = hit ? (j < DPL - 1 ? tot[j + 1] : e_hi) : sp;
-          }
-          const int x2 = px + wta.minX1 - bd - wta.minD;
-          if (minS < SG_MAX_COST)
-            atomicMin(wta.key2 + (size_t)py * wta.w + x2, ((unsigned)minS << 16) | (unsigned)(0xFFFF - px));
-          wta.rec[(size_t)py * wta.w + px + wta.minX1] =
-              make_uint2((unsigned)bd | ((unsigned)minS << 16), (unsigned)sm | ((unsigned)sp << 16));
-        }
-        px += sx;
-        py += sy;
-      }
+      const int py = q / W1, px = q - py * W1;
+      const int x2 = px + wta.minX1 - bd - wta.minD;
+      if (minS < SG_MAX_COST)
+        atomicMin(wta.key2 + (size_t)py * wta.w + x2, ((unsigned)minS << 16) | (unsigned)(0xFFFF - px));
+      wta.rec[(size_t)py * wta.w + px + wta.minX1] =
+          make_uint2((unsigned)bd | ((unsigned)minS << 16), (unsigned)sm | ((unsigned)sp << 16));
     }
   }
 }
@@ -692,7 +733,9 @@ static int sgbm_ensure(vo_ctx* c, int w, int h, const SgResolved& r, bool need_b
     c->sgbm = s;
     for (auto& e : s->ev) VO_CUDA(cudaEventCreate(&e));
     VO_CUDA(cudaEventCreateWithFlags(&s->ev_h, cudaEventDisableTiming));
+    VO_CUDA(cudaEventCreateWithFlags(&s->ev_d, cudaEventDisableTiming));
     VO_CUDA(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
+    VO_CUDA(cudaStreamCreateWithFlags(&s->stream3, cudaStreamNonBlocking));
     VO_CUDA(cudaMalloc(&s->d_n, 4 * sizeof(int)));
     VO_CUDA(cudaMalloc(&s->dQ, 16 * sizeof(double)));
   }
@@ -710,7 +753,7 @@ static int sgbm_ensure(vo_ctx* c, int w, int h, const SgResolved& r, bool need_b
     VO_CUDA(cudaMalloc(&s->hsum, cost * 2 + 64));
     VO_CUDA(cudaMalloc(&s->C, cost * 2 + 64));
     VO_CUDA(cudaMalloc(&s->S, cost * 2 + 64));
-    VO_CUDA(cudaMalloc(&s->SB, cost * 2 + 64));
+    for (int k = 0; k < 3; k++) VO_CUDA(cudaMalloc(&s->vol[k], cost * 2 + 64));
     VO_CUDA(cudaMalloc(&s->key2, npx * sizeof(unsigned)));
     VO_CUDA(cudaMalloc(&s->rec, npx * sizeof(uint2)));
     for (int k = 0; k < 3; k++) VO_CUDA(cudaMalloc(&s->disp[k], npx * sizeof(int16_t)));
@@ -734,39 +777,40 @@ static int sgbm_ensure(vo_ctx* c, int w, int h, const SgResolved& r, bool need_b
   return VO_OK;
 }
 
-template <int DPL, int NIN, bool WTA>
-static int sgbm_path_launch(vo_ctx* c, cudaStream_t st, const int16_t* C, int16_t* S, int16_t* S_b, const int16_t* I1,
-                            const int16_t* I2, const SgResolved& r, int h, int dir_a, int dir_b, int ndirs, int npaths,
-                            const SgWta& wta) {
-  const size_t smem = (size_t)SG_WPB * SgVec<DPL>::STAGES * (1 + NIN) * 32 * 2 * DPL;
-  static bool attr_set = false;
-  if (!attr_set) {
-    VO_CUDA(cudaFuncSetAttribute(sgbm_path_kernel<DPL, NIN, WTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+template <int DPL, bool NARROW>
+static int sgbm_path_launch(vo_ctx* c, cudaStream_t st, const int16_t* C, void* out_a, void* out_b, const SgResolved& r,
+                            int h, int dir_a, int dir_b, int ndirs, int npaths) {
+  const size_t smem = (size_t)SG_WPB * SgVec<DPL>::STAGES * 32 * 2 * DPL;
   c->launch_count++;
-  sgbm_path_kernel<DPL, NIN, WTA><<<dim3(div_up(npaths, SG_WPB), ndirs), SG_WPB * 32, smem, st>>>(
-      C, S, S_b, I1, I2, r.W1, h, r.D, r.P1, r.P2, dir_a, dir_b, npaths, wta);
+  sgbm_path_kernel<DPL, NARROW><<<dim3(div_up(npaths, SG_WPB), ndirs), SG_WPB * 32, smem, st>>>(
+      C, out_a, out_b, r.W1, h, r.D, r.P1, r.P2, dir_a, dir_b, npaths);
   return VO_OK;
 }
 
-// The horizontal paths are the long ones (W1 steps, only 2 * h warps): they run on a second stream into their own
-// volumes (SA = L0, SB = L4) underneath the two diagonal launches (S = L1, then S += L3); the vertical launch then
-// adds S + SA + SB to its own L2 and finishes the pixel.
-template <int DPL>
+// All five directions run at once, each into its own volume: the horizontal pair (the long paths: W1 steps, only
+// 2 * h warps) on a second stream, the diagonal pair on a third, the vertical direction on the main stream; none of
+// them alone fills the machine (a path is one warp), together they stream C five times at HBM speed.  The
+// winner-take-all kernel then sums the five volumes per pixel.
+template <int DPL, bool NARROW>
 static int sgbm_paths(vo_ctx* c, Sgbm* s, const SgResolved& r, int h, const SgWta& wta) {
-  int16_t* SA = reinterpret_cast<int16_t*>(s->hsum);   // hsum is dead once C exists
-  int16_t* SB = s->SB;
+  void* L0 = s->hsum;   // hsum is dead once C exists
   const int nd = r.W1 + h - 1;
   VO_CUDA(cudaStreamWaitEvent(s->stream2, s->ev[3], 0));
-  VO_TRY((sgbm_path_launch<DPL, 0, false>(c, s->stream2, s->C, SA, SB, nullptr, nullptr, r, h, 0, 4, 2, h, wta)));
+  VO_CUDA(cudaStreamWaitEvent(s->stream3, s->ev[3], 0));
+  VO_TRY((sgbm_path_launch<DPL, NARROW>(c, s->stream2, s->C, L0, s->vol[0], r, h, 0, 4, 2, h)));
   VO_CUDA(cudaEventRecord(s->ev_h, s->stream2));
-  VO_TRY((sgbm_path_launch<DPL, 0, false>(c, c->stream, s->C, s->S, nullptr, nullptr, nullptr, r, h, 1, 1, 1, nd, wta)));
-  VO_TRY((sgbm_path_launch<DPL, 1, false>(c, c->stream, s->C, s->S, nullptr, nullptr, nullptr, r, h, 3, 3, 1, nd, wta)));
+  VO_TRY((sgbm_path_launch<DPL, NARROW>(c, s->stream3, s->C, s->vol[1], s->vol[2], r, h, 1, 3, 2, nd)));
+  VO_CUDA(cudaEventRecord(s->ev_d, s->stream3));
+  VO_TRY((sgbm_path_launch<DPL, NARROW>(c, c->stream, s->C, s->S, nullptr, r, h, 2, 2, 1, r.W1)));
   VO_CUDA(cudaEventRecord(s->ev[4], c->stream));
   VO_CUDA(cudaStreamWaitEvent(c->stream, s->ev_h, 0));
+  VO_CUDA(cudaStreamWaitEvent(c->stream, s->ev_d, 0));
   VO_CUDA(cudaEventRecord(s->ev[5], c->stream));
-  VO_TRY((sgbm_path_launch<DPL, 3, true>(c, c->stream, s->C, s->S, nullptr, SA, SB, r, h, 2, 2, 1, r.W1, wta)));
+  {
+    LaunchScope ls(c, VO_K_MISC);
+    sgbm_wta_kernel<DPL, NARROW><<<c->sm_count * 8, 256, 0, c->stream>>>(s->C, L0, s->vol[0], s->vol[1], s->vol[2], s->S, r.W1,
+                                                                      h, r.D, wta);
+  }
   VO_CUDA(cudaGetLastError());
   return VO_OK;
 }
@@ -802,8 +846,15 @@ static int sgbm_run(vo_ctx* c, int w, int h, const vo_sgbm_params* p, const SgRe
     }
     VO_CUDA(cudaEventRecord(s->ev[3], c->stream));
     SgWta wta{s->rec, s->key2, w, r.minD, r.minX1, r.uniq};
-    if (r.D <= 128) VO_TRY(sgbm_paths<4>(c, s, r, h, wta));
-    else VO_TRY(sgbm_paths<8>(c, s, r, h, wta));
+    static const bool wide = getenv("VO_B200_SGBM_WIDE") != nullptr;   // force the int16 volumes (test switch)
+    const bool narrow = r.P2 <= 255 && !wide;
+    if (r.D <= 128) {
+      if (narrow) VO_TRY((sgbm_paths<4, true>(c, s, r, h, wta)));
+      else VO_TRY((sgbm_paths<4, false>(c, s, r, h, wta)));
+    } else {
+      if (narrow) VO_TRY((sgbm_paths<8, true>(c, s, r, h, wta)));
+      else VO_TRY((sgbm_paths<8, false>(c, s, r, h, wta)));
+    }
   } else {
     for (int k = 2; k <= 5; k++) VO_CUDA(cudaEventRecord(s->ev[k], c->stream));
   }

@@ -172,7 +172,7 @@ class VisualFrontEnd:
     def sgbm_timing(self):
         ms = (C.c_float * 9)()
         check(self.lib.vo_sgbm_timing(self.h, ms))
-        names = ("upload", "prefilter", "cost_volume", "paths_diagonal", "paths_horizontal_tail", "path_vertical_wta",
+        names = ("upload", "prefilter", "cost_volume", "paths_vertical", "paths_other_tail", "wta",
                  "lrcheck_median", "speckle", "download")
         return dict(zip(names, [float(v) for v in ms]))
 

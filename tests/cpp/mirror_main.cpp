@@ -72,6 +72,21 @@ int main(int argc, char** argv) {
     write_vec(dir + "/moved.bin", moved);
     std::printf("grid %zu stereo %zu tracked %zu inliers %zu keyframe %zu shutdown %d\n", grid.size(), ref2d.size(),
                 trk2d.size(), inliers.size(), kf2d.size(), (int)slam.SHUTDOWN_FLAG);
+    if (cn == 3) {
+      // the dense-stereo executable's loop body (reference src/StereoCV.cpp:254-259): stereoMatch -> reprojectDisparity
+      vo::StereoProcess sp(slam.ctx());
+      const vo::BgrImage bl{L0.data(), h, w, 3 * w}, br{R0.data(), h, w, 3 * w};
+      vo::Disparity disp = sp.stereoMatch(bl, br);
+      std::vector<vo::Point3f> cloud, colors;
+      sp.reprojectDisparity(disp, cloud, colors);            // t = +baseline: the reference's Q, no point passes
+      const size_t n_ref = cloud.size();
+      sp.baseline = -sp.baseline;
+      sp.reprojectDisparity(disp, cloud, colors);
+      write_vec(dir + "/disp.bin", disp.data);
+      write_vec(dir + "/cloud.bin", cloud);
+      write_vec(dir + "/colors.bin", colors);
+      std::printf("sgbm cloud %zu (reference Q: %zu)\n", cloud.size(), n_ref);
+    }
   } catch (const vo::Error& e) {
     std::fprintf(stderr, "vo::Error %d: %s\n", e.code, e.what());
     return 4;

@@ -80,3 +80,14 @@ def test_cpp_mirror_matches_ctypes_path_and_oracle(tmp_path, cn):
     # (3) keyframe insertion: world points = pose * camera points (src/keyFrameManagement.cpp:20-30)
     assert len(kf2d) == len(kf3d) == len(moved) > 100
     assert np.array_equal(kf3d, moved)
+    # (4) dense stereo through vo::StereoProcess (BGR frames only): stereoMatch + reprojectDisparity == cv2
+    if cn == 3:
+        from oracle import sgbm
+        disp = rd("disp.bin", np.int16, 1).reshape(376, 1241)
+        gl, gr = (cv2.cvtColor(frames[k], cv2.COLOR_BGR2GRAY) for k in ("L0", "R0"))
+        assert np.array_equal(disp, sgbm.sgbm_call_through(gl, gr))
+        assert "(reference Q: 0)" in r.stdout
+        Q = sgbm.rectify_q(718.856, 718.856, 607.1928, 185.2157, -0.5707, 1241, 376)
+        pts, idx = sgbm.reproject_call_through(disp, Q)
+        assert np.array_equal(rd("cloud.bin", np.float32, 3), pts)
+        assert np.array_equal(rd("colors.bin", np.float32, 3), frames["L0"].reshape(-1, 3)[idx].astype(np.float32))
