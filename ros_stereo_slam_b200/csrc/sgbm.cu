@@ -357,24 +357,30 @@ sgbm_path_kernel(const int16_t* __restrict__ C, void* __restrict__ out_a, void* 
 // One warp per pixel (grid-stride): S = min(32767, L0 + L1 + L2 + L3 + L4) -- every L is >= 0, so OpenCV's two
 // saturating adds collapse into this -- then winner-take-all (first minimum), uniqueness test, the neighbours of the
 // minimum for the sub-pixel step, and the right-view disparity (atomicMin on (cost << 16 | 65535 - x)).
-template <int DPL, bool NARROW>
-__device__ __forceinline__ void sg_add_volume(const void* __restrict__ vol, size_t off, int* tot) {
-  if (NARROW) {
-    unsigned w[DPL / 4];
-    if (DPL == 4) {
-      w[0] = __ldg(reinterpret_cast<const unsigned*>(reinterpret_cast<const unsigned char*>(vol) + off));
-    } else {
-      const uint2 t = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned char*>(vol) + off));
-      w[0] = t.x;
-      w[DPL / 4 - 1] = t.y;
-    }
+// wide volumes: tot += L (int16)
+template <int DPL>
+__device__ __forceinline__ void sg_add_wide(const void* __restrict__ vol, size_t off, int* tot) {
+  int t[DPL];
+  sg_unpack<DPL>(__ldg(reinterpret_cast<const typename SgVec<DPL>::T*>(reinterpret_cast<const int16_t*>(vol) + off)), t);
 #pragma unroll
-    for (int j = 0; j < DPL; j++) tot[j] += (int)((w[j / 4] >> (8 * (j & 3))) & 0xFFu);
+  for (int j = 0; j < DPL; j++) tot[j] += t[j];
+}
+// narrow volumes: four bytes are widened to two u16x2 words by PRMT and added as plain 32-bit integers (five bytes
+// sum to at most 1275, no carry between the halves)
+template <int DPL>
+__device__ __forceinline__ void sg_add_narrow(const void* __restrict__ vol, size_t off, unsigned* acc) {
+  unsigned w[DPL / 4];
+  if (DPL == 4) {
+    w[0] = __ldg(reinterpret_cast<const unsigned*>(reinterpret_cast<const unsigned char*>(vol) + off));
   } else {
-    int t[DPL];
-    sg_unpack<DPL>(__ldg(reinterpret_cast<const typename SgVec<DPL>::T*>(reinterpret_cast<const int16_t*>(vol) + off)), t);
+    const uint2 t = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned char*>(vol) + off));
+    w[0] = t.x;
+    w[DPL / 4 - 1] = t.y;
+  }
 #pragma unroll
-    for (int j = 0; j < DPL; j++) tot[j] += t[j];
+  for (int q = 0; q < DPL / 4; q++) {
+    acc[2 * q] += __byte_perm(w[q], 0u, 0x4140);
+    acc[2 * q + 1] += __byte_perm(w[q], 0u, 0x4342);
   }
 }
 
@@ -392,18 +398,30 @@ sgbm_wta_kernel(const int16_t* __restrict__ C, const void* __restrict__ v0, cons
     const size_t off = (size_t)q * D + (active ? DPL * lane : 0);
     int tot[DPL];
     if (NARROW) {       // the volumes hold L - C: S = 5 C + their sum
-      sg_unpack<DPL>(__ldg(reinterpret_cast<const V*>(C + off)), tot);
+      unsigned acc[DPL / 2];
 #pragma unroll
-      for (int j = 0; j < DPL; j++) tot[j] *= 5;
+      for (int k = 0; k < DPL / 2; k++) acc[k] = 0u;
+      sg_add_narrow<DPL>(v0, off, acc);
+      sg_add_narrow<DPL>(v1, off, acc);
+      sg_add_narrow<DPL>(v2, off, acc);
+      sg_add_narrow<DPL>(v3, off, acc);
+      sg_add_narrow<DPL>(v4, off, acc);
+      int cv[DPL];
+      sg_unpack<DPL>(__ldg(reinterpret_cast<const V*>(C + off)), cv);
+#pragma unroll
+      for (int k = 0; k < DPL / 2; k++) {
+        tot[2 * k] = 5 * cv[2 * k] + (int)(acc[k] & 0xFFFFu);
+        tot[2 * k + 1] = 5 * cv[2 * k + 1] + (int)(acc[k] >> 16);
+      }
     } else {
 #pragma unroll
       for (int j = 0; j < DPL; j++) tot[j] = 0;
+      sg_add_wide<DPL>(v0, off, tot);
+      sg_add_wide<DPL>(v1, off, tot);
+      sg_add_wide<DPL>(v2, off, tot);
+      sg_add_wide<DPL>(v3, off, tot);
+      sg_add_wide<DPL>(v4, off, tot);
     }
-    sg_add_volume<DPL, NARROW>(v0, off, tot);
-    sg_add_volume<DPL, NARROW>(v1, off, tot);
-    sg_add_volume<DPL, NARROW>(v2, off, tot);
-    sg_add_volume<DPL, NARROW>(v3, off, tot);
-    sg_add_volume<DPL, NARROW>(v4, off, tot);
 #pragma unroll
     for (int j = 0; j < DPL; j++) tot[j] = min(tot[j], SG_MAX_COST);
     int mykey = (tot[0] << 8) | (DPL * lane);
