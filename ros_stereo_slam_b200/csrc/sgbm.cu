@@ -147,25 +147,36 @@ __device__ __forceinline__ int sg_bt(uchar4 u, uchar4 v, int shift) {
 __global__ void __launch_bounds__(256)
 sgbm_hsum_kernel(const uchar4* __restrict__ pl, int w, int h, int W1, int D, int minD, int minX1, int R,
                  uint16_t* __restrict__ hsum) {
-  extern __shared__ uint16_t sg_pix[];   // [(SG_TX + 2R)][D]
+  extern __shared__ __align__(16) unsigned char sg_smem[];
   const int y = blockIdx.y;
   const int x0 = blockIdx.x * SG_TX;
   const int ncol = SG_TX + 2 * R;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint16_t* sg_pix = reinterpret_cast<uint16_t*>(sg_smem);                       // [ncol][D] pixel costs
+  uchar4* sg_right = reinterpret_cast<uchar4*>(sg_smem + (size_t)ncol * D * 2);  // [2 planes][ncol + D - 1] right-image strip
   const uchar4* L0 = pl + ((size_t)0 * h + y) * w;   // left filtered
   const uchar4* L1 = pl + ((size_t)1 * h + y) * w;   // left raw
   const uchar4* R0 = pl + ((size_t)2 * h + y) * w;   // right filtered
   const uchar4* R1 = pl + ((size_t)3 * h + y) * w;   // right raw
-  // pixel costs of the strip + halo: a warp per column, the lanes over the disparities (the right-image reads of a
-  // warp are 32 consecutive pixels)
+  // the strip of the right image this CTA searches: x2 = x1 - d for every column of the strip (+ halo) and every d
+  const int x1_lo = min(max(x0 - R, 0), W1 - 1) + minX1;
+  const int x2_base = x1_lo - minD - (D - 1);
+  const int nright = ncol + D - 1;
+  for (int i = threadIdx.x; i < nright; i += blockDim.x) {
+    const int x2 = min(x2_base + i, w - 1);          // entries beyond the last column are never used
+    sg_right[i] = __ldg(R0 + x2);
+    sg_right[nright + i] = __ldg(R1 + x2);
+  }
+  __syncthreads();
+  // pixel costs of the strip + halo: a warp per column, the lanes over the disparities
   for (int xi = wid; xi < ncol; xi += 8) {
     const int xw = min(max(x0 - R + xi, 0), W1 - 1);   // columns replicate at the border of the computed range
     const int x1 = xw + minX1;
     const uchar4 u0 = __ldg(L0 + x1), u1 = __ldg(L1 + x1);
-    const uchar4* r0 = R0 + (x1 - minD);
-    const uchar4* r1 = R1 + (x1 - minD);
+    const uchar4* r0 = sg_right + (x1 - minD - x2_base);
+    const uchar4* r1 = r0 + nright;
     uint16_t* dst = sg_pix + xi * D;
-    for (int dd = lane; dd < D; dd += 32) dst[dd] = (uint16_t)(sg_bt(u0, __ldg(r0 - dd), 0) + sg_bt(u1, __ldg(r1 - dd), 2));
+    for (int dd = lane; dd < D; dd += 32) dst[dd] = (uint16_t)(sg_bt(u0, r0[-dd], 0) + sg_bt(u1, r1[-dd], 2));
   }
   __syncthreads();
   // box width: a warp owns SG_TX / 8 consecutive columns and slides the sum along them
@@ -174,12 +185,13 @@ sgbm_hsum_kernel(const uchar4* __restrict__ pl, int w, int h, int W1, int D, int
   const int xo = wid * CPW;
   for (int dd = lane; dd < D; dd += 32) {
     const uint16_t* px = sg_pix + xo * D + dd;
+    uint16_t* hp = hsum + ((size_t)y * W1 + x0 + xo) * D + dd;
     int sum = 0;
     for (int k = 0; k < nb; k++) sum += px[k * D];
 #pragma unroll
     for (int cI = 0; cI < CPW; cI++) {
-      const int x = x0 + xo + cI;
-      if (x < W1) hsum[((size_t)y * W1 + x) * D + dd] = (uint16_t)sum;
+      if (x0 + xo + cI < W1) *hp = (uint16_t)sum;
+      hp += D;
       if (cI + 1 < CPW) sum += (int)px[(cI + nb) * D] - (int)px[cI * D];
     }
   }
@@ -357,73 +369,101 @@ sgbm_path_kernel(const int16_t* __restrict__ C, void* __restrict__ out_a, void* 
 // One warp per pixel (grid-stride): S = min(32767, L0 + L1 + L2 + L3 + L4) -- every L is >= 0, so OpenCV's two
 // saturating adds collapse into this -- then winner-take-all (first minimum), uniqueness test, the neighbours of the
 // minimum for the sub-pixel step, and the right-view disparity (atomicMin on (cost << 16 | 65535 - x)).
-// wide volumes: tot += L (int16)
-template <int DPL>
-__device__ __forceinline__ void sg_add_wide(const void* __restrict__ vol, size_t off, int* tot) {
-  int t[DPL];
-  sg_unpack<DPL>(__ldg(reinterpret_cast<const typename SgVec<DPL>::T*>(reinterpret_cast<const int16_t*>(vol) + off)), t);
+constexpr int SG_WTA_PIX = 8;      // consecutive pixels of a row per warp of the WTA kernel
+
+template <int DPL, bool NARROW>
+struct SgWtaIn {                   // what one lane loads for one pixel: C (narrow only) and the five volumes
+  typename SgVec<DPL>::T c;
+  unsigned n[5][DPL / 4];          // narrow: 4 costs per word
+  typename SgVec<DPL>::T w[5];     // wide: int16 costs
+};
+
+template <int DPL, bool NARROW>
+__device__ __forceinline__ void sg_wta_load(SgWtaIn<DPL, NARROW>& in, const int16_t* __restrict__ C, const void* const* vol,
+                                            size_t off) {
+  using V = typename SgVec<DPL>::T;
+  if (NARROW) {
+    in.c = __ldg(reinterpret_cast<const V*>(C + off));
 #pragma unroll
-  for (int j = 0; j < DPL; j++) tot[j] += t[j];
-}
-// narrow volumes: four bytes are widened to two u16x2 words by PRMT and added as plain 32-bit integers (five bytes
-// sum to at most 1275, no carry between the halves)
-template <int DPL>
-__device__ __forceinline__ void sg_add_narrow(const void* __restrict__ vol, size_t off, unsigned* acc) {
-  unsigned w[DPL / 4];
-  if (DPL == 4) {
-    w[0] = __ldg(reinterpret_cast<const unsigned*>(reinterpret_cast<const unsigned char*>(vol) + off));
+    for (int v = 0; v < 5; v++) {
+      const unsigned char* p = reinterpret_cast<const unsigned char*>(vol[v]) + off;
+      if (DPL == 4) {
+        in.n[v][0] = __ldg(reinterpret_cast<const unsigned*>(p));
+      } else {
+        const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+        in.n[v][0] = t.x;
+        in.n[v][DPL / 4 - 1] = t.y;
+      }
+    }
   } else {
-    const uint2 t = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned char*>(vol) + off));
-    w[0] = t.x;
-    w[DPL / 4 - 1] = t.y;
-  }
 #pragma unroll
-  for (int q = 0; q < DPL / 4; q++) {
-    acc[2 * q] += __byte_perm(w[q], 0u, 0x4140);
-    acc[2 * q + 1] += __byte_perm(w[q], 0u, 0x4342);
+    for (int v = 0; v < 5; v++) in.w[v] = __ldg(reinterpret_cast<const V*>(reinterpret_cast<const int16_t*>(vol[v]) + off));
   }
 }
 
+// S of one pixel: narrow volumes hold L - C, so S = 5 C + their sum; four bytes are widened to two u16x2 words by PRMT
+// and added as plain 32-bit integers (five bytes sum to at most 1275, no carry between the halves)
+template <int DPL, bool NARROW>
+__device__ __forceinline__ void sg_wta_sum(const SgWtaIn<DPL, NARROW>& in, int* tot) {
+  if (NARROW) {
+    unsigned acc[DPL / 2];
+#pragma unroll
+    for (int k = 0; k < DPL / 2; k++) acc[k] = 0u;
+#pragma unroll
+    for (int v = 0; v < 5; v++) {
+#pragma unroll
+      for (int q = 0; q < DPL / 4; q++) {
+        acc[2 * q] += __byte_perm(in.n[v][q], 0u, 0x4140);
+        acc[2 * q + 1] += __byte_perm(in.n[v][q], 0u, 0x4342);
+      }
+    }
+    int cv[DPL];
+    sg_unpack<DPL>(in.c, cv);
+#pragma unroll
+    for (int k = 0; k < DPL / 2; k++) {
+      tot[2 * k] = min(5 * cv[2 * k] + (int)(acc[k] & 0xFFFFu), SG_MAX_COST);
+      tot[2 * k + 1] = min(5 * cv[2 * k + 1] + (int)(acc[k] >> 16), SG_MAX_COST);
+    }
+  } else {
+    int t[DPL];
+#pragma unroll
+    for (int j = 0; j < DPL; j++) tot[j] = 0;
+#pragma unroll
+    for (int v = 0; v < 5; v++) {
+      sg_unpack<DPL>(in.w[v], t);
+#pragma unroll
+      for (int j = 0; j < DPL; j++) tot[j] += t[j];
+    }
+#pragma unroll
+    for (int j = 0; j < DPL; j++) tot[j] = min(tot[j], SG_MAX_COST);
+  }
+}
+
+// A warp owns SG_WTA_PIX consecutive pixels of row blockIdx.y; the loads of the next pixel are issued before the
+// current one is reduced.
 template <int DPL, bool NARROW>
 __global__ void __launch_bounds__(256)
 sgbm_wta_kernel(const int16_t* __restrict__ C, const void* __restrict__ v0, const void* __restrict__ v1,
                 const void* __restrict__ v2, const void* __restrict__ v3, const void* __restrict__ v4, int W1, int H, int D,
                 SgWta wta) {
-  using V = typename SgVec<DPL>::T;
   const int lane = threadIdx.x & 31;
-  const int warps = (gridDim.x * blockDim.x) >> 5;
   const bool active = DPL * lane < D;
-  const int npix = W1 * H;
-  for (int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < npix; q += warps) {
-    const size_t off = (size_t)q * D + (active ? DPL * lane : 0);
+  const int py = blockIdx.y;
+  const int xa = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * SG_WTA_PIX;
+  if (xa >= W1) return;
+  const int xb = min(xa + SG_WTA_PIX, W1);
+  const void* const vol[5] = {v0, v1, v2, v3, v4};
+  size_t off = ((size_t)py * W1 + xa) * D + (active ? DPL * lane : 0);
+  SgWtaIn<DPL, NARROW> cur, nxt;
+  sg_wta_load<DPL, NARROW>(nxt, C, vol, off);
+  unsigned* key2row = wta.key2 + (size_t)py * wta.w;
+  uint2* recrow = wta.rec + (size_t)py * wta.w + wta.minX1;
+  for (int px = xa; px < xb; px++) {
+    cur = nxt;
+    off += D;
+    if (px + 1 < xb) sg_wta_load<DPL, NARROW>(nxt, C, vol, off);
     int tot[DPL];
-    if (NARROW) {       // the volumes hold L - C: S = 5 C + their sum
-      unsigned acc[DPL / 2];
-#pragma unroll
-      for (int k = 0; k < DPL / 2; k++) acc[k] = 0u;
-      sg_add_narrow<DPL>(v0, off, acc);
-      sg_add_narrow<DPL>(v1, off, acc);
-      sg_add_narrow<DPL>(v2, off, acc);
-      sg_add_narrow<DPL>(v3, off, acc);
-      sg_add_narrow<DPL>(v4, off, acc);
-      int cv[DPL];
-      sg_unpack<DPL>(__ldg(reinterpret_cast<const V*>(C + off)), cv);
-#pragma unroll
-      for (int k = 0; k < DPL / 2; k++) {
-        tot[2 * k] = 5 * cv[2 * k] + (int)(acc[k] & 0xFFFFu);
-        tot[2 * k + 1] = 5 * cv[2 * k + 1] + (int)(acc[k] >> 16);
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < DPL; j++) tot[j] = 0;
-      sg_add_wide<DPL>(v0, off, tot);
-      sg_add_wide<DPL>(v1, off, tot);
-      sg_add_wide<DPL>(v2, off, tot);
-      sg_add_wide<DPL>(v3, off, tot);
-      sg_add_wide<DPL>(v4, off, tot);
-    }
-#pragma unroll
-    for (int j = 0; j < DPL; j++) tot[j] = min(tot[j], SG_MAX_COST);
+    sg_wta_sum<DPL, NARROW>(cur, tot);
     int mykey = (tot[0] << 8) | (DPL * lane);
 #pragma unroll
     for (int j = 1; j < DPL; j++) mykey = min(mykey, (tot[j] << 8) | (DPL * lane + j));
@@ -448,12 +488,9 @@ sgbm_wta_kernel(const int16_t* __restrict__ C, const void* __restrict__ v0, cons
         sm = hit ? (j > 0 ? tot[j - 1] : e_lo) : sm;
         sp = hit ? (j < DPL - 1 ? tot[j + 1] : e_hi) : sp;
       }
-      const int py = q / W1, px = q - py * W1;
       const int x2 = px + wta.minX1 - bd - wta.minD;
-      if (minS < SG_MAX_COST)
-        atomicMin(wta.key2 + (size_t)py * wta.w + x2, ((unsigned)minS << 16) | (unsigned)(0xFFFF - px));
-      wta.rec[(size_t)py * wta.w + px + wta.minX1] =
-          make_uint2((unsigned)bd | ((unsigned)minS << 16), (unsigned)sm | ((unsigned)sp << 16));
+      if (minS < SG_MAX_COST) atomicMin(key2row + x2, ((unsigned)minS << 16) | (unsigned)(0xFFFF - px));
+      recrow[px] = make_uint2((unsigned)bd | ((unsigned)minS << 16), (unsigned)sm | ((unsigned)sp << 16));
     }
   }
 }
@@ -826,8 +863,8 @@ static int sgbm_paths(vo_ctx* c, Sgbm* s, const SgResolved& r, int h, const SgWt
   VO_CUDA(cudaEventRecord(s->ev[5], c->stream));
   {
     LaunchScope ls(c, VO_K_MISC);
-    sgbm_wta_kernel<DPL, NARROW><<<c->sm_count * 8, 256, 0, c->stream>>>(s->C, L0, s->vol[0], s->vol[1], s->vol[2], s->S, r.W1,
-                                                                      h, r.D, wta);
+    sgbm_wta_kernel<DPL, NARROW><<<dim3(div_up(r.W1, 8 * SG_WTA_PIX), h), 256, 0, c->stream>>>(s->C, L0, s->vol[0], s->vol[1],
+                                                                                             s->vol[2], s->S, r.W1, h, r.D, wta);
   }
   VO_CUDA(cudaGetLastError());
   return VO_OK;
@@ -851,7 +888,7 @@ static int sgbm_run(vo_ctx* c, int w, int h, const vo_sgbm_params* p, const SgRe
     VO_CUDA(cudaEventRecord(s->ev[2], c->stream));
     {
       LaunchScope ls(c, VO_K_MISC);
-      const size_t smem = (size_t)(SG_TX + 2 * r.R) * r.D * sizeof(uint16_t);
+      const size_t smem = (size_t)(SG_TX + 2 * r.R) * r.D * sizeof(uint16_t) + 2 * (size_t)(SG_TX + 2 * r.R + r.D - 1) * sizeof(uchar4);
       sgbm_hsum_kernel<<<dim3(div_up(r.W1, SG_TX), h), 256, smem, c->stream>>>(s->pl, w, h, r.W1, r.D, r.minD, r.minX1, r.R,
                                                                              s->hsum);
     }
