@@ -305,11 +305,16 @@ sgbm_path_kernel(const int16_t* __restrict__ C, void* __restrict__ out_a, void* 
     }
     sg_cp_commit();
   }
-  int Lp[DPL];
+  // Two disparities per register (s16x2) and per instruction: VIADDMNMX.S16x2 / VIMNMX.S16x2 (the DPX instructions).
+  // Lp[q] = (L(2q), L(2q + 1)).  The value standing in for the missing neighbours d = -1 and d = D only has to
+  // satisfy PAD + P1 >= min_k L + P2; 32767 - P1 does (C + P2 <= 32767 is checked on the host) and cannot wrap.
+  constexpr int NW = DPL / 2;
+  unsigned Lp[NW];
 #pragma unroll
-  for (int j = 0; j < DPL; j++) Lp[j] = 0;
+  for (int q = 0; q < NW; q++) Lp[q] = 0u;
   int minp = 0;
-  const int PAD = SG_MAX_COST;
+  const unsigned PAD2 = (unsigned)(SG_MAX_COST - P1) * 0x10001u;
+  const unsigned P1x2 = (unsigned)P1 * 0x10001u;
 
   for (int i0 = 0; i0 < n; i0 += NST) {
 #pragma unroll
@@ -317,48 +322,51 @@ sgbm_path_kernel(const int16_t* __restrict__ C, void* __restrict__ out_a, void* 
       const int i = i0 + k;
       if (i >= n) break;
       sg_cp_wait<NST - 1>();                  // the group of step i (and every older one) has landed
-      int cv[DPL];
-      sg_unpack<DPL>(*reinterpret_cast<const V*>(ring + k * STG), cv);
+      const V cvec = *reinterpret_cast<const V*>(ring + k * STG);
+      const unsigned* cw = reinterpret_cast<const unsigned*>(&cvec);
       if (i + NST < n) {                      // refill the stage that was just read
         sg_cp_async<VB>(ring_s + k * STG, gC);
         gC += step;
       }
       sg_cp_commit();
       // formula 13 of the SGM paper as OpenCV evaluates it
-      int left = __shfl_up_sync(0xffffffffu, Lp[DPL - 1], 1);
-      int right = __shfl_down_sync(0xffffffffu, Lp[0], 1);
-      if (lane == 0) left = PAD;
-      if (last) right = PAD;
-      const int delta = minp + P2;
-      int Ln[DPL];
+      unsigned left = __shfl_up_sync(0xffffffffu, Lp[NW - 1], 1);     // its high half is L(d - 1) of this lane's first d
+      unsigned right = __shfl_down_sync(0xffffffffu, Lp[0], 1);       // its low half is L(d + 1) of this lane's last d
+      if (lane == 0) left = PAD2;
+      if (last) right = PAD2;
+      const unsigned minp2 = (unsigned)minp * 0x10001u;
+      const unsigned delta2 = minp2 + (unsigned)P2 * 0x10001u;
+      unsigned Ln[NW], rel[NW];
 #pragma unroll
-      for (int j = 0; j < DPL; j++) {
-        const int a = Lp[j];
-        const int b = (j ? Lp[j - 1] : left) + P1;
-        const int c = (j < DPL - 1 ? Lp[j + 1] : right) + P1;
-        Ln[j] = cv[j] + min(min(a, b), min(c, delta)) - minp;
+      for (int q = 0; q < NW; q++) {
+        const unsigned lo = __byte_perm(q ? Lp[q - 1] : left, Lp[q], 0x5432);             // (L(2q - 1), L(2q))
+        const unsigned hi = __byte_perm(Lp[q], q < NW - 1 ? Lp[q + 1] : right, 0x5432);   // (L(2q + 1), L(2q + 2))
+        unsigned t = __viaddmin_s16x2(lo, P1x2, Lp[q]);
+        t = __viaddmin_s16x2(hi, P1x2, t);
+        t = __vmins2(t, delta2);
+        rel[q] = t - minp2;                   // L - C, in [0, P2] per half: no borrow between the halves
+        Ln[q] = rel[q] + cw[q];               // <= 32767 per half: no carry
       }
-      int m = Ln[0];
+      unsigned mw = Ln[0];
 #pragma unroll
-      for (int j = 1; j < DPL; j++) m = min(m, Ln[j]);
+      for (int q = 1; q < NW; q++) mw = __vmins2(mw, Ln[q]);
+      int m = min((int)(mw & 0xFFFFu), (int)(mw >> 16));
       if (!active) m = 0x7fffffff;
 #pragma unroll
-      for (int j = 0; j < DPL; j++) Lp[j] = Ln[j];
+      for (int q = 0; q < NW; q++) Lp[q] = Ln[q];
       minp = __reduce_min_sync(0xffffffffu, m);
-      if (NARROW) {
-        unsigned w[DPL / 4];
+      if (active) {
+        if (NARROW) {
+          if (DPL == 4) *reinterpret_cast<unsigned*>(wS) = __byte_perm(rel[0], rel[1], 0x6420);
+          else *reinterpret_cast<uint2*>(wS) = make_uint2(__byte_perm(rel[0], rel[1], 0x6420),
+                                                           __byte_perm(rel[NW - 2], rel[NW - 1], 0x6420));
+        } else {
+          V o;
+          unsigned* ow = reinterpret_cast<unsigned*>(&o);
 #pragma unroll
-        for (int q = 0; q < DPL / 4; q++) {
-          const unsigned lo = __byte_perm((unsigned)(Ln[4 * q] - cv[4 * q]), (unsigned)(Ln[4 * q + 1] - cv[4 * q + 1]), 0x0040);
-          const unsigned hi = __byte_perm((unsigned)(Ln[4 * q + 2] - cv[4 * q + 2]), (unsigned)(Ln[4 * q + 3] - cv[4 * q + 3]), 0x0040);
-          w[q] = __byte_perm(lo, hi, 0x5410);
+          for (int q = 0; q < NW; q++) ow[q] = Ln[q];
+          *reinterpret_cast<V*>(wS) = o;
         }
-        if (active) {
-          if (DPL == 4) *reinterpret_cast<unsigned*>(wS) = w[0];
-          else *reinterpret_cast<uint2*>(wS) = make_uint2(w[0], w[DPL / 4 - 1]);
-        }
-      } else {
-        if (active) *reinterpret_cast<V*>(wS) = sg_pack<DPL>(Ln);
       }
       wS += step * OB;
     }
