@@ -322,6 +322,9 @@ def run_ours(args):
             arr = np.frombuffer(buf, np.uint8).reshape(ncpu, 2, HEIGHT, WIDTH)
             out["cpu_baseline"] = cpu_reference([arr[i, 0] for i in range(ncpu)], [arr[i, 1] for i in range(ncpu)],
                                                 ncpu - 1)
+            # side figure, not part of the metric: the dense-stereo path on the
+            # first stereo pair of the sequence, through vo_sgbm_compute with host buffers, beside cv2 on the host
+            out["dense_stereo"] = dense_stereo_side_figure(fe, arr[0, 0].copy(), arr[0, 1].copy())
     lib.vo_free_dev(fe.h, d_frames)
     lib.vo_free_host(h_frames)
     fe.close()
@@ -331,6 +334,25 @@ def run_ours(args):
         dist.destroy_process_group()
     if out is not None:
         print(json.dumps(out))
+
+
+def dense_stereo_side_figure(fe, L, R, reps=100):
+    import cv2
+    ref = cv2.StereoSGBM_create(1, 96, 7, 24, 96, 0, 60, 0, 3000, 5)      # reference src/StereoCV.cpp:39-50
+    t0 = time.perf_counter()
+    want = ref.compute(L, R)
+    t_cpu = time.perf_counter() - t0
+    got = fe.stereoMatch(L, R)
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        fe.stereoMatch(L, R)
+        ts.append(time.perf_counter() - t0)
+    return {"api": "vo_sgbm_compute(host left, host right) -> host int16 disparity, StereoSGBM::create(1, 96, 7, 24, 96, 0, "
+                   "60, 0, 3000, 5)", "ms_per_pair": round(1e3 * float(np.median(ts[reps // 2:])), 4),
+            "cv2_ms_per_pair": round(1e3 * t_cpu, 1), "cores": len(os.sched_getaffinity(0)),
+            "bit_identical_to_cv2": bool(np.array_equal(got, want)),
+            "device_stage_ms": {k: round(v, 4) for k, v in fe.sgbm_timing().items()}}
 
 
 # ----------------------------------------------------------------------------- CPU reference

@@ -148,3 +148,39 @@ def test_rejected_arguments(fe):
                dict(block_size=11, p2=30000)):
         with pytest.raises(VoError):
             fe.stereoMatch(L, R, **kw)
+
+
+def test_random_parameter_fuzz_matches_cv2(fe):
+    """40 random (size, parameter) draws inside the supported range, random texture with a random true disparity
+    field: the disparity must equal cv2's bit for bit every time."""
+    import cv2
+    from oracle import sgbm
+    rng = np.random.default_rng(2024)
+    done = 0
+    while done < 40:
+        D = int(rng.choice([16, 32, 48, 64, 96, 128, 160, 256]))
+        min_d = int(rng.integers(-24, 24))
+        block = int(rng.choice([1, 3, 5, 7, 9, 11]))
+        cap = int(rng.integers(0, 127))
+        P1 = int(rng.integers(1, 200))
+        P2 = int(rng.integers(P1 + 1, 2000))
+        ftzero = max(cap, 15) | 1
+        if block * block * (2 * ftzero + 63) + P2 > 32767:
+            continue
+        w = int(rng.integers(max(min_d + D, 0) + block // 2 + 2, max(min_d + D, 0) + 260))
+        h = int(rng.integers(8, 70))
+        kw = dict(num_disp=D, min_disp=min_d, block=block, P1=P1, P2=P2, pre_filter_cap=cap,
+                  disp12_max_diff=int(rng.integers(-1, 4)), uniqueness=int(rng.integers(0, 25)),
+                  speckle_window=int(rng.choice([0, 10, 60, 400])), speckle_range=int(rng.integers(1, 5)))
+        tex = cv2.GaussianBlur(rng.integers(0, 256, (h, w + 300)).astype(np.uint8), (0, 0), float(rng.uniform(0.6, 2.5)))
+        shift = int(rng.integers(max(min_d, -20), max(min_d, -20) + min(D, 40)))
+        L = np.ascontiguousarray(tex[:, 150:150 + w])
+        R = np.ascontiguousarray(tex[:, 150 + shift:150 + shift + w])
+        R[h // 2:] = np.roll(R[h // 2:], 3, 1)                     # a second disparity layer
+        try:
+            want = sgbm.sgbm_call_through(L, R, **kw)
+        except cv2.error:
+            continue
+        got = fe.stereoMatch(L, R, **_abi(kw))
+        assert np.array_equal(got, want), (kw, w, h)
+        done += 1
