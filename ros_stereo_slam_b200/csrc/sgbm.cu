@@ -1143,12 +1143,39 @@ int vo_reproject_disparity(vo_ctx* c, const int16_t* disp, int disp_stride, int 
   if (k > 0) {
     const size_t bx = (size_t)k * sizeof(float3), bi = pix_idx ? (size_t)k * sizeof(int) : 0;
     if (sg_needs_staging(xyz) || (pix_idx && sg_needs_staging(pix_idx))) {
+      // pageable destination: DMA into pinned staging in chunks, each chunk's host copy overlapping the next DMA
       VO_TRY(sg_stage_reserve(&s->h_out, &s->h_out_bytes, bx + bi));
-      VO_CUDA(cudaMemcpyAsync(s->h_out, s->xyz_out, bx, cudaMemcpyDeviceToHost, c->stream));
-      if (bi) VO_CUDA(cudaMemcpyAsync(s->h_out + bx, s->idx_out, bi, cudaMemcpyDeviceToHost, c->stream));
-      VO_CUDA(cudaStreamSynchronize(c->stream));
-      memcpy(xyz, s->h_out, bx);
-      if (bi) memcpy(pix_idx, s->h_out + bx, bi);
+      constexpr size_t CH = 1 << 20;
+      constexpr int NEV = 10;
+      const size_t total = bx + bi;
+      const int nch = (int)((total + CH - 1) / CH);
+      for (int ch = 0; ch < nch; ch++) {
+        const size_t o = (size_t)ch * CH, len = std::min(CH, total - o);
+        // staging layout: points first, indices behind them; a chunk may straddle the two device arrays
+        if (o < bx) {
+          const size_t l1 = std::min(len, bx - o);
+          VO_CUDA(cudaMemcpyAsync(s->h_out + o, reinterpret_cast<const uint8_t*>(s->xyz_out) + o, l1, cudaMemcpyDeviceToHost,
+                                  c->stream));
+          if (l1 < len)
+            VO_CUDA(cudaMemcpyAsync(s->h_out + bx, s->idx_out, len - l1, cudaMemcpyDeviceToHost, c->stream));
+        } else {
+          VO_CUDA(cudaMemcpyAsync(s->h_out + o, reinterpret_cast<const uint8_t*>(s->idx_out) + (o - bx), len,
+                                  cudaMemcpyDeviceToHost, c->stream));
+        }
+        if (ch < NEV) VO_CUDA(cudaEventRecord(s->ev[ch], c->stream));
+      }
+      for (int ch = 0; ch < nch; ch++) {
+        if (ch < NEV) VO_CUDA(cudaEventSynchronize(s->ev[ch]));
+        else VO_CUDA(cudaStreamSynchronize(c->stream));
+        const size_t o = (size_t)ch * CH, len = std::min(CH, total - o);
+        if (o < bx) {
+          const size_t l1 = std::min(len, bx - o);
+          memcpy(reinterpret_cast<uint8_t*>(xyz) + o, s->h_out + o, l1);
+          if (l1 < len) memcpy(pix_idx, s->h_out + bx, len - l1);
+        } else {
+          memcpy(reinterpret_cast<uint8_t*>(pix_idx) + (o - bx), s->h_out + o, len);
+        }
+      }
     } else {
       VO_CUDA(cudaMemcpyAsync(xyz, s->xyz_out, bx, cudaMemcpyDefault, c->stream));
       if (bi) VO_CUDA(cudaMemcpyAsync(pix_idx, s->idx_out, bi, cudaMemcpyDefault, c->stream));
