@@ -144,7 +144,7 @@ __device__ __forceinline__ int sg_bt(uchar4 u, uchar4 v, int shift) {
   return min(c0, c1) >> shift;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 sgbm_hsum_kernel(const uchar4* __restrict__ pl, int w, int h, int W1, int D, int minD, int minX1, int R,
                  uint16_t* __restrict__ hsum) {
   extern __shared__ __align__(16) unsigned char sg_smem[];
@@ -183,34 +183,42 @@ sgbm_hsum_kernel(const uchar4* __restrict__ pl, int w, int h, int W1, int D, int
   constexpr int CPW = SG_TX / 8;
   const int nb = 2 * R + 1;
   const int xo = wid * CPW;
-  for (int dd = lane; dd < D; dd += 32) {
-    const uint16_t* px = sg_pix + xo * D + dd;
-    uint16_t* hp = hsum + ((size_t)y * W1 + x0 + xo) * D + dd;
-    int sum = 0;
-    for (int k = 0; k < nb; k++) sum += px[k * D];
+  const int Dw = D >> 1;                                // two disparities per 32-bit word
+  for (int pp = lane; pp < Dw; pp += 32) {
+    const unsigned* px = reinterpret_cast<const unsigned*>(sg_pix) + xo * Dw + pp;
+    unsigned* hp = reinterpret_cast<unsigned*>(hsum + ((size_t)y * W1 + x0 + xo) * D) + pp;
+    unsigned sum = 0;
+    for (int k = 0; k < nb; k++) sum += px[k * Dw];
 #pragma unroll
     for (int cI = 0; cI < CPW; cI++) {
-      if (x0 + xo + cI < W1) *hp = (uint16_t)sum;
-      hp += D;
-      if (cI + 1 < CPW) sum += (int)px[(cI + nb) * D] - (int)px[cI * D];
+      if (x0 + xo + cI < W1) *hp = sum;
+      hp += Dw;
+      if (cI + 1 < CPW) sum = sum + px[(cI + nb) * Dw] - px[cI * Dw];
     }
   }
 }
 
 // ------------------------------------------------------------------------------------ K_vsum
+// Eight costs per thread as four u16x2 words, added and subtracted as plain 32-bit integers: a window sum is at most
+// 32767 and never smaller than the row that leaves it, so no carry or borrow crosses the halves.
+__device__ __forceinline__ uint4 sg_add4(uint4 a, uint4 b) { return make_uint4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ uint4 sg_sub4(uint4 a, uint4 b) { return make_uint4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+
 __global__ void __launch_bounds__(256)
-sgbm_vsum_kernel(const uint16_t* __restrict__ hsum, int h, size_t row_elems, int R, int rows_per_strip,
-                 int16_t* __restrict__ C) {
+sgbm_vsum_kernel(const uint4* __restrict__ hsum, int h, size_t row_vecs, int R, int rows_per_strip, uint4* __restrict__ C) {
   const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= row_elems) return;
+  if (e >= row_vecs) return;
   const int ya = blockIdx.y * rows_per_strip;
   const int yb = min(ya + rows_per_strip, h);
   if (ya >= yb) return;
-  int s = 0;
-  for (int k = -R; k <= R; k++) s += hsum[(size_t)min(max(ya + k, 0), h - 1) * row_elems + e];
+  uint4 s = make_uint4(0u, 0u, 0u, 0u);
+  for (int k = -R; k <= R; k++) s = sg_add4(s, __ldg(hsum + (size_t)min(max(ya + k, 0), h - 1) * row_vecs + e));
+#pragma unroll 4
   for (int y = ya; y < yb; y++) {
-    C[(size_t)y * row_elems + e] = (int16_t)s;
-    s += (int)hsum[(size_t)min(y + R + 1, h - 1) * row_elems + e] - (int)hsum[(size_t)max(y - R, 0) * row_elems + e];
+    C[(size_t)y * row_vecs + e] = s;
+    const uint4 in = __ldg(hsum + (size_t)min(y + R + 1, h - 1) * row_vecs + e);
+    const uint4 out = __ldg(hsum + (size_t)max(y - R, 0) * row_vecs + e);
+    s = sg_sub4(sg_add4(s, in), out);
   }
 }
 
@@ -902,10 +910,10 @@ static int sgbm_run(vo_ctx* c, int w, int h, const vo_sgbm_params* p, const SgRe
     }
     {
       LaunchScope ls(c, VO_K_MISC);
-      const size_t row_elems = (size_t)r.W1 * r.D;
-      const int strips = 8, rps = div_up(h, strips);
-      sgbm_vsum_kernel<<<dim3((unsigned)((row_elems + 255) / 256), strips), 256, 0, c->stream>>>(s->hsum, h, row_elems, r.R,
-                                                                                               rps, s->C);
+      const size_t row_vecs = (size_t)r.W1 * r.D / 8;     // D is a multiple of 16
+      const int strips = 16, rps = div_up(h, strips);
+      sgbm_vsum_kernel<<<dim3((unsigned)((row_vecs + 255) / 256), strips), 256, 0, c->stream>>>(
+          reinterpret_cast<const uint4*>(s->hsum), h, row_vecs, r.R, rps, reinterpret_cast<uint4*>(s->C));
     }
     VO_CUDA(cudaEventRecord(s->ev[3], c->stream));
     SgWta wta{s->rec, s->key2, w, r.minD, r.minX1, r.uniq};
