@@ -184,3 +184,19 @@ def test_random_parameter_fuzz_matches_cv2(fe):
         got = fe.stereoMatch(L, R, **_abi(kw))
         assert np.array_equal(got, want), (kw, w, h)
         done += 1
+
+
+def test_full_hd_frame(fe):
+    """A 1920x1080 pair (the golden pair upscaled): grids, strides and the 2.3 GB of volumes at a size the reference's
+    KITTI frames never reach."""
+    import cv2
+    from oracle import sgbm
+    g = golden()
+    L = cv2.resize(g["L0"], (1920, 1080), interpolation=cv2.INTER_LINEAR)
+    R = cv2.resize(g["R0"], (1920, 1080), interpolation=cv2.INTER_LINEAR)
+    want = sgbm.sgbm_call_through(L, R)
+    got = fe.stereoMatch(L, R)
+    assert np.array_equal(got, want)
+    assert (want > 0).mean() > 0.3
+    # and back to the KITTI size with the grown buffers
+    assert np.array_equal(fe.stereoMatch(g["L0"], g["R0"]), sgbm.sgbm_call_through(g["L0"], g["R0"]))
