@@ -381,6 +381,109 @@ sgbm_path_kernel(const int16_t* __restrict__ C, void* __restrict__ out_a, void* 
   }
 }
 
+// Two paths per warp (D <= 128): each half-warp walks its own path, 8 disparities per lane.  The diagonal and the
+// vertical directions have thousands of paths and are bound by instruction issue, not by the latency of one path, so
+// the fixed per-step overhead (ring, pointers, loop) is shared by two paths; the price is the min over d as four
+// shuffle steps inside the half-warp instead of one REDUX.  (The horizontal pair stays on the one-path kernel: there
+// the latency of a path is the whole launch.)
+template <bool NARROW>
+__global__ void __launch_bounds__(SG_WPB * 32)
+sgbm_path2_kernel(const int16_t* __restrict__ C, void* __restrict__ out_a, void* __restrict__ out_b, int W1, int H, int D,
+                  int P1, int P2, int dir_a, int dir_b, int npaths) {
+  constexpr int NST = 8, NW = 4, STG = 32 * 16;
+  extern __shared__ __align__(16) unsigned char sg_ring[];   // [warp][stage][lane][16]
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int hl = lane & 15;
+  const int p = 2 * (blockIdx.x * SG_WPB + wib) + (lane >> 4);
+  const int dir = blockIdx.y ? dir_b : dir_a;
+  void* out = blockIdx.y ? out_b : out_a;
+  int x = 0, y = 0, n = 0, sx = 0, sy = 1;
+  if (p < npaths) {
+    switch (dir) {
+      case 2: x = p; y = 0; n = H; sx = 0; break;
+      case 1:
+        if (p < W1) { x = p; y = 0; } else { x = 0; y = p - W1 + 1; }
+        n = min(H - y, W1 - x); sx = 1; break;
+      default:
+        if (p < W1) { x = p; y = 0; } else { x = W1 - 1; y = p - W1 + 1; }
+        n = min(H - y, x + 1); sx = -1; break;
+    }
+  }
+  const int nmax = max(n, __shfl_xor_sync(0xffffffffu, n, 16));
+  if (nmax == 0) return;
+  const bool active = 8 * hl < D;
+  const bool last = 8 * (hl + 1) >= D;
+  const long long step = ((long long)sy * W1 + sx) * D;
+  const size_t base = ((size_t)y * W1 + x) * D + (active ? 8 * hl : 0);
+  const int16_t* gC = C + base;
+  constexpr int OB = NARROW ? 1 : 2;
+  unsigned char* wS = reinterpret_cast<unsigned char*>(out) + base * OB;
+  unsigned char* ring = sg_ring + (size_t)wib * NST * STG + lane * 16;
+  const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
+  const bool loads = active && n > 0;
+
+#pragma unroll
+  for (int k = 0; k < NST; k++) {
+    if (loads && k < n) {
+      sg_cp_async<16>(ring_s + k * STG, gC);
+      gC += step;
+    }
+    sg_cp_commit();
+  }
+  unsigned Lp[NW];
+#pragma unroll
+  for (int q = 0; q < NW; q++) Lp[q] = 0u;
+  int minp = 0;
+  const unsigned PAD2 = (unsigned)(SG_MAX_COST - P1) * 0x10001u;
+  const unsigned P1x2 = (unsigned)P1 * 0x10001u;
+
+  for (int i0 = 0; i0 < nmax; i0 += NST) {
+#pragma unroll
+    for (int k = 0; k < NST; k++) {
+      const int i = i0 + k;
+      if (i >= nmax) break;
+      sg_cp_wait<NST - 1>();
+      const uint4 cvec = *reinterpret_cast<const uint4*>(ring + k * STG);
+      const unsigned cw[NW] = {cvec.x, cvec.y, cvec.z, cvec.w};
+      if (loads && i + NST < n) {
+        sg_cp_async<16>(ring_s + k * STG, gC);
+        gC += step;
+      }
+      sg_cp_commit();
+      unsigned left = __shfl_up_sync(0xffffffffu, Lp[NW - 1], 1, 16);
+      unsigned right = __shfl_down_sync(0xffffffffu, Lp[0], 1, 16);
+      if (hl == 0) left = PAD2;
+      if (last) right = PAD2;
+      const unsigned minp2 = (unsigned)minp * 0x10001u;
+      const unsigned delta2 = minp2 + (unsigned)P2 * 0x10001u;
+      unsigned Ln[NW], rel[NW];
+#pragma unroll
+      for (int q = 0; q < NW; q++) {
+        const unsigned lo = __byte_perm(q ? Lp[q - 1] : left, Lp[q], 0x5432);
+        const unsigned hi = __byte_perm(Lp[q], q < NW - 1 ? Lp[q + 1] : right, 0x5432);
+        unsigned t = __viaddmin_s16x2(lo, P1x2, Lp[q]);
+        t = __viaddmin_s16x2(hi, P1x2, t);
+        t = __vmins2(t, delta2);
+        rel[q] = t - minp2;
+        Ln[q] = rel[q] + cw[q];
+      }
+      unsigned mw = __vmins2(__vmins2(Ln[0], Ln[1]), __vmins2(Ln[2], Ln[3]));
+      int m = min((int)(mw & 0xFFFFu), (int)(mw >> 16));
+      if (!active) m = 0x7fffffff;
+#pragma unroll
+      for (int q = 0; q < NW; q++) Lp[q] = Ln[q];
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o, 16));
+      minp = m;
+      if (active && i < n) {
+        if (NARROW) *reinterpret_cast<uint2*>(wS) = make_uint2(__byte_perm(rel[0], rel[1], 0x6420), __byte_perm(rel[2], rel[3], 0x6420));
+        else *reinterpret_cast<uint4*>(wS) = make_uint4(Ln[0], Ln[1], Ln[2], Ln[3]);
+      }
+      wS += step * OB;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------ K_wta
 // One warp per pixel (grid-stride): S = min(32767, L0 + L1 + L2 + L3 + L4) -- every L is >= 0, so OpenCV's two
 // saturating adds collapse into this -- then winner-take-all (first minimum), uniqueness test, the neighbours of the
@@ -858,6 +961,16 @@ static int sgbm_path_launch(vo_ctx* c, cudaStream_t st, const int16_t* C, void* 
   return VO_OK;
 }
 
+template <bool NARROW>
+static int sgbm_path2_launch(vo_ctx* c, cudaStream_t st, const int16_t* C, void* out_a, void* out_b, const SgResolved& r, int h,
+                             int dir_a, int dir_b, int ndirs, int npaths) {
+  const size_t smem = (size_t)SG_WPB * 8 * 32 * 16;
+  c->launch_count++;
+  sgbm_path2_kernel<NARROW><<<dim3(div_up(npaths, 2 * SG_WPB), ndirs), SG_WPB * 32, smem, st>>>(
+      C, out_a, out_b, r.W1, h, r.D, r.P1, r.P2, dir_a, dir_b, npaths);
+  return VO_OK;
+}
+
 // All five directions run at once, each into its own volume: the horizontal pair (the long paths: W1 steps, only
 // 2 * h warps) on a second stream, the diagonal pair on a third, the vertical direction on the main stream; none of
 // them alone fills the machine (a path is one warp), together they stream C five times at HBM speed.  The
@@ -870,9 +983,13 @@ static int sgbm_paths(vo_ctx* c, Sgbm* s, const SgResolved& r, int h, const SgWt
   VO_CUDA(cudaStreamWaitEvent(s->stream3, s->ev[3], 0));
   VO_TRY((sgbm_path_launch<DPL, NARROW>(c, s->stream2, s->C, L0, s->vol[0], r, h, 0, 4, 2, h)));
   VO_CUDA(cudaEventRecord(s->ev_h, s->stream2));
-  VO_TRY((sgbm_path_launch<DPL, NARROW>(c, s->stream3, s->C, s->vol[1], s->vol[2], r, h, 1, 3, 2, nd)));
+  static const bool one_path = getenv("VO_B200_SGBM_ONE_PATH_PER_WARP") != nullptr;   // experiment switch
+  const bool two = r.D <= 128 && !one_path;
+  if (two) VO_TRY((sgbm_path2_launch<NARROW>(c, s->stream3, s->C, s->vol[1], s->vol[2], r, h, 1, 3, 2, nd)));
+  else VO_TRY((sgbm_path_launch<DPL, NARROW>(c, s->stream3, s->C, s->vol[1], s->vol[2], r, h, 1, 3, 2, nd)));
   VO_CUDA(cudaEventRecord(s->ev_d, s->stream3));
-  VO_TRY((sgbm_path_launch<DPL, NARROW>(c, c->stream, s->C, s->S, nullptr, r, h, 2, 2, 1, r.W1)));
+  if (two) VO_TRY((sgbm_path2_launch<NARROW>(c, c->stream, s->C, s->S, nullptr, r, h, 2, 2, 1, r.W1)));
+  else VO_TRY((sgbm_path_launch<DPL, NARROW>(c, c->stream, s->C, s->S, nullptr, r, h, 2, 2, 1, r.W1)));
   VO_CUDA(cudaEventRecord(s->ev[4], c->stream));
   VO_CUDA(cudaStreamWaitEvent(c->stream, s->ev_h, 0));
   VO_CUDA(cudaStreamWaitEvent(c->stream, s->ev_d, 0));
