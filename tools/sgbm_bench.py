@@ -54,6 +54,22 @@ def main():
     print("device stages of the last call (ms):", {k: round(v, 4) for k, v in stage.items()},
           "sum %.3f" % sum(stage.values()))
     Q = g3["Q_neg"]
+    # StereoProcess::stereoMatch as the reference calls it: imread's BGR frames in, BGR2GRAY on the device
+    Lb, Rb = cv2.cvtColor(L, cv2.COLOR_GRAY2BGR), cv2.cvtColor(R, cv2.COLOR_GRAY2BGR)
+    assert np.array_equal(fe.stereoMatch(Lb, Rb), ref)
+    tb = []
+    for _ in range(60):
+        t = time.perf_counter()
+        fe.stereoMatch(Lb, Rb)
+        tb.append(time.perf_counter() - t)
+    print("vo_stereo_match (host BGR frames in, host disparity out): median %.3f ms" % (1e3 * np.median(tb[10:])))
+    tc3 = []
+    m3 = cv2.StereoSGBM_create(1, 96, 7, 24, 96, 0, 60, 0, 3000, 5)
+    for _ in range(3):
+        t = time.perf_counter()
+        m3.compute(cv2.cvtColor(Lb, cv2.COLOR_BGR2GRAY), cv2.cvtColor(Rb, cv2.COLOR_BGR2GRAY))
+        tc3.append(time.perf_counter() - t)
+    print("cv2 cvtColor x 2 + StereoSGBM.compute on the host: median %.1f ms" % (1e3 * np.median(tc3)))
     # the C entry point with caller-owned, reused output buffers (what a C++ caller does); the numpy mirror above it
     # allocates and copies its results on every call
     import ctypes as C
