@@ -352,7 +352,8 @@ def dense_stereo_side_figure(fe, L, R, reps=100):
                    "60, 0, 3000, 5)", "ms_per_pair": round(1e3 * float(np.median(ts[reps // 2:])), 4),
             "cv2_ms_per_pair": round(1e3 * t_cpu, 1), "cores": len(os.sched_getaffinity(0)),
             "bit_identical_to_cv2": bool(np.array_equal(got, want)),
-            "device_stage_ms": {k: round(v, 4) for k, v in fe.sgbm_timing().items()}}
+            "device_pipeline_ms": round(fe.sgbm_timing()["pipeline"], 4),
+            "note": "a repeated (size, parameters) replays one CUDA graph; per-stage times: tools/sgbm_bench.py"}
 
 
 # ----------------------------------------------------------------------------- CPU reference

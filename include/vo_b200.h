@@ -224,10 +224,13 @@ int vo_stereo_match(vo_ctx* ctx, const uint8_t* left_bgr, const uint8_t* right_b
  * points that passed (VO_ERR_CAPACITY when it exceeds cap; the first cap are written). */
 int vo_reproject_disparity(vo_ctx* ctx, const int16_t* disp, int disp_stride, int width, int height, const double Q[16],
                            float* xyz, int32_t* pix_idx, int cap, int* n);
-/* device milliseconds of the last SGBM call: upload (+ gray conversion), prefilter, cost volume (BT + box sums),
- * vertical paths (the horizontal and diagonal ones run beside them on two more streams), what remained of those
- * after that, sum + winner-take-all, left-right check + median, speckle filter, download */
-int vo_sgbm_timing(vo_ctx* ctx, float ms[9]);
+/* device milliseconds of the last SGBM call.  ms[0] = upload (+ gray conversion), ms[8] = download, *pipeline_ms
+ * (nullable) = everything between.  A repeated (size, parameters) is replayed as one CUDA graph; the per-stage figures
+ * ms[1..7] -- prefilter, cost volume (BT + box sums), vertical paths (the horizontal and diagonal ones run beside them
+ * on two more streams), what remained of those after that, sum + winner-take-all, left-right check + median, speckle
+ * filter -- exist only for calls made as plain launches, i.e. while vo_profile_enable(ctx, mask != 0) is in effect,
+ * and read 0 otherwise. */
+int vo_sgbm_timing(vo_ctx* ctx, float ms[9], float* pipeline_ms);
 /* intermediate stages of the last SGBM call, for parity debugging: 0 = C (int16 [h][W1][D]), 1 = disparity after
  * winner-take-all, 2 = after the left-right check (both int16 [h][w]), 3 = prefilter planes (uchar4 [4][h][w]) */
 int vo_debug_sgbm_stage(vo_ctx* ctx, int stage, void* out, uint64_t bytes);

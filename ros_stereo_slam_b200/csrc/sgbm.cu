@@ -50,7 +50,7 @@ struct Sgbm {
   int16_t* S = nullptr;
   int16_t* vol[3] = {nullptr, nullptr, nullptr};   // path-cost volumes L4, L1, L3 (L0 reuses hsum, L2 is S)
   cudaStream_t stream2 = nullptr, stream3 = nullptr;   // horizontal / diagonal paths run beside the vertical ones
-  cudaEvent_t ev_h = nullptr, ev_d = nullptr;
+  cudaEvent_t ev_h = nullptr, ev_d = nullptr, ev_fork = nullptr;
   unsigned* key2 = nullptr;                 // right-view (cost, x) keys
   uint2* rec = nullptr;                     // winner records
   int16_t* disp[3] = {nullptr, nullptr, nullptr};   // raw WTA, after LR check, after median (+ speckle in place)
@@ -68,6 +68,13 @@ struct Sgbm {
   void* cub_tmp = nullptr;
   size_t cub_bytes = 0;
   bool have_disp = false;
+  cudaGraphExec_t gexec = nullptr;          // the captured pipeline for (g_w, g_h, g_params)
+  int g_w = 0, g_h = 0, g_launches = 0;
+  vo_sgbm_params g_params = {};
+  bool graph_failed = false;
+  bool staged = false;                      // the last call recorded per-stage events
+  float pipeline_ms = 0.f;
+  bool stage_events = true;                 // ev[2..7] are recorded (plain launches); false while capturing / replaying
   int last_w = 0, last_h = 0;
   cudaEvent_t ev[10] = {nullptr};
   float ms[9] = {0};
@@ -84,8 +91,10 @@ void sgbm_free(vo_ctx* c) {
   cudaFreeHost(s->h_out);
   for (auto e : s->ev)
     if (e) cudaEventDestroy(e);
+  if (s->gexec) cudaGraphExecDestroy(s->gexec);
   if (s->ev_h) cudaEventDestroy(s->ev_h);
   if (s->ev_d) cudaEventDestroy(s->ev_d);
+  if (s->ev_fork) cudaEventDestroy(s->ev_fork);
   if (s->stream2) cudaStreamDestroy(s->stream2);
   if (s->stream3) cudaStreamDestroy(s->stream3);
   delete s;
@@ -908,6 +917,7 @@ static int sgbm_ensure(vo_ctx* c, int w, int h, const SgResolved& r, bool need_b
     for (auto& e : s->ev) VO_CUDA(cudaEventCreate(&e));
     VO_CUDA(cudaEventCreateWithFlags(&s->ev_h, cudaEventDisableTiming));
     VO_CUDA(cudaEventCreateWithFlags(&s->ev_d, cudaEventDisableTiming));
+    VO_CUDA(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
     VO_CUDA(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
     VO_CUDA(cudaStreamCreateWithFlags(&s->stream3, cudaStreamNonBlocking));
     VO_CUDA(cudaMalloc(&s->d_n, 4 * sizeof(int)));
@@ -918,6 +928,10 @@ static int sgbm_ensure(vo_ctx* c, int w, int h, const SgResolved& r, bool need_b
   if (npx > (size_t)s->w * s->h || cost > s->cost_elems) {
     VO_CUDA(cudaStreamSynchronize(c->stream));
     sgbm_release_buffers(s);
+    if (s->gexec) {
+      cudaGraphExecDestroy(s->gexec);
+      s->gexec = nullptr;
+    }
     s->have_disp = false;
     s->w = w;
     s->h = h;
@@ -979,8 +993,9 @@ template <int DPL, bool NARROW>
 static int sgbm_paths(vo_ctx* c, Sgbm* s, const SgResolved& r, int h, const SgWta& wta) {
   void* L0 = s->hsum;   // hsum is dead once C exists
   const int nd = r.W1 + h - 1;
-  VO_CUDA(cudaStreamWaitEvent(s->stream2, s->ev[3], 0));
-  VO_CUDA(cudaStreamWaitEvent(s->stream3, s->ev[3], 0));
+  VO_CUDA(cudaEventRecord(s->ev_fork, c->stream));
+  VO_CUDA(cudaStreamWaitEvent(s->stream2, s->ev_fork, 0));
+  VO_CUDA(cudaStreamWaitEvent(s->stream3, s->ev_fork, 0));
   VO_TRY((sgbm_path_launch<DPL, NARROW>(c, s->stream2, s->C, L0, s->vol[0], r, h, 0, 4, 2, h)));
   VO_CUDA(cudaEventRecord(s->ev_h, s->stream2));
   static const bool one_path = getenv("VO_B200_SGBM_ONE_PATH_PER_WARP") != nullptr;   // experiment switch
@@ -990,10 +1005,10 @@ static int sgbm_paths(vo_ctx* c, Sgbm* s, const SgResolved& r, int h, const SgWt
   VO_CUDA(cudaEventRecord(s->ev_d, s->stream3));
   if (two) VO_TRY((sgbm_path2_launch<NARROW>(c, c->stream, s->C, s->S, nullptr, r, h, 2, 2, 1, r.W1)));
   else VO_TRY((sgbm_path_launch<DPL, NARROW>(c, c->stream, s->C, s->S, nullptr, r, h, 2, 2, 1, r.W1)));
-  VO_CUDA(cudaEventRecord(s->ev[4], c->stream));
+  if (s->stage_events) VO_CUDA(cudaEventRecord(s->ev[4], c->stream));
   VO_CUDA(cudaStreamWaitEvent(c->stream, s->ev_h, 0));
   VO_CUDA(cudaStreamWaitEvent(c->stream, s->ev_d, 0));
-  VO_CUDA(cudaEventRecord(s->ev[5], c->stream));
+  if (s->stage_events) VO_CUDA(cudaEventRecord(s->ev[5], c->stream));
   {
     LaunchScope ls(c, VO_K_MISC);
     sgbm_wta_kernel<DPL, NARROW><<<dim3(div_up(r.W1, 8 * SG_WTA_PIX), h), 256, 0, c->stream>>>(s->C, L0, s->vol[0], s->vol[1],
@@ -1004,11 +1019,12 @@ static int sgbm_paths(vo_ctx* c, Sgbm* s, const SgResolved& r, int h, const SgWt
 }
 
 // device pipeline on s->img[0..1] (tight gray) -> s->disp[2]
-static int sgbm_run(vo_ctx* c, int w, int h, const vo_sgbm_params* p, const SgResolved& r) {
+// enqueues the whole pipeline on the context's streams (also under stream capture, see sgbm_run)
+static int sgbm_enqueue(vo_ctx* c, int w, int h, const vo_sgbm_params* p, const SgResolved& r, bool stage_events) {
   Sgbm* s = reinterpret_cast<Sgbm*>(c->sgbm);
   const size_t npx = (size_t)w * h;
   const int n = (int)npx;
-  VO_CUDA(cudaEventRecord(s->ev[1], c->stream));
+  s->stage_events = stage_events;
   {
     LaunchScope ls(c, VO_K_MISC);
     sgbm_fill_kernel<<<div_up(n, 256), 256, 0, c->stream>>>(s->rec, s->key2, npx);
@@ -1018,7 +1034,7 @@ static int sgbm_run(vo_ctx* c, int w, int h, const vo_sgbm_params* p, const SgRe
       LaunchScope ls(c, VO_K_MISC);
       sgbm_prefilter_kernel<<<dim3(div_up(w, 128), h, 2), 128, 0, c->stream>>>(s->img[0], s->img[1], w, h, r.ftzero, s->pl);
     }
-    VO_CUDA(cudaEventRecord(s->ev[2], c->stream));
+    if (s->stage_events) VO_CUDA(cudaEventRecord(s->ev[2], c->stream));
     {
       LaunchScope ls(c, VO_K_MISC);
       const size_t smem = (size_t)(SG_TX + 2 * r.R) * r.D * sizeof(uint16_t) + 2 * (size_t)(SG_TX + 2 * r.R + r.D - 1) * sizeof(uchar4);
@@ -1032,7 +1048,7 @@ static int sgbm_run(vo_ctx* c, int w, int h, const vo_sgbm_params* p, const SgRe
       sgbm_vsum_kernel<<<dim3((unsigned)((row_vecs + 255) / 256), strips), 256, 0, c->stream>>>(
           reinterpret_cast<const uint4*>(s->hsum), h, row_vecs, r.R, rps, reinterpret_cast<uint4*>(s->C));
     }
-    VO_CUDA(cudaEventRecord(s->ev[3], c->stream));
+    if (s->stage_events) VO_CUDA(cudaEventRecord(s->ev[3], c->stream));
     SgWta wta{s->rec, s->key2, w, r.minD, r.minX1, r.uniq};
     static const bool wide = getenv("VO_B200_SGBM_WIDE") != nullptr;   // force the int16 volumes (test switch)
     const bool narrow = r.P2 <= 255 && !wide;
@@ -1044,9 +1060,10 @@ static int sgbm_run(vo_ctx* c, int w, int h, const vo_sgbm_params* p, const SgRe
       else VO_TRY((sgbm_paths<8, false>(c, s, r, h, wta)));
     }
   } else {
-    for (int k = 2; k <= 5; k++) VO_CUDA(cudaEventRecord(s->ev[k], c->stream));
+    for (int k = 2; k <= 5; k++)
+      if (s->stage_events) VO_CUDA(cudaEventRecord(s->ev[k], c->stream));
   }
-  VO_CUDA(cudaEventRecord(s->ev[6], c->stream));
+  if (s->stage_events) VO_CUDA(cudaEventRecord(s->ev[6], c->stream));
   {
     LaunchScope ls(c, VO_K_MISC);
     static const bool keep_raw = getenv("VO_B200_SGBM_DEBUG") != nullptr;   // stage 1 of vo_debug_sgbm_stage
@@ -1057,7 +1074,7 @@ static int sgbm_run(vo_ctx* c, int w, int h, const vo_sgbm_params* p, const SgRe
     LaunchScope ls(c, VO_K_MISC);
     sgbm_median3_kernel<<<dim3(div_up(w, 128), h), 128, 0, c->stream>>>(s->disp[1], w, h, s->disp[2]);
   }
-  VO_CUDA(cudaEventRecord(s->ev[7], c->stream));
+  if (s->stage_events) VO_CUDA(cudaEventRecord(s->ev[7], c->stream));
   if (p->speckle_window_size > 0) {
     const int max_diff = 16 * p->speckle_range;
     {
@@ -1078,14 +1095,62 @@ static int sgbm_run(vo_ctx* c, int w, int h, const vo_sgbm_params* p, const SgRe
                                                                  s->disp[2]);
     }
   }
-  VO_CUDA(cudaEventRecord(s->ev[8], c->stream));
   VO_CUDA(cudaGetLastError());
-  s->have_disp = true;
-  s->last_w = w;
-  s->last_h = h;
   return VO_OK;
 }
 
+// The pipeline is ~17 short launches on three streams: for a repeated (size, parameters) it is captured once into a
+// CUDA graph and replayed with one launch, which removes the launch gaps between the small kernels and most of the
+// host time of a call.  The graph dies with the buffers it points to (sgbm_ensure).
+static int sgbm_run(vo_ctx* c, int w, int h, const vo_sgbm_params* p, const SgResolved& r) {
+  Sgbm* s = reinterpret_cast<Sgbm*>(c->sgbm);
+  static const bool no_graph = getenv("VO_B200_SGBM_NO_GRAPH") != nullptr;
+  s->have_disp = true;
+  s->last_w = w;
+  s->last_h = h;
+  VO_CUDA(cudaEventRecord(s->ev[1], c->stream));
+  // per-stage events only exist on plain launches: profiling (vo_profile_enable) selects them
+  if (no_graph || s->graph_failed || c->prof.mask) {
+    VO_TRY(sgbm_enqueue(c, w, h, p, r, true));
+    s->staged = true;
+    VO_CUDA(cudaEventRecord(s->ev[8], c->stream));
+    return VO_OK;
+  }
+  const bool same = s->gexec && s->g_w == w && s->g_h == h && memcmp(&s->g_params, p, sizeof(*p)) == 0;
+  if (!same) {
+    if (s->gexec) {
+      cudaGraphExecDestroy(s->gexec);
+      s->gexec = nullptr;
+    }
+    const int64_t before = c->launch_count;
+    VO_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = sgbm_enqueue(c, w, h, p, r, false);
+    cudaGraph_t g = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+    s->g_launches = (int)(c->launch_count - before);
+    c->launch_count = before;
+    if (rc != VO_OK || e != cudaSuccess || !g || cudaGraphInstantiate(&s->gexec, g, 0) != cudaSuccess) {
+      if (g) cudaGraphDestroy(g);
+      cudaGetLastError();
+      s->gexec = nullptr;
+      s->graph_failed = true;            // this driver / configuration cannot capture it: plain launches from now on
+      VO_CUDA(cudaEventRecord(s->ev[1], c->stream));
+      VO_TRY(sgbm_enqueue(c, w, h, p, r, true));
+      s->staged = true;
+      VO_CUDA(cudaEventRecord(s->ev[8], c->stream));
+      return VO_OK;
+    }
+    cudaGraphDestroy(g);
+    s->g_w = w;
+    s->g_h = h;
+    s->g_params = *p;
+  }
+  VO_CUDA(cudaGraphLaunch(s->gexec, c->stream));
+  c->launch_count += s->g_launches;
+  s->staged = false;
+  VO_CUDA(cudaEventRecord(s->ev[8], c->stream));
+  return VO_OK;
+}
 
 // Caller buffers are usually pageable (cv::Mat / std::vector memory): a pageable cudaMemcpy runs at a few GB/s, so
 // such buffers go through pinned staging owned by the context (one host memcpy + one DMA); pinned, managed and
@@ -1152,11 +1217,20 @@ static int sgbm_finish(vo_ctx* c, int w, int h, int16_t* disp, int disp_stride) 
     else
       for (int y = 0; y < h; y++) memcpy((uint8_t*)disp + (size_t)y * disp_stride, s->h_out + (size_t)y * row, row);
   }
-  for (int k = 0; k < 9; k++) {
+  auto span = [&](int a, int b) {
     float ms = 0;
-    if (cudaEventElapsedTime(&ms, s->ev[k], s->ev[k + 1]) != cudaSuccess) ms = -1.f;
-    s->ms[k] = ms;
-  }
+    if (cudaEventElapsedTime(&ms, s->ev[a], s->ev[b]) != cudaSuccess) {
+      cudaGetLastError();
+      ms = 0.f;
+    }
+    return ms;
+  };
+  for (int k = 0; k < 9; k++) s->ms[k] = 0.f;
+  s->ms[0] = span(0, 1);
+  s->ms[8] = span(8, 9);
+  s->pipeline_ms = span(1, 8);
+  if (s->staged)
+    for (int k = 1; k < 8; k++) s->ms[k] = span(k, k + 1);
   return VO_OK;
 }
 
@@ -1194,10 +1268,11 @@ int vo_stereo_match(vo_ctx* c, const uint8_t* left_bgr, const uint8_t* right_bgr
   return sgbm_finish(c, width, height, disp, disp_stride);
 }
 
-int vo_sgbm_timing(vo_ctx* c, float ms[9]) {
+int vo_sgbm_timing(vo_ctx* c, float ms[9], float* pipeline_ms) {
   if (!c || !ms || !c->sgbm) return VO_ERR_INVALID_ARG;
   Sgbm* s = reinterpret_cast<Sgbm*>(c->sgbm);
   for (int k = 0; k < 9; k++) ms[k] = s->ms[k];
+  if (pipeline_ms) *pipeline_ms = s->pipeline_ms;
   return VO_OK;
 }
 

@@ -170,11 +170,16 @@ class VisualFrontEnd:
         return xyz[:m].copy(), idx[:m].copy()
 
     def sgbm_timing(self):
+        """Device milliseconds of the last SGBM call; the per-stage entries are filled only for calls made while
+        profiling is enabled (plain launches instead of the CUDA graph), 'pipeline' always."""
         ms = (C.c_float * 9)()
-        check(self.lib.vo_sgbm_timing(self.h, ms))
+        tot = C.c_float()
+        check(self.lib.vo_sgbm_timing(self.h, ms, C.byref(tot)))
         names = ("upload", "prefilter", "cost_volume", "paths_vertical", "paths_other_tail", "wta",
                  "lrcheck_median", "speckle", "download")
-        return dict(zip(names, [float(v) for v in ms]))
+        out = dict(zip(names, [float(v) for v in ms]))
+        out["pipeline"] = float(tot.value)
+        return out
 
     def sgbm_stage(self, stage, shape, dtype):
         out = np.zeros(shape, dtype)
