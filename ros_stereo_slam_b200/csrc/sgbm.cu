@@ -12,11 +12,13 @@
 //            width -> hsum[y][x][d] u16                                                  H*W1*D*2 bytes
 //   K_vsum   running sum over the block height (rows replicated at the border) -> C[y][x][d] s16
 //   K_path   one WARP per path, the D disparities of a pixel spread over the lanes (4 or 8 per lane, one 8/16-byte
-//            access per step), predecessor costs in registers, neighbours d-1/d+1 by two shuffles, min over d by one
+//            access per step), predecessor costs in registers as u16x2 pairs, the recurrence in VIADDMNMX.S16x2 /
+//            VIMNMX.S16x2 (two disparities per instruction), neighbours d-1/d+1 by two shuffles, min over d by one
 //            REDUX; C of the next 16 steps is in flight through a per-warp cp.async ring in shared memory, so the only
 //            latency on the chain is the recurrence itself.  A path is one warp and the paths are few (2h horizontal,
 //            2(W1+h-1) diagonal, W1 vertical), so all five directions run at once on three streams, each into its own
-//            volume L_r[y][x][d] s16.
+//            volume: L - C (it lies in [0, P2]) as one byte per cost when P2 <= 255, L as s16 otherwise.  The diagonal
+//            and vertical launches are issue-bound and put two paths into a warp (K_path2, D <= 128).
 //   K_wta    warp per pixel: S = min(32767, sum of the five L) (every L is >= 0, so OpenCV's two saturating adds
 //            collapse into this and the order of the directions is free), winner-take-all, uniqueness test, the
 //            neighbours for the sub-pixel step and the right-view disparity (one atomicMin on a packed
@@ -26,6 +28,8 @@
 //   K_reproj reprojectImageTo3D on the float-converted 16x disparity + the reference's gate 0.01 < z <= 5 and y flip,
 //            then an order-preserving compaction (CUB DeviceSelect) -> points + their pixel indices for the
 //            caller's colour lookup.
+// A repeated (size, parameters) call replays the whole pipeline as one CUDA graph (sgbm_run); pageable caller buffers
+// travel through pinned staging owned by the context.
 #include <cub/cub.cuh>
 
 #include "common.cuh"
@@ -36,7 +40,6 @@ constexpr int SG_MAX_COST = 32767;
 constexpr int SG_TX = 64;          // columns per K_hsum CTA
 constexpr int SG_MAX_D = 256;
 constexpr int SG_MAX_R = 5;        // block size <= 11
-constexpr int SG_PF = 8;           // prefetch distance of the path kernel (steps)
 constexpr unsigned SG_KEY_INIT = 0xFFFFFFFFu;
 
 struct Sgbm {
