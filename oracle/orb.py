@@ -1,0 +1,159 @@
+"""ORB descriptor stage (rBRIEF) as the reference's loop detector gets it from `ORB::detectAndCompute`
+(reference src/optimizationStuff.cpp:49-56).  TEST INFRASTRUCTURE ONLY.
+
+OpenCV is a third-party dependency the reference does not vendor; the parity pin is cv2 4.13.0 as importable in this
+image.  What is restated here is the *descriptor* half of ORB for caller-made keypoints on one pyramid level
+(`cv2.ORB.compute(img, keypoints)` with octave 0): the smoothing ORB applies before sampling, the rotation of the
+256 test pairs and the comparisons.  The detector half (FAST-9, Harris ranking, the 8-level pyramid, IC_Angle) is not
+restated yet.
+
+Three things had to be recovered from cv2 itself, because OpenCV's source is not in the reference tree:
+
+* PATTERN, the 256 rBRIEF test pairs (orb.cpp: bit_pattern_31_).  cv2 does not export the table.
+  tests/golden/recover_orb_pattern.py recovers it: a keypoint at angle 0 on a constant image with ONE bright (dark)
+  pixel at offset p sets exactly the bits whose second (first) test point lies within the 7x7 smoothing footprint of
+  p; fitting the pair positions to the observed bit maps of all 37 x 37 offsets under the measured impulse response
+  gives every pair uniquely and with zero residual.  tests/test_oracle_orb.py re-checks the table against live cv2
+  with the forward model.
+* the smoothing: ORB blurs each pyramid level in place with GaussianBlur(7x7, sigma 2, BORDER_REFLECT_101); the level
+  is a sub-matrix of the pyramid buffer, for which OpenCV does NOT take its bit-exact fixed-point Gaussian but the
+  generic float separable filter (`cv2.sepFilter2D` with `getGaussianKernel(7, 2, CV_32F)` reproduces ORB's bits,
+  `cv2.GaussianBlur` on the whole image does not: 2,862 of 466,616 pixels differ by 1 on the golden frame).
+* the evaluation order of that float filter in this build (AVX2/FMA dispatch): rows  s = k0*p0, s = fma(k_j, p_j, s)
+  for j = 1..6;  columns  t = k3*s0, t = fma(k_{3+j}, s_{+j} + s_{-j}, t) for j = 1..3;  result = rint(t).  Of the
+  eight fused/unfused/symmetric variants this is the one with zero differing pixels (the others differ at 1-3 pixels
+  per frame), so a cv2 built for another instruction set may differ from this restatement in isolated bits.
+"""
+import numpy as np
+
+# (x1, y1, x2, y2) of test k: bit k of the descriptor = I(p1) < I(p2)
+PATTERN = np.array([
+    (8, -3, 9, 5), (4, 2, 7, -12), (-11, 9, -8, 2), (7, -12, 12, -13),
+    (2, -13, 2, 12), (1, -7, 1, 6), (-2, -10, -2, -4), (-13, -13, -11, -8),
+    (-13, -3, -12, -9), (10, 4, 11, 9), (-13, -8, -8, -9), (-11, 7, -9, 12),
+    (7, 7, 12, 6), (-4, -5, -3, 0), (-13, 2, -12, -3), (-9, 0, -7, 5),
+    (12, -6, 12, -1), (-3, 6, -2, 12), (-6, -13, -4, -8), (11, -13, 12, -8),
+    (4, 7, 5, 1), (5, -3, 10, -3), (3, -7, 6, 12), (-8, -7, -6, -2),
+    (-2, 11, -1, -10), (-13, 12, -8, 10), (-7, 3, -5, -3), (-4, 2, -3, 7),
+    (-10, -12, -6, 11), (5, -12, 6, -7), (5, -6, 7, -1), (1, 0, 4, -5),
+    (9, 11, 11, -13), (4, 7, 4, 12), (2, -1, 4, 4), (-4, -12, -2, 7),
+    (-8, -5, -7, -10), (4, 11, 9, 12), (0, -8, 1, -13), (-13, -2, -8, 2),
+    (-3, -2, -2, 3), (-6, 9, -4, -9), (8, 12, 10, 7), (0, 9, 1, 3),
+    (7, -5, 11, -10), (-13, -6, -11, 0), (10, 7, 12, 1), (-6, -3, -6, 12),
+    (10, -9, 12, -4), (-13, 8, -8, -12), (-13, 0, -8, -4), (3, 3, 7, 8),
+    (5, 7, 10, -7), (-1, 7, 1, -12), (3, -10, 5, 6), (2, -4, 3, -10),
+    (-13, 0, -13, 5), (-13, -7, -12, 12), (-13, 3, -11, 8), (-7, 12, -4, 7),
+    (6, -10, 12, 8), (-9, -1, -7, -6), (-2, -5, 0, 12), (-12, 5, -7, 5),
+    (3, -10, 8, -13), (-7, -7, -4, 5), (-3, -2, -1, -7), (2, 9, 5, -11),
+    (-11, -13, -5, -13), (-1, 6, 0, -1), (5, -3, 5, 2), (-4, -13, -4, 12),
+    (-9, -6, -9, 6), (-12, -10, -8, -4), (10, 2, 12, -3), (7, 12, 12, 12),
+    (-7, -13, -6, 5), (-4, 9, -3, 4), (7, -1, 12, 2), (-7, 6, -5, 1),
+    (-13, 11, -12, 5), (-3, 7, -2, -6), (7, -8, 12, -7), (-13, -7, -11, -12),
+    (1, -3, 12, 12), (2, -6, 3, 0), (-4, 3, -2, -13), (-1, -13, 1, 9),
+    (7, 1, 8, -6), (1, -1, 3, 12), (9, 1, 12, 6), (-1, -9, -1, 3),
+    (-13, -13, -10, 5), (7, 7, 10, 12), (12, -5, 12, 9), (6, 3, 7, 11),
+    (5, -13, 6, 10), (2, -12, 2, 3), (3, 8, 4, -6), (2, 6, 12, -13),
+    (9, -12, 10, 3), (-8, 4, -7, 9), (-11, 12, -4, -6), (1, 12, 2, -8),
+    (6, -9, 7, -4), (2, 3, 3, -2), (6, 3, 11, 0), (3, -3, 8, -8),
+    (7, 8, 9, 3), (-11, -5, -6, -4), (-10, 11, -5, 10), (-5, -8, -3, 12),
+    (-10, 5, -9, 0), (8, -1, 12, -6), (4, -6, 6, -11), (-10, 12, -8, 7),
+    (4, -2, 6, 7), (-2, 0, -2, 12), (-5, -8, -5, 2), (7, -6, 10, 12),
+    (-9, -13, -8, -8), (-5, -13, -5, -2), (8, -8, 9, -13), (-9, -11, -9, 0),
+    (1, -8, 1, -2), (7, -4, 9, 1), (-2, 1, -1, -4), (11, -6, 12, -11),
+    (-12, -9, -6, 4), (3, 7, 7, 12), (5, 5, 10, 8), (0, -4, 2, 8),
+    (-9, 12, -5, -13), (0, 7, 2, 12), (-1, 2, 1, 7), (5, 11, 7, -9),
+    (3, 5, 6, -8), (-13, -4, -8, 9), (-5, 9, -3, -3), (-4, -7, -3, -12),
+    (6, 5, 8, 0), (-7, 6, -6, 12), (-13, 6, -5, -2), (1, -10, 3, 10),
+    (4, 1, 8, -4), (-2, -2, 2, -13), (2, -12, 12, 12), (-2, -13, 0, -6),
+    (4, 1, 9, 3), (-6, -10, -3, -5), (-3, -13, -1, 1), (7, 5, 12, -11),
+    (4, -2, 5, -7), (-13, 9, -9, -5), (7, 1, 8, 6), (7, -8, 7, 6),
+    (-7, -4, -7, 1), (-8, 11, -7, -8), (-13, 6, -12, -8), (2, 4, 3, 9),
+    (10, -5, 12, 3), (-6, -5, -6, 7), (8, -3, 9, -8), (2, -12, 2, 8),
+    (-11, -2, -10, 3), (-12, -13, -7, -9), (-11, 0, -10, -5), (5, -3, 11, 8),
+    (-2, -13, -1, 12), (-1, -8, 0, 9), (-13, -11, -12, -5), (-10, -2, -10, 11),
+    (-3, 9, -2, -13), (2, -3, 3, 2), (-9, -13, -4, 0), (-4, 6, -3, -10),
+    (-4, 12, -2, -7), (-6, -11, -4, 9), (6, -3, 6, 11), (-13, 11, -5, 5),
+    (11, 11, 12, 6), (7, -5, 12, -2), (-1, 12, 0, 7), (-4, -8, -3, -2),
+    (-7, 1, -6, 7), (-13, -12, -8, -13), (-7, -2, -6, -8), (-8, 5, -6, -9),
+    (-5, -1, -4, 5), (-13, 7, -8, 10), (1, 5, 5, -13), (1, 0, 10, -13),
+    (9, 12, 10, -1), (5, -8, 10, -9), (-1, 11, 1, -13), (-9, -3, -6, 2),
+    (-1, -10, 1, 12), (-13, 1, -8, -10), (8, -11, 10, -6), (2, -13, 3, -6),
+    (7, -13, 12, -9), (-10, -10, -5, -7), (-10, -8, -8, -13), (4, -6, 8, 5),
+    (3, 12, 8, -13), (-4, 2, -3, -3), (5, -13, 10, -12), (4, -13, 5, -1),
+    (-9, 9, -4, 3), (0, 3, 3, -9), (-12, 1, -6, 1), (3, 2, 4, -8),
+    (-10, -10, -10, 9), (8, -13, 12, 12), (-8, -12, -6, -5), (2, 2, 3, 7),
+    (10, 6, 11, -8), (6, 8, 8, -12), (-7, 10, -6, 5), (-3, -9, -3, 9),
+    (-1, -13, -1, 5), (-3, -7, -3, 4), (-8, -2, -8, 3), (4, 2, 12, 12),
+    (2, -5, 3, 11), (6, -9, 11, -13), (3, -1, 7, 12), (11, -1, 12, 4),
+    (-3, 0, -3, 6), (4, -11, 4, 12), (2, -4, 2, 1), (-10, -6, -8, 1),
+    (-13, 7, -11, 1), (-13, 12, -11, -13), (6, 0, 11, -13), (0, -1, 1, 4),
+    (-13, 3, -9, -2), (-9, 8, -6, -3), (-13, -6, -8, -2), (5, -9, 8, 10),
+    (2, 7, 3, -9), (-1, -6, -1, -1), (9, 5, 11, -2), (11, -3, 12, -8),
+    (3, 0, 3, 5), (-1, 4, 0, 10), (3, -6, 4, 5), (-13, 0, -10, 5),
+    (5, 8, 12, 11), (8, 9, 9, -6), (7, -4, 8, -12), (-10, 4, -10, 9),
+    (7, 3, 12, 4), (9, -7, 10, -2), (7, 0, 12, -2), (-1, -6, 0, -11),
+], np.int32)
+
+HALF_PATCH_REACH = 19      # no rotated test point leaves [-19, 19]^2 (|p| <= 13 * sqrt(2))
+
+
+def gaussian_kernel_7_2():
+    """getGaussianKernel(7, 2, CV_32F): exp(-x^2 / (2 sigma^2)) normalised, computed in double, stored as float."""
+    x = np.arange(-3, 4, dtype=np.float64)
+    k = np.exp(-(x * x) / 8.0)
+    return (k / k.sum()).astype(np.float32)
+
+
+def _fma(a, b, c):
+    return (a.astype(np.float64) * np.float64(b) + c.astype(np.float64)).astype(np.float32)
+
+
+def smooth(img):
+    """The image ORB samples its descriptors from (see the module docstring for the evaluation order)."""
+    img = np.asarray(img, np.uint8)
+    h, w = img.shape
+    k = gaussian_kernel_7_2()
+    p = np.pad(img, 3, mode="reflect").astype(np.float32)
+    s = (p[:, 0:w] * k[0]).astype(np.float32)
+    for j in range(1, 7):
+        s = _fma(p[:, j:j + w], k[j], s)
+    t = (s[3:3 + h] * k[3]).astype(np.float32)
+    for j in range(1, 4):
+        t = _fma((s[3 + j:3 + j + h] + s[3 - j:3 - j + h]).astype(np.float32), k[3 + j], t)
+    return np.clip(np.rint(t), 0, 255).astype(np.uint8)
+
+
+def smooth_call_through(img):
+    import cv2
+    k = cv2.getGaussianKernel(7, 2, cv2.CV_32F)
+    return cv2.sepFilter2D(np.ascontiguousarray(img), -1, k, k, borderType=cv2.BORDER_REFLECT_101)
+
+
+def describe(img, xy, angle_deg, smoothed=None):
+    """rBRIEF descriptors (n x 32 uint8) of keypoints xy (n x 2 float32) with angles in degrees on ONE level.
+    orb.cpp computeOrbDescriptors: angle *= (float)(CV_PI / 180); a = (float)cos(angle), b = (float)sin(angle);
+    test point (x, y) -> (cvRound(x*a - y*b), cvRound(x*b + y*a)) around (cvRound(pt.x), cvRound(pt.y))."""
+    sm = smooth(img) if smoothed is None else smoothed
+    xy = np.asarray(xy, np.float32).reshape(-1, 2)
+    ang = np.asarray(angle_deg, np.float32).reshape(-1) * np.float32(np.pi / 180.0)
+    a = np.cos(ang.astype(np.float64)).astype(np.float32)[:, None, None]
+    b = np.sin(ang.astype(np.float64)).astype(np.float32)[:, None, None]
+    px = PATTERN[:, [0, 2]].astype(np.float32)[None]
+    py = PATTERN[:, [1, 3]].astype(np.float32)[None]
+    ix = np.rint((px * a).astype(np.float32) - (py * b).astype(np.float32)).astype(np.int64)
+    iy = np.rint((px * b).astype(np.float32) + (py * a).astype(np.float32)).astype(np.int64)
+    cx = np.rint(xy[:, 0]).astype(np.int64)[:, None, None]
+    cy = np.rint(xy[:, 1]).astype(np.int64)[:, None, None]
+    v = sm[cy + iy, cx + ix].astype(np.int32)
+    return np.packbits((v[..., 0] < v[..., 1]).astype(np.uint8), axis=1, bitorder="little")
+
+
+def describe_call_through(img, xy, angle_deg):
+    """cv2.ORB_create().compute on caller-made octave-0 keypoints (size 31); cv2 drops keypoints closer than 31 px
+    to the border, so the caller keeps them inside."""
+    import cv2
+    kps = [cv2.KeyPoint(float(x), float(y), 31.0, float(a), 1.0, 0, -1)
+           for (x, y), a in zip(np.asarray(xy, np.float32), np.asarray(angle_deg, np.float32))]
+    out_kp, desc = cv2.ORB_create().compute(np.ascontiguousarray(img), kps)
+    assert len(out_kp) == len(kps), "cv2 dropped keypoints (too close to the border)"
+    return desc

@@ -1,0 +1,48 @@
+"""oracle/orb.py (ORB's descriptor stage: the recovered rBRIEF table, the smoothing ORB really applies, the rotated
+comparisons) pinned against live cv2 4.13.0 and the golden vectors (tests/golden/vo_golden_v4.npz)."""
+import importlib.util
+import os
+
+import numpy as np
+
+from oracle import orb
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _recover():
+    spec = importlib.util.spec_from_file_location("recover_orb_pattern", os.path.join(GOLD, "recover_orb_pattern.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+def test_pattern_table_reproduces_cv2_impulse_maps():
+    """every one of the 2 x 37 x 37 single-impulse descriptors cv2 produces is predicted by the embedded table"""
+    m = _recover()
+    assert orb.PATTERN.shape == (256, 4) and np.abs(orb.PATTERN).max() == 13
+    assert np.array_equal(m.predict(orb.PATTERN), m.observe())
+    # and a wrong table is noticed
+    bad = orb.PATTERN.copy()
+    bad[17, 0] += 1
+    assert not np.array_equal(m.predict(bad)[:, 17], m.predict(orb.PATTERN)[:, 17])
+
+
+def test_smoothing_and_descriptors_match_cv2():
+    g = np.load(os.path.join(GOLD, "vo_golden_v1.npz"))
+    for key in ("L0", "R1"):
+        assert np.array_equal(orb.smooth(g[key]), orb.smooth_call_through(g[key]))
+    rng = np.random.default_rng(5)
+    n = 2000
+    xy = np.c_[rng.uniform(32, 1208, n), rng.uniform(32, 343, n)].astype(np.float32)
+    ang = rng.uniform(0, 360, n).astype(np.float32)
+    ang[:8] = (0, 90, 180, 270, 45, 359.99, 0.01, 135)
+    assert np.array_equal(orb.describe(g["L0"], xy, ang), orb.describe_call_through(g["L0"], xy, ang))
+
+
+def test_golden_v4():
+    g = np.load(os.path.join(GOLD, "vo_golden_v1.npz"))
+    g4 = np.load(os.path.join(GOLD, "vo_golden_v4.npz"))
+    assert np.array_equal(orb.describe(g["L0"], g4["orb_xy"], g4["orb_angle"]), g4["orb_desc"])
+    sm = orb.smooth(g["L0"])
+    assert int(sm.astype(np.int64).sum()) == int(g4["orb_smooth_sum"]) and np.array_equal(sm[200], g4["orb_smooth_row200"])
