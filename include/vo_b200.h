@@ -235,6 +235,18 @@ int vo_sgbm_timing(vo_ctx* ctx, float ms[9], float* pipeline_ms);
  * winner-take-all, 2 = after the left-right check (both int16 [h][w]), 3 = prefilter planes (uchar4 [4][h][w]) */
 int vo_debug_sgbm_stage(vo_ctx* ctx, int stage, void* out, uint64_t bytes);
 
+/* ---- SURVEY 8(f)-2, first step: the descriptor half of ORB for the loop detector (src/optimizationStuff.cpp:49-56,
+ * ORB::create()->detectAndCompute).  rBRIEF descriptors (32 bytes each) of caller-made keypoints on ONE 8-bit
+ * pyramid level: xy = n x (x, y) in that level's pixels, angle_deg = n keypoint angles in degrees (cv::KeyPoint::angle);
+ * bit-identical to cv2.ORB_create().compute(img, keypoints) of cv2 4.13.0 for octave-0 keypoints.  Keypoints must lie
+ * at least 19.5 px inside the image (cv2 itself drops those closer than 31 px).  The detector half (FAST-9, Harris
+ * ranking, pyramid, IC_Angle) is not built yet. */
+int vo_orb_describe(vo_ctx* ctx, const uint8_t* img, int stride, int width, int height, const float* xy,
+                    const float* angle_deg, int n, uint8_t* desc);
+/* the image ORB samples its descriptors from: GaussianBlur(7x7, sigma 2, BORDER_REFLECT_101) as OpenCV evaluates it on
+ * a pyramid level (the float separable-filter path, not the fixed-point Gaussian) */
+int vo_orb_smooth(vo_ctx* ctx, const uint8_t* img, int stride, int width, int height, uint8_t* out, int out_stride);
+
 /* ---- a-8  Rodrigues + inversion, src/VisualSLAM.cpp:70-74,93-97: pose3x4 = [R^T | -R^T tvec]. */
 int vo_pose_from_pnp(const double rvec[3], const double tvec[3], double pose3x4[12]);
 

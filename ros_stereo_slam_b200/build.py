@@ -32,9 +32,10 @@ SOURCES = {
     "selfcheck.cu": ["--fmad=false"],
     "sor.cu": ["--fmad=false"],
     "sgbm.cu": ["--fmad=false"],
+    "orb.cu": ["--fmad=false"],
     "aux.cu": [],
 }
-HEADERS = ["common.cuh", "cvmath.cuh", "fmat7.cuh", os.path.join("..", "..", "include", "vo_b200.h")]
+HEADERS = ["common.cuh", "cvmath.cuh", "fmat7.cuh", "orb_pattern.h", os.path.join("..", "..", "include", "vo_b200.h")]
 
 
 def _nvcc():

@@ -142,6 +142,7 @@ static void free_chain(vo_ctx* c) {
   if (!c) return;
   if (c->stream) cudaStreamSynchronize(c->stream);
   sgbm_free(c);
+  orb_free(c);
   void* dev[] = {c->d_xy_in, c->d_xy_trk, c->d_status, c->d_err, c->d_xyz_in, c->d_c_ref, c->d_c_trk, c->d_c_xyz,
                  c->d_f_ref, c->d_f_trk, c->d_f_xyz, c->d_xyz_tmp, c->d_mask, c->d_idx, c->d_seq_xy, c->d_seq_xyz,
                  c->d_count, c->d_tile_state, c->d_samples, c->d_models, c->d_counts, c->d_sel, c->d_pose, c->d_cam,

@@ -170,6 +170,7 @@ struct vo_ctx {
   void* d_sor = nullptr;          // SORcloud scratch: sort keys / order / sorted points / CUB temp (lazily allocated)
   size_t sor_tmp_bytes = 0;
   void* sgbm = nullptr;           // vo::Sgbm (sgbm.cu): dense-stereo buffers, allocated by the first SGBM call
+  void* orb = nullptr;            // vo::Orb (orb.cu): ORB descriptor-stage buffers
   float* h_pts = nullptr;         // cap * 8 floats
 
   // LK work counters
@@ -217,6 +218,7 @@ int pyr_unpack_rows(vo_ctx* c, int slot, const uint8_t* d_src, int src_pitch);
 int bgr2gray_launch(vo_ctx* c, const uint8_t* d_bgr, int src_pitch, uint8_t* d_gray, int dst_pitch);
 int bgr2gray_launch_wh(vo_ctx* c, const uint8_t* d_bgr, int src_pitch, uint8_t* d_gray, int dst_pitch, int w, int h);
 void sgbm_free(vo_ctx* c);
+void orb_free(vo_ctx* c);
 PyrView pyr_view(const Pyramid& p);
 
 int lk_launch(vo_ctx* c, int slot_prev, int slot_next, const float2* d_prev, int n, float2* d_next, uint8_t* d_status,

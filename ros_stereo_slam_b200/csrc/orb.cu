@@ -1,0 +1,192 @@
+// orb.cu -- the descriptor half of ORB for the loop detector (reference src/optimizationStuff.cpp:49-56:
+// ORB::create()->detectAndCompute feeds DBoW2).  SURVEY.md section 8(f)-2, first step: rBRIEF descriptors of
+// caller-made keypoints on one pyramid level, bit-identical to cv2.ORB.compute (cv2 4.13.0; oracle/orb.py is the
+// restatement).  The detector half (FAST-9, Harris ranking, 8-level pyramid, IC_Angle) is not built yet.
+//
+//   K_rows   the smoothing ORB applies before sampling is NOT OpenCV's fixed-point Gaussian: the pyramid level is a
+//            sub-matrix, for which GaussianBlur falls back to the generic float separable filter.  Row pass:
+//            s = k0 * p(x-3), then s = fma(k_j, p(x-3+j), s), j = 1..6, BORDER_REFLECT_101 -> float plane
+//   K_cols   t = k3 * s(y), then t = fma(k_{3+j}, s(y+j) + s(y-j), t), j = 1..3; rint, saturate -> u8
+//            (this evaluation order is the one cv2's AVX2/FMA build uses: zero differing pixels on whole frames)
+//   K_desc   a thread per (keypoint, descriptor byte): angle in degrees -> (float)cos/sin of the double angle, the 16
+//            test points of the byte rotated in float without contraction, cvRound, 8 comparisons
+#include "common.cuh"
+#include "orb_pattern.h"
+
+namespace vo {
+
+struct Orb {
+  int w = 0, h = 0, cap = 0;
+  uint8_t* img = nullptr;
+  float* rowf = nullptr;
+  uint8_t* sm = nullptr;
+  float* xy = nullptr;
+  float* ang = nullptr;
+  uint8_t* desc = nullptr;
+};
+
+__constant__ signed char c_orb_pattern[256][4];
+__constant__ float c_orb_gauss[4];
+
+void orb_free(vo_ctx* c) {
+  Orb* o = reinterpret_cast<Orb*>(c->orb);
+  if (!o) return;
+  void* dev[] = {o->img, o->rowf, o->sm, o->xy, o->ang, o->desc};
+  for (void* p : dev) cudaFree(p);
+  delete o;
+  c->orb = nullptr;
+}
+
+__device__ __forceinline__ int orb_reflect101(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * n - 2 - i;
+  return i;
+}
+
+__global__ void orb_smooth_rows_kernel(const uint8_t* __restrict__ img, int w, int h, float* __restrict__ rowf) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= w) return;
+  const uint8_t* r = img + (size_t)y * w;
+  float s = __fmul_rn(c_orb_gauss[0], (float)r[orb_reflect101(x - 3, w)]);
+#pragma unroll
+  for (int j = 1; j < 7; j++) s = __fmaf_rn(c_orb_gauss[j < 4 ? j : 6 - j], (float)r[orb_reflect101(x - 3 + j, w)], s);
+  rowf[(size_t)y * w + x] = s;
+}
+
+__global__ void orb_smooth_cols_kernel(const float* __restrict__ rowf, int w, int h, uint8_t* __restrict__ out) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= w) return;
+  float t = __fmul_rn(c_orb_gauss[3], rowf[(size_t)y * w + x]);
+#pragma unroll
+  for (int j = 1; j < 4; j++) {
+    const float a = rowf[(size_t)orb_reflect101(y + j, h) * w + x], b = rowf[(size_t)orb_reflect101(y - j, h) * w + x];
+    t = __fmaf_rn(c_orb_gauss[3 - j], __fadd_rn(a, b), t);
+  }
+  const int v = __float2int_rn(t);
+  out[(size_t)y * w + x] = (uint8_t)min(max(v, 0), 255);
+}
+
+// computeOrbDescriptors (orb.cpp), WTA_K = 2
+__global__ void orb_describe_kernel(const uint8_t* __restrict__ sm, int w, int h, const float* __restrict__ xy,
+                                    const float* __restrict__ ang, int n, uint8_t* __restrict__ desc) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int kp = t >> 5, byte = t & 31;
+  if (kp >= n) return;
+  float angle = ang[kp];
+  angle = __fmul_rn(angle, (float)(3.14159265358979323846 / 180.0));      // angle *= (float)(CV_PI / 180.f)
+  const float a = (float)cos((double)angle), b = (float)sin((double)angle);
+  const int cx = __float2int_rn(xy[2 * kp]), cy = __float2int_rn(xy[2 * kp + 1]);
+  const uint8_t* center = sm + (size_t)cy * w + cx;
+  unsigned val = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const signed char* p = c_orb_pattern[8 * byte + k];
+    int v[2];
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const float px = (float)p[2 * e], py = (float)p[2 * e + 1];
+      const float x = __fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b));
+      const float y = __fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a));
+      v[e] = center[__float2int_rn(y) * w + __float2int_rn(x)];
+    }
+    val |= (unsigned)(v[0] < v[1]) << k;
+  }
+  desc[(size_t)kp * 32 + byte] = (uint8_t)val;
+}
+
+static int orb_ensure(vo_ctx* c, int w, int h, int n) {
+  Orb* o = reinterpret_cast<Orb*>(c->orb);
+  if (!o) {
+    o = new Orb();
+    c->orb = o;
+    VO_CUDA(cudaMemcpyToSymbol(c_orb_pattern, ORB_PATTERN_31, sizeof(ORB_PATTERN_31)));
+    VO_CUDA(cudaMemcpyToSymbol(c_orb_gauss, ORB_GAUSS_7_2, sizeof(ORB_GAUSS_7_2)));
+  }
+  if ((size_t)w * h > (size_t)o->w * o->h) {
+    VO_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(o->img);
+    cudaFree(o->rowf);
+    cudaFree(o->sm);
+    o->img = nullptr; o->rowf = nullptr; o->sm = nullptr;
+    const size_t npx = (size_t)w * h;
+    VO_CUDA(cudaMalloc(&o->img, npx));
+    VO_CUDA(cudaMalloc(&o->rowf, npx * sizeof(float)));
+    VO_CUDA(cudaMalloc(&o->sm, npx));
+    o->w = w;
+    o->h = h;
+  }
+  if (n > o->cap) {
+    VO_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(o->xy);
+    cudaFree(o->ang);
+    cudaFree(o->desc);
+    o->xy = nullptr; o->ang = nullptr; o->desc = nullptr;
+    VO_CUDA(cudaMalloc(&o->xy, (size_t)n * 2 * sizeof(float)));
+    VO_CUDA(cudaMalloc(&o->ang, (size_t)n * sizeof(float)));
+    VO_CUDA(cudaMalloc(&o->desc, (size_t)n * 32));
+    o->cap = n;
+  }
+  return VO_OK;
+}
+
+static int orb_smooth_enqueue(vo_ctx* c, Orb* o, const uint8_t* img, int stride, int w, int h) {
+  VO_CUDA(cudaMemcpy2DAsync(o->img, w, img, stride, w, h, cudaMemcpyDefault, c->stream));
+  {
+    LaunchScope ls(c, VO_K_MISC);
+    orb_smooth_rows_kernel<<<dim3(div_up(w, 128), h), 128, 0, c->stream>>>(o->img, w, h, o->rowf);
+  }
+  {
+    LaunchScope ls(c, VO_K_MISC);
+    orb_smooth_cols_kernel<<<dim3(div_up(w, 128), h), 128, 0, c->stream>>>(o->rowf, w, h, o->sm);
+  }
+  VO_CUDA(cudaGetLastError());
+  return VO_OK;
+}
+
+}  // namespace vo
+
+using namespace vo;
+
+int vo_orb_smooth(vo_ctx* c, const uint8_t* img, int stride, int width, int height, uint8_t* out, int out_stride) {
+  if (!c) return VO_ERR_INVALID_ARG;
+  VO_CUDA(cudaSetDevice(c->device));
+  if (!img || !out || width < 7 || height < 7 || stride < width || out_stride < width) return VO_ERR_INVALID_ARG;
+  VO_TRY(orb_ensure(c, width, height, 0));
+  Orb* o = reinterpret_cast<Orb*>(c->orb);
+  VO_TRY(orb_smooth_enqueue(c, o, img, stride, width, height));
+  VO_CUDA(cudaMemcpy2DAsync(out, out_stride, o->sm, width, width, height, cudaMemcpyDefault, c->stream));
+  VO_CUDA(cudaStreamSynchronize(c->stream));
+  return VO_OK;
+}
+
+int vo_orb_describe(vo_ctx* c, const uint8_t* img, int stride, int width, int height, const float* xy,
+                    const float* angle_deg, int n, uint8_t* desc) {
+  if (!c) return VO_ERR_INVALID_ARG;
+  VO_CUDA(cudaSetDevice(c->device));
+  if (!img || width < 64 || height < 64 || stride < width || n < 0 || (n > 0 && (!xy || !angle_deg || !desc)))
+    return VO_ERR_INVALID_ARG;
+  if (n == 0) return VO_OK;
+  // a rotated test point reaches 19 px from the rounded centre; cv2 itself drops keypoints closer than 31 px
+  for (int i = 0; i < n; i++) {
+    const float x = xy[2 * i], y = xy[2 * i + 1];
+    if (!(x >= 19.5f && x <= (float)width - 20.5f && y >= 19.5f && y <= (float)height - 20.5f)) {
+      set_error("vo_orb_describe: keypoint %d (%.2f, %.2f) is closer than 19.5 px to the image border", i, x, y);
+      return VO_ERR_INVALID_ARG;
+    }
+  }
+  VO_TRY(orb_ensure(c, width, height, n));
+  Orb* o = reinterpret_cast<Orb*>(c->orb);
+  VO_TRY(orb_smooth_enqueue(c, o, img, stride, width, height));
+  VO_CUDA(cudaMemcpyAsync(o->xy, xy, (size_t)n * 2 * sizeof(float), cudaMemcpyDefault, c->stream));
+  VO_CUDA(cudaMemcpyAsync(o->ang, angle_deg, (size_t)n * sizeof(float), cudaMemcpyDefault, c->stream));
+  {
+    LaunchScope ls(c, VO_K_MISC);
+    orb_describe_kernel<<<div_up(n * 32, 256), 256, 0, c->stream>>>(o->sm, width, height, o->xy, o->ang, n, o->desc);
+  }
+  VO_CUDA(cudaGetLastError());
+  VO_CUDA(cudaMemcpyAsync(desc, o->desc, (size_t)n * 32, cudaMemcpyDefault, c->stream));
+  VO_CUDA(cudaStreamSynchronize(c->stream));
+  return VO_OK;
+}

@@ -186,6 +186,25 @@ class VisualFrontEnd:
         check(self.lib.vo_debug_sgbm_stage(self.h, int(stage), _p(out), C.c_uint64(out.nbytes)))
         return out
 
+    # ---- ORB descriptor stage (reference src/optimizationStuff.cpp:49-56)
+    def orbDescribe(self, img, xy, angle_deg):
+        """rBRIEF descriptors (n x 32 uint8) of caller-made keypoints on one pyramid level, = OpenCV's ORB::compute."""
+        a = _u8img(img)
+        if a.ndim != 2:
+            raise ValueError("gray image expected")
+        pts = _f32(xy, 2)
+        ang = np.ascontiguousarray(angle_deg, np.float32).reshape(-1)
+        n = len(pts)
+        desc = np.zeros((max(n, 1), 32), np.uint8)
+        check(self.lib.vo_orb_describe(self.h, _p(a), a.strides[0], a.shape[1], a.shape[0], _p(pts), _p(ang), n, _p(desc)))
+        return desc[:n]
+
+    def orbSmooth(self, img):
+        a = _u8img(img)
+        out = np.zeros(a.shape, np.uint8)
+        check(self.lib.vo_orb_smooth(self.h, _p(a), a.strides[0], a.shape[1], a.shape[0], _p(out), out.strides[0]))
+        return out
+
     def cvtColorBGR2GRAY(self, bgr):
         """cv::cvtColor(bgr, CV_BGR2GRAY) on the device (bit-exact with OpenCV's 15-bit fixed point)."""
         a = np.ascontiguousarray(bgr)
