@@ -1,0 +1,46 @@
+"""ORB descriptor stage timing on the GPU box: vo_orb_describe (host image + keypoints in, descriptors out) against
+cv2.ORB.compute with the same caller-made keypoints.   python tools/orb_bench.py [n_keypoints]"""
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import cv2
+    from oracle import orb
+    from ros_stereo_slam_b200 import VisualFrontEnd
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
+    g = np.load(os.path.join(ROOT, "tests", "golden", "vo_golden_v1.npz"))
+    img = g["L0"]
+    rng = np.random.default_rng(3)
+    xy = np.c_[rng.uniform(32, 1208, n), rng.uniform(32, 343, n)].astype(np.float32)
+    ang = rng.uniform(0, 360, n).astype(np.float32)
+    fe = VisualFrontEnd()
+    d = fe.orbDescribe(img, xy, ang)
+    ref = orb.describe_call_through(img, xy, ang)
+    print("%d keypoints: %d descriptors differ from cv2 %s" % (n, int((d != ref).any(1).sum()), cv2.__version__))
+    ts = []
+    for _ in range(200):
+        t = time.perf_counter()
+        fe.orbDescribe(img, xy, ang)
+        ts.append(time.perf_counter() - t)
+    print("vo_orb_describe (smoothing + %d descriptors, host in / host out): median %.3f ms" % (n, 1e3 * np.median(ts[50:])))
+    cv2.setNumThreads(len(os.sched_getaffinity(0)))
+    o = cv2.ORB_create()
+    kps = [cv2.KeyPoint(float(x), float(y), 31.0, float(a), 1.0, 0, -1) for (x, y), a in zip(xy, ang)]
+    tc = []
+    for _ in range(10):
+        t = time.perf_counter()
+        o.compute(img, kps)
+        tc.append(time.perf_counter() - t)
+    print("cv2.ORB.compute on %d host cores: median %.2f ms" % (len(os.sched_getaffinity(0)), 1e3 * np.median(tc)))
+    fe.close()
+
+
+if __name__ == "__main__":
+    main()
