@@ -239,10 +239,16 @@ int vo_debug_sgbm_stage(vo_ctx* ctx, int stage, void* out, uint64_t bytes);
  * ORB::create()->detectAndCompute).  rBRIEF descriptors (32 bytes each) of caller-made keypoints on ONE 8-bit
  * pyramid level: xy = n x (x, y) in that level's pixels, angle_deg = n keypoint angles in degrees (cv::KeyPoint::angle);
  * bit-identical to cv2.ORB_create().compute(img, keypoints) of cv2 4.13.0 for octave-0 keypoints.  Keypoints must lie
- * at least 19.5 px inside the image (cv2 itself drops those closer than 31 px).  The detector half (FAST-9, Harris
- * ranking, pyramid, IC_Angle) is not built yet. */
+ * at least 19.5 px inside the image (cv2 itself drops those closer than 31 px).  angle_deg = NULL computes the angles
+ * the way detectAndCompute does (vo_orb_angles below).  The rest of the detector half (FAST-9, Harris ranking, pyramid)
+ * is not built yet. */
 int vo_orb_describe(vo_ctx* ctx, const uint8_t* img, int stride, int width, int height, const float* xy,
                     const float* angle_deg, int n, uint8_t* desc);
+/* ORB's orientation step (orb.cpp ICAngles): intensity-centroid angle in degrees of each keypoint on the UNSMOOTHED
+ * level, patch radius 15, cv::fastAtan2; bit-identical to the angles cv2.ORB.detect reports for octave-0 keypoints.
+ * Keypoints must lie at least 15.5 px inside the image. */
+int vo_orb_angles(vo_ctx* ctx, const uint8_t* img, int stride, int width, int height, const float* xy, int n,
+                  float* angle_deg);
 /* the image ORB samples its descriptors from: GaussianBlur(7x7, sigma 2, BORDER_REFLECT_101) as OpenCV evaluates it on
  * a pyramid level (the float separable-filter path, not the fixed-point Gaussian) */
 int vo_orb_smooth(vo_ctx* ctx, const uint8_t* img, int stride, int width, int height, uint8_t* out, int out_stride);

@@ -157,3 +157,70 @@ def describe_call_through(img, xy, angle_deg):
     out_kp, desc = cv2.ORB_create().compute(np.ascontiguousarray(img), kps)
     assert len(out_kp) == len(kps), "cv2 dropped keypoints (too close to the border)"
     return desc
+
+
+# ---------------------------------------------------------------------------------------------- orientation
+def umax_table(half_patch=15):
+    """orb.cpp: the half-width of every row of the circular patch"""
+    import math
+    s2 = float(np.float32(np.sqrt(np.float32(2.0))))
+    vmax = int(math.floor(half_patch * s2 / 2 + 1))
+    vmin = int(math.ceil(half_patch * s2 / 2))
+    u = [0] * (half_patch + 2)
+    for v in range(vmax + 1):
+        u[v] = int(np.rint(math.sqrt(half_patch * half_patch - v * v)))
+    v0 = 0
+    for v in range(half_patch, vmin - 1, -1):
+        while u[v0] == u[v0 + 1]:
+            v0 += 1
+        u[v] = v0
+        v0 += 1
+    return u[:half_patch + 1]
+
+
+def fast_atan2(y, x):
+    """cv::fastAtan2 (degrees), scalar float path: odd 7th-order polynomial in min/max, no contraction."""
+    f = np.float32
+    y = np.asarray(y, f)
+    x = np.asarray(x, f)
+    s = f(180.0 / np.pi)
+    p1, p3 = f(0.9997878412794807) * s, f(-0.3258083974640975) * s
+    p5, p7 = f(0.1555786518463281) * s, f(-0.04432655554792128) * s
+    ax, ay = np.abs(x), np.abs(y)
+    eps = f(2.220446049250313e-16)
+    with np.errstate(all="ignore"):
+        c = np.where(ax >= ay, ay / (ax + eps), ax / (ay + eps)).astype(f)
+    c2 = (c * c).astype(f)
+    a = ((((((p7 * c2).astype(f) + p5).astype(f) * c2).astype(f) + p3).astype(f) * c2).astype(f) + p1).astype(f)
+    a = (a * c).astype(f)
+    a = np.where(ax >= ay, a, (f(90.0) - a).astype(f))
+    a = np.where(x < 0, (f(180.0) - a).astype(f), a)
+    a = np.where(y < 0, (f(360.0) - a).astype(f), a)
+    return a.astype(f)
+
+
+def ic_angle(img, xy, half_patch=15):
+    """orb.cpp ICAngles on the UNSMOOTHED level: m_10 = sum u*I, m_01 = sum v*I over the circular patch around the
+    rounded keypoint position, angle = fastAtan2((float)m_01, (float)m_10) in degrees."""
+    I = np.asarray(img, np.uint8).astype(np.int64)
+    xy = np.asarray(xy, np.float32).reshape(-1, 2)
+    cx = np.rint(xy[:, 0]).astype(np.int64)
+    cy = np.rint(xy[:, 1]).astype(np.int64)
+    um = umax_table(half_patch)
+    m10 = np.zeros(len(xy), np.int64)
+    m01 = np.zeros(len(xy), np.int64)
+    for v in range(-half_patch, half_patch + 1):
+        d = um[abs(v)]
+        for u in range(-d, d + 1):
+            val = I[cy + v, cx + u]
+            m10 += u * val
+            m01 += v * val
+    return fast_atan2(m01.astype(np.float32), m10.astype(np.float32))
+
+
+def detect_call_through(img, nfeatures=30000, fast_threshold=3, octave=0):
+    """cv2.ORB.detect: (xy, angle) of the keypoints of one octave -- the pin for ic_angle"""
+    import cv2
+    kps = [k for k in cv2.ORB_create(nfeatures=nfeatures, fastThreshold=fast_threshold).detect(np.ascontiguousarray(img), None)
+           if k.octave == octave]
+    return (np.array([k.pt for k in kps], np.float32).reshape(-1, 2), np.array([k.angle for k in kps], np.float32))

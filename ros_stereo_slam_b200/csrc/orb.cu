@@ -1,13 +1,17 @@
 // orb.cu -- the descriptor half of ORB for the loop detector (reference src/optimizationStuff.cpp:49-56:
 // ORB::create()->detectAndCompute feeds DBoW2).  SURVEY.md section 8(f)-2, first step: rBRIEF descriptors of
 // caller-made keypoints on one pyramid level, bit-identical to cv2.ORB.compute (cv2 4.13.0; oracle/orb.py is the
-// restatement).  The detector half (FAST-9, Harris ranking, 8-level pyramid, IC_Angle) is not built yet.
+// restatement).  IC_Angle, the orientation step in front of it, is built too; the rest of the detector half (FAST-9, Harris
+// ranking, 8-level pyramid) is not built yet.
 //
 //   K_rows   the smoothing ORB applies before sampling is NOT OpenCV's fixed-point Gaussian: the pyramid level is a
 //            sub-matrix, for which GaussianBlur falls back to the generic float separable filter.  Row pass:
 //            s = k0 * p(x-3), then s = fma(k_j, p(x-3+j), s), j = 1..6, BORDER_REFLECT_101 -> float plane
 //   K_cols   t = k3 * s(y), then t = fma(k_{3+j}, s(y+j) + s(y-j), t), j = 1..3; rint, saturate -> u8
 //            (this evaluation order is the one cv2's AVX2/FMA build uses: zero differing pixels on whole frames)
+//   K_angle  IC_Angle on the UNSMOOTHED level: a warp per keypoint, lane = column u of the circular patch (radius 15,
+//            row half-widths from OpenCV's u_max table), integer moments m_10 / m_01 reduced by shuffles, then
+//            cv::fastAtan2 (7th-order polynomial, float, no contraction) -> degrees
 //   K_desc   a thread per (keypoint, descriptor byte): angle in degrees -> (float)cos/sin of the double angle, the 16
 //            test points of the byte rotated in float without contraction, cvRound, 8 comparisons
 #include "common.cuh"
@@ -66,6 +70,58 @@ __global__ void orb_smooth_cols_kernel(const float* __restrict__ rowf, int w, in
   }
   const int v = __float2int_rn(t);
   out[(size_t)y * w + x] = (uint8_t)min(max(v, 0), 255);
+}
+
+// orb.cpp: half-width of row v of the circular patch of radius 15
+__constant__ int c_orb_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+
+// cv::fastAtan2(y, x), scalar float path
+__device__ __forceinline__ float orb_fast_atan2(float y, float x) {
+  const float s = (float)(180.0 / 3.14159265358979323846);
+  const float p1 = __fmul_rn(0.9997878412794807f, s), p3 = __fmul_rn(-0.3258083974640975f, s);
+  const float p5 = __fmul_rn(0.1555786518463281f, s), p7 = __fmul_rn(-0.04432655554792128f, s);
+  const float ax = fabsf(x), ay = fabsf(y), eps = 2.220446049250313e-16f;
+  const bool xs = ax >= ay;
+  const float c = xs ? __fdiv_rn(ay, __fadd_rn(ax, eps)) : __fdiv_rn(ax, __fadd_rn(ay, eps));
+  const float c2 = __fmul_rn(c, c);
+  float a = __fadd_rn(__fmul_rn(p7, c2), p5);
+  a = __fadd_rn(__fmul_rn(a, c2), p3);
+  a = __fadd_rn(__fmul_rn(a, c2), p1);
+  a = __fmul_rn(a, c);
+  if (!xs) a = __fsub_rn(90.f, a);
+  if (x < 0) a = __fsub_rn(180.f, a);
+  if (y < 0) a = __fsub_rn(360.f, a);
+  return a;
+}
+
+// ICAngles (orb.cpp): one warp per keypoint, lane l = column u = l - 15 (lane 31 idles)
+__global__ void orb_angle_kernel(const uint8_t* __restrict__ img, int w, int h, const float* __restrict__ xy, int n,
+                                 float* __restrict__ ang) {
+  const int kp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (kp >= n) return;
+  const int cx = __float2int_rn(xy[2 * kp]), cy = __float2int_rn(xy[2 * kp + 1]);
+  const int u = lane - 15;
+  int m10 = 0, m01 = 0;
+  if (lane < 31) {
+    const uint8_t* c = img + (size_t)cy * w + cx + u;
+    int col = c[0];                         // sum of the column (for m_10)
+    const int au = abs(u);
+    for (int v = 1; v <= 15; v++) {
+      if (au <= c_orb_umax[v]) {
+        const int vp = c[v * w], vm = c[-v * w];
+        col += vp + vm;
+        m01 += v * (vp - vm);
+      }
+    }
+    m10 = u * col;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+    m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+  }
+  if (lane == 0) ang[kp] = orb_fast_atan2((float)m01, (float)m10);
 }
 
 // computeOrbDescriptors (orb.cpp), WTA_K = 2
@@ -165,8 +221,7 @@ int vo_orb_describe(vo_ctx* c, const uint8_t* img, int stride, int width, int he
                     const float* angle_deg, int n, uint8_t* desc) {
   if (!c) return VO_ERR_INVALID_ARG;
   VO_CUDA(cudaSetDevice(c->device));
-  if (!img || width < 64 || height < 64 || stride < width || n < 0 || (n > 0 && (!xy || !angle_deg || !desc)))
-    return VO_ERR_INVALID_ARG;
+  if (!img || width < 64 || height < 64 || stride < width || n < 0 || (n > 0 && (!xy || !desc))) return VO_ERR_INVALID_ARG;
   if (n == 0) return VO_OK;
   // a rotated test point reaches 19 px from the rounded centre; cv2 itself drops keypoints closer than 31 px
   for (int i = 0; i < n; i++) {
@@ -180,13 +235,45 @@ int vo_orb_describe(vo_ctx* c, const uint8_t* img, int stride, int width, int he
   Orb* o = reinterpret_cast<Orb*>(c->orb);
   VO_TRY(orb_smooth_enqueue(c, o, img, stride, width, height));
   VO_CUDA(cudaMemcpyAsync(o->xy, xy, (size_t)n * 2 * sizeof(float), cudaMemcpyDefault, c->stream));
-  VO_CUDA(cudaMemcpyAsync(o->ang, angle_deg, (size_t)n * sizeof(float), cudaMemcpyDefault, c->stream));
+  if (angle_deg) {
+    VO_CUDA(cudaMemcpyAsync(o->ang, angle_deg, (size_t)n * sizeof(float), cudaMemcpyDefault, c->stream));
+  } else {   // what detectAndCompute does: IC_Angle on the unsmoothed level
+    LaunchScope ls(c, VO_K_MISC);
+    orb_angle_kernel<<<div_up(n * 32, 256), 256, 0, c->stream>>>(o->img, width, height, o->xy, n, o->ang);
+  }
   {
     LaunchScope ls(c, VO_K_MISC);
     orb_describe_kernel<<<div_up(n * 32, 256), 256, 0, c->stream>>>(o->sm, width, height, o->xy, o->ang, n, o->desc);
   }
   VO_CUDA(cudaGetLastError());
   VO_CUDA(cudaMemcpyAsync(desc, o->desc, (size_t)n * 32, cudaMemcpyDefault, c->stream));
+  VO_CUDA(cudaStreamSynchronize(c->stream));
+  return VO_OK;
+}
+
+int vo_orb_angles(vo_ctx* c, const uint8_t* img, int stride, int width, int height, const float* xy, int n,
+                  float* angle_deg) {
+  if (!c) return VO_ERR_INVALID_ARG;
+  VO_CUDA(cudaSetDevice(c->device));
+  if (!img || width < 64 || height < 64 || stride < width || n < 0 || (n > 0 && (!xy || !angle_deg))) return VO_ERR_INVALID_ARG;
+  if (n == 0) return VO_OK;
+  for (int i = 0; i < n; i++) {
+    const float x = xy[2 * i], y = xy[2 * i + 1];
+    if (!(x >= 15.5f && x <= (float)width - 16.5f && y >= 15.5f && y <= (float)height - 16.5f)) {
+      set_error("vo_orb_angles: keypoint %d (%.2f, %.2f) is closer than 15.5 px to the image border", i, x, y);
+      return VO_ERR_INVALID_ARG;
+    }
+  }
+  VO_TRY(orb_ensure(c, width, height, n));
+  Orb* o = reinterpret_cast<Orb*>(c->orb);
+  VO_CUDA(cudaMemcpy2DAsync(o->img, width, img, stride, width, height, cudaMemcpyDefault, c->stream));
+  VO_CUDA(cudaMemcpyAsync(o->xy, xy, (size_t)n * 2 * sizeof(float), cudaMemcpyDefault, c->stream));
+  {
+    LaunchScope ls(c, VO_K_MISC);
+    orb_angle_kernel<<<div_up(n * 32, 256), 256, 0, c->stream>>>(o->img, width, height, o->xy, n, o->ang);
+  }
+  VO_CUDA(cudaGetLastError());
+  VO_CUDA(cudaMemcpyAsync(angle_deg, o->ang, (size_t)n * sizeof(float), cudaMemcpyDefault, c->stream));
   VO_CUDA(cudaStreamSynchronize(c->stream));
   return VO_OK;
 }

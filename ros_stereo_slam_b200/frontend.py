@@ -187,17 +187,27 @@ class VisualFrontEnd:
         return out
 
     # ---- ORB descriptor stage (reference src/optimizationStuff.cpp:49-56)
-    def orbDescribe(self, img, xy, angle_deg):
-        """rBRIEF descriptors (n x 32 uint8) of caller-made keypoints on one pyramid level, = OpenCV's ORB::compute."""
+    def orbDescribe(self, img, xy, angle_deg=None):
+        """rBRIEF descriptors (n x 32 uint8) of caller-made keypoints on one pyramid level, = OpenCV's ORB::compute;
+        angle_deg=None computes the intensity-centroid angles first, as detectAndCompute does."""
         a = _u8img(img)
         if a.ndim != 2:
             raise ValueError("gray image expected")
         pts = _f32(xy, 2)
-        ang = np.ascontiguousarray(angle_deg, np.float32).reshape(-1)
+        ang = None if angle_deg is None else np.ascontiguousarray(angle_deg, np.float32).reshape(-1)
         n = len(pts)
         desc = np.zeros((max(n, 1), 32), np.uint8)
         check(self.lib.vo_orb_describe(self.h, _p(a), a.strides[0], a.shape[1], a.shape[0], _p(pts), _p(ang), n, _p(desc)))
         return desc[:n]
+
+    def orbAngles(self, img, xy):
+        """ORB's orientation step (ICAngles): angle in degrees of each keypoint."""
+        a = _u8img(img)
+        pts = _f32(xy, 2)
+        n = len(pts)
+        ang = np.zeros(max(n, 1), np.float32)
+        check(self.lib.vo_orb_angles(self.h, _p(a), a.strides[0], a.shape[1], a.shape[0], _p(pts), n, _p(ang)))
+        return ang[:n]
 
     def orbSmooth(self, img):
         a = _u8img(img)

@@ -57,3 +57,18 @@ def test_rejected_keypoints(fe):
     with pytest.raises(VoError):
         fe.orbDescribe(g["L0"], np.array([[10.0, 100.0]], np.float32), np.zeros(1, np.float32))
     assert fe.orbDescribe(g["L0"], np.zeros((0, 2), np.float32), np.zeros(0, np.float32)).shape == (0, 32)
+
+
+def test_orientation_and_detect_and_compute_descriptors(fe):
+    """IC_Angle on the GPU = the angles cv2.ORB.detect reports; describe(angle_deg=None) = detectAndCompute's descriptors"""
+    from oracle import orb
+    g = golden()
+    for key in ("L0", "R1"):
+        xy, ang = orb.detect_call_through(g[key])
+        got = fe.orbAngles(g[key], xy)
+        assert np.array_equal(got, orb.ic_angle(g[key], xy))
+        assert np.array_equal(got, ang)                                # live cv2, bit for bit (integer moments + fastAtan2)
+    xy, ang = orb.detect_call_through(g["L0"])
+    d = fe.orbDescribe(g["L0"], xy)                                    # angles computed on the device
+    assert np.array_equal(d, orb.describe(g["L0"], xy, ang))
+    assert (d != orb.describe_call_through(g["L0"], xy, ang)).any(1).mean() <= 0.001

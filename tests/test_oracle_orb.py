@@ -46,3 +46,20 @@ def test_golden_v4():
     assert np.array_equal(orb.describe(g["L0"], g4["orb_xy"], g4["orb_angle"]), g4["orb_desc"])
     sm = orb.smooth(g["L0"])
     assert int(sm.astype(np.int64).sum()) == int(g4["orb_smooth_sum"]) and np.array_equal(sm[200], g4["orb_smooth_row200"])
+
+
+def test_orientation_matches_cv2_detect():
+    """IC_Angle + fastAtan2: the angle of every octave-0 keypoint cv2.ORB.detect reports, bit for bit"""
+    g = np.load(os.path.join(GOLD, "vo_golden_v1.npz"))
+    assert orb.umax_table() == [15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3]
+    total = 0
+    for key in ("L0", "R1"):
+        xy, ang = orb.detect_call_through(g[key])
+        assert len(xy) > 1500
+        assert np.array_equal(orb.ic_angle(g[key], xy), ang)
+        total += len(xy)
+        # and detectAndCompute's descriptors of those keypoints = describe(ic_angle)
+        if key == "L0":
+            assert np.array_equal(orb.describe(g[key], xy[:800], orb.ic_angle(g[key], xy[:800])),
+                                  orb.describe_call_through(g[key], xy[:800], ang[:800]))
+    assert total > 3000
