@@ -249,6 +249,16 @@ int vo_orb_describe(vo_ctx* ctx, const uint8_t* img, int stride, int width, int 
  * Keypoints must lie at least 15.5 px inside the image. */
 int vo_orb_angles(vo_ctx* ctx, const uint8_t* img, int stride, int width, int height, const float* xy, int n,
                   float* angle_deg);
+/* cv::FAST (TYPE_9_16, the detector ORB runs on every pyramid level with fastThreshold 20 and non-maximum
+ * suppression; orb.cpp computeKeyPoints): corners in raster order with their scores (cornerScore<16>), identical to
+ * cv2.FastFeatureDetector_create(threshold, nonmax).detect -- positions, order and responses.  *n = number of corners
+ * found (VO_ERR_CAPACITY when it exceeds cap; the first cap are written); score may be NULL. */
+int vo_fast9(vo_ctx* ctx, const uint8_t* img, int stride, int width, int height, int threshold, int nonmax_suppression,
+             float* xy, float* score, int cap, int* n);
+/* the response ORB ranks its keypoints by (orb.cpp HarrisResponses, blockSize 7, k = 0.04): bit-identical to
+ * cv::KeyPoint::response of cv2.ORB.detect for octave-0 keypoints.  Keypoints at least 4.5 px inside the image. */
+int vo_orb_harris(vo_ctx* ctx, const uint8_t* img, int stride, int width, int height, const float* xy, int n,
+                  float* response);
 /* the image ORB samples its descriptors from: GaussianBlur(7x7, sigma 2, BORDER_REFLECT_101) as OpenCV evaluates it on
  * a pyramid level (the float separable-filter path, not the fixed-point Gaussian) */
 int vo_orb_smooth(vo_ctx* ctx, const uint8_t* img, int stride, int width, int height, uint8_t* out, int out_stride);

@@ -224,3 +224,87 @@ def detect_call_through(img, nfeatures=30000, fast_threshold=3, octave=0):
     kps = [k for k in cv2.ORB_create(nfeatures=nfeatures, fastThreshold=fast_threshold).detect(np.ascontiguousarray(img), None)
            if k.octave == octave]
     return (np.array([k.pt for k in kps], np.float32).reshape(-1, 2), np.array([k.angle for k in kps], np.float32))
+
+
+# ---------------------------------------------------------------------------------------------- ranking
+def harris_response(img, xy, block=7, k=0.04):
+    """orb.cpp HarrisResponses: 3x3 Sobel-like gradients summed over a block x block window around the rounded
+    keypoint (integers), response = (a*b - c*c - k*(a+b)^2) * scale^4 in float, scale = 1 / (4 * block * 255).
+    This is the `response` cv2.ORB.detect reports and ranks by."""
+    I = np.asarray(img, np.uint8).astype(np.int64)
+    xy = np.asarray(xy, np.float32).reshape(-1, 2)
+    r = block // 2
+    x0 = np.rint(xy[:, 0]).astype(np.int64)
+    y0 = np.rint(xy[:, 1]).astype(np.int64)
+    a = np.zeros(len(xy), np.int64)
+    b = np.zeros(len(xy), np.int64)
+    c = np.zeros(len(xy), np.int64)
+    for i in range(block):
+        for j in range(block):
+            y, x = y0 - r + i, x0 - r + j
+            ix = (I[y, x + 1] - I[y, x - 1]) * 2 + (I[y - 1, x + 1] - I[y - 1, x - 1]) + (I[y + 1, x + 1] - I[y + 1, x - 1])
+            iy = (I[y + 1, x] - I[y - 1, x]) * 2 + (I[y + 1, x - 1] - I[y - 1, x - 1]) + (I[y + 1, x + 1] - I[y - 1, x + 1])
+            a += ix * ix
+            b += iy * iy
+            c += ix * iy
+    f = np.float32
+    scale = f(1.0) / f(f(4 * block) * f(255.0))
+    s4 = f(f(f(scale * scale) * scale) * scale)
+    af, bf, cf = a.astype(f), b.astype(f), c.astype(f)
+    t = ((af * bf).astype(f) - (cf * cf).astype(f)).astype(f)
+    apb = (af + bf).astype(f)
+    t = (t - ((f(k) * apb).astype(f) * apb).astype(f)).astype(f)
+    return (t * s4).astype(f)
+
+
+def detect_call_through_full(img, nfeatures=30000, fast_threshold=3, octave=0):
+    """(xy, angle, response) of cv2.ORB.detect's keypoints of one octave"""
+    import cv2
+    kps = [k for k in cv2.ORB_create(nfeatures=nfeatures, fastThreshold=fast_threshold).detect(np.ascontiguousarray(img), None)
+           if k.octave == octave]
+    return (np.array([k.pt for k in kps], np.float32).reshape(-1, 2), np.array([k.angle for k in kps], np.float32),
+            np.array([k.response for k in kps], np.float32))
+
+
+# ---------------------------------------------------------------------------------------------- detection
+FAST_CIRCLE = [(0, 3), (1, 3), (2, 2), (3, 1), (3, 0), (3, -1), (2, -2), (1, -3), (0, -3), (-1, -3), (-2, -2), (-3, -1),
+               (-3, 0), (-3, 1), (-2, 2), (-1, 3)]
+
+
+def fast9(img, threshold=20, nonmax=True):
+    """cv::FAST (TYPE_9_16), the detector ORB runs on every pyramid level (orb.cpp computeKeyPoints:
+    FastFeatureDetector::create(fastThreshold, true)).  A pixel is a corner when 9 contiguous pixels of the 16-pixel
+    circle are all darker than v - t or all brighter than v + t; its score (cornerScore<16>) is the largest such
+    margin minus 1; non-maximum suppression keeps a corner whose score is strictly greater than its 8 neighbours'
+    (non-corners count as 0).  Returns (xy float32 in raster order, score float32, score map)."""
+    I = np.asarray(img, np.uint8).astype(np.int32)
+    h, w = I.shape
+    v = I[3:h - 3, 3:w - 3]
+    d = np.stack([v - I[3 + dy:h - 3 + dy, 3 + dx:w - 3 + dx] for dx, dy in FAST_CIRCLE], 0)
+    d2 = np.concatenate([d, d[:8]], 0)
+    dark = np.stack([d2[k:k + 9].min(0) for k in range(16)], 0).max(0)
+    bright = np.stack([(-d2[k:k + 9]).min(0) for k in range(16)], 0).max(0)
+    best = np.maximum(dark, bright)
+    S = np.zeros((h, w), np.int32)
+    S[3:h - 3, 3:w - 3] = np.where(best > threshold, best - 1, 0)
+    if nonmax:
+        c = S[1:-1, 1:-1]
+        keep = c > 0
+        for dy in (-1, 0, 1):
+            for dx in (-1, 0, 1):
+                if dx or dy:
+                    keep &= c > S[1 + dy:h - 1 + dy, 1 + dx:w - 1 + dx]
+        K = np.zeros((h, w), bool)
+        K[1:-1, 1:-1] = keep
+    else:
+        K = S > 0
+    ys, xs = np.nonzero(K)
+    return np.c_[xs, ys].astype(np.float32), S[ys, xs].astype(np.float32), S
+
+
+def fast9_call_through(img, threshold=20, nonmax=True):
+    import cv2
+    det = cv2.FastFeatureDetector_create(threshold=threshold, nonmaxSuppression=nonmax,
+                                         type=cv2.FAST_FEATURE_DETECTOR_TYPE_9_16)
+    kps = det.detect(np.ascontiguousarray(img), None)
+    return (np.array([k.pt for k in kps], np.float32).reshape(-1, 2), np.array([k.response for k in kps], np.float32))

@@ -9,11 +9,17 @@
 //            s = k0 * p(x-3), then s = fma(k_j, p(x-3+j), s), j = 1..6, BORDER_REFLECT_101 -> float plane
 //   K_cols   t = k3 * s(y), then t = fma(k_{3+j}, s(y+j) + s(y-j), t), j = 1..3; rint, saturate -> u8
 //            (this evaluation order is the one cv2's AVX2/FMA build uses: zero differing pixels on whole frames)
+//   K_fast   cv::FAST (TYPE_9_16), the detector ORB runs on every level: a thread per pixel gathers the 16 circle
+//            differences, the corner score (cornerScore<16>) is the best over the 16 arcs of 9 of the smallest margin,
+//            minus 1; non-maximum suppression (strictly greater than the 8 neighbours) and a raster-order compaction
+//            (CUB DeviceSelect) give cv::FAST's keypoint list, order included
 //   K_angle  IC_Angle on the UNSMOOTHED level: a warp per keypoint, lane = column u of the circular patch (radius 15,
 //            row half-widths from OpenCV's u_max table), integer moments m_10 / m_01 reduced by shuffles, then
 //            cv::fastAtan2 (7th-order polynomial, float, no contraction) -> degrees
 //   K_desc   a thread per (keypoint, descriptor byte): angle in degrees -> (float)cos/sin of the double angle, the 16
 //            test points of the byte rotated in float without contraction, cvRound, 8 comparisons
+#include <cub/cub.cuh>
+
 #include "common.cuh"
 #include "orb_pattern.h"
 
@@ -27,6 +33,13 @@ struct Orb {
   float* xy = nullptr;
   float* ang = nullptr;
   uint8_t* desc = nullptr;
+  int* score = nullptr;            // FAST corner scores [h][w]
+  uint8_t* flag = nullptr;
+  int* sel = nullptr;              // selected flat pixel indices
+  int* d_n = nullptr;
+  void* cub_tmp = nullptr;
+  size_t cub_bytes = 0;
+  size_t px_cap = 0;               // pixels the FAST buffers are sized for
 };
 
 __constant__ signed char c_orb_pattern[256][4];
@@ -35,7 +48,7 @@ __constant__ float c_orb_gauss[4];
 void orb_free(vo_ctx* c) {
   Orb* o = reinterpret_cast<Orb*>(c->orb);
   if (!o) return;
-  void* dev[] = {o->img, o->rowf, o->sm, o->xy, o->ang, o->desc};
+  void* dev[] = {o->img, o->rowf, o->sm, o->xy, o->ang, o->desc, o->score, o->flag, o->sel, o->d_n, o->cub_tmp};
   for (void* p : dev) cudaFree(p);
   delete o;
   c->orb = nullptr;
@@ -70,6 +83,65 @@ __global__ void orb_smooth_cols_kernel(const float* __restrict__ rowf, int w, in
   }
   const int v = __float2int_rn(t);
   out[(size_t)y * w + x] = (uint8_t)min(max(v, 0), 255);
+}
+
+// cv::FAST, patternSize 16: circle offsets in OpenCV's order
+__constant__ int c_fast_dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+__constant__ int c_fast_dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+
+// score map: cornerScore<16> for corners (> 0 since threshold >= 1 ... the score of a corner is >= threshold), 0 otherwise
+__global__ void fast_score_kernel(const uint8_t* __restrict__ img, int w, int h, int threshold, int* __restrict__ score) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= w) return;
+  int sc = 0;
+  if (x >= 3 && x < w - 3 && y >= 3 && y < h - 3) {
+    const uint8_t* p = img + (size_t)y * w + x;
+    const int v = p[0];
+    int d[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) d[k] = v - (int)p[c_fast_dy[k] * w + c_fast_dx[k]];
+    // quick rejection (the test cv::FAST starts with): an arc of 9 contains one pixel of every opposite pair
+    int best = -256;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      int lo = d[k], hi = d[k];
+#pragma unroll
+      for (int j = 1; j < 9; j++) {
+        const int e = d[(k + j) & 15];
+        lo = min(lo, e);
+        hi = max(hi, e);
+      }
+      best = max(best, max(lo, -hi));      // all darker by >= lo, or all brighter by >= -hi
+    }
+    if (best > threshold) sc = best - 1;
+  }
+  score[(size_t)y * w + x] = sc;
+}
+
+__global__ void fast_nms_kernel(const int* __restrict__ score, int w, int h, int nonmax, uint8_t* __restrict__ flag) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= w) return;
+  const size_t i = (size_t)y * w + x;
+  const int s = score[i];
+  bool keep = s > 0;
+  if (keep && nonmax) {
+    // corners live in [3, w-3) x [3, h-3): the 8 neighbours exist
+    keep = s > score[i - 1] && s > score[i + 1] && s > score[i - w - 1] && s > score[i - w] && s > score[i - w + 1] &&
+           s > score[i + w - 1] && s > score[i + w] && s > score[i + w + 1];
+  }
+  flag[i] = keep ? 1 : 0;
+}
+
+__global__ void fast_gather_kernel(const int* __restrict__ sel, const int* __restrict__ d_n, int cap, const int* __restrict__ score,
+                                   int w, float* __restrict__ xy, float* __restrict__ sc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= min(*d_n, cap)) return;
+  const int q = sel[i];
+  xy[2 * i] = (float)(q % w);
+  xy[2 * i + 1] = (float)(q / w);
+  sc[i] = (float)score[q];
 }
 
 // orb.cpp: half-width of row v of the circular patch of radius 15
@@ -122,6 +194,40 @@ __global__ void orb_angle_kernel(const uint8_t* __restrict__ img, int w, int h, 
     m01 += __shfl_xor_sync(0xffffffffu, m01, o);
   }
   if (lane == 0) ang[kp] = orb_fast_atan2((float)m01, (float)m10);
+}
+
+// HarrisResponses (orb.cpp): the response ORB ranks its keypoints by.  A warp per keypoint, lanes over the 49 window
+// pixels, integer sums reduced by shuffles, the float formula in OpenCV's order.
+__global__ void orb_harris_kernel(const uint8_t* __restrict__ img, int w, int h, const float* __restrict__ xy, int n,
+                                  float harris_k, float* __restrict__ resp) {
+  const int kp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (kp >= n) return;
+  const int x0 = __float2int_rn(xy[2 * kp]), y0 = __float2int_rn(xy[2 * kp + 1]);
+  long long a = 0, b = 0, c = 0;
+  for (int q = lane; q < 49; q += 32) {
+    const uint8_t* p = img + (size_t)(y0 - 3 + q / 7) * w + (x0 - 3 + q % 7);
+    const int ix = ((int)p[1] - (int)p[-1]) * 2 + ((int)p[-w + 1] - (int)p[-w - 1]) + ((int)p[w + 1] - (int)p[w - 1]);
+    const int iy = ((int)p[w] - (int)p[-w]) * 2 + ((int)p[w - 1] - (int)p[-w - 1]) + ((int)p[w + 1] - (int)p[-w + 1]);
+    a += ix * ix;
+    b += iy * iy;
+    c += ix * iy;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+  }
+  if (lane == 0) {
+    const float scale = __fdiv_rn(1.f, __fmul_rn(28.f, 255.f));       // 1 / ((1 << 2) * blockSize * 255)
+    const float s4 = __fmul_rn(__fmul_rn(__fmul_rn(scale, scale), scale), scale);
+    const float af = (float)(int)a, bf = (float)(int)b, cf = (float)(int)c;   // OpenCV accumulates in int
+    float t = __fsub_rn(__fmul_rn(af, bf), __fmul_rn(cf, cf));
+    const float apb = __fadd_rn(af, bf);
+    t = __fsub_rn(t, __fmul_rn(__fmul_rn(harris_k, apb), apb));
+    resp[kp] = __fmul_rn(t, s4);
+  }
 }
 
 // computeOrbDescriptors (orb.cpp), WTA_K = 2
@@ -276,4 +382,88 @@ int vo_orb_angles(vo_ctx* c, const uint8_t* img, int stride, int width, int heig
   VO_CUDA(cudaMemcpyAsync(angle_deg, o->ang, (size_t)n * sizeof(float), cudaMemcpyDefault, c->stream));
   VO_CUDA(cudaStreamSynchronize(c->stream));
   return VO_OK;
+}
+
+int vo_orb_harris(vo_ctx* c, const uint8_t* img, int stride, int width, int height, const float* xy, int n, float* response) {
+  if (!c) return VO_ERR_INVALID_ARG;
+  VO_CUDA(cudaSetDevice(c->device));
+  if (!img || width < 64 || height < 64 || stride < width || n < 0 || (n > 0 && (!xy || !response))) return VO_ERR_INVALID_ARG;
+  if (n == 0) return VO_OK;
+  for (int i = 0; i < n; i++) {
+    const float x = xy[2 * i], y = xy[2 * i + 1];
+    if (!(x >= 4.5f && x <= (float)width - 5.5f && y >= 4.5f && y <= (float)height - 5.5f)) {
+      set_error("vo_orb_harris: keypoint %d (%.2f, %.2f) is closer than 4.5 px to the image border", i, x, y);
+      return VO_ERR_INVALID_ARG;
+    }
+  }
+  VO_TRY(orb_ensure(c, width, height, n));
+  Orb* o = reinterpret_cast<Orb*>(c->orb);
+  VO_CUDA(cudaMemcpy2DAsync(o->img, width, img, stride, width, height, cudaMemcpyDefault, c->stream));
+  VO_CUDA(cudaMemcpyAsync(o->xy, xy, (size_t)n * 2 * sizeof(float), cudaMemcpyDefault, c->stream));
+  {
+    LaunchScope ls(c, VO_K_MISC);
+    orb_harris_kernel<<<div_up(n * 32, 256), 256, 0, c->stream>>>(o->img, width, height, o->xy, n, 0.04f, o->ang);
+  }
+  VO_CUDA(cudaGetLastError());
+  VO_CUDA(cudaMemcpyAsync(response, o->ang, (size_t)n * sizeof(float), cudaMemcpyDefault, c->stream));
+  VO_CUDA(cudaStreamSynchronize(c->stream));
+  return VO_OK;
+}
+
+int vo_fast9(vo_ctx* c, const uint8_t* img, int stride, int width, int height, int threshold, int nonmax_suppression,
+             float* xy, float* score, int cap, int* n_out) {
+  if (!c) return VO_ERR_INVALID_ARG;
+  VO_CUDA(cudaSetDevice(c->device));
+  if (!img || !n_out || width < 7 || height < 7 || stride < width || threshold < 1 || threshold > 254 || cap < 0 ||
+      (cap > 0 && !xy))
+    return VO_ERR_INVALID_ARG;
+  *n_out = 0;
+  VO_TRY(orb_ensure(c, width, height, std::max(cap, 1)));
+  Orb* o = reinterpret_cast<Orb*>(c->orb);
+  const int n = width * height;
+  if (!o->d_n) VO_CUDA(cudaMalloc(&o->d_n, 4 * sizeof(int)));
+  const size_t npx = (size_t)o->w * o->h;            // the image buffers' size (>= n)
+  if (o->px_cap < npx) {
+    VO_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(o->score); cudaFree(o->flag); cudaFree(o->sel); cudaFree(o->cub_tmp);
+    o->score = nullptr; o->flag = nullptr; o->sel = nullptr; o->cub_tmp = nullptr;
+    o->px_cap = 0;
+    VO_CUDA(cudaMalloc(&o->score, npx * sizeof(int)));
+    VO_CUDA(cudaMalloc(&o->flag, npx));
+    VO_CUDA(cudaMalloc(&o->sel, npx * sizeof(int)));
+    size_t tb = 0;
+    VO_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, cub::CountingInputIterator<int>(0), (const uint8_t*)nullptr, (int*)nullptr,
+                                       (int*)nullptr, (int)npx, c->stream));
+    o->cub_bytes = tb;
+    VO_CUDA(cudaMalloc(&o->cub_tmp, tb + 256));
+    o->px_cap = npx;
+  }
+  VO_CUDA(cudaMemcpy2DAsync(o->img, width, img, stride, width, height, cudaMemcpyDefault, c->stream));
+  {
+    LaunchScope ls(c, VO_K_MISC);
+    fast_score_kernel<<<dim3(div_up(width, 128), height), 128, 0, c->stream>>>(o->img, width, height, threshold, o->score);
+  }
+  {
+    LaunchScope ls(c, VO_K_MISC);
+    fast_nms_kernel<<<dim3(div_up(width, 128), height), 128, 0, c->stream>>>(o->score, width, height, nonmax_suppression, o->flag);
+  }
+  size_t tb = o->cub_bytes;
+  VO_CUDA(cub::DeviceSelect::Flagged(o->cub_tmp, tb, cub::CountingInputIterator<int>(0), o->flag, o->sel, o->d_n, n, c->stream));
+  c->launch_count++;
+  if (cap > 0) {
+    LaunchScope ls(c, VO_K_MISC);
+    fast_gather_kernel<<<div_up(cap, 256), 256, 0, c->stream>>>(o->sel, o->d_n, cap, o->score, width, o->xy, o->ang);
+  }
+  VO_CUDA(cudaGetLastError());
+  int hn = 0;
+  VO_CUDA(cudaMemcpyAsync(&hn, o->d_n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  VO_CUDA(cudaStreamSynchronize(c->stream));
+  *n_out = hn;
+  const int k = std::min(hn, cap);
+  if (k > 0) {
+    VO_CUDA(cudaMemcpyAsync(xy, o->xy, (size_t)k * 2 * sizeof(float), cudaMemcpyDefault, c->stream));
+    if (score) VO_CUDA(cudaMemcpyAsync(score, o->ang, (size_t)k * sizeof(float), cudaMemcpyDefault, c->stream));
+    VO_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  return hn > cap ? VO_ERR_CAPACITY : VO_OK;
 }

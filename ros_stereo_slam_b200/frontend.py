@@ -209,6 +209,26 @@ class VisualFrontEnd:
         check(self.lib.vo_orb_angles(self.h, _p(a), a.strides[0], a.shape[1], a.shape[0], _p(pts), n, _p(ang)))
         return ang[:n]
 
+    def fast9(self, img, threshold=20, nonmax=True, cap=200000):
+        """cv::FAST (TYPE_9_16): (xy (n x 2), score (n,)) in raster order."""
+        a = _u8img(img)
+        xy = np.zeros((cap, 2), np.float32)
+        sc = np.zeros(cap, np.float32)
+        n = C.c_int()
+        check(self.lib.vo_fast9(self.h, _p(a), a.strides[0], a.shape[1], a.shape[0], int(threshold), int(bool(nonmax)),
+                                _p(xy), _p(sc), cap, C.byref(n)), ok=(_lib.VO_OK, _lib.VO_ERR_CAPACITY))
+        m = min(n.value, cap)
+        return xy[:m].copy(), sc[:m].copy()
+
+    def orbHarris(self, img, xy):
+        """The Harris response ORB ranks its keypoints by (HarrisResponses, block 7, k 0.04)."""
+        a = _u8img(img)
+        pts = _f32(xy, 2)
+        n = len(pts)
+        r = np.zeros(max(n, 1), np.float32)
+        check(self.lib.vo_orb_harris(self.h, _p(a), a.strides[0], a.shape[1], a.shape[0], _p(pts), n, _p(r)))
+        return r[:n]
+
     def orbSmooth(self, img):
         a = _u8img(img)
         out = np.zeros(a.shape, np.uint8)

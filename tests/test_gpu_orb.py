@@ -72,3 +72,35 @@ def test_orientation_and_detect_and_compute_descriptors(fe):
     d = fe.orbDescribe(g["L0"], xy)                                    # angles computed on the device
     assert np.array_equal(d, orb.describe(g["L0"], xy, ang))
     assert (d != orb.describe_call_through(g["L0"], xy, ang)).any(1).mean() <= 0.001
+
+
+def test_harris_response(fe):
+    from oracle import orb
+    g = golden()
+    for key in ("L0", "R1"):
+        xy, _, resp = orb.detect_call_through_full(g[key])
+        got = fe.orbHarris(g[key], xy)
+        assert np.array_equal(got, orb.harris_response(g[key], xy)) and np.array_equal(got, resp)
+
+
+def test_fast9_matches_cv2(fe):
+    from oracle import orb
+    g = golden()
+    for key, thr, nms in (("L0", 20, True), ("R1", 7, True), ("L1", 3, True), ("L0", 5, False), ("L0", 1, True)):
+        xy, sc = fe.fast9(g[key], thr, nms)
+        rxy, rsc = orb.fast9_call_through(g[key], thr, nms)
+        assert np.array_equal(xy, rxy), (key, thr, nms, len(xy), len(rxy))
+        oxy, osc, _ = orb.fast9(g[key], thr, nms)
+        assert np.array_equal(xy, oxy) and np.array_equal(sc, osc)
+        if nms:
+            assert np.array_equal(sc, rsc)
+    odd = g["L1"][:99, :203].copy()
+    xy, sc = fe.fast9(odd, 4)
+    rxy, rsc = orb.fast9_call_through(odd, 4)
+    assert np.array_equal(xy, rxy) and np.array_equal(sc, rsc)
+    # the level-0 front of ORB's detector: FAST -> Harris ranking -> orientation -> descriptors, all on the device
+    xy, _ = fe.fast9(g["L1"], 20)
+    inside = (xy[:, 0] >= 31) & (xy[:, 0] < 1241 - 31) & (xy[:, 1] >= 31) & (xy[:, 1] < 376 - 31)   # edgeThreshold
+    xy = xy[inside]
+    assert np.array_equal(fe.orbHarris(g["L1"], xy), orb.harris_response(g["L1"], xy))
+    assert np.array_equal(fe.orbDescribe(g["L1"], xy), orb.describe(g["L1"], xy, orb.ic_angle(g["L1"], xy)))

@@ -63,3 +63,21 @@ def test_orientation_matches_cv2_detect():
             assert np.array_equal(orb.describe(g[key], xy[:800], orb.ic_angle(g[key], xy[:800])),
                                   orb.describe_call_through(g[key], xy[:800], ang[:800]))
     assert total > 3000
+
+
+def test_harris_response_matches_cv2_detect():
+    g = np.load(os.path.join(GOLD, "vo_golden_v1.npz"))
+    for key in ("L0", "R1"):
+        xy, _, resp = orb.detect_call_through_full(g[key])
+        assert len(xy) > 1500 and np.array_equal(orb.harris_response(g[key], xy), resp)
+
+
+def test_fast9_matches_cv2():
+    g = np.load(os.path.join(GOLD, "vo_golden_v1.npz"))
+    for key, thr, nms in (("L0", 20, True), ("R1", 7, True), ("L1", 3, True), ("L0", 5, False)):
+        xy, sc, _ = orb.fast9(g[key], thr, nms)
+        rxy, rsc = orb.fast9_call_through(g[key], thr, nms)
+        assert np.array_equal(xy, rxy)                      # same corners in the same (raster) order
+        if nms:                                             # without suppression cv2 does not compute scores
+            assert np.array_equal(sc, rsc)
+    assert len(orb.fast9(g["L1"], 3)[0]) > 2000
