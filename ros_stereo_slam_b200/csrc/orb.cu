@@ -89,7 +89,17 @@ __global__ void orb_smooth_cols_kernel(const float* __restrict__ rowf, int w, in
 __constant__ int c_fast_dx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
 __constant__ int c_fast_dy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
 
-// score map: cornerScore<16> for corners (> 0 since threshold >= 1 ... the score of a corner is >= threshold), 0 otherwise
+// 9 contiguous set bits in a 16-bit circular mask
+__device__ __forceinline__ bool fast_has9(unsigned m) {
+  m |= m << 16;
+  unsigned r = m & (m >> 1);      // runs of 2
+  r &= r >> 2;                    // runs of 4
+  r &= r >> 4;                    // runs of 8
+  r &= m >> 8;                    // runs of 9
+  return (r & 0xFFFFu) != 0u;
+}
+
+// score map: cornerScore<16> for corners (>= threshold >= 1), 0 otherwise
 __global__ void fast_score_kernel(const uint8_t* __restrict__ img, int w, int h, int threshold, int* __restrict__ score) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y;
@@ -98,23 +108,29 @@ __global__ void fast_score_kernel(const uint8_t* __restrict__ img, int w, int h,
   if (x >= 3 && x < w - 3 && y >= 3 && y < h - 3) {
     const uint8_t* p = img + (size_t)y * w + x;
     const int v = p[0];
-    int d[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) d[k] = v - (int)p[c_fast_dy[k] * w + c_fast_dx[k]];
-    // quick rejection (the test cv::FAST starts with): an arc of 9 contains one pixel of every opposite pair
-    int best = -256;
+    int pv[16];
+    unsigned dark = 0u, bright = 0u;
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-      int lo = d[k], hi = d[k];
-#pragma unroll
-      for (int j = 1; j < 9; j++) {
-        const int e = d[(k + j) & 15];
-        lo = min(lo, e);
-        hi = max(hi, e);
-      }
-      best = max(best, max(lo, -hi));      // all darker by >= lo, or all brighter by >= -hi
+      pv[k] = p[c_fast_dy[k] * w + c_fast_dx[k]];
+      dark |= (unsigned)(pv[k] < v - threshold) << k;
+      bright |= (unsigned)(pv[k] > v + threshold) << k;
     }
-    if (best > threshold) sc = best - 1;
+    if (fast_has9(dark) || fast_has9(bright)) {
+      // the largest margin m such that 9 contiguous circle pixels are all darker than v - m or all brighter than v + m
+      int best = threshold;
+#pragma unroll
+      for (int k = 0; k < 16; k++) {
+        int mn = pv[k], mx = pv[k];
+#pragma unroll
+        for (int j = 1; j < 9; j++) {
+          mn = min(mn, pv[(k + j) & 15]);
+          mx = max(mx, pv[(k + j) & 15]);
+        }
+        best = max(best, max(v - mx, mn - v));
+      }
+      sc = best - 1;
+    }
   }
   score[(size_t)y * w + x] = sc;
 }
