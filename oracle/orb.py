@@ -308,3 +308,131 @@ def fast9_call_through(img, threshold=20, nonmax=True):
                                          type=cv2.FAST_FEATURE_DETECTOR_TYPE_9_16)
     kps = det.detect(np.ascontiguousarray(img), None)
     return (np.array([k.pt for k in kps], np.float32).reshape(-1, 2), np.array([k.response for k in kps], np.float32))
+
+
+# ---------------------------------------------------------------------------------------------- pyramid + glue
+def _exact_coeffs(srcsize, dstsize):
+    """resize.cpp interpolationLinear::getCoeffs for 8-bit images: source offset and the 8.8 fixed-point weight of
+    its right/lower neighbour; positions that fall off the source take the border pixel (weight 0)."""
+    import math
+    inv = np.float64(dstsize) / np.float64(srcsize)
+    scale = np.float64(1.0) / inv
+    ofs = np.zeros(dstsize, np.int64)
+    c1 = np.zeros(dstsize, np.int64)
+    for v in range(dstsize):
+        fval = scale * (np.float64(v) + 0.5) - 0.5
+        ival = math.floor(fval)
+        if ival >= 0 and srcsize > 1:
+            if ival < srcsize - 1:
+                ofs[v] = ival
+                c1[v] = int(np.rint((fval - ival) * 256.0))
+            else:
+                ofs[v] = srcsize - 1
+        # else: before the first pixel -> offset 0, weight 0
+    return ofs, c1
+
+
+def resize_linear_exact(src, dw, dh):
+    """cv::resize(..., INTER_LINEAR_EXACT) for 8-bit single-channel images: horizontal pass in 8.8 fixed point,
+    vertical pass in 16.16, rounded half up."""
+    src = np.asarray(src, np.uint8)
+    sh, sw = src.shape
+    s = src.astype(np.int64)
+    ox, cx = _exact_coeffs(sw, dw)
+    oy, cy = _exact_coeffs(sh, dh)
+    hrow = s[:, ox] * (256 - cx) + s[:, np.minimum(ox + 1, sw - 1)] * cx
+    out = hrow[oy] * (256 - cy)[:, None] + hrow[np.minimum(oy + 1, sh - 1)] * cy[:, None]
+    return ((out + 32768) >> 16).astype(np.uint8)
+
+
+SCALE_FACTOR = float(np.float32(1.2))      # ORB::create takes a float 1.2f and keeps it in a double member
+
+
+def level_scales(nlevels=8, scale_factor=SCALE_FACTOR):
+    return [np.float32(np.float64(scale_factor) ** lvl) for lvl in range(nlevels)]     # (float)std::pow(scaleFactor, level)
+
+
+def build_pyramid(img, nlevels=8, scale_factor=SCALE_FACTOR):
+    """orb.cpp detectAndCompute: level k = resize(level k-1, cvRound(size / scale_k), INTER_LINEAR_EXACT)"""
+    img = np.asarray(img, np.uint8)
+    out = [img]
+    for sc in level_scales(nlevels, scale_factor)[1:]:
+        dw = int(np.rint(np.float32(img.shape[1]) / sc))
+        dh = int(np.rint(np.float32(img.shape[0]) / sc))
+        out.append(resize_linear_exact(out[-1], dw, dh))
+    return out
+
+
+def features_per_level(nfeatures=500, nlevels=8, scale_factor=SCALE_FACTOR):
+    f = np.float32
+    factor = f(1.0 / scale_factor)
+    nd = f(f(nfeatures) * f(f(1) - factor)) / f(f(1) - f(np.float64(factor) ** np.float64(nlevels)))
+    nd = f(nd)
+    out, tot = [], 0
+    for _ in range(nlevels - 1):
+        n = int(np.rint(nd))
+        out.append(n)
+        tot += n
+        nd = f(nd * factor)
+    out.append(max(nfeatures - tot, 0))
+    return out
+
+
+def retain_best(resp, n):
+    """KeyPointsFilter::retainBest: indices of all keypoints whose response is >= the n-th largest (ties stay)"""
+    resp = np.asarray(resp)
+    if n <= 0:
+        return np.zeros(0, np.int64)
+    if len(resp) <= n:
+        return np.arange(len(resp))
+    thr = np.sort(resp)[::-1][n - 1]
+    return np.nonzero(resp >= thr)[0]
+
+
+def detect_and_compute(img, nfeatures=500, nlevels=8, scale_factor=SCALE_FACTOR, edge_threshold=31, fast_threshold=20):
+    """ORB::detectAndCompute with the reference's defaults (ORB::create(), src/optimizationStuff.cpp:49-56): per level
+    FAST -> border filter -> retainBest(2n) by FAST score -> Harris response -> retainBest(n) -> IC_Angle -> smoothing ->
+    rBRIEF; positions scaled back to level 0.  Returns a dict of arrays sorted by (octave, y, x): cv2's own order
+    inside a level is whatever std::nth_element leaves and is not part of the contract."""
+    pyr = build_pyramid(img, nlevels, scale_factor)
+    scales = level_scales(nlevels, scale_factor)
+    quota = features_per_level(nfeatures, nlevels, scale_factor)
+    out = dict(xy=[], octave=[], response=[], angle=[], desc=[], level_xy=[])
+    for lvl, (im, sf, n) in enumerate(zip(pyr, scales, quota)):
+        h, w = im.shape
+        if w < 2 * edge_threshold + 7 or h < 2 * edge_threshold + 7:
+            continue
+        xy, sc, _ = fast9(im, fast_threshold, True)
+        inside = (xy[:, 0] >= edge_threshold) & (xy[:, 0] < w - edge_threshold) & \
+                 (xy[:, 1] >= edge_threshold) & (xy[:, 1] < h - edge_threshold)
+        xy, sc = xy[inside], sc[inside]
+        keep = retain_best(sc, 2 * n)
+        xy = xy[keep]
+        resp = harris_response(im, xy)
+        keep = retain_best(resp, n)
+        xy, resp = xy[keep], resp[keep]
+        if len(xy) == 0:
+            continue
+        ang = ic_angle(im, xy)
+        desc = describe(im, xy, ang)
+        order = np.lexsort((xy[:, 0], xy[:, 1]))
+        out["level_xy"].append(xy[order])
+        out["xy"].append((xy[order] * np.float32(sf)).astype(np.float32))
+        out["octave"].append(np.full(len(xy), lvl, np.int32))
+        out["response"].append(resp[order])
+        out["angle"].append(ang[order])
+        out["desc"].append(desc[order])
+    return {k: (np.concatenate(v) if v else np.zeros((0,))) for k, v in out.items()}
+
+
+def detect_and_compute_call_through(img, nfeatures=500):
+    """cv2.ORB_create(nfeatures).detectAndCompute, sorted like detect_and_compute"""
+    import cv2
+    kps, desc = cv2.ORB_create(nfeatures=nfeatures).detectAndCompute(np.ascontiguousarray(img), None)
+    xy = np.array([k.pt for k in kps], np.float32).reshape(-1, 2)
+    octv = np.array([k.octave for k in kps], np.int32)
+    resp = np.array([k.response for k in kps], np.float32)
+    ang = np.array([k.angle for k in kps], np.float32)
+    order = np.lexsort((xy[:, 0], xy[:, 1], octv))
+    return dict(xy=xy[order], octave=octv[order], response=resp[order], angle=ang[order],
+                desc=(desc[order] if desc is not None else np.zeros((0, 32), np.uint8)))

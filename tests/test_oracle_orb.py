@@ -81,3 +81,24 @@ def test_fast9_matches_cv2():
         if nms:                                             # without suppression cv2 does not compute scores
             assert np.array_equal(sc, rsc)
     assert len(orb.fast9(g["L1"], 3)[0]) > 2000
+
+
+def test_pyramid_and_detect_and_compute_match_cv2():
+    """the 8-level INTER_LINEAR_EXACT pyramid, and the whole of ORB::detectAndCompute with the reference's defaults:
+    the keypoint SET of every octave (positions, responses, angles) and the descriptors, bit for bit"""
+    import cv2
+    g = np.load(os.path.join(GOLD, "vo_golden_v1.npz"))
+    pyr = orb.build_pyramid(g["L0"])
+    assert [p.shape for p in pyr][:3] == [(376, 1241), (313, 1034), (261, 862)]
+    prev = g["L0"]
+    for lvl in range(1, 8):
+        ref = cv2.resize(prev, pyr[lvl].shape[::-1], interpolation=cv2.INTER_LINEAR_EXACT)
+        assert np.array_equal(pyr[lvl], ref)
+        prev = ref
+    assert orb.features_per_level() == [109, 90, 75, 63, 52, 44, 36, 31]
+    for key, nf in (("L0", 500), ("R1", 500), ("L1", 2000)):
+        a = orb.detect_and_compute(g[key], nf)
+        b = orb.detect_and_compute_call_through(g[key], nf)
+        assert len(a["xy"]) == len(b["xy"]) > 300
+        for k in ("xy", "octave", "response", "angle", "desc"):
+            assert np.array_equal(a[k], b[k]), (key, k)
