@@ -249,6 +249,15 @@ int vo_orb_describe(vo_ctx* ctx, const uint8_t* img, int stride, int width, int 
  * Keypoints must lie at least 15.5 px inside the image. */
 int vo_orb_angles(vo_ctx* ctx, const uint8_t* img, int stride, int width, int height, const float* xy, int n,
                   float* angle_deg);
+/* ORB::create()->detectAndCompute(img, noArray(), keypoints, descriptors) as the loop detector calls it
+ * (src/optimizationStuff.cpp:49-56; ORB::create() defaults with nfeatures = 500 there): 8-level INTER_LINEAR_EXACT
+ * pyramid, per level FAST-9/16 (threshold 20, suppression) -> border filter (31) -> retainBest(2n) by FAST score ->
+ * Harris response -> retainBest(n) -> IC_Angle -> smoothing -> rBRIEF, positions scaled back to level 0.  The keypoint
+ * SET of every octave (position, response, angle) and the descriptors are bit-identical to cv2 4.13.0; the order is
+ * (octave, y, x) -- OpenCV's order inside an octave is whatever std::nth_element leaves.  octave / response /
+ * angle_deg may be NULL; *n = number of keypoints (VO_ERR_CAPACITY when it exceeds cap). */
+int vo_orb_detect_and_compute(vo_ctx* ctx, const uint8_t* img, int stride, int width, int height, int nfeatures, float* xy,
+                              int32_t* octave, float* response, float* angle_deg, uint8_t* desc, int cap, int* n);
 /* cv::FAST (TYPE_9_16, the detector ORB runs on every pyramid level with fastThreshold 20 and non-maximum
  * suppression; orb.cpp computeKeyPoints): corners in raster order with their scores (cornerScore<16>), identical to
  * cv2.FastFeatureDetector_create(threshold, nonmax).detect -- positions, order and responses.  *n = number of corners

@@ -76,7 +76,7 @@ SYMBOLS = [
     "vo_synth_render_dev", "vo_alloc_host", "vo_free_host", "vo_alloc_dev", "vo_free_dev", "vo_memcpy_d2h",
     "vo_memcpy_h2d",
     "vo_sgbm_default_params", "vo_sgbm_compute", "vo_stereo_match", "vo_reproject_disparity", "vo_sgbm_timing",
-    "vo_debug_sgbm_stage", "vo_orb_describe", "vo_orb_smooth", "vo_orb_angles", "vo_orb_harris", "vo_fast9",
+    "vo_debug_sgbm_stage", "vo_orb_describe", "vo_orb_smooth", "vo_orb_angles", "vo_orb_harris", "vo_fast9", "vo_orb_detect_and_compute",
 ]
 
 

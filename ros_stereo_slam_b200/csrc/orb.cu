@@ -20,6 +20,11 @@
 //            test points of the byte rotated in float without contraction, cvRound, 8 comparisons
 #include <cub/cub.cuh>
 
+#include <algorithm>
+#include <cmath>
+#include <functional>
+#include <numeric>
+
 #include "common.cuh"
 #include "orb_pattern.h"
 
@@ -40,6 +45,10 @@ struct Orb {
   void* cub_tmp = nullptr;
   size_t cub_bytes = 0;
   size_t px_cap = 0;               // pixels the FAST buffers are sized for
+  uint8_t* pyr = nullptr;          // pyramid levels 1.. of vo_orb_detect_and_compute, packed
+  size_t pyr_bytes = 0;
+  int* coef = nullptr;             // resize offsets / weights: ox, cx, oy, cy
+  int coef_cap = 0;
 };
 
 __constant__ signed char c_orb_pattern[256][4];
@@ -48,7 +57,7 @@ __constant__ float c_orb_gauss[4];
 void orb_free(vo_ctx* c) {
   Orb* o = reinterpret_cast<Orb*>(c->orb);
   if (!o) return;
-  void* dev[] = {o->img, o->rowf, o->sm, o->xy, o->ang, o->desc, o->score, o->flag, o->sel, o->d_n, o->cub_tmp};
+  void* dev[] = {o->img, o->rowf, o->sm, o->xy, o->ang, o->desc, o->score, o->flag, o->sel, o->d_n, o->cub_tmp, o->pyr, o->coef};
   for (void* p : dev) cudaFree(p);
   delete o;
   c->orb = nullptr;
@@ -210,6 +219,23 @@ __global__ void orb_angle_kernel(const uint8_t* __restrict__ img, int w, int h, 
     m01 += __shfl_xor_sync(0xffffffffu, m01, o);
   }
   if (lane == 0) ang[kp] = orb_fast_atan2((float)m01, (float)m10);
+}
+
+// cv::resize(INTER_LINEAR_EXACT), 8-bit: horizontal pass in 8.8 fixed point, vertical pass in 16.16, rounded half up;
+// offsets and weights come from the host (they are computed in double, orb_exact_coeffs)
+__global__ void orb_resize_exact_kernel(const uint8_t* __restrict__ src, int sw, int sh, uint8_t* __restrict__ dst, int dw, int dh,
+                                        const int* __restrict__ ox, const int* __restrict__ cx, const int* __restrict__ oy,
+                                        const int* __restrict__ cy) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= dw) return;
+  const int x0 = ox[x], x1 = min(x0 + 1, sw - 1), wx = cx[x];
+  const int y0 = oy[y], y1 = min(y0 + 1, sh - 1), wy = cy[y];
+  const uint8_t* r0 = src + (size_t)y0 * sw;
+  const uint8_t* r1 = src + (size_t)y1 * sw;
+  const int h0 = (int)r0[x0] * (256 - wx) + (int)r0[x1] * wx;
+  const int h1 = (int)r1[x0] * (256 - wx) + (int)r1[x1] * wx;
+  dst[(size_t)y * dw + x] = (uint8_t)((h0 * (256 - wy) + h1 * wy + 32768) >> 16);
 }
 
 // HarrisResponses (orb.cpp): the response ORB ranks its keypoints by.  A warp per keypoint, lanes over the 49 window
@@ -482,4 +508,247 @@ int vo_fast9(vo_ctx* c, const uint8_t* img, int stride, int width, int height, i
     VO_CUDA(cudaStreamSynchronize(c->stream));
   }
   return hn > cap ? VO_ERR_CAPACITY : VO_OK;
+}
+
+// ---------------------------------------------------------------------------------------- ORB::detectAndCompute
+namespace {
+
+// resize.cpp interpolationLinear::getCoeffs (8-bit): IEEE double arithmetic, like OpenCV's softdouble
+void orb_exact_coeffs(int srcsize, int dstsize, int* ofs, int* c1) {
+  const double inv = (double)dstsize / (double)srcsize;
+  const double scale = 1.0 / inv;
+  for (int v = 0; v < dstsize; v++) {
+    const double fval = scale * ((double)v + 0.5) - 0.5;
+    const int ival = (int)std::floor(fval);
+    ofs[v] = 0;
+    c1[v] = 0;
+    if (ival >= 0 && srcsize > 1) {
+      if (ival < srcsize - 1) {
+        ofs[v] = ival;
+        c1[v] = (int)std::nearbyint((fval - (double)ival) * 256.0);
+      } else {
+        ofs[v] = srcsize - 1;
+      }
+    }
+  }
+}
+
+// KeyPointsFilter::retainBest: every keypoint whose response is >= the n-th largest stays (ties included)
+std::vector<int> orb_retain_best(const std::vector<float>& resp, int n) {
+  std::vector<int> keep;
+  if (n <= 0) return keep;
+  if ((int)resp.size() <= n) {
+    keep.resize(resp.size());
+    std::iota(keep.begin(), keep.end(), 0);
+    return keep;
+  }
+  std::vector<float> tmp(resp);
+  std::nth_element(tmp.begin(), tmp.begin() + (n - 1), tmp.end(), std::greater<float>());
+  const float thr = tmp[n - 1];
+  for (int i = 0; i < (int)resp.size(); i++)
+    if (resp[i] >= thr) keep.push_back(i);
+  return keep;
+}
+
+}  // namespace
+
+int vo_orb_detect_and_compute(vo_ctx* c, const uint8_t* img, int stride, int width, int height, int nfeatures, float* xy,
+                              int32_t* octave, float* response, float* angle_deg, uint8_t* desc, int cap, int* n_out) {
+  if (!c) return VO_ERR_INVALID_ARG;
+  VO_CUDA(cudaSetDevice(c->device));
+  if (!img || !n_out || width < 64 || height < 64 || stride < width || nfeatures < 1 || cap < 0 || (cap > 0 && (!xy || !desc)))
+    return VO_ERR_INVALID_ARG;
+  *n_out = 0;
+  // ORB::create() defaults (the reference passes none, src/optimizationStuff.cpp:49): scaleFactor 1.2f kept in a
+  // double, 8 levels, edgeThreshold 31, firstLevel 0, WTA_K 2, HARRIS_SCORE, patchSize 31, fastThreshold 20
+  constexpr int NL = 8, EDGE = 31, FAST_T = 20;
+  const double scale_factor = (double)1.2f;
+  float lscale[NL];
+  int lw[NL], lh[NL], quota[NL];
+  for (int l = 0; l < NL; l++) {
+    lscale[l] = (float)std::pow(scale_factor, (double)l);
+    lw[l] = (int)std::lrintf((float)width / lscale[l]);      // cvRound(image.cols / scale)
+    lh[l] = (int)std::lrintf((float)height / lscale[l]);
+  }
+  {
+    const float factor = (float)(1.0 / scale_factor);
+    float nd = nfeatures * (1 - factor) / (1 - (float)std::pow((double)factor, (double)NL));
+    int sum = 0;
+    for (int l = 0; l < NL - 1; l++) {
+      quota[l] = (int)std::lrintf(nd);
+      sum += quota[l];
+      nd *= factor;
+    }
+    quota[NL - 1] = std::max(nfeatures - sum, 0);
+  }
+  const int n_cand = width * height / 9 + 16;       // after 3x3 suppression at most one corner per 2x2 pixels; generous
+  VO_TRY(orb_ensure(c, width, height, n_cand));
+  Orb* o = reinterpret_cast<Orb*>(c->orb);
+  // FAST buffers
+  if (!o->d_n) VO_CUDA(cudaMalloc(&o->d_n, 4 * sizeof(int)));
+  const size_t npx = (size_t)o->w * o->h;
+  if (o->px_cap < npx) {
+    VO_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(o->score); cudaFree(o->flag); cudaFree(o->sel); cudaFree(o->cub_tmp);
+    o->score = nullptr; o->flag = nullptr; o->sel = nullptr; o->cub_tmp = nullptr;
+    o->px_cap = 0;
+    VO_CUDA(cudaMalloc(&o->score, npx * sizeof(int)));
+    VO_CUDA(cudaMalloc(&o->flag, npx));
+    VO_CUDA(cudaMalloc(&o->sel, npx * sizeof(int)));
+    size_t tb = 0;
+    VO_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, cub::CountingInputIterator<int>(0), (const uint8_t*)nullptr, (int*)nullptr,
+                                       (int*)nullptr, (int)npx, c->stream));
+    o->cub_bytes = tb;
+    VO_CUDA(cudaMalloc(&o->cub_tmp, tb + 256));
+    o->px_cap = npx;
+  }
+  // pyramid levels 1.. and the resize tables
+  size_t pyr_need = 0;
+  for (int l = 1; l < NL; l++) pyr_need += (size_t)lw[l] * lh[l];
+  if (pyr_need > o->pyr_bytes) {
+    VO_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(o->pyr);
+    o->pyr = nullptr;
+    VO_CUDA(cudaMalloc(&o->pyr, pyr_need));
+    o->pyr_bytes = pyr_need;
+  }
+  const int coef_need = 2 * (width + height);
+  if (coef_need > o->coef_cap) {
+    VO_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(o->coef);
+    o->coef = nullptr;
+    VO_CUDA(cudaMalloc(&o->coef, (size_t)coef_need * sizeof(int)));
+    o->coef_cap = coef_need;
+  }
+  VO_CUDA(cudaMemcpy2DAsync(o->img, width, img, stride, width, height, cudaMemcpyDefault, c->stream));
+
+  std::vector<float> h_xy, h_sc, h_resp, h_ang;
+  std::vector<uint8_t> h_desc;
+  std::vector<int> h_coef;
+  int total = 0;
+  const uint8_t* prev = o->img;
+  uint8_t* next = o->pyr;
+  for (int l = 0; l < NL; l++) {
+    const int w = lw[l], h = lh[l];
+    const uint8_t* cur = prev;
+    if (l > 0) {
+      // resize(prevImg, currImg, sz, 0, 0, INTER_LINEAR_EXACT)
+      h_coef.resize(2 * (w + h));
+      orb_exact_coeffs(lw[l - 1], w, h_coef.data(), h_coef.data() + w);
+      orb_exact_coeffs(lh[l - 1], h, h_coef.data() + 2 * w, h_coef.data() + 2 * w + h);
+      VO_CUDA(cudaMemcpyAsync(o->coef, h_coef.data(), h_coef.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+      {
+        LaunchScope ls(c, VO_K_MISC);
+        orb_resize_exact_kernel<<<dim3(div_up(w, 128), h), 128, 0, c->stream>>>(prev, lw[l - 1], lh[l - 1], next, w, h, o->coef,
+                                                                               o->coef + w, o->coef + 2 * w, o->coef + 2 * w + h);
+      }
+      VO_CUDA(cudaStreamSynchronize(c->stream));      // h_coef is reused by the next level
+      cur = next;
+      next += (size_t)w * h;
+    }
+    prev = cur;
+    if (w < 2 * EDGE + 7 || h < 2 * EDGE + 7 || quota[l] <= 0) continue;
+    // FAST (threshold 20, suppression) on the level
+    {
+      LaunchScope ls(c, VO_K_MISC);
+      fast_score_kernel<<<dim3(div_up(w, 128), h), 128, 0, c->stream>>>(cur, w, h, FAST_T, o->score);
+    }
+    {
+      LaunchScope ls(c, VO_K_MISC);
+      fast_nms_kernel<<<dim3(div_up(w, 128), h), 128, 0, c->stream>>>(o->score, w, h, 1, o->flag);
+    }
+    size_t tb = o->cub_bytes;
+    VO_CUDA(cub::DeviceSelect::Flagged(o->cub_tmp, tb, cub::CountingInputIterator<int>(0), o->flag, o->sel, o->d_n, w * h, c->stream));
+    c->launch_count++;
+    {
+      LaunchScope ls(c, VO_K_MISC);
+      fast_gather_kernel<<<div_up(o->cap, 256), 256, 0, c->stream>>>(o->sel, o->d_n, o->cap, o->score, w, o->xy, o->ang);
+    }
+    int nc = 0;
+    VO_CUDA(cudaMemcpyAsync(&nc, o->d_n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    VO_CUDA(cudaStreamSynchronize(c->stream));
+    nc = std::min(nc, o->cap);
+    if (nc == 0) continue;
+    h_xy.resize(2 * (size_t)nc);
+    h_sc.resize(nc);
+    VO_CUDA(cudaMemcpyAsync(h_xy.data(), o->xy, h_xy.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    VO_CUDA(cudaMemcpyAsync(h_sc.data(), o->ang, h_sc.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    VO_CUDA(cudaStreamSynchronize(c->stream));
+    // KeyPointsFilter::runByImageBorder(edgeThreshold), then retainBest(2 * featuresNum) by FAST score
+    std::vector<float> kxy, ksc;
+    for (int i = 0; i < nc; i++) {
+      const float x = h_xy[2 * i], y = h_xy[2 * i + 1];
+      if (x >= EDGE && x < w - EDGE && y >= EDGE && y < h - EDGE) {
+        kxy.push_back(x);
+        kxy.push_back(y);
+        ksc.push_back(h_sc[i]);
+      }
+    }
+    std::vector<int> keep = orb_retain_best(ksc, 2 * quota[l]);
+    std::vector<float> sxy;
+    for (int i : keep) {
+      sxy.push_back(kxy[2 * i]);
+      sxy.push_back(kxy[2 * i + 1]);
+    }
+    int n1 = (int)keep.size();
+    if (n1 == 0) continue;
+    // HarrisResponses, then retainBest(featuresNum)
+    VO_CUDA(cudaMemcpyAsync(o->xy, sxy.data(), sxy.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    {
+      LaunchScope ls(c, VO_K_MISC);
+      orb_harris_kernel<<<div_up(n1 * 32, 256), 256, 0, c->stream>>>(cur, w, h, o->xy, n1, 0.04f, o->ang);
+    }
+    h_resp.resize(n1);
+    VO_CUDA(cudaMemcpyAsync(h_resp.data(), o->ang, (size_t)n1 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    VO_CUDA(cudaStreamSynchronize(c->stream));
+    keep = orb_retain_best(h_resp, quota[l]);
+    // output order inside a level: raster (y, x); OpenCV's is whatever std::nth_element leaves
+    std::sort(keep.begin(), keep.end(), [&](int a, int b) {
+      return sxy[2 * a + 1] != sxy[2 * b + 1] ? sxy[2 * a + 1] < sxy[2 * b + 1] : sxy[2 * a] < sxy[2 * b];
+    });
+    const int n2 = (int)keep.size();
+    std::vector<float> fxy(2 * (size_t)n2), fresp(n2);
+    for (int i = 0; i < n2; i++) {
+      fxy[2 * i] = sxy[2 * keep[i]];
+      fxy[2 * i + 1] = sxy[2 * keep[i] + 1];
+      fresp[i] = h_resp[keep[i]];
+    }
+    // ICAngles on the unsmoothed level, GaussianBlur of the level, computeOrbDescriptors
+    VO_CUDA(cudaMemcpyAsync(o->xy, fxy.data(), fxy.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    {
+      LaunchScope ls(c, VO_K_MISC);
+      orb_angle_kernel<<<div_up(n2 * 32, 256), 256, 0, c->stream>>>(cur, w, h, o->xy, n2, o->ang);
+    }
+    {
+      LaunchScope ls(c, VO_K_MISC);
+      orb_smooth_rows_kernel<<<dim3(div_up(w, 128), h), 128, 0, c->stream>>>(cur, w, h, o->rowf);
+    }
+    {
+      LaunchScope ls(c, VO_K_MISC);
+      orb_smooth_cols_kernel<<<dim3(div_up(w, 128), h), 128, 0, c->stream>>>(o->rowf, w, h, o->sm);
+    }
+    {
+      LaunchScope ls(c, VO_K_MISC);
+      orb_describe_kernel<<<div_up(n2 * 32, 256), 256, 0, c->stream>>>(o->sm, w, h, o->xy, o->ang, n2, o->desc);
+    }
+    VO_CUDA(cudaGetLastError());
+    h_ang.resize(n2);
+    h_desc.resize((size_t)n2 * 32);
+    VO_CUDA(cudaMemcpyAsync(h_ang.data(), o->ang, (size_t)n2 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    VO_CUDA(cudaMemcpyAsync(h_desc.data(), o->desc, h_desc.size(), cudaMemcpyDeviceToHost, c->stream));
+    VO_CUDA(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < n2; i++) {
+      if (total < cap) {
+        xy[2 * total] = fxy[2 * i] * lscale[l];          // allKeypoints[i].pt *= scale
+        xy[2 * total + 1] = fxy[2 * i + 1] * lscale[l];
+        if (octave) octave[total] = l;
+        if (response) response[total] = fresp[i];
+        if (angle_deg) angle_deg[total] = h_ang[i];
+        memcpy(desc + (size_t)total * 32, h_desc.data() + (size_t)i * 32, 32);
+      }
+      total++;
+    }
+  }
+  *n_out = total;
+  return total > cap ? VO_ERR_CAPACITY : VO_OK;
 }

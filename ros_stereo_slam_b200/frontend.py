@@ -209,6 +209,23 @@ class VisualFrontEnd:
         check(self.lib.vo_orb_angles(self.h, _p(a), a.strides[0], a.shape[1], a.shape[0], _p(pts), n, _p(ang)))
         return ang[:n]
 
+    def orbDetectAndCompute(self, img, nfeatures=500):
+        """ORB::create(nfeatures)->detectAndCompute (reference src/optimizationStuff.cpp:49-56): dict of xy, octave,
+        response, angle, desc sorted by (octave, y, x)."""
+        a = _u8img(img)
+        cap = 2 * int(nfeatures) + 4096
+        xy = np.zeros((cap, 2), np.float32)
+        octv = np.zeros(cap, np.int32)
+        resp = np.zeros(cap, np.float32)
+        ang = np.zeros(cap, np.float32)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = C.c_int()
+        check(self.lib.vo_orb_detect_and_compute(self.h, _p(a), a.strides[0], a.shape[1], a.shape[0], int(nfeatures), _p(xy),
+                                                 _p(octv), _p(resp), _p(ang), _p(desc), cap, C.byref(n)))
+        m = n.value
+        return dict(xy=xy[:m].copy(), octave=octv[:m].copy(), response=resp[:m].copy(), angle=ang[:m].copy(),
+                    desc=desc[:m].copy())
+
     def fast9(self, img, threshold=20, nonmax=True, cap=200000):
         """cv::FAST (TYPE_9_16): (xy (n x 2), score (n,)) in raster order."""
         a = _u8img(img)

@@ -104,3 +104,20 @@ def test_fast9_matches_cv2(fe):
     xy = xy[inside]
     assert np.array_equal(fe.orbHarris(g["L1"], xy), orb.harris_response(g["L1"], xy))
     assert np.array_equal(fe.orbDescribe(g["L1"], xy), orb.describe(g["L1"], xy, orb.ic_angle(g["L1"], xy)))
+
+
+def test_detect_and_compute_matches_cv2(fe):
+    """the whole of ORB::detectAndCompute on the device: keypoint sets per octave (position, response, angle) and
+    descriptors equal cv2's and the restatement's"""
+    from oracle import orb
+    g = golden()
+    for key, nf in (("L0", 500), ("R1", 500), ("L1", 2000)):
+        got = fe.orbDetectAndCompute(g[key], nf)
+        want = orb.detect_and_compute(g[key], nf)
+        live = orb.detect_and_compute_call_through(g[key], nf)
+        assert len(got["xy"]) == len(want["xy"]) == len(live["xy"]) > 300
+        for k in ("xy", "octave", "response", "angle", "desc"):
+            assert np.array_equal(got[k], want[k]), (key, k)
+        for k in ("xy", "octave", "response", "angle"):
+            assert np.array_equal(got[k], live[k]), (key, k)
+        assert (got["desc"] != live["desc"]).any(1).mean() <= 0.001     # exact unless cv2's blur dispatch differs
