@@ -39,6 +39,24 @@ def main():
         o.compute(img, kps)
         tc.append(time.perf_counter() - t)
     print("cv2.ORB.compute on %d host cores: median %.2f ms" % (len(os.sched_getaffinity(0)), 1e3 * np.median(tc)))
+    # the whole of ORB::create()->detectAndCompute, as the loop detector calls it on every frame
+    got = fe.orbDetectAndCompute(img, 500)
+    want = orb.detect_and_compute_call_through(img, 500)
+    same = len(got["xy"]) == len(want["xy"]) and all(np.array_equal(got[k], want[k]) for k in ("xy", "octave", "response", "angle", "desc"))
+    print("detectAndCompute(nfeatures 500): %d keypoints, identical to cv2: %s" % (len(got["xy"]), same))
+    td = []
+    for _ in range(60):
+        t = time.perf_counter()
+        fe.orbDetectAndCompute(img, 500)
+        td.append(time.perf_counter() - t)
+    print("vo_orb_detect_and_compute (host image in, keypoints + descriptors out): median %.3f ms" % (1e3 * np.median(td[10:])))
+    o5 = cv2.ORB_create(nfeatures=500)
+    tc = []
+    for _ in range(10):
+        t = time.perf_counter()
+        o5.detectAndCompute(img, None)
+        tc.append(time.perf_counter() - t)
+    print("cv2.ORB.detectAndCompute on %d host cores: median %.2f ms" % (len(os.sched_getaffinity(0)), 1e3 * np.median(tc)))
     fe.close()
 
 
