@@ -121,3 +121,24 @@ def test_detect_and_compute_matches_cv2(fe):
         for k in ("xy", "octave", "response", "angle"):
             assert np.array_equal(got[k], live[k]), (key, k)
         assert (got["desc"] != live["desc"]).any(1).mean() <= 0.001     # exact unless cv2's blur dispatch differs
+
+
+def _textured(img):
+    """a corner-rich variant of the golden frame (about 10,800 FAST corners on level 0 instead of 35)"""
+    import cv2
+    rng = np.random.default_rng(7)
+    tex = cv2.GaussianBlur(rng.integers(0, 256, img.shape).astype(np.uint8), (0, 0), 1.2).astype(np.float32)
+    return np.clip(0.6 * img.astype(np.float32) + 0.9 * (tex - 128) + 50, 0, 255).astype(np.uint8)
+
+
+def test_detect_and_compute_on_a_corner_rich_frame(fe):
+    from oracle import orb
+    img = _textured(golden()["L0"])
+    assert len(orb.fast9_call_through(img, 20)[0]) > 8000
+    for nf in (500, 1500):
+        got = fe.orbDetectAndCompute(img, nf)
+        live = orb.detect_and_compute_call_through(img, nf)
+        assert len(got["xy"]) == len(live["xy"]) >= nf
+        for k in ("xy", "octave", "response", "angle"):
+            assert np.array_equal(got[k], live[k]), (nf, k)
+        assert (got["desc"] != live["desc"]).any(1).mean() <= 0.001
