@@ -335,6 +335,27 @@ static int orb_ensure(vo_ctx* c, int w, int h, int n) {
   return VO_OK;
 }
 
+// the per-pixel buffers of the FAST stage follow the image buffers' size
+static int orb_ensure_fast(vo_ctx* c, Orb* o) {
+  if (!o->d_n) VO_CUDA(cudaMalloc(&o->d_n, 4 * sizeof(int)));
+  const size_t npx = (size_t)o->w * o->h;
+  if (o->px_cap >= npx) return VO_OK;
+  VO_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(o->score); cudaFree(o->flag); cudaFree(o->sel); cudaFree(o->cub_tmp);
+  o->score = nullptr; o->flag = nullptr; o->sel = nullptr; o->cub_tmp = nullptr;
+  o->px_cap = 0;
+  VO_CUDA(cudaMalloc(&o->score, npx * sizeof(int)));
+  VO_CUDA(cudaMalloc(&o->flag, npx));
+  VO_CUDA(cudaMalloc(&o->sel, npx * sizeof(int)));
+  size_t tb = 0;
+  VO_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, cub::CountingInputIterator<int>(0), (const uint8_t*)nullptr, (int*)nullptr,
+                                     (int*)nullptr, (int)npx, c->stream));
+  o->cub_bytes = tb;
+  VO_CUDA(cudaMalloc(&o->cub_tmp, tb + 256));
+  o->px_cap = npx;
+  return VO_OK;
+}
+
 static int orb_smooth_enqueue(vo_ctx* c, Orb* o, const uint8_t* img, int stride, int w, int h) {
   VO_CUDA(cudaMemcpy2DAsync(o->img, w, img, stride, w, h, cudaMemcpyDefault, c->stream));
   {
@@ -463,23 +484,7 @@ int vo_fast9(vo_ctx* c, const uint8_t* img, int stride, int width, int height, i
   VO_TRY(orb_ensure(c, width, height, std::max(cap, 1)));
   Orb* o = reinterpret_cast<Orb*>(c->orb);
   const int n = width * height;
-  if (!o->d_n) VO_CUDA(cudaMalloc(&o->d_n, 4 * sizeof(int)));
-  const size_t npx = (size_t)o->w * o->h;            // the image buffers' size (>= n)
-  if (o->px_cap < npx) {
-    VO_CUDA(cudaStreamSynchronize(c->stream));
-    cudaFree(o->score); cudaFree(o->flag); cudaFree(o->sel); cudaFree(o->cub_tmp);
-    o->score = nullptr; o->flag = nullptr; o->sel = nullptr; o->cub_tmp = nullptr;
-    o->px_cap = 0;
-    VO_CUDA(cudaMalloc(&o->score, npx * sizeof(int)));
-    VO_CUDA(cudaMalloc(&o->flag, npx));
-    VO_CUDA(cudaMalloc(&o->sel, npx * sizeof(int)));
-    size_t tb = 0;
-    VO_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, cub::CountingInputIterator<int>(0), (const uint8_t*)nullptr, (int*)nullptr,
-                                       (int*)nullptr, (int)npx, c->stream));
-    o->cub_bytes = tb;
-    VO_CUDA(cudaMalloc(&o->cub_tmp, tb + 256));
-    o->px_cap = npx;
-  }
+  VO_TRY(orb_ensure_fast(c, o));
   VO_CUDA(cudaMemcpy2DAsync(o->img, width, img, stride, width, height, cudaMemcpyDefault, c->stream));
   {
     LaunchScope ls(c, VO_K_MISC);
@@ -584,24 +589,7 @@ int vo_orb_detect_and_compute(vo_ctx* c, const uint8_t* img, int stride, int wid
   const int n_cand = width * height / 9 + 16;       // after 3x3 suppression at most one corner per 2x2 pixels; generous
   VO_TRY(orb_ensure(c, width, height, n_cand));
   Orb* o = reinterpret_cast<Orb*>(c->orb);
-  // FAST buffers
-  if (!o->d_n) VO_CUDA(cudaMalloc(&o->d_n, 4 * sizeof(int)));
-  const size_t npx = (size_t)o->w * o->h;
-  if (o->px_cap < npx) {
-    VO_CUDA(cudaStreamSynchronize(c->stream));
-    cudaFree(o->score); cudaFree(o->flag); cudaFree(o->sel); cudaFree(o->cub_tmp);
-    o->score = nullptr; o->flag = nullptr; o->sel = nullptr; o->cub_tmp = nullptr;
-    o->px_cap = 0;
-    VO_CUDA(cudaMalloc(&o->score, npx * sizeof(int)));
-    VO_CUDA(cudaMalloc(&o->flag, npx));
-    VO_CUDA(cudaMalloc(&o->sel, npx * sizeof(int)));
-    size_t tb = 0;
-    VO_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, cub::CountingInputIterator<int>(0), (const uint8_t*)nullptr, (int*)nullptr,
-                                       (int*)nullptr, (int)npx, c->stream));
-    o->cub_bytes = tb;
-    VO_CUDA(cudaMalloc(&o->cub_tmp, tb + 256));
-    o->px_cap = npx;
-  }
+  VO_TRY(orb_ensure_fast(c, o));
   // pyramid levels 1.. and the resize tables
   size_t pyr_need = 0;
   for (int l = 1; l < NL; l++) pyr_need += (size_t)lw[l] * lh[l];
@@ -612,41 +600,47 @@ int vo_orb_detect_and_compute(vo_ctx* c, const uint8_t* img, int stride, int wid
     VO_CUDA(cudaMalloc(&o->pyr, pyr_need));
     o->pyr_bytes = pyr_need;
   }
-  const int coef_need = 2 * (width + height);
-  if (coef_need > o->coef_cap) {
+  // the resize tables of all levels in one upload, then the whole pyramid: resize(prevImg, currImg, sz, 0, 0,
+  // INTER_LINEAR_EXACT), each level from the previous one
+  std::vector<int> h_coef;
+  size_t coef_ofs[NL] = {0};
+  for (int l = 1; l < NL; l++) {
+    coef_ofs[l] = h_coef.size();
+    h_coef.resize(h_coef.size() + 2 * (size_t)(lw[l] + lh[l]));
+    int* t = h_coef.data() + coef_ofs[l];
+    orb_exact_coeffs(lw[l - 1], lw[l], t, t + lw[l]);
+    orb_exact_coeffs(lh[l - 1], lh[l], t + 2 * lw[l], t + 2 * lw[l] + lh[l]);
+  }
+  if ((int)h_coef.size() > o->coef_cap) {
     VO_CUDA(cudaStreamSynchronize(c->stream));
     cudaFree(o->coef);
     o->coef = nullptr;
-    VO_CUDA(cudaMalloc(&o->coef, (size_t)coef_need * sizeof(int)));
-    o->coef_cap = coef_need;
+    VO_CUDA(cudaMalloc(&o->coef, h_coef.size() * sizeof(int)));
+    o->coef_cap = (int)h_coef.size();
   }
   VO_CUDA(cudaMemcpy2DAsync(o->img, width, img, stride, width, height, cudaMemcpyDefault, c->stream));
+  VO_CUDA(cudaMemcpyAsync(o->coef, h_coef.data(), h_coef.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  const uint8_t* level[NL];
+  level[0] = o->img;
+  {
+    uint8_t* next = o->pyr;
+    for (int l = 1; l < NL; l++) {
+      const int* t = o->coef + coef_ofs[l];
+      LaunchScope ls(c, VO_K_MISC);
+      orb_resize_exact_kernel<<<dim3(div_up(lw[l], 128), lh[l]), 128, 0, c->stream>>>(level[l - 1], lw[l - 1], lh[l - 1], next, lw[l],
+                                                                                    lh[l], t, t + lw[l], t + 2 * lw[l],
+                                                                                    t + 2 * lw[l] + lh[l]);
+      level[l] = next;
+      next += (size_t)lw[l] * lh[l];
+    }
+  }
 
   std::vector<float> h_xy, h_sc, h_resp, h_ang;
   std::vector<uint8_t> h_desc;
-  std::vector<int> h_coef;
   int total = 0;
-  const uint8_t* prev = o->img;
-  uint8_t* next = o->pyr;
   for (int l = 0; l < NL; l++) {
     const int w = lw[l], h = lh[l];
-    const uint8_t* cur = prev;
-    if (l > 0) {
-      // resize(prevImg, currImg, sz, 0, 0, INTER_LINEAR_EXACT)
-      h_coef.resize(2 * (w + h));
-      orb_exact_coeffs(lw[l - 1], w, h_coef.data(), h_coef.data() + w);
-      orb_exact_coeffs(lh[l - 1], h, h_coef.data() + 2 * w, h_coef.data() + 2 * w + h);
-      VO_CUDA(cudaMemcpyAsync(o->coef, h_coef.data(), h_coef.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-      {
-        LaunchScope ls(c, VO_K_MISC);
-        orb_resize_exact_kernel<<<dim3(div_up(w, 128), h), 128, 0, c->stream>>>(prev, lw[l - 1], lh[l - 1], next, w, h, o->coef,
-                                                                               o->coef + w, o->coef + 2 * w, o->coef + 2 * w + h);
-      }
-      VO_CUDA(cudaStreamSynchronize(c->stream));      // h_coef is reused by the next level
-      cur = next;
-      next += (size_t)w * h;
-    }
-    prev = cur;
+    const uint8_t* cur = level[l];
     if (w < 2 * EDGE + 7 || h < 2 * EDGE + 7 || quota[l] <= 0) continue;
     // FAST (threshold 20, suppression) on the level
     {
