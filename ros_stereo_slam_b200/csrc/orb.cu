@@ -49,6 +49,8 @@ struct Orb {
   size_t pyr_bytes = 0;
   int* coef = nullptr;             // resize offsets / weights: ox, cx, oy, cy
   int coef_cap = 0;
+  uint8_t* h_pin = nullptr;        // pinned host scratch of vo_orb_detect_and_compute: image | xy | scalar | descriptors
+  size_t h_pin_bytes = 0;
 };
 
 __constant__ signed char c_orb_pattern[256][4];
@@ -59,6 +61,7 @@ void orb_free(vo_ctx* c) {
   if (!o) return;
   void* dev[] = {o->img, o->rowf, o->sm, o->xy, o->ang, o->desc, o->score, o->flag, o->sel, o->d_n, o->cub_tmp, o->pyr, o->coef};
   for (void* p : dev) cudaFree(p);
+  cudaFreeHost(o->h_pin);
   delete o;
   c->orb = nullptr;
 }
@@ -618,7 +621,23 @@ int vo_orb_detect_and_compute(vo_ctx* c, const uint8_t* img, int stride, int wid
     VO_CUDA(cudaMalloc(&o->coef, h_coef.size() * sizeof(int)));
     o->coef_cap = (int)h_coef.size();
   }
-  VO_CUDA(cudaMemcpy2DAsync(o->img, width, img, stride, width, height, cudaMemcpyDefault, c->stream));
+  // pinned scratch: pageable copies are staged by the driver at a few GB/s and serialise with the stream
+  constexpr int DESC_CAP = 8192;
+  const size_t pin_img = (size_t)width * height, pin_xy = 2 * (size_t)o->cap * sizeof(float),
+               pin_sc = (size_t)o->cap * sizeof(float), pin_desc = (size_t)DESC_CAP * 32;
+  if (pin_img + pin_xy + pin_sc + pin_desc > o->h_pin_bytes) {
+    VO_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFreeHost(o->h_pin);
+    o->h_pin = nullptr;
+    o->h_pin_bytes = 0;
+    VO_CUDA(cudaMallocHost(&o->h_pin, pin_img + pin_xy + pin_sc + pin_desc));
+    o->h_pin_bytes = pin_img + pin_xy + pin_sc + pin_desc;
+  }
+  float* p_xy = reinterpret_cast<float*>(o->h_pin + pin_img);
+  float* p_sc = reinterpret_cast<float*>(o->h_pin + pin_img + pin_xy);
+  uint8_t* p_desc = o->h_pin + pin_img + pin_xy + pin_sc;
+  for (int y = 0; y < height; y++) memcpy(o->h_pin + (size_t)y * width, img + (size_t)y * stride, width);
+  VO_CUDA(cudaMemcpyAsync(o->img, o->h_pin, pin_img, cudaMemcpyHostToDevice, c->stream));
   VO_CUDA(cudaMemcpyAsync(o->coef, h_coef.data(), h_coef.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   const uint8_t* level[NL];
   level[0] = o->img;
@@ -635,7 +654,7 @@ int vo_orb_detect_and_compute(vo_ctx* c, const uint8_t* img, int stride, int wid
     }
   }
 
-  std::vector<float> h_xy, h_sc, h_resp, h_ang;
+  std::vector<float> h_resp, h_ang;
   std::vector<uint8_t> h_desc;
   int total = 0;
   for (int l = 0; l < NL; l++) {
@@ -663,10 +682,10 @@ int vo_orb_detect_and_compute(vo_ctx* c, const uint8_t* img, int stride, int wid
     VO_CUDA(cudaStreamSynchronize(c->stream));
     nc = std::min(nc, o->cap);
     if (nc == 0) continue;
-    h_xy.resize(2 * (size_t)nc);
-    h_sc.resize(nc);
-    VO_CUDA(cudaMemcpyAsync(h_xy.data(), o->xy, h_xy.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    VO_CUDA(cudaMemcpyAsync(h_sc.data(), o->ang, h_sc.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    const float* h_xy = p_xy;
+    const float* h_sc = p_sc;
+    VO_CUDA(cudaMemcpyAsync(p_xy, o->xy, 2 * (size_t)nc * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    VO_CUDA(cudaMemcpyAsync(p_sc, o->ang, (size_t)nc * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     VO_CUDA(cudaStreamSynchronize(c->stream));
     // KeyPointsFilter::runByImageBorder(edgeThreshold), then retainBest(2 * featuresNum) by FAST score
     std::vector<float> kxy, ksc;
@@ -692,9 +711,9 @@ int vo_orb_detect_and_compute(vo_ctx* c, const uint8_t* img, int stride, int wid
       LaunchScope ls(c, VO_K_MISC);
       orb_harris_kernel<<<div_up(n1 * 32, 256), 256, 0, c->stream>>>(cur, w, h, o->xy, n1, 0.04f, o->ang);
     }
-    h_resp.resize(n1);
-    VO_CUDA(cudaMemcpyAsync(h_resp.data(), o->ang, (size_t)n1 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    VO_CUDA(cudaMemcpyAsync(p_sc, o->ang, (size_t)n1 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     VO_CUDA(cudaStreamSynchronize(c->stream));
+    h_resp.assign(p_sc, p_sc + n1);
     keep = orb_retain_best(h_resp, quota[l]);
     // output order inside a level: raster (y, x); OpenCV's is whatever std::nth_element leaves
     std::sort(keep.begin(), keep.end(), [&](int a, int b) {
@@ -728,9 +747,17 @@ int vo_orb_detect_and_compute(vo_ctx* c, const uint8_t* img, int stride, int wid
     VO_CUDA(cudaGetLastError());
     h_ang.resize(n2);
     h_desc.resize((size_t)n2 * 32);
-    VO_CUDA(cudaMemcpyAsync(h_ang.data(), o->ang, (size_t)n2 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    VO_CUDA(cudaMemcpyAsync(h_desc.data(), o->desc, h_desc.size(), cudaMemcpyDeviceToHost, c->stream));
-    VO_CUDA(cudaStreamSynchronize(c->stream));
+    if (n2 <= DESC_CAP) {
+      VO_CUDA(cudaMemcpyAsync(p_sc, o->ang, (size_t)n2 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+      VO_CUDA(cudaMemcpyAsync(p_desc, o->desc, (size_t)n2 * 32, cudaMemcpyDeviceToHost, c->stream));
+      VO_CUDA(cudaStreamSynchronize(c->stream));
+      memcpy(h_ang.data(), p_sc, (size_t)n2 * sizeof(float));
+      memcpy(h_desc.data(), p_desc, (size_t)n2 * 32);
+    } else {
+      VO_CUDA(cudaMemcpyAsync(h_ang.data(), o->ang, (size_t)n2 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+      VO_CUDA(cudaMemcpyAsync(h_desc.data(), o->desc, h_desc.size(), cudaMemcpyDeviceToHost, c->stream));
+      VO_CUDA(cudaStreamSynchronize(c->stream));
+    }
     for (int i = 0; i < n2; i++) {
       if (total < cap) {
         xy[2 * total] = fxy[2 * i] * lscale[l];          // allKeypoints[i].pt *= scale
