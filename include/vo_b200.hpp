@@ -9,6 +9,7 @@
 // (low inliers); this mirror does the same.  Any other failure of the library throws
 // vo::Error -- there is no CPU fallback to hide it.
 #pragma once
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <stdexcept>
@@ -224,6 +225,37 @@ class StereoProcess {
   }
   vo_ctx* ctx_;
   BgrImage lImg_;
+};
+
+// Mirror of the loop detector's feature extraction (reference src/optimizationStuff.cpp:49-56:
+// `Ptr<ORB> orb = ORB::create(); orb->detectAndCompute(img, noArray(), kps, descriptors)`).  Keypoints carry what
+// cv::KeyPoint carries; descriptors are n x 32 bytes, the rows DBoW2's FORB takes.
+struct OrbKeyPoint { Point2f pt; float size, angle, response; int octave; };
+
+class ORB {
+ public:
+  explicit ORB(vo_ctx* ctx, int nfeatures = 500) : ctx_(ctx), nfeatures_(nfeatures) {}
+
+  void detectAndCompute(const Image& img, std::vector<OrbKeyPoint>& keypoints, std::vector<uint8_t>& descriptors) {
+    const int cap = 2 * nfeatures_ + 4096;
+    std::vector<float> xy(2 * (size_t)cap), resp(cap), ang(cap);
+    std::vector<int32_t> oct(cap);
+    descriptors.assign((size_t)cap * 32, 0);
+    int n = 0;
+    const int r = vo_orb_detect_and_compute(ctx_, img.data, img.step, img.cols, img.rows, nfeatures_, xy.data(), oct.data(),
+                                            resp.data(), ang.data(), descriptors.data(), cap, &n);
+    if (r != VO_OK) throw Error(r, std::string(vo_strerror(r)) + ": " + vo_last_error());
+    descriptors.resize((size_t)n * 32);
+    keypoints.resize(n);
+    float scale[8];
+    for (int l = 0; l < 8; l++) scale[l] = (float)std::pow((double)1.2f, (double)l);     // orb.cpp getScale
+    for (int i = 0; i < n; i++)
+      keypoints[i] = OrbKeyPoint{{xy[2 * i], xy[2 * i + 1]}, 31.f * scale[oct[i]], ang[i], resp[i], oct[i]};
+  }
+
+ private:
+  vo_ctx* ctx_;
+  int nfeatures_;
 };
 
 }  // namespace vo

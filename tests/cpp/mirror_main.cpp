@@ -72,6 +72,16 @@ int main(int argc, char** argv) {
     write_vec(dir + "/moved.bin", moved);
     std::printf("grid %zu stereo %zu tracked %zu inliers %zu keyframe %zu shutdown %d\n", grid.size(), ref2d.size(),
                 trk2d.size(), inliers.size(), kf2d.size(), (int)slam.SHUTDOWN_FLAG);
+    if (cn == 1) {
+      // the loop detector's per-frame feature extraction (reference src/optimizationStuff.cpp:49-56)
+      vo::ORB orb(slam.ctx());
+      std::vector<vo::OrbKeyPoint> kps;
+      std::vector<uint8_t> desc;
+      orb.detectAndCompute(view(L1), kps, desc);
+      write_vec(dir + "/orb_kps.bin", kps);
+      write_vec(dir + "/orb_desc.bin", desc);
+      std::printf("orb %zu keypoints\n", kps.size());
+    }
     if (cn == 3) {
       // the dense-stereo executable's loop body (reference src/StereoCV.cpp:254-259): stereoMatch -> reprojectDisparity
       vo::StereoProcess sp(slam.ctx());

@@ -80,6 +80,17 @@ def test_cpp_mirror_matches_ctypes_path_and_oracle(tmp_path, cn):
     # (3) keyframe insertion: world points = pose * camera points (src/keyFrameManagement.cpp:20-30)
     assert len(kf2d) == len(kf3d) == len(moved) > 100
     assert np.array_equal(kf3d, moved)
+    # (5) the loop detector's ORB through vo::ORB (gray frames): keypoints and descriptors == cv2's
+    if cn == 1:
+        from oracle import orb
+        kp = np.fromfile(str(tmp_path / "orb_kps.bin"), np.dtype([("x", "f4"), ("y", "f4"), ("size", "f4"), ("angle", "f4"),
+                                                                   ("response", "f4"), ("octave", "i4")]))
+        desc = rd("orb_desc.bin", np.uint8, 32)
+        live = orb.detect_and_compute_call_through(frames["L1"], 500)
+        assert len(kp) == len(live["xy"]) > 300
+        assert np.array_equal(np.c_[kp["x"], kp["y"]], live["xy"]) and np.array_equal(kp["octave"], live["octave"])
+        assert np.array_equal(kp["angle"], live["angle"]) and np.array_equal(kp["response"], live["response"])
+        assert (desc != live["desc"]).any(1).mean() <= 0.001
     # (4) dense stereo through vo::StereoProcess (BGR frames only): stereoMatch + reprojectDisparity == cv2
     if cn == 3:
         from oracle import sgbm
