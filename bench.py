@@ -325,6 +325,8 @@ def run_ours(args):
             # side figure, not part of the metric: the dense-stereo path on the
             # first stereo pair of the sequence, through vo_sgbm_compute with host buffers, beside cv2 on the host
             out["dense_stereo"] = dense_stereo_side_figure(fe, arr[0, 0].copy(), arr[0, 1].copy())
+            # and the loop detector's per-frame feature extraction
+            out["loop_detector_orb"] = orb_side_figure(fe, arr[0, 0].copy())
     lib.vo_free_dev(fe.h, d_frames)
     lib.vo_free_host(h_frames)
     fe.close()
@@ -354,6 +356,28 @@ def dense_stereo_side_figure(fe, L, R, reps=100):
             "bit_identical_to_cv2": bool(np.array_equal(got, want)),
             "device_pipeline_ms": round(fe.sgbm_timing()["pipeline"], 4),
             "note": "a repeated (size, parameters) replays one CUDA graph; per-stage times: tools/sgbm_bench.py"}
+
+
+def orb_side_figure(fe, img, reps=60):
+    import cv2
+    ref = cv2.ORB_create()                                   # reference src/optimizationStuff.cpp:49
+    t0 = time.perf_counter()
+    kps, want = ref.detectAndCompute(img, None)
+    t_cpu = time.perf_counter() - t0
+    got = fe.orbDetectAndCompute(img, 500)
+    key = sorted(range(len(kps)), key=lambda i: (kps[i].octave, kps[i].pt[1], kps[i].pt[0]))
+    same = len(kps) == len(got["xy"]) and all(
+        kps[i].pt == (float(got["xy"][j, 0]), float(got["xy"][j, 1])) and np.array_equal(want[i], got["desc"][j])
+        for j, i in enumerate(key))
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        fe.orbDetectAndCompute(img, 500)
+        ts.append(time.perf_counter() - t0)
+    return {"api": "vo_orb_detect_and_compute(host image, nfeatures 500) -> keypoints + 32-byte descriptors, = ORB::create()"
+                   "->detectAndCompute", "ms_per_frame": round(1e3 * float(np.median(ts[reps // 2:])), 4),
+            "cv2_ms_per_frame": round(1e3 * t_cpu, 2), "cores": len(os.sched_getaffinity(0)), "keypoints": len(kps),
+            "bit_identical_to_cv2": bool(same)}
 
 
 # ----------------------------------------------------------------------------- CPU reference
