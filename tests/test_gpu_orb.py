@@ -142,3 +142,18 @@ def test_detect_and_compute_on_a_corner_rich_frame(fe):
         for k in ("xy", "octave", "response", "angle"):
             assert np.array_equal(got[k], live[k]), (nf, k)
         assert (got["desc"] != live["desc"]).any(1).mean() <= 0.001
+
+
+def test_detect_and_compute_other_sizes(fe):
+    """640 x 480 and an odd 517 x 389 frame: other level sizes, other resize tables, buffers regrown and reused"""
+    import cv2
+    from oracle import orb
+    base = _textured(golden()["L0"])
+    for size in ((640, 480), (517, 389), (1241, 376)):
+        img = cv2.resize(base, size, interpolation=cv2.INTER_AREA)
+        got = fe.orbDetectAndCompute(img, 500)
+        live = orb.detect_and_compute_call_through(img, 500)
+        assert len(got["xy"]) == len(live["xy"]) > 200, size
+        for k in ("xy", "octave", "response", "angle"):
+            assert np.array_equal(got[k], live[k]), (size, k)
+        assert (got["desc"] != live["desc"]).any(1).mean() <= 0.001
