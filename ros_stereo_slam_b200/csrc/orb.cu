@@ -541,6 +541,13 @@ void orb_exact_coeffs(int srcsize, int dstsize, int* ofs, int* c1) {
   }
 }
 
+// what one pyramid level contributes to the result
+struct OrbLevelOut {
+  int level = 0, n = 0, pin_ofs = -1;
+  std::vector<float> xy, resp, ang;
+  std::vector<uint8_t> desc;
+};
+
 // KeyPointsFilter::retainBest: every keypoint whose response is >= the n-th largest stays (ties included)
 std::vector<int> orb_retain_best(const std::vector<float>& resp, int n) {
   std::vector<int> keep;
@@ -624,7 +631,7 @@ int vo_orb_detect_and_compute(vo_ctx* c, const uint8_t* img, int stride, int wid
   // pinned scratch: pageable copies are staged by the driver at a few GB/s and serialise with the stream
   constexpr int DESC_CAP = 8192;
   const size_t pin_img = (size_t)width * height, pin_xy = 2 * (size_t)o->cap * sizeof(float),
-               pin_sc = (size_t)o->cap * sizeof(float), pin_desc = (size_t)DESC_CAP * 32;
+               pin_sc = (size_t)o->cap * sizeof(float), pin_desc = (size_t)DESC_CAP * (32 + sizeof(float));
   if (pin_img + pin_xy + pin_sc + pin_desc > o->h_pin_bytes) {
     VO_CUDA(cudaStreamSynchronize(c->stream));
     cudaFreeHost(o->h_pin);
@@ -635,7 +642,9 @@ int vo_orb_detect_and_compute(vo_ctx* c, const uint8_t* img, int stride, int wid
   }
   float* p_xy = reinterpret_cast<float*>(o->h_pin + pin_img);
   float* p_sc = reinterpret_cast<float*>(o->h_pin + pin_img + pin_xy);
-  uint8_t* p_desc = o->h_pin + pin_img + pin_xy + pin_sc;
+  uint8_t* p_desc = o->h_pin + pin_img + pin_xy + pin_sc;                    // descriptors of all levels, appended
+  float* p_ang = reinterpret_cast<float*>(p_desc + (size_t)DESC_CAP * 32);   // their angles
+  int pin_used = 0;          // keypoints whose angle / descriptor copies are in flight (one synchronisation at the end)
   for (int y = 0; y < height; y++) memcpy(o->h_pin + (size_t)y * width, img + (size_t)y * stride, width);
   VO_CUDA(cudaMemcpyAsync(o->img, o->h_pin, pin_img, cudaMemcpyHostToDevice, c->stream));
   VO_CUDA(cudaMemcpyAsync(o->coef, h_coef.data(), h_coef.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
@@ -654,9 +663,8 @@ int vo_orb_detect_and_compute(vo_ctx* c, const uint8_t* img, int stride, int wid
     }
   }
 
-  std::vector<float> h_resp, h_ang;
-  std::vector<uint8_t> h_desc;
-  int total = 0;
+  std::vector<float> h_resp;
+  std::vector<OrbLevelOut> pending;
   for (int l = 0; l < NL; l++) {
     const int w = lw[l], h = lh[l];
     const uint8_t* cur = level[l];
@@ -745,27 +753,50 @@ int vo_orb_detect_and_compute(vo_ctx* c, const uint8_t* img, int stride, int wid
       orb_describe_kernel<<<div_up(n2 * 32, 256), 256, 0, c->stream>>>(o->sm, w, h, o->xy, o->ang, n2, o->desc);
     }
     VO_CUDA(cudaGetLastError());
-    h_ang.resize(n2);
-    h_desc.resize((size_t)n2 * 32);
-    if (n2 <= DESC_CAP) {
-      VO_CUDA(cudaMemcpyAsync(p_sc, o->ang, (size_t)n2 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-      VO_CUDA(cudaMemcpyAsync(p_desc, o->desc, (size_t)n2 * 32, cudaMemcpyDeviceToHost, c->stream));
+    // the copies of this level's angles and descriptors are only enqueued: the stream orders them before the next
+    // level reuses the device buffers, and the host reads them after the one synchronisation behind the loop
+    if (pin_used + n2 > DESC_CAP) {        // more keypoints than the pinned block holds: drain what is in flight
       VO_CUDA(cudaStreamSynchronize(c->stream));
-      memcpy(h_ang.data(), p_sc, (size_t)n2 * sizeof(float));
-      memcpy(h_desc.data(), p_desc, (size_t)n2 * 32);
+      for (auto& r : pending) {
+        r.ang.assign(p_ang + r.pin_ofs, p_ang + r.pin_ofs + r.n);
+        r.desc.assign(p_desc + (size_t)r.pin_ofs * 32, p_desc + (size_t)(r.pin_ofs + r.n) * 32);
+        r.pin_ofs = -1;
+      }
+      pin_used = 0;
+    }
+    OrbLevelOut rec;
+    rec.level = l;
+    rec.n = n2;
+    rec.xy.swap(fxy);
+    rec.resp.swap(fresp);
+    if (n2 <= DESC_CAP) {
+      rec.pin_ofs = pin_used;
+      VO_CUDA(cudaMemcpyAsync(p_ang + pin_used, o->ang, (size_t)n2 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+      VO_CUDA(cudaMemcpyAsync(p_desc + (size_t)pin_used * 32, o->desc, (size_t)n2 * 32, cudaMemcpyDeviceToHost, c->stream));
+      pin_used += n2;
     } else {
-      VO_CUDA(cudaMemcpyAsync(h_ang.data(), o->ang, (size_t)n2 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-      VO_CUDA(cudaMemcpyAsync(h_desc.data(), o->desc, h_desc.size(), cudaMemcpyDeviceToHost, c->stream));
+      rec.pin_ofs = -1;
+      rec.ang.resize(n2);
+      rec.desc.resize((size_t)n2 * 32);
+      VO_CUDA(cudaMemcpyAsync(rec.ang.data(), o->ang, (size_t)n2 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+      VO_CUDA(cudaMemcpyAsync(rec.desc.data(), o->desc, rec.desc.size(), cudaMemcpyDeviceToHost, c->stream));
       VO_CUDA(cudaStreamSynchronize(c->stream));
     }
-    for (int i = 0; i < n2; i++) {
+    pending.push_back(std::move(rec));
+  }
+  VO_CUDA(cudaStreamSynchronize(c->stream));
+  int total = 0;
+  for (const auto& r : pending) {
+    const float* ang = r.pin_ofs >= 0 ? p_ang + r.pin_ofs : r.ang.data();
+    const uint8_t* dsc = r.pin_ofs >= 0 ? p_desc + (size_t)r.pin_ofs * 32 : r.desc.data();
+    for (int i = 0; i < r.n; i++) {
       if (total < cap) {
-        xy[2 * total] = fxy[2 * i] * lscale[l];          // allKeypoints[i].pt *= scale
-        xy[2 * total + 1] = fxy[2 * i + 1] * lscale[l];
-        if (octave) octave[total] = l;
-        if (response) response[total] = fresp[i];
-        if (angle_deg) angle_deg[total] = h_ang[i];
-        memcpy(desc + (size_t)total * 32, h_desc.data() + (size_t)i * 32, 32);
+        xy[2 * total] = r.xy[2 * i] * lscale[r.level];          // allKeypoints[i].pt *= scale
+        xy[2 * total + 1] = r.xy[2 * i + 1] * lscale[r.level];
+        if (octave) octave[total] = r.level;
+        if (response) response[total] = r.resp[i];
+        if (angle_deg) angle_deg[total] = ang[i];
+        memcpy(desc + (size_t)total * 32, dsc + (size_t)i * 32, 32);
       }
       total++;
     }
