@@ -235,13 +235,12 @@ int vo_sgbm_timing(vo_ctx* ctx, float ms[9], float* pipeline_ms);
  * winner-take-all, 2 = after the left-right check (both int16 [h][w]), 3 = prefilter planes (uchar4 [4][h][w]) */
 int vo_debug_sgbm_stage(vo_ctx* ctx, int stage, void* out, uint64_t bytes);
 
-/* ---- SURVEY 8(f)-2, first step: the descriptor half of ORB for the loop detector (src/optimizationStuff.cpp:49-56,
- * ORB::create()->detectAndCompute).  rBRIEF descriptors (32 bytes each) of caller-made keypoints on ONE 8-bit
+/* ---- SURVEY 8(f)-2, the stages of ORB one by one (vo_orb_detect_and_compute below assembles them).  The descriptor
+ * stage (orb.cpp computeOrbDescriptors): rBRIEF descriptors (32 bytes each) of caller-made keypoints on ONE 8-bit
  * pyramid level: xy = n x (x, y) in that level's pixels, angle_deg = n keypoint angles in degrees (cv::KeyPoint::angle);
  * bit-identical to cv2.ORB_create().compute(img, keypoints) of cv2 4.13.0 for octave-0 keypoints.  Keypoints must lie
  * at least 19.5 px inside the image (cv2 itself drops those closer than 31 px).  angle_deg = NULL computes the angles
- * the way detectAndCompute does (vo_orb_angles below).  The rest of the detector half (FAST-9, Harris ranking, pyramid)
- * is not built yet. */
+ * the way detectAndCompute does (vo_orb_angles below). */
 int vo_orb_describe(vo_ctx* ctx, const uint8_t* img, int stride, int width, int height, const float* xy,
                     const float* angle_deg, int n, uint8_t* desc);
 /* ORB's orientation step (orb.cpp ICAngles): intensity-centroid angle in degrees of each keypoint on the UNSMOOTHED

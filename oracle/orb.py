@@ -1,11 +1,12 @@
-"""ORB descriptor stage (rBRIEF) as the reference's loop detector gets it from `ORB::detectAndCompute`
-(reference src/optimizationStuff.cpp:49-56).  TEST INFRASTRUCTURE ONLY.
+"""ORB::detectAndCompute as the reference's loop detector calls it (reference src/optimizationStuff.cpp:49-56),
+restated stage by stage.  TEST INFRASTRUCTURE ONLY.
 
 OpenCV is a third-party dependency the reference does not vendor; the parity pin is cv2 4.13.0 as importable in this
-image.  What is restated here is the *descriptor* half of ORB for caller-made keypoints on one pyramid level
-(`cv2.ORB.compute(img, keypoints)` with octave 0): the smoothing ORB applies before sampling, the rotation of the
-256 test pairs and the comparisons.  The detector half (FAST-9, Harris ranking, the 8-level pyramid, IC_Angle) is not
-restated yet.
+image.  Every stage below is pinned against what cv2 exposes of it (tests/test_oracle_orb.py): the
+INTER_LINEAR_EXACT pyramid (cv2.resize), FAST-9/16 with suppression (cv2.FastFeatureDetector: positions, order,
+scores), the Harris ranking response and the IC_Angle orientation (KeyPoint::response / angle of cv2.ORB.detect),
+the smoothing ORB applies before sampling and the rBRIEF descriptors (cv2.ORB.compute on caller-made keypoints), and
+the assembled detect_and_compute (cv2.ORB.detectAndCompute: per-octave keypoint sets and descriptors, bit for bit).
 
 Three things had to be recovered from cv2 itself, because OpenCV's source is not in the reference tree:
 

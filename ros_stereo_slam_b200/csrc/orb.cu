@@ -1,8 +1,9 @@
-// orb.cu -- the descriptor half of ORB for the loop detector (reference src/optimizationStuff.cpp:49-56:
-// ORB::create()->detectAndCompute feeds DBoW2).  SURVEY.md section 8(f)-2, first step: rBRIEF descriptors of
-// caller-made keypoints on one pyramid level, bit-identical to cv2.ORB.compute (cv2 4.13.0; oracle/orb.py is the
-// restatement).  IC_Angle, the orientation step in front of it, is built too; the rest of the detector half (FAST-9, Harris
-// ranking, 8-level pyramid) is not built yet.
+// orb.cu -- ORB for the loop detector (reference src/optimizationStuff.cpp:49-56: ORB::create()->detectAndCompute feeds
+// DBoW2).  SURVEY.md section 8(f)-2.  Every stage is bit-identical to cv2 4.13.0 (oracle/orb.py is the stage-by-stage
+// restatement): the INTER_LINEAR_EXACT pyramid, FAST-9/16 with suppression, the Harris ranking response, IC_Angle,
+// the smoothing ORB really applies, the rBRIEF descriptors (test-pair table recovered from cv2 itself, orb_pattern.h).
+// vo_orb_detect_and_compute runs them per level with OpenCV's selection rules (quota, border filter, retainBest)
+// on the host between the kernels.
 //
 //   K_rows   the smoothing ORB applies before sampling is NOT OpenCV's fixed-point Gaussian: the pyramid level is a
 //            sub-matrix, for which GaussianBlur falls back to the generic float separable filter.  Row pass:
