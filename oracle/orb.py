@@ -401,7 +401,7 @@ def detect_and_compute(img, nfeatures=500, nlevels=8, scale_factor=SCALE_FACTOR,
     out = dict(xy=[], octave=[], response=[], angle=[], desc=[], level_xy=[])
     for lvl, (im, sf, n) in enumerate(zip(pyr, scales, quota)):
         h, w = im.shape
-        if w < 2 * edge_threshold + 7 or h < 2 * edge_threshold + 7:
+        if w <= 2 * edge_threshold or h <= 2 * edge_threshold:      # the border filter leaves nothing
             continue
         xy, sc, _ = fast9(im, fast_threshold, True)
         inside = (xy[:, 0] >= edge_threshold) & (xy[:, 0] < w - edge_threshold) & \

@@ -597,7 +597,7 @@ int vo_orb_detect_and_compute(vo_ctx* c, const uint8_t* img, int stride, int wid
     }
     quota[NL - 1] = std::max(nfeatures - sum, 0);
   }
-  const int n_cand = width * height / 9 + 16;       // after 3x3 suppression at most one corner per 2x2 pixels; generous
+  const int n_cand = width * height / 4 + 16;       // after 3x3 suppression at most one corner per 2x2 pixels
   VO_TRY(orb_ensure(c, width, height, n_cand));
   Orb* o = reinterpret_cast<Orb*>(c->orb);
   VO_TRY(orb_ensure_fast(c, o));
@@ -669,7 +669,7 @@ int vo_orb_detect_and_compute(vo_ctx* c, const uint8_t* img, int stride, int wid
   for (int l = 0; l < NL; l++) {
     const int w = lw[l], h = lh[l];
     const uint8_t* cur = level[l];
-    if (w < 2 * EDGE + 7 || h < 2 * EDGE + 7 || quota[l] <= 0) continue;
+    if (w <= 2 * EDGE || h <= 2 * EDGE || quota[l] <= 0) continue;      // the border filter would leave nothing
     // FAST (threshold 20, suppression) on the level
     {
       LaunchScope ls(c, VO_K_MISC);

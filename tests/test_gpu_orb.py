@@ -149,11 +149,13 @@ def test_detect_and_compute_other_sizes(fe):
     import cv2
     from oracle import orb
     base = _textured(golden()["L0"])
-    for size in ((640, 480), (517, 389), (1241, 376)):
-        img = cv2.resize(base, size, interpolation=cv2.INTER_AREA)
+    noise = np.random.default_rng(1).integers(0, 256, (240, 320)).astype(np.uint8)     # corners almost everywhere
+    small = np.random.default_rng(2).integers(0, 256, (130, 170)).astype(np.uint8)     # top levels smaller than the border
+    for size in ((640, 480), (517, 389), (1241, 376), noise, small):
+        img = size if isinstance(size, np.ndarray) else cv2.resize(base, size, interpolation=cv2.INTER_AREA)
         got = fe.orbDetectAndCompute(img, 500)
         live = orb.detect_and_compute_call_through(img, 500)
-        assert len(got["xy"]) == len(live["xy"]) > 200, size
+        assert len(got["xy"]) == len(live["xy"]) > 200, img.shape
         for k in ("xy", "octave", "response", "angle"):
-            assert np.array_equal(got[k], live[k]), (size, k)
+            assert np.array_equal(got[k], live[k]), (img.shape, k)
         assert (got["desc"] != live["desc"]).any(1).mean() <= 0.001

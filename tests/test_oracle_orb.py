@@ -102,3 +102,15 @@ def test_pyramid_and_detect_and_compute_match_cv2():
         assert len(a["xy"]) == len(b["xy"]) > 300
         for k in ("xy", "octave", "response", "angle", "desc"):
             assert np.array_equal(a[k], b[k]), (key, k)
+
+
+def test_detect_and_compute_on_small_and_noisy_frames():
+    """pure noise (corners almost everywhere, ties in every selection) and frames whose top pyramid levels are smaller
+    than the border filter: the levels that still have an interior must be processed, the others contribute nothing"""
+    for seed, shape in ((1, (240, 320)), (2, (130, 170))):
+        img = np.random.default_rng(seed).integers(0, 256, shape).astype(np.uint8)
+        a = orb.detect_and_compute(img, 500)
+        b = orb.detect_and_compute_call_through(img, 500)
+        assert len(a["xy"]) == len(b["xy"]) > 300
+        for k in ("xy", "octave", "response", "angle", "desc"):
+            assert np.array_equal(a[k], b[k]), (shape, k)
