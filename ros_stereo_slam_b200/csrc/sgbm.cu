@@ -43,7 +43,7 @@ constexpr int SG_MAX_R = 5;        // block size <= 11
 constexpr unsigned SG_KEY_INIT = 0xFFFFFFFFu;
 
 struct Sgbm {
-  int w = 0, h = 0, D = 0;                  // allocation is for w*h pixels and (w - ...)*D costs
+  int w = 0, h = 0;                         // the per-pixel buffers hold w*h pixels, the volumes cost_elems costs
   size_t cost_elems = 0;
   uint8_t* img[2] = {nullptr, nullptr};     // tight gray images
   uint8_t* bgr[2] = {nullptr, nullptr};     // tight BGR staging (vo_stereo_match)
