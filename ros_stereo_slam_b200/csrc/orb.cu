@@ -341,7 +341,7 @@ static int orb_ensure(vo_ctx* c, int w, int h, int n) {
 
 // the per-pixel buffers of the FAST stage follow the image buffers' size
 static int orb_ensure_fast(vo_ctx* c, Orb* o) {
-  if (!o->d_n) VO_CUDA(cudaMalloc(&o->d_n, 4 * sizeof(int)));
+  if (!o->d_n) VO_CUDA(cudaMalloc(&o->d_n, 16 * sizeof(int)));
   const size_t npx = (size_t)o->w * o->h;
   if (o->px_cap >= npx) return VO_OK;
   VO_CUDA(cudaStreamSynchronize(c->stream));
@@ -597,7 +597,15 @@ int vo_orb_detect_and_compute(vo_ctx* c, const uint8_t* img, int stride, int wid
     }
     quota[NL - 1] = std::max(nfeatures - sum, 0);
   }
-  const int n_cand = width * height / 4 + 16;       // after 3x3 suppression at most one corner per 2x2 pixels
+  // per-level slices of the candidate buffers: after 3x3 suppression there is at most one corner per 2x2 pixels
+  bool active[NL];
+  int cand_ofs[NL + 1];
+  cand_ofs[0] = 0;
+  for (int l = 0; l < NL; l++) {
+    active[l] = lw[l] > 2 * EDGE && lh[l] > 2 * EDGE && quota[l] > 0;      // else the border filter leaves nothing
+    cand_ofs[l + 1] = cand_ofs[l] + (active[l] ? lw[l] * lh[l] / 4 + 16 : 0);
+  }
+  const int n_cand = std::max(cand_ofs[NL], 1);
   VO_TRY(orb_ensure(c, width, height, n_cand));
   Orb* o = reinterpret_cast<Orb*>(c->orb);
   VO_TRY(orb_ensure_fast(c, o));
@@ -630,9 +638,9 @@ int vo_orb_detect_and_compute(vo_ctx* c, const uint8_t* img, int stride, int wid
     o->coef_cap = (int)h_coef.size();
   }
   // pinned scratch: pageable copies are staged by the driver at a few GB/s and serialise with the stream
-  constexpr int DESC_CAP = 8192;
+  const int DESC_CAP = std::max(8192, 2 * nfeatures + 4096);     // keypoints the result staging holds
   const size_t pin_img = (size_t)width * height, pin_xy = 2 * (size_t)o->cap * sizeof(float),
-               pin_sc = (size_t)o->cap * sizeof(float), pin_desc = (size_t)DESC_CAP * (32 + sizeof(float));
+               pin_sc = (size_t)o->cap * sizeof(float), pin_desc = (size_t)DESC_CAP * (32 + sizeof(float)) + 64;
   if (pin_img + pin_xy + pin_sc + pin_desc > o->h_pin_bytes) {
     VO_CUDA(cudaStreamSynchronize(c->stream));
     cudaFreeHost(o->h_pin);
@@ -645,7 +653,6 @@ int vo_orb_detect_and_compute(vo_ctx* c, const uint8_t* img, int stride, int wid
   float* p_sc = reinterpret_cast<float*>(o->h_pin + pin_img + pin_xy);
   uint8_t* p_desc = o->h_pin + pin_img + pin_xy + pin_sc;                    // descriptors of all levels, appended
   float* p_ang = reinterpret_cast<float*>(p_desc + (size_t)DESC_CAP * 32);   // their angles
-  int pin_used = 0;          // keypoints whose angle / descriptor copies are in flight (one synchronisation at the end)
   for (int y = 0; y < height; y++) memcpy(o->h_pin + (size_t)y * width, img + (size_t)y * stride, width);
   VO_CUDA(cudaMemcpyAsync(o->img, o->h_pin, pin_img, cudaMemcpyHostToDevice, c->stream));
   VO_CUDA(cudaMemcpyAsync(o->coef, h_coef.data(), h_coef.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
@@ -664,41 +671,56 @@ int vo_orb_detect_and_compute(vo_ctx* c, const uint8_t* img, int stride, int wid
     }
   }
 
-  std::vector<float> h_resp;
-  std::vector<OrbLevelOut> pending;
+  // ---- phase 1: FAST (threshold 20, suppression) on every level, corners and scores into the level's slice
   for (int l = 0; l < NL; l++) {
+    if (!active[l]) continue;
     const int w = lw[l], h = lh[l];
-    const uint8_t* cur = level[l];
-    if (w <= 2 * EDGE || h <= 2 * EDGE || quota[l] <= 0) continue;      // the border filter would leave nothing
-    // FAST (threshold 20, suppression) on the level
     {
       LaunchScope ls(c, VO_K_MISC);
-      fast_score_kernel<<<dim3(div_up(w, 128), h), 128, 0, c->stream>>>(cur, w, h, FAST_T, o->score);
+      fast_score_kernel<<<dim3(div_up(w, 128), h), 128, 0, c->stream>>>(level[l], w, h, FAST_T, o->score);
     }
     {
       LaunchScope ls(c, VO_K_MISC);
       fast_nms_kernel<<<dim3(div_up(w, 128), h), 128, 0, c->stream>>>(o->score, w, h, 1, o->flag);
     }
     size_t tb = o->cub_bytes;
-    VO_CUDA(cub::DeviceSelect::Flagged(o->cub_tmp, tb, cub::CountingInputIterator<int>(0), o->flag, o->sel, o->d_n, w * h, c->stream));
+    VO_CUDA(cub::DeviceSelect::Flagged(o->cub_tmp, tb, cub::CountingInputIterator<int>(0), o->flag, o->sel, o->d_n + l, w * h,
+                                       c->stream));
     c->launch_count++;
+    const int ccap = cand_ofs[l + 1] - cand_ofs[l];
     {
       LaunchScope ls(c, VO_K_MISC);
-      fast_gather_kernel<<<div_up(o->cap, 256), 256, 0, c->stream>>>(o->sel, o->d_n, o->cap, o->score, w, o->xy, o->ang);
+      fast_gather_kernel<<<div_up(ccap, 256), 256, 0, c->stream>>>(o->sel, o->d_n + l, ccap, o->score, w, o->xy + 2 * cand_ofs[l],
+                                                                   o->ang + cand_ofs[l]);
     }
-    int nc = 0;
-    VO_CUDA(cudaMemcpyAsync(&nc, o->d_n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    VO_CUDA(cudaStreamSynchronize(c->stream));
-    nc = std::min(nc, o->cap);
-    if (nc == 0) continue;
-    const float* h_xy = p_xy;
-    const float* h_sc = p_sc;
-    VO_CUDA(cudaMemcpyAsync(p_xy, o->xy, 2 * (size_t)nc * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    VO_CUDA(cudaMemcpyAsync(p_sc, o->ang, (size_t)nc * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    VO_CUDA(cudaStreamSynchronize(c->stream));
-    // KeyPointsFilter::runByImageBorder(edgeThreshold), then retainBest(2 * featuresNum) by FAST score
+  }
+  VO_CUDA(cudaGetLastError());
+  int* p_cnt = reinterpret_cast<int*>(p_ang + DESC_CAP);
+  VO_CUDA(cudaMemcpyAsync(p_cnt, o->d_n, NL * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  VO_CUDA(cudaStreamSynchronize(c->stream));
+  int nc[NL];
+  for (int l = 0; l < NL; l++) {
+    nc[l] = active[l] ? std::min(p_cnt[l], cand_ofs[l + 1] - cand_ofs[l]) : 0;
+    if (nc[l] == 0) continue;
+    VO_CUDA(cudaMemcpyAsync(p_xy + 2 * cand_ofs[l], o->xy + 2 * cand_ofs[l], 2 * (size_t)nc[l] * sizeof(float),
+                            cudaMemcpyDeviceToHost, c->stream));
+    VO_CUDA(cudaMemcpyAsync(p_sc + cand_ofs[l], o->ang + cand_ofs[l], (size_t)nc[l] * sizeof(float), cudaMemcpyDeviceToHost,
+                            c->stream));
+  }
+  VO_CUDA(cudaStreamSynchronize(c->stream));
+
+  // ---- phase 2: KeyPointsFilter::runByImageBorder(edgeThreshold), retainBest(2 * featuresNum) by FAST score, then
+  // HarrisResponses of the survivors on every level
+  std::vector<float> sxy[NL];
+  int n1[NL];
+  for (int l = 0; l < NL; l++) {
+    n1[l] = 0;
+    if (nc[l] == 0) continue;
+    const int w = lw[l], h = lh[l];
+    const float* h_xy = p_xy + 2 * cand_ofs[l];
+    const float* h_sc = p_sc + cand_ofs[l];
     std::vector<float> kxy, ksc;
-    for (int i = 0; i < nc; i++) {
+    for (int i = 0; i < nc[l]; i++) {
       const float x = h_xy[2 * i], y = h_xy[2 * i + 1];
       if (x >= EDGE && x < w - EDGE && y >= EDGE && y < h - EDGE) {
         kxy.push_back(x);
@@ -706,44 +728,73 @@ int vo_orb_detect_and_compute(vo_ctx* c, const uint8_t* img, int stride, int wid
         ksc.push_back(h_sc[i]);
       }
     }
-    std::vector<int> keep = orb_retain_best(ksc, 2 * quota[l]);
-    std::vector<float> sxy;
+    const std::vector<int> keep = orb_retain_best(ksc, 2 * quota[l]);
     for (int i : keep) {
-      sxy.push_back(kxy[2 * i]);
-      sxy.push_back(kxy[2 * i + 1]);
+      sxy[l].push_back(kxy[2 * i]);
+      sxy[l].push_back(kxy[2 * i + 1]);
     }
-    int n1 = (int)keep.size();
-    if (n1 == 0) continue;
-    // HarrisResponses, then retainBest(featuresNum)
-    VO_CUDA(cudaMemcpyAsync(o->xy, sxy.data(), sxy.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    n1[l] = (int)keep.size();
+  }
+  for (int l = 0; l < NL; l++) {
+    if (n1[l] == 0) continue;
+    float* px = p_xy + 2 * cand_ofs[l];            // the phase-1 results in this slice have been consumed
+    memcpy(px, sxy[l].data(), sxy[l].size() * sizeof(float));
+    VO_CUDA(cudaMemcpyAsync(o->xy + 2 * cand_ofs[l], px, sxy[l].size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     {
       LaunchScope ls(c, VO_K_MISC);
-      orb_harris_kernel<<<div_up(n1 * 32, 256), 256, 0, c->stream>>>(cur, w, h, o->xy, n1, 0.04f, o->ang);
+      orb_harris_kernel<<<div_up(n1[l] * 32, 256), 256, 0, c->stream>>>(level[l], lw[l], lh[l], o->xy + 2 * cand_ofs[l], n1[l], 0.04f,
+                                                                       o->ang + cand_ofs[l]);
     }
-    VO_CUDA(cudaMemcpyAsync(p_sc, o->ang, (size_t)n1 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    VO_CUDA(cudaStreamSynchronize(c->stream));
-    h_resp.assign(p_sc, p_sc + n1);
-    keep = orb_retain_best(h_resp, quota[l]);
-    // output order inside a level: raster (y, x); OpenCV's is whatever std::nth_element leaves
+    VO_CUDA(cudaMemcpyAsync(p_sc + cand_ofs[l], o->ang + cand_ofs[l], (size_t)n1[l] * sizeof(float), cudaMemcpyDeviceToHost,
+                            c->stream));
+  }
+  VO_CUDA(cudaGetLastError());
+  VO_CUDA(cudaStreamSynchronize(c->stream));
+
+  // ---- phase 3: retainBest(featuresNum) by Harris response, then ICAngles on the unsmoothed level, GaussianBlur of the
+  // level and computeOrbDescriptors; the order inside a level is raster (y, x), OpenCV's is what std::nth_element leaves
+  std::vector<OrbLevelOut> pending;
+  int pin_used = 0;
+  for (int l = 0; l < NL; l++) {
+    if (n1[l] == 0) continue;
+    const int w = lw[l], h = lh[l];
+    const float* resp = p_sc + cand_ofs[l];
+    const std::vector<float> h_resp(resp, resp + n1[l]);
+    std::vector<int> keep = orb_retain_best(h_resp, quota[l]);
+    const std::vector<float>& sx = sxy[l];
     std::sort(keep.begin(), keep.end(), [&](int a, int b) {
-      return sxy[2 * a + 1] != sxy[2 * b + 1] ? sxy[2 * a + 1] < sxy[2 * b + 1] : sxy[2 * a] < sxy[2 * b];
+      return sx[2 * a + 1] != sx[2 * b + 1] ? sx[2 * a + 1] < sx[2 * b + 1] : sx[2 * a] < sx[2 * b];
     });
     const int n2 = (int)keep.size();
-    std::vector<float> fxy(2 * (size_t)n2), fresp(n2);
+    if (n2 == 0) continue;
+    if (pin_used + n2 > DESC_CAP) {
+      set_error("vo_orb_detect_and_compute: more than %d keypoints", DESC_CAP);
+      return VO_ERR_CAPACITY;
+    }
+    OrbLevelOut rec;
+    rec.level = l;
+    rec.n = n2;
+    rec.pin_ofs = pin_used;
+    rec.xy.resize(2 * (size_t)n2);
+    rec.resp.resize(n2);
     for (int i = 0; i < n2; i++) {
-      fxy[2 * i] = sxy[2 * keep[i]];
-      fxy[2 * i + 1] = sxy[2 * keep[i] + 1];
-      fresp[i] = h_resp[keep[i]];
+      rec.xy[2 * i] = sx[2 * keep[i]];
+      rec.xy[2 * i + 1] = sx[2 * keep[i] + 1];
+      rec.resp[i] = h_resp[keep[i]];
     }
-    // ICAngles on the unsmoothed level, GaussianBlur of the level, computeOrbDescriptors
-    VO_CUDA(cudaMemcpyAsync(o->xy, fxy.data(), fxy.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    float* px = p_xy + 2 * cand_ofs[l];
+    memcpy(px, rec.xy.data(), rec.xy.size() * sizeof(float));
+    float* d_xy = o->xy + 2 * cand_ofs[l];
+    float* d_ang = o->ang + cand_ofs[l];
+    uint8_t* d_desc = o->desc + (size_t)cand_ofs[l] * 32;
+    VO_CUDA(cudaMemcpyAsync(d_xy, px, rec.xy.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     {
       LaunchScope ls(c, VO_K_MISC);
-      orb_angle_kernel<<<div_up(n2 * 32, 256), 256, 0, c->stream>>>(cur, w, h, o->xy, n2, o->ang);
+      orb_angle_kernel<<<div_up(n2 * 32, 256), 256, 0, c->stream>>>(level[l], w, h, d_xy, n2, d_ang);
     }
     {
       LaunchScope ls(c, VO_K_MISC);
-      orb_smooth_rows_kernel<<<dim3(div_up(w, 128), h), 128, 0, c->stream>>>(cur, w, h, o->rowf);
+      orb_smooth_rows_kernel<<<dim3(div_up(w, 128), h), 128, 0, c->stream>>>(level[l], w, h, o->rowf);
     }
     {
       LaunchScope ls(c, VO_K_MISC);
@@ -751,45 +802,19 @@ int vo_orb_detect_and_compute(vo_ctx* c, const uint8_t* img, int stride, int wid
     }
     {
       LaunchScope ls(c, VO_K_MISC);
-      orb_describe_kernel<<<div_up(n2 * 32, 256), 256, 0, c->stream>>>(o->sm, w, h, o->xy, o->ang, n2, o->desc);
+      orb_describe_kernel<<<div_up(n2 * 32, 256), 256, 0, c->stream>>>(o->sm, w, h, d_xy, d_ang, n2, d_desc);
     }
-    VO_CUDA(cudaGetLastError());
-    // the copies of this level's angles and descriptors are only enqueued: the stream orders them before the next
-    // level reuses the device buffers, and the host reads them after the one synchronisation behind the loop
-    if (pin_used + n2 > DESC_CAP) {        // more keypoints than the pinned block holds: drain what is in flight
-      VO_CUDA(cudaStreamSynchronize(c->stream));
-      for (auto& r : pending) {
-        r.ang.assign(p_ang + r.pin_ofs, p_ang + r.pin_ofs + r.n);
-        r.desc.assign(p_desc + (size_t)r.pin_ofs * 32, p_desc + (size_t)(r.pin_ofs + r.n) * 32);
-        r.pin_ofs = -1;
-      }
-      pin_used = 0;
-    }
-    OrbLevelOut rec;
-    rec.level = l;
-    rec.n = n2;
-    rec.xy.swap(fxy);
-    rec.resp.swap(fresp);
-    if (n2 <= DESC_CAP) {
-      rec.pin_ofs = pin_used;
-      VO_CUDA(cudaMemcpyAsync(p_ang + pin_used, o->ang, (size_t)n2 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-      VO_CUDA(cudaMemcpyAsync(p_desc + (size_t)pin_used * 32, o->desc, (size_t)n2 * 32, cudaMemcpyDeviceToHost, c->stream));
-      pin_used += n2;
-    } else {
-      rec.pin_ofs = -1;
-      rec.ang.resize(n2);
-      rec.desc.resize((size_t)n2 * 32);
-      VO_CUDA(cudaMemcpyAsync(rec.ang.data(), o->ang, (size_t)n2 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-      VO_CUDA(cudaMemcpyAsync(rec.desc.data(), o->desc, rec.desc.size(), cudaMemcpyDeviceToHost, c->stream));
-      VO_CUDA(cudaStreamSynchronize(c->stream));
-    }
+    VO_CUDA(cudaMemcpyAsync(p_ang + pin_used, d_ang, (size_t)n2 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    VO_CUDA(cudaMemcpyAsync(p_desc + (size_t)pin_used * 32, d_desc, (size_t)n2 * 32, cudaMemcpyDeviceToHost, c->stream));
+    pin_used += n2;
     pending.push_back(std::move(rec));
   }
+  VO_CUDA(cudaGetLastError());
   VO_CUDA(cudaStreamSynchronize(c->stream));
   int total = 0;
   for (const auto& r : pending) {
-    const float* ang = r.pin_ofs >= 0 ? p_ang + r.pin_ofs : r.ang.data();
-    const uint8_t* dsc = r.pin_ofs >= 0 ? p_desc + (size_t)r.pin_ofs * 32 : r.desc.data();
+    const float* ang = p_ang + r.pin_ofs;
+    const uint8_t* dsc = p_desc + (size_t)r.pin_ofs * 32;
     for (int i = 0; i < r.n; i++) {
       if (total < cap) {
         xy[2 * total] = r.xy[2 * i] * lscale[r.level];          // allKeypoints[i].pt *= scale
