@@ -544,9 +544,8 @@ void orb_exact_coeffs(int srcsize, int dstsize, int* ofs, int* c1) {
 
 // what one pyramid level contributes to the result
 struct OrbLevelOut {
-  int level = 0, n = 0, pin_ofs = -1;
-  std::vector<float> xy, resp, ang;
-  std::vector<uint8_t> desc;
+  int level = 0, n = 0, pin_ofs = 0;     // pin_ofs: where its angles / descriptors sit in the pinned result staging
+  std::vector<float> xy, resp;
 };
 
 // KeyPointsFilter::retainBest: every keypoint whose response is >= the n-th largest stays (ties included)
