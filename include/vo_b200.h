@@ -362,6 +362,9 @@ int64_t vo_launch_count(vo_ctx* ctx);          /* kernels launched by this ctx s
 /* Cumulative LK work counters since vo_create: (point, level) pairs processed and LK iterations
  * executed -- the units of the LK roofline in DESIGN.md.  Take differences around a region. */
 int vo_lk_work(vo_ctx* ctx, int64_t* point_levels, int64_t* iterations);
+/* Of those, how many took the sequential float-chain path (a partial window sum could reach 2^24, where
+ * OpenCV's float accumulators start rounding): (point, level) window extractions and iterations. */
+int vo_lk_slow_paths(vo_ctx* ctx, int64_t* window_sums, int64_t* iterations);
 /* FP32 issue-rate microbenchmark (dependent FFMA chains on every SM): TFLOP/s achieved. */
 int vo_measure_fp32_peak(vo_ctx* ctx, double* tflops);
 /* synthetic scene renderer (harness only; same scene as oracle/synth.py): renders frame

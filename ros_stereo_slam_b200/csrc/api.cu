@@ -131,9 +131,9 @@ static int alloc_chain(vo_ctx* c) {
     VO_CUDA(cudaMallocHost(&c->h_flags, 8 * sizeof(int)));
   }
   if (p->channels == 3) VO_CUDA(cudaMalloc(&c->d_bgr, (size_t)3 * p->width * p->height));
-  VO_CUDA(cudaMalloc(&c->d_lk_work, 2 * sizeof(unsigned long long)));
-  VO_CUDA(cudaMallocHost(&c->h_lk_work, 2 * sizeof(unsigned long long)));
-  VO_CUDA(cudaMemsetAsync(c->d_lk_work, 0, 2 * sizeof(unsigned long long), c->stream));
+  VO_CUDA(cudaMalloc(&c->d_lk_work, 4 * sizeof(unsigned long long)));
+  VO_CUDA(cudaMallocHost(&c->h_lk_work, 4 * sizeof(unsigned long long)));
+  VO_CUDA(cudaMemsetAsync(c->d_lk_work, 0, 4 * sizeof(unsigned long long), c->stream));
   VO_CUDA(cudaStreamSynchronize(c->stream));
   return VO_OK;
 }
@@ -1691,6 +1691,20 @@ int vo_lk_work(vo_ctx* c, int64_t* point_levels, int64_t* iterations) {
   }
   if (point_levels) *point_levels = pl;
   if (iterations) *iterations = it;
+  return VO_OK;
+}
+
+int vo_lk_slow_paths(vo_ctx* c, int64_t* window_sums, int64_t* iterations) {
+  CHECK_CTX(c);
+  int64_t a = 0, b = 0;
+  for (vo_ctx* k : {c, c->aux}) {
+    VO_CUDA(cudaMemcpyAsync(k->h_lk_work, k->d_lk_work, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, k->stream));
+    VO_TRY(sync_stream(k));
+    a += (int64_t)k->h_lk_work[2];
+    b += (int64_t)k->h_lk_work[3];
+  }
+  if (window_sums) *window_sums = a;
+  if (iterations) *iterations = b;
   return VO_OK;
 }
 

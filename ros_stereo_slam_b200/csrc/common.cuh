@@ -40,7 +40,10 @@ struct PyrLevel {
   size_t plane;      // elements (bytes of img, short2 of deriv) per plane = (h + 2*PAD_Y) * pitch
   uint8_t* img;      // padded buffer base; pixel (x,y) of plane k at img[k*plane + (y+PAD_Y)*pitch + x + PAD_L]
   short2* deriv;     // padded (dx,dy) buffer, same geometry, element pitch = pitch
+  uint8_t* img_alloc;  // cudaMalloc'ed block: GUARD_ROWS rows before img and after the last plane, so that the LK
+                       // tiles (staged with a margin, lk.cu) may read a few rows beyond the padded image
 };
+constexpr int GUARD_ROWS = 8;
 
 struct Pyramid {
   PyrLevel lv[MAX_LEVELS];

@@ -1,51 +1,65 @@
-// lk.cu -- K2: pyramidal Lucas-Kanade tracking, one warp per keypoint, all pyramid levels
-// in one launch.  Replaces cv::calcOpticalFlowPyrLK as the reference calls it with all
-// defaults (src/tracking.cpp:18 stereo L->R, :52 temporal): 21x21 window, 4 levels,
-// 30 iterations / eps 0.01, minEigThreshold 1e-4, 1-channel u8 images.
+// lk.cu -- K2: pyramidal Lucas-Kanade tracking, one warp per keypoint, all pyramid levels in one
+// launch.  Replaces cv::calcOpticalFlowPyrLK as the reference calls it with all defaults
+// (src/tracking.cpp:18 stereo L->R, :52 temporal): 21x21 window, 4 levels, 30 iterations / eps 0.01,
+// minEigThreshold 1e-4.
 //
-// Arithmetic follows OpenCV's LKTrackerInvoker exactly where it is exact: 14-bit fixed
-// point bilinear weights (round-half-even), CV_DESCALE, int16-range patch/derivative
-// values, FLT_SCALE = 2^-20, float 2x2 solve with every product and sum rounded
-// separately (no FMA contraction), status decided at level 0 only, the oscillation
-// half-step rule, the final err pass.  The 441-term window sums are accumulated EXACTLY
-// in integers (per-lane int32 partials, warp REDUX on a hi/lo split) and rounded to float
-// once; OpenCV accumulates them in float SIMD lanes, which is the only source of
-// difference (~1e-5 px typical).  oracle/lk.py is the bit-exact twin.
+// BIT-IDENTICAL to OpenCV 4.13 (SSE baseline build of video/lkpyramid.cpp), including the order in
+// which OpenCV accumulates its window sums in float.  OpenCV walks a window row in steps of 8
+// samples: the A sums (Ix*Ix, Ix*Iy, Iy*Iy) go through four float SIMD lanes (sample x -> lane x&3,
+// product and sum each rounded), the b sums (diff*Ix, diff*Iy) through the same four lanes with the
+// exact int32 pair sum of samples (x, x+4) converted to float first; the samples left over after the
+// last full step of 8 (x = 16..20) go through ONE scalar float accumulator.  Per sum that is FIVE
+// sequential float CHAINS over the whole window (row-major), combined at the end as
+//     total = tail + ((c0 + c2) + (c1 + c3))          (every + rounded to float)
+// oracle/lk.py restates this and is pinned bit for bit against cv2 (tests/test_oracle_lk.py).
 //
-// Mapping: the 21x21 window is cut into 63 horizontal segments of 7 pixels; lane l owns
-// segments l and l+32 (14 pixels, lane 31 has 7).  I / Ix / Iy patches stay in registers
-// across iterations.  Every bilinear sample is two DP2A instructions (signed 16-bit weight pair
-// x unsigned 8-bit pixel pair) with the rounding constant folded into the accumulator.
+// How the sequential chains are evaluated in parallel: every term is an INTEGER, so a chain is exact --
+// and therefore order-independent -- as long as no partial sum reaches 2^24.  Each lane accumulates
+// its samples in integers into per-chain registers (the chain of a sample is a compile-time property of
+// its register), and next to them a bound on the sum of |term| per chain.  If the warp-wide bounds stay
+// below 2^24 (98-99 % of the iterations on the synthetic sequences) the five exact chain totals go
+// through the final float combination above and the result is OpenCV's, bit for bit.  Otherwise the warp
+// takes the slow path: the float terms are written to shared memory and lanes 0..9 (0..4 per A sum) add
+// them up one by one in OpenCV's order.
 //
-// Memory path (what ncu said about the first two versions: l1tex 73 % then 92 % busy, issue only
-// 37-66 %): a warp-wide load whose lanes sit in 11 different image rows costs 11+ L1 wavefronts,
-// whatever its width.  So the 22x22-byte source patch is first STAGED into a warp-private
-// shared-memory tile with row-coalesced loads (lane -> (row = 4i + lane/8, word = lane%8): 6
-// loads of 4 rows each, ~30 wavefronts instead of ~130), then every lane reads its segments from
-// shared memory (3 words per row, realigned with a funnel shift).  The derivative patch
-// (22x22 short2) is staged the same way once per level.  Levels live padded in HBM/L2
-// (common.cuh), so none of this carries bounds logic.
-#include "common.cuh"
+// Mapping: a window row is cut into two OCTS (samples 0..7, 8..15) and one TAIL (16..20).  Lane l owns
+// oct l in slot A; in slot B lanes 0..9 own octs 32..41 and lanes 10..30 the tail of row l-10 (processed
+// as an oct whose samples 5..7 have zero multiplicands).  In an oct, sample i belongs to chain i&3 and
+// (i, i+4) is one of OpenCV's int32 pairs.  Bilinear samples are two DP2A each (signed 16-bit weight
+// pair x unsigned 8-bit pixel pair), from a warp-private shared-memory tile.
+//
+// Memory path: the 28 x 32-byte J tile is staged with cp.async (row-coalesced: 8 lanes per row) around the
+// window WITH A MARGIN of 3 px, so that the usual sub-pixel moves of an LK iteration never restage; the
+// tile of a level is requested before the window extraction of that level starts and lands behind it.
+// Levels live padded in HBM/L2 (common.cuh), so none of this carries bounds logic.
+#include "lk_v1.cuh"
 
 namespace vo {
 
+namespace {
+
 constexpr int WIN = LK_WIN;
-constexpr int SEG = 7;                      // pixels per segment
-constexpr int SEGS_PER_ROW = WIN / SEG;     // 3
-constexpr int NSEG = WIN * SEGS_PER_ROW;    // 63
 constexpr int W_BITS = 14;
+constexpr int TROWS = 28;                 // staged rows
+constexpr int TS = 9;                     // tile row stride in words (8 used + 1: conflict-poor)
+constexpr int TILE_WORDS = TROWS * TS;    // 252
+constexpr int DROWS = WIN + 1;            // 22 derivative rows
+constexpr int DS = 24;                    // derivative tile row stride (16-byte aligned rows)
+constexpr int DTILE_WORDS = DROWS * DS + 8;   // 536 (the tail lanes read one word past the last row)
+constexpr int NB_SIMD = 2 * WIN;          // 42 pair terms per SIMD chain of a b sum
+constexpr int NA_SIMD = 4 * WIN;          // 84 terms per SIMD chain of an A sum
+constexpr int N_TAIL = 5 * WIN;           // 105 terms of the scalar chain
+constexpr int FB_WORDS = 2 * (4 * NB_SIMD + N_TAIL);   // 546: b1 | b2 terms
+constexpr int FA_WORDS = 4 * NA_SIMD + N_TAIL;         // 441: one A sum at a time
+constexpr int SCRATCH_WORDS = (TILE_WORDS + DTILE_WORDS) > FB_WORDS ? (TILE_WORDS + DTILE_WORDS) : FB_WORDS;  // 780
+constexpr int WARP_WORDS = TILE_WORDS + SCRATCH_WORDS;  // J tile | {I tile + derivative tile} U {chain terms}
+constexpr int LK_WARPS = 4;
+constexpr int MARGIN = 3;
+constexpr int SAFE_LIMIT = 1 << 24;
+constexpr unsigned FULL = 0xffffffffu;
 
-__device__ __forceinline__ long long warp_sum_exact(int v) {
-  // exact 64-bit sum of 32 int32 partials (|v| < 2^30) with two REDUX instructions
-  const int hi = v >> 12;
-  const int lo = v & 4095;
-  const int shi = __reduce_add_sync(0xffffffffu, hi);
-  const int slo = __reduce_add_sync(0xffffffffu, lo);
-  return (long long)shi * 4096 + (long long)slo;
-}
-
-__device__ __forceinline__ void lk_weights(float a, float b, unsigned& wt, unsigned& wb, int& iw00, int& iw01,
-                                           int& iw10, int& iw11) {
+__device__ __forceinline__ void lk_weights(float a, float b, unsigned& wt, unsigned& wb, int& iw00, int& iw01, int& iw10,
+                                           int& iw11) {
   const float s = (float)(1 << W_BITS);
   const float oma = __fsub_rn(1.f, a), omb = __fsub_rn(1.f, b);
   iw00 = __float2int_rn(__fmul_rn(__fmul_rn(oma, omb), s));
@@ -56,138 +70,149 @@ __device__ __forceinline__ void lk_weights(float a, float b, unsigned& wt, unsig
   wb = ((unsigned)iw10 & 0xffffu) | ((unsigned)iw11 << 16);
 }
 
-// d = c + a.s16[0]*b.u8[0] + a.s16[1]*b.u8[1]  (signed 16-bit weights: iw11 = 2^14 - the other
-// three can be -1; unsigned 8-bit pixels).  Plain (non-volatile) asm so that ptxas may schedule it.
-__device__ __forceinline__ int dp2a_w(unsigned w, unsigned px, int c) {
+// d = c + a.s16[0]*b.u8[0] + a.s16[1]*b.u8[1]   (.hi: bytes 2,3 of b)
+__device__ __forceinline__ int dp2a_lo(unsigned w, unsigned px, int c) {
   int d;
   asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(px), "r"(c));
   return d;
 }
-// same with bytes 2,3 of px
-__device__ __forceinline__ int dp2a_w_hi(unsigned w, unsigned px, int c) {
+__device__ __forceinline__ int dp2a_hi(unsigned w, unsigned px, int c) {
   int d;
   asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(w), "r"(px), "r"(c));
   return d;
 }
 
-constexpr int PROWS = WIN + 1;   // 22 source rows
-#ifndef LK_OPT_HI
-#define LK_OPT_HI 1
-#endif
-#ifndef LK_OPT_DENSE
-#define LK_OPT_DENSE 1
-#endif
-#ifndef LK_OPT_HOIST
-#define LK_OPT_HOIST 1
-#endif
-constexpr int PS = LK_OPT_DENSE ? 7 : 9;            // tile row stride in 32-bit words (dense: conflict-free stores, 2-way loads)
-constexpr int DS = LK_OPT_DENSE ? 22 : 23;           // derivative tile row stride in short2 (dense, same reasoning)
-constexpr int TILE_WORDS = PROWS * PS;          // 198
-constexpr int DTILE_WORDS = PROWS * DS;         // 506
-constexpr int WARP_SMEM_WORDS = TILE_WORDS + DTILE_WORDS;
-constexpr int LK_WARPS = 4;
-
-// Stage the 22 x 28-byte patch whose (unaligned) origin is `a0` into `tile`; returns the byte
-// offset (0..3) of the origin inside the first staged word.  lane_off = (lane/8)*(pitch/4) +
-// lane%8 and step = 4*(pitch/4) are per-level constants, so each load is one 64-bit pointer bump.
-// `staged` (optional, warp-uniform) remembers the word-aligned origin that is in the tile: an LK iteration
-// usually moves the window by a fraction of a pixel, so the next iteration's patch is the one already staged
-// (same rows, same first word, only the byte offset and the bilinear weights change) and the six loads, six
-// stores and the exposed L2 latency of re-staging it are skipped.
-__device__ __forceinline__ unsigned stage_patch(const uint8_t* a0, int lane_off, int step, unsigned* tile_lane,
-                                                bool col_ok, bool last_ok, uintptr_t* staged = nullptr) {
-  const uintptr_t a = reinterpret_cast<uintptr_t>(a0);
-  if (staged) {
-    if (*staged == (a & ~uintptr_t(3))) return (unsigned)(a & 3);
-    *staged = a & ~uintptr_t(3);
-  }
-  const unsigned* w = reinterpret_cast<const unsigned*>(a & ~uintptr_t(3)) + lane_off;
-  __syncwarp();   // everyone is done reading the previous tile
-  unsigned v[6];
-#pragma unroll
-  for (int i = 0; i < 6; i++) {
-    v[i] = 0;
-    if (col_ok && (i < 5 || last_ok)) v[i] = __ldg(w);
-    w += step;
-  }
-#pragma unroll
-  for (int i = 0; i < 6; i++)
-    if (col_ok && (i < 5 || last_ok)) tile_lane[i * 4 * PS] = v[i];
-  __syncwarp();
-  return (unsigned)(a & 3);
+__device__ __forceinline__ void cp_async4(unsigned* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// bilinear samples (x = 0..6) of the segment at (row, byte offset bo) of a staged tile
-__device__ __forceinline__ void seg_bilinear(const unsigned* tile, int row, unsigned bo, unsigned wt, unsigned wb,
-                                             int out[SEG]) {
-  const unsigned* p = tile + row * PS + (bo >> 2);
+// Request the 28 x 8-word tile whose first word is at `src` (4-byte aligned): lane -> (row 4i + lane/8, word lane%8).
+__device__ __forceinline__ void stage_tile(unsigned* tile_lane, const uint8_t* src, int pitch, int lane) {
+  const unsigned* w = reinterpret_cast<const unsigned*>(src) + (lane >> 3) * (pitch >> 2) + (lane & 7);
+#pragma unroll
+  for (int i = 0; i < TROWS / 4; i++) {
+    cp_async4(tile_lane + i * 4 * TS, w);
+    w += pitch;   // 4 rows, in words
+  }
+}
+
+// the 8 bilinear samples of the oct whose first source byte is byte `bo` of tile row `rowp` (and the row below)
+__device__ __forceinline__ void oct_sample(const unsigned* rowp, unsigned bo, unsigned wt, unsigned wb, int out[8]) {
+  const unsigned* p = rowp + (bo >> 2);
   const unsigned sh = (bo & 3) * 8;
-  const unsigned t0 = __funnelshift_r(p[0], p[1], sh), t1 = __funnelshift_r(p[1], p[2], sh);
-  const unsigned b0 = __funnelshift_r(p[PS], p[PS + 1], sh), b1 = __funnelshift_r(p[PS + 1], p[PS + 2], sh);
-#if !LK_OPT_HI
-  const unsigned tp[SEG] = {t0, t0 >> 8, t0 >> 16, __funnelshift_r(t0, t1, 24), t1, t1 >> 8, t1 >> 16};
-  const unsigned bp[SEG] = {b0, b0 >> 8, b0 >> 16, __funnelshift_r(b0, b1, 24), b1, b1 >> 8, b1 >> 16};
-#pragma unroll
-  for (int x = 0; x < SEG; x++)
-    out[x] = dp2a_w(wb, bp[x], dp2a_w(wt, tp[x], 1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
-#else
-  // pixel pairs (x, x+1): bytes (0,1),(2,3) of t0 / t1 via dp2a.lo/.hi; the odd ones from the
-  // registers shifted by one byte -- 2 extra shifts per row instead of 5
-  const unsigned tu = __funnelshift_r(t0, t1, 8), tv = t1 >> 8;
-  const unsigned bu = __funnelshift_r(b0, b1, 8), bv = b1 >> 8;
+  const unsigned a0 = p[0], a1 = p[1], a2 = p[2];
+  const unsigned c0 = p[TS], c1 = p[TS + 1], c2 = p[TS + 2];
+  const unsigned t0 = __funnelshift_r(a0, a1, sh), t1 = __funnelshift_r(a1, a2, sh), t2 = a2 >> sh;
+  const unsigned b0 = __funnelshift_r(c0, c1, sh), b1 = __funnelshift_r(c1, c2, sh), b2 = c2 >> sh;
+  // pixel pairs (x, x+1): even x from t0/t1 via dp2a.lo/.hi, odd x from the registers shifted by one byte
+  const unsigned tu = __funnelshift_r(t0, t1, 8), tv = __funnelshift_r(t1, t2, 8);
+  const unsigned bu = __funnelshift_r(b0, b1, 8), bv = __funnelshift_r(b1, b2, 8);
   const int rc = 1 << (W_BITS - 5 - 1);
-  out[0] = dp2a_w(wb, b0, dp2a_w(wt, t0, rc)) >> (W_BITS - 5);
-  out[1] = dp2a_w(wb, bu, dp2a_w(wt, tu, rc)) >> (W_BITS - 5);
-  out[2] = dp2a_w_hi(wb, b0, dp2a_w_hi(wt, t0, rc)) >> (W_BITS - 5);
-  out[3] = dp2a_w_hi(wb, bu, dp2a_w_hi(wt, tu, rc)) >> (W_BITS - 5);
-  out[4] = dp2a_w(wb, b1, dp2a_w(wt, t1, rc)) >> (W_BITS - 5);
-  out[5] = dp2a_w(wb, bv, dp2a_w(wt, tv, rc)) >> (W_BITS - 5);
-  out[6] = dp2a_w_hi(wb, b1, dp2a_w_hi(wt, t1, rc)) >> (W_BITS - 5);
-#endif
+  out[0] = dp2a_lo(wb, b0, dp2a_lo(wt, t0, rc)) >> (W_BITS - 5);
+  out[1] = dp2a_lo(wb, bu, dp2a_lo(wt, tu, rc)) >> (W_BITS - 5);
+  out[2] = dp2a_hi(wb, b0, dp2a_hi(wt, t0, rc)) >> (W_BITS - 5);
+  out[3] = dp2a_hi(wb, bu, dp2a_hi(wt, tu, rc)) >> (W_BITS - 5);
+  out[4] = dp2a_lo(wb, b1, dp2a_lo(wt, t1, rc)) >> (W_BITS - 5);
+  out[5] = dp2a_lo(wb, bv, dp2a_lo(wt, tv, rc)) >> (W_BITS - 5);
+  out[6] = dp2a_hi(wb, b1, dp2a_hi(wt, t1, rc)) >> (W_BITS - 5);
+  out[7] = dp2a_hi(wb, bv, dp2a_hi(wt, tv, rc)) >> (W_BITS - 5);
 }
 
-#ifndef LK_MINBLOCKS
-#define LK_MINBLOCKS 4
-#endif
-__global__ void __launch_bounds__(128)
+// bilinear (Ix, Iy) of the 8 samples of an oct from the staged short2 derivative tile (row pointer d, 9 columns)
+__device__ __forceinline__ void oct_deriv(const unsigned* d, int iw00, int iw01, int iw10, int iw11, int ix[8], int iy[8]) {
+  unsigned top_[9], bot_[9];
+  {
+    const uint4 q0 = *reinterpret_cast<const uint4*>(d), q1 = *reinterpret_cast<const uint4*>(d + 4);
+    const uint4 r0 = *reinterpret_cast<const uint4*>(d + DS), r1 = *reinterpret_cast<const uint4*>(d + DS + 4);
+    top_[0] = q0.x; top_[1] = q0.y; top_[2] = q0.z; top_[3] = q0.w; top_[4] = q1.x; top_[5] = q1.y; top_[6] = q1.z; top_[7] = q1.w;
+    bot_[0] = r0.x; bot_[1] = r0.y; bot_[2] = r0.z; bot_[3] = r0.w; bot_[4] = r1.x; bot_[5] = r1.y; bot_[6] = r1.z; bot_[7] = r1.w;
+    top_[8] = d[8];
+    bot_[8] = d[DS + 8];
+  }
+#pragma unroll
+  for (int x = 0; x < 8; x++) {
+    // short2 packed in a word: .x = low half (dx), .y = high half (dy)
+    ix[x] = ((int)(short)(top_[x] & 0xffff) * iw00 + (int)(short)(top_[x + 1] & 0xffff) * iw01 +
+             (int)(short)(bot_[x] & 0xffff) * iw10 + (int)(short)(bot_[x + 1] & 0xffff) * iw11 + (1 << (W_BITS - 1))) >> W_BITS;
+    iy[x] = (((int)top_[x] >> 16) * iw00 + ((int)top_[x + 1] >> 16) * iw01 + ((int)bot_[x] >> 16) * iw10 +
+             ((int)bot_[x + 1] >> 16) * iw11 + (1 << (W_BITS - 1))) >> W_BITS;
+  }
+}
+
+// OpenCV's final combination of the five chains of one sum (every + rounded to float)
+__device__ __forceinline__ float chain_combine(float c0, float c1, float c2, float c3, float tail) {
+  return __fadd_rn(tail, __fadd_rn(__fadd_rn(c0, c2), __fadd_rn(c1, c3)));
+}
+
+// per-lane chain totals of one sum: slot A (always an oct) + slot B (an oct for !isq, a tail for isq)
+__device__ __forceinline__ void lane_chains(const int a[4], const int b[4], int notq, int isq, int c[5]) {
+#pragma unroll
+  for (int k = 0; k < 4; k++) c[k] = a[k] + notq * b[k];
+  c[4] = isq * ((b[0] + b[1]) + (b[2] + b[3]));
+}
+
+// lanes 0 .. nsum*5-1 add up their chain of float terms one by one (OpenCV's order); terms of sum s start at
+// f + s*stride: four SIMD chains of n_simd terms, then the tail chain of N_TAIL terms.  Returns the five
+// chain values of sum `s` broadcast to every lane.
+__device__ __forceinline__ float run_chain(const float* f, int lane, int nsum, int n_simd) {
+  float acc = 0.f;
+  if (lane < nsum * 5) {
+    const int s = lane / 5, k = lane - s * 5;
+    const float* t = f + s * (4 * n_simd + N_TAIL) + (k < 4 ? k * n_simd : 4 * n_simd);
+    const int n = k < 4 ? n_simd : N_TAIL;
+    for (int j = 0; j < n; j++) acc = __fadd_rn(acc, t[j]);
+  }
+  return acc;
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(LK_WARPS * 32)
 lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n, float2* __restrict__ next_pts,
           uint8_t* __restrict__ status, float* __restrict__ err, int max_iters, double eps_sq, float min_eig_thr,
           unsigned long long* __restrict__ work, const int* __restrict__ n_dev) {
   if (n_dev) n = min(n, *n_dev);
-  __shared__ unsigned smem[LK_WARPS * WARP_SMEM_WORDS];
+  __shared__ __align__(16) unsigned smem[LK_WARPS * WARP_WORDS];
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= n) return;
-  unsigned* tile = smem + (threadIdx.x >> 5) * WARP_SMEM_WORDS;
-  unsigned* dtile = tile + TILE_WORDS;
-  // staging role of this lane: row (lane/8) + 4i, word lane%8 (< 7) of the 22 x 7-word tile
-  unsigned* tile_lane = tile + (lane >> 3) * PS + (lane & 7);
-  const bool st_col_ok = (lane & 7) < 7, st_last_ok = (lane >> 3) < PROWS - 20;
+  unsigned* jtile = smem + (threadIdx.x >> 5) * WARP_WORDS;
+  unsigned* itile = jtile + TILE_WORDS;        // scratch: I tile | derivative tile, later the chain terms
+  unsigned* dtile = itile + TILE_WORDS;
+  float* fterms = reinterpret_cast<float*>(itile);
+  const int st_lane = (lane >> 3) * TS + (lane & 7);
   const float2 pt = prev_pts[warp];
   const float half_win = (WIN - 1) * 0.5f;
   const float FLT_SCALE = 1.f / (1 << 20);
   const float eps_lo = (float)(eps_sq * (1.0 - 1e-5)), eps_hi = (float)(eps_sq * (1.0 + 1e-5));
 
-  // this lane's two segments (fixed for the whole kernel)
-  const int rowA = lane / SEGS_PER_ROW, colA = (lane - rowA * SEGS_PER_ROW) * SEG;
-  const int sB = lane + 32;
-  const bool hasB = sB < NSEG;
-  const int rowB = hasB ? sB / SEGS_PER_ROW : 0, colB = hasB ? (sB - rowB * SEGS_PER_ROW) * SEG : 0;
+  // this lane's two units (fixed for the whole kernel)
+  const int rowA = lane >> 1, colA = (lane & 1) * 8;
+  const bool isq_b = lane >= 10;               // slot B is a tail (or, lane 31, nothing)
+  const bool hasB = lane < 31;
+  const int isq = isq_b ? 1 : 0, notq = 1 - isq;
+  const int rowB = isq_b ? (hasB ? lane - 10 : 0) : 16 + (lane >> 1);
+  const int colB = isq_b ? 16 : (lane & 1) * 8;
 
   float outx = 0.f, outy = 0.f;  // nextPts[ptidx] as OpenCV keeps it between levels
   bool st = true;
   float errv = 0.f;
-  unsigned int n_levels_done = 0, n_iters_done = 0;
+  unsigned int n_levels_done = 0, n_iters_done = 0, n_slow_a = 0, n_slow_b = 0;
 
-  int Iw[2 * SEG], Ix[2 * SEG], Iy[2 * SEG];
+  int Iw[16], Ix[16], Iy[16];
+  int mpA[4], mB[8];
 
   const int top = prev.nlevels - 1;
   for (int level = top; level >= 0; level--) {
     const PyrLevelView I = prev.lv[level];
     const PyrLevelView J = next.lv[level];
     const int pitch = I.pitch;
-    const int st_step = pitch;                              // 4 rows, in words: 4 * (pitch / 4)
-    const int st_off = (lane >> 3) * (pitch >> 2) + (lane & 7);
     const float scale = 1.f / (float)(1 << level);
     float px = __fmul_rn(pt.x, scale), py = __fmul_rn(pt.y, scale);
     float nx, ny;
@@ -203,7 +228,7 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
 
     px = __fsub_rn(px, half_win);
     py = __fsub_rn(py, half_win);
-    int ipx = (int)floorf(px), ipy = (int)floorf(py);
+    const int ipx = (int)floorf(px), ipy = (int)floorf(py);
     if (ipx < -WIN || ipx >= I.w || ipy < -WIN || ipy >= I.h) {
       if (level == 0) {
         st = false;
@@ -215,77 +240,135 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
     unsigned wt, wb;
     lk_weights(__fsub_rn(px, (float)ipx), __fsub_rn(py, (float)ipy), wt, wb, iw00, iw01, iw10, iw11);
 
-    // ---- window extraction from the previous image + its Scharr derivative
-    int sA11 = 0, sA12 = 0, sA22 = 0, sC1 = 0, sC2 = 0;
-    uintptr_t staged = 0;     // the I patch below goes through the tile unconditionally; J patches are cached
+    // ---- request the I tile, the derivative patch and (with a margin) the J tile of the start position
+    nx = __fsub_rn(nx, half_win);
+    ny = __fsub_rn(ny, half_win);
+    int tX0 = -(1 << 20), tY0 = -(1 << 20);     // origin of the staged J tile in padded coordinates (none yet)
+    __syncwarp();                                // everyone is done with the tiles of the previous level
+    const int iX = ipx + PAD_L, iY = ipy + PAD_Y;
     {
-      const size_t o0 = (size_t)(ipy + PAD_Y) * pitch + (ipx + PAD_L);
-      const unsigned sh = stage_patch(I.img + o0, st_off, st_step, tile_lane, st_col_ok, st_last_ok);
-      // derivative patch: 484 short2, row-coalesced (lane -> consecutive elements)
-      {
-        const unsigned* dsrc = reinterpret_cast<const unsigned*>(I.deriv + o0);
-        int r = 0, x = lane;
-        if (x >= PROWS) { x -= PROWS; r = 1; }
+      stage_tile(itile + st_lane, I.img + (size_t)iY * pitch + (iX & ~3), pitch, lane);
+      // derivative patch: 22 x 22 short2, row-coalesced (lane -> consecutive elements)
+      const unsigned* dsrc = reinterpret_cast<const unsigned*>(I.deriv + (size_t)iY * pitch + iX);
+      int r = 0, x = lane;
+      if (x >= DROWS) { x -= DROWS; r = 1; }
 #pragma unroll
-        for (int i = 0; i < 16; i++) {
-          if (r < PROWS) dtile[r * DS + x] = __ldg(dsrc + (size_t)r * pitch + x);
-          x += 32 - PROWS; r += 1;                       // advance by 32 elements of 22-wide rows
-          if (x >= PROWS) { x -= PROWS; r += 1; }
+      for (int i = 0; i < 16; i++) {
+        if (r < DROWS) cp_async4(dtile + r * DS + x, dsrc + (size_t)r * pitch + x);
+        x += 32 - DROWS; r += 1;                       // advance by 32 elements of 22-wide rows
+        if (x >= DROWS) { x -= DROWS; r += 1; }
+      }
+      cp_async_commit();
+      const int inx = (int)floorf(nx), iny = (int)floorf(ny);
+      if (!(inx < -WIN || inx >= J.w || iny < -WIN || iny >= J.h)) {
+        tX0 = (inx + PAD_L - MARGIN) & ~3;
+        tY0 = iny + PAD_Y - MARGIN;
+        stage_tile(jtile + st_lane, J.img + (size_t)tY0 * pitch + tX0, pitch, lane);
+      }
+      cp_async_commit();
+      cp_async_wait<1>();
+      __syncwarp();
+    }
+
+    // ---- window extraction from the previous image + its Scharr derivative
+    int cA11[5], cA12[5], cA22[5], cC1[5], cC2[5], cU[5];
+    {
+      const unsigned bI = (unsigned)(iX & 3);
+      oct_sample(itile + rowA * TS, bI + colA, wt, wb, Iw);
+      oct_sample(itile + rowB * TS, bI + colB, wt, wb, Iw + 8);
+      oct_deriv(dtile + rowA * DS + colA, iw00, iw01, iw10, iw11, Ix, Iy);
+      oct_deriv(dtile + rowB * DS + colB, iw00, iw01, iw10, iw11, Ix + 8, Iy + 8);
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const bool valid = hasB && (!isq_b || i < 5);
+        if (!valid) { Iw[8 + i] = 0; Ix[8 + i] = 0; Iy[8 + i] = 0; }
+      }
+      int a11[4] = {0, 0, 0, 0}, a12[4] = {0, 0, 0, 0}, a22[4] = {0, 0, 0, 0}, c1[4] = {0, 0, 0, 0}, c2[4] = {0, 0, 0, 0}, u[4] = {0, 0, 0, 0};
+      int b11[4] = {0, 0, 0, 0}, b12[4] = {0, 0, 0, 0}, b22[4] = {0, 0, 0, 0}, d1[4] = {0, 0, 0, 0}, d2[4] = {0, 0, 0, 0}, v[4] = {0, 0, 0, 0};
+      int mA[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int k = i & 3;
+        a11[k] += Ix[i] * Ix[i];
+        a12[k] += Ix[i] * Iy[i];
+        a22[k] += Iy[i] * Iy[i];
+        c1[k] += Iw[i] * Ix[i];
+        c2[k] += Iw[i] * Iy[i];
+        mA[i] = max(abs(Ix[i]), abs(Iy[i]));
+        u[k] += mA[i] * mA[i];
+        b11[k] += Ix[8 + i] * Ix[8 + i];
+        b12[k] += Ix[8 + i] * Iy[8 + i];
+        b22[k] += Iy[8 + i] * Iy[8 + i];
+        d1[k] += Iw[8 + i] * Ix[8 + i];
+        d2[k] += Iw[8 + i] * Iy[8 + i];
+        mB[i] = max(abs(Ix[8 + i]), abs(Iy[8 + i]));
+        v[k] += mB[i] * mB[i];
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) mpA[k] = max(mA[k], mA[k + 4]);
+      lane_chains(a11, b11, notq, isq, cA11);
+      lane_chains(a12, b12, notq, isq, cA12);
+      lane_chains(a22, b22, notq, isq, cA22);
+      lane_chains(c1, d1, notq, isq, cC1);
+      lane_chains(c2, d2, notq, isq, cC2);
+      lane_chains(u, v, notq, isq, cU);
+    }
+    bool safeA = true;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+      cA11[k] = __reduce_add_sync(FULL, cA11[k]);
+      cA12[k] = __reduce_add_sync(FULL, cA12[k]);
+      cA22[k] = __reduce_add_sync(FULL, cA22[k]);
+      cC1[k] = __reduce_add_sync(FULL, cC1[k]);     // modulo 2^32: only differences with the per-iteration sums are used
+      cC2[k] = __reduce_add_sync(FULL, cC2[k]);
+      // sum over the chain of max(Ix^2, Iy^2) >= every partial sum of the chain's terms (clamped per lane: no overflow)
+      safeA = safeA && (__reduce_add_sync(FULL, min(cU[k], SAFE_LIMIT)) < SAFE_LIMIT);
+    }
+    float A11, A12, A22;
+    if (safeA) {
+      A11 = chain_combine((float)cA11[0], (float)cA11[1], (float)cA11[2], (float)cA11[3], (float)cA11[4]);
+      A12 = chain_combine((float)cA12[0], (float)cA12[1], (float)cA12[2], (float)cA12[3], (float)cA12[4]);
+      A22 = chain_combine((float)cA22[0], (float)cA22[1], (float)cA22[2], (float)cA22[3], (float)cA22[4]);
+    } else {
+      // slow path: the float terms in OpenCV's order, one A sum at a time (the I / derivative tiles are consumed)
+      n_slow_a++;
+      float res[3];
+#pragma unroll
+      for (int s = 0; s < 3; s++) {
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const int pa = s == 0 ? Ix[i] * Ix[i] : (s == 1 ? Ix[i] * Iy[i] : Iy[i] * Iy[i]);
+          fterms[(i & 3) * NA_SIMD + 4 * rowA + (colA >> 2) + (i >> 2)] = __int2float_rn(pa);
+          const int pb = s == 0 ? Ix[8 + i] * Ix[8 + i] : (s == 1 ? Ix[8 + i] * Iy[8 + i] : Iy[8 + i] * Iy[8 + i]);
+          if (!isq_b) fterms[(i & 3) * NA_SIMD + 4 * rowB + (colB >> 2) + (i >> 2)] = __int2float_rn(pb);
+          else if (hasB && i < 5) fterms[4 * NA_SIMD + 5 * rowB + i] = __int2float_rn(pb);
         }
         __syncwarp();
+        const float acc = run_chain(fterms, lane, 1, NA_SIMD);
+        res[s] = chain_combine(__shfl_sync(FULL, acc, 0), __shfl_sync(FULL, acc, 1), __shfl_sync(FULL, acc, 2),
+                               __shfl_sync(FULL, acc, 3), __shfl_sync(FULL, acc, 4));
       }
-      seg_bilinear(tile, rowA, colA + sh, wt, wb, Iw);
-      if (hasB) seg_bilinear(tile, rowB, colB + sh, wt, wb, Iw + SEG);
-#pragma unroll
-      for (int sgi = 0; sgi < 2; sgi++) {
-        if (sgi == 1 && !hasB) {
-#pragma unroll
-          for (int x = 0; x < SEG; x++) { Iw[SEG + x] = 0; Ix[SEG + x] = 0; Iy[SEG + x] = 0; }
-          break;
-        }
-        const unsigned* d = dtile + (sgi ? rowB : rowA) * DS + (sgi ? colB : colA);
-        unsigned top_[SEG + 1], bot_[SEG + 1];
-#pragma unroll
-        for (int x = 0; x <= SEG; x++) {
-          top_[x] = d[x];
-          bot_[x] = d[DS + x];
-        }
-#pragma unroll
-        for (int x = 0; x < SEG; x++) {
-          // short2 packed in a word: .x = low half (dx), .y = high half (dy)
-          const int ixv = ((int)(short)(top_[x] & 0xffff) * iw00 + (int)(short)(top_[x + 1] & 0xffff) * iw01 +
-                           (int)(short)(bot_[x] & 0xffff) * iw10 + (int)(short)(bot_[x + 1] & 0xffff) * iw11 +
-                           (1 << (W_BITS - 1))) >> W_BITS;
-          const int iyv = (((int)top_[x] >> 16) * iw00 + ((int)top_[x + 1] >> 16) * iw01 + ((int)bot_[x] >> 16) * iw10 +
-                           ((int)bot_[x + 1] >> 16) * iw11 + (1 << (W_BITS - 1))) >> W_BITS;
-          Ix[sgi * SEG + x] = ixv;
-          Iy[sgi * SEG + x] = iyv;
-          sA11 += ixv * ixv;
-          sA12 += ixv * iyv;
-          sA22 += iyv * iyv;
-          sC1 += Iw[sgi * SEG + x] * ixv;
-          sC2 += Iw[sgi * SEG + x] * iyv;
-        }
-      }
+      A11 = res[0];
+      A12 = res[1];
+      A22 = res[2];
     }
-    const float A11 = __fmul_rn(__ll2float_rn(warp_sum_exact(sA11)), FLT_SCALE);
-    const float A12 = __fmul_rn(__ll2float_rn(warp_sum_exact(sA12)), FLT_SCALE);
-    const float A22 = __fmul_rn(__ll2float_rn(warp_sum_exact(sA22)), FLT_SCALE);
-    // sum(diff*Ix) = sum(J*Ix) - sum(I*Ix): the second term is constant over the iterations
-    const long long C1 = LK_OPT_HOIST ? warp_sum_exact(sC1) : 0, C2 = LK_OPT_HOIST ? warp_sum_exact(sC2) : 0;
+    A11 = __fmul_rn(A11, FLT_SCALE);
+    A12 = __fmul_rn(A12, FLT_SCALE);
+    A22 = __fmul_rn(A22, FLT_SCALE);
     float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
     const float dd = __fsub_rn(A11, A22);
     const float q = __fadd_rn(__fmul_rn(dd, dd), __fmul_rn(__fmul_rn(4.f, A12), A12));
     const float min_eig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), __fsqrt_rn(q)), (float)(2 * WIN * WIN));
     n_levels_done++;
+    cp_async_wait<0>();
+    __syncwarp();
     if (min_eig < min_eig_thr || D < 1.1920929e-07f) {
       if (level == 0) st = false;
       continue;
     }
     D = __fdiv_rn(1.f, D);
 
-    nx = __fsub_rn(nx, half_win);
-    ny = __fsub_rn(ny, half_win);
     float pdx = 0.f, pdy = 0.f;
     for (int j = 0; j < max_iters; j++) {
       const int inx = (int)floorf(nx), iny = (int)floorf(ny);
@@ -294,36 +377,93 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
         break;
       }
       lk_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), wt, wb, iw00, iw01, iw10, iw11);
-      const unsigned sh = stage_patch(J.img + ((iny + PAD_Y) * pitch + (inx + PAD_L)), st_off, st_step, tile_lane,
-                                      st_col_ok, st_last_ok, &staged);
-      int sb1 = 0, sb2 = 0;
+      int bx = inx + PAD_L - tX0, by = iny + PAD_Y - tY0;
+      if ((unsigned)bx > 10u || (unsigned)by > 6u) {   // the window left the staged tile
+        __syncwarp();
+        tX0 = (inx + PAD_L - MARGIN) & ~3;
+        tY0 = iny + PAD_Y - MARGIN;
+        stage_tile(jtile + st_lane, J.img + (size_t)tY0 * pitch + tX0, pitch, lane);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncwarp();
+        bx = inx + PAD_L - tX0;
+        by = MARGIN;
+      }
+      const unsigned* rowpA = jtile + (by + rowA) * TS;
+      const unsigned* rowpB = jtile + (by + rowB) * TS;
+      int c1[5], c2[5], cu[5];
       {
-        // four independent accumulators per sum (ncu: 29 % of the stalls were `wait`, i.e. the 14-deep
-        // dependent IMAD chains of a single accumulator with only 3 warps per scheduler to hide them)
-        int p1[4] = {0, 0, 0, 0}, p2[4] = {0, 0, 0, 0};
-        int jv[SEG];
-        seg_bilinear(tile, rowA, colA + sh, wt, wb, jv);
+        int a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0}, ua[4];
+        int b1[4] = {0, 0, 0, 0}, b2[4] = {0, 0, 0, 0}, ub[4] = {0, 0, 0, 0};
+        int jv[8];
+        oct_sample(rowpA, bx + colA, wt, wb, jv);
 #pragma unroll
-        for (int x = 0; x < SEG; x++) {
-          const int dj = LK_OPT_HOIST ? jv[x] : jv[x] - Iw[x];
-          p1[x & 1] += dj * Ix[x];
-          p2[x & 1] += dj * Iy[x];
+        for (int i = 0; i < 8; i++) {
+          a1[i & 3] += jv[i] * Ix[i];
+          a2[i & 3] += jv[i] * Iy[i];
         }
-        if (hasB) {
-          seg_bilinear(tile, rowB, colB + sh, wt, wb, jv);
 #pragma unroll
-          for (int x = 0; x < SEG; x++) {
-            const int dj = LK_OPT_HOIST ? jv[x] : jv[x] - Iw[SEG + x];
-            p1[2 + (x & 1)] += dj * Ix[SEG + x];
-            p2[2 + (x & 1)] += dj * Iy[SEG + x];
-          }
+        for (int k = 0; k < 4; k++) ua[k] = (int)__sad(jv[k + 4], Iw[k + 4], __sad(jv[k], Iw[k], 0u)) * mpA[k];
+        oct_sample(rowpB, bx + colB, wt, wb, jv);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          b1[i & 3] += jv[i] * Ix[8 + i];
+          b2[i & 3] += jv[i] * Iy[8 + i];
+          ub[i & 3] += (int)__sad(jv[i], Iw[8 + i], 0u) * mB[i];
         }
-        sb1 = (p1[0] + p1[1]) + (p1[2] + p1[3]);
-        sb2 = (p2[0] + p2[1]) + (p2[2] + p2[3]);
+        lane_chains(a1, b1, notq, isq, c1);
+        lane_chains(a2, b2, notq, isq, c2);
+        lane_chains(ua, ub, notq, isq, cu);
       }
       n_iters_done++;
-      const float b1 = __fmul_rn(__ll2float_rn(warp_sum_exact(sb1) - C1), FLT_SCALE);
-      const float b2 = __fmul_rn(__ll2float_rn(warp_sum_exact(sb2) - C2), FLT_SCALE);
+      bool safe = true;
+#pragma unroll
+      for (int k = 0; k < 5; k++) {
+        c1[k] = (int)((unsigned)__reduce_add_sync(FULL, c1[k]) - (unsigned)cC1[k]);   // sum(diff*Ix) = sum(J*Ix) - sum(I*Ix), modulo 2^32
+        c2[k] = (int)((unsigned)__reduce_add_sync(FULL, c2[k]) - (unsigned)cC2[k]);
+        safe = safe && (__reduce_add_sync(FULL, min(cu[k], SAFE_LIMIT)) < SAFE_LIMIT);
+      }
+      float b1f, b2f;
+      if (safe) {
+        b1f = chain_combine((float)c1[0], (float)c1[1], (float)c1[2], (float)c1[3], (float)c1[4]);
+        b2f = chain_combine((float)c2[0], (float)c2[1], (float)c2[2], (float)c2[3], (float)c2[4]);
+      } else {
+        // slow path: float(pair sums) / float(tail products) to shared memory, lanes 0..9 add them in OpenCV's order
+        n_slow_b++;
+        int jv[8];
+        __syncwarp();
+        oct_sample(rowpA, bx + colA, wt, wb, jv);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const int dA = jv[k] - Iw[k], dB = jv[k + 4] - Iw[k + 4];
+          fterms[k * NB_SIMD + 2 * rowA + (colA >> 3)] = __int2float_rn(dA * Ix[k] + dB * Ix[k + 4]);
+          fterms[FB_WORDS / 2 + k * NB_SIMD + 2 * rowA + (colA >> 3)] = __int2float_rn(dA * Iy[k] + dB * Iy[k + 4]);
+        }
+        oct_sample(rowpB, bx + colB, wt, wb, jv);
+        if (!isq_b) {
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const int dA = jv[k] - Iw[8 + k], dB = jv[k + 4] - Iw[12 + k];
+            fterms[k * NB_SIMD + 2 * rowB + (colB >> 3)] = __int2float_rn(dA * Ix[8 + k] + dB * Ix[12 + k]);
+            fterms[FB_WORDS / 2 + k * NB_SIMD + 2 * rowB + (colB >> 3)] = __int2float_rn(dA * Iy[8 + k] + dB * Iy[12 + k]);
+          }
+        } else if (hasB) {
+#pragma unroll
+          for (int i = 0; i < 5; i++) {
+            const int dA = jv[i] - Iw[8 + i];
+            fterms[4 * NB_SIMD + 5 * rowB + i] = __int2float_rn(dA * Ix[8 + i]);
+            fterms[FB_WORDS / 2 + 4 * NB_SIMD + 5 * rowB + i] = __int2float_rn(dA * Iy[8 + i]);
+          }
+        }
+        __syncwarp();
+        const float acc = run_chain(fterms, lane, 2, NB_SIMD);
+        b1f = chain_combine(__shfl_sync(FULL, acc, 0), __shfl_sync(FULL, acc, 1), __shfl_sync(FULL, acc, 2),
+                            __shfl_sync(FULL, acc, 3), __shfl_sync(FULL, acc, 4));
+        b2f = chain_combine(__shfl_sync(FULL, acc, 5), __shfl_sync(FULL, acc, 6), __shfl_sync(FULL, acc, 7),
+                            __shfl_sync(FULL, acc, 8), __shfl_sync(FULL, acc, 9));
+      }
+      const float b1 = __fmul_rn(b1f, FLT_SCALE);
+      const float b2 = __fmul_rn(b2f, FLT_SCALE);
       const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
       const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
       nx = __fadd_rn(nx, dx);
@@ -357,20 +497,31 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
         st = false;
       } else if (err) {   // callers that do not read err (the reference never does) skip the sum, not the test above
         lk_weights(__fsub_rn(fx, (float)inx), __fsub_rn(fy, (float)iny), wt, wb, iw00, iw01, iw10, iw11);
-        const unsigned sh = stage_patch(J.img + ((iny + PAD_Y) * pitch + (inx + PAD_L)), st_off, st_step, tile_lane,
-                                      st_col_ok, st_last_ok, &staged);
-        int se = 0;
-        int jv[SEG];
-        seg_bilinear(tile, rowA, colA + sh, wt, wb, jv);
-#pragma unroll
-        for (int x = 0; x < SEG; x++) se += abs(jv[x] - Iw[x]);
-        if (hasB) {
-          seg_bilinear(tile, rowB, colB + sh, wt, wb, jv);
-#pragma unroll
-          for (int x = 0; x < SEG; x++) se += abs(jv[x] - Iw[SEG + x]);
+        int bx = inx + PAD_L - tX0, by = iny + PAD_Y - tY0;
+        if ((unsigned)bx > 10u || (unsigned)by > 6u) {
+          __syncwarp();
+          tX0 = (inx + PAD_L - MARGIN) & ~3;
+          tY0 = iny + PAD_Y - MARGIN;
+          stage_tile(jtile + st_lane, J.img + (size_t)tY0 * pitch + tX0, pitch, lane);
+          cp_async_commit();
+          cp_async_wait<0>();
+          __syncwarp();
+          bx = inx + PAD_L - tX0;
+          by = MARGIN;
         }
-        const int tot = __reduce_add_sync(0xffffffffu, se);  // <= 441*8160 fits int32
-        errv = __fmul_rn((float)tot, 1.f / (32 * WIN * WIN));
+        unsigned se = 0;
+        int jv[8];
+        oct_sample(jtile + (by + rowA) * TS, bx + colA, wt, wb, jv);
+#pragma unroll
+        for (int i = 0; i < 8; i++) se = __sad(jv[i], Iw[i], se);
+        oct_sample(jtile + (by + rowB) * TS, bx + colB, wt, wb, jv);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const bool valid = hasB && (!isq_b || i < 5);
+          se += valid ? __sad(jv[i], Iw[8 + i], 0u) : 0u;
+        }
+        const int tot = __reduce_add_sync(FULL, (int)se);  // <= 441*8160 < 2^24: OpenCV's float sum is exact
+        errv = __fdiv_rn((float)tot, (float)(32 * WIN * WIN));
       }
     }
   }
@@ -382,262 +533,8 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
     if (work) {
       atomicAdd(&work[0], (unsigned long long)n_levels_done);
       atomicAdd(&work[1], (unsigned long long)n_iters_done);
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------ 3-channel (BGR) LK
-// cv::calcOpticalFlowPyrLK on 3-channel images -- what the reference actually feeds it (imread's default
-// BGR output, reference src/keyFrameManagement.cpp:52,64).  OpenCV walks the window as 21 rows x 63
-// interleaved samples (neighbour = +cn): every sum runs over the three channels of the window, the
-// bilinear samples and derivatives are per channel.  With planar storage (common.cuh) that is the
-// 1-channel computation repeated per plane with ONE set of sums: same segment mapping, same staging,
-// same DP2A samples.  Ix/Iy of the 3 x 14 samples a lane owns are kept packed (s16 | s16 << 16) in 42
-// registers; I is not kept (the sum of I*Ix is hoisted) and is re-sampled once for the err pass.
-// minEig is normalised by the window AREA (no channel factor) and err by area * cn, as in OpenCV.
-__device__ __forceinline__ void lk_deriv_seg(const unsigned* dtile, int row, int col, int iw00, int iw01, int iw10, int iw11,
-                                             const int* Iw, unsigned* ixy, int& sA11, int& sA12, int& sA22, int& sC1,
-                                             int& sC2) {
-  const unsigned* d = dtile + row * DS + col;
-  unsigned top_[SEG + 1], bot_[SEG + 1];
-#pragma unroll
-  for (int x = 0; x <= SEG; x++) {
-    top_[x] = d[x];
-    bot_[x] = d[DS + x];
-  }
-#pragma unroll
-  for (int x = 0; x < SEG; x++) {
-    const int ixv = ((int)(short)(top_[x] & 0xffff) * iw00 + (int)(short)(top_[x + 1] & 0xffff) * iw01 +
-                     (int)(short)(bot_[x] & 0xffff) * iw10 + (int)(short)(bot_[x + 1] & 0xffff) * iw11 + (1 << (W_BITS - 1))) >>
-                    W_BITS;
-    const int iyv = (((int)top_[x] >> 16) * iw00 + ((int)top_[x + 1] >> 16) * iw01 + ((int)bot_[x] >> 16) * iw10 +
-                     ((int)bot_[x + 1] >> 16) * iw11 + (1 << (W_BITS - 1))) >>
-                    W_BITS;
-    ixy[x] = ((unsigned)ixv & 0xffffu) | ((unsigned)iyv << 16);
-    sA11 += ixv * ixv;
-    sA12 += ixv * iyv;
-    sA22 += iyv * iyv;
-    sC1 += Iw[x] * ixv;
-    sC2 += Iw[x] * iyv;
-  }
-}
-
-__global__ void __launch_bounds__(128)
-lk_kernel_c3(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n, float2* __restrict__ next_pts,
-             uint8_t* __restrict__ status, float* __restrict__ err, int max_iters, double eps_sq, float min_eig_thr,
-             unsigned long long* __restrict__ work, const int* __restrict__ n_dev) {
-  constexpr int CN = 3;
-  if (n_dev) n = min(n, *n_dev);
-  // one image tile per channel (so that the J patches of an iteration can stay staged, see stage_patch)
-  // + one derivative tile
-  constexpr int WARP_WORDS_C3 = CN * TILE_WORDS + DTILE_WORDS;
-  __shared__ unsigned smem[LK_WARPS * WARP_WORDS_C3];
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= n) return;
-  unsigned* tile0 = smem + (threadIdx.x >> 5) * WARP_WORDS_C3;
-  unsigned* dtile = tile0 + CN * TILE_WORDS;
-  unsigned* tile_lane0 = tile0 + (lane >> 3) * PS + (lane & 7);
-  const bool st_col_ok = (lane & 7) < 7, st_last_ok = (lane >> 3) < PROWS - 20;
-  const float2 pt = prev_pts[warp];
-  const float half_win = (WIN - 1) * 0.5f;
-  const float FLT_SCALE = 1.f / (1 << 20);
-  const float eps_lo = (float)(eps_sq * (1.0 - 1e-5)), eps_hi = (float)(eps_sq * (1.0 + 1e-5));
-
-  const int rowA = lane / SEGS_PER_ROW, colA = (lane - rowA * SEGS_PER_ROW) * SEG;
-  const int sB = lane + 32;
-  const bool hasB = sB < NSEG;
-  const int rowB = hasB ? sB / SEGS_PER_ROW : 0, colB = hasB ? (sB - rowB * SEGS_PER_ROW) * SEG : 0;
-
-  float outx = 0.f, outy = 0.f;
-  bool st = true;
-  float errv = 0.f;
-  unsigned int n_levels_done = 0, n_iters_done = 0;
-
-  unsigned ixy[CN][2 * SEG];   // packed (Ix, Iy) of this lane's samples, per plane
-
-  const int top = prev.nlevels - 1;
-  for (int level = top; level >= 0; level--) {
-    const PyrLevelView I = prev.lv[level];
-    const PyrLevelView J = next.lv[level];
-    const int pitch = I.pitch;
-    const int st_step = pitch;
-    const int st_off = (lane >> 3) * (pitch >> 2) + (lane & 7);
-    const float scale = 1.f / (float)(1 << level);
-    float px = __fmul_rn(pt.x, scale), py = __fmul_rn(pt.y, scale);
-    float nx, ny;
-    if (level == top) {
-      nx = px;
-      ny = py;
-    } else {
-      nx = __fmul_rn(outx, 2.f);
-      ny = __fmul_rn(outy, 2.f);
-    }
-    outx = nx;
-    outy = ny;
-
-    px = __fsub_rn(px, half_win);
-    py = __fsub_rn(py, half_win);
-    const int ipx = (int)floorf(px), ipy = (int)floorf(py);
-    if (ipx < -WIN || ipx >= I.w || ipy < -WIN || ipy >= I.h) {
-      if (level == 0) {
-        st = false;
-        errv = 0.f;
-      }
-      continue;
-    }
-    int iw00, iw01, iw10, iw11;
-    unsigned wt, wb;
-    lk_weights(__fsub_rn(px, (float)ipx), __fsub_rn(py, (float)ipy), wt, wb, iw00, iw01, iw10, iw11);
-    const unsigned wtI = wt, wbI = wb;
-    const size_t o0 = (size_t)(ipy + PAD_Y) * pitch + (ipx + PAD_L);
-
-    // ---- window extraction from the previous image + its Scharr derivative, all planes
-    int sA11 = 0, sA12 = 0, sA22 = 0, sC1 = 0, sC2 = 0;
-    uintptr_t staged[CN] = {0, 0, 0};
-#pragma unroll
-    for (int ch = 0; ch < CN; ch++) {
-      unsigned* tile = tile0 + ch * TILE_WORDS;
-      unsigned* tile_lane = tile_lane0 + ch * TILE_WORDS;
-      const unsigned sh = stage_patch(I.img + (size_t)ch * I.plane + o0, st_off, st_step, tile_lane, st_col_ok, st_last_ok);
-      {
-        const unsigned* dsrc = reinterpret_cast<const unsigned*>(I.deriv + (size_t)ch * I.plane + o0);
-        int r = 0, x = lane;
-        if (x >= PROWS) { x -= PROWS; r = 1; }
-#pragma unroll
-        for (int i = 0; i < 16; i++) {
-          if (r < PROWS) dtile[r * DS + x] = __ldg(dsrc + (size_t)r * pitch + x);
-          x += 32 - PROWS; r += 1;
-          if (x >= PROWS) { x -= PROWS; r += 1; }
-        }
-        __syncwarp();
-      }
-      int Iw[SEG];
-      seg_bilinear(tile, rowA, colA + sh, wt, wb, Iw);
-      lk_deriv_seg(dtile, rowA, colA, iw00, iw01, iw10, iw11, Iw, ixy[ch], sA11, sA12, sA22, sC1, sC2);
-      if (hasB) {
-        seg_bilinear(tile, rowB, colB + sh, wt, wb, Iw);
-        lk_deriv_seg(dtile, rowB, colB, iw00, iw01, iw10, iw11, Iw, ixy[ch] + SEG, sA11, sA12, sA22, sC1, sC2);
-      } else {
-#pragma unroll
-        for (int x = 0; x < SEG; x++) ixy[ch][SEG + x] = 0;
-      }
-    }
-    const float A11 = __fmul_rn(__ll2float_rn(warp_sum_exact(sA11)), FLT_SCALE);
-    const float A12 = __fmul_rn(__ll2float_rn(warp_sum_exact(sA12)), FLT_SCALE);
-    const float A22 = __fmul_rn(__ll2float_rn(warp_sum_exact(sA22)), FLT_SCALE);
-    const long long C1 = warp_sum_exact(sC1), C2 = warp_sum_exact(sC2);
-    float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
-    const float dd = __fsub_rn(A11, A22);
-    const float q = __fadd_rn(__fmul_rn(dd, dd), __fmul_rn(__fmul_rn(4.f, A12), A12));
-    const float min_eig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), __fsqrt_rn(q)), (float)(2 * WIN * WIN));
-    n_levels_done++;
-    if (min_eig < min_eig_thr || D < 1.1920929e-07f) {
-      if (level == 0) st = false;
-      continue;
-    }
-    D = __fdiv_rn(1.f, D);
-
-    nx = __fsub_rn(nx, half_win);
-    ny = __fsub_rn(ny, half_win);
-    float pdx = 0.f, pdy = 0.f;
-    for (int j = 0; j < max_iters; j++) {
-      const int inx = (int)floorf(nx), iny = (int)floorf(ny);
-      if (inx < -WIN || inx >= J.w || iny < -WIN || iny >= J.h) {
-        if (level == 0) st = false;
-        break;
-      }
-      lk_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), wt, wb, iw00, iw01, iw10, iw11);
-      const size_t oj = (size_t)(iny + PAD_Y) * pitch + (inx + PAD_L);
-      int sb1 = 0, sb2 = 0;
-#pragma unroll
-      for (int ch = 0; ch < CN; ch++) {
-        unsigned* tile = tile0 + ch * TILE_WORDS;
-        const unsigned sh = stage_patch(J.img + (size_t)ch * J.plane + oj, st_off, st_step, tile_lane0 + ch * TILE_WORDS,
-                                        st_col_ok, st_last_ok, &staged[ch]);
-        int jv[SEG];
-        seg_bilinear(tile, rowA, colA + sh, wt, wb, jv);
-#pragma unroll
-        for (int x = 0; x < SEG; x++) {
-          sb1 += jv[x] * (int)(short)(ixy[ch][x] & 0xffff);
-          sb2 += jv[x] * ((int)ixy[ch][x] >> 16);
-        }
-        if (hasB) {
-          seg_bilinear(tile, rowB, colB + sh, wt, wb, jv);
-#pragma unroll
-          for (int x = 0; x < SEG; x++) {
-            sb1 += jv[x] * (int)(short)(ixy[ch][SEG + x] & 0xffff);
-            sb2 += jv[x] * ((int)ixy[ch][SEG + x] >> 16);
-          }
-        }
-      }
-      n_iters_done++;
-      const float b1 = __fmul_rn(__ll2float_rn(warp_sum_exact(sb1) - C1), FLT_SCALE);
-      const float b2 = __fmul_rn(__ll2float_rn(warp_sum_exact(sb2) - C2), FLT_SCALE);
-      const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
-      const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
-      nx = __fadd_rn(nx, dx);
-      ny = __fadd_rn(ny, dy);
-      outx = __fadd_rn(nx, half_win);
-      outy = __fadd_rn(ny, half_win);
-      {
-        const float s2 = fmaf(dx, dx, dy * dy);
-        bool conv;
-        if (s2 < eps_lo) conv = true;
-        else if (s2 > eps_hi) conv = false;
-        else conv = __dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)) <= eps_sq;
-        if (conv) break;
-      }
-      if (j > 0 && (double)fabsf(__fadd_rn(dx, pdx)) < 0.01 && (double)fabsf(__fadd_rn(dy, pdy)) < 0.01) {
-        outx = __fsub_rn(outx, __fmul_rn(dx, 0.5f));
-        outy = __fsub_rn(outy, __fmul_rn(dy, 0.5f));
-        break;
-      }
-      pdx = dx;
-      pdy = dy;
-    }
-
-    // ---- err pass: mean |J - I| / 32 over the window and the channels at the final position
-    if (st && level == 0) {
-      const float fx = __fsub_rn(outx, half_win), fy = __fsub_rn(outy, half_win);
-      const int inx = (int)floorf(fx), iny = (int)floorf(fy);
-      if (inx < -WIN || inx >= J.w || iny < -WIN || iny >= J.h) {
-        st = false;
-      } else if (err) {
-        lk_weights(__fsub_rn(fx, (float)inx), __fsub_rn(fy, (float)iny), wt, wb, iw00, iw01, iw10, iw11);
-        const size_t oj = (size_t)(iny + PAD_Y) * pitch + (inx + PAD_L);
-        int se = 0;
-#pragma unroll
-        for (int ch = 0; ch < CN; ch++) {
-          int iv[2 * SEG], jv[SEG];
-          unsigned* tile = tile0 + ch * TILE_WORDS;
-          unsigned* tile_lane = tile_lane0 + ch * TILE_WORDS;
-          const unsigned shI = stage_patch(I.img + (size_t)ch * I.plane + o0, st_off, st_step, tile_lane, st_col_ok, st_last_ok);
-          seg_bilinear(tile, rowA, colA + shI, wtI, wbI, iv);
-          if (hasB) seg_bilinear(tile, rowB, colB + shI, wtI, wbI, iv + SEG);
-          const unsigned sh = stage_patch(J.img + (size_t)ch * J.plane + oj, st_off, st_step, tile_lane, st_col_ok, st_last_ok);
-          seg_bilinear(tile, rowA, colA + sh, wt, wb, jv);
-#pragma unroll
-          for (int x = 0; x < SEG; x++) se += abs(jv[x] - iv[x]);
-          if (hasB) {
-            seg_bilinear(tile, rowB, colB + sh, wt, wb, jv);
-#pragma unroll
-            for (int x = 0; x < SEG; x++) se += abs(jv[x] - iv[SEG + x]);
-          }
-        }
-        const int tot = __reduce_add_sync(0xffffffffu, se);  // <= 3*441*8160 fits int32
-        errv = __fmul_rn((float)tot, 1.f / (32 * WIN * CN * WIN));
-      }
-    }
-  }
-
-  if (lane == 0) {
-    next_pts[warp] = make_float2(outx, outy);
-    status[warp] = st ? 1 : 0;
-    if (err) err[warp] = errv;
-    if (work) {
-      atomicAdd(&work[0], (unsigned long long)n_levels_done);
-      atomicAdd(&work[1], (unsigned long long)n_iters_done);
+      atomicAdd(&work[2], (unsigned long long)n_slow_a);
+      atomicAdd(&work[3], (unsigned long long)n_slow_b);
     }
   }
 }
@@ -651,12 +548,17 @@ int lk_launch(vo_ctx* c, int slot_prev, int slot_next, const float2* d_prev, int
   eps *= eps;
   const int threads = 128;
   const int blocks = div_up(n * 32, threads);
+  static const bool use_v1 = getenv("VO_LK_V1") != nullptr;   // A/B baseline only (profiling)
   {
     LaunchScope ls(c, VO_K_LK);
     if (c->p.channels == 3)
-      lk_kernel_c3<<<blocks, threads, 0, c->stream>>>(pyr_view(c->pyr[slot_prev]), pyr_view(c->pyr[slot_next]), d_prev, n,
-                                                      d_next, d_status, d_err, max_iters, eps, (float)c->p.lk_min_eig,
-                                                      c->d_lk_work, c->n_dev);
+      v1::lk_kernel_c3<<<blocks, threads, 0, c->stream>>>(pyr_view(c->pyr[slot_prev]), pyr_view(c->pyr[slot_next]), d_prev, n,
+                                                          d_next, d_status, d_err, max_iters, eps, (float)c->p.lk_min_eig,
+                                                          c->d_lk_work, c->n_dev);
+    else if (use_v1)
+      v1::lk_kernel<<<blocks, threads, 0, c->stream>>>(pyr_view(c->pyr[slot_prev]), pyr_view(c->pyr[slot_next]), d_prev, n,
+                                                       d_next, d_status, d_err, max_iters, eps, (float)c->p.lk_min_eig,
+                                                       c->d_lk_work, c->n_dev);
     else
       lk_kernel<<<blocks, threads, 0, c->stream>>>(pyr_view(c->pyr[slot_prev]), pyr_view(c->pyr[slot_next]), d_prev, n,
                                                    d_next, d_status, d_err, max_iters, eps, (float)c->p.lk_min_eig,

@@ -375,9 +375,11 @@ int pyr_alloc(vo_ctx* c, Pyramid& p) {
     L.h = h;
     L.pitch = ((w + PAD_L + PAD_R + 127) / 128) * 128;
     L.plane = ((size_t)h + 2 * PAD_Y) * L.pitch;
-    VO_CUDA(cudaMalloc(&L.img, cn * L.plane));
+    const size_t guard = (size_t)GUARD_ROWS * L.pitch;
+    VO_CUDA(cudaMalloc(&L.img_alloc, cn * L.plane + 2 * guard));
+    L.img = L.img_alloc + guard;
     VO_CUDA(cudaMalloc(&L.deriv, cn * L.plane * sizeof(short2)));
-    VO_CUDA(cudaMemsetAsync(L.img, 0, cn * L.plane, c->stream));
+    VO_CUDA(cudaMemsetAsync(L.img_alloc, 0, cn * L.plane + 2 * guard, c->stream));
     VO_CUDA(cudaMemsetAsync(L.deriv, 0, cn * L.plane * sizeof(short2), c->stream));
     p.nlevels = l + 1;
   }
@@ -420,9 +422,10 @@ int pyr_alloc(vo_ctx* c, Pyramid& p) {
 
 void pyr_free(Pyramid& p) {
   for (int l = 0; l < p.nlevels; l++) {
-    cudaFree(p.lv[l].img);
+    cudaFree(p.lv[l].img_alloc);
     cudaFree(p.lv[l].deriv);
     p.lv[l].img = nullptr;
+    p.lv[l].img_alloc = nullptr;
     p.lv[l].deriv = nullptr;
   }
   p.nlevels = 0;

@@ -489,6 +489,12 @@ class VisualFrontEnd:
         check(self.lib.vo_lk_work(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def lk_slow_paths(self):
+        """(window extractions, iterations) that took the sequential float-chain path since vo_create."""
+        a, b = C.c_int64(), C.c_int64()
+        check(self.lib.vo_lk_slow_paths(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def measure_fp32_peak(self):
         t = C.c_double()
         check(self.lib.vo_measure_fp32_peak(self.h, C.byref(t)))
