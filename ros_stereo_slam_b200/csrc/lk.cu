@@ -53,7 +53,10 @@ constexpr int FB_WORDS = 2 * (4 * NB_SIMD + N_TAIL);   // 546: b1 | b2 terms
 constexpr int FA_WORDS = 4 * NA_SIMD + N_TAIL;         // 441: one A sum at a time
 constexpr int SCRATCH_WORDS = (TILE_WORDS + DTILE_WORDS) > FB_WORDS ? (TILE_WORDS + DTILE_WORDS) : FB_WORDS;  // 780
 constexpr int WARP_WORDS = TILE_WORDS + SCRATCH_WORDS;  // J tile | {I tile + derivative tile} U {chain terms}
-constexpr int LK_WARPS = 4;
+#ifndef LK_WARPS_N
+#define LK_WARPS_N 4
+#endif
+constexpr int LK_WARPS = LK_WARPS_N;
 constexpr int MARGIN = 3;
 constexpr int SAFE_LIMIT = 1 << 24;
 constexpr unsigned FULL = 0xffffffffu;
@@ -102,10 +105,8 @@ __device__ __forceinline__ void stage_tile(unsigned* tile_lane, const uint8_t* s
   }
 }
 
-// the 8 bilinear samples of the oct whose first source byte is byte `bo` of tile row `rowp` (and the row below)
-__device__ __forceinline__ void oct_sample(const unsigned* rowp, unsigned bo, unsigned wt, unsigned wb, int out[8]) {
-  const unsigned* p = rowp + (bo >> 2);
-  const unsigned sh = (bo & 3) * 8;
+// the 8 bilinear samples of the oct whose first source byte is `sh`/8 bytes into the tile word p[0] (and the row below)
+__device__ __forceinline__ void oct_sample(const unsigned* p, unsigned sh, unsigned wt, unsigned wb, int out[8]) {
   const unsigned a0 = p[0], a1 = p[1], a2 = p[2];
   const unsigned c0 = p[TS], c1 = p[TS + 1], c2 = p[TS + 2];
   const unsigned t0 = __funnelshift_r(a0, a1, sh), t1 = __funnelshift_r(a1, a2, sh), t2 = a2 >> sh;
@@ -173,10 +174,11 @@ __device__ __forceinline__ float run_chain(const float* f, int lane, int nsum, i
 
 }  // namespace
 
-__global__ void __launch_bounds__(LK_WARPS * 32)
+template <int MINB>
+__global__ void __launch_bounds__(LK_WARPS * 32, MINB * 4 / LK_WARPS)
 lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n, float2* __restrict__ next_pts,
-          uint8_t* __restrict__ status, float* __restrict__ err, int max_iters, double eps_sq, float min_eig_thr,
-          unsigned long long* __restrict__ work, const int* __restrict__ n_dev) {
+          uint8_t* __restrict__ status, float* __restrict__ err, int max_iters, double eps_sq, float eps_lo, float eps_hi,
+          float min_eig_thr, unsigned long long* __restrict__ work, const int* __restrict__ n_dev) {
   if (n_dev) n = min(n, *n_dev);
   __shared__ __align__(16) unsigned smem[LK_WARPS * WARP_WORDS];
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -190,15 +192,30 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
   const float2 pt = prev_pts[warp];
   const float half_win = (WIN - 1) * 0.5f;
   const float FLT_SCALE = 1.f / (1 << 20);
-  const float eps_lo = (float)(eps_sq * (1.0 - 1e-5)), eps_hi = (float)(eps_sq * (1.0 + 1e-5));
 
-  // this lane's two units (fixed for the whole kernel)
-  const int rowA = lane >> 1, colA = (lane & 1) * 8;
-  const bool isq_b = lane >= 10;               // slot B is a tail (or, lane 31, nothing)
-  const bool hasB = lane < 31;
-  const int isq = isq_b ? 1 : 0, notq = 1 - isq;
-  const int rowB = isq_b ? (hasB ? lane - 10 : 0) : 16 + (lane >> 1);
-  const int colB = isq_b ? 16 : (lane & 1) * 8;
+  // this lane's two units (fixed for the whole kernel).  The per-lane constants are packed into one register
+  // behind an opaque move: under register pressure ptxas otherwise re-derives them from %tid in every iteration.
+  unsigned cfg;
+  {
+    const int rA = lane >> 1, cA = (lane & 1) * 8;
+    const bool q = lane >= 10, hb = lane < 31;
+    const int rB = q ? (hb ? lane - 10 : 0) : 16 + (lane >> 1);
+    const int cB = q ? 16 : (lane & 1) * 8;
+    const unsigned v = (unsigned)(rA * TS + (cA >> 2)) | ((unsigned)(rB * TS + (cB >> 2)) << 8) | ((unsigned)rA << 16) |
+                       ((unsigned)rB << 21) | ((unsigned)(cA >> 3) << 26) | ((unsigned)(cB >> 3) << 27) | (q ? 1u << 29 : 0u) |
+                       (hb ? 1u << 30 : 0u);
+    asm volatile("mov.b32 %0, %1;" : "=r"(cfg) : "r"(v));
+  }
+#define offA ((int)(cfg & 0xffu))            /* word offsets of the two units in a tile */
+#define offB ((int)((cfg >> 8) & 0xffu))
+#define rowA ((int)((cfg >> 16) & 31u))
+#define rowB ((int)((cfg >> 21) & 31u))
+#define colA ((int)((cfg >> 26) & 1u) * 8)
+#define colB ((int)((cfg >> 27) & 3u) * 8)
+#define isq_b ((cfg & (1u << 29)) != 0)     /* slot B is a tail (or, lane 31, nothing) */
+#define hasB ((cfg & (1u << 30)) != 0)
+#define isq ((int)((cfg >> 29) & 1u))
+#define notq (1 - isq)
 
   float outx = 0.f, outy = 0.f;  // nextPts[ptidx] as OpenCV keeps it between levels
   bool st = true;
@@ -213,7 +230,7 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
     const PyrLevelView I = prev.lv[level];
     const PyrLevelView J = next.lv[level];
     const int pitch = I.pitch;
-    const float scale = 1.f / (float)(1 << level);
+    const float scale = __int_as_float((127 - level) << 23);   // 2^-level
     float px = __fmul_rn(pt.x, scale), py = __fmul_rn(pt.y, scale);
     float nx, ny;
     if (level == top) {
@@ -248,15 +265,20 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
     const int iX = ipx + PAD_L, iY = ipy + PAD_Y;
     {
       stage_tile(itile + st_lane, I.img + (size_t)iY * pitch + (iX & ~3), pitch, lane);
-      // derivative patch: 22 x 22 short2, row-coalesced (lane -> consecutive elements)
-      const unsigned* dsrc = reinterpret_cast<const unsigned*>(I.deriv + (size_t)iY * pitch + iX);
-      int r = 0, x = lane;
-      if (x >= DROWS) { x -= DROWS; r = 1; }
+      // derivative patch: 22 rows x 24 short2 (22 used), 8 lanes x 3 words per row, 4 rows per step
+      {
+        const unsigned* dsrc = reinterpret_cast<const unsigned*>(I.deriv + (size_t)iY * pitch + iX) + (lane >> 3) * pitch + (lane & 7);
+        unsigned* ddst = dtile + (lane >> 3) * DS + (lane & 7);
 #pragma unroll
-      for (int i = 0; i < 16; i++) {
-        if (r < DROWS) cp_async4(dtile + r * DS + x, dsrc + (size_t)r * pitch + x);
-        x += 32 - DROWS; r += 1;                       // advance by 32 elements of 22-wide rows
-        if (x >= DROWS) { x -= DROWS; r += 1; }
+        for (int i = 0; i < 6; i++) {
+          if (i < 5 || (lane >> 3) < DROWS - 20) {
+            cp_async4(ddst, dsrc);
+            cp_async4(ddst + 8, dsrc + 8);
+            cp_async4(ddst + 16, dsrc + 16);
+          }
+          dsrc += 4 * pitch;
+          ddst += 4 * DS;
+        }
       }
       cp_async_commit();
       const int inx = (int)floorf(nx), iny = (int)floorf(ny);
@@ -271,11 +293,11 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
     }
 
     // ---- window extraction from the previous image + its Scharr derivative
-    int cA11[5], cA12[5], cA22[5], cC1[5], cC2[5], cU[5];
+    int cA11[5], cA12[5], cA22[5], cC1[5], cC2[5];
     {
-      const unsigned bI = (unsigned)(iX & 3);
-      oct_sample(itile + rowA * TS, bI + colA, wt, wb, Iw);
-      oct_sample(itile + rowB * TS, bI + colB, wt, wb, Iw + 8);
+      const unsigned shI = (unsigned)(iX & 3) * 8;
+      oct_sample(itile + offA, shI, wt, wb, Iw);
+      oct_sample(itile + offB, shI, wt, wb, Iw + 8);
       oct_deriv(dtile + rowA * DS + colA, iw00, iw01, iw10, iw11, Ix, Iy);
       oct_deriv(dtile + rowB * DS + colB, iw00, iw01, iw10, iw11, Ix + 8, Iy + 8);
 #pragma unroll
@@ -283,8 +305,8 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
         const bool valid = hasB && (!isq_b || i < 5);
         if (!valid) { Iw[8 + i] = 0; Ix[8 + i] = 0; Iy[8 + i] = 0; }
       }
-      int a11[4] = {0, 0, 0, 0}, a12[4] = {0, 0, 0, 0}, a22[4] = {0, 0, 0, 0}, c1[4] = {0, 0, 0, 0}, c2[4] = {0, 0, 0, 0}, u[4] = {0, 0, 0, 0};
-      int b11[4] = {0, 0, 0, 0}, b12[4] = {0, 0, 0, 0}, b22[4] = {0, 0, 0, 0}, d1[4] = {0, 0, 0, 0}, d2[4] = {0, 0, 0, 0}, v[4] = {0, 0, 0, 0};
+      int a11[4] = {0, 0, 0, 0}, a12[4] = {0, 0, 0, 0}, a22[4] = {0, 0, 0, 0}, c1[4] = {0, 0, 0, 0}, c2[4] = {0, 0, 0, 0};
+      int b11[4] = {0, 0, 0, 0}, b12[4] = {0, 0, 0, 0}, b22[4] = {0, 0, 0, 0}, d1[4] = {0, 0, 0, 0}, d2[4] = {0, 0, 0, 0};
       int mA[8];
 #pragma unroll
       for (int i = 0; i < 8; i++) {
@@ -295,14 +317,12 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
         c1[k] += Iw[i] * Ix[i];
         c2[k] += Iw[i] * Iy[i];
         mA[i] = max(abs(Ix[i]), abs(Iy[i]));
-        u[k] += mA[i] * mA[i];
         b11[k] += Ix[8 + i] * Ix[8 + i];
         b12[k] += Ix[8 + i] * Iy[8 + i];
         b22[k] += Iy[8 + i] * Iy[8 + i];
         d1[k] += Iw[8 + i] * Ix[8 + i];
         d2[k] += Iw[8 + i] * Iy[8 + i];
         mB[i] = max(abs(Ix[8 + i]), abs(Iy[8 + i]));
-        v[k] += mB[i] * mB[i];
       }
 #pragma unroll
       for (int k = 0; k < 4; k++) mpA[k] = max(mA[k], mA[k + 4]);
@@ -311,7 +331,6 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
       lane_chains(a22, b22, notq, isq, cA22);
       lane_chains(c1, d1, notq, isq, cC1);
       lane_chains(c2, d2, notq, isq, cC2);
-      lane_chains(u, v, notq, isq, cU);
     }
     bool safeA = true;
 #pragma unroll
@@ -321,8 +340,9 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
       cA22[k] = __reduce_add_sync(FULL, cA22[k]);
       cC1[k] = __reduce_add_sync(FULL, cC1[k]);     // modulo 2^32: only differences with the per-iteration sums are used
       cC2[k] = __reduce_add_sync(FULL, cC2[k]);
-      // sum over the chain of max(Ix^2, Iy^2) >= every partial sum of the chain's terms (clamped per lane: no overflow)
-      safeA = safeA && (__reduce_add_sync(FULL, min(cU[k], SAFE_LIMIT)) < SAFE_LIMIT);
+      // the terms of the A11 / A22 chains are squares, so the chain totals (<= 105 * 4080^2 < 2^31) bound every
+      // partial sum; |Ix*Iy| <= max(Ix^2, Iy^2) covers the A12 chain
+      safeA = safeA && cA11[k] < SAFE_LIMIT && cA22[k] < SAFE_LIMIT;
     }
     float A11, A12, A22;
     if (safeA) {
@@ -353,6 +373,8 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
       A12 = res[1];
       A22 = res[2];
     }
+    const int C1tot = (int)((unsigned)cC1[0] + (unsigned)cC1[1] + (unsigned)cC1[2] + (unsigned)cC1[3] + (unsigned)cC1[4]);
+    const int C2tot = (int)((unsigned)cC2[0] + (unsigned)cC2[1] + (unsigned)cC2[2] + (unsigned)cC2[3] + (unsigned)cC2[4]);
     A11 = __fmul_rn(A11, FLT_SCALE);
     A12 = __fmul_rn(A12, FLT_SCALE);
     A22 = __fmul_rn(A22, FLT_SCALE);
@@ -389,14 +411,16 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
         bx = inx + PAD_L - tX0;
         by = MARGIN;
       }
-      const unsigned* rowpA = jtile + (by + rowA) * TS;
-      const unsigned* rowpB = jtile + (by + rowB) * TS;
+      const unsigned* jp = jtile + by * TS + (bx >> 2);
+      const unsigned shJ = (unsigned)(bx & 3) * 8;
       int c1[5], c2[5], cu[5];
+      int t1, t2, tu;
+      bool all_exact = true;
       {
         int a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0}, ua[4];
         int b1[4] = {0, 0, 0, 0}, b2[4] = {0, 0, 0, 0}, ub[4] = {0, 0, 0, 0};
         int jv[8];
-        oct_sample(rowpA, bx + colA, wt, wb, jv);
+        oct_sample(jp + offA, shJ, wt, wb, jv);
 #pragma unroll
         for (int i = 0; i < 8; i++) {
           a1[i & 3] += jv[i] * Ix[i];
@@ -404,27 +428,41 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
         }
 #pragma unroll
         for (int k = 0; k < 4; k++) ua[k] = (int)__sad(jv[k + 4], Iw[k + 4], __sad(jv[k], Iw[k], 0u)) * mpA[k];
-        oct_sample(rowpB, bx + colB, wt, wb, jv);
+        oct_sample(jp + offB, shJ, wt, wb, jv);
 #pragma unroll
         for (int i = 0; i < 8; i++) {
           b1[i & 3] += jv[i] * Ix[8 + i];
           b2[i & 3] += jv[i] * Iy[8 + i];
           ub[i & 3] += (int)__sad(jv[i], Iw[8 + i], 0u) * mB[i];
         }
-        lane_chains(a1, b1, notq, isq, c1);
-        lane_chains(a2, b2, notq, isq, c2);
-        lane_chains(ua, ub, notq, isq, cu);
+        t1 = ((a1[0] + a1[1]) + (a1[2] + a1[3])) + ((b1[0] + b1[1]) + (b1[2] + b1[3]));
+        t2 = ((a2[0] + a2[1]) + (a2[2] + a2[3])) + ((b2[0] + b2[1]) + (b2[2] + b2[3]));
+        tu = ((ua[0] + ua[1]) + (ua[2] + ua[3])) + ((ub[0] + ub[1]) + (ub[2] + ub[3]));   // < 2^30
+        if (__reduce_add_sync(FULL, min(tu, SAFE_LIMIT)) >= SAFE_LIMIT) {
+          lane_chains(a1, b1, notq, isq, c1);
+          lane_chains(a2, b2, notq, isq, c2);
+          lane_chains(ua, ub, notq, isq, cu);
+          all_exact = false;
+        }
       }
       n_iters_done++;
-      bool safe = true;
-#pragma unroll
-      for (int k = 0; k < 5; k++) {
-        c1[k] = (int)((unsigned)__reduce_add_sync(FULL, c1[k]) - (unsigned)cC1[k]);   // sum(diff*Ix) = sum(J*Ix) - sum(I*Ix), modulo 2^32
-        c2[k] = (int)((unsigned)__reduce_add_sync(FULL, c2[k]) - (unsigned)cC2[k]);
-        safe = safe && (__reduce_add_sync(FULL, min(cu[k], SAFE_LIMIT)) < SAFE_LIMIT);
-      }
       float b1f, b2f;
-      if (safe) {
+      bool safe = true;
+      // tier 1 (all_exact): the bound on the sum of |term| over the WHOLE window stays below 2^24 -- every chain
+      // and every step of the final combination is exact, the result is float(total)
+      if (all_exact) {
+        b1f = (float)(int)((unsigned)__reduce_add_sync(FULL, t1) - (unsigned)C1tot);
+        b2f = (float)(int)((unsigned)__reduce_add_sync(FULL, t2) - (unsigned)C2tot);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+          c1[k] = (int)((unsigned)__reduce_add_sync(FULL, c1[k]) - (unsigned)cC1[k]);   // sum(diff*Ix) = sum(J*Ix) - sum(I*Ix), modulo 2^32
+          c2[k] = (int)((unsigned)__reduce_add_sync(FULL, c2[k]) - (unsigned)cC2[k]);
+          safe = safe && (__reduce_add_sync(FULL, min(cu[k], SAFE_LIMIT)) < SAFE_LIMIT);
+        }
+      }
+      if (all_exact) {
+      } else if (safe) {
         b1f = chain_combine((float)c1[0], (float)c1[1], (float)c1[2], (float)c1[3], (float)c1[4]);
         b2f = chain_combine((float)c2[0], (float)c2[1], (float)c2[2], (float)c2[3], (float)c2[4]);
       } else {
@@ -432,14 +470,14 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
         n_slow_b++;
         int jv[8];
         __syncwarp();
-        oct_sample(rowpA, bx + colA, wt, wb, jv);
+        oct_sample(jp + offA, shJ, wt, wb, jv);
 #pragma unroll
         for (int k = 0; k < 4; k++) {
           const int dA = jv[k] - Iw[k], dB = jv[k + 4] - Iw[k + 4];
           fterms[k * NB_SIMD + 2 * rowA + (colA >> 3)] = __int2float_rn(dA * Ix[k] + dB * Ix[k + 4]);
           fterms[FB_WORDS / 2 + k * NB_SIMD + 2 * rowA + (colA >> 3)] = __int2float_rn(dA * Iy[k] + dB * Iy[k + 4]);
         }
-        oct_sample(rowpB, bx + colB, wt, wb, jv);
+        oct_sample(jp + offB, shJ, wt, wb, jv);
         if (!isq_b) {
 #pragma unroll
           for (int k = 0; k < 4; k++) {
@@ -480,7 +518,8 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
         else conv = __dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)) <= eps_sq;
         if (conv) break;
       }
-      if (j > 0 && (double)fabsf(__fadd_rn(dx, pdx)) < 0.01 && (double)fabsf(__fadd_rn(dy, pdy)) < 0.01) {
+      // OpenCV: std::abs(delta.x + prevDelta.x) < 0.01 in double; 0.01f is the largest float below 0.01
+      if (j > 0 && fabsf(__fadd_rn(dx, pdx)) <= 0.01f && fabsf(__fadd_rn(dy, pdy)) <= 0.01f) {
         outx = __fsub_rn(outx, __fmul_rn(dx, 0.5f));
         outy = __fsub_rn(outy, __fmul_rn(dy, 0.5f));
         break;
@@ -511,10 +550,12 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
         }
         unsigned se = 0;
         int jv[8];
-        oct_sample(jtile + (by + rowA) * TS, bx + colA, wt, wb, jv);
+        const unsigned* jp = jtile + by * TS + (bx >> 2);
+        const unsigned shJ = (unsigned)(bx & 3) * 8;
+        oct_sample(jp + offA, shJ, wt, wb, jv);
 #pragma unroll
         for (int i = 0; i < 8; i++) se = __sad(jv[i], Iw[i], se);
-        oct_sample(jtile + (by + rowB) * TS, bx + colB, wt, wb, jv);
+        oct_sample(jp + offB, shJ, wt, wb, jv);
 #pragma unroll
         for (int i = 0; i < 8; i++) {
           const bool valid = hasB && (!isq_b || i < 5);
@@ -539,6 +580,17 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
   }
 }
 
+#undef offA
+#undef offB
+#undef rowA
+#undef rowB
+#undef colA
+#undef colB
+#undef isq_b
+#undef hasB
+#undef isq
+#undef notq
+
 int lk_launch(vo_ctx* c, int slot_prev, int slot_next, const float2* d_prev, int n, float2* d_next, uint8_t* d_status,
               float* d_err) {
   if (n <= 0) return VO_OK;
@@ -546,9 +598,11 @@ int lk_launch(vo_ctx* c, int slot_prev, int slot_next, const float2* d_prev, int
   int max_iters = c->p.lk_max_iters < 0 ? 0 : (c->p.lk_max_iters > 100 ? 100 : c->p.lk_max_iters);
   double eps = c->p.lk_eps < 0 ? 0 : (c->p.lk_eps > 10 ? 10 : c->p.lk_eps);
   eps *= eps;
-  const int threads = 128;
+  const int threads = LK_WARPS * 32;
   const int blocks = div_up(n * 32, threads);
+  const float eps_lo = (float)(eps * (1.0 - 1e-5)), eps_hi = (float)(eps * (1.0 + 1e-5));
   static const bool use_v1 = getenv("VO_LK_V1") != nullptr;   // A/B baseline only (profiling)
+  static const int variant = getenv("VO_LK_MINB") ? atoi(getenv("VO_LK_MINB")) : 4;
   {
     LaunchScope ls(c, VO_K_LK);
     if (c->p.channels == 3)
@@ -559,10 +613,22 @@ int lk_launch(vo_ctx* c, int slot_prev, int slot_next, const float2* d_prev, int
       v1::lk_kernel<<<blocks, threads, 0, c->stream>>>(pyr_view(c->pyr[slot_prev]), pyr_view(c->pyr[slot_next]), d_prev, n,
                                                        d_next, d_status, d_err, max_iters, eps, (float)c->p.lk_min_eig,
                                                        c->d_lk_work, c->n_dev);
+    else if (variant == 4)
+      lk_kernel<4><<<blocks, threads, 0, c->stream>>>(pyr_view(c->pyr[slot_prev]), pyr_view(c->pyr[slot_next]), d_prev, n,
+                                                      d_next, d_status, d_err, max_iters, eps, eps_lo, eps_hi,
+                                                      (float)c->p.lk_min_eig, c->d_lk_work, c->n_dev);
+    else if (variant == 5)
+      lk_kernel<5><<<blocks, threads, 0, c->stream>>>(pyr_view(c->pyr[slot_prev]), pyr_view(c->pyr[slot_next]), d_prev, n,
+                                                      d_next, d_status, d_err, max_iters, eps, eps_lo, eps_hi, (float)c->p.lk_min_eig,
+                                                      c->d_lk_work, c->n_dev);
+    else if (variant == 2)
+      lk_kernel<2><<<blocks, threads, 0, c->stream>>>(pyr_view(c->pyr[slot_prev]), pyr_view(c->pyr[slot_next]), d_prev, n,
+                                                      d_next, d_status, d_err, max_iters, eps, eps_lo, eps_hi, (float)c->p.lk_min_eig,
+                                                      c->d_lk_work, c->n_dev);
     else
-      lk_kernel<<<blocks, threads, 0, c->stream>>>(pyr_view(c->pyr[slot_prev]), pyr_view(c->pyr[slot_next]), d_prev, n,
-                                                   d_next, d_status, d_err, max_iters, eps, (float)c->p.lk_min_eig,
-                                                   c->d_lk_work, c->n_dev);
+      lk_kernel<3><<<blocks, threads, 0, c->stream>>>(pyr_view(c->pyr[slot_prev]), pyr_view(c->pyr[slot_next]), d_prev, n,
+                                                      d_next, d_status, d_err, max_iters, eps, eps_lo, eps_hi, (float)c->p.lk_min_eig,
+                                                      c->d_lk_work, c->n_dev);
   }
   VO_CUDA(cudaGetLastError());
   return VO_OK;
