@@ -367,6 +367,9 @@ int vo_lk_work(vo_ctx* ctx, int64_t* point_levels, int64_t* iterations);
 int vo_lk_slow_paths(vo_ctx* ctx, int64_t* window_sums, int64_t* iterations);
 /* FP32 issue-rate microbenchmark (dependent FFMA chains on every SM): TFLOP/s achieved. */
 int vo_measure_fp32_peak(vo_ctx* ctx, double* tflops);
+/* INT32 issue-rate microbenchmark (dependent IMAD chains on every SM): Tops/s achieved (multiply-add = 2 ops);
+ * the denominator of the LK roofline (integer kernel). */
+int vo_measure_int32_peak(vo_ctx* ctx, double* tops);
 /* synthetic scene renderer (harness only; same scene as oracle/synth.py): renders frame
  * `frame` of scene `seed` into a DEVICE buffer of width*height bytes.  eye 0 = left, 1 = right. */
 int vo_synth_render_dev(vo_ctx* ctx, int seed, int frame, int eye, uint8_t* out_dev);

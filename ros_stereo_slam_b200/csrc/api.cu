@@ -1694,6 +1694,12 @@ int vo_lk_work(vo_ctx* c, int64_t* point_levels, int64_t* iterations) {
   return VO_OK;
 }
 
+int vo_measure_int32_peak(vo_ctx* c, double* tops) {
+  CHECK_CTX(c);
+  if (!tops) return VO_ERR_INVALID_ARG;
+  return int32_peak_launch(c, tops);
+}
+
 int vo_lk_slow_paths(vo_ctx* c, int64_t* window_sums, int64_t* iterations) {
   CHECK_CTX(c);
   int64_t a = 0, b = 0;

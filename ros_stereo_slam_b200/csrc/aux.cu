@@ -349,4 +349,46 @@ int fp32_peak_launch(vo_ctx* c, double* tflops) {
   return VO_OK;
 }
 
+// ------------------------------------------------------------------------------------ INT32 issue-rate peak
+// The LK kernel is integer work (IMAD, DP2A, shifts): its roofline denominator is the IMAD issue rate, measured
+// the same way as the FFMA one above (8 independent dependent chains per thread).
+__global__ void int32_peak_kernel(int* out, int iters) {
+  int a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const int m = 3 + (int)blockIdx.x, b = 7 + (int)threadIdx.x;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      a0 = a0 * m + b; a1 = a1 * m + b; a2 = a2 * m + b; a3 = a3 * m + b;
+      a4 = a4 * m + b; a5 = a5 * m + b; a6 = a6 * m + b; a7 = a7 * m + b;
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+int int32_peak_launch(vo_ctx* c, double* tops) {
+  const int blocks = c->sm_count * 8, threads = 256, iters = 4096;
+  int* d = nullptr;
+  VO_CUDA(cudaMalloc(&d, (size_t)blocks * threads * sizeof(int)));
+  cudaEvent_t a, b;
+  VO_CUDA(cudaEventCreate(&a));
+  VO_CUDA(cudaEventCreate(&b));
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; rep++) {
+    VO_CUDA(cudaEventRecord(a, c->stream));
+    c->launch_count++;
+    int32_peak_kernel<<<blocks, threads, 0, c->stream>>>(d, iters);
+    VO_CUDA(cudaEventRecord(b, c->stream));
+    VO_CUDA(cudaEventSynchronize(b));
+    float ms = 0;
+    VO_CUDA(cudaEventElapsedTime(&ms, a, b));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(d);
+  const double ops = (double)blocks * threads * iters * 16.0 * 8.0 * 2.0;
+  *tops = ops / (best * 1e-3) / 1e12;
+  return VO_OK;
+}
+
 }  // namespace vo

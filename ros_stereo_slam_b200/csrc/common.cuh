@@ -264,5 +264,6 @@ int anms_launch(vo_ctx* c, const float* h_xy, const float* h_resp, int n, int nu
                 int* n_keep);
 int synth_launch(vo_ctx* c, int seed, int frame, int eye, uint8_t* d_out);
 int fp32_peak_launch(vo_ctx* c, double* tflops);
+int int32_peak_launch(vo_ctx* c, double* tops);
 
 }  // namespace vo

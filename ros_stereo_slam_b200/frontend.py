@@ -500,6 +500,11 @@ class VisualFrontEnd:
         check(self.lib.vo_measure_fp32_peak(self.h, C.byref(t)))
         return t.value
 
+    def measure_int32_peak(self):
+        t = C.c_double()
+        check(self.lib.vo_measure_int32_peak(self.h, C.byref(t)))
+        return t.value
+
     def synth_render(self, seed, frame, eye):
         """Harness: render one synthetic frame on the GPU and return it as a numpy array."""
         w, h = self.params.width, self.params.height
