@@ -319,7 +319,11 @@ int vo_pnp_frame(vo_ctx* ctx, const uint8_t* ref_img, const uint8_t* cur_img, in
  * The hot-path part of the per-frame loop of visualSLAM::initSequence (src/VisualSLAM.cpp:31,
  * 58-64,70-74,93-97,120-151) with all state (reference image pyramid, reference 2-D/3-D points)
  * kept in HBM between frames; only the pose and the counters cross PCIe per frame.  Images may
- * be host pointers (copied H2D inside the call) or device pointers (is_device != 0). */
+ * be host pointers (copied H2D inside the call) or device pointers (is_device != 0).
+ * The stage entry points above that take images (vo_lk_track, vo_dense_lk_tracking, vo_stereo_triangulate,
+ * vo_insert_keyframe, vo_track_frame, vo_pnp_frame, vo_debug_pyramid_*) build their pyramids in the same
+ * slots: calling one of them ends the sequence (vo_seq_track returns VO_ERR_INVALID_ARG until the next
+ * vo_seq_init). */
 typedef struct vo_frame_result {
   double rvec[3], tvec[3];   /* solvePnPRansac output (world -> camera)        */
   double pose3x4[12];        /* [R|t] camera -> world, src/VisualSLAM.cpp:70-97 */

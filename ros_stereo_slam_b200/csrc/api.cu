@@ -64,6 +64,7 @@ static void prof_drain(vo_ctx* c) {
 }
 
 static void make_projections(const vo_params& p, double* P /*24*/);
+constexpr int F_CHUNK = 48, PNP_CHUNK = 32, F_CHUNK_TEMPORAL = 96;   // first-chunk sizes of the fused chains (see below)
 
 static int alloc_chain(vo_ctx* c) {
   const vo_params* p = &c->p;
@@ -97,7 +98,8 @@ static int alloc_chain(vo_ctx* c) {
   }
   VO_CUDA(cudaMalloc(&c->d_count, 16 * sizeof(int)));
   VO_CUDA(cudaMallocHost(&c->h_count, 16 * sizeof(int)));
-  VO_CUDA(cudaMalloc(&c->d_tile_state, 256 * sizeof(unsigned long long)));
+  const int n_tiles = std::max(256, (cap + 2047) / 2048 + 1);   // compaction tiles of 2048 flags (points.cu CP_TILE)
+  VO_CUDA(cudaMalloc(&c->d_tile_state, n_tiles * sizeof(unsigned long long)));
   {
     const unsigned one = 1;
     VO_CUDA(cudaMalloc(&c->d_epoch, sizeof(unsigned)));
@@ -107,11 +109,12 @@ static int alloc_chain(vo_ctx* c) {
     VO_CUDA(cudaMalloc(&c->d_Pst, sizeof(P)));
     VO_CUDA(cudaMemcpy(c->d_Pst, P, sizeof(P), cudaMemcpyHostToDevice));
   }
-  VO_CUDA(cudaMemsetAsync(c->d_tile_state, 0, 256 * sizeof(unsigned long long), c->stream));
+  VO_CUDA(cudaMemsetAsync(c->d_tile_state, 0, n_tiles * sizeof(unsigned long long), c->stream));
   VO_CUDA(cudaMallocHost(&c->h_pts, (size_t)cap * 8 * sizeof(float)));
   const int ch = p->max_hypotheses;
   c->cap_h = ch;
   VO_CUDA(cudaMalloc(&c->d_samples, (size_t)ch * 7 * sizeof(int32_t)));
+  VO_CUDA(cudaMemset(c->d_samples, 0, (size_t)ch * 7 * sizeof(int32_t)));   // never a stale index in front of a gather
   VO_CUDA(cudaMallocHost(&c->h_samples, (size_t)ch * 7 * sizeof(int32_t)));
   VO_CUDA(cudaMalloc(&c->d_models, (size_t)ch * 27 * sizeof(double)));
   VO_CUDA(cudaMalloc(&c->d_counts, (size_t)ch * 3 * sizeof(int32_t)));
@@ -266,6 +269,22 @@ int vo_create(const vo_params* p, vo_ctx** out) {
   if (p->width < 64 || p->height < 64 || p->max_points < 32 || p->max_hypotheses < 1 || p->lk_max_level < 0) {
     set_error("bad geometry/capacity");
     return VO_ERR_INVALID_ARG;
+  }
+  if (p->lk_max_level > MAX_LEVELS - 1) {
+    set_error("lk_max_level=%d: the pyramid holds at most %d levels (the reference uses maxLevel 3)", p->lk_max_level, MAX_LEVELS);
+    return VO_ERR_NOT_IMPLEMENTED;
+  }
+  {
+    // the single-synchronisation chains write their first chunk of hypotheses without asking the host: the
+    // buffers must hold it (the host-driven loops check their own sizes per call)
+    const int f_first = p->f_exhaustive ? std::min(std::max(p->f_max_iters, 1), 1024) : std::min(F_CHUNK_TEMPORAL, std::max(p->f_max_iters, 1));
+    const int it = std::max(p->pnp_iters, 1);
+    const int p_first = p->ransac_exhaustive ? (it <= 1024 ? it : 0) : std::min(it, PNP_CHUNK);
+    const int need = std::max(f_first, p_first);
+    if (p->max_hypotheses < need) {
+      set_error("max_hypotheses=%d is below the %d hypotheses the fused chains evaluate in their first chunk", p->max_hypotheses, need);
+      return VO_ERR_INVALID_ARG;
+    }
   }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
@@ -756,13 +775,11 @@ static int pnp_two_attempts(vo_ctx* c, int k, int* n_inl, int* attempt) {
 // the common case (adaptive stop not reached inside the first chunk, too few points, low inlier
 // count -> second PnP attempt, sampler overflow) is detected after that synchronisation and the
 // stage is redone on the host-driven path above, which handles every case.
-constexpr int F_CHUNK = 48, PNP_CHUNK = 32;
 // First-chunk size of the fused F-RANSAC.  OpenCV stops after niters = log(1-conf)/log(1-w^7) samples
 // (w = inlier ratio of the best model so far): 48 samples cover w >= 0.71, which the stereo pairs
 // (threshold 3 px) always reach; the temporal pairs (threshold 1 px) sit at w = 0.60..0.70 on ~13 % of
 // the bench frames (niters 49..143), and every miss costs a host-driven redo of F + PnP (~1 ms).
 // 96 samples cover w >= 0.64 for +14 us of scoring.
-constexpr int F_CHUNK_TEMPORAL = 96;
 static int fused_f_chunk(const vo_ctx* c, bool temporal) {
   if (c->p.f_exhaustive) return std::min(std::max(c->p.f_max_iters, 1), 1024);
   return std::min(temporal ? F_CHUNK_TEMPORAL : F_CHUNK, std::max(c->p.f_max_iters, 1));
@@ -986,6 +1003,7 @@ int vo_lk_track(vo_ctx* c, const uint8_t* prev, const uint8_t* next, int stride,
   if (!prev || !next || !prev_xy || !next_xy || !status || n < 0) return VO_ERR_INVALID_ARG;
   if (n > c->cap) return VO_ERR_CAPACITY;
   if (n == 0) return VO_OK;
+  c->seq_ref_slot = -1;   // the stage entry points reuse the sequence driver's pyramid slots: vo_seq_init again before vo_seq_track
   VO_TRY(load_image(c, 0, prev, stride, 0, true));
   VO_TRY(load_image(c, 1, next, stride, 0, false));
   VO_CUDA(cudaMemcpyAsync(c->d_xy_in, prev_xy, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
@@ -1034,6 +1052,7 @@ int vo_debug_pyramid_level(vo_ctx* c, const uint8_t* img, int stride, int level,
                            int* w, int* h) {
   CHECK_CTX(c);
   if (!img) return VO_ERR_INVALID_ARG;
+  c->seq_ref_slot = -1;   // the stage entry points reuse the sequence driver's pyramid slots: vo_seq_init again before vo_seq_track
   VO_TRY(load_image(c, 0, img, stride, 0, true));
   Pyramid& p = c->pyr[0];
   if (level < 0 || level >= p.nlevels) return VO_ERR_INVALID_ARG;
@@ -1047,6 +1066,7 @@ int vo_debug_pyramid_padded(vo_ctx* c, const uint8_t* img, int stride, int level
                             int16_t* out_deriv) {
   CHECK_CTX(c);
   if (!img || pad < 0 || pad > PAD_Y) return VO_ERR_INVALID_ARG;
+  c->seq_ref_slot = -1;   // the stage entry points reuse the sequence driver's pyramid slots: vo_seq_init again before vo_seq_track
   VO_TRY(load_image(c, 0, img, stride, 0, true));
   Pyramid& p = c->pyr[0];
   if (level < 0 || level >= p.nlevels) return VO_ERR_INVALID_ARG;
@@ -1269,6 +1289,7 @@ int vo_dense_lk_tracking(vo_ctx* c, const uint8_t* ref_img, const uint8_t* cur_i
   if (n > c->cap) return VO_ERR_CAPACITY;
   *m = 0;
   if (n == 0) return VO_OK;
+  c->seq_ref_slot = -1;   // the stage entry points reuse the sequence driver's pyramid slots: vo_seq_init again before vo_seq_track
   VO_TRY(load_image(c, 0, ref_img, stride, 0, true));
   VO_TRY(load_image(c, 1, cur_img, stride, 0, false));
   VO_CUDA(cudaMemcpyAsync(c->d_xy_in, ref_xy, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
@@ -1307,6 +1328,7 @@ static int stereo_host(vo_ctx* c, const uint8_t* left, const uint8_t* right, int
     return VO_ERR_INVALID_ARG;
   }
   *n = 0;
+  c->seq_ref_slot = -1;   // the stage entry points reuse the sequence driver's pyramid slots: vo_seq_init again before vo_seq_track
   VO_TRY(load_image(c, 0, left, stride, 0, true));
   VO_TRY(load_image(c, 2, right, stride, 0, false));
   int k = 0;
@@ -1347,6 +1369,7 @@ static int track_host(vo_ctx* c, const uint8_t* ref_img, const uint8_t* cur_img,
   if (n > c->cap) return VO_ERR_CAPACITY;
   *k = 0;
   if (n == 0) return VO_OK;
+  c->seq_ref_slot = -1;   // the stage entry points reuse the sequence driver's pyramid slots: vo_seq_init again before vo_seq_track
   VO_TRY(load_image(c, 0, ref_img, stride, 0, true));
   VO_TRY(load_image(c, 1, cur_img, stride, 0, false));
   VO_CUDA(cudaMemcpyAsync(c->d_xy_in, ref_xy, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
@@ -1388,6 +1411,7 @@ int vo_pnp_frame(vo_ctx* c, const uint8_t* ref_img, const uint8_t* cur_img, int 
   if (n == 0) {
     r = pnp_two_attempts(c, 0, &ni, &att);
   } else {
+    c->seq_ref_slot = -1;   // the stage entry points reuse the sequence driver's pyramid slots: vo_seq_init again before vo_seq_track
     VO_TRY(load_image(c, 0, ref_img, stride, 0, true));
     VO_TRY(load_image(c, 1, cur_img, stride, 0, false));
     VO_CUDA(cudaMemcpyAsync(c->d_xy_in, ref_xy, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, c->stream));

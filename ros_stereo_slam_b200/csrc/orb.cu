@@ -638,7 +638,8 @@ int vo_orb_detect_and_compute(vo_ctx* c, const uint8_t* img, int stride, int wid
   }
   // pinned scratch: pageable copies are staged by the driver at a few GB/s and serialise with the stream
   const int DESC_CAP = std::max(8192, 2 * nfeatures + 4096);     // keypoints the result staging holds
-  const size_t pin_img = (size_t)width * height, pin_xy = 2 * (size_t)o->cap * sizeof(float),
+  // every section starts 16-byte aligned (float views, aligned async copies)
+  const size_t pin_img = (((size_t)width * height) + 15) & ~(size_t)15, pin_xy = 2 * (size_t)o->cap * sizeof(float),
                pin_sc = (size_t)o->cap * sizeof(float), pin_desc = (size_t)DESC_CAP * (32 + sizeof(float)) + 64;
   if (pin_img + pin_xy + pin_sc + pin_desc > o->h_pin_bytes) {
     VO_CUDA(cudaStreamSynchronize(c->stream));
@@ -653,7 +654,7 @@ int vo_orb_detect_and_compute(vo_ctx* c, const uint8_t* img, int stride, int wid
   uint8_t* p_desc = o->h_pin + pin_img + pin_xy + pin_sc;                    // descriptors of all levels, appended
   float* p_ang = reinterpret_cast<float*>(p_desc + (size_t)DESC_CAP * 32);   // their angles
   for (int y = 0; y < height; y++) memcpy(o->h_pin + (size_t)y * width, img + (size_t)y * stride, width);
-  VO_CUDA(cudaMemcpyAsync(o->img, o->h_pin, pin_img, cudaMemcpyHostToDevice, c->stream));
+  VO_CUDA(cudaMemcpyAsync(o->img, o->h_pin, (size_t)width * height, cudaMemcpyHostToDevice, c->stream));
   VO_CUDA(cudaMemcpyAsync(o->coef, h_coef.data(), h_coef.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   const uint8_t* level[NL];
   level[0] = o->img;
@@ -768,6 +769,7 @@ int vo_orb_detect_and_compute(vo_ctx* c, const uint8_t* img, int stride, int wid
     if (n2 == 0) continue;
     if (pin_used + n2 > DESC_CAP) {
       set_error("vo_orb_detect_and_compute: more than %d keypoints", DESC_CAP);
+      cudaStreamSynchronize(c->stream);   // kernels and copies into the pinned staging of earlier levels are still in flight
       return VO_ERR_CAPACITY;
     }
     OrbLevelOut rec;

@@ -472,6 +472,9 @@ sample_kernel(const uint32_t* __restrict__ raw, int raw_len, const int* __restri
   if (t == 0) s_bad = 0;
   __syncthreads();
   if (n < M + 1) {   // too few points for this estimator's RANSAC path (host decides what to do)
+    // the solve kernels of a fused chain still run on `out` before the host sees the flag: give them indices they
+    // may dereference (index 0 of buffers that always hold >= 32 elements), never stale memory
+    for (int i = t; i < M * H; i += blockDim.x) out[i] = 0;
     if (t == 0) *flag = 2;
     return;
   }

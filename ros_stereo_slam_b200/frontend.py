@@ -60,6 +60,24 @@ class VisualFrontEnd:
         except Exception:
             pass
 
+    # ------------------------------------------------------------------ image marshalling
+    def _ctx_img(self, img):
+        """An image of the CONTEXT's geometry (the C ABI takes width/height/channels from vo_params, not from the
+        call): wrong shapes or channel counts would be read with the wrong layout, so they are rejected here."""
+        a = _u8img(img)
+        p = self.params
+        cn = 1 if a.ndim == 2 else a.shape[2]
+        if a.shape[0] != p.height or a.shape[1] != p.width or cn != p.channels:
+            raise ValueError("image is %s, the context was created for %d x %d x %d" % (a.shape, p.height, p.width, p.channels))
+        return a
+
+    def _ctx_pair(self, img_a, img_b):
+        """Two context-geometry images behind ONE row stride (the two-image entry points take a single stride)."""
+        a, b = self._ctx_img(img_a), self._ctx_img(img_b)
+        if a.strides[0] != b.strides[0]:
+            a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+        return a, b
+
     # ------------------------------------------------------------------ intrinsics helpers
     @property
     def K(self):
@@ -86,20 +104,17 @@ class VisualFrontEnd:
 
     def calcOpticalFlowPyrLK(self, prevImg, nextImg, prevPts):
         """cv::calcOpticalFlowPyrLK with the reference's defaults -> (nextPts, status, err)."""
-        a, b = _u8img(prevImg), _u8img(nextImg)
+        a, b = self._ctx_pair(prevImg, nextImg)
         pts = _f32(prevPts, 2)
         n = len(pts)
         nxt = np.zeros((n, 2), np.float32)
         st = np.zeros(n, np.uint8)
         err = np.zeros(n, np.float32)
-        if a.strides[0] != b.strides[0]:
-            b = np.ascontiguousarray(b)
-            a = np.ascontiguousarray(a)
         check(self.lib.vo_lk_track(self.h, _p(a), _p(b), a.strides[0], _p(pts), n, _p(nxt), _p(st), _p(err)))
         return nxt, st, err
 
     def pyramid_level(self, img, level):
-        a = _u8img(img)
+        a = self._ctx_img(img)
         w, h = C.c_int(), C.c_int()
         check(self.lib.vo_debug_pyramid_level(self.h, _p(a), a.strides[0], level, None, None, C.byref(w), C.byref(h)))
         cn = self.params.channels
@@ -345,7 +360,7 @@ class VisualFrontEnd:
     # ------------------------------------------------------------------ the reference's method boundaries
     def denseLKtracking(self, refImg, curImg, refPts):
         """visualSLAM::denseLKtracking (src/tracking.cpp:14-28) -> (refPts_kept, trackPts_kept)."""
-        a, b = _u8img(refImg), _u8img(curImg)
+        a, b = self._ctx_pair(refImg, curImg)
         pts = _f32(refPts, 2)
         n = len(pts)
         r = np.zeros((n, 2), np.float32)
@@ -366,7 +381,7 @@ class VisualFrontEnd:
 
     def stereoTriangulate(self, im1, im2):
         """visualSLAM::stereoTriangulate (src/triangulation.cpp:73-166) -> (ref3dPts, ref2dPts)."""
-        a, b = _u8img(im1), _u8img(im2)
+        a, b = self._ctx_pair(im1, im2)
         if a is None or b is None:
             print("NULL IMG")
             return None
@@ -379,7 +394,7 @@ class VisualFrontEnd:
     def insertKeyFrames(self, imL, imR, pose4dTransform):
         """visualSLAM::insertKeyFrames (src/keyFrameManagement.cpp:9-31)
         -> (ref3dCoords world, ftrPts, untransformed)."""
-        a, b = _u8img(imL), _u8img(imR)
+        a, b = self._ctx_pair(imL, imR)
         M = np.ascontiguousarray(pose4dTransform, np.float64).reshape(3, 4)
         xyz = np.zeros((self.cap, 3), np.float32)
         cam = np.zeros((self.cap, 3), np.float32)
@@ -392,7 +407,7 @@ class VisualFrontEnd:
     def PyrLKtrackFrame2Frame(self, refimg, curImg, refPts, ref3dpts):
         """visualSLAM::PyrLKtrackFrame2Frame (src/tracking.cpp:46-91)
         -> (refRetpts = tracked 2-D, ref3dretPts, inlierReferencePyrLKPts)."""
-        a, b = _u8img(refimg), _u8img(curImg)
+        a, b = self._ctx_pair(refimg, curImg)
         p2, p3 = _f32(refPts, 2), _f32(ref3dpts, 3)
         n = len(p2)
         t2 = np.zeros((n, 2), np.float32)
@@ -406,7 +421,7 @@ class VisualFrontEnd:
     def PerspectiveNpointEstimation(self, prevImg, curImg, ref2dPoints, ref3dPoints):
         """visualSLAM::PerspectiveNpointEstimation (src/keyFrameManagement.cpp:73-94)
         -> dict(trk2d, trk3d, ref2d_inl, rvec, tvec, inliers, attempt, shutdown)."""
-        a, b = _u8img(prevImg), _u8img(curImg)
+        a, b = self._ctx_pair(prevImg, curImg)
         p2, p3 = _f32(ref2dPoints, 2), _f32(ref3dPoints, 3)
         n = len(p2)
         t2 = np.zeros((n, 2), np.float32)
@@ -429,13 +444,13 @@ class VisualFrontEnd:
             check(self.lib.vo_seq_init(self.h, C.c_void_p(left), C.c_void_p(right), stride or self.params.width, 1,
                                        C.byref(n)))
         else:
-            a, b = _u8img(left), _u8img(right)
+            a, b = self._ctx_pair(left, right)
             check(self.lib.vo_seq_init(self.h, _p(a), _p(b), a.strides[0], 0, C.byref(n)))
         return n.value
 
     def seq_prefetch(self, left, right=None):
         """Announce the next frame's host images (vo_seq_prefetch); pass the SAME arrays to seq_track later."""
-        a, b = _u8img(left), _u8img(right)
+        a, b = self._ctx_pair(left, right)
         self._prefetched = (a, b)            # keep them alive until they are consumed
         check(self.lib.vo_seq_prefetch(self.h, _p(a), _p(b), a.strides[0]))
 
@@ -445,7 +460,7 @@ class VisualFrontEnd:
             r = self.lib.vo_seq_track(self.h, C.c_void_p(left), C.c_void_p(right) if right else None,
                                       stride or self.params.width, 1, int(force_keyframe), C.byref(res))
         else:
-            a, b = _u8img(left), _u8img(right)
+            a, b = self._ctx_pair(left, right)
             r = self.lib.vo_seq_track(self.h, _p(a), _p(b), a.strides[0], 0, int(force_keyframe), C.byref(res))
         check(r, (_lib.VO_OK, _lib.VO_ERR_LOW_INLIERS))
         return res, r

@@ -605,3 +605,63 @@ def test_gpu_renderer_matches_oracle_renderer(fe):
     print("renderer agreement (identical, within 1 level, max):", stats)
     for ident, near, _mx in stats:
         assert ident >= 0.95 and near >= 0.999, stats
+
+
+def test_textureless_first_frame_on_a_fresh_context():
+    """with fewer LK survivors than a minimal sample the device-side sampler leaves its output to the
+    solve kernels of the fused chain -- on a FRESH context (nothing ever written to the sample buffer) that must
+    not turn into a wild gather.  A constant image has no trackable point at all."""
+    flat = np.full((376, 1241), 90, np.uint8)
+    for _ in range(2):
+        f = make_frontend()
+        xyz, ref2d = f.stereoTriangulate(flat, flat)
+        assert len(xyz) == 0 and len(ref2d) == 0
+        assert f.seq_init(flat, flat) == 0
+        f.close()
+    f = make_frontend()
+    pts = glue.dense_keypoint_extractor(376, 1241, 30)
+    with pytest.raises(Exception) as e:
+        f.PerspectiveNpointEstimation(flat, flat, pts, np.ones((len(pts), 3), np.float32))
+    assert "LOW_INLIERS" in str(e.value) or "TOO_FEW" in str(e.value) or "NO_MODEL" in str(e.value)
+    # the context is still healthy afterwards
+    g = golden()
+    xyz, ref2d = f.stereoTriangulate(g["L0"], g["R0"])
+    assert len(xyz) > 300
+    f.close()
+
+
+def test_create_rejects_capacities_the_fused_chains_would_overrun():
+    with pytest.raises(Exception):
+        make_frontend(max_hypotheses=32)                       # below the 96-sample first chunk of the temporal F-RANSAC
+    with pytest.raises(Exception):
+        make_frontend(max_hypotheses=512, pnp_iters=1024, ransac_exhaustive=1)
+    with pytest.raises(Exception):
+        make_frontend(lk_max_level=4)                          # would silently be clamped to 4 levels
+    f = make_frontend(max_hypotheses=96, max_points=600000)     # more compaction tiles than the old fixed table held
+    f.close()
+
+
+def test_stage_call_ends_the_sequence(G):
+    """The stage entry points build their pyramids in the sequence driver's slots: a sequence must be re-initialised."""
+    f = make_frontend()
+    assert f.seq_init(G["L0"], G["R0"]) > 300
+    f.calcOpticalFlowPyrLK(G["L0"], G["L1"], glue.dense_keypoint_extractor(376, 1241, 30))
+    with pytest.raises(Exception):
+        f.seq_track(G["L1"], G["R0"])
+    assert f.seq_init(G["L0"], G["R0"]) > 300
+    res, code = f.seq_track(G["L1"], G["R0"])
+    assert res.n_inliers > 100
+    f.close()
+
+
+def test_wrapper_rejects_images_of_another_geometry(fe, G):
+    with pytest.raises(ValueError):
+        fe.calcOpticalFlowPyrLK(G["L0"][:300], G["L1"][:300], np.zeros((4, 2), np.float32))
+    with pytest.raises(ValueError):
+        fe.stereoTriangulate(cv2.cvtColor(G["L0"], cv2.COLOR_GRAY2BGR), cv2.cvtColor(G["R0"], cv2.COLOR_GRAY2BGR))
+    # a row-strided left view next to a contiguous right image: both are brought to one stride
+    wide = np.zeros((376, 1300), np.uint8)
+    wide[:, :1241] = G["L0"]
+    p, st, _ = fe.calcOpticalFlowPyrLK(wide[:, :1241], G["L1"], glue.dense_keypoint_extractor(376, 1241, 30))
+    p0, st0, _ = fe.calcOpticalFlowPyrLK(G["L0"], G["L1"], glue.dense_keypoint_extractor(376, 1241, 30))
+    assert np.array_equal(st, st0) and np.array_equal(p, p0)
