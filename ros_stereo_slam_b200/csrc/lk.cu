@@ -580,6 +580,564 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
   }
 }
 
+// ------------------------------------------------------------------------------------ 3-channel (BGR) LK
+// cv::calcOpticalFlowPyrLK on 3-channel images -- what the reference actually feeds it (imread's default BGR
+// output, reference src/keyFrameManagement.cpp:52,64).  OpenCV walks a window row as 63 INTERLEAVED samples
+// x = 3*col + ch in steps of 8: the SIMD part is x < 56 (sample x -> float lane x & 3, pairs (x, x + 4) inside a
+// step of 8), the scalar chain takes x = 56..62 (column 18 channel 2, columns 19 and 20).  With the planar storage
+// of common.cuh that is THREE WARPS per keypoint, one per plane, each running the 1-channel mapping on its plane
+// (same octs / tails, same staging, same DP2A samples); x & 3 == (ch - col) & 3, so in an oct (col0 = 0 or 8) the
+// sample i of plane ch belongs to chain (ch - i) & 3 -- the per-lane accumulators are the 1-channel ones, only
+// their chain index is rotated by the plane.  Of a tail (columns 16..20) the samples with 3*i + ch < 8 are SIMD
+// samples (i = 0, 1 and, for ch < 2, i = 2), the rest belong to the scalar chain.  The three warps exchange their
+// per-chain integer sums through shared memory (one __syncthreads per exchange, double-buffered) and then all run
+// the same float arithmetic on the same numbers, so they take every branch together.  The sequential fall-back
+// (a partial sum may reach 2^24) gathers the float terms of all planes in one shared buffer and lanes 0..4 of
+// warp 0 add them up in OpenCV's interleaved order.  minEig is normalised by the window AREA (no channel
+// factor) and err by area * cn, as in OpenCV.
+namespace {
+constexpr int C3 = 3;
+constexpr int XROW = WIN * C3;              // 63 interleaved samples per window row
+constexpr int XSIMD = (XROW / 8) * 8;       // 56
+constexpr int PBUF_WORDS = WIN * XROW;      // 1323: one value per window sample, OpenCV's interleaved order
+constexpr int XCH_WORDS = 2 * C3 * 32;      // exchange area: [phase][plane][32]
+constexpr int PB_REGION = (C3 * PBUF_WORDS > C3 * SCRATCH_WORDS) ? C3 * PBUF_WORDS : C3 * SCRATCH_WORDS;   // 3969: three term
+                                            // buffers (one per sum), aliasing the three scratch regions
+
+// sum over the three planes of NV warp-uniform values; pos[k] = slot of value k (a rotation of the chain index)
+template <int NV>
+__device__ __forceinline__ void plane_combine(int* xch, unsigned& phase, int ch, int lane, int v[NV], const int pos[NV]) {
+  int* buf = xch + (phase & 1u) * (C3 * 32);
+  phase++;
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; k++) buf[ch * 32 + pos[k]] = v[k];
+  }
+  __syncthreads();
+  int mine = 0;
+  if (lane < NV) mine = (int)((unsigned)buf[lane] + (unsigned)buf[32 + lane] + (unsigned)buf[64 + lane]);
+#pragma unroll
+  for (int k = 0; k < NV; k++) v[k] = __shfl_sync(FULL, mine, k);
+}
+
+// per-lane chain totals in the LOCAL index space q = i & 3 (true chain = (ch - q) & 3): slot A is an oct, slot B an
+// oct (b[i] of all 8 samples) or a tail whose first `nsimd` samples are SIMD samples and the others scalar
+__device__ __forceinline__ void lane_chains3(const int a[4], const int b[8], bool tail, int nsimd, int c[5]) {
+  int sc = 0;
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const bool simd_lo = !tail || q < nsimd;
+    c[q] = a[q] + (simd_lo ? b[q] : 0) + (tail ? 0 : b[q + 4]);
+    sc += (tail && !simd_lo ? b[q] : 0) + (tail ? b[q + 4] : 0);
+  }
+  c[4] = sc;
+}
+
+// One chain of a b sum over the interleaved int32 products P[row][x] of all planes, evaluated by ONE WARP:
+// element j = (row r, step t): SIMD chain k < 4 -> P[r][8t+k] + P[r][8t+k+4] (OpenCV's int32 pair), scalar chain ->
+// P[r][56+t].  Lane r < 21 walks its row; a warp scan gives the exact prefix in front of every row.  If no partial
+// sum and no element reaches 2^24 the float chain is exact and equals the total; otherwise lane 0 adds the float
+// terms one by one in OpenCV's order.  (int32 wrap-around cannot hide a violation: elements are < 2^27, so a
+// prefix cannot get from (-2^24, 2^24) to an aliasing value without passing through a flagged one.)
+__device__ __forceinline__ float chain_b3(const int* P, int k, int lane) {
+  int e[7];
+  int run = 0;
+  const int* row = P + (lane < WIN ? lane : 0) * XROW;
+#pragma unroll
+  for (int t = 0; t < 7; t++) {
+    e[t] = k < 4 ? row[8 * t + k] + row[8 * t + k + 4] : row[XSIMD + t];
+    if (lane >= WIN) e[t] = 0;
+    run += e[t];
+  }
+  int incl = run;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int v = __shfl_up_sync(FULL, incl, d);
+    if (lane >= d) incl += v;
+  }
+  int p = incl - run;      // exact prefix in front of this row
+  int worst = 0;
+#pragma unroll
+  for (int t = 0; t < 7; t++) {
+    p += e[t];
+    worst = max(worst, max(abs(p), abs(e[t])));
+  }
+  const int total = __shfl_sync(FULL, incl, 31);
+  const bool exact = __reduce_max_sync(FULL, min(worst, SAFE_LIMIT)) < SAFE_LIMIT;
+  float acc = (float)total;
+  if (!exact) {
+    acc = 0.f;
+    if (lane == 0) {
+      for (int r = 0; r < WIN; r++)
+        for (int t = 0; t < 7; t++) {
+          const int* q = P + r * XROW;
+          acc = __fadd_rn(acc, __int2float_rn(k < 4 ? q[8 * t + k] + q[8 * t + k + 4] : q[XSIMD + t]));
+        }
+    }
+    acc = __shfl_sync(FULL, acc, 0);
+  }
+  return acc;
+}
+}  // namespace
+
+__global__ void __launch_bounds__(C3 * 32, 5)
+lk_kernel_c3(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n, float2* __restrict__ next_pts,
+             uint8_t* __restrict__ status, float* __restrict__ err, int max_iters, double eps_sq, float eps_lo, float eps_hi,
+             float min_eig_thr, unsigned long long* __restrict__ work, const int* __restrict__ n_dev) {
+  if (n_dev) n = min(n, *n_dev);
+  __shared__ __align__(16) unsigned smem[C3 * TILE_WORDS + PB_REGION + XCH_WORDS];
+  const int point = blockIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int ch = threadIdx.x >> 5;            // this warp's plane
+  if (point >= n) return;
+  unsigned* jtile = smem + ch * TILE_WORDS;
+  unsigned* itile = smem + C3 * TILE_WORDS + ch * SCRATCH_WORDS;
+  unsigned* dtile = itile + TILE_WORDS;
+  unsigned* pbuf = smem + C3 * TILE_WORDS;     // all planes' terms (slow paths; the scratch regions are dead by then)
+  int* xch = reinterpret_cast<int*>(smem + C3 * TILE_WORDS + PB_REGION);
+  unsigned phase = 0;
+  const int st_lane = (lane >> 3) * TS + (lane & 7);
+  const float2 pt = prev_pts[point];
+  const float half_win = (WIN - 1) * 0.5f;
+  const float FLT_SCALE = 1.f / (1 << 20);
+
+  unsigned cfg;
+  {
+    const int rA = lane >> 1, cA = (lane & 1) * 8;
+    const bool q = lane >= 10, hb = lane < 31;
+    const int rB = q ? (hb ? lane - 10 : 0) : 16 + (lane >> 1);
+    const int cB = q ? 16 : (lane & 1) * 8;
+    const unsigned v = (unsigned)(rA * TS + (cA >> 2)) | ((unsigned)(rB * TS + (cB >> 2)) << 8) | ((unsigned)rA << 16) |
+                       ((unsigned)rB << 21) | ((unsigned)(cA >> 3) << 26) | ((unsigned)(cB >> 3) << 27) | (q ? 1u << 29 : 0u) |
+                       (hb ? 1u << 30 : 0u);
+    asm volatile("mov.b32 %0, %1;" : "=r"(cfg) : "r"(v));
+  }
+  const int nsimd = ch == 2 ? 2 : 3;          // SIMD samples of a tail in this plane (3*i + ch < 8)
+  // slot of the local chain q in the exchange rows: the true chain index
+  int rot[4];
+#pragma unroll
+  for (int q = 0; q < 4; q++) rot[q] = (ch - q) & 3;
+
+  float outx = 0.f, outy = 0.f;
+  bool st = true;
+  float errv = 0.f;
+  unsigned int n_levels_done = 0, n_iters_done = 0, n_slow_a = 0, n_slow_b = 0;
+
+  int Iw[16], Ix[16], Iy[16];
+  int mpA[4], mB[8];
+
+  const int top = prev.nlevels - 1;
+  for (int level = top; level >= 0; level--) {
+    const PyrLevelView I = prev.lv[level];
+    const PyrLevelView J = next.lv[level];
+    const int pitch = I.pitch;
+    const uint8_t* Iimg = I.img + (size_t)ch * I.plane;
+    const short2* Ider = I.deriv + (size_t)ch * I.plane;
+    const uint8_t* Jimg = J.img + (size_t)ch * J.plane;
+    const float scale = __int_as_float((127 - level) << 23);   // 2^-level
+    float px = __fmul_rn(pt.x, scale), py = __fmul_rn(pt.y, scale);
+    float nx, ny;
+    if (level == top) {
+      nx = px;
+      ny = py;
+    } else {
+      nx = __fmul_rn(outx, 2.f);
+      ny = __fmul_rn(outy, 2.f);
+    }
+    outx = nx;
+    outy = ny;
+
+    px = __fsub_rn(px, half_win);
+    py = __fsub_rn(py, half_win);
+    const int ipx = (int)floorf(px), ipy = (int)floorf(py);
+    if (ipx < -WIN || ipx >= I.w || ipy < -WIN || ipy >= I.h) {
+      if (level == 0) {
+        st = false;
+        errv = 0.f;
+      }
+      continue;
+    }
+    int iw00, iw01, iw10, iw11;
+    unsigned wt, wb;
+    lk_weights(__fsub_rn(px, (float)ipx), __fsub_rn(py, (float)ipy), wt, wb, iw00, iw01, iw10, iw11);
+
+    nx = __fsub_rn(nx, half_win);
+    ny = __fsub_rn(ny, half_win);
+    int tX0 = -(1 << 20), tY0 = -(1 << 20);
+    __syncthreads();                             // every plane is done with the tiles / term buffer of the previous level
+    const int iX = ipx + PAD_L, iY = ipy + PAD_Y;
+    {
+      stage_tile(itile + st_lane, Iimg + (size_t)iY * pitch + (iX & ~3), pitch, lane);
+      {
+        const unsigned* dsrc = reinterpret_cast<const unsigned*>(Ider + (size_t)iY * pitch + iX) + (lane >> 3) * pitch + (lane & 7);
+        unsigned* ddst = dtile + (lane >> 3) * DS + (lane & 7);
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+          if (i < 5 || (lane >> 3) < DROWS - 20) {
+            cp_async4(ddst, dsrc);
+            cp_async4(ddst + 8, dsrc + 8);
+            cp_async4(ddst + 16, dsrc + 16);
+          }
+          dsrc += 4 * pitch;
+          ddst += 4 * DS;
+        }
+      }
+      cp_async_commit();
+      const int inx = (int)floorf(nx), iny = (int)floorf(ny);
+      if (!(inx < -WIN || inx >= J.w || iny < -WIN || iny >= J.h)) {
+        tX0 = (inx + PAD_L - MARGIN) & ~3;
+        tY0 = iny + PAD_Y - MARGIN;
+        stage_tile(jtile + st_lane, Jimg + (size_t)tY0 * pitch + tX0, pitch, lane);
+      }
+      cp_async_commit();
+      cp_async_wait<1>();
+      __syncwarp();
+    }
+
+    // ---- window extraction of this plane
+    int sums[25];     // A11 | A12 | A22 | C1 | C2, five chains each (local chain order until the exchange)
+    {
+      const unsigned shI = (unsigned)(iX & 3) * 8;
+      oct_sample(itile + offA, shI, wt, wb, Iw);
+      oct_sample(itile + offB, shI, wt, wb, Iw + 8);
+      oct_deriv(dtile + rowA * DS + colA, iw00, iw01, iw10, iw11, Ix, Iy);
+      oct_deriv(dtile + rowB * DS + colB, iw00, iw01, iw10, iw11, Ix + 8, Iy + 8);
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const bool valid = hasB && (!isq_b || i < 5);
+        if (!valid) { Iw[8 + i] = 0; Ix[8 + i] = 0; Iy[8 + i] = 0; }
+      }
+      int a11[4] = {0, 0, 0, 0}, a12[4] = {0, 0, 0, 0}, a22[4] = {0, 0, 0, 0}, c1[4] = {0, 0, 0, 0}, c2[4] = {0, 0, 0, 0};
+      int b11[8], b12[8], b22[8], d1[8], d2[8];
+      int mA[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const int k = i & 3;
+        a11[k] += Ix[i] * Ix[i];
+        a12[k] += Ix[i] * Iy[i];
+        a22[k] += Iy[i] * Iy[i];
+        c1[k] += Iw[i] * Ix[i];
+        c2[k] += Iw[i] * Iy[i];
+        mA[i] = max(abs(Ix[i]), abs(Iy[i]));
+        b11[i] = Ix[8 + i] * Ix[8 + i];
+        b12[i] = Ix[8 + i] * Iy[8 + i];
+        b22[i] = Iy[8 + i] * Iy[8 + i];
+        d1[i] = Iw[8 + i] * Ix[8 + i];
+        d2[i] = Iw[8 + i] * Iy[8 + i];
+        mB[i] = max(abs(Ix[8 + i]), abs(Iy[8 + i]));
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) mpA[k] = max(mA[k], mA[k + 4]);
+      lane_chains3(a11, b11, isq_b, nsimd, sums + 0);
+      lane_chains3(a12, b12, isq_b, nsimd, sums + 5);
+      lane_chains3(a22, b22, isq_b, nsimd, sums + 10);
+      lane_chains3(c1, d1, isq_b, nsimd, sums + 15);
+      lane_chains3(c2, d2, isq_b, nsimd, sums + 20);
+    }
+    int pos25[25];
+#pragma unroll
+    for (int s = 0; s < 5; s++) {
+#pragma unroll
+      for (int q = 0; q < 4; q++) pos25[s * 5 + q] = s * 5 + rot[q];
+      pos25[s * 5 + 4] = s * 5 + 4;
+    }
+#pragma unroll
+    for (int k = 0; k < 25; k++) sums[k] = __reduce_add_sync(FULL, sums[k]);
+    // The A11 / A22 chain totals are sums of squares and bound every partial sum of their chain (and of the A12
+    // chain: |Ix*Iy| <= max(Ix^2, Iy^2)).  One plane's part (<= 98 * 4080^2 < 2^31) cannot wrap, the sum over the
+    // planes could: clamp the parts at 2^24 -- a clamped value only ever feeds the "unsafe" decision.
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+      sums[k] = min(sums[k], SAFE_LIMIT);
+      sums[10 + k] = min(sums[10 + k], SAFE_LIMIT);
+    }
+    plane_combine<25>(xch, phase, ch, lane, sums, pos25);      // now in TRUE chain order, summed over the planes
+    const int* cA11 = sums + 0;
+    const int* cA12 = sums + 5;
+    const int* cA22 = sums + 10;
+    const int* cC1 = sums + 15;
+    const int* cC2 = sums + 20;
+    bool safeA = true;
+#pragma unroll
+    for (int k = 0; k < 5; k++) safeA = safeA && cA11[k] < SAFE_LIMIT && cA22[k] < SAFE_LIMIT;
+    float A11, A12, A22;
+    if (safeA) {
+      A11 = chain_combine((float)cA11[0], (float)cA11[1], (float)cA11[2], (float)cA11[3], (float)cA11[4]);
+      A12 = chain_combine((float)cA12[0], (float)cA12[1], (float)cA12[2], (float)cA12[3], (float)cA12[4]);
+      A22 = chain_combine((float)cA22[0], (float)cA22[1], (float)cA22[2], (float)cA22[3], (float)cA22[4]);
+    } else {
+      // slow path: the float terms of all planes in OpenCV's interleaved order, one buffer per A sum; warp s adds
+      // up sum s (lanes 0..4 = its five chains)
+      if (ch == 0) n_slow_a++;
+      __syncthreads();      // tiles consumed by every plane
+#pragma unroll
+      for (int s = 0; s < 3; s++) {
+        float* ft = reinterpret_cast<float*>(pbuf) + s * PBUF_WORDS;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const int pa = s == 0 ? Ix[i] * Ix[i] : (s == 1 ? Ix[i] * Iy[i] : Iy[i] * Iy[i]);
+          ft[rowA * XROW + 3 * (colA + i) + ch] = __int2float_rn(pa);
+          const int pb = s == 0 ? Ix[8 + i] * Ix[8 + i] : (s == 1 ? Ix[8 + i] * Iy[8 + i] : Iy[8 + i] * Iy[8 + i]);
+          if (hasB && (!isq_b || i < 5)) ft[rowB * XROW + 3 * (colB + i) + ch] = __int2float_rn(pb);
+        }
+      }
+      __syncthreads();
+      {
+        const float* ft = reinterpret_cast<const float*>(pbuf) + ch * PBUF_WORDS;
+        float acc = 0.f;
+        if (lane < 4) {
+          for (int r = 0; r < WIN; r++)
+            for (int x = lane; x < XSIMD; x += 4) acc = __fadd_rn(acc, ft[r * XROW + x]);
+        } else if (lane == 4) {
+          for (int r = 0; r < WIN; r++)
+            for (int x = XSIMD; x < XROW; x++) acc = __fadd_rn(acc, ft[r * XROW + x]);
+        }
+        if (lane < 5) xch[(phase & 1u) * (C3 * 32) + ch * 32 + lane] = __float_as_int(acc);
+      }
+      __syncthreads();
+      float res[3];
+      {
+        const int* rb = xch + (phase & 1u) * (C3 * 32);
+        phase++;
+#pragma unroll
+        for (int s = 0; s < 3; s++)
+          res[s] = chain_combine(__int_as_float(rb[s * 32 + 0]), __int_as_float(rb[s * 32 + 1]), __int_as_float(rb[s * 32 + 2]),
+                                 __int_as_float(rb[s * 32 + 3]), __int_as_float(rb[s * 32 + 4]));
+      }
+      A11 = res[0];
+      A12 = res[1];
+      A22 = res[2];
+    }
+    const int C1tot = (int)((unsigned)cC1[0] + (unsigned)cC1[1] + (unsigned)cC1[2] + (unsigned)cC1[3] + (unsigned)cC1[4]);
+    const int C2tot = (int)((unsigned)cC2[0] + (unsigned)cC2[1] + (unsigned)cC2[2] + (unsigned)cC2[3] + (unsigned)cC2[4]);
+    int kC1[5], kC2[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) { kC1[k] = cC1[k]; kC2[k] = cC2[k]; }
+    A11 = __fmul_rn(A11, FLT_SCALE);
+    A12 = __fmul_rn(A12, FLT_SCALE);
+    A22 = __fmul_rn(A22, FLT_SCALE);
+    float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+    const float dd = __fsub_rn(A11, A22);
+    const float q = __fadd_rn(__fmul_rn(dd, dd), __fmul_rn(__fmul_rn(4.f, A12), A12));
+    const float min_eig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), __fsqrt_rn(q)), (float)(2 * WIN * WIN));
+    n_levels_done++;
+    cp_async_wait<0>();
+    __syncwarp();
+    if (min_eig < min_eig_thr || D < 1.1920929e-07f) {
+      if (level == 0) st = false;
+      continue;
+    }
+    D = __fdiv_rn(1.f, D);
+
+    float pdx = 0.f, pdy = 0.f;
+    for (int j = 0; j < max_iters; j++) {
+      const int inx = (int)floorf(nx), iny = (int)floorf(ny);
+      if (inx < -WIN || inx >= J.w || iny < -WIN || iny >= J.h) {
+        if (level == 0) st = false;
+        break;
+      }
+      lk_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), wt, wb, iw00, iw01, iw10, iw11);
+      int bx = inx + PAD_L - tX0, by = iny + PAD_Y - tY0;
+      if ((unsigned)bx > 10u || (unsigned)by > 6u) {   // the window left the staged tile
+        __syncwarp();
+        tX0 = (inx + PAD_L - MARGIN) & ~3;
+        tY0 = iny + PAD_Y - MARGIN;
+        stage_tile(jtile + st_lane, Jimg + (size_t)tY0 * pitch + tX0, pitch, lane);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncwarp();
+        bx = inx + PAD_L - tX0;
+        by = MARGIN;
+      }
+      const unsigned* jp = jtile + by * TS + (bx >> 2);
+      const unsigned shJ = (unsigned)(bx & 3) * 8;
+      int a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0}, ua[4];
+      int b1[8], b2[8], ub[8];
+      int tot[3];
+      {
+        int jv[8];
+        oct_sample(jp + offA, shJ, wt, wb, jv);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          a1[i & 3] += jv[i] * Ix[i];
+          a2[i & 3] += jv[i] * Iy[i];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) ua[k] = (int)__sad(jv[k + 4], Iw[k + 4], __sad(jv[k], Iw[k], 0u)) * mpA[k];
+        oct_sample(jp + offB, shJ, wt, wb, jv);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          b1[i] = jv[i] * Ix[8 + i];
+          b2[i] = jv[i] * Iy[8 + i];
+          ub[i] = (int)__sad(jv[i], Iw[8 + i], 0u) * mB[i];
+        }
+        const int t1 = ((a1[0] + a1[1]) + (a1[2] + a1[3])) + (((b1[0] + b1[1]) + (b1[2] + b1[3])) + ((b1[4] + b1[5]) + (b1[6] + b1[7])));
+        const int t2 = ((a2[0] + a2[1]) + (a2[2] + a2[3])) + (((b2[0] + b2[1]) + (b2[2] + b2[3])) + ((b2[4] + b2[5]) + (b2[6] + b2[7])));
+        const int tu = ((ua[0] + ua[1]) + (ua[2] + ua[3])) + (((ub[0] + ub[1]) + (ub[2] + ub[3])) + ((ub[4] + ub[5]) + (ub[6] + ub[7])));
+        tot[0] = min(__reduce_add_sync(FULL, min(tu, SAFE_LIMIT)), SAFE_LIMIT);
+        tot[1] = __reduce_add_sync(FULL, t1);
+        tot[2] = __reduce_add_sync(FULL, t2);
+      }
+      if (ch == 0) n_iters_done++;
+      {
+        const int pos3[3] = {0, 1, 2};
+        plane_combine<3>(xch, phase, ch, lane, tot, pos3);
+      }
+      float b1f, b2f;
+      if (tot[0] < SAFE_LIMIT) {
+        // tier 1: every chain and every step of the final combination is exact
+        b1f = (float)(int)((unsigned)tot[1] - (unsigned)C1tot);
+        b2f = (float)(int)((unsigned)tot[2] - (unsigned)C2tot);
+      } else {
+        int cs[15];
+        lane_chains3(a1, b1, isq_b, nsimd, cs + 0);
+        lane_chains3(a2, b2, isq_b, nsimd, cs + 5);
+        lane_chains3(ua, ub, isq_b, nsimd, cs + 10);
+        int pos15[15];
+#pragma unroll
+        for (int s = 0; s < 3; s++) {
+#pragma unroll
+          for (int q = 0; q < 4; q++) pos15[s * 5 + q] = s * 5 + rot[q];
+          pos15[s * 5 + 4] = s * 5 + 4;
+        }
+#pragma unroll
+        for (int k = 0; k < 10; k++) cs[k] = __reduce_add_sync(FULL, cs[k]);
+#pragma unroll
+        for (int k = 10; k < 15; k++) cs[k] = min(__reduce_add_sync(FULL, min(cs[k], SAFE_LIMIT)), SAFE_LIMIT);
+        plane_combine<15>(xch, phase, ch, lane, cs, pos15);
+        bool safe = true;
+#pragma unroll
+        for (int k = 0; k < 5; k++) safe = safe && cs[10 + k] < SAFE_LIMIT;
+        if (safe) {
+          int e1[5], e2[5];
+#pragma unroll
+          for (int k = 0; k < 5; k++) {
+            e1[k] = (int)((unsigned)cs[k] - (unsigned)kC1[k]);
+            e2[k] = (int)((unsigned)cs[5 + k] - (unsigned)kC2[k]);
+          }
+          b1f = chain_combine((float)e1[0], (float)e1[1], (float)e1[2], (float)e1[3], (float)e1[4]);
+          b2f = chain_combine((float)e2[0], (float)e2[1], (float)e2[2], (float)e2[3], (float)e2[4]);
+        } else {
+          // The bound on sum |term| failed: exchange the int32 products of all planes (interleaved order) and
+          // evaluate the ten chains exactly, chain c on warp c % 3 (chain_b3: prefix test, sequential fall-back)
+          if (ch == 0) n_slow_b++;
+          int* p1 = reinterpret_cast<int*>(pbuf);
+          int* p2 = p1 + PBUF_WORDS;
+          __syncthreads();
+          {
+            int jv[8];
+            oct_sample(jp + offA, shJ, wt, wb, jv);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+              const int d = jv[i] - Iw[i], o = rowA * XROW + 3 * (colA + i) + ch;
+              p1[o] = d * Ix[i];
+              p2[o] = d * Iy[i];
+            }
+            oct_sample(jp + offB, shJ, wt, wb, jv);
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+              if (hasB && (!isq_b || i < 5)) {
+                const int d = jv[i] - Iw[8 + i], o = rowB * XROW + 3 * (colB + i) + ch;
+                p1[o] = d * Ix[8 + i];
+                p2[o] = d * Iy[8 + i];
+              }
+          }
+          __syncthreads();
+          int* xb = xch + (phase & 1u) * (C3 * 32);
+          for (int c = ch; c < 10; c += C3) {
+            const float v = chain_b3(c < 5 ? p1 : p2, c < 5 ? c : c - 5, lane);
+            if (lane == 0) xb[c] = __float_as_int(v);
+          }
+          __syncthreads();
+          phase++;
+          float resb[2];
+#pragma unroll
+          for (int s = 0; s < 2; s++)
+            resb[s] = chain_combine(__int_as_float(xb[s * 5 + 0]), __int_as_float(xb[s * 5 + 1]), __int_as_float(xb[s * 5 + 2]),
+                                    __int_as_float(xb[s * 5 + 3]), __int_as_float(xb[s * 5 + 4]));
+          b1f = resb[0];
+          b2f = resb[1];
+        }
+      }
+      const float bb1 = __fmul_rn(b1f, FLT_SCALE);
+      const float bb2 = __fmul_rn(b2f, FLT_SCALE);
+      const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, bb2), __fmul_rn(A22, bb1)), D);
+      const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, bb1), __fmul_rn(A11, bb2)), D);
+      nx = __fadd_rn(nx, dx);
+      ny = __fadd_rn(ny, dy);
+      outx = __fadd_rn(nx, half_win);
+      outy = __fadd_rn(ny, half_win);
+      {
+        const float s2 = fmaf(dx, dx, dy * dy);
+        bool conv;
+        if (s2 < eps_lo) conv = true;
+        else if (s2 > eps_hi) conv = false;
+        else conv = __dadd_rn(__dmul_rn((double)dx, (double)dx), __dmul_rn((double)dy, (double)dy)) <= eps_sq;
+        if (conv) break;
+      }
+      if (j > 0 && fabsf(__fadd_rn(dx, pdx)) <= 0.01f && fabsf(__fadd_rn(dy, pdy)) <= 0.01f) {
+        outx = __fsub_rn(outx, __fmul_rn(dx, 0.5f));
+        outy = __fsub_rn(outy, __fmul_rn(dy, 0.5f));
+        break;
+      }
+      pdx = dx;
+      pdy = dy;
+    }
+
+    // ---- err pass: mean |J - I| / 32 over the window and the channels at the final position
+    if (st && level == 0) {
+      const float fx = __fsub_rn(outx, half_win), fy = __fsub_rn(outy, half_win);
+      const int inx = (int)floorf(fx), iny = (int)floorf(fy);
+      if (inx < -WIN || inx >= J.w || iny < -WIN || iny >= J.h) {
+        st = false;
+      } else if (err) {
+        lk_weights(__fsub_rn(fx, (float)inx), __fsub_rn(fy, (float)iny), wt, wb, iw00, iw01, iw10, iw11);
+        int bx = inx + PAD_L - tX0, by = iny + PAD_Y - tY0;
+        if ((unsigned)bx > 10u || (unsigned)by > 6u) {
+          __syncwarp();
+          tX0 = (inx + PAD_L - MARGIN) & ~3;
+          tY0 = iny + PAD_Y - MARGIN;
+          stage_tile(jtile + st_lane, Jimg + (size_t)tY0 * pitch + tX0, pitch, lane);
+          cp_async_commit();
+          cp_async_wait<0>();
+          __syncwarp();
+          bx = inx + PAD_L - tX0;
+          by = MARGIN;
+        }
+        unsigned se = 0;
+        int jv[8];
+        const unsigned* jp = jtile + by * TS + (bx >> 2);
+        const unsigned shJ = (unsigned)(bx & 3) * 8;
+        oct_sample(jp + offA, shJ, wt, wb, jv);
+#pragma unroll
+        for (int i = 0; i < 8; i++) se = __sad(jv[i], Iw[i], se);
+        oct_sample(jp + offB, shJ, wt, wb, jv);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const bool valid = hasB && (!isq_b || i < 5);
+          se += valid ? __sad(jv[i], Iw[8 + i], 0u) : 0u;
+        }
+        int tot[1] = {__reduce_add_sync(FULL, (int)se)};
+        const int pos1[1] = {0};
+        plane_combine<1>(xch, phase, ch, lane, tot, pos1);   // <= 1323*8160 < 2^24: OpenCV's float sum is exact
+        errv = __fdiv_rn((float)tot[0], (float)(32 * WIN * C3 * WIN));
+      }
+    }
+  }
+
+  if (ch == 0 && lane == 0) {
+    next_pts[point] = make_float2(outx, outy);
+    status[point] = st ? 1 : 0;
+    if (err) err[point] = errv;
+    if (work) {
+      atomicAdd(&work[0], (unsigned long long)n_levels_done);
+      atomicAdd(&work[1], (unsigned long long)n_iters_done);
+      atomicAdd(&work[2], (unsigned long long)n_slow_a);
+      atomicAdd(&work[3], (unsigned long long)n_slow_b);
+    }
+  }
+}
+
 #undef offA
 #undef offB
 #undef rowA
@@ -605,12 +1163,16 @@ int lk_launch(vo_ctx* c, int slot_prev, int slot_next, const float2* d_prev, int
   static const int variant = getenv("VO_LK_MINB") ? atoi(getenv("VO_LK_MINB")) : 4;
   {
     LaunchScope ls(c, VO_K_LK);
-    if (c->p.channels == 3)
-      v1::lk_kernel_c3<<<blocks, threads, 0, c->stream>>>(pyr_view(c->pyr[slot_prev]), pyr_view(c->pyr[slot_next]), d_prev, n,
-                                                          d_next, d_status, d_err, max_iters, eps, (float)c->p.lk_min_eig,
-                                                          c->d_lk_work, c->n_dev);
+    if (c->p.channels == 3 && use_v1)
+      v1::lk_kernel_c3<<<div_up(n * 32, 128), 128, 0, c->stream>>>(pyr_view(c->pyr[slot_prev]), pyr_view(c->pyr[slot_next]), d_prev, n,
+                                                                   d_next, d_status, d_err, max_iters, eps, (float)c->p.lk_min_eig,
+                                                                   c->d_lk_work, c->n_dev);
+    else if (c->p.channels == 3)
+      lk_kernel_c3<<<n, C3 * 32, 0, c->stream>>>(pyr_view(c->pyr[slot_prev]), pyr_view(c->pyr[slot_next]), d_prev, n, d_next,
+                                                 d_status, d_err, max_iters, eps, eps_lo, eps_hi, (float)c->p.lk_min_eig,
+                                                 c->d_lk_work, c->n_dev);
     else if (use_v1)
-      v1::lk_kernel<<<blocks, threads, 0, c->stream>>>(pyr_view(c->pyr[slot_prev]), pyr_view(c->pyr[slot_next]), d_prev, n,
+      v1::lk_kernel<<<div_up(n * 32, 128), 128, 0, c->stream>>>(pyr_view(c->pyr[slot_prev]), pyr_view(c->pyr[slot_next]), d_prev, n,
                                                        d_next, d_status, d_err, max_iters, eps, (float)c->p.lk_min_eig,
                                                        c->d_lk_work, c->n_dev);
     else if (variant == 4)

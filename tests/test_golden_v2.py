@@ -63,7 +63,8 @@ def test_cuda_reproduces_v2_vectors():
         p, st, err = fe3.calcOpticalFlowPyrLK(A, B, pts)
         assert np.array_equal(st, g2[f"bgr_{kind}_lk_status"])
         ok = st == 1
-        assert np.abs(p - g2[f"bgr_{kind}_lk_pts"]).max(1)[ok].max() <= 0.01   # TODO(c3): equality once lk_kernel_c3 follows
+        assert np.array_equal(p[ok], g2[f"bgr_{kind}_lk_pts"][ok])        # cv2's bits
+        assert np.array_equal(err[ok], g2[f"bgr_{kind}_lk_err"][ok])
         lv, dv = fe3.pyramid_level(A, 3)
         assert np.array_equal(lv, g2[f"bgr_{kind}_pyr_l3"]) and np.array_equal(dv, g2[f"bgr_{kind}_pyr_l3_deriv"])
         for l in range(4):

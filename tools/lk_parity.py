@@ -80,6 +80,23 @@ def main():
     allok &= run(fe, "checker shift(0.8,0.4)", cb, shift(cb, 0.8, 0.4), glue.dense_keypoint_extractor(376, 1241, 9), reps=0)
     allok &= run(fe, "checker vs noise", cb, harsh(L0, 3), glue.dense_keypoint_extractor(376, 1241, 9), reps=0)
     fe.close()
+    # 3-channel input (the reference's imread frames): replicated gray, a genuinely coloured pair, a harsh one
+    fe3 = VisualFrontEnd(max_points=131072, channels=3)
+
+    def colorize(img):
+        f = img.astype(np.float32)
+        return np.stack([f, 255.0 - 0.8 * f, 255.0 * (f / 255.0) ** 0.7], -1).round().clip(0, 255).astype(np.uint8)
+
+    for step in ((9,) if quick else (30, 9, 5)):
+        pts = np.concatenate([glue.dense_keypoint_extractor(376, 1241, step), extra])
+        allok &= run(fe3, "bgr gray3 step%d temporal" % step, cv2.cvtColor(L0, cv2.COLOR_GRAY2BGR), cv2.cvtColor(L1, cv2.COLOR_GRAY2BGR),
+                     pts, reps=5 if step == 5 else 0)
+        allok &= run(fe3, "bgr color step%d stereo" % step, colorize(L0), colorize(R0), pts, reps=5 if step == 5 else 0)
+    Hc = np.stack([H0, harsh(L0, 5), 255 - H0], -1)
+    Hs = np.stack([shift(Hc[:, :, c], 1.3, 0.6) for c in range(3)], -1)
+    allok &= run(fe3, "bgr harsh shift(1.3,0.6)", Hc, Hs, np.concatenate([glue.dense_keypoint_extractor(376, 1241, 9), extra]), reps=3)
+    allok &= run(fe3, "bgr harsh vs other", Hc, np.ascontiguousarray(Hc[:, ::-1]), glue.dense_keypoint_extractor(376, 1241, 15))
+    fe3.close()
     print("ALL OK" if allok else "SOME FAILED")
     return 0 if allok else 1
 
