@@ -219,6 +219,8 @@ def run_frames(fe, lib, seq, first, count, device_resident, record=None):
     kp = 0
     for i in range(first, first + count):
         if device_resident:
+            if i + 1 < first + count:     # the next frame is resident too: announce it (look-ahead of its temporal LK)
+                _lib.check(lib.vo_seq_announce(fe.h, C.c_void_p(seq.dptr(i + 1, 0)), C.c_void_p(seq.dptr(i + 1, 1)), seq.stride, 1))
             r = lib.vo_seq_track(fe.h, C.c_void_p(seq.dptr(i, 0)), C.c_void_p(seq.dptr(i, 1)), seq.stride, 1, 0, C.byref(res))
         else:
             if i + 1 < first + count:

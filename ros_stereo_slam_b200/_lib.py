@@ -71,7 +71,7 @@ SYMBOLS = [
     "vo_grid_keypoints", "vo_anms", "vo_lk_track", "vo_debug_pyramid_level", "vo_debug_pyramid_padded", "vo_fmat_ransac", "vo_triangulate",
     "vo_pnp_ransac", "vo_debug_last_pnp", "vo_debug_last_fmat", "vo_debug_epnp", "vo_transform_points", "vo_bgr_to_gray", "vo_sor_cloud", "vo_pose_from_pnp",
     "vo_dense_lk_tracking", "vo_fmat_thresholding", "vo_stereo_triangulate", "vo_insert_keyframe",
-    "vo_track_frame", "vo_pnp_frame", "vo_seq_init", "vo_seq_track", "vo_seq_prefetch", "vo_seq_get_reference", "vo_cuda_stream",
+    "vo_track_frame", "vo_pnp_frame", "vo_seq_init", "vo_seq_track", "vo_seq_prefetch", "vo_seq_announce", "vo_seq_get_reference", "vo_cuda_stream",
     "vo_sync", "vo_profile_enable", "vo_profile_read", "vo_debug_timeline", "vo_launch_count", "vo_lk_work", "vo_lk_slow_paths", "vo_measure_fp32_peak", "vo_measure_int32_peak",
     "vo_synth_render_dev", "vo_alloc_host", "vo_free_host", "vo_alloc_dev", "vo_free_dev", "vo_memcpy_d2h",
     "vo_memcpy_h2d",

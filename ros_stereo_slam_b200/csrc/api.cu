@@ -302,10 +302,10 @@ int vo_create(const vo_params* p, vo_ctx** out) {
   cudaDeviceProp prop;
   VO_CUDA(cudaGetDeviceProperties(&prop, p->device));
   c->sm_count = prop.multiProcessorCount;
-  c->pyr = new Pyramid[3];
+  c->pyr = new Pyramid[4];
   int r = alloc_chain(c);
   if (r == VO_OK) {
-    for (int s = 0; s < 3 && r == VO_OK; s++) r = pyr_alloc(c, c->pyr[s]);
+    for (int s = 0; s < 4 && r == VO_OK; s++) r = pyr_alloc(c, c->pyr[s]);
   }
   if (r == VO_OK) {
     vo_ctx* a = new vo_ctx();
@@ -318,9 +318,22 @@ int vo_create(const vo_params* p, vo_ctx** out) {
     r = alloc_chain(a);
   }
   if (r == VO_OK) {
+    vo_ctx* l = new vo_ctx();     // look-ahead chain (see common.cuh)
+    l->p = *p;
+    l->device = p->device;
+    l->sm_count = c->sm_count;
+    l->is_aux = true;
+    l->pyr = c->pyr;
+    c->la = l;
+    r = alloc_chain(l);
+  }
+  if (r == VO_OK) {
     if (cudaEventCreateWithFlags(&c->ev_left, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_lk, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_xform, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_la, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_gather, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_slk, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_stereo, cudaEventDisableTiming) != cudaSuccess) {
       set_error("cudaEventCreate failed");
       r = VO_ERR_CUDA;
@@ -359,8 +372,15 @@ int vo_destroy(vo_ctx* c) {
     free_chain(c->aux);
     delete c->aux;
   }
+  if (c->la) {
+    free_chain(c->la);
+    delete c->la;
+  }
+  if (c->ev_la) cudaEventDestroy(c->ev_la);
+  if (c->ev_gather) cudaEventDestroy(c->ev_gather);
+  if (c->ev_slk) cudaEventDestroy(c->ev_slk);
   if (c->pyr) {
-    for (int s = 0; s < 3; s++) pyr_free(c->pyr[s]);
+    for (int s = 0; s < 4; s++) pyr_free(c->pyr[s]);
     delete[] c->pyr;
   }
   if (c->ev_left) cudaEventDestroy(c->ev_left);
@@ -662,17 +682,18 @@ static int prefetch_issue(vo_ctx* c) {
 // pts_to_host: also bring the (at most n) surviving correspondences to c->h_pts in the same
 // synchronisation -- the F-matrix sampler needs them for OpenCV's collinearity subset check.
 static int lk_and_compact(vo_ctx* c, int slot_a, int slot_b, const float2* d_in, const float3* d_in_xyz, int n, int* m,
-                          bool pts_to_host = false) {
+                          bool pts_to_host = false, bool lk_done = false) {
   *m = 0;
   if (n <= 0) return VO_OK;
-  VO_TRY(lk_launch(c, slot_a, slot_b, d_in, n, c->d_xy_trk, c->d_status, nullptr));   // err is not consumed: test only
+  // lk_done: d_xy_trk / d_status were filled from the look-ahead launch (vo_seq_track)
+  if (!lk_done) VO_TRY(lk_launch(c, slot_a, slot_b, d_in, n, c->d_xy_trk, c->d_status, nullptr));   // err is not consumed: test only
   VO_TRY(compact_launch(c, c->d_status, n, d_in, c->d_c_ref, c->d_xy_trk, c->d_c_trk, d_in_xyz, c->d_c_xyz, nullptr, 0));
   if (pts_to_host) {
     VO_CUDA(cudaMemcpyAsync(c->h_pts, c->d_c_ref, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
     VO_CUDA(cudaMemcpyAsync(c->h_pts + (size_t)2 * c->cap, c->d_c_trk, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost,
                             c->stream));
   }
-  if (!c->is_aux) VO_TRY(prefetch_issue(c));   // the next frame's H2D copies go out while this LK runs
+  if (!c->is_aux && !c->pf_by_worker) VO_TRY(prefetch_issue(c));   // the next frame's H2D copies go out while this LK runs
   {
     TraceScope tw(6);
     VO_TRY(read_counts(c));
@@ -683,7 +704,8 @@ static int lk_and_compact(vo_ctx* c, int slot_a, int slot_b, const float2* d_in,
 
 // F-RANSAC on d_c_* (m points) + mask compaction into d_f_*; *k = survivors.
 // have_host_pts: c->h_pts already holds the correspondences (lk_and_compact(pts_to_host)).
-static int fmat_and_compact(vo_ctx* c, int m, double thr, bool with_xyz, int* k, bool have_host_pts = false) {
+static int fmat_and_compact(vo_ctx* c, int m, double thr, bool with_xyz, int* k, bool have_host_pts = false,
+                            int32_t* idx_out = nullptr) {
   *k = 0;
   if (m <= 0) return VO_OK;
   float* h1 = c->h_pts;
@@ -695,7 +717,7 @@ static int fmat_and_compact(vo_ctx* c, int m, double thr, bool with_xyz, int* k,
   }
   auto tail = [&]() -> int {
     VO_TRY(compact_launch(c, c->d_mask, m, c->d_c_ref, c->d_f_ref, c->d_c_trk, c->d_f_trk,
-                          with_xyz ? c->d_c_xyz : nullptr, c->d_f_xyz, nullptr, 1));
+                          with_xyz ? c->d_c_xyz : nullptr, c->d_f_xyz, idx_out, 1));
     VO_CUDA(cudaMemcpyAsync(c->h_count, c->d_count, 16 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     return VO_OK;
   };
@@ -723,13 +745,17 @@ static void make_projections(const vo_params& p, double* P /*24*/) {
 
 // stereoTriangulate on pyramids slot_l / slot_r (already built).  Result: d_f_ref (2-D left),
 // d_xyz_tmp (camera frame) and, when pose != NULL, d_f_xyz <- pose * xyz (world frame).
-static int stereo_pipeline(vo_ctx* c, int slot_l, int slot_r, const double* pose3x4, int* n_out, int* n_grid_out) {
+// after_lk (optional): called with the number of stereo-LK survivors (d_c_ref) before F-RANSAC is enqueued;
+// idx_out (optional): indices of the F-RANSAC inliers in that survivor order.
+static int stereo_pipeline(vo_ctx* c, int slot_l, int slot_r, const double* pose3x4, int* n_out, int* n_grid_out,
+                           const std::function<int(int)>& after_lk = nullptr, int32_t* idx_out = nullptr) {
   int ng = 0;
   VO_TRY(grid_launch(c, c->p.height, c->p.width, c->p.grid_step, c->d_xy_in, &ng));
   if (n_grid_out) *n_grid_out = ng;
   int m = 0, k = 0;
   VO_TRY(lk_and_compact(c, slot_l, slot_r, c->d_xy_in, nullptr, ng, &m, true));
-  VO_TRY(fmat_and_compact(c, m, c->p.f_thr_stereo, false, &k, true));
+  if (after_lk) VO_TRY(after_lk(m));
+  VO_TRY(fmat_and_compact(c, m, c->p.f_thr_stereo, false, &k, true, idx_out));
   double P[36];
   make_projections(c->p, P);
   if (pose3x4) memcpy(P + 24, pose3x4, 12 * sizeof(double));
@@ -742,9 +768,9 @@ static int stereo_pipeline(vo_ctx* c, int slot_l, int slot_r, const double* pose
 
 // PyrLKtrackFrame2Frame on device data: d_ref_xy/d_ref_xyz (n) -> d_f_trk, d_f_xyz, d_f_ref (k)
 static int track_pipeline(vo_ctx* c, int slot_ref, int slot_cur, const float2* d_ref_xy, const float3* d_ref_xyz, int n,
-                          int* k) {
+                          int* k, bool lk_done = false) {
   int m = 0;
-  VO_TRY(lk_and_compact(c, slot_ref, slot_cur, d_ref_xy, d_ref_xyz, n, &m, true));
+  VO_TRY(lk_and_compact(c, slot_ref, slot_cur, d_ref_xy, d_ref_xyz, n, &m, true, lk_done));
   return fmat_and_compact(c, m, c->p.f_thr_temporal, true, k, true);
 }
 
@@ -964,6 +990,36 @@ static int temporal_finish(vo_ctx* c, int* k, int* n_inl, int* attempt) {
   return pnp_two_attempts(c, *k, n_inl, attempt);
 }
 
+// left-image pyramid slots rotate 0 -> 1 -> 3 -> 0 (slot 2 is the right image): reference, current, look-ahead
+static inline int next_left_slot(int s) { return s == 0 ? 1 : (s == 1 ? 3 : 0); }
+
+// Enqueue the NEXT frame's temporal LK on the look-ahead chain (called by the stereo worker once this frame's
+// stereo-LK survivors -- the superset of the new keyframe's points -- are in aux->d_c_ref, m of them).
+static int lookahead_enqueue(vo_ctx* c, int m, int slot_cur, int slot_next, const uint8_t* img, int stride, cudaEvent_t img_ready,
+                             const uint8_t* identity) {
+  vo_ctx* a = c->aux;
+  vo_ctx* l = c->la;
+  if (m <= 0) return VO_OK;
+  VO_CUDA(cudaEventRecord(c->ev_slk, a->stream));               // survivors complete
+  VO_CUDA(cudaStreamWaitEvent(l->stream, c->ev_slk, 0));
+  VO_CUDA(cudaStreamWaitEvent(l->stream, c->ev_gather, 0));      // the previous look-ahead's tracks have been gathered
+  if (img_ready) VO_CUDA(cudaStreamWaitEvent(l->stream, img_ready, 0));
+  VO_TRY(load_image(l, slot_next, img, stride, 1, true));
+  VO_TRY(lk_launch(l, slot_cur, slot_next, a->d_c_ref, m, l->d_xy_trk, l->d_status, nullptr));
+  VO_CUDA(cudaEventRecord(c->ev_la, l->stream));
+  c->la_valid = true;
+  c->la_left = identity;
+  c->la_m = m;
+  return VO_OK;
+}
+
+// a call that touches the pyramid slots outside the sequence driver: let an in-flight look-ahead finish first
+static void lookahead_quiesce(vo_ctx* c) {
+  if (c->la && (c->la_inflight || c->la_valid)) cudaStreamSynchronize(c->la->stream);
+  c->la_inflight = c->la_valid = false;
+  c->ann_left = c->ann_right = nullptr;
+}
+
 static void pose_from_pnp(const double rvec[3], const double tvec[3], double pose[12]) {
   double R[9];
   rodrigues_vec2mat(rvec, R);
@@ -1004,6 +1060,7 @@ int vo_lk_track(vo_ctx* c, const uint8_t* prev, const uint8_t* next, int stride,
   if (n > c->cap) return VO_ERR_CAPACITY;
   if (n == 0) return VO_OK;
   c->seq_ref_slot = -1;   // the stage entry points reuse the sequence driver's pyramid slots: vo_seq_init again before vo_seq_track
+  lookahead_quiesce(c);
   VO_TRY(load_image(c, 0, prev, stride, 0, true));
   VO_TRY(load_image(c, 1, next, stride, 0, false));
   VO_CUDA(cudaMemcpyAsync(c->d_xy_in, prev_xy, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
@@ -1053,6 +1110,7 @@ int vo_debug_pyramid_level(vo_ctx* c, const uint8_t* img, int stride, int level,
   CHECK_CTX(c);
   if (!img) return VO_ERR_INVALID_ARG;
   c->seq_ref_slot = -1;   // the stage entry points reuse the sequence driver's pyramid slots: vo_seq_init again before vo_seq_track
+  lookahead_quiesce(c);
   VO_TRY(load_image(c, 0, img, stride, 0, true));
   Pyramid& p = c->pyr[0];
   if (level < 0 || level >= p.nlevels) return VO_ERR_INVALID_ARG;
@@ -1067,6 +1125,7 @@ int vo_debug_pyramid_padded(vo_ctx* c, const uint8_t* img, int stride, int level
   CHECK_CTX(c);
   if (!img || pad < 0 || pad > PAD_Y) return VO_ERR_INVALID_ARG;
   c->seq_ref_slot = -1;   // the stage entry points reuse the sequence driver's pyramid slots: vo_seq_init again before vo_seq_track
+  lookahead_quiesce(c);
   VO_TRY(load_image(c, 0, img, stride, 0, true));
   Pyramid& p = c->pyr[0];
   if (level < 0 || level >= p.nlevels) return VO_ERR_INVALID_ARG;
@@ -1290,6 +1349,7 @@ int vo_dense_lk_tracking(vo_ctx* c, const uint8_t* ref_img, const uint8_t* cur_i
   *m = 0;
   if (n == 0) return VO_OK;
   c->seq_ref_slot = -1;   // the stage entry points reuse the sequence driver's pyramid slots: vo_seq_init again before vo_seq_track
+  lookahead_quiesce(c);
   VO_TRY(load_image(c, 0, ref_img, stride, 0, true));
   VO_TRY(load_image(c, 1, cur_img, stride, 0, false));
   VO_CUDA(cudaMemcpyAsync(c->d_xy_in, ref_xy, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
@@ -1329,6 +1389,7 @@ static int stereo_host(vo_ctx* c, const uint8_t* left, const uint8_t* right, int
   }
   *n = 0;
   c->seq_ref_slot = -1;   // the stage entry points reuse the sequence driver's pyramid slots: vo_seq_init again before vo_seq_track
+  lookahead_quiesce(c);
   VO_TRY(load_image(c, 0, left, stride, 0, true));
   VO_TRY(load_image(c, 2, right, stride, 0, false));
   int k = 0;
@@ -1370,6 +1431,7 @@ static int track_host(vo_ctx* c, const uint8_t* ref_img, const uint8_t* cur_img,
   *k = 0;
   if (n == 0) return VO_OK;
   c->seq_ref_slot = -1;   // the stage entry points reuse the sequence driver's pyramid slots: vo_seq_init again before vo_seq_track
+  lookahead_quiesce(c);
   VO_TRY(load_image(c, 0, ref_img, stride, 0, true));
   VO_TRY(load_image(c, 1, cur_img, stride, 0, false));
   VO_CUDA(cudaMemcpyAsync(c->d_xy_in, ref_xy, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
@@ -1412,6 +1474,7 @@ int vo_pnp_frame(vo_ctx* c, const uint8_t* ref_img, const uint8_t* cur_img, int 
     r = pnp_two_attempts(c, 0, &ni, &att);
   } else {
     c->seq_ref_slot = -1;   // the stage entry points reuse the sequence driver's pyramid slots: vo_seq_init again before vo_seq_track
+  lookahead_quiesce(c);
     VO_TRY(load_image(c, 0, ref_img, stride, 0, true));
     VO_TRY(load_image(c, 1, cur_img, stride, 0, false));
     VO_CUDA(cudaMemcpyAsync(c->d_xy_in, ref_xy, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, c->stream));
@@ -1443,6 +1506,7 @@ int vo_seq_init(vo_ctx* c, const uint8_t* left, const uint8_t* right, int stride
   // a new sequence: forget announced frames (their copies, if any, are left to finish)
   c->pf_left[0] = c->pf_left[1] = c->pf_wait_left = nullptr;
   if (c->copy_stream) VO_CUDA(cudaStreamSynchronize(c->copy_stream));
+  lookahead_quiesce(c);
   VO_TRY(load_image(c, 0, left, stride, is_device, true));
   VO_TRY(load_image(c, 2, right, stride, is_device, false));
   int k = 0;
@@ -1477,11 +1541,22 @@ int vo_seq_prefetch(vo_ctx* c, const uint8_t* left, const uint8_t* right, int st
   return VO_OK;
 }
 
+int vo_seq_announce(vo_ctx* c, const uint8_t* left, const uint8_t* right, int stride, int is_device) {
+  if (!is_device) return vo_seq_prefetch(c, left, right, stride);
+  CHECK_CTX(c);
+  if (!left || stride < c->p.width * c->p.channels) return VO_ERR_INVALID_ARG;
+  c->ann_left = left;
+  c->ann_right = right;
+  c->ann_stride = stride;
+  return VO_OK;
+}
+
 int vo_seq_track(vo_ctx* c, const uint8_t* left, const uint8_t* right, int stride, int is_device, int force_keyframe,
                  vo_frame_result* out) {
   CHECK_CTX(c);
   if (!left || !out || c->seq_ref_slot < 0) return VO_ERR_INVALID_ARG;
   memset(out, 0, sizeof(*out));
+  const uint8_t* left_id = left;     // the pointer the caller announced / passes (before the staging substitution below)
   if (!is_device && c->pf_wait_left == left) c->pf_wait_left = nullptr;   // announced but never issued: copy it now
   if (!is_device) {
     // images announced by vo_seq_prefetch are already (being) copied: use the device staging instead
@@ -1494,37 +1569,60 @@ int vo_seq_track(vo_ctx* c, const uint8_t* left, const uint8_t* right, int strid
         stride = c->p.width * c->p.channels;
         is_device = 1;
         c->pf_left[s] = nullptr;
+        c->pf_next = 1 - s;      // this call reads staging set s: the next announced frame goes to the other one
         break;
       }
     }
   }
-  const int ref = c->seq_ref_slot, cur = 1 - ref;
-  // with derivatives: this left image is the previous image of this frame's stereo LK and of the
-  // next frame's temporal LK (one fused launch builds levels, borders and Scharr planes)
-  VO_TRY(load_image(c, cur, left, stride, is_device, true));
+  const int ref = c->seq_ref_slot, cur = next_left_slot(ref);
   out->n_lk_in = c->seq_n;
 
   // A keyframe that is known before PnP (caller forces it, or the policy fires on every frame
   // because no inlier count can reach kf_min_inliers) does not depend on this frame's tracking:
   // run the stereo pipeline on the auxiliary chain concurrently with tracking + PnP.
   const bool kf_known = right && (force_keyframe || c->p.kf_min_inliers > c->p.max_points);
+  // default: the fused single-synchronisation chains (2 host synchronisations per frame); VO_B200_SEQ_HOST=1 selects the
+  // host-driven chains (3-4 synchronisations per chain, host-side sampling)
+  static const bool host_driven = getenv("VO_B200_SEQ_HOST") != nullptr;
+  // Look-ahead is opt-in (VO_B200_LOOKAHEAD=1): measured on the bench workload it LOSES (858 vs 881 frames/s) -- a full
+  // LK launch occupies every SM's register file, so the latency-bound solver kernels of the tracking chain it was meant
+  // to hide under wait for LK blocks to retire (pnp_solve 0.27 -> 0.49 ms).  Kept because it is exact and because it
+  // is the right schedule once the chains run on disjoint SM partitions.
+  static const bool la_enabled = getenv("VO_B200_LOOKAHEAD") != nullptr;
+
+  // Look-ahead bookkeeping.  have_la: the previous call already built this image's pyramid (slot `cur`) and tracked
+  // the keyframe's points into it on the look-ahead chain.
+  bool have_la = false;
+  if (c->la_inflight) {
+    have_la = kf_known && host_driven && c->la_valid && c->la_left == left_id && c->seq_n > 0;
+    VO_CUDA(cudaStreamWaitEvent(c->stream, c->ev_la, 0));   // either way: it writes the slot this call uses
+    c->la_inflight = false;
+    c->la_valid = false;
+  }
+  // with derivatives: this left image is the previous image of this frame's stereo LK and of the
+  // next frame's temporal LK (one fused launch builds levels, borders and Scharr planes)
+  if (!have_la) VO_TRY(load_image(c, cur, left, stride, is_device, true));
   vo_ctx* a = c->aux;
   int kk = 0, ng = 0;
   int k = 0, ni = 0, att = 1;
   int r;
+  if (have_la) {
+    // this frame's tracks: the F-RANSAC inliers of the keyframe (aux->d_idx, order of d_seq_xy) out of the look-ahead
+    // launch over all stereo-LK survivors
+    VO_TRY(gather_tracks_launch(c, a->d_idx, c->seq_n, c->la->d_xy_trk, c->la->d_status, c->d_xy_trk, c->d_status));
+  }
+  VO_CUDA(cudaEventRecord(c->ev_gather, c->stream));   // the look-ahead buffers and aux->d_idx are free again
   if (c->xform_pending) {   // previous frame's world transform still reads the stereo chain's outputs
     VO_CUDA(cudaStreamWaitEvent(a->stream, c->ev_xform, 0));
     c->xform_pending = false;
   }
-  // Two drivers for the dual-chain frame.  Measured on the bench workload (B200, 200 frames):
-  //   host-driven chains, stereo chain on the worker thread (2-3 synchronisations per chain)  956 frames/s, e2e 910
-  //   fused single-sync chains enqueued by this thread (device-side sampling)                  919 frames/s, e2e 874
-  // The fused chain is what the single-chain entry points use (one synchronisation per call; vo_pnp_frame is
-  // 47 us faster with it).  With two chains in flight it loses: without the host gaps between its stages the
-  // tracking chain reaches pnp_solve_kernel ~90 us earlier, while the stereo chain's LK launch (low priority,
-  // dispatched after the tracking LK) is still running -- and that latency-bound kernel slows down by more
-  // (0.30 -> 0.40 ms) than the gaps were worth.  VO_B200_SEQ_FUSED=1 selects the fused form.
-  static const bool host_driven = getenv("VO_B200_SEQ_FUSED") == nullptr;
+  // Two drivers for the dual-chain frame.  Measured on the bench workload (B200, 60 frames, round 2):
+  //   fused single-sync chains enqueued by this thread (device-side sampling)                  868 frames/s, e2e 876
+  //   host-driven chains, stereo chain on the worker thread (2-3 synchronisations per chain)  883 frames/s, e2e 873
+  // Equal within the run-to-run spread; the fused form is the default because it needs two host synchronisations
+  // per frame instead of seven, which is what keeps eight ranks on one host from disturbing each other.  (Round 1
+  // measured 919 vs 956 the other way round: without the host gaps the tracking chain reaches pnp_solve_kernel
+  // while the stereo chain's LK is still running.)  The look-ahead lives in the host-driven form only.
   if (kf_known && c->seq_n > 0 && temporal_fusable(c) && !host_driven) {
     // both chains are enqueued by this thread, the critical one (tracking + PnP, high-priority
     // stream) first; one synchronisation per chain at the end
@@ -1551,25 +1649,64 @@ int vo_seq_track(vo_ctx* c, const uint8_t* left, const uint8_t* right, int strid
     VO_CUDA(cudaEventRecord(c->ev_stereo, a->stream));
     if (r == VO_OK) r = rs;
   } else {
+    // VO_B200_LK_FIRST=1: the tracking chain's LK (critical path) is launched before the stereo worker is released and
+    // the stereo chain waits for it, so the two full-GPU LK launches run back to back instead of side by side
+    static const bool lk_first_env = getenv("VO_B200_LK_FIRST") != nullptr;
+    const bool lk_first = lk_first_env && host_driven && kf_known && !have_la && c->seq_n > 0;
     if (kf_known) {
       VO_CUDA(cudaEventRecord(c->ev_left, c->stream));
+      if (lk_first) {
+        VO_TRY(lk_launch(c, ref, cur, c->d_seq_xy, c->seq_n, c->d_xy_trk, c->d_status, nullptr));
+        VO_CUDA(cudaEventRecord(c->ev_lk, c->stream));
+        VO_CUDA(cudaStreamWaitEvent(a->stream, c->ev_lk, 0));
+      }
       VO_CUDA(cudaStreamWaitEvent(a->stream, c->ev_left, 0));
+      VO_CUDA(cudaStreamWaitEvent(a->stream, c->ev_gather, 0));   // aux->d_idx / d_c_ref of the previous keyframe are released
+      // The next frame, if the caller announced it: device-resident (vo_seq_announce) or host (vo_seq_prefetch, copied
+      // to the staging buffers by the worker).  Its temporal LK is enqueued by the worker as soon as the stereo-LK
+      // survivors are known (lookahead_enqueue).
+      const bool do_la = la_enabled && host_driven && c->la != nullptr;
+      const uint8_t* nxt_dev = do_la ? c->ann_left : nullptr;
+      const int nxt_dev_stride = c->ann_stride;
+      const bool nxt_host = do_la && !nxt_dev && c->pf_wait_left != nullptr && c->pf_wait_left != left_id;
+      c->ann_left = c->ann_right = nullptr;
+      c->pf_by_worker = nxt_host;
+      const int la_slot = next_left_slot(cur);
       post_task(c, [=, &kk, &ng]() -> int {
+        const uint8_t* nimg = nxt_dev;
+        int nstride = nxt_dev_stride;
+        cudaEvent_t nready = nullptr;
+        const uint8_t* nid = nxt_dev;
+        if (nxt_host) {
+          VO_TRY(prefetch_issue(c));                 // H2D copies of the announced frame (copy stream)
+          const int sl = 1 - c->pf_next;             // the staging set they went to
+          nimg = c->d_stage[sl][0];
+          nstride = c->p.width * c->p.channels;
+          nready = c->ev_prefetch[sl];
+          nid = c->pf_left[sl];
+        }
         VO_TRY(load_image(a, 2, right, stride, is_device, false));
-        if (host_driven) VO_TRY(stereo_pipeline(a, cur, 2, nullptr, &kk, &ng));
-        else VO_TRY(stereo_any(a, cur, 2, &kk, &ng));             // camera-frame xyz in a->d_xyz_tmp
+        if (host_driven) {
+          std::function<int(int)> hook = nullptr;
+          if (nimg) hook = [=](int m) -> int { return lookahead_enqueue(c, m, cur, la_slot, nimg, nstride, nready, nid); };
+          VO_TRY(stereo_pipeline(a, cur, 2, nullptr, &kk, &ng, hook, a->d_idx));
+        } else {
+          VO_TRY(stereo_any(a, cur, 2, &kk, &ng));             // camera-frame xyz in a->d_xyz_tmp
+        }
         VO_CUDA(cudaEventRecord(c->ev_stereo, a->stream));
         return VO_OK;
       });
     }
     if (host_driven) {
-      r = track_pipeline(c, ref, cur, c->d_seq_xy, c->d_seq_xyz, c->seq_n, &k);
+      r = track_pipeline(c, ref, cur, c->d_seq_xy, c->d_seq_xyz, c->seq_n, &k, have_la || lk_first);
       if (r == VO_OK) r = pnp_two_attempts(c, k, &ni, &att);
     } else {
       r = temporal_any(c, ref, cur, c->d_seq_xy, c->d_seq_xyz, c->seq_n, &k, &ni, &att);
     }
     if (kf_known) {
       const int rs = wait_task(c);     // always join: the auxiliary chain must be idle on return
+      c->pf_by_worker = false;
+      c->la_inflight = c->la_valid;    // set by lookahead_enqueue on the worker thread (ordered by the join)
       if (r == VO_OK) r = rs;
     }
   }
@@ -1646,6 +1783,7 @@ void* vo_cuda_stream(vo_ctx* c) { return c ? (void*)c->stream : nullptr; }
 
 int vo_sync(vo_ctx* c) {
   CHECK_CTX(c);
+  VO_TRY(sync_stream(c->la));
   return sync_stream(c);
 }
 
@@ -1653,10 +1791,13 @@ int vo_profile_enable(vo_ctx* c, int mask) {
   CHECK_CTX(c);
   VO_TRY(sync_stream(c));
   VO_TRY(sync_stream(c->aux));
+  VO_TRY(sync_stream(c->la));
   prof_drain(c);
   prof_drain(c->aux);
+  prof_drain(c->la);
   c->prof.mask = (unsigned)mask;
   c->aux->prof.mask = (unsigned)mask;
+  c->la->prof.mask = (unsigned)mask;
   return VO_OK;
 }
 
@@ -1665,13 +1806,15 @@ int vo_profile_read(vo_ctx* c, int kernel, int64_t* launches, double* ms, int re
   if (kernel < 0 || kernel >= VO_K_COUNT) return VO_ERR_INVALID_ARG;
   VO_TRY(sync_stream(c));
   VO_TRY(sync_stream(c->aux));
+  VO_TRY(sync_stream(c->la));
   prof_drain(c);
   prof_drain(c->aux);
-  if (launches) *launches = c->prof.launches[kernel] + c->aux->prof.launches[kernel];
-  if (ms) *ms = c->prof.ms[kernel] + c->aux->prof.ms[kernel];
+  prof_drain(c->la);
+  if (launches) *launches = c->prof.launches[kernel] + c->aux->prof.launches[kernel] + c->la->prof.launches[kernel];
+  if (ms) *ms = c->prof.ms[kernel] + c->aux->prof.ms[kernel] + c->la->prof.ms[kernel];
   if (reset) {
-    c->prof.launches[kernel] = c->aux->prof.launches[kernel] = 0;
-    c->prof.ms[kernel] = c->aux->prof.ms[kernel] = 0;
+    c->prof.launches[kernel] = c->aux->prof.launches[kernel] = c->la->prof.launches[kernel] = 0;
+    c->prof.ms[kernel] = c->aux->prof.ms[kernel] = c->la->prof.ms[kernel] = 0;
   }
   return VO_OK;
 }
@@ -1681,12 +1824,13 @@ int vo_debug_timeline(vo_ctx* c, float* rows, int cap, int* n) {
   if (!rows || !n) return VO_ERR_INVALID_ARG;
   VO_TRY(sync_stream(c));
   VO_TRY(sync_stream(c->aux));
+  VO_TRY(sync_stream(c->la));
   *n = 0;
   cudaEvent_t t0 = nullptr;
   if (!c->prof.pending.empty()) t0 = c->prof.pending.front().a;
   if (!t0) return VO_OK;
   int chain = 0;
-  for (vo_ctx* k : {c, c->aux}) {
+  for (vo_ctx* k : {c, c->aux, c->la}) {
     for (auto& pe : k->prof.pending) {
       if (*n >= cap) break;
       float st = 0, du = 0;
@@ -1702,12 +1846,14 @@ int vo_debug_timeline(vo_ctx* c, float* rows, int cap, int* n) {
   return VO_OK;
 }
 
-int64_t vo_launch_count(vo_ctx* c) { return c ? c->launch_count + (c->aux ? c->aux->launch_count : 0) : 0; }
+int64_t vo_launch_count(vo_ctx* c) {
+  return c ? c->launch_count + (c->aux ? c->aux->launch_count : 0) + (c->la ? c->la->launch_count : 0) : 0;
+}
 
 int vo_lk_work(vo_ctx* c, int64_t* point_levels, int64_t* iterations) {
   CHECK_CTX(c);
   int64_t pl = 0, it = 0;
-  for (vo_ctx* k : {c, c->aux}) {
+  for (vo_ctx* k : {c, c->aux, c->la}) {
     VO_CUDA(cudaMemcpyAsync(k->h_lk_work, k->d_lk_work, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, k->stream));
     VO_TRY(sync_stream(k));
     pl += (int64_t)k->h_lk_work[0];
@@ -1727,7 +1873,7 @@ int vo_measure_int32_peak(vo_ctx* c, double* tops) {
 int vo_lk_slow_paths(vo_ctx* c, int64_t* window_sums, int64_t* iterations) {
   CHECK_CTX(c);
   int64_t a = 0, b = 0;
-  for (vo_ctx* k : {c, c->aux}) {
+  for (vo_ctx* k : {c, c->aux, c->la}) {
     VO_CUDA(cudaMemcpyAsync(k->h_lk_work, k->d_lk_work, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, k->stream));
     VO_TRY(sync_stream(k));
     a += (int64_t)k->h_lk_work[2];

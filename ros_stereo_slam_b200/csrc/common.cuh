@@ -104,9 +104,25 @@ struct vo_ctx {
   bool xform_pending = false;          // the last keyframe transform was enqueued without a final synchronisation
   cudaEvent_t ev_lk_done = nullptr;    // when set, track_pnp_fused_enqueue records it right after its LK launch
 
-  // image staging + pyramids: slot 0/1 ping-pong left images (reference <-> current), slot 2 right
+  // Look-ahead (vo_seq_announce / vo_seq_prefetch + a keyframe on every frame): the NEXT frame's temporal LK does
+  // not depend on this frame's pose, only on this keyframe's 2-D points -- it runs on a third chain (`la`) as soon
+  // as the stereo LK of this frame has its survivors, under the RANSAC solvers of the tracking chain, on ALL
+  // survivors; the next call gathers the F-RANSAC inliers' tracks from it (LK is independent per point, so the
+  // numbers are those of the in-frame launch).
+  vo_ctx* la = nullptr;
+  bool la_inflight = false;          // a look-ahead was enqueued during the previous vo_seq_track call
+  bool la_valid = false;             // ... and la->d_xy_trk / d_status hold the tracks of `la_left`
+  const uint8_t* la_left = nullptr;  // identity of that image: the pointer the caller announced
+  int la_m = 0;                      // points it ran on (stereo-LK survivors, order of aux->d_c_ref)
+  cudaEvent_t ev_la = nullptr, ev_gather = nullptr, ev_slk = nullptr;
+  const uint8_t* ann_left = nullptr;  // frame announced as DEVICE-resident (vo_seq_announce)
+  const uint8_t* ann_right = nullptr;
+  int ann_stride = 0;
+  bool pf_by_worker = false;         // this call's prefetch copies are issued by the stereo worker thread
+
+  // image staging + pyramids: slots 0/1/3 rotate through the left images (reference, current, look-ahead), slot 2 right
   uint8_t* d_raw[3] = {nullptr, nullptr, nullptr};
-  vo::Pyramid* pyr = nullptr;   // 3 slots, owned by the primary chain, shared with aux
+  vo::Pyramid* pyr = nullptr;   // 4 slots, owned by the primary chain, shared with the other chains
   uint64_t stamp_counter = 0;
 
   // point buffers (capacity max_points)
@@ -231,6 +247,9 @@ int grid_launch(vo_ctx* c, int rows, int cols, int step, float2* d_xy, int* n_ou
 // order-preserving compaction of up to three parallel arrays by flag==1; count -> d_count[slot]
 int compact_launch(vo_ctx* c, const uint8_t* d_flags, int n, const float2* a_in, float2* a_out, const float2* b_in,
                    float2* b_out, const float3* c_in, float3* c_out, int32_t* idx_out, int count_slot);
+// tracks of the points idx[0..n) gathered from another launch's outputs (look-ahead LK): out[j] = in[idx[j]]
+int gather_tracks_launch(vo_ctx* c, const int32_t* d_idx, int n, const float2* trk_in, const uint8_t* st_in, float2* trk_out,
+                         uint8_t* st_out);
 int triangulate_launch(vo_ctx* c, const double* d_P1P2, const float2* a, const float2* b, int n, float3* out,
                        const double* d_M /*nullable: fused rigid transform -> out2*/, float3* out2);
 int transform_launch(vo_ctx* c, const double* d_M, const float3* in, int n, float3* out);

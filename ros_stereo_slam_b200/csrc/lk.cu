@@ -1161,6 +1161,24 @@ int lk_launch(vo_ctx* c, int slot_prev, int slot_next, const float2* d_prev, int
   const float eps_lo = (float)(eps * (1.0 - 1e-5)), eps_hi = (float)(eps * (1.0 + 1e-5));
   static const bool use_v1 = getenv("VO_LK_V1") != nullptr;   // A/B baseline only (profiling)
   static const int variant = getenv("VO_LK_MINB") ? atoi(getenv("VO_LK_MINB")) : 4;
+  // experiment: cap the resident LK blocks per SM with a dynamic shared-memory request, so that the register file
+  // keeps room for the latency-bound solver kernels of the other chain
+  static const int maxblk = getenv("VO_LK_MAXBLK") ? atoi(getenv("VO_LK_MAXBLK")) : 0;
+  static const int maxblk_aux_only = getenv("VO_LK_MAXBLK_AUX") ? atoi(getenv("VO_LK_MAXBLK_AUX")) : 0;
+  size_t dyn = 0;
+  {
+    const int mb = c->is_aux ? (maxblk_aux_only ? maxblk_aux_only : maxblk) : maxblk;
+    if (mb > 0) {
+      const size_t per = (size_t)(227 * 1024) / (mb + 1) + 1024;     // more than 1/(mb+1) of the SM's shared memory
+      const size_t stat = LK_WARPS * WARP_WORDS * 4;
+      dyn = per > stat ? per - stat : 0;
+      static bool attr_set = false;
+      if (!attr_set) {
+        cudaFuncSetAttribute(lk_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set = true;
+      }
+    }
+  }
   {
     LaunchScope ls(c, VO_K_LK);
     if (c->p.channels == 3 && use_v1)
@@ -1176,7 +1194,7 @@ int lk_launch(vo_ctx* c, int slot_prev, int slot_next, const float2* d_prev, int
                                                        d_next, d_status, d_err, max_iters, eps, (float)c->p.lk_min_eig,
                                                        c->d_lk_work, c->n_dev);
     else if (variant == 4)
-      lk_kernel<4><<<blocks, threads, 0, c->stream>>>(pyr_view(c->pyr[slot_prev]), pyr_view(c->pyr[slot_next]), d_prev, n,
+      lk_kernel<4><<<blocks, threads, dyn, c->stream>>>(pyr_view(c->pyr[slot_prev]), pyr_view(c->pyr[slot_next]), d_prev, n,
                                                       d_next, d_status, d_err, max_iters, eps, eps_lo, eps_hi,
                                                       (float)c->p.lk_min_eig, c->d_lk_work, c->n_dev);
     else if (variant == 5)

@@ -143,6 +143,28 @@ int compact_launch(vo_ctx* c, const uint8_t* d_flags, int n, const float2* a_in,
   return VO_OK;
 }
 
+// ---------------------------------------------------------------------------- look-ahead gather
+__global__ void __launch_bounds__(256)
+gather_tracks_kernel(const int32_t* __restrict__ idx, int n, const float2* __restrict__ trk_in, const uint8_t* __restrict__ st_in,
+                     float2* __restrict__ trk_out, uint8_t* __restrict__ st_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int j = idx[i];
+  trk_out[i] = trk_in[j];
+  st_out[i] = st_in[j];
+}
+
+int gather_tracks_launch(vo_ctx* c, const int32_t* d_idx, int n, const float2* trk_in, const uint8_t* st_in, float2* trk_out,
+                         uint8_t* st_out) {
+  if (n <= 0) return VO_OK;
+  {
+    LaunchScope ls(c, VO_K_COMPACT);
+    gather_tracks_kernel<<<div_up(n, 256), 256, 0, c->stream>>>(d_idx, n, trk_in, st_in, trk_out, st_out);
+  }
+  VO_CUDA(cudaGetLastError());
+  return VO_OK;
+}
+
 // ---------------------------------------------------------------------------- triangulation
 // One thread per correspondence: 4x4 DLT matrix in FP64, OpenCV's Jacobi SVD (bit-exact
 // operation order, cvmath.cuh), last right-singular vector -> float -> divide by w in

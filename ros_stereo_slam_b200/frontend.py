@@ -454,6 +454,11 @@ class VisualFrontEnd:
         self._prefetched = (a, b)            # keep them alive until they are consumed
         check(self.lib.vo_seq_prefetch(self.h, _p(a), _p(b), a.strides[0]))
 
+    def seq_announce(self, left, right, stride=None):
+        """Announce the next frame's DEVICE-resident images (vo_seq_announce); pass the same pointers to seq_track."""
+        check(self.lib.vo_seq_announce(self.h, C.c_void_p(left), C.c_void_p(right) if right else None,
+                                       stride or self.params.width * self.params.channels, 1))
+
     def seq_track(self, left, right=None, is_device=False, stride=None, force_keyframe=False):
         res = VoFrameResult()
         if is_device:

@@ -612,9 +612,8 @@ def test_textureless_first_frame_on_a_fresh_context():
         f.close()
     f = make_frontend()
     pts = glue.dense_keypoint_extractor(376, 1241, 30)
-    with pytest.raises(Exception) as e:
-        f.PerspectiveNpointEstimation(flat, flat, pts, np.ones((len(pts), 3), np.float32))
-    assert "LOW_INLIERS" in str(e.value) or "TOO_FEW" in str(e.value) or "NO_MODEL" in str(e.value)
+    res = f.PerspectiveNpointEstimation(flat, flat, pts, np.ones((len(pts), 3), np.float32))
+    assert res["shutdown"] and len(res["trk2d"]) == 0 and len(res["inliers"]) == 0      # the reference's SHUTDOWN_FLAG
     # the context is still healthy afterwards
     g = golden()
     xyz, ref2d = f.stereoTriangulate(g["L0"], g["R0"])
@@ -657,3 +656,67 @@ def test_wrapper_rejects_images_of_another_geometry(fe, G):
     p, st, _ = fe.calcOpticalFlowPyrLK(wide[:, :1241], G["L1"], glue.dense_keypoint_extractor(376, 1241, 30))
     p0, st0, _ = fe.calcOpticalFlowPyrLK(G["L0"], G["L1"], glue.dense_keypoint_extractor(376, 1241, 30))
     assert np.array_equal(st, st0) and np.array_equal(p, p0)
+
+
+@pytest.mark.parametrize("channels", [1, 3])
+def test_lookahead_changes_the_schedule_not_the_numbers(channels):
+    """Keyframe on every frame + an announced next frame: its temporal LK runs one call early on the look-ahead chain
+    (all stereo-LK survivors, inliers gathered afterwards).  Every per-frame result and the final reference set must be
+    identical to the run without announcements, for device-resident (vo_seq_announce) and host (vo_seq_prefetch)
+    frames, and when the caller then passes a DIFFERENT frame than the one it announced."""
+    import ctypes as C
+    from ros_stereo_slam_b200 import _lib
+    sc = synth.Scene(4)
+    n = 7
+    Ls = [sc.render(i, "L") for i in range(n)]
+    Rs = [sc.render(i, "R") for i in range(n)]
+    if channels == 3:
+        Ls = [cv2.cvtColor(x, cv2.COLOR_GRAY2BGR) for x in Ls]
+        Rs = [cv2.cvtColor(x, cv2.COLOR_GRAY2BGR) for x in Rs]
+
+    def fields(res):
+        return (res.n_lk_in, res.n_tracked, res.n_inliers, res.attempt_used, res.keyframe, res.n_kf_points,
+                res.n_lk_in_stereo, tuple(res.rvec), tuple(res.tvec), tuple(res.pose3x4))
+
+    order = [1, 2, 3, 5, 4, 6]          # frame 5 arrives where 4 was announced: that look-ahead is discarded
+
+    def run(mode):
+        fe = make_frontend(kf_min_inliers=2 ** 31 - 1, channels=channels, grid_step=9)
+        nb = Ls[0].nbytes
+        d = C.c_void_p()
+        if mode == "device":
+            _lib.check(fe.lib.vo_alloc_dev(fe.h, C.byref(d), C.c_uint64(2 * n * nb)))
+            for i in range(n):
+                for e, img in enumerate((Ls[i], Rs[i])):
+                    _lib.check(fe.lib.vo_memcpy_h2d(fe.h, C.c_void_p(d.value + (2 * i + e) * nb), img.ctypes.data_as(C.c_void_p), C.c_uint64(nb)))
+        dp = lambda i, e: d.value + (2 * i + e) * nb
+        stride = Ls[0].strides[0]
+        if mode == "device":
+            fe.seq_init(dp(0, 0), dp(0, 1), is_device=True, stride=stride)
+        else:
+            fe.seq_init(Ls[0], Rs[0])
+        rows = []
+        for j, i in enumerate(order):
+            announced = i + 1 if j + 1 < len(order) and i + 1 < n else None     # always the NEXT INDEX, not the next in `order`
+            if announced is not None and mode == "device":
+                fe.seq_announce(dp(announced, 0), dp(announced, 1), stride)
+            elif announced is not None and mode == "host":
+                fe.seq_prefetch(Ls[announced], Rs[announced])
+            if mode == "device":
+                res, code = fe.seq_track(dp(i, 0), dp(i, 1), is_device=True, stride=stride)
+            else:
+                res, code = fe.seq_track(Ls[i], Rs[i])
+            assert code == 0
+            rows.append(fields(res))
+        ref = fe.seq_reference()
+        launches = fe.launch_count()
+        if mode == "device":
+            fe.lib.vo_free_dev(fe.h, d)
+        fe.close()
+        return rows, ref, launches
+
+    plain = run("plain")
+    for mode in ("device", "host"):
+        got = run(mode)
+        assert got[0] == plain[0], mode
+        assert np.array_equal(got[1][0], plain[1][0]) and np.array_equal(got[1][1], plain[1][1]), mode

@@ -13,10 +13,15 @@ for i in range(8):
 Ls = [d.value + (2 * i) * W * H for i in range(8)]
 Rs = [d.value + (2 * i + 1) * W * H for i in range(8)]
 fe.seq_init(Ls[0], Rs[0], is_device=True)
+ANN = os.environ.get("VO_TIMELINE_ANNOUNCE", "1") == "1"
 for i in range(1, 6):
+    if ANN:
+        fe.seq_announce(Ls[i + 1], Rs[i + 1])
     fe.seq_track(Ls[i], Rs[i], is_device=True)
 fe.profile_enable("all"); fe.profile_read(reset=True)
 import time
+if ANN:
+    fe.seq_announce(Ls[7], Rs[7])
 t0 = time.perf_counter(); fe.seq_track(Ls[6], Rs[6], is_device=True); dt = time.perf_counter() - t0
 rows = np.zeros((512, 4), np.float32); n = C.c_int()
 _lib.check(fe.lib.vo_debug_timeline(fe.h, rows.ctypes.data_as(C.c_void_p), 512, C.byref(n)))
