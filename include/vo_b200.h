@@ -52,7 +52,11 @@ enum {
   VO_ERR_SELF_CHECK = -9      /* device numerics differ from the IEEE host evaluation of the same code */
 };
 
-/* minimal solvers for vo_pnp_ransac */
+/* minimal solvers for vo_pnp_ransac.  EPNP5 = what cv::solvePnPRansac uses with the reference's (default) flags:
+ * RANSAC over 5-point EPnP samples for n >= 6; for n == 5 / n == 4 OpenCV solves once on all points (EPnP / P3P),
+ * keeps every point as an inlier and does not refine -- so does this library.  P3P4 names that four-point solver
+ * explicitly and is accepted for n == 4 only (RANSAC over P3P samples is cv::solvePnPRansac(flags = SOLVEPNP_P3P),
+ * which the reference never calls: VO_ERR_INVALID_ARG). */
 enum { VO_PNP_EPNP5 = 0, VO_PNP_P3P4 = 1 };
 
 typedef struct vo_ctx vo_ctx;
@@ -136,8 +140,11 @@ int vo_debug_pyramid_padded(vo_ctx* ctx, const uint8_t* img, int stride, int lev
  * src/tracking.cpp:34 (thr 3.0) and :75 (thr 1.0).
  * samples7: NULL -> OpenCV's RNG stream (seed 0xFFFFFFFFFFFFFFFF) incl. the collinearity
  * subset check; else an n_samples x 7 replay list of accepted subsets.  mask receives n
- * bytes (0/1); F (row-major 3x3) and n_inliers may be NULL.  Requires n >= 15 (below that
- * OpenCV switches estimator; VO_ERR_TOO_FEW_POINTS). */
+ * bytes (0/1); F (row-major 3x3) and n_inliers may be NULL.  Below 15 points OpenCV does not run
+ * RANSAC and neither does this call: 8 <= n <= 14 -> OpenCV's LMedS estimator (a fixed number of 7-point
+ * samples, smallest median error, mask = err <= sigma^2; thr is not used), n == 7 -> the raw 7-point result
+ * (its first solution in F) with a mask of ones, n < 7 -> VO_ERR_TOO_FEW_POINTS (OpenCV returns an empty
+ * matrix and no mask). */
 int vo_fmat_ransac(vo_ctx* ctx, const float* xy1, const float* xy2, int n, double thr, double conf,
                    const int32_t* samples7, int n_samples, uint8_t* mask, double F[9], int* n_inliers);
 
@@ -150,7 +157,8 @@ int vo_triangulate(vo_ctx* ctx, const double P1[12], const double P2[12],
  * src/keyFrameManagement.cpp:84,88.  K comes from the ctx params.  samples: NULL -> OpenCV's
  * RNG stream; else n_samples x 5 (EPNP5) or x 4 (P3P4) replay list.  inliers receives up to
  * cap ascending indices of the best model's inliers (before refinement, as OpenCV);
- * rvec/tvec are the LM-refined pose. */
+ * rvec/tvec are the LM-refined pose.  n == 5 / n == 4: the direct solve described at VO_PNP_*; n < 4:
+ * VO_ERR_TOO_FEW_POINTS (OpenCV asserts). */
 int vo_pnp_ransac(vo_ctx* ctx, const float* xyz, const float* xy, int n, int iters, double thr, double conf,
                   int min_solver, const int32_t* samples, int n_samples,
                   double rvec[3], double tvec[3], int32_t* inliers, int cap, int* n_inl);

@@ -100,6 +100,43 @@ def fmat_error(F, m1, m2):
     return err.astype(np.float32)
 
 
+def fmat_lmeds(m1, m2, conf=0.99, max_iters=1000):
+    """findFundamentalMat(m1, m2, FM_RANSAC, ...) for 8 <= N <= 14 points: OpenCV does not run RANSAC there but
+    LMeDSPointSetRegistrator::run (calib3d fundam.cpp / ptsetreg.cpp): a fixed number of 7-point samples
+    (RANSACUpdateNumIters(conf, 0.45, 7, maxIters)), the model with the smallest MEDIAN error wins (first one on
+    ties), sigma = 2.5*1.4826*(1 + 5/(N-7))*sqrt(median) (>= 0.001), mask = err <= sigma^2.
+    For N <= 13 the median is taken among the seven sample points themselves (errors ~1e-27): the winner is decided
+    by rounding noise, in OpenCV too.  Returns (F or None, mask)."""
+    m1 = np.ascontiguousarray(m1, np.float32)
+    m2 = np.ascontiguousarray(m2, np.float32)
+    n = len(m1)
+    assert 8 <= n <= 14
+    rng = CvRNG(RANSAC_SEED)
+    niters = ransac_update_num_iters(conf, 0.45, 7, max_iters)
+    best, min_med = None, np.inf
+    for _ in range(niters):
+        idx = None
+        for _att in range(10000):
+            cand = draw_subset(rng, n, 7)
+            if fmat_check_subset(m1, m2, cand):
+                idx = cand
+                break
+        if idx is None:
+            break
+        for F in fmat_7point_models(m1[idx], m2[idx]):
+            s_err = np.sort(fmat_error(F, m1, m2))
+            med = float(s_err[n // 2]) if n % 2 else float(np.float32(s_err[n // 2 - 1] + s_err[n // 2])) * 0.5
+            if med < min_med:
+                min_med, best = med, F
+    if best is None:
+        return None, np.zeros(n, np.uint8)
+    sigma = max(2.5 * 1.4826 * (1 + 5.0 / (n - 7)) * np.sqrt(min_med), 0.001)
+    mask = (fmat_error(best, m1, m2) <= np.float32(sigma * sigma)).astype(np.uint8)
+    if mask.sum() < 7:
+        return None, np.zeros(n, np.uint8)
+    return best, mask
+
+
 def fmat_ransac(m1, m2, thr, conf, max_iters=1000, samples=None, exhaustive=False):
     """findFundamentalMat(m1, m2, FM_RANSAC, thr, conf) for N >= 15 points.
 

@@ -2,6 +2,7 @@
 // (the reference's method boundaries, include/visualSLAM.h:152-169 of the reference tree),
 // OpenCV-compatible RANSAC sample generation, and the device-resident sequence driver.
 // No CPU compute path exists: every stage launches the CUDA kernels of this library.
+#include <float.h>
 #include <math.h>
 #include <stdarg.h>
 
@@ -518,6 +519,62 @@ static int draw_fmat_samples(CvRng& rng, const float* m1, const float* m2, int n
   return want;
 }
 
+// cv::RANSACUpdateNumIters on the host (the LMedS estimator fixes its sample count with it)
+static int host_update_num_iters(double p, double ep, int model_points, int max_iters) {
+  p = std::max(p, 0.);
+  p = std::min(p, 1.);
+  ep = std::max(ep, 0.);
+  ep = std::min(ep, 1.);
+  double num = std::max(1. - p, DBL_MIN);
+  double denom = 1. - pow(1. - ep, (double)model_points);
+  if (denom < DBL_MIN) return 0;
+  num = log(num);
+  denom = log(denom);
+  return denom >= 0 || -num >= max_iters * (-denom) ? max_iters : (int)rint(num / denom);
+}
+
+// findFundamentalMat(FM_RANSAC) below 15 points (calib3d fundam.cpp): N == 7 -> the raw 7-point result and a mask of
+// ones; 8 <= N <= 14 -> OpenCV's LMedS estimator (ransac.cu, fmat_lmeds_kernel).  Same outputs as run_fmat.
+static int run_fmat_small(vo_ctx* c, const float2* m1, const float2* m2, int n, double conf, const int32_t* replay,
+                          int n_replay, const float* h_m1, const float* h_m2, const std::function<int()>& tail) {
+  int H = 1;
+  if (n == 7) {
+    for (int i = 0; i < 7; i++) c->h_samples[i] = i;
+  } else {
+    double cf = conf;
+    if (cf < DBL_EPSILON || cf > 1 - DBL_EPSILON) cf = 0.99;
+    H = replay ? n_replay : host_update_num_iters(cf, 0.45, 7, std::max(c->p.f_max_iters, 1));
+    if (H > c->cap_h) {
+      set_error("%d LMedS samples exceed max_hypotheses %d", H, c->cap_h);
+      return VO_ERR_CAPACITY;
+    }
+    if (replay) {
+      memcpy(c->h_samples, replay, (size_t)H * 7 * sizeof(int32_t));
+      for (int i = 0; i < H * 7; i++)
+        if (c->h_samples[i] < 0 || c->h_samples[i] >= n) {
+          set_error("replay sample index out of range");
+          return VO_ERR_INVALID_ARG;
+        }
+    } else {
+      CvRng rng(0xffffffffffffffffULL);
+      H = draw_fmat_samples(rng, h_m1, h_m2, n, H, c->h_samples);   // a failed getSubset ends OpenCV's loop
+    }
+  }
+  if (H <= 0) {
+    set_error("findFundamentalMat: no admissible 7-point subset");
+    return VO_ERR_NO_MODEL;
+  }
+  VO_CUDA(cudaMemcpyAsync(c->d_samples, c->h_samples, (size_t)H * 7 * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+  VO_TRY(fmat_solve_launch(c, m1, m2, c->d_samples, H, c->d_models, c->d_counts));
+  if (n == 7) VO_TRY(fmat_seven_launch(c, c->d_counts, n, c->d_sel, c->d_mask));
+  else VO_TRY(fmat_lmeds_launch(c, m1, m2, n, c->d_models, c->d_counts, 3 * H, c->d_sel, c->d_mask));
+  if (tail) VO_TRY(tail());
+  VO_CUDA(cudaMemcpyAsync(c->h_sel, c->d_sel, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  VO_TRY(sync_stream(c));
+  c->last_f_h = H;
+  return VO_OK;
+}
+
 // ------------------------------------------------------------------------------------ F-RANSAC
 // Device inputs m1, m2 (n points).  h_m1/h_m2: host copies for the collinearity check (unused
 // with a replay list).  On return d_sel holds (best, niters, best_count, records), d_mask the
@@ -529,10 +586,12 @@ static int draw_fmat_samples(CvRng& rng, const float* m1, const float* m2, int n
 static int run_fmat(vo_ctx* c, const float2* m1, const float2* m2, int n, double thr, double conf,
                     const int32_t* replay, int n_replay, const float* h_m1, const float* h_m2,
                     const std::function<int()>& tail = nullptr) {
-  if (n < 15) {
-    set_error("findFundamentalMat(FM_RANSAC) with %d < 15 points switches estimator in OpenCV; not supported", n);
+  if (n < 7) {
+    // OpenCV returns an empty matrix and leaves the mask untouched; the reference would then index an empty mask
+    set_error("findFundamentalMat with %d < 7 points: OpenCV returns no model", n);
     return VO_ERR_TOO_FEW_POINTS;
   }
+  if (n < 15) return run_fmat_small(c, m1, m2, n, conf, replay, n_replay, h_m1, h_m2, tail);
   const int max_iters = std::max(c->p.f_max_iters, 1);
   const int H = replay ? n_replay : max_iters;
   if (H > c->cap_h) {
@@ -592,13 +651,32 @@ static int run_fmat(vo_ctx* c, const float2* m1, const float2* m2, int n, double
 static int run_pnp(vo_ctx* c, const float3* xyz, const float2* xy, int n, int iters, double thr, double conf,
                    int min_solver, const int32_t* replay, int n_replay, int* n_inl_out) {
   *n_inl_out = 0;
-  if (min_solver != VO_PNP_EPNP5) {
-    set_error("P3P minimal solver (only used by OpenCV when N == 4) is not implemented");
-    return VO_ERR_NOT_IMPLEMENTED;
+  if (min_solver != VO_PNP_EPNP5 && min_solver != VO_PNP_P3P4) return VO_ERR_INVALID_ARG;
+  if (n < 4) {
+    // OpenCV: CV_Assert(npoints >= 4) -- an uncaught cv::Exception in the reference
+    set_error("solvePnPRansac needs at least 4 points, got %d", n);
+    return VO_ERR_TOO_FEW_POINTS;
+  }
+  if (min_solver == VO_PNP_P3P4 && n != 4) {
+    set_error("VO_PNP_P3P4 is OpenCV's choice for exactly four points (solvePnPRansac with default flags); RANSAC over "
+              "P3P samples (flags = SOLVEPNP_P3P, which the reference never passes) is outside this library");
+    return VO_ERR_INVALID_ARG;
   }
   if (n <= 5) {
-    set_error("solvePnPRansac with %d <= 5 points takes OpenCV's non-RANSAC path; not supported", n);
-    return VO_ERR_TOO_FEW_POINTS;
+    // the minimal sample is the whole set: OpenCV solves once (P3P for 4, EPnP for 5), keeps every point as an
+    // inlier and does not refine (calib3d solvepnp.cpp, `model_points == npoints`)
+    VO_TRY(pnp_direct_launch(c, xyz, xy, n, c->d_samples, c->d_models, c->d_counts, c->d_sel, c->d_idx, c->d_count + 4,
+                             c->d_pose));
+    VO_CUDA(cudaMemcpyAsync(c->h_sel, c->d_sel, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    VO_CUDA(cudaMemcpyAsync(c->h_pose, c->d_pose, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    VO_TRY(read_counts(c));
+    c->last_pnp_h = 1;
+    if (c->h_sel[0] < 0) {
+      set_error("solvePnP: no pose from %d points", n);
+      return VO_ERR_NO_MODEL;
+    }
+    *n_inl_out = c->h_count[4];
+    return VO_OK;
   }
   const int max_iters = std::max(iters, 1);
   const int H = replay ? n_replay : max_iters;

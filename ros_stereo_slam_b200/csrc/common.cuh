@@ -266,6 +266,13 @@ int pnp_score_launch(vo_ctx* c, const float3* xyz, const float2* xy, int n, cons
                      int h, float thr2);
 int pnp_mask_launch(vo_ctx* c, const float3* xyz, const float2* xy, int n, const double* d_models, const int* d_sel,
                     float thr2, uint8_t* d_mask);
+// solvePnPRansac with 4 or 5 points: the direct solve (P3P / EPnP on all points), every point an inlier, no refinement
+int pnp_direct_launch(vo_ctx* c, const float3* xyz, const float2* xy, int n, int32_t* d_samples, double* d_models,
+                      int32_t* d_counts, int* d_sel, int32_t* d_idx, int* d_n_inl, double* d_pose);
+// findFundamentalMat's small-N estimators: LMedS for 8..14 points, the raw 7-point result for 7
+int fmat_lmeds_launch(vo_ctx* c, const float2* m1, const float2* m2, int n, const double* d_models, const int32_t* d_counts,
+                      int n_models, int* d_sel, uint8_t* d_mask);
+int fmat_seven_launch(vo_ctx* c, const int32_t* d_counts, int n, int* d_sel, uint8_t* d_mask);
 // RANSAC record-setter scan: counts[n_models] (flattened, models_per_sample each) -> d_sel
 constexpr int RNG_LEN = 1 << 17;
 // device-side minimal-sample generation (OpenCV getSubset semantics); M = 7 checks collinearity

@@ -650,6 +650,347 @@ int pnp_mask_launch(vo_ctx* c, const float3* xyz, const float2* xy, int n, const
   return VO_OK;
 }
 
+// ================================================================ four and five points
+// cv::solvePnPRansac does not run RANSAC when the minimal sample is the whole set (calib3d solvepnp.cpp,
+// `model_points == npoints`): five points -> solvePnP(EPNP) on all of them, four points -> solvePnP(P3P) (three points
+// give up to four poses, the fourth picks the one with the smallest reprojection error); the inlier list is every
+// point and no refinement follows.  The five-point case is pnp_solve_kernel on the sample (0..4).  For four points:
+// Grunert's formulation with the distance ratios u = s2/s1, v = s3/s1, which leaves one quartic in v (coefficients by
+// polynomial arithmetic, roots by Durand-Kerner + Newton); the pose follows from the two orthonormal frames spanned
+// by the triangle in world and camera coordinates.  OpenCV's own P3P code is a different formulation of the same
+// equations: the poses agree to rounding, not bit for bit (tests: 1e-6 rad / 1e-6 m against cv2).
+__device__ void poly_mul(const double* a, int na, const double* b, int nb, double* out) {   // ascending powers
+  for (int i = 0; i <= na + nb; i++) out[i] = 0;
+  for (int i = 0; i <= na; i++)
+    for (int j = 0; j <= nb; j++) out[i + j] += a[i] * b[j];
+}
+
+__device__ int quartic_real_roots(const double c[5], double roots[4]) {
+  // degree handling: a vanishing leading coefficient (degenerate geometry) lowers the degree
+  int deg = 4;
+  double scale = 0;
+  for (int i = 0; i <= 4; i++) scale = fmax(scale, fabs(c[i]));
+  if (scale == 0) return 0;
+  while (deg > 0 && fabs(c[deg]) < 1e-14 * scale) deg--;
+  if (deg == 0) return 0;
+  double a[5];
+  for (int i = 0; i <= deg; i++) a[i] = c[i] / c[deg];      // monic
+  double zr[4], zi[4];
+  // Durand-Kerner from points on a circle of the Cauchy bound
+  double bound = 0;
+  for (int i = 0; i < deg; i++) bound = fmax(bound, fabs(a[i]));
+  bound += 1;
+  for (int k = 0; k < deg; k++) {
+    const double ang = 0.4 + 6.283185307179586 * k / deg;
+    zr[k] = 0.5 * bound * cos(ang);
+    zi[k] = 0.5 * bound * sin(ang);
+  }
+  for (int it = 0; it < 200; it++) {
+    double change = 0;
+    for (int k = 0; k < deg; k++) {
+      double pr = 1, pi = 0;                      // p(z_k), Horner, monic
+      for (int i = deg - 1; i >= 0; i--) {
+        const double tr = pr * zr[k] - pi * zi[k] + a[i], ti = pr * zi[k] + pi * zr[k];
+        pr = tr;
+        pi = ti;
+      }
+      double qr = 1, qi = 0;                      // prod (z_k - z_j)
+      for (int j = 0; j < deg; j++)
+        if (j != k) {
+          const double dr = zr[k] - zr[j], di = zi[k] - zi[j];
+          const double tr = qr * dr - qi * di, ti = qr * di + qi * dr;
+          qr = tr;
+          qi = ti;
+        }
+      const double den = qr * qr + qi * qi;
+      if (den == 0) continue;
+      const double wr = (pr * qr + pi * qi) / den, wi = (pi * qr - pr * qi) / den;
+      zr[k] -= wr;
+      zi[k] -= wi;
+      change = fmax(change, fabs(wr) + fabs(wi));
+    }
+    if (change < 1e-15 * bound) break;
+  }
+  int n = 0;
+  for (int k = 0; k < deg; k++) {
+    if (fabs(zi[k]) > 1e-7 * (1 + fabs(zr[k]))) continue;
+    double x = zr[k];
+    for (int it = 0; it < 8; it++) {               // Newton polish on the real polynomial
+      double f = 1, d = 0;
+      for (int i = deg - 1; i >= 0; i--) {
+        d = d * x + f;
+        f = f * x + a[i];
+      }
+      if (d == 0) break;
+      x -= f / d;
+    }
+    roots[n++] = x;
+  }
+  return n;
+}
+
+// up to 4 poses (R row-major, t) from three correspondences; f = unit bearing vectors, P = world points
+__device__ int p3p_solve3(const double P[3][3], const double f[3][3], double Rs[4][9], double ts[4][3]) {
+  auto sub = [](const double* a, const double* b, double* o) { for (int i = 0; i < 3; i++) o[i] = a[i] - b[i]; };
+  auto dot = [](const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
+  auto cross = [](const double* a, const double* b, double* o) {
+    o[0] = a[1] * b[2] - a[2] * b[1];
+    o[1] = a[2] * b[0] - a[0] * b[2];
+    o[2] = a[0] * b[1] - a[1] * b[0];
+  };
+  double d[3];
+  sub(P[1], P[2], d); const double a2 = dot(d, d);
+  sub(P[0], P[2], d); const double b2 = dot(d, d);
+  sub(P[0], P[1], d); const double c2 = dot(d, d);
+  if (a2 == 0 || b2 == 0 || c2 == 0) return 0;
+  const double ca = dot(f[1], f[2]), cb = dot(f[0], f[2]), cg = dot(f[0], f[1]);
+  const double K1 = (a2 - c2) / b2, K2 = c2 / b2;
+  // u = N(v) / D(v);  D^2 + N^2 - 2 N D cos(gamma) - K2 (1 + v^2 - 2 v cos(beta)) D^2 = 0
+  const double N[3] = {1 + K1, -2 * K1 * cb, K1 - 1};
+  const double D[2] = {2 * cg, -2 * ca};
+  const double Q[3] = {1, -2 * cb, 1};
+  double D2[3], N2[5], ND[4], QD2[5], c[5];
+  poly_mul(D, 1, D, 1, D2);
+  poly_mul(N, 2, N, 2, N2);
+  poly_mul(N, 2, D, 1, ND);
+  poly_mul(Q, 2, D2, 2, QD2);
+  for (int i = 0; i < 5; i++) c[i] = N2[i] - K2 * QD2[i] + (i < 3 ? D2[i] : 0) - (i < 4 ? 2 * cg * ND[i] : 0);
+  double v[4];
+  const int nr = quartic_real_roots(c, v);
+  int ns = 0;
+  for (int r = 0; r < nr && ns < 4; r++) {
+    const double vv = v[r];
+    const double den = D[0] + D[1] * vv;
+    const double q = 1 + vv * vv - 2 * vv * cb;
+    if (fabs(den) < 1e-12 || q <= 0) continue;
+    const double uu = (N[0] + N[1] * vv + N[2] * vv * vv) / den;
+    const double s1 = sqrt(b2 / q);
+    const double s2 = uu * s1, s3 = vv * s1;
+    if (!(s2 > 0) || !(s3 > 0)) continue;
+    bool dup = false;                              // double roots of the quartic give the same pose twice
+    for (int k = 0; k < r; k++) dup |= fabs(v[k] - vv) < 1e-9 * (1 + fabs(vv));
+    if (dup) continue;
+    double C[3][3];
+    for (int i = 0; i < 3; i++) {
+      C[0][i] = s1 * f[0][i];
+      C[1][i] = s2 * f[1][i];
+      C[2][i] = s3 * f[2][i];
+    }
+    // orthonormal frames of the two triangles
+    double ep[3][3], ec[3][3], t1[3], t2[3];
+    for (int w = 0; w < 2; w++) {
+      const double(*X)[3] = w == 0 ? P : C;
+      double(*e)[3] = w == 0 ? ep : ec;
+      sub(X[1], X[0], t1);
+      sub(X[2], X[0], t2);
+      double n1 = sqrt(dot(t1, t1));
+      for (int i = 0; i < 3; i++) e[0][i] = t1[i] / n1;
+      cross(e[0], t2, e[2]);
+      double n3 = sqrt(dot(e[2], e[2]));
+      if (n3 == 0) return ns;                      // collinear points
+      for (int i = 0; i < 3; i++) e[2][i] /= n3;
+      cross(e[2], e[0], e[1]);
+    }
+    // R = Ec^T Ep  (maps world frame vectors to camera frame vectors)
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) Rs[ns][i * 3 + j] = ec[0][i] * ep[0][j] + ec[1][i] * ep[1][j] + ec[2][i] * ep[2][j];
+    for (int i = 0; i < 3; i++)
+      ts[ns][i] = C[0][i] - (Rs[ns][i * 3] * P[0][0] + Rs[ns][i * 3 + 1] * P[0][1] + Rs[ns][i * 3 + 2] * P[0][2]);
+    ns++;
+  }
+  return ns;
+}
+
+// model (PNP_STRIDE doubles, layout of pnp_solve_kernel) of the first four points; counts[0] = 0 or -1
+__global__ void pnp_p3p4_kernel(const float3* __restrict__ xyz, const float2* __restrict__ xy, Intrinsics K,
+                                double* __restrict__ models, int32_t* __restrict__ counts) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double P[3][3], f[3][3];
+  for (int i = 0; i < 3; i++) {
+    P[i][0] = xyz[i].x; P[i][1] = xyz[i].y; P[i][2] = xyz[i].z;
+    const double x = ((double)xy[i].x - K.cx) / K.fx, y = ((double)xy[i].y - K.cy) / K.fy;
+    const double nn = sqrt(x * x + y * y + 1);
+    f[i][0] = x / nn; f[i][1] = y / nn; f[i][2] = 1 / nn;
+  }
+  double Rs[4][9], ts[4][3];
+  const int n = p3p_solve3(P, f, Rs, ts);
+  int best = -1;
+  double best_e = 0;
+  const double X = xyz[3].x, Y = xyz[3].y, Z = xyz[3].z;
+  for (int i = 0; i < n; i++) {
+    const double xc = Rs[i][0] * X + Rs[i][1] * Y + Rs[i][2] * Z + ts[i][0];
+    const double yc = Rs[i][3] * X + Rs[i][4] * Y + Rs[i][5] * Z + ts[i][1];
+    const double zc = Rs[i][6] * X + Rs[i][7] * Y + Rs[i][8] * Z + ts[i][2];
+    const double u = K.cx + K.fx * xc / zc, v = K.cy + K.fy * yc / zc;
+    const double e = (u - xy[3].x) * (u - xy[3].x) + (v - xy[3].y) * (v - xy[3].y);
+    if (best < 0 || best_e > e) {
+      best = i;
+      best_e = e;
+    }
+  }
+  if (best < 0) {
+    counts[0] = -1;
+    return;
+  }
+  double rvec[3], R2[9];
+  rodrigues_mat2vec(Rs[best], rvec);
+  rodrigues_vec2mat(rvec, R2);
+  for (int i = 0; i < 3; i++) {
+    models[i] = rvec[i];
+    models[3 + i] = ts[best][i];
+  }
+  for (int i = 0; i < 9; i++) models[6 + i] = R2[i];
+  models[15] = 0;
+  counts[0] = 0;
+}
+
+// outputs of the direct (non-RANSAC) solve: every point is an inlier, the pose is the model itself
+__global__ void pnp_direct_finish_kernel(const double* __restrict__ models, const int32_t* __restrict__ counts, int n,
+                                         int* __restrict__ sel, int32_t* __restrict__ idx, int* __restrict__ n_inl,
+                                         double* __restrict__ pose) {
+  const int ok = counts[0] >= 0;
+  if (threadIdx.x < n) idx[threadIdx.x] = threadIdx.x;
+  if (threadIdx.x == 0) {
+    sel[0] = ok ? 0 : -1;
+    sel[1] = 1;
+    sel[2] = ok ? n : 0;
+    sel[3] = 1;
+    *n_inl = ok ? n : 0;
+    for (int i = 0; i < 6; i++) pose[i] = models[i];
+  }
+}
+
+int pnp_direct_launch(vo_ctx* c, const float3* xyz, const float2* xy, int n, int32_t* d_samples, double* d_models,
+                      int32_t* d_counts, int* d_sel, int32_t* d_idx, int* d_n_inl, double* d_pose) {
+  if (n == 5) {
+    const int32_t five[5] = {0, 1, 2, 3, 4};
+    VO_CUDA(cudaMemcpyAsync(d_samples, five, sizeof(five), cudaMemcpyHostToDevice, c->stream));
+    VO_TRY(pnp_solve_launch(c, xyz, xy, d_samples, 1, d_models, d_counts));
+  } else if (n == 4) {
+    LaunchScope ls(c, VO_K_PNP_SOLVE);
+    pnp_p3p4_kernel<<<1, 32, 0, c->stream>>>(xyz, xy, intr(c), d_models, d_counts);
+  } else {
+    return VO_ERR_INVALID_ARG;
+  }
+  {
+    LaunchScope ls(c, VO_K_SELECT);
+    pnp_direct_finish_kernel<<<1, 32, 0, c->stream>>>(d_models, d_counts, n, d_sel, d_idx, d_n_inl, d_pose);
+  }
+  VO_CUDA(cudaGetLastError());
+  return VO_OK;
+}
+
+// ================================================================ small point sets
+// cv::findFundamentalMat(FM_RANSAC) with 8 <= N <= 14 points does not run RANSAC: OpenCV switches to its LMedS
+// estimator (calib3d fundam.cpp: `(method & ~3) == FM_RANSAC && npoints >= 15`, else createLMeDSPointSetRegistrator).
+// LMeDSPointSetRegistrator::run: a FIXED number of samples (RANSACUpdateNumIters(conf, 0.45, 7, maxIters), drawn like
+// RANSAC's), every model's error vector is sorted, the model with the smallest median wins (first one on ties), then
+// sigma = 2.5 * 1.4826 * (1 + 5 / (N - 7)) * sqrt(median), at least 0.001, and the mask is err <= sigma^2.
+// One CTA: thread t handles the models t, t + blockDim, ...; errors are OpenCV's (fmat_err, float).
+constexpr int LMEDS_THREADS = 256;
+constexpr int LMEDS_MAX_N = 14;
+
+__global__ void __launch_bounds__(LMEDS_THREADS)
+fmat_lmeds_kernel(const float2* __restrict__ m1, const float2* __restrict__ m2, int n, const double* __restrict__ models,
+                  const int32_t* __restrict__ counts, int n_models, int* __restrict__ sel, uint8_t* __restrict__ mask) {
+  __shared__ double s_med[LMEDS_THREADS];
+  __shared__ int s_idx[LMEDS_THREADS];
+  __shared__ float2 s1[LMEDS_MAX_N], s2[LMEDS_MAX_N];
+  const int t = threadIdx.x;
+  if (t < n) {
+    s1[t] = m1[t];
+    s2[t] = m2[t];
+  }
+  __syncthreads();
+  double best = 1.7976931348623157e308;   // DBL_MAX: `median < minMedian` never accepts a NaN or an infinite median
+  int best_i = -1;
+  for (int m = t; m < n_models; m += blockDim.x) {
+    if (counts[m] < 0) continue;           // sample with fewer than 3 solutions
+    float e[LMEDS_MAX_N];
+    for (int i = 0; i < n; i++) e[i] = fmat_err(models + (size_t)m * F_STRIDE, s1[i], s2[i]);
+    // OpenCV sorts the float errors as int32 bit patterns (they are non-negative)
+    for (int i = 1; i < n; i++) {
+      const float v = e[i];
+      const int vi = __float_as_int(v);
+      int j = i - 1;
+      while (j >= 0 && __float_as_int(e[j]) > vi) {
+        e[j + 1] = e[j];
+        j--;
+      }
+      e[j + 1] = v;
+    }
+    const double med = (n & 1) ? (double)e[n / 2] : (double)__fadd_rn(e[n / 2 - 1], e[n / 2]) * 0.5;
+    if (med < best) {      // models of one thread are visited in increasing order: first minimum kept
+      best = med;
+      best_i = m;
+    }
+  }
+  s_med[t] = best;
+  s_idx[t] = best_i;
+  __syncthreads();
+  if (t == 0) {
+    double bm = 1.7976931348623157e308;
+    int bi = -1;
+    for (int k = 0; k < blockDim.x; k++) {
+      const int i = s_idx[k];
+      if (i < 0) continue;
+      if (s_med[k] < bm || (s_med[k] == bm && i < bi)) {   // the sequential loop keeps the FIRST model with the minimum
+        bm = s_med[k];
+        bi = i;
+      }
+    }
+    int good = 0;
+    if (bi >= 0) {
+      double sigma = 2.5 * 1.4826 * (1 + 5. / (n - 7)) * sqrt(bm);
+      sigma = sigma > 0.001 ? sigma : 0.001;
+      const float thr = (float)(sigma * sigma);
+      for (int i = 0; i < n; i++) {
+        const uint8_t f = fmat_err(models + (size_t)bi * F_STRIDE, s1[i], s2[i]) <= thr;
+        mask[i] = f;
+        good += f;
+      }
+      if (good < 7) bi = -1;               // LMeDS: result = count >= modelPoints
+    }
+    if (bi < 0)
+      for (int i = 0; i < n; i++) mask[i] = 0;
+    sel[0] = bi;
+    sel[1] = n_models / 3;
+    sel[2] = good;
+    sel[3] = 1;
+  }
+}
+
+int fmat_lmeds_launch(vo_ctx* c, const float2* m1, const float2* m2, int n, const double* d_models, const int32_t* d_counts,
+                      int n_models, int* d_sel, uint8_t* d_mask) {
+  if (n < 8 || n > LMEDS_MAX_N) return VO_ERR_INVALID_ARG;
+  {
+    LaunchScope ls(c, VO_K_SELECT);
+    fmat_lmeds_kernel<<<1, LMEDS_THREADS, 0, c->stream>>>(m1, m2, n, d_models, d_counts, n_models, d_sel, d_mask);
+  }
+  VO_CUDA(cudaGetLastError());
+  return VO_OK;
+}
+
+// N == 7: OpenCV returns the raw 7-point result and a mask of ones (fundam.cpp: `npoints == 7 -> cb->runKernel`)
+__global__ void fmat_seven_kernel(const int32_t* __restrict__ counts, int n, int* __restrict__ sel, uint8_t* __restrict__ mask) {
+  if (threadIdx.x < n) mask[threadIdx.x] = 1;
+  if (threadIdx.x == 0) {
+    sel[0] = counts[0] >= 0 ? 0 : -1;
+    sel[1] = 1;
+    sel[2] = n;
+    sel[3] = 1;
+  }
+}
+
+int fmat_seven_launch(vo_ctx* c, const int32_t* d_counts, int n, int* d_sel, uint8_t* d_mask) {
+  {
+    LaunchScope ls(c, VO_K_SELECT);
+    fmat_seven_kernel<<<1, 32, 0, c->stream>>>(d_counts, n, d_sel, d_mask);
+  }
+  VO_CUDA(cudaGetLastError());
+  return VO_OK;
+}
+
 int select_launch(vo_ctx* c, const int32_t* d_counts, int n_samples, int models_per_sample, int model_points,
                   int n_points, double conf, int max_iters, int* d_sel) {
   {

@@ -318,7 +318,7 @@ class VisualFrontEnd:
         check(self.lib.vo_triangulate(self.h, _p(P1), _p(P2), _p(a), _p(b), len(a), _p(out)))
         return out
 
-    def solvePnPRansac(self, pts3d, pts2d, iters=100, thr=1.0, conf=0.99, samples=None):
+    def solvePnPRansac(self, pts3d, pts2d, iters=100, thr=1.0, conf=0.99, samples=None, min_solver=None):
         """cv::solvePnPRansac(..., false, iters, thr, conf, inliers) -> dict(ok, rvec, tvec, inliers)."""
         X, x = _f32(pts3d, 3), _f32(pts2d, 2)
         n = len(X)
@@ -328,7 +328,7 @@ class VisualFrontEnd:
         ni = C.c_int()
         s = None if samples is None else np.ascontiguousarray(samples, np.int32).reshape(-1, 5)
         r = self.lib.vo_pnp_ransac(self.h, _p(X), _p(x), n, int(iters), C.c_double(thr), C.c_double(conf),
-                                   _lib.VO_PNP_EPNP5, _p(s), 0 if s is None else len(s),
+                                   _lib.VO_PNP_EPNP5 if min_solver is None else int(min_solver), _p(s), 0 if s is None else len(s),
                                    _p(rvec), _p(tvec), _p(inl), len(inl), C.byref(ni))
         check(r, (_lib.VO_OK, _lib.VO_ERR_NO_MODEL))
         return dict(ok=r == _lib.VO_OK, rvec=rvec, tvec=tvec, inliers=inl[:ni.value].copy())

@@ -71,3 +71,43 @@ def test_pnp_ransac_bit_identical(n, frac, iters, thr, conf):
     assert np.array_equal(r2["inliers"], r["inliers"]) and np.array_equal(r2["rvec"], r["rvec"])
     # the default sample list is OpenCV's RNG stream
     assert np.array_equal(cvrng.sample_list(n, 5, len(r["samples"])), r["samples"])
+
+
+def test_small_point_sets_follow_opencv():
+    """Below 15 points cv2.findFundamentalMat(FM_RANSAC) switches estimator: N == 7 -> 7-point result, mask of ones;
+    8..14 -> LMedS (restated in replay.fmat_lmeds); N < 7 -> nothing.  solvePnPRansac with 5 / 4 points is one
+    EPnP / P3P solve with every point an inlier."""
+    import cv2
+    from oracle import synth
+    sc = synth.Scene(0)
+    L0, L1 = sc.render(0, "L"), sc.render(1, "L")
+    pts = glue.dense_keypoint_extractor(376, 1241, 30)
+    p1, st, _ = cv2.calcOpticalFlowPyrLK(L0, L1, pts.reshape(-1, 1, 2), None)
+    ok = st.ravel() == 1
+    a, b = pts[ok], p1.reshape(-1, 2)[ok]
+    rng = np.random.default_rng(0)
+    same = total = 0
+    for n in range(8, 15):
+        for trial in range(4):
+            sel = rng.choice(len(a), n, replace=False)
+            x, y = a[sel].copy(), b[sel].copy()
+            if trial % 2:
+                y[:2] += rng.normal(0, 5, (2, 2)).astype(np.float32)
+            F, mask = cv2.findFundamentalMat(x, y, cv2.FM_RANSAC, 1.0, 0.99)
+            F2, m2 = replay.fmat_lmeds(x, y, 0.99)
+            total += 1
+            same += int(mask is not None and np.array_equal(mask.ravel(), m2))
+            if n == 14:     # the only size whose median involves a point outside the sample: not noise-decided
+                assert mask is not None and np.array_equal(mask.ravel(), m2)
+    assert same >= 0.85 * total, (same, total)
+    s7 = rng.choice(len(a), 7, replace=False)     # (the first grid points are collinear: OpenCV asserts on those)
+    F, mask = cv2.findFundamentalMat(a[s7], b[s7], cv2.FM_RANSAC, 1.0, 0.99)
+    assert F.shape[0] in (3, 6, 9) and np.all(mask.ravel() == 1)
+    F, mask = cv2.findFundamentalMat(a[s7[:6]], b[s7[:6]], cv2.FM_RANSAC, 1.0, 0.99)
+    assert F is None and mask is None
+    X, xy, _, _, _ = synth.pnp_stress_case(50, 0.0, 0.2, seed=1)
+    for n, flag in ((5, cv2.SOLVEPNP_EPNP), (4, cv2.SOLVEPNP_P3P)):
+        ok_, r, t, inl = cv2.solvePnPRansac(X[:n].reshape(-1, 1, 3), xy[:n].reshape(-1, 1, 2), glue.K, np.zeros((4, 1)), None,
+                                            None, False, 100, 1.0, 0.99)
+        ok2, r2, t2 = cv2.solvePnP(X[:n].reshape(-1, 1, 3), xy[:n].reshape(-1, 1, 2), glue.K, np.zeros((4, 1)), flags=flag)
+        assert ok_ and np.array_equal(inl.ravel(), np.arange(n)) and np.array_equal(r, r2) and np.array_equal(t, t2)
