@@ -768,7 +768,7 @@ def test_small_point_sets_take_opencv_paths(fe, G):
             res = fe.solvePnPRansac(X[:n], xy[:n], 100, 1.0, 0.99)
             assert res["ok"] == bool(ok_)
             assert np.array_equal(res["inliers"], np.arange(n))
-            tol = 1e-9 if n == 5 else 1e-6
+            tol = 1e-9 if n == 5 else 1e-5     # P3P: another formulation of the same quartic than OpenCV's (required: 1e-4 rad, 1e-3 m)
             assert np.abs(res["rvec"] - r0.ravel()).max() <= tol and np.abs(res["tvec"] - t0.ravel()).max() <= tol, (n, seed)
         res = fe.solvePnPRansac(X[:4], xy[:4], 100, 1.0, 0.99, min_solver=_lib.VO_PNP_P3P4)
         assert res["ok"] and len(res["inliers"]) == 4
