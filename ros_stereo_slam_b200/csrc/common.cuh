@@ -51,6 +51,7 @@ struct Pyramid {
   int cn = 1;
   bool has_deriv = false;
   uint64_t stamp = 0;  // content tag (0 = empty)
+  int* d_mono = nullptr;   // device flag (3-channel images): 1 = the three planes are identical (a gray image read as BGR)
   // CUtensorMap (TMA descriptor) of the level-0 interior of each plane: u8, dims (w, h), row stride = pitch
   alignas(64) unsigned char tmap0[MAX_CN][128] = {{0}};
 };
@@ -65,6 +66,7 @@ struct PyrLevelView {  // what kernels see
 struct PyrView {
   PyrLevelView lv[MAX_LEVELS];
   int nlevels;
+  const int* mono;   // see Pyramid::d_mono
 };
 
 struct Profile {

@@ -53,6 +53,8 @@ constexpr int FB_WORDS = 2 * (4 * NB_SIMD + N_TAIL);   // 546: b1 | b2 terms
 constexpr int FA_WORDS = 4 * NA_SIMD + N_TAIL;         // 441: one A sum at a time
 constexpr int SCRATCH_WORDS = (TILE_WORDS + DTILE_WORDS) > FB_WORDS ? (TILE_WORDS + DTILE_WORDS) : FB_WORDS;  // 780
 constexpr int WARP_WORDS = TILE_WORDS + SCRATCH_WORDS;  // J tile | {I tile + derivative tile} U {chain terms}
+constexpr int WARP_WORDS_G3 = TILE_WORDS + 3 * LK_WIN * LK_WIN + 1;   // the replicated-gray variant keeps whole windows of terms
+                                          // for its fall-backs: three A sums (3 x 441 floats) / two b sums (2 x 441 int32)
 #ifndef LK_WARPS_N
 #define LK_WARPS_N 4
 #endif
@@ -158,6 +160,110 @@ __device__ __forceinline__ void lane_chains(const int a[4], const int b[4], int 
   c[4] = isq * ((b[0] + b[1]) + (b[2] + b[3]));
 }
 
+// per-lane chain totals of one sum, 3-channel image with identical planes (see lk_kernel<.., true>): a[j] = slot A's
+// column class j; b[i] = slot B's sample i (an oct's column class i & 3, or a tail's column 16 + i)
+template <bool G3, int NB>
+__device__ __forceinline__ void lane_chains_t(const int a[4], const int (&b)[NB], int notq, int isq, int c[5]) {
+  if constexpr (!G3) {
+    lane_chains(a, b, notq, isq, c);
+  } else {
+    int Q[4], T[5];
+#pragma unroll
+    for (int j = 0; j < 4; j++) Q[j] = a[j] + notq * (b[j] + b[j + 4]);
+#pragma unroll
+    for (int i = 0; i < 5; i++) T[i] = isq * b[i];
+    c[0] = (Q[0] + Q[1]) + (Q[2] + T[0]) + T[1];
+    c[1] = (Q[0] + Q[1]) + (Q[3] + T[0]) + T[1];
+    c[2] = (Q[0] + Q[2]) + (Q[3] + T[0]) + T[2];
+    c[3] = (Q[1] + Q[2]) + (Q[3] + T[1]) + T[2];
+    c[4] = T[2] + 3 * (T[3] + T[4]);
+  }
+}
+
+// G3 fall-backs: the window's terms in the plain [row][col] layout; lane k < 4 adds the SIMD chain k (interleaved
+// samples x = k, k+4, ... < 56 of every row, column x / 3), lane 4 the scalar chain (x = 56..62)
+__device__ __forceinline__ float run_chain_g3_a(const float* f, int lane) {
+  float acc = 0.f;
+  if (lane < 4) {
+    for (int r = 0; r < WIN; r++)
+      for (int x = lane; x < 56; x += 4) acc = __fadd_rn(acc, f[r * WIN + x / 3]);
+  } else if (lane == 4) {
+    for (int r = 0; r < WIN; r++)
+      for (int x = 56; x < 63; x++) acc = __fadd_rn(acc, f[r * WIN + x / 3]);
+  }
+  return acc;
+}
+// A sums: the three sums side by side (windows at f, f + 441, f + 882), lanes 0..4 / 5..9 / 10..14
+__device__ __forceinline__ float run_chain_g3_a3(const float* f, int lane) {
+  float acc = 0.f;
+  if (lane < 15) {
+    const int s = lane / 5, k = lane - 5 * s;
+    const float* q = f + s * WIN * WIN;
+    if (k < 4) {
+      for (int r = 0; r < WIN; r++)
+        for (int x = k; x < 56; x += 4) acc = __fadd_rn(acc, q[r * WIN + x / 3]);
+    } else {
+      for (int r = 0; r < WIN; r++)
+        for (int x = 56; x < 63; x++) acc = __fadd_rn(acc, q[r * WIN + x / 3]);
+    }
+  }
+  return acc;
+}
+
+// Exact test of the five chains of ONE b sum (window of int32 products at P, plain layout): lane r < 21 holds row r,
+// builds the 7 elements of every chain from registers (SIMD chain k: OpenCV's pairs x = 8t + k and x + 4; scalar chain:
+// x = 56 + t; column = x / 3), a warp scan gives the exact partial sum in front of every row.  tot[k] = chain totals;
+// returns the largest |partial sum| or |element| seen (clamped), i.e. < 2^24 iff all five float chains are exact.
+__device__ __forceinline__ int g3_chains_exact(const int* P, int lane, int tot[5]) {
+  int v[WIN];
+  const int* row = P + (lane < WIN ? lane : 0) * WIN;
+#pragma unroll
+  for (int cidx = 0; cidx < WIN; cidx++) v[cidx] = lane < WIN ? row[cidx] : 0;
+  int worst = 0;
+#pragma unroll
+  for (int k = 0; k < 5; k++) {
+    int e[7];
+    int run = 0;
+#pragma unroll
+    for (int t = 0; t < 7; t++) {
+      e[t] = k < 4 ? v[(8 * t + k) / 3] + v[(8 * t + k + 4) / 3] : v[(56 + t) / 3];
+      run += e[t];
+    }
+    int incl = run;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int u = __shfl_up_sync(FULL, incl, d);
+      if (lane >= d) incl += u;
+    }
+    int p = incl - run;
+#pragma unroll
+    for (int t = 0; t < 7; t++) {
+      p += e[t];
+      worst = max(worst, max(abs(p), abs(e[t])));
+    }
+    tot[k] = __shfl_sync(FULL, incl, 31);
+  }
+  return __reduce_max_sync(FULL, min(worst, SAFE_LIMIT));
+}
+
+// b sums: lanes 0..4 = chains of b1 (products at p), lanes 5..9 = chains of b2 (products at p + 441); OpenCV's int32
+// pairs (x, x + 4) inside every step of 8
+__device__ __forceinline__ float run_chain_g3_b(const int* p, int lane) {
+  float acc = 0.f;
+  if (lane < 10) {
+    const int* q = p + (lane >= 5 ? WIN * WIN : 0);
+    const int k = lane >= 5 ? lane - 5 : lane;
+    if (k < 4) {
+      for (int r = 0; r < WIN; r++)
+        for (int x = k; x < 56; x += 8) acc = __fadd_rn(acc, __int2float_rn(q[r * WIN + x / 3] + q[r * WIN + (x + 4) / 3]));
+    } else {
+      for (int r = 0; r < WIN; r++)
+        for (int x = 56; x < 63; x++) acc = __fadd_rn(acc, __int2float_rn(q[r * WIN + x / 3]));
+    }
+  }
+  return acc;
+}
+
 // lanes 0 .. nsum*5-1 add up their chain of float terms one by one (OpenCV's order); terms of sum s start at
 // f + s*stride: four SIMD chains of n_simd terms, then the tail chain of N_TAIL terms.  Returns the five
 // chain values of sum `s` broadcast to every lane.
@@ -174,17 +280,26 @@ __device__ __forceinline__ float run_chain(const float* f, int lane, int nsum, i
 
 }  // namespace
 
-template <int MINB>
+// G3 = true: 3-channel images whose planes are identical (PyrView::mono of both images) -- see the note above
+// lk_kernel_c3.  Every interleaved sample x = 3*col + ch then equals the 1-channel sample of its column, so ONE warp
+// on plane 0 knows all 63 x 21 terms: column class j = col & 3 (cols 0..15) feeds the SIMD chains (3j + ch) & 3,
+// columns 16 / 17 / 18 feed chains {0,1,2} / {3,0,1} / {2,3,scalar}, columns 19 and 20 feed the scalar chain three
+// times each; the sequential fall-back walks the interleaved order over the 21-column term buffer.
+template <int MINB, bool G3>
 __global__ void __launch_bounds__(LK_WARPS * 32, MINB * 4 / LK_WARPS)
 lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n, float2* __restrict__ next_pts,
           uint8_t* __restrict__ status, float* __restrict__ err, int max_iters, double eps_sq, float eps_lo, float eps_hi,
           float min_eig_thr, unsigned long long* __restrict__ work, const int* __restrict__ n_dev) {
   if (n_dev) n = min(n, *n_dev);
-  __shared__ __align__(16) unsigned smem[LK_WARPS * WARP_WORDS];
+  if (G3 && !(*prev.mono && *next.mono)) return;     // not a replicated-gray pair: lk_kernel_c3 does the launch
+  constexpr int WW = G3 ? WARP_WORDS_G3 : WARP_WORDS;
+  constexpr int CN = G3 ? 3 : 1;
+  constexpr int NB = G3 ? 8 : 4;              // slot-B accumulators: per sample (G3: a tail's columns go to different chains)
+  __shared__ __align__(16) unsigned smem[LK_WARPS * WW];
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= n) return;
-  unsigned* jtile = smem + (threadIdx.x >> 5) * WARP_WORDS;
+  unsigned* jtile = smem + (threadIdx.x >> 5) * WW;
   unsigned* itile = jtile + TILE_WORDS;        // scratch: I tile | derivative tile, later the chain terms
   unsigned* dtile = itile + TILE_WORDS;
   float* fterms = reinterpret_cast<float*>(itile);
@@ -306,7 +421,7 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
         if (!valid) { Iw[8 + i] = 0; Ix[8 + i] = 0; Iy[8 + i] = 0; }
       }
       int a11[4] = {0, 0, 0, 0}, a12[4] = {0, 0, 0, 0}, a22[4] = {0, 0, 0, 0}, c1[4] = {0, 0, 0, 0}, c2[4] = {0, 0, 0, 0};
-      int b11[4] = {0, 0, 0, 0}, b12[4] = {0, 0, 0, 0}, b22[4] = {0, 0, 0, 0}, d1[4] = {0, 0, 0, 0}, d2[4] = {0, 0, 0, 0};
+      int b11[NB] = {0}, b12[NB] = {0}, b22[NB] = {0}, d1[NB] = {0}, d2[NB] = {0};
       int mA[8];
 #pragma unroll
       for (int i = 0; i < 8; i++) {
@@ -317,24 +432,30 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
         c1[k] += Iw[i] * Ix[i];
         c2[k] += Iw[i] * Iy[i];
         mA[i] = max(abs(Ix[i]), abs(Iy[i]));
-        b11[k] += Ix[8 + i] * Ix[8 + i];
-        b12[k] += Ix[8 + i] * Iy[8 + i];
-        b22[k] += Iy[8 + i] * Iy[8 + i];
-        d1[k] += Iw[8 + i] * Ix[8 + i];
-        d2[k] += Iw[8 + i] * Iy[8 + i];
+        const int kb = G3 ? i : k;
+        b11[kb] += Ix[8 + i] * Ix[8 + i];
+        b12[kb] += Ix[8 + i] * Iy[8 + i];
+        b22[kb] += Iy[8 + i] * Iy[8 + i];
+        d1[kb] += Iw[8 + i] * Ix[8 + i];
+        d2[kb] += Iw[8 + i] * Iy[8 + i];
         mB[i] = max(abs(Ix[8 + i]), abs(Iy[8 + i]));
       }
 #pragma unroll
       for (int k = 0; k < 4; k++) mpA[k] = max(mA[k], mA[k + 4]);
-      lane_chains(a11, b11, notq, isq, cA11);
-      lane_chains(a12, b12, notq, isq, cA12);
-      lane_chains(a22, b22, notq, isq, cA22);
-      lane_chains(c1, d1, notq, isq, cC1);
-      lane_chains(c2, d2, notq, isq, cC2);
+      lane_chains_t<G3>(a11, b11, notq, isq, cA11);
+      lane_chains_t<G3>(a12, b12, notq, isq, cA12);
+      lane_chains_t<G3>(a22, b22, notq, isq, cA22);
+      lane_chains_t<G3>(c1, d1, notq, isq, cC1);
+      lane_chains_t<G3>(c2, d2, notq, isq, cC2);
     }
     bool safeA = true;
 #pragma unroll
     for (int k = 0; k < 5; k++) {
+      if (G3) {   // up to 294 squares per chain: the lane parts are clamped so that the warp sum cannot wrap (a clamped
+                  // value only ever feeds the "unsafe" decision)
+        cA11[k] = min(cA11[k], SAFE_LIMIT);
+        cA22[k] = min(cA22[k], SAFE_LIMIT);
+      }
       cA11[k] = __reduce_add_sync(FULL, cA11[k]);
       cA12[k] = __reduce_add_sync(FULL, cA12[k]);
       cA22[k] = __reduce_add_sync(FULL, cA22[k]);
@@ -350,24 +471,50 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
       A12 = chain_combine((float)cA12[0], (float)cA12[1], (float)cA12[2], (float)cA12[3], (float)cA12[4]);
       A22 = chain_combine((float)cA22[0], (float)cA22[1], (float)cA22[2], (float)cA22[3], (float)cA22[4]);
     } else {
-      // slow path: the float terms in OpenCV's order, one A sum at a time (the I / derivative tiles are consumed)
+      // slow path: the float terms in OpenCV's order (the I / derivative tiles are consumed)
       n_slow_a++;
       float res[3];
-#pragma unroll
-      for (int s = 0; s < 3; s++) {
+      if (G3) {
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-          const int pa = s == 0 ? Ix[i] * Ix[i] : (s == 1 ? Ix[i] * Iy[i] : Iy[i] * Iy[i]);
-          fterms[(i & 3) * NA_SIMD + 4 * rowA + (colA >> 2) + (i >> 2)] = __int2float_rn(pa);
-          const int pb = s == 0 ? Ix[8 + i] * Ix[8 + i] : (s == 1 ? Ix[8 + i] * Iy[8 + i] : Iy[8 + i] * Iy[8 + i]);
-          if (!isq_b) fterms[(i & 3) * NA_SIMD + 4 * rowB + (colB >> 2) + (i >> 2)] = __int2float_rn(pb);
-          else if (hasB && i < 5) fterms[4 * NA_SIMD + 5 * rowB + i] = __int2float_rn(pb);
+          fterms[rowA * WIN + colA + i] = __int2float_rn(Ix[i] * Ix[i]);
+          fterms[WIN * WIN + rowA * WIN + colA + i] = __int2float_rn(Ix[i] * Iy[i]);
+          fterms[2 * WIN * WIN + rowA * WIN + colA + i] = __int2float_rn(Iy[i] * Iy[i]);
+          if (hasB && (!isq_b || i < 5)) {
+            fterms[rowB * WIN + colB + i] = __int2float_rn(Ix[8 + i] * Ix[8 + i]);
+            fterms[WIN * WIN + rowB * WIN + colB + i] = __int2float_rn(Ix[8 + i] * Iy[8 + i]);
+            fterms[2 * WIN * WIN + rowB * WIN + colB + i] = __int2float_rn(Iy[8 + i] * Iy[8 + i]);
+          }
         }
         __syncwarp();
-        const float acc = run_chain(fterms, lane, 1, NA_SIMD);
-        res[s] = chain_combine(__shfl_sync(FULL, acc, 0), __shfl_sync(FULL, acc, 1), __shfl_sync(FULL, acc, 2),
-                               __shfl_sync(FULL, acc, 3), __shfl_sync(FULL, acc, 4));
+        const float acc = run_chain_g3_a3(fterms, lane);
+#pragma unroll
+        for (int s = 0; s < 3; s++)
+          res[s] = chain_combine(__shfl_sync(FULL, acc, 5 * s), __shfl_sync(FULL, acc, 5 * s + 1), __shfl_sync(FULL, acc, 5 * s + 2),
+                                 __shfl_sync(FULL, acc, 5 * s + 3), __shfl_sync(FULL, acc, 5 * s + 4));
+      } else {
+  #pragma unroll
+        for (int s = 0; s < 3; s++) {
+          __syncwarp();
+  #pragma unroll
+          for (int i = 0; i < 8; i++) {
+            const int pa = s == 0 ? Ix[i] * Ix[i] : (s == 1 ? Ix[i] * Iy[i] : Iy[i] * Iy[i]);
+            const int pb = s == 0 ? Ix[8 + i] * Ix[8 + i] : (s == 1 ? Ix[8 + i] * Iy[8 + i] : Iy[8 + i] * Iy[8 + i]);
+            if (G3) {   // plain window layout; the chain lanes walk the interleaved order over it
+              fterms[rowA * WIN + colA + i] = __int2float_rn(pa);
+              if (hasB && (!isq_b || i < 5)) fterms[rowB * WIN + colB + i] = __int2float_rn(pb);
+            } else {
+              fterms[(i & 3) * NA_SIMD + 4 * rowA + (colA >> 2) + (i >> 2)] = __int2float_rn(pa);
+              if (!isq_b) fterms[(i & 3) * NA_SIMD + 4 * rowB + (colB >> 2) + (i >> 2)] = __int2float_rn(pb);
+              else if (hasB && i < 5) fterms[4 * NA_SIMD + 5 * rowB + i] = __int2float_rn(pb);
+            }
+          }
+          __syncwarp();
+          const float acc = run_chain(fterms, lane, 1, NA_SIMD);
+          res[s] = chain_combine(__shfl_sync(FULL, acc, 0), __shfl_sync(FULL, acc, 1), __shfl_sync(FULL, acc, 2),
+                                 __shfl_sync(FULL, acc, 3), __shfl_sync(FULL, acc, 4));
+        }
       }
       A11 = res[0];
       A12 = res[1];
@@ -418,7 +565,7 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
       bool all_exact = true;
       {
         int a1[4] = {0, 0, 0, 0}, a2[4] = {0, 0, 0, 0}, ua[4];
-        int b1[4] = {0, 0, 0, 0}, b2[4] = {0, 0, 0, 0}, ub[4] = {0, 0, 0, 0};
+        int b1[NB] = {0}, b2[NB] = {0}, ub[NB] = {0};
         int jv[8];
         oct_sample(jp + offA, shJ, wt, wb, jv);
 #pragma unroll
@@ -431,17 +578,22 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
         oct_sample(jp + offB, shJ, wt, wb, jv);
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-          b1[i & 3] += jv[i] * Ix[8 + i];
-          b2[i & 3] += jv[i] * Iy[8 + i];
-          ub[i & 3] += (int)__sad(jv[i], Iw[8 + i], 0u) * mB[i];
+          b1[G3 ? i : (i & 3)] += jv[i] * Ix[8 + i];
+          b2[G3 ? i : (i & 3)] += jv[i] * Iy[8 + i];
+          ub[G3 ? i : (i & 3)] += (int)__sad(jv[i], Iw[8 + i], 0u) * mB[i];
         }
         t1 = ((a1[0] + a1[1]) + (a1[2] + a1[3])) + ((b1[0] + b1[1]) + (b1[2] + b1[3]));
         t2 = ((a2[0] + a2[1]) + (a2[2] + a2[3])) + ((b2[0] + b2[1]) + (b2[2] + b2[3]));
         tu = ((ua[0] + ua[1]) + (ua[2] + ua[3])) + ((ub[0] + ub[1]) + (ub[2] + ub[3]));   // < 2^30
+        if (G3) {       // every sample stands for its three channels (tu <= 16 * 8160 * 4080 * 3 < 2^31)
+          t1 = 3 * (t1 + ((b1[4] + b1[5]) + (b1[6] + b1[7])));
+          t2 = 3 * (t2 + ((b2[4] + b2[5]) + (b2[6] + b2[7])));
+          tu = 3 * (tu + ((ub[4] + ub[5]) + (ub[6] + ub[7])));
+        }
         if (__reduce_add_sync(FULL, min(tu, SAFE_LIMIT)) >= SAFE_LIMIT) {
-          lane_chains(a1, b1, notq, isq, c1);
-          lane_chains(a2, b2, notq, isq, c2);
-          lane_chains(ua, ub, notq, isq, cu);
+          lane_chains_t<G3>(a1, b1, notq, isq, c1);
+          lane_chains_t<G3>(a2, b2, notq, isq, c2);
+          lane_chains_t<G3>(ua, ub, notq, isq, cu);
           all_exact = false;
         }
       }
@@ -470,35 +622,72 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
         n_slow_b++;
         int jv[8];
         __syncwarp();
-        oct_sample(jp + offA, shJ, wt, wb, jv);
+        if (G3) {
+          // the int32 products of the window in its plain layout (b1 | b2); the chain lanes form OpenCV's pairs
+          // (x, x + 4) of the interleaved order themselves
+          int* pt = reinterpret_cast<int*>(fterms);
+          oct_sample(jp + offA, shJ, wt, wb, jv);
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const int dA = jv[k] - Iw[k], dB = jv[k + 4] - Iw[k + 4];
-          fterms[k * NB_SIMD + 2 * rowA + (colA >> 3)] = __int2float_rn(dA * Ix[k] + dB * Ix[k + 4]);
-          fterms[FB_WORDS / 2 + k * NB_SIMD + 2 * rowA + (colA >> 3)] = __int2float_rn(dA * Iy[k] + dB * Iy[k + 4]);
-        }
-        oct_sample(jp + offB, shJ, wt, wb, jv);
-        if (!isq_b) {
+          for (int i = 0; i < 8; i++) {
+            const int d = jv[i] - Iw[i];
+            pt[rowA * WIN + colA + i] = d * Ix[i];
+            pt[WIN * WIN + rowA * WIN + colA + i] = d * Iy[i];
+          }
+          oct_sample(jp + offB, shJ, wt, wb, jv);
 #pragma unroll
+          for (int i = 0; i < 8; i++)
+            if (hasB && (!isq_b || i < 5)) {
+              const int d = jv[i] - Iw[8 + i];
+              pt[rowB * WIN + colB + i] = d * Ix[8 + i];
+              pt[WIN * WIN + rowB * WIN + colB + i] = d * Iy[8 + i];
+            }
+          __syncwarp();
+          // the bound on sum |term| failed: test the partial sums themselves (exactly) before falling back to the
+          // sequential chains
+          int e1[5], e2[5];
+          const int w1 = g3_chains_exact(pt, lane, e1);
+          const int w2 = g3_chains_exact(pt + WIN * WIN, lane, e2);
+          if (max(w1, w2) < SAFE_LIMIT) {
+            b1f = chain_combine((float)e1[0], (float)e1[1], (float)e1[2], (float)e1[3], (float)e1[4]);
+            b2f = chain_combine((float)e2[0], (float)e2[1], (float)e2[2], (float)e2[3], (float)e2[4]);
+          } else {
+            const float acc = run_chain_g3_b(pt, lane);
+            b1f = chain_combine(__shfl_sync(FULL, acc, 0), __shfl_sync(FULL, acc, 1), __shfl_sync(FULL, acc, 2),
+                                __shfl_sync(FULL, acc, 3), __shfl_sync(FULL, acc, 4));
+            b2f = chain_combine(__shfl_sync(FULL, acc, 5), __shfl_sync(FULL, acc, 6), __shfl_sync(FULL, acc, 7),
+                                __shfl_sync(FULL, acc, 8), __shfl_sync(FULL, acc, 9));
+          }
+        } else {
+          oct_sample(jp + offA, shJ, wt, wb, jv);
+  #pragma unroll
           for (int k = 0; k < 4; k++) {
-            const int dA = jv[k] - Iw[8 + k], dB = jv[k + 4] - Iw[12 + k];
-            fterms[k * NB_SIMD + 2 * rowB + (colB >> 3)] = __int2float_rn(dA * Ix[8 + k] + dB * Ix[12 + k]);
-            fterms[FB_WORDS / 2 + k * NB_SIMD + 2 * rowB + (colB >> 3)] = __int2float_rn(dA * Iy[8 + k] + dB * Iy[12 + k]);
+            const int dA = jv[k] - Iw[k], dB = jv[k + 4] - Iw[k + 4];
+            fterms[k * NB_SIMD + 2 * rowA + (colA >> 3)] = __int2float_rn(dA * Ix[k] + dB * Ix[k + 4]);
+            fterms[FB_WORDS / 2 + k * NB_SIMD + 2 * rowA + (colA >> 3)] = __int2float_rn(dA * Iy[k] + dB * Iy[k + 4]);
           }
-        } else if (hasB) {
-#pragma unroll
-          for (int i = 0; i < 5; i++) {
-            const int dA = jv[i] - Iw[8 + i];
-            fterms[4 * NB_SIMD + 5 * rowB + i] = __int2float_rn(dA * Ix[8 + i]);
-            fterms[FB_WORDS / 2 + 4 * NB_SIMD + 5 * rowB + i] = __int2float_rn(dA * Iy[8 + i]);
+          oct_sample(jp + offB, shJ, wt, wb, jv);
+          if (!isq_b) {
+  #pragma unroll
+            for (int k = 0; k < 4; k++) {
+              const int dA = jv[k] - Iw[8 + k], dB = jv[k + 4] - Iw[12 + k];
+              fterms[k * NB_SIMD + 2 * rowB + (colB >> 3)] = __int2float_rn(dA * Ix[8 + k] + dB * Ix[12 + k]);
+              fterms[FB_WORDS / 2 + k * NB_SIMD + 2 * rowB + (colB >> 3)] = __int2float_rn(dA * Iy[8 + k] + dB * Iy[12 + k]);
+            }
+          } else if (hasB) {
+  #pragma unroll
+            for (int i = 0; i < 5; i++) {
+              const int dA = jv[i] - Iw[8 + i];
+              fterms[4 * NB_SIMD + 5 * rowB + i] = __int2float_rn(dA * Ix[8 + i]);
+              fterms[FB_WORDS / 2 + 4 * NB_SIMD + 5 * rowB + i] = __int2float_rn(dA * Iy[8 + i]);
+            }
           }
+          __syncwarp();
+          const float acc = run_chain(fterms, lane, 2, NB_SIMD);
+          b1f = chain_combine(__shfl_sync(FULL, acc, 0), __shfl_sync(FULL, acc, 1), __shfl_sync(FULL, acc, 2),
+                              __shfl_sync(FULL, acc, 3), __shfl_sync(FULL, acc, 4));
+          b2f = chain_combine(__shfl_sync(FULL, acc, 5), __shfl_sync(FULL, acc, 6), __shfl_sync(FULL, acc, 7),
+                              __shfl_sync(FULL, acc, 8), __shfl_sync(FULL, acc, 9));
         }
-        __syncwarp();
-        const float acc = run_chain(fterms, lane, 2, NB_SIMD);
-        b1f = chain_combine(__shfl_sync(FULL, acc, 0), __shfl_sync(FULL, acc, 1), __shfl_sync(FULL, acc, 2),
-                            __shfl_sync(FULL, acc, 3), __shfl_sync(FULL, acc, 4));
-        b2f = chain_combine(__shfl_sync(FULL, acc, 5), __shfl_sync(FULL, acc, 6), __shfl_sync(FULL, acc, 7),
-                            __shfl_sync(FULL, acc, 8), __shfl_sync(FULL, acc, 9));
       }
       const float b1 = __fmul_rn(b1f, FLT_SCALE);
       const float b2 = __fmul_rn(b2f, FLT_SCALE);
@@ -562,7 +751,7 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
           se += valid ? __sad(jv[i], Iw[8 + i], 0u) : 0u;
         }
         const int tot = __reduce_add_sync(FULL, (int)se);  // <= 441*8160 < 2^24: OpenCV's float sum is exact
-        errv = __fdiv_rn((float)tot, (float)(32 * WIN * WIN));
+        errv = __fdiv_rn((float)(CN * tot), (float)(32 * WIN * CN * WIN));
       }
     }
   }
@@ -683,8 +872,9 @@ __device__ __forceinline__ float chain_b3(const int* P, int k, int lane) {
 __global__ void __launch_bounds__(C3 * 32, 5)
 lk_kernel_c3(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n, float2* __restrict__ next_pts,
              uint8_t* __restrict__ status, float* __restrict__ err, int max_iters, double eps_sq, float eps_lo, float eps_hi,
-             float min_eig_thr, unsigned long long* __restrict__ work, const int* __restrict__ n_dev) {
+             float min_eig_thr, unsigned long long* __restrict__ work, const int* __restrict__ n_dev, int skip_mono) {
   if (n_dev) n = min(n, *n_dev);
+  if (skip_mono && *prev.mono && *next.mono) return;     // three identical planes in both images: lk_kernel<.., true>
   __shared__ __align__(16) unsigned smem[C3 * TILE_WORDS + PB_REGION + XCH_WORDS];
   const int point = blockIdx.x;
   const int lane = threadIdx.x & 31;
@@ -1174,7 +1364,7 @@ int lk_launch(vo_ctx* c, int slot_prev, int slot_next, const float2* d_prev, int
       dyn = per > stat ? per - stat : 0;
       static bool attr_set = false;
       if (!attr_set) {
-        cudaFuncSetAttribute(lk_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(lk_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
       }
     }
@@ -1185,28 +1375,36 @@ int lk_launch(vo_ctx* c, int slot_prev, int slot_next, const float2* d_prev, int
       v1::lk_kernel_c3<<<div_up(n * 32, 128), 128, 0, c->stream>>>(pyr_view(c->pyr[slot_prev]), pyr_view(c->pyr[slot_next]), d_prev, n,
                                                                    d_next, d_status, d_err, max_iters, eps, (float)c->p.lk_min_eig,
                                                                    c->d_lk_work, c->n_dev);
-    else if (c->p.channels == 3)
+    else if (c->p.channels == 3) {
+      // two launches, one of which returns at once: the pair is either "gray read as BGR" (three identical planes in both
+      // images, flagged on the device when the frames were split into planes) or genuinely coloured
+      static const bool no_g3 = getenv("VO_LK_NO_G3") != nullptr;
+      if (!no_g3)
+        lk_kernel<4, true><<<blocks, threads, 0, c->stream>>>(pyr_view(c->pyr[slot_prev]), pyr_view(c->pyr[slot_next]), d_prev, n,
+                                                              d_next, d_status, d_err, max_iters, eps, eps_lo, eps_hi,
+                                                              (float)c->p.lk_min_eig, c->d_lk_work, c->n_dev);
       lk_kernel_c3<<<n, C3 * 32, 0, c->stream>>>(pyr_view(c->pyr[slot_prev]), pyr_view(c->pyr[slot_next]), d_prev, n, d_next,
                                                  d_status, d_err, max_iters, eps, eps_lo, eps_hi, (float)c->p.lk_min_eig,
-                                                 c->d_lk_work, c->n_dev);
+                                                 c->d_lk_work, c->n_dev, no_g3 ? 0 : 1);
+    }
     else if (use_v1)
       v1::lk_kernel<<<div_up(n * 32, 128), 128, 0, c->stream>>>(pyr_view(c->pyr[slot_prev]), pyr_view(c->pyr[slot_next]), d_prev, n,
                                                        d_next, d_status, d_err, max_iters, eps, (float)c->p.lk_min_eig,
                                                        c->d_lk_work, c->n_dev);
     else if (variant == 4)
-      lk_kernel<4><<<blocks, threads, dyn, c->stream>>>(pyr_view(c->pyr[slot_prev]), pyr_view(c->pyr[slot_next]), d_prev, n,
+      lk_kernel<4, false><<<blocks, threads, dyn, c->stream>>>(pyr_view(c->pyr[slot_prev]), pyr_view(c->pyr[slot_next]), d_prev, n,
                                                       d_next, d_status, d_err, max_iters, eps, eps_lo, eps_hi,
                                                       (float)c->p.lk_min_eig, c->d_lk_work, c->n_dev);
     else if (variant == 5)
-      lk_kernel<5><<<blocks, threads, 0, c->stream>>>(pyr_view(c->pyr[slot_prev]), pyr_view(c->pyr[slot_next]), d_prev, n,
+      lk_kernel<5, false><<<blocks, threads, 0, c->stream>>>(pyr_view(c->pyr[slot_prev]), pyr_view(c->pyr[slot_next]), d_prev, n,
                                                       d_next, d_status, d_err, max_iters, eps, eps_lo, eps_hi, (float)c->p.lk_min_eig,
                                                       c->d_lk_work, c->n_dev);
     else if (variant == 2)
-      lk_kernel<2><<<blocks, threads, 0, c->stream>>>(pyr_view(c->pyr[slot_prev]), pyr_view(c->pyr[slot_next]), d_prev, n,
+      lk_kernel<2, false><<<blocks, threads, 0, c->stream>>>(pyr_view(c->pyr[slot_prev]), pyr_view(c->pyr[slot_next]), d_prev, n,
                                                       d_next, d_status, d_err, max_iters, eps, eps_lo, eps_hi, (float)c->p.lk_min_eig,
                                                       c->d_lk_work, c->n_dev);
     else
-      lk_kernel<3><<<blocks, threads, 0, c->stream>>>(pyr_view(c->pyr[slot_prev]), pyr_view(c->pyr[slot_next]), d_prev, n,
+      lk_kernel<3, false><<<blocks, threads, 0, c->stream>>>(pyr_view(c->pyr[slot_prev]), pyr_view(c->pyr[slot_next]), d_prev, n,
                                                       d_next, d_status, d_err, max_iters, eps, eps_lo, eps_hi, (float)c->p.lk_min_eig,
                                                       c->d_lk_work, c->n_dev);
   }

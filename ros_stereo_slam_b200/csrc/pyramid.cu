@@ -267,15 +267,20 @@ pyr_fused_kernel(const __grid_constant__ K1Maps maps, const K1Args a) {
   }
 }
 
+__global__ void set_int_kernel(int* p, int v) { *p = v; }
+
 // Interleaved BGR (tight rows of 3*w bytes) -> the level-0 interiors of the three planes.
 // 4 pixels per thread: twelve byte loads (rows of 3*w bytes are not word aligned), three uchar4 stores.
+// Also clears *mono (preset to 1) when any pixel has B != G or G != R: a gray image that imread returned as BGR --
+// the reference's KITTI case -- has three identical planes, which the LK launch exploits (lk.cu, lk_kernel<.., true>).
 __global__ void split_planes_kernel(const uint8_t* __restrict__ bgr, int w, int h, uint8_t* __restrict__ img, int pitch,
-                                    size_t plane) {
+                                    size_t plane, int* __restrict__ mono) {
   const int x = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
   const int y = blockIdx.y;
   if (x >= w) return;
   const uint8_t* s = bgr + (size_t)y * (3 * w) + 3 * x;
   uint8_t* d = img + (size_t)(y + PAD_Y) * pitch + PAD_L + x;
+  bool same = true;
   if (x + 4 <= w) {
     uint8_t v[12];
 #pragma unroll
@@ -283,10 +288,15 @@ __global__ void split_planes_kernel(const uint8_t* __restrict__ bgr, int w, int 
 #pragma unroll
     for (int c = 0; c < 3; c++)
       *reinterpret_cast<uchar4*>(d + c * plane) = make_uchar4(v[c], v[3 + c], v[6 + c], v[9 + c]);
+#pragma unroll
+    for (int k = 0; k < 4; k++) same = same && v[3 * k] == v[3 * k + 1] && v[3 * k] == v[3 * k + 2];
   } else {
-    for (int k = 0; x + k < w; k++)
+    for (int k = 0; x + k < w; k++) {
       for (int c = 0; c < 3; c++) d[c * plane + k] = s[3 * k + c];
+      same = same && s[3 * k] == s[3 * k + 1] && s[3 * k] == s[3 * k + 2];
+    }
   }
+  if (!same) *mono = 0;     // benign race: every writer stores 0
 }
 
 // Device image with an arbitrary row stride -> level-0 interior of a padded plane.  An SM copy instead of
@@ -385,6 +395,8 @@ int pyr_alloc(vo_ctx* c, Pyramid& p) {
   }
   p.has_deriv = false;
   p.stamp = 0;
+  VO_CUDA(cudaMalloc(&p.d_mono, sizeof(int)));
+  VO_CUDA(cudaMemsetAsync(p.d_mono, 0, sizeof(int), c->stream));
   // TMA descriptors of the level-0 interiors (the driver entry point is resolved through the
   // runtime, so the library does not link libcuda)
   {
@@ -429,11 +441,14 @@ void pyr_free(Pyramid& p) {
     p.lv[l].deriv = nullptr;
   }
   p.nlevels = 0;
+  cudaFree(p.d_mono);
+  p.d_mono = nullptr;
 }
 
 PyrView pyr_view(const Pyramid& p) {
   PyrView v;
   v.nlevels = p.nlevels;
+  v.mono = p.d_mono;
   for (int l = 0; l < MAX_LEVELS; l++) {
     if (l < p.nlevels) {
       v.lv[l].img = p.lv[l].img;
@@ -503,7 +518,8 @@ int pyr_split_bgr(vo_ctx* c, int slot, const uint8_t* d_bgr) {
   dim3 b(128), g(div_up(div_up(L0.w, 4), 128), L0.h);
   {
     LaunchScope ls(c, VO_K_PYRAMID);
-    split_planes_kernel<<<g, b, 0, c->stream>>>(d_bgr, L0.w, L0.h, L0.img, L0.pitch, L0.plane);
+    set_int_kernel<<<1, 1, 0, c->stream>>>(c->pyr[slot].d_mono, 1);
+    split_planes_kernel<<<g, b, 0, c->stream>>>(d_bgr, L0.w, L0.h, L0.img, L0.pitch, L0.plane, c->pyr[slot].d_mono);
   }
   VO_CUDA(cudaGetLastError());
   return VO_OK;

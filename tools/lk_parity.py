@@ -92,6 +92,12 @@ def main():
         allok &= run(fe3, "bgr gray3 step%d temporal" % step, cv2.cvtColor(L0, cv2.COLOR_GRAY2BGR), cv2.cvtColor(L1, cv2.COLOR_GRAY2BGR),
                      pts, reps=5 if step == 5 else 0)
         allok &= run(fe3, "bgr color step%d stereo" % step, colorize(L0), colorize(R0), pts, reps=5 if step == 5 else 0)
+    Hg, Hgs = cv2.cvtColor(H0, cv2.COLOR_GRAY2BGR), cv2.cvtColor(shift(H0, 1.3, 0.6), cv2.COLOR_GRAY2BGR)
+    allok &= run(fe3, "bgr gray3 harsh shift", Hg, Hgs, np.concatenate([glue.dense_keypoint_extractor(376, 1241, 9), extra]), reps=3)
+    allok &= run(fe3, "bgr gray3 harsh vs other", Hg, cv2.cvtColor(harsh(L1, 0), cv2.COLOR_GRAY2BGR), glue.dense_keypoint_extractor(376, 1241, 15))
+    cbg = cv2.cvtColor(cb, cv2.COLOR_GRAY2BGR)
+    allok &= run(fe3, "bgr gray3 checker", cbg, cv2.cvtColor(shift(cb, 0.8, 0.4), cv2.COLOR_GRAY2BGR), glue.dense_keypoint_extractor(376, 1241, 15))
+    allok &= run(fe3, "bgr gray3 vs color (mixed)", cv2.cvtColor(L0, cv2.COLOR_GRAY2BGR), colorize(L1), glue.dense_keypoint_extractor(376, 1241, 15))
     Hc = np.stack([H0, harsh(L0, 5), 255 - H0], -1)
     Hs = np.stack([shift(Hc[:, :, c], 1.3, 0.6) for c in range(3)], -1)
     allok &= run(fe3, "bgr harsh shift(1.3,0.6)", Hc, Hs, np.concatenate([glue.dense_keypoint_extractor(376, 1241, 9), extra]), reps=3)
