@@ -346,6 +346,8 @@ int vo_create(const vo_params* p, vo_ctx** out) {
     vo_destroy(c);
     return r;
   }
+  c->opt_host_chains = getenv("VO_B200_SEQ_HOST") != nullptr;      // read per context (tests flip them)
+  c->opt_lookahead = getenv("VO_B200_LOOKAHEAD") != nullptr;
   c->worker = std::thread(worker_main, c);
   *out = c;
   return VO_OK;
@@ -1661,12 +1663,15 @@ int vo_seq_track(vo_ctx* c, const uint8_t* left, const uint8_t* right, int strid
   const bool kf_known = right && (force_keyframe || c->p.kf_min_inliers > c->p.max_points);
   // default: the fused single-synchronisation chains (2 host synchronisations per frame); VO_B200_SEQ_HOST=1 selects the
   // host-driven chains (3-4 synchronisations per chain, host-side sampling)
-  static const bool host_driven = getenv("VO_B200_SEQ_HOST") != nullptr;
+  // With the reference's keyframe rule (keyframe only when inliers < 200) the single tracking chain runs host-driven:
+  // its F-RANSAC often needs more than the fused chain's first chunk of samples (threshold 1 px on a thinning point
+  // set), and every such miss costs a redo -- measured 1129 vs 927 frames/s (config 1) and 973 vs 802 (config-2 sizes).
+  const bool host_driven = c->opt_host_chains || !kf_known;
   // Look-ahead is opt-in (VO_B200_LOOKAHEAD=1): measured on the bench workload it LOSES (858 vs 881 frames/s) -- a full
   // LK launch occupies every SM's register file, so the latency-bound solver kernels of the tracking chain it was meant
   // to hide under wait for LK blocks to retire (pnp_solve 0.27 -> 0.49 ms).  Kept because it is exact and because it
   // is the right schedule once the chains run on disjoint SM partitions.
-  static const bool la_enabled = getenv("VO_B200_LOOKAHEAD") != nullptr;
+  const bool la_enabled = c->opt_lookahead;
 
   // Look-ahead bookkeeping.  have_la: the previous call already built this image's pyramid (slot `cur`) and tracked
   // the keyframe's points into it on the look-ahead chain.

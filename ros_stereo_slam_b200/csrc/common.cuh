@@ -121,6 +121,8 @@ struct vo_ctx {
   const uint8_t* ann_right = nullptr;
   int ann_stride = 0;
   bool pf_by_worker = false;         // this call's prefetch copies are issued by the stereo worker thread
+  bool opt_host_chains = false;      // VO_B200_SEQ_HOST at vo_create: host-driven chains also when the keyframe is known
+  bool opt_lookahead = false;        // VO_B200_LOOKAHEAD at vo_create (needs the host-driven chains)
 
   // image staging + pyramids: slots 0/1/3 rotate through the left images (reference, current, look-ahead), slot 2 right
   uint8_t* d_raw[3] = {nullptr, nullptr, nullptr};

@@ -681,7 +681,14 @@ def test_lookahead_changes_the_schedule_not_the_numbers(channels):
     order = [1, 2, 3, 5, 4, 6]          # frame 5 arrives where 4 was announced: that look-ahead is discarded
 
     def run(mode):
-        fe = make_frontend(kf_min_inliers=2 ** 31 - 1, channels=channels, grid_step=9)
+        import os
+        # the look-ahead is opt-in and lives in the host-driven chains; the switches are read at vo_create
+        os.environ["VO_B200_SEQ_HOST"] = "1"
+        os.environ["VO_B200_LOOKAHEAD"] = "1"
+        try:
+            fe = make_frontend(kf_min_inliers=2 ** 31 - 1, channels=channels, grid_step=9)
+        finally:
+            del os.environ["VO_B200_SEQ_HOST"], os.environ["VO_B200_LOOKAHEAD"]
         nb = Ls[0].nbytes
         d = C.c_void_p()
         if mode == "device":
