@@ -35,7 +35,7 @@ SOURCES = {
     "orb.cu": ["--fmad=false"],
     "aux.cu": [],
 }
-HEADERS = ["common.cuh", "cvmath.cuh", "fmat7.cuh", "jacobi_warp.cuh", "lk_v1.cuh", "orb_pattern.h", os.path.join("..", "..", "include", "vo_b200.h")]
+HEADERS = ["common.cuh", "cvmath.cuh", "fmat7.cuh", "jacobi_warp.cuh", "orb_pattern.h", os.path.join("..", "..", "include", "vo_b200.h")]
 
 
 def _nvcc():

@@ -1732,17 +1732,8 @@ int vo_seq_track(vo_ctx* c, const uint8_t* left, const uint8_t* right, int strid
     VO_CUDA(cudaEventRecord(c->ev_stereo, a->stream));
     if (r == VO_OK) r = rs;
   } else {
-    // VO_B200_LK_FIRST=1: the tracking chain's LK (critical path) is launched before the stereo worker is released and
-    // the stereo chain waits for it, so the two full-GPU LK launches run back to back instead of side by side
-    static const bool lk_first_env = getenv("VO_B200_LK_FIRST") != nullptr;
-    const bool lk_first = lk_first_env && host_driven && kf_known && !have_la && c->seq_n > 0;
     if (kf_known) {
       VO_CUDA(cudaEventRecord(c->ev_left, c->stream));
-      if (lk_first) {
-        VO_TRY(lk_launch(c, ref, cur, c->d_seq_xy, c->seq_n, c->d_xy_trk, c->d_status, nullptr));
-        VO_CUDA(cudaEventRecord(c->ev_lk, c->stream));
-        VO_CUDA(cudaStreamWaitEvent(a->stream, c->ev_lk, 0));
-      }
       VO_CUDA(cudaStreamWaitEvent(a->stream, c->ev_left, 0));
       VO_CUDA(cudaStreamWaitEvent(a->stream, c->ev_gather, 0));   // aux->d_idx / d_c_ref of the previous keyframe are released
       // The next frame, if the caller announced it: device-resident (vo_seq_announce) or host (vo_seq_prefetch, copied
@@ -1781,7 +1772,7 @@ int vo_seq_track(vo_ctx* c, const uint8_t* left, const uint8_t* right, int strid
       });
     }
     if (host_driven) {
-      r = track_pipeline(c, ref, cur, c->d_seq_xy, c->d_seq_xyz, c->seq_n, &k, have_la || lk_first);
+      r = track_pipeline(c, ref, cur, c->d_seq_xy, c->d_seq_xyz, c->seq_n, &k, have_la);
       if (r == VO_OK) r = pnp_two_attempts(c, k, &ni, &att);
     } else {
       r = temporal_any(c, ref, cur, c->d_seq_xy, c->d_seq_xyz, c->seq_n, &k, &ni, &att);

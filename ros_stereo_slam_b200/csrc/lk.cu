@@ -32,7 +32,7 @@
 // window WITH A MARGIN of 3 px, so that the usual sub-pixel moves of an LK iteration never restage; the
 // tile of a level is requested before the window extraction of that level starts and lands behind it.
 // Levels live padded in HBM/L2 (common.cuh), so none of this carries bounds logic.
-#include "lk_v1.cuh"
+#include "common.cuh"
 
 namespace vo {
 
@@ -1348,65 +1348,24 @@ int lk_launch(vo_ctx* c, int slot_prev, int slot_next, const float2* d_prev, int
   eps *= eps;
   const int threads = LK_WARPS * 32;
   const int blocks = div_up(n * 32, threads);
+  // OpenCV tests (double)dx*dx + (double)dy*dy <= eps^2; the kernel decides in float outside this band
   const float eps_lo = (float)(eps * (1.0 - 1e-5)), eps_hi = (float)(eps * (1.0 + 1e-5));
-  static const bool use_v1 = getenv("VO_LK_V1") != nullptr;   // A/B baseline only (profiling)
-  static const int variant = getenv("VO_LK_MINB") ? atoi(getenv("VO_LK_MINB")) : 4;
-  // experiment: cap the resident LK blocks per SM with a dynamic shared-memory request, so that the register file
-  // keeps room for the latency-bound solver kernels of the other chain
-  static const int maxblk = getenv("VO_LK_MAXBLK") ? atoi(getenv("VO_LK_MAXBLK")) : 0;
-  static const int maxblk_aux_only = getenv("VO_LK_MAXBLK_AUX") ? atoi(getenv("VO_LK_MAXBLK_AUX")) : 0;
-  size_t dyn = 0;
-  {
-    const int mb = c->is_aux ? (maxblk_aux_only ? maxblk_aux_only : maxblk) : maxblk;
-    if (mb > 0) {
-      const size_t per = (size_t)(227 * 1024) / (mb + 1) + 1024;     // more than 1/(mb+1) of the SM's shared memory
-      const size_t stat = LK_WARPS * WARP_WORDS * 4;
-      dyn = per > stat ? per - stat : 0;
-      static bool attr_set = false;
-      if (!attr_set) {
-        cudaFuncSetAttribute(lk_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
-      }
-    }
-  }
+  const PyrView pv = pyr_view(c->pyr[slot_prev]), nv = pyr_view(c->pyr[slot_next]);
+  const float min_eig = (float)c->p.lk_min_eig;
   {
     LaunchScope ls(c, VO_K_LK);
-    if (c->p.channels == 3 && use_v1)
-      v1::lk_kernel_c3<<<div_up(n * 32, 128), 128, 0, c->stream>>>(pyr_view(c->pyr[slot_prev]), pyr_view(c->pyr[slot_next]), d_prev, n,
-                                                                   d_next, d_status, d_err, max_iters, eps, (float)c->p.lk_min_eig,
-                                                                   c->d_lk_work, c->n_dev);
-    else if (c->p.channels == 3) {
+    if (c->p.channels == 3) {
       // two launches, one of which returns at once: the pair is either "gray read as BGR" (three identical planes in both
       // images, flagged on the device when the frames were split into planes) or genuinely coloured
-      static const bool no_g3 = getenv("VO_LK_NO_G3") != nullptr;
-      if (!no_g3)
-        lk_kernel<4, true><<<blocks, threads, 0, c->stream>>>(pyr_view(c->pyr[slot_prev]), pyr_view(c->pyr[slot_next]), d_prev, n,
-                                                              d_next, d_status, d_err, max_iters, eps, eps_lo, eps_hi,
-                                                              (float)c->p.lk_min_eig, c->d_lk_work, c->n_dev);
-      lk_kernel_c3<<<n, C3 * 32, 0, c->stream>>>(pyr_view(c->pyr[slot_prev]), pyr_view(c->pyr[slot_next]), d_prev, n, d_next,
-                                                 d_status, d_err, max_iters, eps, eps_lo, eps_hi, (float)c->p.lk_min_eig,
-                                                 c->d_lk_work, c->n_dev, no_g3 ? 0 : 1);
+      lk_kernel<4, true><<<blocks, threads, 0, c->stream>>>(pv, nv, d_prev, n, d_next, d_status, d_err, max_iters, eps, eps_lo,
+                                                            eps_hi, min_eig, c->d_lk_work, c->n_dev);
+      lk_kernel_c3<<<n, C3 * 32, 0, c->stream>>>(pv, nv, d_prev, n, d_next, d_status, d_err, max_iters, eps, eps_lo, eps_hi,
+                                                 min_eig, c->d_lk_work, c->n_dev, 1);
+    } else {
+      // 128 registers / 16 warps per SM: measured best (168 registers 0.254 ms, 96 registers with spills 0.290 ms)
+      lk_kernel<4, false><<<blocks, threads, 0, c->stream>>>(pv, nv, d_prev, n, d_next, d_status, d_err, max_iters, eps, eps_lo,
+                                                             eps_hi, min_eig, c->d_lk_work, c->n_dev);
     }
-    else if (use_v1)
-      v1::lk_kernel<<<div_up(n * 32, 128), 128, 0, c->stream>>>(pyr_view(c->pyr[slot_prev]), pyr_view(c->pyr[slot_next]), d_prev, n,
-                                                       d_next, d_status, d_err, max_iters, eps, (float)c->p.lk_min_eig,
-                                                       c->d_lk_work, c->n_dev);
-    else if (variant == 4)
-      lk_kernel<4, false><<<blocks, threads, dyn, c->stream>>>(pyr_view(c->pyr[slot_prev]), pyr_view(c->pyr[slot_next]), d_prev, n,
-                                                      d_next, d_status, d_err, max_iters, eps, eps_lo, eps_hi,
-                                                      (float)c->p.lk_min_eig, c->d_lk_work, c->n_dev);
-    else if (variant == 5)
-      lk_kernel<5, false><<<blocks, threads, 0, c->stream>>>(pyr_view(c->pyr[slot_prev]), pyr_view(c->pyr[slot_next]), d_prev, n,
-                                                      d_next, d_status, d_err, max_iters, eps, eps_lo, eps_hi, (float)c->p.lk_min_eig,
-                                                      c->d_lk_work, c->n_dev);
-    else if (variant == 2)
-      lk_kernel<2, false><<<blocks, threads, 0, c->stream>>>(pyr_view(c->pyr[slot_prev]), pyr_view(c->pyr[slot_next]), d_prev, n,
-                                                      d_next, d_status, d_err, max_iters, eps, eps_lo, eps_hi, (float)c->p.lk_min_eig,
-                                                      c->d_lk_work, c->n_dev);
-    else
-      lk_kernel<3, false><<<blocks, threads, 0, c->stream>>>(pyr_view(c->pyr[slot_prev]), pyr_view(c->pyr[slot_next]), d_prev, n,
-                                                      d_next, d_status, d_err, max_iters, eps, eps_lo, eps_hi, (float)c->p.lk_min_eig,
-                                                      c->d_lk_work, c->n_dev);
   }
   VO_CUDA(cudaGetLastError());
   return VO_OK;
