@@ -35,6 +35,10 @@
 #define VO_HDM inline
 #endif
 
+#ifndef VO_JACOBI_SPEC_M3
+#define VO_JACOBI_SPEC_M3 1
+#endif
+
 namespace vo {
 
 // ---------------------------------------------------------------------------------------
@@ -116,10 +120,15 @@ VO_HDN void jacobi_svd(double* At, double* _W, double* Vt) {
         }
 #pragma unroll
         for (k = 0; k < m; k++) p += ri[k] * rj[k];
+        // latency-bound callers (SPEC): the skip test's square root and the hypot of the rotation are independent
+        // chains, started together; throughput-bound ones (triangulation) keep the test first
+        constexpr bool SPEC = VO_JACOBI_SPEC_M3 && M == 3;
+        double beta = a - b, gamma = 0;
+        const double p2 = p * 2;
+        if (SPEC) gamma = cv_hypot(p2, beta);
         if (fabs(p) <= eps * sqrt(a * b)) continue;
-
-        p *= 2;
-        double beta = a - b, gamma = cv_hypot(p, beta);
+        p = p2;
+        if (!SPEC) gamma = cv_hypot(p, beta);
         if (beta < 0) {
           double delta = (gamma - beta) * 0.5;
           s = sqrt(delta / gamma);
@@ -290,30 +299,55 @@ VO_HDF void solve_svd(const double* A, const double* b, double* x) {
 // operations in the same order as the compile-time versions.  EPnP's three beta initialisations
 // solve 6x4, 6x3 and 6x5 systems; on the device they run on three lanes of one warp, and sharing
 // ONE instruction stream (instead of three template instantiations) keeps those lanes converged.
-VO_HDN void jacobi_svd_rt(double* At, int astep, double* _W, double* Vt, int vstep, int m, int n) {
+template <int M, int NMAX>
+VO_HDN void jacobi_svd_rt(double* At, double* _W, double* Vt, int n) {
+  constexpr int astep = M, m = M, vstep = NMAX;   // Vt: n rows of stride NMAX (columns n..NMAX-1 stay zero)
   double W[8];
   const double minval = DBL_MIN, eps = DBL_EPSILON * 10;
-  int i, j, k, iter, max_iter = m > 30 ? m : 30;
+  int i, j, k, iter;
+  constexpr int max_iter = m > 30 ? m : 30;
   double c, s, sd;
+#pragma unroll 1
   for (i = 0; i < n; i++) {
-    for (k = 0, sd = 0; k < m; k++) {
+    sd = 0;
+#pragma unroll
+    for (k = 0; k < m; k++) {
       double t = At[i * astep + k];
       sd += t * t;
     }
     W[i] = sd;
-    for (k = 0; k < n; k++) Vt[i * vstep + k] = 0;
+#pragma unroll
+    for (k = 0; k < NMAX; k++) Vt[i * vstep + k] = 0;
     Vt[i * vstep + i] = 1;
   }
+#pragma unroll 1
   for (iter = 0; iter < max_iter; iter++) {
     bool changed = false;
+#pragma unroll 1
     for (i = 0; i < n - 1; i++)
+#pragma unroll 1
       for (j = i + 1; j < n; j++) {
         double *Ai = At + i * astep, *Aj = At + j * astep;
         double a = W[i], p = 0, b = W[j];
-        for (k = 0; k < m; k++) p += Ai[k] * Aj[k];
-        if (fabs(p) <= eps * sqrt(a * b)) continue;
-        p *= 2;
-        double beta = a - b, gamma = cv_hypot(p, beta);
+        double ri[M], rj[M], vi[NMAX], vj[NMAX];
+        double *Vi = Vt + i * vstep, *Vj = Vt + j * vstep;
+#pragma unroll
+        for (k = 0; k < m; k++) {
+          ri[k] = Ai[k];
+          rj[k] = Aj[k];
+        }
+#pragma unroll
+        for (k = 0; k < NMAX; k++) {   // requested early: the loads complete under the divide / square-root chain
+          vi[k] = Vi[k];
+          vj[k] = Vj[k];
+        }
+#pragma unroll
+        for (k = 0; k < m; k++) p += ri[k] * rj[k];
+        const double skip_thr = eps * sqrt(a * b);
+        const double p2 = p * 2;
+        double beta = a - b, gamma = cv_hypot(p2, beta);   // evaluated next to the skip test's square root (two independent chains)
+        if (fabs(p) <= skip_thr) continue;
+        p = p2;
         if (beta < 0) {
           double delta = (gamma - beta) * 0.5;
           s = sqrt(delta / gamma);
@@ -323,9 +357,10 @@ VO_HDN void jacobi_svd_rt(double* At, int astep, double* _W, double* Vt, int vst
           s = p / (gamma * c * 2);
         }
         a = b = 0;
+#pragma unroll
         for (k = 0; k < m; k++) {
-          double t0 = c * Ai[k] + s * Aj[k];
-          double t1 = -s * Ai[k] + c * Aj[k];
+          double t0 = c * ri[k] + s * rj[k];
+          double t1 = -s * ri[k] + c * rj[k];
           Ai[k] = t0;
           Aj[k] = t1;
           a += t0 * t0;
@@ -334,36 +369,43 @@ VO_HDN void jacobi_svd_rt(double* At, int astep, double* _W, double* Vt, int vst
         W[i] = a;
         W[j] = b;
         changed = true;
-        double *Vi = Vt + i * vstep, *Vj = Vt + j * vstep;
-        for (k = 0; k < n; k++) {
-          double t0 = c * Vi[k] + s * Vj[k];
-          double t1 = -s * Vi[k] + c * Vj[k];
+#pragma unroll
+        for (k = 0; k < NMAX; k++) {
+          double t0 = c * vi[k] + s * vj[k];
+          double t1 = -s * vi[k] + c * vj[k];
           Vi[k] = t0;
           Vj[k] = t1;
         }
       }
     if (!changed) break;
   }
+#pragma unroll 1
   for (i = 0; i < n; i++) {
-    for (k = 0, sd = 0; k < m; k++) {
+    sd = 0;
+#pragma unroll
+    for (k = 0; k < m; k++) {
       double t = At[i * astep + k];
       sd += t * t;
     }
     W[i] = sqrt(sd);
   }
+#pragma unroll 1
   for (i = 0; i < n - 1; i++) {
     j = i;
+#pragma unroll 1
     for (k = i + 1; k < n; k++)
       if (W[j] < W[k]) j = k;
     if (i != j) {
       double t = W[i];
       W[i] = W[j];
       W[j] = t;
+#pragma unroll 1
       for (k = 0; k < m; k++) {
         t = At[i * astep + k];
         At[i * astep + k] = At[j * astep + k];
         At[j * astep + k] = t;
       }
+#pragma unroll 1
       for (k = 0; k < n; k++) {
         t = Vt[i * vstep + k];
         Vt[i * vstep + k] = Vt[j * vstep + k];
@@ -371,31 +413,41 @@ VO_HDN void jacobi_svd_rt(double* At, int astep, double* _W, double* Vt, int vst
       }
     }
   }
+#pragma unroll 1
   for (i = 0; i < n; i++) _W[i] = W[i];
   CvRng rng(0x12345678);
+#pragma unroll 1
   for (i = 0; i < n; i++) {
     sd = W[i];
+#pragma unroll 1
     for (int ii = 0; ii < 100 && sd <= minval; ii++) {
       const double val0 = 1. / m;
+#pragma unroll 1
       for (k = 0; k < m; k++) {
         double val = (rng.next() & 256) != 0 ? val0 : -val0;
         At[i * astep + k] = val;
       }
+#pragma unroll 1
       for (iter = 0; iter < 2; iter++) {
+#pragma unroll 1
         for (j = 0; j < i; j++) {
           sd = 0;
+#pragma unroll 1
           for (k = 0; k < m; k++) sd += At[i * astep + k] * At[j * astep + k];
           double asum = 0;
+#pragma unroll 1
           for (k = 0; k < m; k++) {
             double t = At[i * astep + k] - sd * At[j * astep + k];
             At[i * astep + k] = t;
             asum += fabs(t);
           }
           asum = asum > eps * 100 ? 1 / asum : 0;
+#pragma unroll 1
           for (k = 0; k < m; k++) At[i * astep + k] *= asum;
         }
       }
       sd = 0;
+#pragma unroll 1
       for (k = 0; k < m; k++) {
         double t = At[i * astep + k];
         sd += t * t;
@@ -403,6 +455,7 @@ VO_HDN void jacobi_svd_rt(double* At, int astep, double* _W, double* Vt, int vst
       sd = sqrt(sd);
     }
     s = sd > minval ? 1 / sd : 0.;
+#pragma unroll
     for (k = 0; k < m; k++) At[i * astep + k] *= s;
   }
 }
@@ -413,7 +466,7 @@ VO_HDN void solve_svd_6xn(const double* A, const double* b, double* x, int n) {
   double at[30], w[5], v[25];
   for (int i = 0; i < n; i++)
     for (int j = 0; j < m; j++) at[i * m + j] = A[j * n + i];
-  jacobi_svd_rt(at, m, w, v, n, m, n);
+  jacobi_svd_rt<6, 5>(at, w, v, n);
   double threshold = 0;
   for (int i = 0; i < n; i++) {
     x[i] = 0;
@@ -427,7 +480,7 @@ VO_HDN void solve_svd_6xn(const double* A, const double* b, double* x, int n) {
     double s = 0;
     for (int j = 0; j < m; j++) s += at[i * m + j] * b[j];
     s *= wi;
-    for (int j = 0; j < n; j++) x[j] = x[j] + s * v[i * n + j];
+    for (int j = 0; j < n; j++) x[j] = x[j] + s * v[i * 5 + j];
   }
 }
 

@@ -26,7 +26,7 @@ namespace vo {
 // shared memory (initialised by the caller exactly like the serial code: sequential sum of
 // squares).  All 32 lanes must call.  On return the rows are orthogonal (not yet normalised /
 // sorted: jacobi_svd<..., SKIP_SWEEPS=true> does that).
-template <int M, int N>
+template <int M, int N, bool SPEC = false>
 __device__ __forceinline__ void jacobi_sweeps_warp(double* At, double* W, int lane) {
   constexpr int H = N / 2;          // max independent pairs per anti-diagonal
   constexpr int P = N;              // steps between the starts of consecutive sweeps
@@ -58,10 +58,15 @@ __device__ __forceinline__ void jacobi_sweeps_warp(double* At, double* W, int la
         }
 #pragma unroll
         for (int k = 0; k < M; k++) p += ri[k] * rj[k];
+        // SPEC: the hypot of the rotation is started next to the skip test's square root (two independent chains)
+        const double p2 = p * 2;
+        const double beta = a - b;
+        double gamma = 0;
+        if (SPEC) gamma = cv_hypot(p2, beta);
         if (!(fabs(p) <= eps * sqrt(a * b))) {
           double c, s;
-          p *= 2;
-          const double beta = a - b, gamma = cv_hypot(p, beta);
+          p = p2;
+          if (!SPEC) gamma = cv_hypot(p, beta);
           if (beta < 0) {
             const double delta = (gamma - beta) * 0.5;
             s = sqrt(delta / gamma);

@@ -144,7 +144,7 @@ pnp_solve_kernel(const float3* __restrict__ xyz, const float2* __restrict__ xy, 
     W[lane] = sd;
   }
   __syncwarp();
-  jacobi_sweeps_warp<12, 12>(at, W, lane);
+  jacobi_sweeps_warp<12, 12, true>(at, W, lane);
   double* l_6x10 = sm.M;
   double* rho = sm.M + 60;
   if (lane == 0) {
