@@ -102,9 +102,9 @@ static int alloc_chain(vo_ctx* c) {
   const int n_tiles = std::max(256, (cap + 2047) / 2048 + 1);   // compaction tiles of 2048 flags (points.cu CP_TILE)
   VO_CUDA(cudaMalloc(&c->d_tile_state, n_tiles * sizeof(unsigned long long)));
   {
-    const unsigned one = 1;
-    VO_CUDA(cudaMalloc(&c->d_epoch, sizeof(unsigned)));
-    VO_CUDA(cudaMemcpy(c->d_epoch, &one, sizeof(one), cudaMemcpyHostToDevice));
+    const unsigned one[4] = {1, 0, 0, 0};
+    VO_CUDA(cudaMalloc(&c->d_epoch, sizeof(one)));
+    VO_CUDA(cudaMemcpy(c->d_epoch, one, sizeof(one), cudaMemcpyHostToDevice));
     double P[24];
     make_projections(c->p, P);
     VO_CUDA(cudaMalloc(&c->d_Pst, sizeof(P)));
@@ -904,11 +904,10 @@ static int enqueue_fmat_fused(vo_ctx* c, int n_max, double thr, bool with_xyz) {
   c->n_dev = c->d_count + 0;
   VO_TRY(sample_launch(c, 7, c->d_c_ref, c->d_c_trk, n_max, H, c->d_samples, c->d_flags + 0));
   VO_TRY(fmat_solve_launch(c, c->d_c_ref, c->d_c_trk, c->d_samples, H, c->d_models, c->d_counts));
-  VO_TRY(fmat_score_launch(c, c->d_c_ref, c->d_c_trk, n_max, c->d_models, c->d_counts, H, thr2));
-  VO_TRY(select_launch(c, c->d_counts, H, 3, 7, n_max, c->p.f_conf, std::max(c->p.f_max_iters, 1), c->d_sel + 4));
-  VO_TRY(fmat_mask_launch(c, c->d_c_ref, c->d_c_trk, n_max, c->d_models, c->d_sel + 4, thr2, c->d_mask));
-  VO_TRY(compact_launch(c, c->d_mask, n_max, c->d_c_ref, c->d_f_ref, c->d_c_trk, c->d_f_trk,
-                        with_xyz ? c->d_c_xyz : nullptr, c->d_f_xyz, nullptr, 1));
+  VO_TRY(fmat_score_select_launch(c, c->d_c_ref, c->d_c_trk, n_max, c->d_models, c->d_counts, H, thr2, c->p.f_conf,
+                                  std::max(c->p.f_max_iters, 1), c->d_sel + 4));
+  VO_TRY(fmat_mask_compact_launch(c, c->d_c_ref, c->d_c_trk, with_xyz ? c->d_c_xyz : nullptr, n_max, c->d_models, c->d_sel + 4,
+                                  thr2, c->d_mask, c->d_f_ref, c->d_f_trk, c->d_f_xyz, 1));
   c->n_dev = nullptr;
   c->last_f_h = H;
   return VO_OK;
@@ -941,10 +940,8 @@ static int track_pnp_fused_enqueue(vo_ctx* c, int slot_ref, int slot_cur, const 
   c->n_dev = c->d_count + 1;
   VO_TRY(sample_launch(c, 5, nullptr, nullptr, n, Hp, c->d_samples, c->d_flags + 1));
   VO_TRY(pnp_solve_launch(c, c->d_f_xyz, c->d_f_trk, c->d_samples, Hp, c->d_models, c->d_counts));
-  VO_TRY(pnp_score_launch(c, c->d_f_xyz, c->d_f_trk, n, c->d_models, c->d_counts, Hp, thr2));
-  VO_TRY(select_launch(c, c->d_counts, Hp, 1, 5, n, c->p.pnp_conf, iters, c->d_sel));
-  VO_TRY(pnp_mask_launch(c, c->d_f_xyz, c->d_f_trk, n, c->d_models, c->d_sel, thr2, c->d_mask));
-  VO_TRY(compact_launch(c, c->d_mask, n, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, c->d_idx, 4));
+  VO_TRY(pnp_score_select_launch(c, c->d_f_xyz, c->d_f_trk, n, c->d_models, c->d_counts, Hp, thr2, c->p.pnp_conf, iters, c->d_sel));
+  VO_TRY(pnp_mask_compact_launch(c, c->d_f_xyz, c->d_f_trk, n, c->d_models, c->d_sel, thr2, c->d_mask, c->d_idx, 4));
   c->n_dev = nullptr;
   VO_TRY(pnp_refine_launch(c, c->d_f_xyz, c->d_f_trk, c->d_idx, c->d_count + 4, c->d_models, c->d_sel, c->d_pose));
   c->last_pnp_h = Hp;

@@ -145,7 +145,7 @@ struct vo_ctx {
   int* d_count = nullptr;                                // small int scratch (16 ints)
   int* h_count = nullptr;                                // pinned mirror
   unsigned long long* d_tile_state = nullptr;            // compaction look-back (epoch<<32 | tile total)
-  unsigned* d_epoch = nullptr;                           // device-side launch epoch of the compaction
+  unsigned* d_epoch = nullptr;                           // [0] device-side launch epoch of the compaction, [1] CTA completion counter of a score launch
   double* d_Pst = nullptr;                               // P1 | P2 of the stereo rig (constant)
   // When set, kernels take their element count from this device pointer (clamped to the host-side
   // upper bound they were launched with): lets a whole chain run without a host round trip.
@@ -229,6 +229,69 @@ struct LaunchScope {
   ~LaunchScope();
 };
 
+// ---------------------------------------------------------------------------- ordered compaction core
+// Single pass with decoupled look-back (points.cu compact_kernel, ransac.cu mask_compact_kernel): every CTA owns a
+// tile of CP_TILE elements (CP_ITEMS consecutive ones per thread), scans its per-thread counts, publishes its tile
+// total tagged with the launch epoch, and sums the totals of the lower-indexed tiles (all co-resident, so the wait
+// is short and cannot deadlock).  Returns the output position of the calling thread's first kept element; the last
+// CTA writes the overall count and bumps the device-side epoch (graph-replay safe).
+constexpr int CP_THREADS = 256;
+constexpr int CP_ITEMS = 8;
+constexpr int CP_TILE = CP_THREADS * CP_ITEMS;
+
+#ifdef __CUDACC__
+__device__ __forceinline__ int compact_tile_offset(int cnt, int* __restrict__ count_out, volatile unsigned long long* tile_state,
+                                                   unsigned* epoch_ctr) {
+  const unsigned epoch = *reinterpret_cast<volatile unsigned*>(epoch_ctr);
+  __shared__ int warp_tot[CP_THREADS / 32];
+  __shared__ int s_base;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  int incl = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += v;
+  }
+  if (lane == 31) warp_tot[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    // exclusive scan of the 8 warp totals, publish the tile total, look back
+    int wt = lane < CP_THREADS / 32 ? warp_tot[lane] : 0;
+    int wi = wt;
+#pragma unroll
+    for (int d = 1; d < 8; d <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, wi, d);
+      if (lane >= d) wi += v;
+    }
+    const int tile_total = __shfl_sync(0xffffffffu, wi, CP_THREADS / 32 - 1);
+    if (lane < CP_THREADS / 32) warp_tot[lane] = wi - wt;
+    if (lane == 0) {
+      tile_state[blockIdx.x] = ((unsigned long long)epoch << 32) | (unsigned)tile_total;
+      __threadfence();
+    }
+    int base = 0;
+    for (int j = lane; j < (int)blockIdx.x; j += 32) {
+      unsigned long long v;
+      do {
+        v = tile_state[j];
+      } while ((unsigned)(v >> 32) != epoch);
+      base += (int)(unsigned)v;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) base += __shfl_xor_sync(0xffffffffu, base, d);
+    if (lane == 0) {
+      s_base = base;
+      if (blockIdx.x == gridDim.x - 1) {
+        *count_out = base + tile_total;
+        *epoch_ctr = epoch + 1;
+      }
+    }
+  }
+  __syncthreads();
+  return s_base + warp_tot[w] + incl - cnt;
+}
+#endif
+
 static inline int div_up(int a, int b) { return (a + b - 1) / b; }
 
 // stage launchers (each returns VO_OK / VO_ERR_CUDA) -------------------------------------
@@ -277,6 +340,16 @@ int pnp_direct_launch(vo_ctx* c, const float3* xyz, const float2* xy, int n, int
 int fmat_lmeds_launch(vo_ctx* c, const float2* m1, const float2* m2, int n, const double* d_models, const int32_t* d_counts,
                       int n_models, int* d_sel, uint8_t* d_mask);
 int fmat_seven_launch(vo_ctx* c, const int32_t* d_counts, int n, int* d_sel, uint8_t* d_mask);
+// fused-chain forms: scoring with the acceptance replay in its last CTA; best-model mask + ordered compaction in one launch
+int fmat_score_select_launch(vo_ctx* c, const float2* m1, const float2* m2, int n, const double* d_models, int32_t* d_counts,
+                             int h, float thr2, double conf, int max_iters, int* d_sel);
+int fmat_mask_compact_launch(vo_ctx* c, const float2* m1, const float2* m2, const float3* xyz, int n, const double* d_models,
+                             const int* d_sel, float thr2, uint8_t* d_mask, float2* o1, float2* o2, float3* oxyz,
+                             int count_slot);
+int pnp_score_select_launch(vo_ctx* c, const float3* xyz, const float2* xy, int n, const double* d_models, int32_t* d_counts,
+                            int h, float thr2, double conf, int max_iters, int* d_sel);
+int pnp_mask_compact_launch(vo_ctx* c, const float3* xyz, const float2* xy, int n, const double* d_models, const int* d_sel,
+                            float thr2, uint8_t* d_mask, int32_t* d_idx, int count_slot);
 // RANSAC record-setter scan: counts[n_models] (flattened, models_per_sample each) -> d_sel
 constexpr int RNG_LEN = 1 << 17;
 // device-side minimal-sample generation (OpenCV getSubset semantics); M = 7 checks collinearity

@@ -44,22 +44,13 @@ int grid_launch(vo_ctx* c, int rows, int cols, int step, float2* d_xy, int* n_ou
 // 64-bit load), scans it, publishes its tile total tagged with the launch epoch, and sums the
 // totals of the lower-indexed tiles (at most 64 tiles, all co-resident, so the wait is short
 // and cannot deadlock).  The arrays are L2-resident (<= 1.5 MB): latency-, not bandwidth-bound.
-constexpr int CP_THREADS = 256;
-constexpr int CP_ITEMS = 8;
-constexpr int CP_TILE = CP_THREADS * CP_ITEMS;
-
 __global__ void __launch_bounds__(CP_THREADS)
 compact_kernel(const uint8_t* __restrict__ flags, int n, const float2* __restrict__ a_in, float2* __restrict__ a_out,
                const float2* __restrict__ b_in, float2* __restrict__ b_out, const float3* __restrict__ c_in,
                float3* __restrict__ c_out, int32_t* __restrict__ idx_out, int* __restrict__ count_out,
                volatile unsigned long long* tile_state, unsigned* epoch_ctr, const int* __restrict__ n_dev) {
   if (n_dev) n = min(n, *n_dev);
-  // launch epoch from a device counter (graph-replay safe): every CTA reads it before publishing its
-  // tile total, and the last CTA -- whose look-back has then seen every publication -- bumps it
-  const unsigned epoch = *reinterpret_cast<volatile unsigned*>(epoch_ctr);
-  __shared__ int warp_tot[CP_THREADS / 32];
-  __shared__ int s_base;
-  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const int t = threadIdx.x;
   const int beg = blockIdx.x * CP_TILE + t * CP_ITEMS;
   unsigned long long bits = 0;  // byte k = flag of element beg+k
   if (beg + CP_ITEMS <= n) {
@@ -71,49 +62,7 @@ compact_kernel(const uint8_t* __restrict__ flags, int n, const float2* __restric
   int cnt = 0;
 #pragma unroll
   for (int k = 0; k < CP_ITEMS; k++) cnt += ((bits >> (8 * k)) & 0xff) == 1;
-  int incl = cnt;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const int v = __shfl_up_sync(0xffffffffu, incl, d);
-    if (lane >= d) incl += v;
-  }
-  if (lane == 31) warp_tot[w] = incl;
-  __syncthreads();
-  if (w == 0) {
-    // exclusive scan of the 8 warp totals, publish the tile total, look back
-    int wt = lane < CP_THREADS / 32 ? warp_tot[lane] : 0;
-    int wi = wt;
-#pragma unroll
-    for (int d = 1; d < 8; d <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, wi, d);
-      if (lane >= d) wi += v;
-    }
-    const int tile_total = __shfl_sync(0xffffffffu, wi, CP_THREADS / 32 - 1);
-    if (lane < CP_THREADS / 32) warp_tot[lane] = wi - wt;
-    if (lane == 0) {
-      tile_state[blockIdx.x] = ((unsigned long long)epoch << 32) | (unsigned)tile_total;
-      __threadfence();
-    }
-    int base = 0;
-    for (int j = lane; j < (int)blockIdx.x; j += 32) {
-      unsigned long long v;
-      do {
-        v = tile_state[j];
-      } while ((unsigned)(v >> 32) != epoch);
-      base += (int)(unsigned)v;
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) base += __shfl_xor_sync(0xffffffffu, base, d);
-    if (lane == 0) {
-      s_base = base;
-      if (blockIdx.x == gridDim.x - 1) {
-        *count_out = base + tile_total;
-        *epoch_ctr = epoch + 1;
-      }
-    }
-  }
-  __syncthreads();
-  int pos = s_base + warp_tot[w] + incl - cnt;
+  int pos = compact_tile_offset(cnt, count_out, tile_state, epoch_ctr);
 #pragma unroll
   for (int k = 0; k < CP_ITEMS; k++) {
     if (((bits >> (8 * k)) & 0xff) == 1) {

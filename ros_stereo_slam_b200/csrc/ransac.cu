@@ -200,6 +200,145 @@ int epnp_debug_launch(vo_ctx* c, const float* d_obj, const float* d_img, double*
   return VO_OK;
 }
 
+// ================================================================ sequential acceptance replay
+// cv::RANSACUpdateNumIters
+__device__ int ransac_update_num_iters(double p, double ep, int model_points, int max_iters) {
+  p = fmax(p, 0.);
+  p = fmin(p, 1.);
+  ep = fmax(ep, 0.);
+  ep = fmin(ep, 1.);
+  double num = fmax(1. - p, DBL_MIN);
+  double denom = 1. - pow(1. - ep, (double)model_points);
+  if (denom < DBL_MIN) return 0;
+  num = log(num);
+  denom = log(denom);
+  return denom >= 0 || -num >= max_iters * (-denom) ? max_iters : (int)rint(num / denom);
+}
+
+constexpr int SEL_THREADS = 1024;
+
+// What the selection needs besides the counts; passed by value to the score kernels when the selection is fused
+// into their last CTA (sel == nullptr: no fused selection).
+struct SelectArgs {
+  int n_samples, mps, model_points, n_points;
+  double conf;
+  int max_iters;
+  int* sel;
+  unsigned* done;   // CTA completion counter of the score launch (zero between launches)
+};
+
+// counts: flattened [sample][model] inlier counts (-1 = no such model).  One CTA of NT threads.
+// A model is a *candidate* iff its count exceeds every earlier count and modelPoints-1
+// (prefix max); candidates are then replayed in order with the adaptive iteration limit.
+// The counts are read through L2 (__ldcg): the fused caller's CTA may hold stale lines of them in L1.
+template <int NT>
+__device__ __forceinline__ void select_block(const int32_t* __restrict__ counts, int n_samples, int mps, int model_points,
+                                             int n_points, double conf, int max_iters, int* __restrict__ sel) {
+  __shared__ int s_excl[NT];
+  __shared__ int s_warp[32];
+  __shared__ unsigned s_cand[32];
+  const int t = threadIdx.x;
+  const int total = n_samples * mps;
+  const int chunk = (total + NT - 1) / NT;
+  const int beg = t * chunk, end = min(beg + chunk, total);
+  int mx = -1;
+  for (int i = beg; i < end; i++) mx = max(mx, __ldcg(counts + i));
+  // inclusive prefix max over threads
+  int incl = mx;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int v = __shfl_up_sync(0xffffffffu, incl, d);
+    if ((t & 31) >= d) incl = max(incl, v);
+  }
+  if ((t & 31) == 31) s_warp[t >> 5] = incl;
+  __syncthreads();
+  if (t < 32) {
+    int w = t < NT / 32 ? s_warp[t] : -1;
+    int wi = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int v = __shfl_up_sync(0xffffffffu, wi, d);
+      if (t >= d) wi = max(wi, v);
+    }
+    // exclusive over warps
+    int ex = __shfl_up_sync(0xffffffffu, wi, 1);
+    s_warp[t] = t == 0 ? -1 : ex;
+  }
+  __syncthreads();
+  int ex_lane = __shfl_up_sync(0xffffffffu, incl, 1);
+  if ((t & 31) == 0) ex_lane = -1;
+  const int floor0 = model_points - 1;
+  const int excl = max(max(s_warp[t >> 5], ex_lane), floor0);
+  s_excl[t] = excl;
+  const unsigned cand = __ballot_sync(0xffffffffu, mx > excl);
+  if ((t & 31) == 0) s_cand[t >> 5] = cand;
+  __syncthreads();
+  if (t == 0) {
+    int niters = max(max_iters, 1);
+    int best = -1, best_count = 0, n_rec = 0;
+    int open_sample = -1;  // OpenCV tests `iter < niters` once per sample: all models of an
+                           // admitted sample are scored even if the first one shrinks niters
+    bool stop = false;
+    for (int w = 0; w < NT / 32 && !stop; w++) {
+      unsigned bits = s_cand[w];
+      while (bits && !stop) {
+        const int l = __ffs(bits) - 1;
+        bits &= bits - 1;
+        const int th = w * 32 + l;
+        int run = s_excl[th];
+        const int b2 = th * chunk, e2 = min(b2 + chunk, total);
+        for (int i = b2; i < e2; i++) {
+          const int g = __ldcg(counts + i);
+          if (g > run) {
+            const int smp = i / mps;
+            if (smp != open_sample) {
+              if (smp >= niters) {
+                stop = true;
+                break;
+              }
+              open_sample = smp;
+            }
+            run = g;
+            best = i;
+            best_count = g;
+            n_rec++;
+            niters = ransac_update_num_iters(conf, (double)(n_points - g) / n_points, model_points, niters);
+          }
+        }
+      }
+    }
+    sel[0] = best;
+    sel[1] = niters;
+    sel[2] = best_count;
+    sel[3] = n_rec;
+  }
+}
+
+__global__ void __launch_bounds__(SEL_THREADS)
+select_kernel(const int32_t* __restrict__ counts, int n_samples, int mps, int model_points, int n_points, double conf,
+              int max_iters, int* __restrict__ sel, const int* __restrict__ n_dev) {
+  if (n_dev) n_points = min(n_points, *n_dev);
+  select_block<SEL_THREADS>(counts, n_samples, mps, model_points, n_points, conf, max_iters, sel);
+}
+
+// Tail of a score kernel with a fused selection: the CTA that finishes last (device counter) replays the
+// acceptance sequence over the now complete counts.  Every thread fences its own count updates first.
+template <int NT>
+__device__ __forceinline__ void score_tail_select(const int32_t* __restrict__ counts, const SelectArgs& sa, int n_points) {
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned total = gridDim.x * gridDim.y;
+    s_last = atomicAdd(sa.done, 1u) == total - 1;
+    if (s_last) *sa.done = 0;   // ready for the next launch (stream order)
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  select_block<NT>(counts, sa.n_samples, sa.mps, sa.model_points, n_points, sa.conf, sa.max_iters, sa.sel);
+}
+
 // ================================================================ scoring
 __device__ __forceinline__ float fmat_err(const double* F, float2 p1, float2 p2) {
   const double x1 = p1.x, y1 = p1.y, x2 = p2.x, y2 = p2.y;
@@ -242,13 +381,13 @@ constexpr int SCORE_HB = 16;  // hypotheses per CTA (staged in shared memory)
 __global__ void __launch_bounds__(SCORE_TPB)
 fmat_score_kernel(const float2* __restrict__ m1, const float2* __restrict__ m2, int n, const double* __restrict__ models,
                   int32_t* __restrict__ counts, int n_models, float thr2, const int* __restrict__ limit,
-                  const int* __restrict__ n_dev) {
+                  const int* __restrict__ n_dev, SelectArgs sa) {
   if (n_dev) n = min(n, *n_dev);
   __shared__ double sF[SCORE_HB * F_STRIDE];
   __shared__ int sCnt[SCORE_HB];
   __shared__ int sValid[SCORE_HB];
   const int m0 = blockIdx.y * SCORE_HB;
-  if (limit && m0 >= *limit * 3) return;
+  if (limit && m0 >= *limit * 3) return;   // (never together with a fused selection)
   for (int i = threadIdx.x; i < SCORE_HB * F_STRIDE; i += blockDim.x) {
     const int m = m0 + i / F_STRIDE;
     sF[i] = m < n_models ? models[(size_t)m0 * F_STRIDE + i] : 0.;
@@ -276,12 +415,13 @@ fmat_score_kernel(const float2* __restrict__ m1, const float2* __restrict__ m2, 
   __syncthreads();
   if (threadIdx.x < SCORE_HB && sValid[threadIdx.x] && sCnt[threadIdx.x])
     atomicAdd(&counts[m0 + threadIdx.x], sCnt[threadIdx.x]);
+  if (sa.sel) score_tail_select<SCORE_TPB>(counts, sa, n);
 }
 
 __global__ void __launch_bounds__(SCORE_TPB)
 pnp_score_kernel(const float3* __restrict__ xyz, const float2* __restrict__ xy, int n, const double* __restrict__ models,
                  int32_t* __restrict__ counts, int n_models, Intrinsics K, float thr2, const int* __restrict__ limit,
-                 const int* __restrict__ n_dev) {
+                 const int* __restrict__ n_dev, SelectArgs sa) {
   if (n_dev) n = min(n, *n_dev);
   __shared__ double sM[SCORE_HB * PNP_STRIDE];
   __shared__ int sCnt[SCORE_HB];
@@ -310,6 +450,7 @@ pnp_score_kernel(const float3* __restrict__ xyz, const float2* __restrict__ xy, 
   }
   __syncthreads();
   if (threadIdx.x < kmax && sCnt[threadIdx.x]) atomicAdd(&counts[m0 + threadIdx.x], sCnt[threadIdx.x]);
+  if (sa.sel) score_tail_select<SCORE_TPB>(counts, sa, n);
 }
 
 // ================================================================ best-model inlier mask
@@ -337,107 +478,61 @@ __global__ void pnp_mask_kernel(const float3* __restrict__ xyz, const float2* __
   mask[i] = v;
 }
 
-// ================================================================ sequential acceptance replay
-// cv::RANSACUpdateNumIters
-__device__ int ransac_update_num_iters(double p, double ep, int model_points, int max_iters) {
-  p = fmax(p, 0.);
-  p = fmin(p, 1.);
-  ep = fmax(ep, 0.);
-  ep = fmin(ep, 1.);
-  double num = fmax(1. - p, DBL_MIN);
-  double denom = 1. - pow(1. - ep, (double)model_points);
-  if (denom < DBL_MIN) return 0;
-  num = log(num);
-  denom = log(denom);
-  return denom >= 0 || -num >= max_iters * (-denom) ? max_iters : (int)rint(num / denom);
-}
-
-constexpr int SEL_THREADS = 1024;
-
-// counts: flattened [sample][model] inlier counts (-1 = no such model).  One CTA.
-// A model is a *candidate* iff its count exceeds every earlier count and modelPoints-1
-// (prefix max); candidates are then replayed in order with the adaptive iteration limit.
-__global__ void __launch_bounds__(SEL_THREADS)
-select_kernel(const int32_t* __restrict__ counts, int n_samples, int mps, int model_points, int n_points, double conf,
-              int max_iters, int* __restrict__ sel, const int* __restrict__ n_dev) {
-  if (n_dev) n_points = min(n_points, *n_dev);
-  __shared__ int s_excl[SEL_THREADS];
-  __shared__ int s_warp[32];
-  __shared__ unsigned s_cand[32];
+// ================================================================ best-model mask + ordered compaction, one launch
+// The fused chains' "mask -> compact" pair: every thread evaluates the best model on its CP_ITEMS consecutive
+// correspondences, the tile is compacted with the shared look-back core (common.cuh).  PNP = false: F-matrix error on
+// (a_in, b_in), survivors of a_in / b_in / c_in (optional) are copied; PNP = true: reprojection error of (c_in, a_in),
+// the survivors' indices are written.
+template <bool PNP>
+__global__ void __launch_bounds__(CP_THREADS)
+mask_compact_kernel(const float2* __restrict__ a_in, const float2* __restrict__ b_in, const float3* __restrict__ c_in, int n,
+                    const double* __restrict__ models, const int* __restrict__ sel, Intrinsics K, float thr2,
+                    uint8_t* __restrict__ mask, float2* __restrict__ a_out, float2* __restrict__ b_out,
+                    float3* __restrict__ c_out, int32_t* __restrict__ idx_out, int* __restrict__ count_out,
+                    volatile unsigned long long* tile_state, unsigned* epoch_ctr, const int* __restrict__ n_dev) {
+  if (n_dev) n = min(n, *n_dev);
+  constexpr int STRIDE = PNP ? PNP_STRIDE : F_STRIDE;
+  __shared__ double sM[STRIDE];
+  const int best = sel[0];
   const int t = threadIdx.x;
-  const int total = n_samples * mps;
-  const int chunk = (total + SEL_THREADS - 1) / SEL_THREADS;
-  const int beg = t * chunk, end = min(beg + chunk, total);
-  int mx = -1;
-  for (int i = beg; i < end; i++) mx = max(mx, counts[i]);
-  // inclusive prefix max over threads
-  int incl = mx;
+  if (best >= 0 && t < STRIDE) sM[t] = models[(size_t)best * STRIDE + t];
+  __syncthreads();
+  const int beg = blockIdx.x * CP_TILE + t * CP_ITEMS;
+  unsigned long long bits = 0;
+  int cnt = 0;
+  if (best >= 0) {
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    int v = __shfl_up_sync(0xffffffffu, incl, d);
-    if ((t & 31) >= d) incl = max(incl, v);
-  }
-  if ((t & 31) == 31) s_warp[t >> 5] = incl;
-  __syncthreads();
-  if (t < 32) {
-    int w = s_warp[t];
-    int wi = w;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      int v = __shfl_up_sync(0xffffffffu, wi, d);
-      if (t >= d) wi = max(wi, v);
-    }
-    // exclusive over warps
-    int ex = __shfl_up_sync(0xffffffffu, wi, 1);
-    s_warp[t] = t == 0 ? -1 : ex;
-  }
-  __syncthreads();
-  int ex_lane = __shfl_up_sync(0xffffffffu, incl, 1);
-  if ((t & 31) == 0) ex_lane = -1;
-  const int floor0 = model_points - 1;
-  const int excl = max(max(s_warp[t >> 5], ex_lane), floor0);
-  s_excl[t] = excl;
-  const unsigned cand = __ballot_sync(0xffffffffu, mx > excl);
-  if ((t & 31) == 0) s_cand[t >> 5] = cand;
-  __syncthreads();
-  if (t == 0) {
-    int niters = max(max_iters, 1);
-    int best = -1, best_count = 0, n_rec = 0;
-    int open_sample = -1;  // OpenCV tests `iter < niters` once per sample: all models of an
-                           // admitted sample are scored even if the first one shrinks niters
-    bool stop = false;
-    for (int w = 0; w < 32 && !stop; w++) {
-      unsigned bits = s_cand[w];
-      while (bits && !stop) {
-        const int l = __ffs(bits) - 1;
-        bits &= bits - 1;
-        const int th = w * 32 + l;
-        int run = s_excl[th];
-        const int b2 = th * chunk, e2 = min(b2 + chunk, total);
-        for (int i = b2; i < e2; i++) {
-          const int g = counts[i];
-          if (g > run) {
-            const int smp = i / mps;
-            if (smp != open_sample) {
-              if (smp >= niters) {
-                stop = true;
-                break;
-              }
-              open_sample = smp;
-            }
-            run = g;
-            best = i;
-            best_count = g;
-            n_rec++;
-            niters = ransac_update_num_iters(conf, (double)(n_points - g) / n_points, model_points, niters);
-          }
-        }
+    for (int k = 0; k < CP_ITEMS; k++) {
+      const int i = beg + k;
+      if (i < n) {
+        bool in;
+        if (PNP) in = pnp_err(sM, K, c_in[i], a_in[i]) <= thr2;
+        else in = fmat_err(sM, a_in[i], b_in[i]) <= thr2;
+        bits |= (unsigned long long)in << (8 * k);
+        cnt += in;
       }
     }
-    sel[0] = best;
-    sel[1] = niters;
-    sel[2] = best_count;
-    sel[3] = n_rec;
+  }
+  if (beg + CP_ITEMS <= n) {
+    *reinterpret_cast<unsigned long long*>(mask + beg) = bits;
+  } else {
+    for (int k = 0; k < CP_ITEMS; k++)
+      if (beg + k < n) mask[beg + k] = (uint8_t)(bits >> (8 * k));
+  }
+  int pos = compact_tile_offset(cnt, count_out, tile_state, epoch_ctr);
+#pragma unroll
+  for (int k = 0; k < CP_ITEMS; k++) {
+    if ((bits >> (8 * k)) & 1) {
+      const int i = beg + k;
+      if (PNP) {
+        idx_out[pos] = i;
+      } else {
+        a_out[pos] = a_in[i];
+        b_out[pos] = b_in[i];
+        if (c_in) c_out[pos] = c_in[i];
+      }
+      pos++;
+    }
   }
 }
 
@@ -598,7 +693,38 @@ int fmat_score_launch(vo_ctx* c, const float2* m1, const float2* m2, int n, cons
   dim3 g(div_up(n, SCORE_TPB), div_up(h * 3, SCORE_HB));
   {
     LaunchScope ls(c, VO_K_FMAT_SCORE);
-    fmat_score_kernel<<<g, SCORE_TPB, 0, c->stream>>>(m1, m2, n, d_models, d_counts, h * 3, thr2, nullptr, c->n_dev);
+    fmat_score_kernel<<<g, SCORE_TPB, 0, c->stream>>>(m1, m2, n, d_models, d_counts, h * 3, thr2, nullptr, c->n_dev, SelectArgs{});
+  }
+  VO_CUDA(cudaGetLastError());
+  return VO_OK;
+}
+
+// scoring with the selection (select_launch's arguments) fused into the last CTA
+int fmat_score_select_launch(vo_ctx* c, const float2* m1, const float2* m2, int n, const double* d_models, int32_t* d_counts,
+                             int h, float thr2, double conf, int max_iters, int* d_sel) {
+  if (h <= 0 || n <= 0) return select_launch(c, d_counts, h, 3, 7, n, conf, max_iters, d_sel);
+  dim3 g(div_up(n, SCORE_TPB), div_up(h * 3, SCORE_HB));
+  {
+    LaunchScope ls(c, VO_K_FMAT_SCORE);
+    fmat_score_kernel<<<g, SCORE_TPB, 0, c->stream>>>(m1, m2, n, d_models, d_counts, h * 3, thr2, nullptr, c->n_dev,
+                                                     SelectArgs{h, 3, 7, n, conf, max_iters, d_sel, c->d_epoch + 1});
+  }
+  VO_CUDA(cudaGetLastError());
+  return VO_OK;
+}
+
+int fmat_mask_compact_launch(vo_ctx* c, const float2* m1, const float2* m2, const float3* xyz, int n, const double* d_models,
+                             const int* d_sel, float thr2, uint8_t* d_mask, float2* o1, float2* o2, float3* oxyz,
+                             int count_slot) {
+  if (n <= 0) {
+    VO_CUDA(cudaMemsetAsync(c->d_count + count_slot, 0, sizeof(int), c->stream));
+    return VO_OK;
+  }
+  {
+    LaunchScope ls(c, VO_K_COMPACT);
+    mask_compact_kernel<false><<<div_up(n, CP_TILE), CP_THREADS, 0, c->stream>>>(
+        m1, m2, xyz, n, d_models, d_sel, intr(c), thr2, d_mask, o1, o2, oxyz, nullptr, c->d_count + count_slot,
+        c->d_tile_state, c->d_epoch, c->n_dev);
   }
   VO_CUDA(cudaGetLastError());
   return VO_OK;
@@ -633,7 +759,37 @@ int pnp_score_launch(vo_ctx* c, const float3* xyz, const float2* xy, int n, cons
   dim3 g(div_up(n, SCORE_TPB), div_up(h, SCORE_HB));
   {
     LaunchScope ls(c, VO_K_PNP_SCORE);
-    pnp_score_kernel<<<g, SCORE_TPB, 0, c->stream>>>(xyz, xy, n, d_models, d_counts, h, intr(c), thr2, nullptr, c->n_dev);
+    pnp_score_kernel<<<g, SCORE_TPB, 0, c->stream>>>(xyz, xy, n, d_models, d_counts, h, intr(c), thr2, nullptr, c->n_dev,
+                                                    SelectArgs{});
+  }
+  VO_CUDA(cudaGetLastError());
+  return VO_OK;
+}
+
+int pnp_score_select_launch(vo_ctx* c, const float3* xyz, const float2* xy, int n, const double* d_models, int32_t* d_counts,
+                            int h, float thr2, double conf, int max_iters, int* d_sel) {
+  if (h <= 0 || n <= 0) return select_launch(c, d_counts, h, 1, 5, n, conf, max_iters, d_sel);
+  dim3 g(div_up(n, SCORE_TPB), div_up(h, SCORE_HB));
+  {
+    LaunchScope ls(c, VO_K_PNP_SCORE);
+    pnp_score_kernel<<<g, SCORE_TPB, 0, c->stream>>>(xyz, xy, n, d_models, d_counts, h, intr(c), thr2, nullptr, c->n_dev,
+                                                    SelectArgs{h, 1, 5, n, conf, max_iters, d_sel, c->d_epoch + 1});
+  }
+  VO_CUDA(cudaGetLastError());
+  return VO_OK;
+}
+
+int pnp_mask_compact_launch(vo_ctx* c, const float3* xyz, const float2* xy, int n, const double* d_models, const int* d_sel,
+                            float thr2, uint8_t* d_mask, int32_t* d_idx, int count_slot) {
+  if (n <= 0) {
+    VO_CUDA(cudaMemsetAsync(c->d_count + count_slot, 0, sizeof(int), c->stream));
+    return VO_OK;
+  }
+  {
+    LaunchScope ls(c, VO_K_COMPACT);
+    mask_compact_kernel<true><<<div_up(n, CP_TILE), CP_THREADS, 0, c->stream>>>(
+        xy, nullptr, xyz, n, d_models, d_sel, intr(c), thr2, d_mask, nullptr, nullptr, nullptr, d_idx, c->d_count + count_slot,
+        c->d_tile_state, c->d_epoch, c->n_dev);
   }
   VO_CUDA(cudaGetLastError());
   return VO_OK;
