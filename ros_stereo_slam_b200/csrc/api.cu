@@ -92,6 +92,7 @@ static int alloc_chain(vo_ctx* c) {
   VO_CUDA(cudaMalloc(&c->d_f_xyz, cap * sizeof(float3)));
   VO_CUDA(cudaMalloc(&c->d_xyz_tmp, cap * sizeof(float3)));
   VO_CUDA(cudaMalloc(&c->d_mask, cap));
+  VO_TRY(refine_init());
   VO_CUDA(cudaMalloc(&c->d_idx, cap * sizeof(int32_t)));
   if (!c->is_aux) {
     VO_CUDA(cudaMalloc(&c->d_seq_xy, cap * sizeof(float2)));

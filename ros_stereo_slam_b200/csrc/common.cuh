@@ -357,6 +357,7 @@ int sample_launch(vo_ctx* c, int model_points, const float2* m1, const float2* m
                   int* d_flag);
 int select_launch(vo_ctx* c, const int32_t* d_counts, int n_samples, int models_per_sample, int model_points, int n_points,
                   double conf, int max_iters, int* d_sel);
+int refine_init();   // constant tables of the refinement kernel (once per process)
 int pnp_refine_launch(vo_ctx* c, const float3* xyz, const float2* xy, const int32_t* d_idx, const int* d_n_inl,
                       const double* d_models, const int* d_sel, double* d_pose);
 

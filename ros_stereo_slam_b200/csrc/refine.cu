@@ -20,6 +20,20 @@ namespace vo {
 constexpr int REF_THREADS = 512;
 constexpr int REF_CLUSTER = 8;   // CTAs per thread-block cluster (portable maximum)
 constexpr int NACC = 28;         // 21 (JtJ upper) + 6 (JtErr) + 1 (|err|^2)
+constexpr int REF_RPT = 4;       // inliers per thread kept in registers across the LM passes (covers 16,384 inliers)
+
+// CvLevMarq's damping factors 10^k as OpenCV forms them, exp(k * log(10.)), k = -16 .. 16: evaluated once on the host
+// instead of two libm calls on the one thread every CTA waits for
+__constant__ double c_lm_lambda[33];
+
+int refine_init() {
+  static int rc = [] {
+    double tab[33];
+    for (int k = -16; k <= 16; k++) tab[k + 16] = exp(k * log(10.));
+    return cudaMemcpyToSymbol(c_lm_lambda, tab, sizeof(tab)) == cudaSuccess ? VO_OK : VO_ERR_CUDA;
+  }();
+  return rc;
+}
 
 struct PoseJac {
   double R[9];
@@ -101,7 +115,7 @@ __device__ void solve6(const double* A_in, const double* b_in, double* x) {
 // reduces to 28 partial sums in its own shared memory, and after a cluster barrier every CTA
 // adds up all partials through distributed shared memory in the same order -- so all CTAs hold
 // bit-identical sums and run the (cheap) LM state machine redundantly instead of broadcasting.
-__global__ void __cluster_dims__(REF_CLUSTER, 1, 1) __launch_bounds__(REF_THREADS)
+__global__ void __cluster_dims__(REF_CLUSTER, 1, 1) __launch_bounds__(REF_THREADS, 1)
 pnp_refine_kernel(const float3* __restrict__ xyz, const float2* __restrict__ xy, const int32_t* __restrict__ idx,
                   const int* __restrict__ n_inl_p, const double* __restrict__ models, const int* __restrict__ sel,
                   Intrinsics K, double* __restrict__ pose_out) {
@@ -121,8 +135,9 @@ pnp_refine_kernel(const float3* __restrict__ xyz, const float2* __restrict__ xy,
     if (t == 0 && rank == 0) pose_out[6] = -1;
     return;
   }
-  // thread-0 state (CvLevMarq), replicated in every CTA
-  double param[6], prev_param[6], JtJ[36], JtErr[6];
+  // thread-0 state (CvLevMarq), replicated in every CTA; in shared memory so that the other 511 threads do not carry
+  // 100 registers of it
+  __shared__ double param[6], prev_param[6], JtJ[36], JtErr[6];
   double prev_err_norm = DBL_MAX, err_norm = 0;
   int lambda_lg10 = -3, iters = 0;
   const int max_iter = 20;
@@ -138,6 +153,22 @@ pnp_refine_kernel(const float3* __restrict__ xyz, const float2* __restrict__ xy,
   }
   __syncthreads();
 
+  // this thread's inliers: gathered once (two dependent global loads each), reused by every pass
+  const int first = rank * REF_THREADS + t;
+  float3 Pk[REF_RPT];
+  float2 qk[REF_RPT];
+#pragma unroll
+  for (int k = 0; k < REF_RPT; k++) {
+    const int i = first + k * REF_CLUSTER * REF_THREADS;
+    Pk[k] = make_float3(0, 0, 1);
+    qk[k] = make_float2(0, 0);
+    if (i < n) {
+      const int id = idx[i];
+      Pk[k] = xyz[id];
+      qk[k] = xy[id];
+    }
+  }
+
   int buf = 0;
   for (int guard = 0; guard < 1000; guard++) {
     const int state = s_state;
@@ -146,17 +177,13 @@ pnp_refine_kernel(const float3* __restrict__ xyz, const float2* __restrict__ xy,
     __syncthreads();
     // J is accumulated on every pass: when a candidate is accepted, the next LM step needs J at
     // exactly this parameter vector, and recomputing it would cost a second pass over the inliers
-    const bool need_j = true;
     double acc[NACC];
 #pragma unroll
     for (int k = 0; k < NACC; k++) acc[k] = 0;
     const double* R = s_pj.R;
     const double* dR = s_pj.dRdr;
     const double t0 = s_param[3], t1 = s_param[4], t2 = s_param[5];
-    for (int i = rank * REF_THREADS + t; i < n; i += REF_CLUSTER * REF_THREADS) {
-      const int id = idx[i];
-      const float3 P = xyz[id];
-      const float2 q = xy[id];
+    auto accumulate = [&](const float3 P, const float2 q) {
       const double X = P.x, Y = P.y, Z = P.z;
       double x = R[0] * X + R[1] * Y + R[2] * Z + t0;
       double y = R[3] * X + R[4] * Y + R[5] * Z + t1;
@@ -167,34 +194,77 @@ pnp_refine_kernel(const float3* __restrict__ xyz, const float2* __restrict__ xy,
       const double ex = (x * K.fx + K.cx) - (double)q.x;
       const double ey = (y * K.fy + K.cy) - (double)q.y;
       acc[27] += ex * ex + ey * ey;
-      if (need_j) {
-        double jx[6], jy[6];
+      double jx[6], jy[6];
 #pragma unroll
-        for (int j = 0; j < 3; j++) {
-          const double dx0 = X * dR[j * 9 + 0] + Y * dR[j * 9 + 1] + Z * dR[j * 9 + 2];
-          const double dy0 = X * dR[j * 9 + 3] + Y * dR[j * 9 + 4] + Z * dR[j * 9 + 5];
-          const double dz0 = X * dR[j * 9 + 6] + Y * dR[j * 9 + 7] + Z * dR[j * 9 + 8];
-          jx[j] = K.fx * (z * (dx0 - x * dz0));
-          jy[j] = K.fy * (z * (dy0 - y * dz0));
-        }
-        jx[3] = K.fx * z; jx[4] = 0; jx[5] = K.fx * (-x * z);
-        jy[3] = 0; jy[4] = K.fy * z; jy[5] = K.fy * (-y * z);
-        int k = 0;
-#pragma unroll
-        for (int a = 0; a < 6; a++)
-#pragma unroll
-          for (int b = a; b < 6; b++) acc[k++] += jx[a] * jx[b] + jy[a] * jy[b];
-#pragma unroll
-        for (int a = 0; a < 6; a++) acc[21 + a] += jx[a] * ex + jy[a] * ey;
+      for (int j = 0; j < 3; j++) {
+        const double dx0 = X * dR[j * 9 + 0] + Y * dR[j * 9 + 1] + Z * dR[j * 9 + 2];
+        const double dy0 = X * dR[j * 9 + 3] + Y * dR[j * 9 + 4] + Z * dR[j * 9 + 5];
+        const double dz0 = X * dR[j * 9 + 6] + Y * dR[j * 9 + 7] + Z * dR[j * 9 + 8];
+        jx[j] = K.fx * (z * (dx0 - x * dz0));
+        jy[j] = K.fy * (z * (dy0 - y * dz0));
       }
+      jx[3] = K.fx * z; jx[4] = 0; jx[5] = K.fx * (-x * z);
+      jy[3] = 0; jy[4] = K.fy * z; jy[5] = K.fy * (-y * z);
+      int k = 0;
+#pragma unroll
+      for (int a = 0; a < 6; a++)
+#pragma unroll
+        for (int b = a; b < 6; b++) acc[k++] += jx[a] * jx[b] + jy[a] * jy[b];
+#pragma unroll
+      for (int a = 0; a < 6; a++) acc[21 + a] += jx[a] * ex + jy[a] * ey;
+    };
+#pragma unroll
+    for (int k = 0; k < REF_RPT; k++)
+      if (first + k * REF_CLUSTER * REF_THREADS < n) accumulate(Pk[k], qk[k]);
+    for (int i = first + REF_RPT * REF_CLUSTER * REF_THREADS; i < n; i += REF_CLUSTER * REF_THREADS) {
+      const int id = idx[i];
+      accumulate(xyz[id], xy[id]);
     }
-    // CTA reduction -> s_part[buf]
+    // CTA reduction -> s_part[buf].  Warp level: a folding butterfly -- at step d a lane keeps the half of its
+    // values its bit d selects and receives the partner's sums of that half, so 32 (padded) accumulators end as one
+    // total per lane after 16+8+4+2+1 exchanges instead of 28 x 5.
+    {
+      double v16[16], v8[8], v4[4], v2[2], v1;
+      {
+        const bool up = lane & 16;
 #pragma unroll
-    for (int k = 0; k < NACC; k++) {
-      double v = acc[k];
+        for (int k = 0; k < 16; k++) {
+          const double lo = acc[k], hi = k + 16 < NACC ? acc[k + 16] : 0.;
+          const double send = up ? lo : hi;
+          v16[k] = (up ? hi : lo) + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+      }
+      {
+        const bool up = lane & 8;
 #pragma unroll
-      for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-      if (lane == 0) s_warp[w * NACC + k] = v;
+        for (int k = 0; k < 8; k++) {
+          const double send = up ? v16[k] : v16[k + 8];
+          v8[k] = (up ? v16[k + 8] : v16[k]) + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+      }
+      {
+        const bool up = lane & 4;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const double send = up ? v8[k] : v8[k + 4];
+          v4[k] = (up ? v8[k + 4] : v8[k]) + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+      }
+      {
+        const bool up = lane & 2;
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+          const double send = up ? v4[k] : v4[k + 2];
+          v2[k] = (up ? v4[k + 2] : v4[k]) + __shfl_xor_sync(0xffffffffu, send, 2);
+        }
+      }
+      {
+        const bool up = lane & 1;
+        const double send = up ? v2[0] : v2[1];
+        v1 = (up ? v2[1] : v2[0]) + __shfl_xor_sync(0xffffffffu, send, 1);
+      }
+      // the lane's value is the warp total of accumulator (lane & 16) + (lane & 8) + ... = lane's bits, i.e. index `lane`
+      if (lane < NACC) s_warp[w * NACC + lane] = v1;
     }
     __syncthreads();
     if (t < NACC) {
@@ -214,7 +284,7 @@ pnp_refine_kernel(const float3* __restrict__ xyz, const float2* __restrict__ xy,
     if (t == 0) {
       // LM step from prev_param with the current JtJ/JtErr and lambda
       auto lm_step = [&]() {
-        const double lambda = exp(lambda_lg10 * log(10.));
+        const double lambda = c_lm_lambda[lambda_lg10 + 16];
         double A[36], x[6];
         for (int i = 0; i < 36; i++) A[i] = JtJ[i];
         for (int i = 0; i < 6; i++) A[i * 6 + i] *= 1. + lambda;
