@@ -2,8 +2,8 @@
 // DBoW2).  SURVEY.md section 8(f)-2.  Every stage is bit-identical to cv2 4.13.0 (oracle/orb.py is the stage-by-stage
 // restatement): the INTER_LINEAR_EXACT pyramid, FAST-9/16 with suppression, the Harris ranking response, IC_Angle,
 // the smoothing ORB really applies, the rBRIEF descriptors (test-pair table recovered from cv2 itself, orb_pattern.h).
-// vo_orb_detect_and_compute runs them per level with OpenCV's selection rules (quota, border filter, retainBest)
-// on the host between the kernels.
+// vo_orb_detect_and_compute runs them for all levels at once with OpenCV's selection rules (quota, border filter,
+// retainBest with ties) on the device: one host synchronisation per frame.
 //
 //   K_rows   the smoothing ORB applies before sampling is NOT OpenCV's fixed-point Gaussian: the pyramid level is a
 //            sub-matrix, for which GaussianBlur falls back to the generic float separable filter.  Row pass:
@@ -50,8 +50,26 @@ struct Orb {
   size_t pyr_bytes = 0;
   int* coef = nullptr;             // resize offsets / weights: ox, cx, oy, cy
   int coef_cap = 0;
-  uint8_t* h_pin = nullptr;        // pinned host scratch of vo_orb_detect_and_compute: image | xy | scalar | descriptors
+  uint8_t* h_pin = nullptr;        // pinned host scratch of vo_orb_detect_and_compute: image | header | packed results
   size_t h_pin_bytes = 0;
+  // vo_orb_detect_and_compute, all levels at once: per-pixel buffers over the concatenated levels, packed results
+  size_t all_px = 0;
+  int* a_score = nullptr;
+  uint8_t* a_flag = nullptr;
+  int* a_sel = nullptr;
+  float* a_rowf = nullptr;
+  uint8_t* a_sm = nullptr;
+  void* a_cub = nullptr;
+  size_t a_cub_bytes = 0;
+  int n_cand = 0;
+  float2* c_xy = nullptr;          // per-level candidate slices: positions ...
+  float* c_resp = nullptr;         // ... and Harris responses
+  int out_cap = 0;
+  float2* o_xy = nullptr;          // packed over the levels: position * level scale, response, angle, descriptor
+  float* o_resp = nullptr;
+  float* o_ang = nullptr;
+  uint8_t* o_desc = nullptr;
+  int* d_hdr = nullptr;            // [0..7] keypoints per level, [8..15] after the first selection, [16] FAST corners
 };
 
 __constant__ signed char c_orb_pattern[256][4];
@@ -60,7 +78,9 @@ __constant__ float c_orb_gauss[4];
 void orb_free(vo_ctx* c) {
   Orb* o = reinterpret_cast<Orb*>(c->orb);
   if (!o) return;
-  void* dev[] = {o->img, o->rowf, o->sm, o->xy, o->ang, o->desc, o->score, o->flag, o->sel, o->d_n, o->cub_tmp, o->pyr, o->coef};
+  void* dev[] = {o->img, o->rowf, o->sm, o->xy, o->ang, o->desc, o->score, o->flag, o->sel, o->d_n, o->cub_tmp, o->pyr, o->coef,
+                 o->a_score, o->a_flag, o->a_sel, o->a_rowf, o->a_sm, o->a_cub, o->c_xy, o->c_resp, o->o_xy, o->o_resp, o->o_ang,
+                 o->o_desc, o->d_hdr};
   for (void* p : dev) cudaFree(p);
   cudaFreeHost(o->h_pin);
   delete o;
@@ -304,6 +324,393 @@ __global__ void orb_describe_kernel(const uint8_t* __restrict__ sm, int w, int h
   desc[(size_t)kp * 32 + byte] = (uint8_t)val;
 }
 
+
+// ======================================================================================== all levels at once
+// vo_orb_detect_and_compute keeps every selection of ORB::detectAndCompute on the device: one launch per stage covers
+// all pyramid levels (blockIdx.z = level, or a flat index decoded through the per-level counts), and the host
+// synchronises once, when the packed result has arrived.
+constexpr int ORB_NL = 8, ORB_EDGE = 31, ORB_FAST_T = 20;
+
+struct OrbLv {
+  const uint8_t* img[ORB_NL];
+  int w[ORB_NL], h[ORB_NL];
+  int px_ofs[ORB_NL + 1];      // level offsets inside the concatenated per-pixel buffers
+  int cand_ofs[ORB_NL + 1];    // level slices of the candidate buffers
+  int quota[ORB_NL];
+  int active[ORB_NL];
+  float scale[ORB_NL];
+};
+
+__device__ __forceinline__ int fast_score_px(const uint8_t* __restrict__ img, int w, int h, int x, int y, int threshold) {
+  int sc = 0;
+  if (x >= 3 && x < w - 3 && y >= 3 && y < h - 3) {
+    const uint8_t* p = img + (size_t)y * w + x;
+    const int v = p[0];
+    int pv[16];
+    unsigned dark = 0u, bright = 0u;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      pv[k] = p[c_fast_dy[k] * w + c_fast_dx[k]];
+      dark |= (unsigned)(pv[k] < v - threshold) << k;
+      bright |= (unsigned)(pv[k] > v + threshold) << k;
+    }
+    if (fast_has9(dark) || fast_has9(bright)) {
+      int best = threshold;
+#pragma unroll
+      for (int k = 0; k < 16; k++) {
+        int mn = pv[k], mx = pv[k];
+#pragma unroll
+        for (int j = 1; j < 9; j++) {
+          mn = min(mn, pv[(k + j) & 15]);
+          mx = max(mx, pv[(k + j) & 15]);
+        }
+        best = max(best, max(v - mx, mn - v));
+      }
+      sc = best - 1;
+    }
+  }
+  return sc;
+}
+
+__global__ void orb_fast_score_all_kernel(const OrbLv lv, int* __restrict__ score) {
+  const int l = blockIdx.z, x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  const int w = lv.w[l], h = lv.h[l];
+  if (x >= w || y >= h) return;
+  score[lv.px_ofs[l] + y * w + x] = lv.active[l] ? fast_score_px(lv.img[l], w, h, x, y, ORB_FAST_T) : 0;
+}
+
+__global__ void orb_fast_nms_all_kernel(const OrbLv lv, const int* __restrict__ score_all, uint8_t* __restrict__ flag) {
+  const int l = blockIdx.z, x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  const int w = lv.w[l], h = lv.h[l];
+  if (x >= w || y >= h) return;
+  const int* score = score_all + lv.px_ofs[l];
+  const int i = y * w + x;
+  const int s = score[i];
+  bool keep = s > 0;
+  if (keep)   // corners live in [3, w-3) x [3, h-3): the 8 neighbours exist
+    keep = s > score[i - 1] && s > score[i + 1] && s > score[i - w - 1] && s > score[i - w] && s > score[i - w + 1] &&
+           s > score[i + w - 1] && s > score[i + w] && s > score[i + w + 1];
+  flag[lv.px_ofs[l] + i] = keep ? 1 : 0;
+}
+
+constexpr int ORB_SEL_T = 1024;
+
+// Ordered append of one tile (one element per thread) by a whole CTA of ORB_SEL_T threads: returns the output position
+// of the calling thread's element (valid if keep) and advances *base (shared) by the tile's count.
+__device__ __forceinline__ int orb_tile_append(bool keep, int* s_wcnt /*32*/, int* s_base) {
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const unsigned b = __ballot_sync(0xffffffffu, keep);
+  if (lane == 0) s_wcnt[w] = __popc(b);
+  __syncthreads();
+  int before = 0, total = 0;
+#pragma unroll 8
+  for (int k = 0; k < ORB_SEL_T / 32; k++) {
+    const int cnt = s_wcnt[k];
+    before += k < w ? cnt : 0;
+    total += cnt;
+  }
+  const int pos = *s_base + before + __popc(b & ((1u << lane) - 1u));
+  __syncthreads();
+  if (t == 0) *s_base += total;
+  __syncthreads();
+  return pos;
+}
+
+// first position in the ascending list sel[0..n) whose value is >= v
+__device__ __forceinline__ int orb_lower_bound(const int* __restrict__ sel, int n, int v) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (sel[mid] < v) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+
+// Per level (one CTA): cv::FAST's corner list of the level (its range of the raster-ordered selection) ->
+// KeyPointsFilter::runByImageBorder(edgeThreshold) -> retainBest(2 * quota) by FAST score, ties kept: the scores are
+// small integers, so the n-th largest is read off a 256-bin histogram.  Survivors keep their raster order.
+__global__ void __launch_bounds__(ORB_SEL_T)
+orb_select1_kernel(const OrbLv lv, const int* __restrict__ sel, const int* __restrict__ n_sel, const int* __restrict__ score,
+                   float2* __restrict__ c_xy, int* __restrict__ hdr) {
+  __shared__ int s_hist[256];
+  __shared__ int s_wcnt[32];
+  __shared__ int s_base, s_thr, s_lo, s_hi;
+  const int l = blockIdx.x, t = threadIdx.x;
+  const int w = lv.w[l], h = lv.h[l];
+  if (t < 256) s_hist[t] = 0;
+  if (t == 0) {
+    const int n = *n_sel;
+    s_lo = orb_lower_bound(sel, n, lv.px_ofs[l]);
+    s_hi = orb_lower_bound(sel, n, lv.px_ofs[l + 1]);
+    s_base = 0;
+    if (l == 0) hdr[16] = n;
+  }
+  __syncthreads();
+  const int lo = s_lo, hi = lv.active[l] ? s_hi : s_lo;
+  for (int i = lo + t; i < hi; i += ORB_SEL_T) {
+    const int q = sel[i] - lv.px_ofs[l];
+    const int x = q % w, y = q / w;
+    if (x >= ORB_EDGE && x < w - ORB_EDGE && y >= ORB_EDGE && y < h - ORB_EDGE) atomicAdd(&s_hist[min(score[lv.px_ofs[l] + q], 255)], 1);
+  }
+  __syncthreads();
+  if (t == 0) {
+    const int target = 2 * lv.quota[l];
+    int m = 0;
+    for (int k = 0; k < 256; k++) m += s_hist[k];
+    int thr = 0;
+    if (m > target) {
+      int cum = 0;
+      for (thr = 255; thr > 0; thr--) {
+        cum += s_hist[thr];
+        if (cum >= target) break;
+      }
+    }
+    s_thr = target > 0 ? thr : 256;
+  }
+  __syncthreads();
+  const int thr = s_thr;
+  float2* out = c_xy + lv.cand_ofs[l];
+  for (int i0 = lo; i0 < hi; i0 += ORB_SEL_T) {
+    const int i = i0 + t;
+    bool keep = false;
+    int x = 0, y = 0;
+    if (i < hi) {
+      const int q = sel[i] - lv.px_ofs[l];
+      x = q % w;
+      y = q / w;
+      keep = x >= ORB_EDGE && x < w - ORB_EDGE && y >= ORB_EDGE && y < h - ORB_EDGE && min(score[lv.px_ofs[l] + q], 255) >= thr;
+    }
+    const int pos = orb_tile_append(keep, s_wcnt, &s_base);
+    if (keep) out[pos] = make_float2((float)x, (float)y);
+  }
+  if (t == 0) hdr[8 + l] = s_base;
+}
+
+// flat index over the per-level counts n[0..8) -> (level, index inside the level); false past the end
+__device__ __forceinline__ bool orb_decode(const int* __restrict__ n, int k, int& l, int& i, int& before) {
+  before = 0;
+#pragma unroll
+  for (int j = 0; j < ORB_NL; j++) {
+    const int c = n[j];
+    if (k < before + c) {
+      l = j;
+      i = k - before;
+      return true;
+    }
+    before += c;
+  }
+  return false;
+}
+
+__device__ __forceinline__ float orb_harris_warp(const uint8_t* __restrict__ img, int w, int x0, int y0, float harris_k, int lane) {
+  long long a = 0, b = 0, c = 0;
+  for (int q = lane; q < 49; q += 32) {
+    const uint8_t* p = img + (size_t)(y0 - 3 + q / 7) * w + (x0 - 3 + q % 7);
+    const int ix = ((int)p[1] - (int)p[-1]) * 2 + ((int)p[-w + 1] - (int)p[-w - 1]) + ((int)p[w + 1] - (int)p[w - 1]);
+    const int iy = ((int)p[w] - (int)p[-w]) * 2 + ((int)p[w - 1] - (int)p[-w - 1]) + ((int)p[w + 1] - (int)p[-w + 1]);
+    a += ix * ix;
+    b += iy * iy;
+    c += ix * iy;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+  }
+  const float scale = __fdiv_rn(1.f, __fmul_rn(28.f, 255.f));       // 1 / ((1 << 2) * blockSize * 255)
+  const float s4 = __fmul_rn(__fmul_rn(__fmul_rn(scale, scale), scale), scale);
+  const float af = (float)(int)a, bf = (float)(int)b, cf = (float)(int)c;   // OpenCV accumulates in int
+  float t = __fsub_rn(__fmul_rn(af, bf), __fmul_rn(cf, cf));
+  const float apb = __fadd_rn(af, bf);
+  t = __fsub_rn(t, __fmul_rn(__fmul_rn(harris_k, apb), apb));
+  return __fmul_rn(t, s4);
+}
+
+// HarrisResponses of the first selection's survivors, all levels: a warp per keypoint, grid-stride
+__global__ void orb_harris_all_kernel(const OrbLv lv, const int* __restrict__ hdr, const float2* __restrict__ c_xy,
+                                      float* __restrict__ c_resp) {
+  const int lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;; k += nwarps) {
+    int l, i, before;
+    if (!orb_decode(hdr + 8, k, l, i, before)) break;
+    const float2 p = c_xy[lv.cand_ofs[l] + i];
+    const float r = orb_harris_warp(lv.img[l], lv.w[l], __float2int_rn(p.x), __float2int_rn(p.y), 0.04f, lane);
+    if (lane == 0) c_resp[lv.cand_ofs[l] + i] = r;
+  }
+}
+
+// order-preserving key of a float (-0 counts as +0, like the float comparison it stands for)
+__device__ __forceinline__ unsigned orb_float_key(float f) {
+  unsigned u = __float_as_uint(f == 0.f ? 0.f : f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// Per level (one CTA): retainBest(quota) by Harris response -- the quota-th largest response by an exact radix select
+// on the float keys (four 8-bit passes), everything >= it stays (ties included), raster order kept, in place.
+__global__ void __launch_bounds__(ORB_SEL_T)
+orb_select2_kernel(const OrbLv lv, float2* __restrict__ c_xy, float* __restrict__ c_resp, int* __restrict__ hdr) {
+  __shared__ int s_hist[256];
+  __shared__ int s_wcnt[32];
+  __shared__ int s_base, s_k;
+  __shared__ unsigned s_prefix;
+  const int l = blockIdx.x, t = threadIdx.x;
+  const int n = hdr[8 + l], quota = lv.quota[l];
+  float2* xy = c_xy + lv.cand_ofs[l];
+  float* resp = c_resp + lv.cand_ofs[l];
+  unsigned thr_key = 0;     // keep everything
+  if (n > quota && quota > 0) {
+    if (t == 0) {
+      s_prefix = 0;
+      s_k = quota;
+    }
+    for (int pass = 0; pass < 4; pass++) {
+      const int shift = 24 - 8 * pass;
+      if (t < 256) s_hist[t] = 0;
+      __syncthreads();
+      const unsigned prefix = s_prefix, pmask = pass == 0 ? 0u : 0xffffffffu << (shift + 8);
+      for (int i = t; i < n; i += ORB_SEL_T) {
+        const unsigned key = orb_float_key(resp[i]);
+        if ((key & pmask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1);
+      }
+      __syncthreads();
+      if (t == 0) {
+        int k = s_k, d = 255;
+        for (; d > 0; d--) {
+          if (s_hist[d] >= k) break;
+          k -= s_hist[d];
+        }
+        s_k = k;
+        s_prefix = prefix | ((unsigned)d << shift);
+      }
+      __syncthreads();
+    }
+    thr_key = s_prefix;
+  }
+  if (t == 0) s_base = 0;
+  __syncthreads();
+  const int n_in = quota > 0 ? n : 0;
+  for (int i0 = 0; i0 < n_in; i0 += ORB_SEL_T) {
+    const int i = i0 + t;
+    bool keep = false;
+    float2 p = make_float2(0.f, 0.f);
+    float r = 0.f;
+    if (i < n_in) {
+      p = xy[i];
+      r = resp[i];
+      keep = orb_float_key(r) >= thr_key;
+    }
+    const int pos = orb_tile_append(keep, s_wcnt, &s_base);   // (its barriers separate this tile's reads from its writes)
+    if (keep) {
+      xy[pos] = p;
+      resp[pos] = r;
+    }
+  }
+  if (t == 0) hdr[l] = s_base;
+}
+
+// ICAngles of the final keypoints of all levels (warp per keypoint, grid-stride); lane 0 also writes the keypoint's
+// packed position (level coordinates times the level scale) and response
+__global__ void orb_angle_all_kernel(const OrbLv lv, const int* __restrict__ hdr, const float2* __restrict__ c_xy,
+                                     const float* __restrict__ c_resp, int out_cap, float2* __restrict__ o_xy,
+                                     float* __restrict__ o_resp, float* __restrict__ o_ang) {
+  const int lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < out_cap; k += nwarps) {
+    int l, i, before;
+    if (!orb_decode(hdr, k, l, i, before)) break;
+    const float2 p = c_xy[lv.cand_ofs[l] + i];
+    const int w = lv.w[l];
+    const int cx = __float2int_rn(p.x), cy = __float2int_rn(p.y);
+    const int u = lane - 15;
+    int m10 = 0, m01 = 0;
+    if (lane < 31) {
+      const uint8_t* c = lv.img[l] + (size_t)cy * w + cx + u;
+      int col = c[0];
+      const int au = abs(u);
+      for (int v = 1; v <= 15; v++) {
+        if (au <= c_orb_umax[v]) {
+          const int vp = c[v * w], vm = c[-v * w];
+          col += vp + vm;
+          m01 += v * (vp - vm);
+        }
+      }
+      m10 = u * col;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      m10 += __shfl_xor_sync(0xffffffffu, m10, o);
+      m01 += __shfl_xor_sync(0xffffffffu, m01, o);
+    }
+    if (lane == 0) {
+      o_ang[k] = orb_fast_atan2((float)m01, (float)m10);
+      o_xy[k] = make_float2(__fmul_rn(p.x, lv.scale[l]), __fmul_rn(p.y, lv.scale[l]));   // allKeypoints[i].pt *= scale
+      o_resp[k] = c_resp[lv.cand_ofs[l] + i];
+    }
+  }
+}
+
+__global__ void orb_smooth_rows_all_kernel(const OrbLv lv, float* __restrict__ rowf) {
+  const int l = blockIdx.z, x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  const int w = lv.w[l], h = lv.h[l];
+  if (x >= w || y >= h || !lv.active[l]) return;
+  const uint8_t* r = lv.img[l] + (size_t)y * w;
+  float s = __fmul_rn(c_orb_gauss[0], (float)r[orb_reflect101(x - 3, w)]);
+#pragma unroll
+  for (int j = 1; j < 7; j++) s = __fmaf_rn(c_orb_gauss[j < 4 ? j : 6 - j], (float)r[orb_reflect101(x - 3 + j, w)], s);
+  rowf[lv.px_ofs[l] + y * w + x] = s;
+}
+
+__global__ void orb_smooth_cols_all_kernel(const OrbLv lv, const float* __restrict__ rowf_all, uint8_t* __restrict__ out) {
+  const int l = blockIdx.z, x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  const int w = lv.w[l], h = lv.h[l];
+  if (x >= w || y >= h || !lv.active[l]) return;
+  const float* rowf = rowf_all + lv.px_ofs[l];
+  float t = __fmul_rn(c_orb_gauss[3], rowf[(size_t)y * w + x]);
+#pragma unroll
+  for (int j = 1; j < 4; j++) {
+    const float a = rowf[(size_t)orb_reflect101(y + j, h) * w + x], b = rowf[(size_t)orb_reflect101(y - j, h) * w + x];
+    t = __fmaf_rn(c_orb_gauss[3 - j], __fadd_rn(a, b), t);
+  }
+  const int v = __float2int_rn(t);
+  out[lv.px_ofs[l] + y * w + x] = (uint8_t)min(max(v, 0), 255);
+}
+
+// computeOrbDescriptors of the final keypoints of all levels: a thread per (keypoint, descriptor byte), grid-stride
+__global__ void orb_describe_all_kernel(const OrbLv lv, const int* __restrict__ hdr, const float2* __restrict__ c_xy,
+                                        const float* __restrict__ o_ang, const uint8_t* __restrict__ sm_all, int out_cap,
+                                        uint8_t* __restrict__ o_desc) {
+  const int byte = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < out_cap; k += nwarps) {
+    int l, i, before;
+    if (!orb_decode(hdr, k, l, i, before)) break;
+    const float2 p = c_xy[lv.cand_ofs[l] + i];
+    const int w = lv.w[l];
+    float angle = o_ang[k];
+    angle = __fmul_rn(angle, (float)(3.14159265358979323846 / 180.0));      // angle *= (float)(CV_PI / 180.f)
+    const float a = (float)cos((double)angle), b = (float)sin((double)angle);
+    const uint8_t* center = sm_all + lv.px_ofs[l] + (size_t)__float2int_rn(p.y) * w + __float2int_rn(p.x);
+    unsigned val = 0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const signed char* pt = c_orb_pattern[8 * byte + q];
+      int v[2];
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const float px = (float)pt[2 * e], py = (float)pt[2 * e + 1];
+        const float x = __fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b));
+        const float y = __fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a));
+        v[e] = center[__float2int_rn(y) * w + __float2int_rn(x)];
+      }
+      val |= (unsigned)(v[0] < v[1]) << q;
+    }
+    o_desc[(size_t)k * 32 + byte] = (uint8_t)val;
+  }
+}
+
 static int orb_ensure(vo_ctx* c, int w, int h, int n) {
   Orb* o = reinterpret_cast<Orb*>(c->orb);
   if (!o) {
@@ -359,6 +766,53 @@ static int orb_ensure_fast(vo_ctx* c, Orb* o) {
   o->px_cap = npx;
   return VO_OK;
 }
+
+// buffers of the all-level pipeline (vo_orb_detect_and_compute)
+static int orb_ensure_all(vo_ctx* c, Orb* o, size_t all_px, int n_cand, int out_cap) {
+  if (!o->d_hdr) {
+    VO_CUDA(cudaMalloc(&o->d_hdr, 32 * sizeof(int)));
+    VO_CUDA(cudaMemsetAsync(o->d_hdr, 0, 32 * sizeof(int), c->stream));
+  }
+  if (all_px > o->all_px) {
+    VO_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(o->a_score); cudaFree(o->a_flag); cudaFree(o->a_sel); cudaFree(o->a_rowf); cudaFree(o->a_sm); cudaFree(o->a_cub);
+    o->a_score = nullptr; o->a_flag = nullptr; o->a_sel = nullptr; o->a_rowf = nullptr; o->a_sm = nullptr; o->a_cub = nullptr;
+    o->all_px = 0;
+    VO_CUDA(cudaMalloc(&o->a_score, all_px * sizeof(int)));
+    VO_CUDA(cudaMalloc(&o->a_flag, all_px));
+    VO_CUDA(cudaMalloc(&o->a_sel, all_px * sizeof(int)));
+    VO_CUDA(cudaMalloc(&o->a_rowf, all_px * sizeof(float)));
+    VO_CUDA(cudaMalloc(&o->a_sm, all_px));
+    size_t tb = 0;
+    VO_CUDA(cub::DeviceSelect::Flagged(nullptr, tb, cub::CountingInputIterator<int>(0), (const uint8_t*)nullptr, (int*)nullptr,
+                                       (int*)nullptr, (int)all_px, c->stream));
+    o->a_cub_bytes = tb;
+    VO_CUDA(cudaMalloc(&o->a_cub, tb + 256));
+    o->all_px = all_px;
+  }
+  if (n_cand > o->n_cand) {
+    VO_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(o->c_xy); cudaFree(o->c_resp);
+    o->c_xy = nullptr; o->c_resp = nullptr;
+    o->n_cand = 0;
+    VO_CUDA(cudaMalloc(&o->c_xy, (size_t)n_cand * sizeof(float2)));
+    VO_CUDA(cudaMalloc(&o->c_resp, (size_t)n_cand * sizeof(float)));
+    o->n_cand = n_cand;
+  }
+  if (out_cap > o->out_cap) {
+    VO_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(o->o_xy); cudaFree(o->o_resp); cudaFree(o->o_ang); cudaFree(o->o_desc);
+    o->o_xy = nullptr; o->o_resp = nullptr; o->o_ang = nullptr; o->o_desc = nullptr;
+    o->out_cap = 0;
+    VO_CUDA(cudaMalloc(&o->o_xy, (size_t)out_cap * sizeof(float2)));
+    VO_CUDA(cudaMalloc(&o->o_resp, (size_t)out_cap * sizeof(float)));
+    VO_CUDA(cudaMalloc(&o->o_ang, (size_t)out_cap * sizeof(float)));
+    VO_CUDA(cudaMalloc(&o->o_desc, (size_t)out_cap * 32));
+    o->out_cap = out_cap;
+  }
+  return VO_OK;
+}
+
 
 static int orb_smooth_enqueue(vo_ctx* c, Orb* o, const uint8_t* img, int stride, int w, int h) {
   VO_CUDA(cudaMemcpy2DAsync(o->img, w, img, stride, w, h, cudaMemcpyDefault, c->stream));
@@ -542,29 +996,6 @@ void orb_exact_coeffs(int srcsize, int dstsize, int* ofs, int* c1) {
   }
 }
 
-// what one pyramid level contributes to the result
-struct OrbLevelOut {
-  int level = 0, n = 0, pin_ofs = 0;     // pin_ofs: where its angles / descriptors sit in the pinned result staging
-  std::vector<float> xy, resp;
-};
-
-// KeyPointsFilter::retainBest: every keypoint whose response is >= the n-th largest stays (ties included)
-std::vector<int> orb_retain_best(const std::vector<float>& resp, int n) {
-  std::vector<int> keep;
-  if (n <= 0) return keep;
-  if ((int)resp.size() <= n) {
-    keep.resize(resp.size());
-    std::iota(keep.begin(), keep.end(), 0);
-    return keep;
-  }
-  std::vector<float> tmp(resp);
-  std::nth_element(tmp.begin(), tmp.begin() + (n - 1), tmp.end(), std::greater<float>());
-  const float thr = tmp[n - 1];
-  for (int i = 0; i < (int)resp.size(); i++)
-    if (resp[i] >= thr) keep.push_back(i);
-  return keep;
-}
-
 }  // namespace
 
 int vo_orb_detect_and_compute(vo_ctx* c, const uint8_t* img, int stride, int width, int height, int nfeatures, float* xy,
@@ -576,7 +1007,7 @@ int vo_orb_detect_and_compute(vo_ctx* c, const uint8_t* img, int stride, int wid
   *n_out = 0;
   // ORB::create() defaults (the reference passes none, src/optimizationStuff.cpp:49): scaleFactor 1.2f kept in a
   // double, 8 levels, edgeThreshold 31, firstLevel 0, WTA_K 2, HARRIS_SCORE, patchSize 31, fastThreshold 20
-  constexpr int NL = 8, EDGE = 31, FAST_T = 20;
+  constexpr int NL = ORB_NL, EDGE = ORB_EDGE;
   const double scale_factor = (double)1.2f;
   float lscale[NL];
   int lw[NL], lh[NL], quota[NL];
@@ -597,17 +1028,24 @@ int vo_orb_detect_and_compute(vo_ctx* c, const uint8_t* img, int stride, int wid
     quota[NL - 1] = std::max(nfeatures - sum, 0);
   }
   // per-level slices of the candidate buffers: after 3x3 suppression there is at most one corner per 2x2 pixels
-  bool active[NL];
-  int cand_ofs[NL + 1];
-  cand_ofs[0] = 0;
+  OrbLv lv;
+  lv.px_ofs[0] = 0;
+  lv.cand_ofs[0] = 0;
   for (int l = 0; l < NL; l++) {
-    active[l] = lw[l] > 2 * EDGE && lh[l] > 2 * EDGE && quota[l] > 0;      // else the border filter leaves nothing
-    cand_ofs[l + 1] = cand_ofs[l] + (active[l] ? lw[l] * lh[l] / 4 + 16 : 0);
+    lv.w[l] = lw[l];
+    lv.h[l] = lh[l];
+    lv.quota[l] = quota[l];
+    lv.scale[l] = lscale[l];
+    lv.active[l] = lw[l] > 2 * EDGE && lh[l] > 2 * EDGE && quota[l] > 0;      // else the border filter leaves nothing
+    lv.px_ofs[l + 1] = lv.px_ofs[l] + lw[l] * lh[l];
+    lv.cand_ofs[l + 1] = lv.cand_ofs[l] + (lv.active[l] ? lw[l] * lh[l] / 4 + 16 : 0);
   }
-  const int n_cand = std::max(cand_ofs[NL], 1);
-  VO_TRY(orb_ensure(c, width, height, n_cand));
+  const int n_cand = std::max(lv.cand_ofs[NL], 1);
+  const size_t all_px = (size_t)lv.px_ofs[NL];
+  VO_TRY(orb_ensure(c, width, height, 1));
   Orb* o = reinterpret_cast<Orb*>(c->orb);
-  VO_TRY(orb_ensure_fast(c, o));
+  const int DESC_CAP = std::max(8192, 2 * nfeatures + 4096);     // keypoints the packed result holds
+  VO_TRY(orb_ensure_all(c, o, all_px, n_cand, DESC_CAP));
   // pyramid levels 1.. and the resize tables
   size_t pyr_need = 0;
   for (int l = 1; l < NL; l++) pyr_need += (size_t)lw[l] * lh[l];
@@ -620,212 +1058,141 @@ int vo_orb_detect_and_compute(vo_ctx* c, const uint8_t* img, int stride, int wid
   }
   // the resize tables of all levels in one upload, then the whole pyramid: resize(prevImg, currImg, sz, 0, 0,
   // INTER_LINEAR_EXACT), each level from the previous one
-  std::vector<int> h_coef;
   size_t coef_ofs[NL] = {0};
+  size_t n_coef = 0;
   for (int l = 1; l < NL; l++) {
-    coef_ofs[l] = h_coef.size();
-    h_coef.resize(h_coef.size() + 2 * (size_t)(lw[l] + lh[l]));
-    int* t = h_coef.data() + coef_ofs[l];
-    orb_exact_coeffs(lw[l - 1], lw[l], t, t + lw[l]);
-    orb_exact_coeffs(lh[l - 1], lh[l], t + 2 * lw[l], t + 2 * lw[l] + lh[l]);
+    coef_ofs[l] = n_coef;
+    n_coef += 2 * (size_t)(lw[l] + lh[l]);
   }
-  if ((int)h_coef.size() > o->coef_cap) {
+  if ((int)n_coef > o->coef_cap) {
     VO_CUDA(cudaStreamSynchronize(c->stream));
     cudaFree(o->coef);
     o->coef = nullptr;
-    VO_CUDA(cudaMalloc(&o->coef, h_coef.size() * sizeof(int)));
-    o->coef_cap = (int)h_coef.size();
+    VO_CUDA(cudaMalloc(&o->coef, n_coef * sizeof(int)));
+    o->coef_cap = (int)n_coef;
   }
-  // pinned scratch: pageable copies are staged by the driver at a few GB/s and serialise with the stream
-  const int DESC_CAP = std::max(8192, 2 * nfeatures + 4096);     // keypoints the result staging holds
-  // every section starts 16-byte aligned (float views, aligned async copies)
-  const size_t pin_img = (((size_t)width * height) + 15) & ~(size_t)15, pin_xy = 2 * (size_t)o->cap * sizeof(float),
-               pin_sc = (size_t)o->cap * sizeof(float), pin_desc = (size_t)DESC_CAP * (32 + sizeof(float)) + 64;
-  if (pin_img + pin_xy + pin_sc + pin_desc > o->h_pin_bytes) {
+  // pinned scratch (pageable copies are staged by the driver at a few GB/s and serialise with the stream):
+  // image | resize tables | header | packed results; every section 16-byte aligned
+  const size_t pin_img = (((size_t)width * height) + 15) & ~(size_t)15, pin_coef = ((n_coef * sizeof(int)) + 15) & ~(size_t)15,
+               pin_hdr = 32 * sizeof(int), pin_out = (size_t)DESC_CAP * (8 + 4 + 4 + 32);
+  if (pin_img + pin_coef + pin_hdr + pin_out > o->h_pin_bytes) {
     VO_CUDA(cudaStreamSynchronize(c->stream));
     cudaFreeHost(o->h_pin);
     o->h_pin = nullptr;
     o->h_pin_bytes = 0;
-    VO_CUDA(cudaMallocHost(&o->h_pin, pin_img + pin_xy + pin_sc + pin_desc));
-    o->h_pin_bytes = pin_img + pin_xy + pin_sc + pin_desc;
+    VO_CUDA(cudaMallocHost(&o->h_pin, pin_img + pin_coef + pin_hdr + pin_out));
+    o->h_pin_bytes = pin_img + pin_coef + pin_hdr + pin_out;
   }
-  float* p_xy = reinterpret_cast<float*>(o->h_pin + pin_img);
-  float* p_sc = reinterpret_cast<float*>(o->h_pin + pin_img + pin_xy);
-  uint8_t* p_desc = o->h_pin + pin_img + pin_xy + pin_sc;                    // descriptors of all levels, appended
-  float* p_ang = reinterpret_cast<float*>(p_desc + (size_t)DESC_CAP * 32);   // their angles
+  int* p_coef = reinterpret_cast<int*>(o->h_pin + pin_img);
+  int* p_hdr = reinterpret_cast<int*>(o->h_pin + pin_img + pin_coef);
+  float* p_xy = reinterpret_cast<float*>(o->h_pin + pin_img + pin_coef + pin_hdr);
+  float* p_resp = p_xy + 2 * (size_t)DESC_CAP;
+  float* p_ang = p_resp + DESC_CAP;
+  uint8_t* p_desc = reinterpret_cast<uint8_t*>(p_ang + DESC_CAP);
+  for (int l = 1; l < NL; l++) {
+    int* t = p_coef + coef_ofs[l];
+    orb_exact_coeffs(lw[l - 1], lw[l], t, t + lw[l]);
+    orb_exact_coeffs(lh[l - 1], lh[l], t + 2 * lw[l], t + 2 * lw[l] + lh[l]);
+  }
   for (int y = 0; y < height; y++) memcpy(o->h_pin + (size_t)y * width, img + (size_t)y * stride, width);
   VO_CUDA(cudaMemcpyAsync(o->img, o->h_pin, (size_t)width * height, cudaMemcpyHostToDevice, c->stream));
-  VO_CUDA(cudaMemcpyAsync(o->coef, h_coef.data(), h_coef.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-  const uint8_t* level[NL];
-  level[0] = o->img;
+  VO_CUDA(cudaMemcpyAsync(o->coef, p_coef, n_coef * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  lv.img[0] = o->img;
   {
     uint8_t* next = o->pyr;
     for (int l = 1; l < NL; l++) {
       const int* t = o->coef + coef_ofs[l];
       LaunchScope ls(c, VO_K_MISC);
-      orb_resize_exact_kernel<<<dim3(div_up(lw[l], 128), lh[l]), 128, 0, c->stream>>>(level[l - 1], lw[l - 1], lh[l - 1], next, lw[l],
+      orb_resize_exact_kernel<<<dim3(div_up(lw[l], 128), lh[l]), 128, 0, c->stream>>>(lv.img[l - 1], lw[l - 1], lh[l - 1], next, lw[l],
                                                                                     lh[l], t, t + lw[l], t + 2 * lw[l],
                                                                                     t + 2 * lw[l] + lh[l]);
-      level[l] = next;
+      lv.img[l] = next;
       next += (size_t)lw[l] * lh[l];
     }
   }
-
-  // ---- phase 1: FAST (threshold 20, suppression) on every level, corners and scores into the level's slice
-  for (int l = 0; l < NL; l++) {
-    if (!active[l]) continue;
-    const int w = lw[l], h = lh[l];
-    {
-      LaunchScope ls(c, VO_K_MISC);
-      fast_score_kernel<<<dim3(div_up(w, 128), h), 128, 0, c->stream>>>(level[l], w, h, FAST_T, o->score);
-    }
-    {
-      LaunchScope ls(c, VO_K_MISC);
-      fast_nms_kernel<<<dim3(div_up(w, 128), h), 128, 0, c->stream>>>(o->score, w, h, 1, o->flag);
-    }
-    size_t tb = o->cub_bytes;
-    VO_CUDA(cub::DeviceSelect::Flagged(o->cub_tmp, tb, cub::CountingInputIterator<int>(0), o->flag, o->sel, o->d_n + l, w * h,
-                                       c->stream));
+  // ---- FAST (threshold 20, suppression) on every level: one score launch, one suppression launch, one raster-ordered
+  // selection over the concatenated levels
+  const dim3 g_px(div_up(width, 128), height, NL);
+  {
+    LaunchScope ls(c, VO_K_MISC);
+    orb_fast_score_all_kernel<<<g_px, 128, 0, c->stream>>>(lv, o->a_score);
+  }
+  {
+    LaunchScope ls(c, VO_K_MISC);
+    orb_fast_nms_all_kernel<<<g_px, 128, 0, c->stream>>>(lv, o->a_score, o->a_flag);
+  }
+  {
+    size_t tb = o->a_cub_bytes;
+    VO_CUDA(cub::DeviceSelect::Flagged(o->a_cub, tb, cub::CountingInputIterator<int>(0), o->a_flag, o->a_sel, o->d_hdr + 17,
+                                       (int)all_px, c->stream));
     c->launch_count++;
-    const int ccap = cand_ofs[l + 1] - cand_ofs[l];
-    {
-      LaunchScope ls(c, VO_K_MISC);
-      fast_gather_kernel<<<div_up(ccap, 256), 256, 0, c->stream>>>(o->sel, o->d_n + l, ccap, o->score, w, o->xy + 2 * cand_ofs[l],
-                                                                   o->ang + cand_ofs[l]);
-    }
+  }
+  // ---- runByImageBorder + retainBest(2 * quota) by FAST score, HarrisResponses, retainBest(quota) by response
+  {
+    LaunchScope ls(c, VO_K_MISC);
+    orb_select1_kernel<<<NL, ORB_SEL_T, 0, c->stream>>>(lv, o->a_sel, o->d_hdr + 17, o->a_score, o->c_xy, o->d_hdr);
+  }
+  {
+    LaunchScope ls(c, VO_K_MISC);
+    orb_harris_all_kernel<<<296, 256, 0, c->stream>>>(lv, o->d_hdr, o->c_xy, o->c_resp);
+  }
+  {
+    LaunchScope ls(c, VO_K_MISC);
+    orb_select2_kernel<<<NL, ORB_SEL_T, 0, c->stream>>>(lv, o->c_xy, o->c_resp, o->d_hdr);
+  }
+  // ---- ICAngles on the unsmoothed levels, GaussianBlur of the levels, computeOrbDescriptors; the order inside a level is
+  // raster (y, x), OpenCV's is what std::nth_element leaves
+  {
+    LaunchScope ls(c, VO_K_MISC);
+    orb_angle_all_kernel<<<296, 256, 0, c->stream>>>(lv, o->d_hdr, o->c_xy, o->c_resp, DESC_CAP, o->o_xy, o->o_resp, o->o_ang);
+  }
+  {
+    LaunchScope ls(c, VO_K_MISC);
+    orb_smooth_rows_all_kernel<<<g_px, 128, 0, c->stream>>>(lv, o->a_rowf);
+  }
+  {
+    LaunchScope ls(c, VO_K_MISC);
+    orb_smooth_cols_all_kernel<<<g_px, 128, 0, c->stream>>>(lv, o->a_rowf, o->a_sm);
+  }
+  {
+    LaunchScope ls(c, VO_K_MISC);
+    orb_describe_all_kernel<<<592, 256, 0, c->stream>>>(lv, o->d_hdr, o->c_xy, o->o_ang, o->a_sm, DESC_CAP, o->o_desc);
   }
   VO_CUDA(cudaGetLastError());
-  int* p_cnt = reinterpret_cast<int*>(p_ang + DESC_CAP);
-  VO_CUDA(cudaMemcpyAsync(p_cnt, o->d_n, NL * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  VO_CUDA(cudaStreamSynchronize(c->stream));
-  int nc[NL];
-  for (int l = 0; l < NL; l++) {
-    nc[l] = active[l] ? std::min(p_cnt[l], cand_ofs[l + 1] - cand_ofs[l]) : 0;
-    if (nc[l] == 0) continue;
-    VO_CUDA(cudaMemcpyAsync(p_xy + 2 * cand_ofs[l], o->xy + 2 * cand_ofs[l], 2 * (size_t)nc[l] * sizeof(float),
-                            cudaMemcpyDeviceToHost, c->stream));
-    VO_CUDA(cudaMemcpyAsync(p_sc + cand_ofs[l], o->ang + cand_ofs[l], (size_t)nc[l] * sizeof(float), cudaMemcpyDeviceToHost,
-                            c->stream));
-  }
-  VO_CUDA(cudaStreamSynchronize(c->stream));
-
-  // ---- phase 2: KeyPointsFilter::runByImageBorder(edgeThreshold), retainBest(2 * featuresNum) by FAST score, then
-  // HarrisResponses of the survivors on every level
-  std::vector<float> sxy[NL];
-  int n1[NL];
-  for (int l = 0; l < NL; l++) {
-    n1[l] = 0;
-    if (nc[l] == 0) continue;
-    const int w = lw[l], h = lh[l];
-    const float* h_xy = p_xy + 2 * cand_ofs[l];
-    const float* h_sc = p_sc + cand_ofs[l];
-    std::vector<float> kxy, ksc;
-    for (int i = 0; i < nc[l]; i++) {
-      const float x = h_xy[2 * i], y = h_xy[2 * i + 1];
-      if (x >= EDGE && x < w - EDGE && y >= EDGE && y < h - EDGE) {
-        kxy.push_back(x);
-        kxy.push_back(y);
-        ksc.push_back(h_sc[i]);
-      }
-    }
-    const std::vector<int> keep = orb_retain_best(ksc, 2 * quota[l]);
-    for (int i : keep) {
-      sxy[l].push_back(kxy[2 * i]);
-      sxy[l].push_back(kxy[2 * i + 1]);
-    }
-    n1[l] = (int)keep.size();
-  }
-  for (int l = 0; l < NL; l++) {
-    if (n1[l] == 0) continue;
-    float* px = p_xy + 2 * cand_ofs[l];            // the phase-1 results in this slice have been consumed
-    memcpy(px, sxy[l].data(), sxy[l].size() * sizeof(float));
-    VO_CUDA(cudaMemcpyAsync(o->xy + 2 * cand_ofs[l], px, sxy[l].size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    {
-      LaunchScope ls(c, VO_K_MISC);
-      orb_harris_kernel<<<div_up(n1[l] * 32, 256), 256, 0, c->stream>>>(level[l], lw[l], lh[l], o->xy + 2 * cand_ofs[l], n1[l], 0.04f,
-                                                                       o->ang + cand_ofs[l]);
-    }
-    VO_CUDA(cudaMemcpyAsync(p_sc + cand_ofs[l], o->ang + cand_ofs[l], (size_t)n1[l] * sizeof(float), cudaMemcpyDeviceToHost,
-                            c->stream));
-  }
-  VO_CUDA(cudaGetLastError());
-  VO_CUDA(cudaStreamSynchronize(c->stream));
-
-  // ---- phase 3: retainBest(featuresNum) by Harris response, then ICAngles on the unsmoothed level, GaussianBlur of the
-  // level and computeOrbDescriptors; the order inside a level is raster (y, x), OpenCV's is what std::nth_element leaves
-  std::vector<OrbLevelOut> pending;
-  int pin_used = 0;
-  for (int l = 0; l < NL; l++) {
-    if (n1[l] == 0) continue;
-    const int w = lw[l], h = lh[l];
-    const float* resp = p_sc + cand_ofs[l];
-    const std::vector<float> h_resp(resp, resp + n1[l]);
-    std::vector<int> keep = orb_retain_best(h_resp, quota[l]);
-    const std::vector<float>& sx = sxy[l];
-    std::sort(keep.begin(), keep.end(), [&](int a, int b) {
-      return sx[2 * a + 1] != sx[2 * b + 1] ? sx[2 * a + 1] < sx[2 * b + 1] : sx[2 * a] < sx[2 * b];
-    });
-    const int n2 = (int)keep.size();
-    if (n2 == 0) continue;
-    if (pin_used + n2 > DESC_CAP) {
-      set_error("vo_orb_detect_and_compute: more than %d keypoints", DESC_CAP);
-      cudaStreamSynchronize(c->stream);   // kernels and copies into the pinned staging of earlier levels are still in flight
-      return VO_ERR_CAPACITY;
-    }
-    OrbLevelOut rec;
-    rec.level = l;
-    rec.n = n2;
-    rec.pin_ofs = pin_used;
-    rec.xy.resize(2 * (size_t)n2);
-    rec.resp.resize(n2);
-    for (int i = 0; i < n2; i++) {
-      rec.xy[2 * i] = sx[2 * keep[i]];
-      rec.xy[2 * i + 1] = sx[2 * keep[i] + 1];
-      rec.resp[i] = h_resp[keep[i]];
-    }
-    float* px = p_xy + 2 * cand_ofs[l];
-    memcpy(px, rec.xy.data(), rec.xy.size() * sizeof(float));
-    float* d_xy = o->xy + 2 * cand_ofs[l];
-    float* d_ang = o->ang + cand_ofs[l];
-    uint8_t* d_desc = o->desc + (size_t)cand_ofs[l] * 32;
-    VO_CUDA(cudaMemcpyAsync(d_xy, px, rec.xy.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    {
-      LaunchScope ls(c, VO_K_MISC);
-      orb_angle_kernel<<<div_up(n2 * 32, 256), 256, 0, c->stream>>>(level[l], w, h, d_xy, n2, d_ang);
-    }
-    {
-      LaunchScope ls(c, VO_K_MISC);
-      orb_smooth_rows_kernel<<<dim3(div_up(w, 128), h), 128, 0, c->stream>>>(level[l], w, h, o->rowf);
-    }
-    {
-      LaunchScope ls(c, VO_K_MISC);
-      orb_smooth_cols_kernel<<<dim3(div_up(w, 128), h), 128, 0, c->stream>>>(o->rowf, w, h, o->sm);
-    }
-    {
-      LaunchScope ls(c, VO_K_MISC);
-      orb_describe_kernel<<<div_up(n2 * 32, 256), 256, 0, c->stream>>>(o->sm, w, h, d_xy, d_ang, n2, d_desc);
-    }
-    VO_CUDA(cudaMemcpyAsync(p_ang + pin_used, d_ang, (size_t)n2 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    VO_CUDA(cudaMemcpyAsync(p_desc + (size_t)pin_used * 32, d_desc, (size_t)n2 * 32, cudaMemcpyDeviceToHost, c->stream));
-    pin_used += n2;
-    pending.push_back(std::move(rec));
-  }
-  VO_CUDA(cudaGetLastError());
+  // the packed result: the header and the first `guess` keypoints travel before the one synchronisation; a frame with
+  // more (ties at a selection threshold) fetches the remainder afterwards
+  const int guess = std::min(DESC_CAP, nfeatures + 512);
+  auto fetch = [&](int from, int to) -> int {
+    const size_t m = (size_t)(to - from);
+    VO_CUDA(cudaMemcpyAsync(p_xy + 2 * (size_t)from, o->o_xy + from, m * sizeof(float2), cudaMemcpyDeviceToHost, c->stream));
+    VO_CUDA(cudaMemcpyAsync(p_resp + from, o->o_resp + from, m * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    VO_CUDA(cudaMemcpyAsync(p_ang + from, o->o_ang + from, m * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    VO_CUDA(cudaMemcpyAsync(p_desc + (size_t)from * 32, o->o_desc + (size_t)from * 32, m * 32, cudaMemcpyDeviceToHost, c->stream));
+    return VO_OK;
+  };
+  VO_CUDA(cudaMemcpyAsync(p_hdr, o->d_hdr, 18 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  VO_TRY(fetch(0, guess));
   VO_CUDA(cudaStreamSynchronize(c->stream));
   int total = 0;
-  for (const auto& r : pending) {
-    const float* ang = p_ang + r.pin_ofs;
-    const uint8_t* dsc = p_desc + (size_t)r.pin_ofs * 32;
-    for (int i = 0; i < r.n; i++) {
-      if (total < cap) {
-        xy[2 * total] = r.xy[2 * i] * lscale[r.level];          // allKeypoints[i].pt *= scale
-        xy[2 * total + 1] = r.xy[2 * i + 1] * lscale[r.level];
-        if (octave) octave[total] = r.level;
-        if (response) response[total] = r.resp[i];
-        if (angle_deg) angle_deg[total] = ang[i];
-        memcpy(desc + (size_t)total * 32, dsc + (size_t)i * 32, 32);
-      }
-      total++;
+  for (int l = 0; l < NL; l++) total += p_hdr[l];
+  if (total > DESC_CAP) {
+    set_error("vo_orb_detect_and_compute: more than %d keypoints", DESC_CAP);
+    return VO_ERR_CAPACITY;
+  }
+  if (total > guess) {
+    VO_TRY(fetch(guess, total));
+    VO_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  const int n_copy = std::min(total, cap);
+  if (n_copy > 0) {
+    memcpy(xy, p_xy, (size_t)n_copy * 2 * sizeof(float));
+    if (response) memcpy(response, p_resp, (size_t)n_copy * sizeof(float));
+    if (angle_deg) memcpy(angle_deg, p_ang, (size_t)n_copy * sizeof(float));
+    memcpy(desc, p_desc, (size_t)n_copy * 32);
+    if (octave) {
+      int k = 0;
+      for (int l = 0; l < NL; l++)
+        for (int i = 0; i < p_hdr[l] && k < n_copy; i++) octave[k++] = l;
     }
   }
   *n_out = total;

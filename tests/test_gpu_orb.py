@@ -159,3 +159,17 @@ def test_detect_and_compute_other_sizes(fe):
         for k in ("xy", "octave", "response", "angle"):
             assert np.array_equal(got[k], live[k]), (img.shape, k)
         assert (got["desc"] != live["desc"]).any(1).mean() <= 0.001
+
+
+def test_detect_and_compute_keeps_ties_like_cv2(fe):
+    """a lattice of single bright pixels: thousands of corners share one FAST score and one Harris response, so both
+    retainBest selections keep far more than their quota (ties stay) and the packed result exceeds the first transfer"""
+    from oracle import orb
+    yy, xx = np.mgrid[0:480, 0:640]
+    img = (((xx % 10) == 3) & ((yy % 10) == 3)).astype(np.uint8) * 200 + 20
+    got = fe.orbDetectAndCompute(img, 100)
+    live = orb.detect_and_compute_call_through(img, 100)
+    assert len(got["xy"]) == len(live["xy"]) > 2000, len(live["xy"])
+    for k in ("xy", "octave", "response", "angle"):
+        assert np.array_equal(got[k], live[k]), k
+    assert (got["desc"] != live["desc"]).any(1).mean() <= 0.001
