@@ -348,6 +348,7 @@ int vo_create(const vo_params* p, vo_ctx** out) {
     return r;
   }
   c->opt_host_chains = getenv("VO_B200_SEQ_HOST") != nullptr;      // read per context (tests flip them)
+  c->opt_no_pyramid_ahead = getenv("VO_B200_NO_PYRAMID_AHEAD") != nullptr;
   c->opt_lookahead = getenv("VO_B200_LOOKAHEAD") != nullptr;
   c->worker = std::thread(worker_main, c);
   *out = c;
@@ -1091,9 +1092,43 @@ static int lookahead_enqueue(vo_ctx* c, int m, int slot_cur, int slot_next, cons
   return VO_OK;
 }
 
+// The announced next frame's left pyramid, built ahead on the `la` stream into the slot the next call will use as its
+// current image (ev_la marks its completion).  The image is either device-resident (vo_seq_announce) or on its way into
+// the staging buffers (vo_seq_prefetch + prefetch_issue).
+static int pyramid_ahead_enqueue(vo_ctx* c, int slot_next, const uint8_t* current_id) {
+  vo_ctx* l = c->la;
+  if (!l || c->opt_lookahead || c->opt_no_pyramid_ahead) return VO_OK;
+  const uint8_t* img = nullptr;
+  const uint8_t* id = nullptr;
+  int stride = 0;
+  cudaEvent_t ready = nullptr;
+  if (c->ann_left) {
+    img = id = c->ann_left;
+    stride = c->ann_stride;
+    c->ann_left = c->ann_right = nullptr;
+  } else if (c->copy_stream) {
+    const int sl = 1 - c->pf_next;     // the staging set the last prefetch_issue filled
+    if (c->pf_left[sl]) {
+      img = c->d_stage[sl][0];
+      id = c->pf_left[sl];
+      stride = c->p.width * c->p.channels;
+      ready = c->ev_prefetch[sl];
+    }
+  }
+  if (!img || id == current_id) return VO_OK;
+  if (ready) VO_CUDA(cudaStreamWaitEvent(l->stream, ready, 0));
+  VO_TRY(load_image(l, slot_next, img, stride, 1, true));
+  VO_CUDA(cudaEventRecord(c->ev_la, l->stream));
+  c->pa_valid = true;
+  c->pa_left = id;
+  c->pa_slot = slot_next;
+  return VO_OK;
+}
+
 // a call that touches the pyramid slots outside the sequence driver: let an in-flight look-ahead finish first
 static void lookahead_quiesce(vo_ctx* c) {
-  if (c->la && (c->la_inflight || c->la_valid)) cudaStreamSynchronize(c->la->stream);
+  if (c->la && (c->la_inflight || c->la_valid || c->pa_valid)) cudaStreamSynchronize(c->la->stream);
+  c->pa_valid = false;
   c->la_inflight = c->la_valid = false;
   c->ann_left = c->ann_right = nullptr;
 }
@@ -1680,9 +1715,15 @@ int vo_seq_track(vo_ctx* c, const uint8_t* left, const uint8_t* right, int strid
     c->la_inflight = false;
     c->la_valid = false;
   }
+  bool have_pa = false;     // the previous call built this image's pyramid ahead (pyramid_ahead_enqueue)
+  if (c->pa_valid) {
+    have_pa = !have_la && c->pa_left == left_id && c->pa_slot == cur;
+    VO_CUDA(cudaStreamWaitEvent(c->stream, c->ev_la, 0));     // either way: it writes a slot this call may use
+    c->pa_valid = false;
+  }
   // with derivatives: this left image is the previous image of this frame's stereo LK and of the
   // next frame's temporal LK (one fused launch builds levels, borders and Scharr planes)
-  if (!have_la) VO_TRY(load_image(c, cur, left, stride, is_device, true));
+  if (!have_la && !have_pa) VO_TRY(load_image(c, cur, left, stride, is_device, true));
   vo_ctx* a = c->aux;
   int kk = 0, ng = 0;
   int k = 0, ni = 0, att = 1;
@@ -1724,6 +1765,9 @@ int vo_seq_track(vo_ctx* c, const uint8_t* left, const uint8_t* right, int strid
       rs = load_image(a, 2, right, stride, is_device, false);
       if (rs == VO_OK) rs = stereo_fused_enqueue(a, cur, 2, &ng, lk_order ? c->ev_lk : nullptr);
     }
+    // everything of this frame is enqueued: the next frame's copies (if announced from the host) and its left pyramid
+    VO_TRY(prefetch_issue(c));
+    VO_TRY(pyramid_ahead_enqueue(c, next_left_slot(cur), left_id));
     r = temporal_finish(c, &k, &ni, &att);
     if (rs == VO_OK) rs = stereo_fused_finish(a, &kk);
     else cudaStreamSynchronize(a->stream);

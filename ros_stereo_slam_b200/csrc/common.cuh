@@ -120,6 +120,12 @@ struct vo_ctx {
   const uint8_t* ann_left = nullptr;  // frame announced as DEVICE-resident (vo_seq_announce)
   const uint8_t* ann_right = nullptr;
   int ann_stride = 0;
+  // Pyramid-ahead (fused two-chain frame): the announced next frame's LEFT pyramid depends on nothing but the image; it
+  // is built on the `la` stream while this frame's chains run, and the next call finds it in its `cur` slot
+  bool pa_valid = false;
+  const uint8_t* pa_left = nullptr;  // identity (the pointer the caller announced / will pass)
+  int pa_slot = -1;
+  bool opt_no_pyramid_ahead = false; // VO_B200_NO_PYRAMID_AHEAD at vo_create
   bool pf_by_worker = false;         // this call's prefetch copies are issued by the stereo worker thread
   bool opt_host_chains = false;      // VO_B200_SEQ_HOST at vo_create: host-driven chains also when the keyframe is known
   bool opt_lookahead = false;        // VO_B200_LOOKAHEAD at vo_create (needs the host-driven chains)

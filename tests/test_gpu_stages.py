@@ -729,6 +729,66 @@ def test_lookahead_changes_the_schedule_not_the_numbers(channels):
         assert np.array_equal(got[1][0], plain[1][0]) and np.array_equal(got[1][1], plain[1][1]), mode
 
 
+def test_pyramid_ahead_changes_the_schedule_not_the_numbers():
+    """Default (fused) chains + an announced next frame: its LEFT pyramid is built one call early on the third stream.
+    Every per-frame result and the final reference set must equal the run without announcements, for device-resident
+    (vo_seq_announce) and host (vo_seq_prefetch) frames, and when the caller passes another frame than it announced."""
+    import ctypes as C
+    from ros_stereo_slam_b200 import _lib
+    sc = synth.Scene(4)
+    n = 7
+    Ls = [sc.render(i, "L") for i in range(n)]
+    Rs = [sc.render(i, "R") for i in range(n)]
+
+    def fields(res):
+        return (res.n_lk_in, res.n_tracked, res.n_inliers, res.attempt_used, res.keyframe, res.n_kf_points,
+                res.n_lk_in_stereo, tuple(res.rvec), tuple(res.tvec), tuple(res.pose3x4))
+
+    order = [1, 2, 3, 5, 4, 6]          # frame 5 arrives where 4 was announced: that pyramid is discarded
+
+    def run(mode):
+        fe = make_frontend(kf_min_inliers=2 ** 31 - 1, grid_step=9)
+        nb = Ls[0].nbytes
+        d = C.c_void_p()
+        if mode == "device":
+            _lib.check(fe.lib.vo_alloc_dev(fe.h, C.byref(d), C.c_uint64(2 * n * nb)))
+            for i in range(n):
+                for e, img in enumerate((Ls[i], Rs[i])):
+                    _lib.check(fe.lib.vo_memcpy_h2d(fe.h, C.c_void_p(d.value + (2 * i + e) * nb), img.ctypes.data_as(C.c_void_p), C.c_uint64(nb)))
+        dp = lambda i, e: d.value + (2 * i + e) * nb
+        stride = Ls[0].strides[0]
+        if mode == "device":
+            fe.seq_init(dp(0, 0), dp(0, 1), is_device=True, stride=stride)
+        else:
+            fe.seq_init(Ls[0], Rs[0])
+        rows = []
+        for j, i in enumerate(order):
+            announced = i + 1 if j + 1 < len(order) and i + 1 < n else None
+            if announced is not None and mode == "device":
+                fe.seq_announce(dp(announced, 0), dp(announced, 1), stride)
+            elif announced is not None and mode == "host":
+                fe.seq_prefetch(Ls[announced], Rs[announced])
+            if mode == "device":
+                res, code = fe.seq_track(dp(i, 0), dp(i, 1), is_device=True, stride=stride)
+            else:
+                res, code = fe.seq_track(Ls[i], Rs[i])
+            assert code == 0
+            rows.append(fields(res))
+        ref = fe.seq_reference()
+        # a stage call while a pyramid built ahead may still be in flight must not disturb it (and ends the sequence)
+        fe.denseKeypointExtractor(Ls[0], 30)
+        if mode == "device":
+            fe.lib.vo_free_dev(fe.h, d)
+        fe.close()
+        return rows, ref
+
+    plain = run("plain")
+    for mode in ("device", "host"):
+        got = run(mode)
+        assert got[0] == plain[0], mode
+        assert np.array_equal(got[1][0], plain[1][0]) and np.array_equal(got[1][1], plain[1][1]), mode
+
+
 def test_small_point_sets_take_opencv_paths(fe, G):
     """SURVEY 8 a-5 / a-7 small-N behaviour (missing items 1-2): findFundamentalMat with 7 and 8..14 points,
     solvePnPRansac with 5 and 4 points, against the live cv2."""
