@@ -146,6 +146,20 @@ def aggregate(elapsed_ms, frames, keypoints, world, backend=None):
     return float(t.item()), int(u[0].item()), int(u[1].item())
 
 
+def rank_times(elapsed_ms, world, backend=None):
+    """Every rank's elapsed time (ms), rank order: shows whether a sub-linear aggregate is one slow GPU (the aggregate
+    divides by the MAX over ranks) or a slowdown of all of them."""
+    if world == 1:
+        return [float(elapsed_ms)]
+    import torch
+    import torch.distributed as dist
+    dev = "cuda" if (backend or dist.get_backend()) == "nccl" else "cpu"
+    mine = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    allt = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(allt, mine)
+    return [float(x.item()) for x in allt]
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -455,6 +469,7 @@ def run_ours(args):
 
     e_ms, frames, kps = aggregate(dev_run["ms"], K, dev_run["kp"], world)
     h_ms, frames_h, kps_h = aggregate(host_run["ms"], K, host_run["kp"], world)
+    per_rank = [rank_times(dev_run["ms"], world), rank_times(host_run["ms"], world)]
 
     out = None
     if rank == 0:
@@ -519,6 +534,8 @@ def run_ours(args):
             "gpu_launches_per_step": round(dev_run["launches"] / K, 1),
             "clocks": dev_run["clocks"],
             "wall_ms_per_step": round(dev_run["wall_ms"] / K, 4),
+            "rank_ms_per_step": {"value": [round(x / K, 4) for x in per_rank[0]], "e2e": [round(x / K, 4) for x in per_rank[1]],
+                                 "note": "every rank's own device-timed ms per step; the aggregate uses the slowest"},
             "roofline": roofline,
             "stage_ms_per_frame_overlapped": {k: round(v["ms_per_frame"], 4) for k, v in breakdown.items()},
             "stage_ms_note": "per-launch event brackets from a separate profiling pass; the tracking and the stereo chain run "

@@ -17,6 +17,7 @@ def _worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import bench
     ms, frames, kp = bench.aggregate(10.0 + 5.0 * rank, 100, 1000 * (rank + 1), world, backend="gloo")
+    assert bench.rank_times(10.0 + 5.0 * rank, world, backend="gloo") == [10.0, 15.0]
     q.put((rank, ms, frames, kp))
     dist.barrier()
     dist.destroy_process_group()
@@ -40,6 +41,7 @@ def test_aggregate_world2_gloo():
 def test_aggregate_single():
     import bench
     assert bench.aggregate(12.5, 10, 99, 1) == (12.5, 10, 99)
+    assert bench.rank_times(12.5, 1) == [12.5]
 
 
 def test_dist_env_defaults(monkeypatch):
