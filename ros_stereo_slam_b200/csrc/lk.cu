@@ -61,6 +61,7 @@ constexpr int WARP_WORDS_G3 = TILE_WORDS + 3 * LK_WIN * LK_WIN + 1;   // the rep
 constexpr int LK_WARPS = LK_WARPS_N;
 constexpr int MARGIN = 3;
 constexpr int SAFE_LIMIT = 1 << 24;
+constexpr int BOUND_CLAMP = 1 << 26;    // per-lane clamp of a bound before the warp sum (32 x 2^26 fits 32 bits)
 constexpr unsigned FULL = 0xffffffffu;
 
 __device__ __forceinline__ void lk_weights(float a, float b, unsigned& wt, unsigned& wb, int& iw00, int& iw01, int& iw10,
@@ -590,7 +591,15 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
           t2 = 3 * (t2 + ((b2[4] + b2[5]) + (b2[6] + b2[7])));
           tu = 3 * (tu + ((ub[4] + ub[5]) + (ub[6] + ub[7])));
         }
-        if (__reduce_add_sync(FULL, min(tu, SAFE_LIMIT)) >= SAFE_LIMIT) {
+        // Exactness bound.  With U >= sum |term| and T = sum term, the positive terms add up to at most (U + T) / 2 and
+        // the negative ones to at most (U - T) / 2, so EVERY partial sum of the terms, in any order and grouping (the
+        // chains, OpenCV's int32 pairs, the final combination), lies within +-(U + |T|) / 2: all float additions are
+        // exact iff U + |T| < 2^25.  (The lane parts are clamped so that the warp sum cannot wrap; a clamped lane
+        // fails the test by itself.  T is computed modulo 2^32 and is exact whenever the test can pass.)
+        const unsigned U = __reduce_add_sync(FULL, (unsigned)min(tu, BOUND_CLAMP));
+        t1 = (int)((unsigned)__reduce_add_sync(FULL, t1) - (unsigned)C1tot);
+        t2 = (int)((unsigned)__reduce_add_sync(FULL, t2) - (unsigned)C2tot);
+        if (U + (unsigned)max(abs(t1), abs(t2)) >= 2u * SAFE_LIMIT || U >= 2u * SAFE_LIMIT) {
           lane_chains_t<G3>(a1, b1, notq, isq, c1);
           lane_chains_t<G3>(a2, b2, notq, isq, c2);
           lane_chains_t<G3>(ua, ub, notq, isq, cu);
@@ -600,17 +609,17 @@ lk_kernel(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, int n
       n_iters_done++;
       float b1f, b2f;
       bool safe = true;
-      // tier 1 (all_exact): the bound on the sum of |term| over the WHOLE window stays below 2^24 -- every chain
-      // and every step of the final combination is exact, the result is float(total)
+      // tier 1 (all_exact): every chain and every step of the final combination is exact, the result is float(total)
       if (all_exact) {
-        b1f = (float)(int)((unsigned)__reduce_add_sync(FULL, t1) - (unsigned)C1tot);
-        b2f = (float)(int)((unsigned)__reduce_add_sync(FULL, t2) - (unsigned)C2tot);
+        b1f = (float)t1;
+        b2f = (float)t2;
       } else {
 #pragma unroll
         for (int k = 0; k < 5; k++) {
           c1[k] = (int)((unsigned)__reduce_add_sync(FULL, c1[k]) - (unsigned)cC1[k]);   // sum(diff*Ix) = sum(J*Ix) - sum(I*Ix), modulo 2^32
           c2[k] = (int)((unsigned)__reduce_add_sync(FULL, c2[k]) - (unsigned)cC2[k]);
-          safe = safe && (__reduce_add_sync(FULL, min(cu[k], SAFE_LIMIT)) < SAFE_LIMIT);
+          const unsigned Uk = __reduce_add_sync(FULL, (unsigned)min(cu[k], BOUND_CLAMP));
+          safe = safe && Uk < 2u * SAFE_LIMIT && Uk + (unsigned)max(abs(c1[k]), abs(c2[k])) < 2u * SAFE_LIMIT;
         }
       }
       if (all_exact) {
@@ -1164,7 +1173,7 @@ lk_kernel_c3(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, in
         const int t1 = ((a1[0] + a1[1]) + (a1[2] + a1[3])) + (((b1[0] + b1[1]) + (b1[2] + b1[3])) + ((b1[4] + b1[5]) + (b1[6] + b1[7])));
         const int t2 = ((a2[0] + a2[1]) + (a2[2] + a2[3])) + (((b2[0] + b2[1]) + (b2[2] + b2[3])) + ((b2[4] + b2[5]) + (b2[6] + b2[7])));
         const int tu = ((ua[0] + ua[1]) + (ua[2] + ua[3])) + (((ub[0] + ub[1]) + (ub[2] + ub[3])) + ((ub[4] + ub[5]) + (ub[6] + ub[7])));
-        tot[0] = min(__reduce_add_sync(FULL, min(tu, SAFE_LIMIT)), SAFE_LIMIT);
+        tot[0] = (int)min(__reduce_add_sync(FULL, (unsigned)min(tu, BOUND_CLAMP)), (unsigned)BOUND_CLAMP);
         tot[1] = __reduce_add_sync(FULL, t1);
         tot[2] = __reduce_add_sync(FULL, t2);
       }
@@ -1174,10 +1183,11 @@ lk_kernel_c3(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, in
         plane_combine<3>(xch, phase, ch, lane, tot, pos3);
       }
       float b1f, b2f;
-      if (tot[0] < SAFE_LIMIT) {
-        // tier 1: every chain and every step of the final combination is exact
-        b1f = (float)(int)((unsigned)tot[1] - (unsigned)C1tot);
-        b2f = (float)(int)((unsigned)tot[2] - (unsigned)C2tot);
+      const int T1 = (int)((unsigned)tot[1] - (unsigned)C1tot), T2 = (int)((unsigned)tot[2] - (unsigned)C2tot);
+      if ((unsigned)tot[0] + (unsigned)max(abs(T1), abs(T2)) < 2u * SAFE_LIMIT) {
+        // tier 1: every chain and every step of the final combination is exact (bound U + |T| < 2^25, see lk_kernel)
+        b1f = (float)T1;
+        b2f = (float)T2;
       } else {
         int cs[15];
         lane_chains3(a1, b1, isq_b, nsimd, cs + 0);
@@ -1193,18 +1203,18 @@ lk_kernel_c3(PyrView prev, PyrView next, const float2* __restrict__ prev_pts, in
 #pragma unroll
         for (int k = 0; k < 10; k++) cs[k] = __reduce_add_sync(FULL, cs[k]);
 #pragma unroll
-        for (int k = 10; k < 15; k++) cs[k] = min(__reduce_add_sync(FULL, min(cs[k], SAFE_LIMIT)), SAFE_LIMIT);
+        for (int k = 10; k < 15; k++)
+          cs[k] = (int)min(__reduce_add_sync(FULL, (unsigned)min(cs[k], BOUND_CLAMP)), (unsigned)BOUND_CLAMP);
         plane_combine<15>(xch, phase, ch, lane, cs, pos15);
         bool safe = true;
+        int e1[5], e2[5];
 #pragma unroll
-        for (int k = 0; k < 5; k++) safe = safe && cs[10 + k] < SAFE_LIMIT;
+        for (int k = 0; k < 5; k++) {
+          e1[k] = (int)((unsigned)cs[k] - (unsigned)kC1[k]);
+          e2[k] = (int)((unsigned)cs[5 + k] - (unsigned)kC2[k]);
+          safe = safe && (unsigned)cs[10 + k] + (unsigned)max(abs(e1[k]), abs(e2[k])) < 2u * SAFE_LIMIT;
+        }
         if (safe) {
-          int e1[5], e2[5];
-#pragma unroll
-          for (int k = 0; k < 5; k++) {
-            e1[k] = (int)((unsigned)cs[k] - (unsigned)kC1[k]);
-            e2[k] = (int)((unsigned)cs[5 + k] - (unsigned)kC2[k]);
-          }
           b1f = chain_combine((float)e1[0], (float)e1[1], (float)e1[2], (float)e1[3], (float)e1[4]);
           b2f = chain_combine((float)e2[0], (float)e2[1], (float)e2[2], (float)e2[3], (float)e2[4]);
         } else {
