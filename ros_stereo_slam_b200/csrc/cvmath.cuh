@@ -43,18 +43,29 @@ namespace vo {
 
 // ---------------------------------------------------------------------------------------
 // OpenCV's own hypot (lapack.cpp shadows ::hypot inside namespace cv).
+// One instruction stream for both orderings (the lanes of a warp that rotate different row pairs do not diverge):
+// the larger magnitude divides the smaller one, exactly as the two branches of OpenCV's code do.
 VO_HD double cv_hypot(double a, double b) {
   a = fabs(a);
   b = fabs(b);
-  if (a > b) {
-    b /= a;
-    return a * sqrt(1 + b * b);
-  }
-  if (b > 0) {
-    a /= b;
-    return b * sqrt(1 + a * a);
-  }
-  return 0;
+  const bool a_larger = a > b;
+  const double hi = a_larger ? a : b, lo = a_larger ? b : a;
+  if (!(hi > 0)) return 0;
+  const double q = lo / hi;
+  return hi * sqrt(1 + q * q);
+}
+
+// The rotation of OpenCV's one-sided Jacobi (JacobiSVDImpl_): beta < 0: s = sqrt(delta / gamma), c = p / (gamma * s * 2);
+// otherwise c = sqrt((gamma + beta) / (gamma * 2)), s = p / (gamma * c * 2) -- the same two operations on selected
+// operands, written once so that lanes with different signs of beta share the instruction stream.
+VO_HD void cv_jacobi_cs(double p, double beta, double gamma, double& c, double& s) {
+  const bool neg = beta < 0;
+  const double num = neg ? (gamma - beta) * 0.5 : gamma + beta;
+  const double den = neg ? gamma : gamma * 2;
+  const double r1 = sqrt(num / den);
+  const double r2 = p / (gamma * r1 * 2);
+  s = neg ? r1 : r2;
+  c = neg ? r2 : r1;
 }
 
 // cv::RNG (multiply-with-carry)
@@ -129,14 +140,7 @@ VO_HDN void jacobi_svd(double* At, double* _W, double* Vt) {
         if (fabs(p) <= eps * sqrt(a * b)) continue;
         p = p2;
         if (!SPEC) gamma = cv_hypot(p, beta);
-        if (beta < 0) {
-          double delta = (gamma - beta) * 0.5;
-          s = sqrt(delta / gamma);
-          c = p / (gamma * s * 2);
-        } else {
-          c = sqrt((gamma + beta) / (gamma * 2));
-          s = p / (gamma * c * 2);
-        }
+        cv_jacobi_cs(p, beta, gamma, c, s);
 
         a = b = 0;
 #pragma unroll
@@ -348,14 +352,7 @@ VO_HDN void jacobi_svd_rt(double* At, double* _W, double* Vt, int n) {
         double beta = a - b, gamma = cv_hypot(p2, beta);   // evaluated next to the skip test's square root (two independent chains)
         if (fabs(p) <= skip_thr) continue;
         p = p2;
-        if (beta < 0) {
-          double delta = (gamma - beta) * 0.5;
-          s = sqrt(delta / gamma);
-          c = p / (gamma * s * 2);
-        } else {
-          c = sqrt((gamma + beta) / (gamma * 2));
-          s = p / (gamma * c * 2);
-        }
+        cv_jacobi_cs(p, beta, gamma, c, s);
         a = b = 0;
 #pragma unroll
         for (k = 0; k < m; k++) {

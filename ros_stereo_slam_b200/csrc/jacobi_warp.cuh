@@ -67,14 +67,7 @@ __device__ __forceinline__ void jacobi_sweeps_warp(double* At, double* W, int la
           double c, s;
           p = p2;
           if (!SPEC) gamma = cv_hypot(p, beta);
-          if (beta < 0) {
-            const double delta = (gamma - beta) * 0.5;
-            s = sqrt(delta / gamma);
-            c = p / (gamma * s * 2);
-          } else {
-            c = sqrt((gamma + beta) / (gamma * 2));
-            s = p / (gamma * c * 2);
-          }
+          cv_jacobi_cs(p, beta, gamma, c, s);
           a = b = 0;
 #pragma unroll
           for (int k = 0; k < M; k++) {
