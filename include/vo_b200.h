@@ -355,9 +355,11 @@ int vo_seq_track(vo_ctx* ctx, const uint8_t* left, const uint8_t* right, int str
 int vo_seq_prefetch(vo_ctx* ctx, const uint8_t* left, const uint8_t* right, int stride);
 /* The same announcement for either kind of pointer: is_device = 0 is vo_seq_prefetch; is_device != 0 announces a
  * frame that is already resident in device memory (nothing is copied).  When the keyframe policy inserts a keyframe
- * on every frame, an announced frame also lets the library run the NEXT frame's temporal LK -- which depends on this
- * keyframe's 2-D points but not on this frame's pose -- under the current frame's RANSAC solvers (a look-ahead
- * chain); the next vo_seq_track call must pass the announced pointers to use it, any other image simply discards it.
+ * on every frame, an announced frame (of either kind) lets the library build the NEXT frame's left image pyramid -- which
+ * depends on nothing but the image -- on a third stream while the current frame is processed (default), or, opt-in
+ * (VO_B200_LOOKAHEAD=1 with VO_B200_SEQ_HOST=1), run the next frame's whole temporal LK there.  The announced image
+ * must stay unchanged until the vo_seq_track call that passes it has returned; the next vo_seq_track call must pass
+ * the announced pointers to use the work done ahead, any other image simply discards it.
  * Results are identical with and without the announcement. */
 int vo_seq_announce(vo_ctx* ctx, const uint8_t* left, const uint8_t* right, int stride, int is_device);
 /* current reference set (after the last vo_seq_* call); any pointer may be NULL */
