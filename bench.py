@@ -74,54 +74,75 @@ def bench_config(world, steps, warmup):
 
 # ----------------------------------------------------------------------------- helpers
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled every 200 ms during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clocks and throttle reasons of the given GPUs, sampled every 20 ms by an NVML thread of THIS process while it
+    is running (started before the warm-up, so the timed region lies inside the sampled span; mark() brackets it).
+    A spawned `nvidia-smi -lms` -- the first version -- starts up inside a 20 ms timed region and takes driver locks
+    the frame loop needs; at N > 1 only rank 0 samples (all N GPUs), the other ranks run undisturbed."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
-    def __init__(self, device):
-        self.device = device
-        self.proc = None
-        self.lines = []
+    def __init__(self, devices):
+        self.devices = list(devices)
+        self.rows = []          # (t, device, sm_mhz, max_mhz, reasons_bitmask)
+        self.t0 = self.t1 = None
+        self.stop_flag = False
+        self.thread = None
+        self.err = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            ids = [int(x) for x in vis.split(",")] if vis and all(x.strip().isdigit() for x in vis.split(",")) else None
+            hs = [pynvml.nvmlDeviceGetHandleByIndex(ids[d] if ids else d) for d in self.devices]
+            mx = [pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM) for h in hs]
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        except Exception as e:       # noqa: BLE001
+            self.err = "NVML unavailable: %s" % e
+            return
 
-    def _read(self):
-        for l in self.proc.stdout:
-            self.lines.append(l.strip())
+        def loop():
+            while not self.stop_flag:
+                t = time.perf_counter()
+                for d, h, m in zip(self.devices, hs, mx):
+                    try:
+                        self.rows.append((t, d, pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM), m,
+                                          get_reasons(h)))
+                    except Exception:   # noqa: BLE001
+                        pass
+                time.sleep(0.02)
+
+        self.thread = threading.Thread(target=loop, daemon=True)
+        self.thread.start()
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for l in self.lines:
-            f = [x.strip() for x in l.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.err or "not sampled on this rank"]}
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        inside = [r for r in self.rows if self.t0 is not None and self.t0 <= r[0] <= (self.t1 or 1e30)]
+        # a 20-step region lasts ~20 ms: if no sample fell inside it, the neighbouring ones (same load) stand in
+        used = inside if inside else [r for r in self.rows if self.t0 is None or abs(r[0] - self.t0) < 0.25]
+        sm = [r[2] for r in used]
+        bits = 0
+        for r in used:
+            bits |= r[4]
+        per_gpu = {}
+        for r in used:
+            per_gpu.setdefault(r[1], []).append(r[2])
+        out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max((r[3] for r in used), default=None),
+               "samples": len(used), "samples_inside_timed_region": len(inside),
+               "reasons": [n for n, b in self.REASONS if bits & b], "source": "NVML, 20 ms period"}
+        if len(self.devices) > 1:
+            out["sm_mhz_per_gpu"] = {str(d): float(np.median(v)) for d, v in sorted(per_gpu.items())}
+        return out
 
 
 def dist_env():
@@ -426,15 +447,21 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def timed(device_resident):
+        import gc
+        sampler = ClockSampler(range(world) if rank == 0 else [])
+        if rank == 0:
+            sampler.start()
+        barrier()     # the first collective sets up the NCCL communicator: keep that out of the timed region's barrier
         seq_init(fe, lib, seq, device_resident)
         run_frames(fe, lib, seq, 1, W, device_resident)           # warm-up
         fe.profile_enable(["lk"])                                  # events around the LK launches only
         fe.profile_read(reset=True)
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
-        sampler = ClockSampler(dev)
-        sampler.start()
+        gc.collect()
+        gc.disable()                                               # no collection pause inside a 20 ms region
         barrier()
+        sampler.mark_begin()
         l0 = fe.launch_count()
         t0 = time.perf_counter()
         w0 = fe.lk_work()
@@ -443,6 +470,8 @@ def run_ours(args):
         kp = run_frames(fe, lib, seq, 1 + W, K, device_resident, rec)
         e1.record(stream)
         barrier()
+        sampler.mark_end()
+        gc.enable()
         wall_ms = (time.perf_counter() - t0) * 1e3
         launches = fe.launch_count() - l0
         clocks = sampler.stop()
