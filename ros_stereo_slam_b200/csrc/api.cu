@@ -98,8 +98,20 @@ static int alloc_chain(vo_ctx* c) {
     VO_CUDA(cudaMalloc(&c->d_seq_xy, cap * sizeof(float2)));
     VO_CUDA(cudaMalloc(&c->d_seq_xyz, cap * sizeof(float3)));
   }
-  VO_CUDA(cudaMalloc(&c->d_count, 16 * sizeof(int)));
-  VO_CUDA(cudaMallocHost(&c->h_count, 16 * sizeof(int)));
+  // the small results a fused chain reads back -- pose (16 doubles) | counts (16 ints) | selection (8) | flags (8) -- live
+  // in ONE block on either side, so that a chain ends with one device-to-host copy instead of four
+  VO_CUDA(cudaMalloc(&c->d_res, RES_BYTES));
+  VO_CUDA(cudaMemset(c->d_res, 0, RES_BYTES));
+  VO_CUDA(cudaMallocHost(&c->h_res, RES_BYTES));
+  memset(c->h_res, 0, RES_BYTES);
+  c->d_pose = reinterpret_cast<double*>(c->d_res);
+  c->h_pose = reinterpret_cast<double*>(c->h_res);
+  c->d_count = reinterpret_cast<int*>(c->d_res + 16 * sizeof(double));
+  c->h_count = reinterpret_cast<int*>(c->h_res + 16 * sizeof(double));
+  c->d_sel = c->d_count + 16;
+  c->h_sel = c->h_count + 16;
+  c->d_flags = c->d_count + 24;
+  c->h_flags = c->h_count + 24;
   const int n_tiles = std::max(256, (cap + 2047) / 2048 + 1);   // compaction tiles of 2048 flags (points.cu CP_TILE)
   VO_CUDA(cudaMalloc(&c->d_tile_state, n_tiles * sizeof(unsigned long long)));
   {
@@ -120,10 +132,7 @@ static int alloc_chain(vo_ctx* c) {
   VO_CUDA(cudaMallocHost(&c->h_samples, (size_t)ch * 7 * sizeof(int32_t)));
   VO_CUDA(cudaMalloc(&c->d_models, (size_t)ch * 27 * sizeof(double)));
   VO_CUDA(cudaMalloc(&c->d_counts, (size_t)ch * 3 * sizeof(int32_t)));
-  VO_CUDA(cudaMalloc(&c->d_sel, 8 * sizeof(int)));
-  VO_CUDA(cudaMallocHost(&c->h_sel, 8 * sizeof(int)));
-  VO_CUDA(cudaMalloc(&c->d_pose, 16 * sizeof(double)));
-  VO_CUDA(cudaMallocHost(&c->h_pose, 16 * sizeof(double)));
+
   VO_CUDA(cudaMalloc(&c->d_cam, 48 * sizeof(double)));
   {
     std::vector<uint32_t> raw(RNG_LEN);
@@ -131,9 +140,7 @@ static int alloc_chain(vo_ctx* c) {
     for (int i = 0; i < RNG_LEN; i++) raw[i] = rng.next();
     VO_CUDA(cudaMalloc(&c->d_rng, RNG_LEN * sizeof(uint32_t)));
     VO_CUDA(cudaMemcpy(c->d_rng, raw.data(), RNG_LEN * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    VO_CUDA(cudaMalloc(&c->d_flags, 8 * sizeof(int)));
-    VO_CUDA(cudaMemset(c->d_flags, 0, 8 * sizeof(int)));
-    VO_CUDA(cudaMallocHost(&c->h_flags, 8 * sizeof(int)));
+
   }
   if (p->channels == 3) VO_CUDA(cudaMalloc(&c->d_bgr, (size_t)3 * p->width * p->height));
   VO_CUDA(cudaMalloc(&c->d_lk_work, 4 * sizeof(unsigned long long)));
@@ -150,10 +157,10 @@ static void free_chain(vo_ctx* c) {
   orb_free(c);
   void* dev[] = {c->d_xy_in, c->d_xy_trk, c->d_status, c->d_err, c->d_xyz_in, c->d_c_ref, c->d_c_trk, c->d_c_xyz,
                  c->d_f_ref, c->d_f_trk, c->d_f_xyz, c->d_xyz_tmp, c->d_mask, c->d_idx, c->d_seq_xy, c->d_seq_xyz,
-                 c->d_count, c->d_tile_state, c->d_samples, c->d_models, c->d_counts, c->d_sel, c->d_pose, c->d_cam,
-                 c->d_lk_work, c->d_rng, c->d_flags, c->d_epoch, c->d_Pst, c->d_bgr, c->d_gray, c->d_sor};
+                 c->d_res, c->d_tile_state, c->d_samples, c->d_models, c->d_counts, c->d_cam,
+                 c->d_lk_work, c->d_rng, c->d_epoch, c->d_Pst, c->d_bgr, c->d_gray, c->d_sor};
   for (void* p : dev) cudaFree(p);
-  void* host[] = {c->h_count, c->h_pts, c->h_samples, c->h_sel, c->h_pose, c->h_lk_work, c->h_flags};
+  void* host[] = {c->h_res, c->h_pts, c->h_samples, c->h_lk_work};
   for (void* p : host) cudaFreeHost(p);
   for (auto& pe : c->prof.pending) {
     cudaEventDestroy(pe.a);
@@ -947,10 +954,7 @@ static int track_pnp_fused_enqueue(vo_ctx* c, int slot_ref, int slot_cur, const 
   c->n_dev = nullptr;
   VO_TRY(pnp_refine_launch(c, c->d_f_xyz, c->d_f_trk, c->d_idx, c->d_count + 4, c->d_models, c->d_sel, c->d_pose));
   c->last_pnp_h = Hp;
-  VO_CUDA(cudaMemcpyAsync(c->h_sel, c->d_sel, 8 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  VO_CUDA(cudaMemcpyAsync(c->h_flags, c->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  VO_CUDA(cudaMemcpyAsync(c->h_pose, c->d_pose, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  VO_CUDA(cudaMemcpyAsync(c->h_count, c->d_count, 16 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  VO_CUDA(cudaMemcpyAsync(c->h_res, c->d_res, RES_BYTES, cudaMemcpyDeviceToHost, c->stream));   // pose, counts, selection, flags
   return VO_OK;
 }
 
@@ -992,9 +996,7 @@ static int stereo_fused_enqueue(vo_ctx* c, int slot_l, int slot_r, int* n_grid_o
   c->n_dev = c->d_count + 1;
   VO_TRY(triangulate_launch(c, c->d_Pst, c->d_f_ref, c->d_f_trk, ng, c->d_xyz_tmp, nullptr, nullptr));
   c->n_dev = nullptr;
-  VO_CUDA(cudaMemcpyAsync(c->h_sel, c->d_sel, 8 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  VO_CUDA(cudaMemcpyAsync(c->h_flags, c->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  VO_CUDA(cudaMemcpyAsync(c->h_count, c->d_count, 16 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  VO_CUDA(cudaMemcpyAsync(c->h_res, c->d_res, RES_BYTES, cudaMemcpyDeviceToHost, c->stream));   // counts, selection, flags
   return VO_OK;
 }
 
@@ -1838,11 +1840,7 @@ int vo_seq_track(vo_ctx* c, const uint8_t* left, const uint8_t* right, int strid
   if (kf_known) {
     // insertKeyFrames epilogue: world points = pose * camera points (src/keyFrameManagement.cpp:20-30)
     VO_CUDA(cudaStreamWaitEvent(c->stream, c->ev_stereo, 0));
-    VO_CUDA(cudaMemcpyAsync(c->d_cam + 24, out->pose3x4, 12 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    if (kk) {
-      VO_TRY(transform_launch(c, c->d_cam + 24, a->d_xyz_tmp, kk, c->d_seq_xyz));
-      VO_CUDA(cudaMemcpyAsync(c->d_seq_xy, a->d_f_ref, (size_t)kk * sizeof(float2), cudaMemcpyDeviceToDevice, c->stream));
-    }
+    VO_TRY(keyframe_epilogue_launch(c, out->pose3x4, a->d_xyz_tmp, a->d_f_ref, kk, c->d_seq_xyz, c->d_seq_xy));
     c->seq_n = kk;
     out->keyframe = 1;
     out->n_kf_points = kk;

@@ -148,6 +148,8 @@ struct vo_ctx {
   float3* d_xyz_tmp = nullptr;                           // triangulation / transform output
   uint8_t* d_mask = nullptr;
   int32_t* d_idx = nullptr;                              // inlier indices
+  uint8_t* d_res = nullptr;                              // result block: pose (16 doubles) | d_count (16 ints) | d_sel (8) | d_flags (8)
+  uint8_t* h_res = nullptr;                              // pinned mirror of it (h_pose, h_count, h_sel, h_flags point into it)
   int* d_count = nullptr;                                // small int scratch (16 ints)
   int* h_count = nullptr;                                // pinned mirror
   unsigned long long* d_tile_state = nullptr;            // compaction look-back (epoch<<32 | tile total)
@@ -298,6 +300,8 @@ __device__ __forceinline__ int compact_tile_offset(int cnt, int* __restrict__ co
 }
 #endif
 
+constexpr size_t RES_BYTES = 16 * sizeof(double) + 32 * sizeof(int);
+
 static inline int div_up(int a, int b) { return (a + b - 1) / b; }
 
 // stage launchers (each returns VO_OK / VO_ERR_CUDA) -------------------------------------
@@ -326,6 +330,8 @@ int gather_tracks_launch(vo_ctx* c, const int32_t* d_idx, int n, const float2* t
 int triangulate_launch(vo_ctx* c, const double* d_P1P2, const float2* a, const float2* b, int n, float3* out,
                        const double* d_M /*nullable: fused rigid transform -> out2*/, float3* out2);
 int transform_launch(vo_ctx* c, const double* d_M, const float3* in, int n, float3* out);
+int keyframe_epilogue_launch(vo_ctx* c, const double* pose3x4, const float3* cam, const float2* xy_in, int n, float3* world,
+                             float2* xy_out);
 
 int fmat_solve_launch(vo_ctx* c, const float2* m1, const float2* m2, const int32_t* d_samples, int h, double* d_models,
                       int32_t* d_counts);

@@ -168,6 +168,33 @@ __global__ void transform_kernel(const double* __restrict__ M, const float3* __r
   out[i] = rigid_apply(sM, in[i]);
 }
 
+// The keyframe epilogue of the sequence driver in one launch: world points = pose * camera points (the pose travels as a
+// kernel argument, no upload) and the keyframe's 2-D points copied next to them.
+struct Pose3x4 {
+  double m[12];
+};
+
+__global__ void keyframe_epilogue_kernel(const Pose3x4 M, const float3* __restrict__ cam, const float2* __restrict__ xy_in, int n,
+                                         float3* __restrict__ world, float2* __restrict__ xy_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  world[i] = rigid_apply(M.m, cam[i]);
+  xy_out[i] = xy_in[i];
+}
+
+int keyframe_epilogue_launch(vo_ctx* c, const double* pose3x4, const float3* cam, const float2* xy_in, int n, float3* world,
+                             float2* xy_out) {
+  if (n <= 0) return VO_OK;
+  Pose3x4 M;
+  for (int i = 0; i < 12; i++) M.m[i] = pose3x4[i];
+  {
+    LaunchScope ls(c, VO_K_MISC);
+    keyframe_epilogue_kernel<<<div_up(n, 256), 256, 0, c->stream>>>(M, cam, xy_in, n, world, xy_out);
+  }
+  VO_CUDA(cudaGetLastError());
+  return VO_OK;
+}
+
 int transform_launch(vo_ctx* c, const double* d_M, const float3* in, int n, float3* out) {
   if (n <= 0) return VO_OK;
   {
