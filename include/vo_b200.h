@@ -261,8 +261,10 @@ int vo_orb_angles(vo_ctx* ctx, const uint8_t* img, int stride, int width, int he
  * pyramid, per level FAST-9/16 (threshold 20, suppression) -> border filter (31) -> retainBest(2n) by FAST score ->
  * Harris response -> retainBest(n) -> IC_Angle -> smoothing -> rBRIEF, positions scaled back to level 0.  The keypoint
  * SET of every octave (position, response, angle) and the descriptors are bit-identical to cv2 4.13.0; the order is
- * (octave, y, x) -- OpenCV's order inside an octave is whatever std::nth_element leaves.  octave / response /
- * angle_deg may be NULL; *n = number of keypoints (VO_ERR_CAPACITY when it exceeds cap). */
+ * (octave, y, x) -- OpenCV's order inside an octave is whatever std::nth_element leaves.  Both retainBest selections
+ * keep every tie of their threshold (as OpenCV's do), so *n can exceed nfeatures.  All selections run on the device; the
+ * call synchronises once.  octave / response / angle_deg may be NULL; *n = number of keypoints (VO_ERR_CAPACITY when it
+ * exceeds cap, or 2 * nfeatures + 4096, what the library's staging holds). */
 int vo_orb_detect_and_compute(vo_ctx* ctx, const uint8_t* img, int stride, int width, int height, int nfeatures, float* xy,
                               int32_t* octave, float* response, float* angle_deg, uint8_t* desc, int cap, int* n);
 /* cv::FAST (TYPE_9_16, the detector ORB runs on every pyramid level with fastThreshold 20 and non-maximum
