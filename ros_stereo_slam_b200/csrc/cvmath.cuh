@@ -303,79 +303,83 @@ VO_HDF void solve_svd(const double* A, const double* b, double* x) {
 // operations in the same order as the compile-time versions.  EPnP's three beta initialisations
 // solve 6x4, 6x3 and 6x5 systems; on the device they run on three lanes of one warp, and sharing
 // ONE instruction stream (instead of three template instantiations) keeps those lanes converged.
+// The three parts are separate functions because the device runs the sweeps of EPnP's three 6 x n problems as
+// wavefronts over lane groups (jacobi_warp.cuh, jacobi_sweeps_groups) around the same init / rotate / finish code.
+// Vt: n rows of stride NMAX (columns n..NMAX-1 stay zero).
 template <int M, int NMAX>
-VO_HDN void jacobi_svd_rt(double* At, double* _W, double* Vt, int n) {
-  constexpr int astep = M, m = M, vstep = NMAX;   // Vt: n rows of stride NMAX (columns n..NMAX-1 stay zero)
-  double W[8];
-  const double minval = DBL_MIN, eps = DBL_EPSILON * 10;
-  int i, j, k, iter;
-  constexpr int max_iter = m > 30 ? m : 30;
-  double c, s, sd;
+VO_HD void jacobi_rt_init(const double* At, double* W, double* Vt, int n) {
 #pragma unroll 1
-  for (i = 0; i < n; i++) {
-    sd = 0;
+  for (int i = 0; i < n; i++) {
+    double sd = 0;
 #pragma unroll
-    for (k = 0; k < m; k++) {
-      double t = At[i * astep + k];
+    for (int k = 0; k < M; k++) {
+      double t = At[i * M + k];
       sd += t * t;
     }
     W[i] = sd;
 #pragma unroll
-    for (k = 0; k < NMAX; k++) Vt[i * vstep + k] = 0;
-    Vt[i * vstep + i] = 1;
+    for (int k = 0; k < NMAX; k++) Vt[i * NMAX + k] = 0;
+    Vt[i * NMAX + i] = 1;
   }
-#pragma unroll 1
-  for (iter = 0; iter < max_iter; iter++) {
-    bool changed = false;
-#pragma unroll 1
-    for (i = 0; i < n - 1; i++)
-#pragma unroll 1
-      for (j = i + 1; j < n; j++) {
-        double *Ai = At + i * astep, *Aj = At + j * astep;
-        double a = W[i], p = 0, b = W[j];
-        double ri[M], rj[M], vi[NMAX], vj[NMAX];
-        double *Vi = Vt + i * vstep, *Vj = Vt + j * vstep;
+}
+
+// one pair (i, j) of a sweep: rows i and j of At and Vt, W[i], W[j]; returns whether it rotated
+template <int M, int NMAX>
+VO_HD bool jacobi_rt_rotate(double* At, double* W, double* Vt, int i, int j) {
+  const double eps = DBL_EPSILON * 10;
+  double *Ai = At + i * M, *Aj = At + j * M;
+  double a = W[i], p = 0, b = W[j];
+  double ri[M], rj[M], vi[NMAX], vj[NMAX];
+  double *Vi = Vt + i * NMAX, *Vj = Vt + j * NMAX;
 #pragma unroll
-        for (k = 0; k < m; k++) {
-          ri[k] = Ai[k];
-          rj[k] = Aj[k];
-        }
-#pragma unroll
-        for (k = 0; k < NMAX; k++) {   // requested early: the loads complete under the divide / square-root chain
-          vi[k] = Vi[k];
-          vj[k] = Vj[k];
-        }
-#pragma unroll
-        for (k = 0; k < m; k++) p += ri[k] * rj[k];
-        const double skip_thr = eps * sqrt(a * b);
-        const double p2 = p * 2;
-        double beta = a - b, gamma = cv_hypot(p2, beta);   // evaluated next to the skip test's square root (two independent chains)
-        if (fabs(p) <= skip_thr) continue;
-        p = p2;
-        cv_jacobi_cs(p, beta, gamma, c, s);
-        a = b = 0;
-#pragma unroll
-        for (k = 0; k < m; k++) {
-          double t0 = c * ri[k] + s * rj[k];
-          double t1 = -s * ri[k] + c * rj[k];
-          Ai[k] = t0;
-          Aj[k] = t1;
-          a += t0 * t0;
-          b += t1 * t1;
-        }
-        W[i] = a;
-        W[j] = b;
-        changed = true;
-#pragma unroll
-        for (k = 0; k < NMAX; k++) {
-          double t0 = c * vi[k] + s * vj[k];
-          double t1 = -s * vi[k] + c * vj[k];
-          Vi[k] = t0;
-          Vj[k] = t1;
-        }
-      }
-    if (!changed) break;
+  for (int k = 0; k < M; k++) {
+    ri[k] = Ai[k];
+    rj[k] = Aj[k];
   }
+#pragma unroll
+  for (int k = 0; k < NMAX; k++) {   // requested early: the loads complete under the divide / square-root chain
+    vi[k] = Vi[k];
+    vj[k] = Vj[k];
+  }
+#pragma unroll
+  for (int k = 0; k < M; k++) p += ri[k] * rj[k];
+  const double skip_thr = eps * sqrt(a * b);
+  const double p2 = p * 2;
+  double beta = a - b, gamma = cv_hypot(p2, beta);   // evaluated next to the skip test's square root (two independent chains)
+  if (fabs(p) <= skip_thr) return false;
+  p = p2;
+  double c, s;
+  cv_jacobi_cs(p, beta, gamma, c, s);
+  a = b = 0;
+#pragma unroll
+  for (int k = 0; k < M; k++) {
+    double t0 = c * ri[k] + s * rj[k];
+    double t1 = -s * ri[k] + c * rj[k];
+    Ai[k] = t0;
+    Aj[k] = t1;
+    a += t0 * t0;
+    b += t1 * t1;
+  }
+  W[i] = a;
+  W[j] = b;
+#pragma unroll
+  for (int k = 0; k < NMAX; k++) {
+    double t0 = c * vi[k] + s * vj[k];
+    double t1 = -s * vi[k] + c * vj[k];
+    Vi[k] = t0;
+    Vj[k] = t1;
+  }
+  return true;
+}
+
+// after the sweeps: singular values, ordering, normalisation of the rows (completion of zero rows)
+template <int M, int NMAX>
+VO_HD void jacobi_rt_finish(double* At, double* _W, double* Vt, int n) {
+  constexpr int astep = M, m = M, vstep = NMAX;
+  double W[8];
+  const double minval = DBL_MIN, eps = DBL_EPSILON * 10;
+  int i, j, k, iter;
+  double s, sd;
 #pragma unroll 1
   for (i = 0; i < n; i++) {
     sd = 0;
@@ -457,13 +461,27 @@ VO_HDN void jacobi_svd_rt(double* At, double* _W, double* Vt, int n) {
   }
 }
 
+template <int M, int NMAX>
+VO_HDN void jacobi_svd_rt(double* At, double* _W, double* Vt, int n) {
+  double W[8];
+  constexpr int max_iter = M > 30 ? M : 30;
+  jacobi_rt_init<M, NMAX>(At, W, Vt, n);
+#pragma unroll 1
+  for (int iter = 0; iter < max_iter; iter++) {
+    bool changed = false;
+#pragma unroll 1
+    for (int i = 0; i < n - 1; i++)
+#pragma unroll 1
+      for (int j = i + 1; j < n; j++) changed |= jacobi_rt_rotate<M, NMAX>(At, W, Vt, i, j);
+    if (!changed) break;
+  }
+  jacobi_rt_finish<M, NMAX>(At, _W, Vt, n);
+}
+
 // cv::solve(A (6 x n), b (6), x (n), DECOMP_SVD) for n <= 5
-VO_HDN void solve_svd_6xn(const double* A, const double* b, double* x, int n) {
+// SVBkSbImpl_ with nb == 1 on the Jacobi result: u = at (uT, n rows of 6), v (vT, stride 5), eps = 2 * DBL_EPSILON
+VO_HD void svd_backsubst_6xn(const double* at, const double* w, const double* v, const double* b, double* x, int n) {
   const int m = 6;
-  double at[30], w[5], v[25];
-  for (int i = 0; i < n; i++)
-    for (int j = 0; j < m; j++) at[i * m + j] = A[j * n + i];
-  jacobi_svd_rt<6, 5>(at, w, v, n);
   double threshold = 0;
   for (int i = 0; i < n; i++) {
     x[i] = 0;
@@ -900,16 +918,20 @@ VO_HDN void epnp_prepare(const EpnpWork& w, const double* ut, double* l_6x10 /*6
 
 // variant N in {1,2,3}: betas (4, out), R, t; returns the mean reprojection error.
 // find_betas_approx_1 uses columns [0 1 3 6] of L, _2 columns [0 1 2], _3 columns [0 1 2 3 4].
-VO_HDN double epnp_variant(int N, const EpnpWork& w, const Intrinsics& K, const double* ut, const double* l_6x10,
-                           const double* rho, double* betas, double R[3][3], double t[3]) {
-  const int ncol = N == 1 ? 4 : (N == 2 ? 3 : 5);
-  double l[30], bx[5] = {0, 0, 0, 0, 0};
-  for (int i = 0; i < 6; i++)
-    for (int j = 0; j < ncol; j++) {
-      const int col = N == 1 ? (j == 0 ? 0 : j == 1 ? 1 : j == 2 ? 3 : 6) : j;
-      l[i * ncol + j] = l_6x10[i * 10 + col];
-    }
-  solve_svd_6xn(l, rho, bx, ncol);
+// Three steps, so that the device can run the Jacobi sweeps of the three 6 x n systems side by side as wavefronts:
+// epnp_variant_system (the transposed system, n rows of 6), the SVD solve, epnp_variant_back (everything after it).
+VO_HD int epnp_variant_ncol(int N) { return N == 1 ? 4 : (N == 2 ? 3 : 5); }
+
+VO_HD void epnp_variant_system(int N, const double* l_6x10, double* at /* ncol x 6 */) {
+  const int ncol = epnp_variant_ncol(N);
+  for (int j = 0; j < ncol; j++) {
+    const int col = N == 1 ? (j == 0 ? 0 : j == 1 ? 1 : j == 2 ? 3 : 6) : j;
+    for (int i = 0; i < 6; i++) at[j * 6 + i] = l_6x10[i * 10 + col];
+  }
+}
+
+VO_HDN double epnp_variant_back(int N, const EpnpWork& w, const Intrinsics& K, const double* ut, const double* l_6x10,
+                                const double* rho, const double* bx, double* betas, double R[3][3], double t[3]) {
   if (N == 1) {
     if (bx[0] < 0) {
       betas[0] = sqrt(-bx[0]);
@@ -936,6 +958,16 @@ VO_HDN double epnp_variant(int N, const EpnpWork& w, const Intrinsics& K, const 
   }
   epnp_gauss_newton(l_6x10, rho, betas);
   return epnp_compute_R_and_t(w, K, ut, betas, R, t);
+}
+
+VO_HDN double epnp_variant(int N, const EpnpWork& w, const Intrinsics& K, const double* ut, const double* l_6x10,
+                           const double* rho, double* betas, double R[3][3], double t[3]) {
+  const int ncol = epnp_variant_ncol(N);
+  double at[30], sw[5], v[25], bx[5] = {0, 0, 0, 0, 0};
+  epnp_variant_system(N, l_6x10, at);
+  jacobi_svd_rt<6, 5>(at, sw, v, ncol);
+  svd_backsubst_6xn(at, sw, v, rho, bx, ncol);
+  return epnp_variant_back(N, w, K, ut, l_6x10, rho, bx, betas, R, t);
 }
 
 VO_HDN void epnp5_back(const EpnpWork& w, const Intrinsics& K, const double* ut, double Rout[9], double tout[3],

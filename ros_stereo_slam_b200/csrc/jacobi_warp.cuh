@@ -100,4 +100,57 @@ __device__ __forceinline__ void jacobi_sweeps_warp(double* At, double* W, int la
   }
 }
 
+// The sweeps of up to four small runtime-size problems (M columns, n_g <= NMAX rows, V accumulated: jacobi_rt_rotate of
+// cvmath.cuh) side by side: lane group g = lane / 8 works on problem g with the same wavefront schedule as above -- pair
+// (i, j) of sweep s at step s * n + i + j, H = n / 2 lanes on the older and H on the newer sweep in flight (for n = 3 the
+// pairs of a sweep are strictly sequential and one lane suffices).  EPnP's three beta initialisations are 6 x 4, 6 x 3
+// and 6 x 5 systems: the 10 pairs per sweep of the largest take 5 steps instead of 10.  At / W / Vt: problem g at
+// base + g * stride.  n_g = 0 marks an unused group.  All 32 lanes must call.
+template <int M, int NMAX>
+__device__ __forceinline__ void jacobi_sweeps_groups(double* At, int at_stride, double* W, int w_stride, double* Vt,
+                                                     int v_stride, int n_g, int lane) {
+  constexpr int max_iter = M > 30 ? M : 30;
+  const int g = lane >> 3, idx = lane & 7;
+  const int n = n_g;
+  const int H = n >> 1, P = n, D = 2 * n - 3;
+  double* At_g = At + g * at_stride;
+  double* W_g = W + g * w_stride;
+  double* Vt_g = Vt + g * v_stride;
+  bool done = n < 2;
+  bool chg_old = false, chg_new = false;    // group-uniform
+  int s_new = 0;
+  const unsigned half = (1u << H) - 1u;
+  for (int step = 1;; step++) {
+    const int t_new = step - s_new * P;      // anti-diagonal of the newer sweep, 1..P
+    const bool is_new = idx >= H;
+    const int sweep = is_new ? s_new : s_new - 1;
+    const int t = is_new ? t_new : t_new + P;
+    bool rotated = false;
+    if (!done && idx < 2 * H && sweep >= 0 && sweep < max_iter && t <= D) {
+      const int li = is_new ? idx - H : idx;
+      const int i0 = t - (n - 1) > 0 ? t - (n - 1) : 0;
+      const int i = i0 + li, j = t - i;
+      if (i < j) rotated = jacobi_rt_rotate<M, NMAX>(At_g, W_g, Vt_g, i, j);
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, rotated);
+    __syncwarp();   // row / W / V updates visible before the next anti-diagonal
+    if (!done) {
+      const unsigned grp = (bal >> (8 * g)) & 0xffu;
+      chg_old |= (grp & half) != 0;
+      chg_new |= ((grp >> H) & half) != 0;
+      if (D > P) {   // a sweep ends in the older role
+        if (s_new >= 1 && t_new + P == D && (!chg_old || s_new - 1 == max_iter - 1)) done = true;
+      } else {       // n = 3: it ends where the next one starts
+        if (t_new == D && (!chg_new || s_new == max_iter - 1)) done = true;
+      }
+      if (t_new == P) {   // next step opens a new sweep; the newer one becomes the older one
+        chg_old = chg_new;
+        chg_new = false;
+        s_new++;
+      }
+    }
+    if (__all_sync(0xffffffffu, done)) break;
+  }
+}
+
 }  // namespace vo

@@ -93,6 +93,7 @@ struct PnpWarpSmem {
   double M[120];       // 10x12 design matrix; reused for l_6x10 (60) + rho (6) afterwards
   EpnpWork work;
   double var[3][13];   // per variant: reprojection error, R (9), t (3)
+  double vAt[3][30], vV[3][25], vW[3][5];   // the three 6 x n systems of the beta initialisations (U^T rows, V^T, norms)
 };
 
 __global__ void __launch_bounds__(SOLVE_WARPS * 32)
@@ -153,9 +154,22 @@ pnp_solve_kernel(const float3* __restrict__ xyz, const float2* __restrict__ xy, 
     epnp_prepare(sm.work, at, l_6x10, rho);
   }
   __syncwarp();
+  // the three beta initialisations: their 6 x n SVDs run as wavefronts side by side (lane group g = variant g + 1), the
+  // rest of a variant on one lane each (three lanes, one instruction stream)
   if (lane < 3) {
+    epnp_variant_system(lane + 1, l_6x10, sm.vAt[lane]);
+    jacobi_rt_init<6, 5>(sm.vAt[lane], sm.vW[lane], sm.vV[lane], epnp_variant_ncol(lane + 1));
+  }
+  __syncwarp();
+  jacobi_sweeps_groups<6, 5>(&sm.vAt[0][0], 30, &sm.vW[0][0], 5, &sm.vV[0][0], 25, lane < 24 ? epnp_variant_ncol((lane >> 3) + 1) : 0, lane);
+  __syncwarp();
+  if (lane < 3) {
+    const int ncol = epnp_variant_ncol(lane + 1);
+    double sw[5], bx[5] = {0, 0, 0, 0, 0};
+    jacobi_rt_finish<6, 5>(sm.vAt[lane], sw, sm.vV[lane], ncol);
+    svd_backsubst_6xn(sm.vAt[lane], sw, sm.vV[lane], rho, bx, ncol);
     double betas[4], R[3][3], t[3];
-    const double rep = epnp_variant(lane + 1, sm.work, K, at, l_6x10, rho, betas, R, t);
+    const double rep = epnp_variant_back(lane + 1, sm.work, K, at, l_6x10, rho, bx, betas, R, t);
     double* o = sm.var[lane];
     o[0] = rep;
     for (int i = 0; i < 3; i++) {

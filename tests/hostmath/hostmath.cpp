@@ -18,6 +18,51 @@ void hm_solve(const double* A, const double* b, int n, double* x) {
   if (n == 4) solve_svd<6, 4>(A, b, x);
   if (n == 5) solve_svd<6, 5>(A, b, x);
 }
+// cv::solve(A 6 x n, DECOMP_SVD) through the runtime-size Jacobi pieces; wavefront != 0 walks the pairs in the order and
+// with the completion rule of the device's lane-group schedule (jacobi_warp.cuh, jacobi_sweeps_groups): pair (i, j) of
+// sweep s at step s * n + i + j, two sweeps in flight, the sweep after an unchanged one started speculatively
+void hm_solve_rt(const double* A, const double* b, int n, int wavefront, double* x) {
+  double at[30], w[5], v[25], W[8];
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < 6; j++) at[i * 6 + j] = A[j * n + i];
+  if (!wavefront) {
+    jacobi_svd_rt<6, 5>(at, w, v, n);
+  } else {
+    const int max_iter = 30, H = n >> 1, P = n, D = 2 * n - 3;
+    jacobi_rt_init<6, 5>(at, W, v, n);
+    bool done = n < 2, chg_old = false, chg_new = false;
+    int s_new = 0;
+    for (int step = 1; !done; step++) {
+      const int t_new = step - s_new * P;
+      bool rot[8] = {false, false, false, false, false, false, false, false};
+      for (int idx = 0; idx < 2 * H; idx++) {      // the lanes of the group (their pairs are disjoint)
+        const bool is_new = idx >= H;
+        const int sweep = is_new ? s_new : s_new - 1;
+        const int t = is_new ? t_new : t_new + P;
+        if (sweep >= 0 && sweep < max_iter && t <= D) {
+          const int li = is_new ? idx - H : idx;
+          const int i0 = t - (n - 1) > 0 ? t - (n - 1) : 0;
+          const int i = i0 + li, j = t - i;
+          if (i < j) rot[idx] = jacobi_rt_rotate<6, 5>(at, W, v, i, j);
+        }
+      }
+      for (int idx = 0; idx < H; idx++) chg_old |= rot[idx];
+      for (int idx = H; idx < 2 * H; idx++) chg_new |= rot[idx];
+      if (D > P) {
+        if (s_new >= 1 && t_new + P == D && (!chg_old || s_new - 1 == max_iter - 1)) done = true;
+      } else {
+        if (t_new == D && (!chg_new || s_new == max_iter - 1)) done = true;
+      }
+      if (t_new == P) {
+        chg_old = chg_new;
+        chg_new = false;
+        s_new++;
+      }
+    }
+    jacobi_rt_finish<6, 5>(at, w, v, n);
+  }
+  svd_backsubst_6xn(at, w, v, b, x, n);
+}
 void hm_invert3(const double* A, double* inv) { invert3_svd(A, inv); }
 void hm_mtm12(const double* M, int rows, int fma_, double* out) {
   if (fma_) mul_transposed<12, true>(M, rows, out); else mul_transposed<12, false>(M, rows, out);

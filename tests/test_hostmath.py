@@ -56,6 +56,20 @@ def test_solve_invert_multransposed_bit_exact(lib):
             lib.hm_solve(P(A), P(b), n, P(x))
             _, x0 = cv2.solve(A, b.reshape(6, 1), flags=cv2.DECOMP_SVD)
             assert np.array_equal(x0.ravel(), x)
+    # the runtime-size pieces EPnP's beta initialisations use, serial and in the device's wavefront order (incl. rank-deficient
+    # and nearly converged systems, where the speculative next sweep must leave the data alone)
+    for n in (3, 4, 5):
+        for k in range(60):
+            A = rng.standard_normal((6, n)); b = rng.standard_normal(6)
+            if k % 3 == 1:
+                A[:, -1] = A[:, 0] * 2.0                      # rank deficient
+            if k % 3 == 2:
+                A = np.linalg.qr(rng.standard_normal((6, 6)))[0][:, :n] * rng.uniform(0.1, 10, n)   # orthogonal columns
+            _, x0 = cv2.solve(A, b.reshape(6, 1), flags=cv2.DECOMP_SVD)
+            for wavefront in (0, 1):
+                x = np.zeros(n)
+                lib.hm_solve_rt(P(np.ascontiguousarray(A)), P(b), n, wavefront, P(x))
+                assert np.array_equal(x0.ravel(), x), (n, k, wavefront)
     for _ in range(40):
         A = rng.standard_normal((3, 3)); inv = np.zeros((3, 3))
         lib.hm_invert3(P(A), P(inv))
