@@ -6,6 +6,8 @@
 #include <math.h>
 #include <stdarg.h>
 
+#include <cuda.h>   // types of the green-context driver API (entry points come through the runtime)
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -66,6 +68,107 @@ static void prof_drain(vo_ctx* c) {
 
 static void make_projections(const vo_params& p, double* P /*24*/);
 constexpr int F_CHUNK = 48, PNP_CHUNK = 32, F_CHUNK_TEMPORAL = 96;   // first-chunk sizes of the fused chains (see below)
+
+// ------------------------------------------------------------------------------------ SM partition (green contexts)
+// VO_B200_ISLAND=<SMs>: the device's SMs are split into an island and the rest; streams created on the two green
+// contexts are confined to their SMs.  The driver entry points come through the runtime (no libcuda link).
+static int partition_create(vo_ctx* c, int island_sms) {
+  typedef CUresult (*fn_devget)(CUdevice*, int);
+  typedef CUresult (*fn_getres)(CUdevice, CUdevResource*, CUdevResourceType);
+  typedef CUresult (*fn_split)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int);
+  typedef CUresult (*fn_desc)(CUdevResourceDesc*, CUdevResource*, unsigned int);
+  typedef CUresult (*fn_gcreate)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int);
+  typedef CUresult (*fn_gstream)(CUstream*, CUgreenCtx, unsigned int, int);
+  void* f[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  const char* names[6] = {"cuDeviceGet", "cuDeviceGetDevResource", "cuDevSmResourceSplitByCount", "cuDevResourceGenerateDesc",
+                          "cuGreenCtxCreate", "cuGreenCtxStreamCreate"};
+  for (int i = 0; i < 6; i++) {
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(names[i], &f[i], cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !f[i]) {
+      cudaGetLastError();
+      set_error("SM partition: %s is not available in this driver", names[i]);
+      return VO_ERR_CUDA;
+    }
+  }
+  CUdevice dev;
+  CUdevResource all, island, rest;
+  unsigned int nb = 1;
+  CUdevResourceDesc d_island, d_rest;
+  CUgreenCtx g_island = nullptr, g_big = nullptr;
+#define VO_CU(call)                                                   \
+  do {                                                                \
+    const CUresult r_ = (call);                                       \
+    if (r_ != CUDA_SUCCESS) {                                         \
+      set_error("SM partition: %s failed (%d)", #call, (int)r_);      \
+      return VO_ERR_CUDA;                                             \
+    }                                                                 \
+  } while (0)
+  VO_CU(((fn_devget)f[0])(&dev, c->device));
+  VO_CU(((fn_getres)f[1])(dev, &all, CU_DEV_RESOURCE_TYPE_SM));
+  VO_CU(((fn_split)f[2])(&island, &nb, &all, &rest, 0, (unsigned)island_sms));
+  VO_CU(((fn_desc)f[3])(&d_island, &island, 1));
+  VO_CU(((fn_desc)f[3])(&d_rest, &rest, 1));
+  VO_CU(((fn_gcreate)f[4])(&g_island, d_island, dev, CU_GREEN_CTX_DEFAULT_STREAM));
+  VO_CU(((fn_gcreate)f[4])(&g_big, d_rest, dev, CU_GREEN_CTX_DEFAULT_STREAM));
+  int lo = 0, hi = 0;
+  VO_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  CUstream si = nullptr, sl = nullptr, sa = nullptr;
+  VO_CU(((fn_gstream)f[5])(&si, g_island, CU_STREAM_NON_BLOCKING, hi));
+  VO_CU(((fn_gstream)f[5])(&sl, g_big, CU_STREAM_NON_BLOCKING, hi));
+  VO_CU(((fn_gstream)f[5])(&sa, g_big, CU_STREAM_NON_BLOCKING, lo));
+#undef VO_CU
+  c->g_island = g_island;
+  c->g_big = g_big;
+  c->s_island = (cudaStream_t)si;
+  c->s_lk = (cudaStream_t)sl;
+  c->s_lk_aux = (cudaStream_t)sa;
+  for (int i = 0; i < 4; i++) VO_CUDA(cudaEventCreateWithFlags(&c->ev_p[i], cudaEventDisableTiming));
+  c->island_sms = (int)island.sm.smCount;
+  if (getenv("VO_B200_DEBUG_FALLBACK"))
+    fprintf(stderr, "[vo partition] island %u SMs, rest %u SMs\n", island.sm.smCount, rest.sm.smCount);
+  return VO_OK;
+}
+
+static void partition_destroy(vo_ctx* c) {
+  if (!c->g_island && !c->g_big) return;
+  for (cudaStream_t st : {c->s_island, c->s_lk, c->s_lk_aux})
+    if (st) {
+      cudaStreamSynchronize(st);
+      cudaStreamDestroy(st);
+    }
+  for (int i = 0; i < 4; i++)
+    if (c->ev_p[i]) {
+      cudaEventDestroy(c->ev_p[i]);
+      c->ev_p[i] = nullptr;
+    }
+  typedef CUresult (*fn_gdestroy)(CUgreenCtx);
+  void* f = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuGreenCtxDestroy", &f, cudaEnableDefault, &q) == cudaSuccess && f) {
+    if (c->g_island) ((fn_gdestroy)f)((CUgreenCtx)c->g_island);
+    if (c->g_big) ((fn_gdestroy)f)((CUgreenCtx)c->g_big);
+  } else {
+    cudaGetLastError();
+  }
+  c->g_island = c->g_big = nullptr;
+  c->s_island = c->s_lk = c->s_lk_aux = nullptr;
+}
+
+// run `body` with c->stream replaced by `s` (a green-context stream): everything enqueued so far on c->stream precedes it,
+// everything enqueued afterwards on c->stream follows it
+template <class F>
+static int on_stream(vo_ctx* c, cudaStream_t s, cudaEvent_t e_in, cudaEvent_t e_out, F body) {
+  VO_CUDA(cudaEventRecord(e_in, c->stream));
+  VO_CUDA(cudaStreamWaitEvent(s, e_in, 0));
+  cudaStream_t keep = c->stream;
+  c->stream = s;
+  const int r = body();
+  c->stream = keep;
+  VO_TRY(r);
+  VO_CUDA(cudaEventRecord(e_out, s));
+  VO_CUDA(cudaStreamWaitEvent(c->stream, e_out, 0));
+  return VO_OK;
+}
 
 static int alloc_chain(vo_ctx* c) {
   const vo_params* p = &c->p;
@@ -153,6 +256,11 @@ static int alloc_chain(vo_ctx* c) {
 static void free_chain(vo_ctx* c) {
   if (!c) return;
   if (c->stream) cudaStreamSynchronize(c->stream);
+  for (int i = 0; i < 4; i++)      // partition events of an auxiliary chain (the streams belong to the main context)
+    if (c->ev_p[i]) {
+      cudaEventDestroy(c->ev_p[i]);
+      c->ev_p[i] = nullptr;
+    }
   sgbm_free(c);
   orb_free(c);
   void* dev[] = {c->d_xy_in, c->d_xy_trk, c->d_status, c->d_err, c->d_xyz_in, c->d_c_ref, c->d_c_trk, c->d_c_xyz,
@@ -356,6 +464,20 @@ int vo_create(const vo_params* p, vo_ctx** out) {
   }
   c->opt_host_chains = getenv("VO_B200_SEQ_HOST") != nullptr;      // read per context (tests flip them)
   c->opt_no_pyramid_ahead = getenv("VO_B200_NO_PYRAMID_AHEAD") != nullptr;
+  if (getenv("VO_B200_ISLAND") && atoi(getenv("VO_B200_ISLAND")) > 0) {
+    r = partition_create(c, atoi(getenv("VO_B200_ISLAND")));
+    if (r != VO_OK) {
+      vo_destroy(c);
+      return r;
+    }
+    // the stereo chain's LK launch goes to the large partition through its own (low-priority) stream and events
+    c->aux->s_lk_aux = c->s_lk_aux;
+    for (int i = 0; i < 2; i++)
+      if (cudaEventCreateWithFlags(&c->aux->ev_p[i], cudaEventDisableTiming) != cudaSuccess) {
+        vo_destroy(c);
+        return VO_ERR_CUDA;
+      }
+  }
   c->opt_lookahead = getenv("VO_B200_LOOKAHEAD") != nullptr;
   c->worker = std::thread(worker_main, c);
   *out = c;
@@ -388,6 +510,7 @@ int vo_destroy(vo_ctx* c) {
     free_chain(c->la);
     delete c->la;
   }
+  partition_destroy(c);
   if (c->ev_la) cudaEventDestroy(c->ev_la);
   if (c->ev_gather) cudaEventDestroy(c->ev_gather);
   if (c->ev_slk) cudaEventDestroy(c->ev_slk);
@@ -940,11 +1063,36 @@ static int track_pnp_fused_enqueue(vo_ctx* c, int slot_ref, int slot_cur, const 
   const int Hp = c->p.ransac_exhaustive ? iters : std::min(iters, PNP_CHUNK);
   const float thr2 = (float)(c->p.pnp_thr * c->p.pnp_thr);
   c->n_dev = d_n;
+  if (c->s_island) {
+    // SM partition: the LK launch on the large partition, the F-RANSAC stage on the island no LK launch can occupy
+    VO_TRY(on_stream(c, c->s_lk, c->ev_p[0], c->ev_p[1], [&]() {
+      return lk_launch(c, slot_ref, slot_cur, d_ref_xy, n, c->d_xy_trk, c->d_status, nullptr);
+    }));
+    // latency-bound kernels (compaction, sampling, 7-point solve, mask + compaction) on the island; the scoring launch
+    // is throughput work (1,080 CTAs) and runs on the whole device
+    const int H = fused_f_chunk(c, true);
+    const float thr2f = (float)(c->p.f_thr_temporal * c->p.f_thr_temporal);
+    VO_TRY(on_stream(c, c->s_island, c->ev_p[2], c->ev_p[3], [&]() {
+      VO_TRY(compact_launch(c, c->d_status, n, d_ref_xy, c->d_c_ref, c->d_xy_trk, c->d_c_trk, d_ref_xyz, c->d_c_xyz, nullptr, 0));
+      c->n_dev = c->d_count + 0;
+      VO_TRY(sample_launch(c, 7, c->d_c_ref, c->d_c_trk, n, H, c->d_samples, c->d_flags + 0));
+      return fmat_solve_launch(c, c->d_c_ref, c->d_c_trk, c->d_samples, H, c->d_models, c->d_counts);
+    }));
+    VO_TRY(fmat_score_select_launch(c, c->d_c_ref, c->d_c_trk, n, c->d_models, c->d_counts, H, thr2f, c->p.f_conf,
+                                    std::max(c->p.f_max_iters, 1), c->d_sel + 4));
+    VO_TRY(on_stream(c, c->s_island, c->ev_p[0], c->ev_p[1], [&]() {
+      return fmat_mask_compact_launch(c, c->d_c_ref, c->d_c_trk, c->d_c_xyz, n, c->d_models, c->d_sel + 4, thr2f, c->d_mask,
+                                      c->d_f_ref, c->d_f_trk, c->d_f_xyz, 1);
+    }));
+    c->n_dev = nullptr;
+    c->last_f_h = H;
+  } else {
   VO_TRY(lk_launch(c, slot_ref, slot_cur, d_ref_xy, n, c->d_xy_trk, c->d_status, nullptr));
   if (c->ev_lk_done) VO_CUDA(cudaEventRecord(c->ev_lk_done, c->stream));
   VO_TRY(compact_launch(c, c->d_status, n, d_ref_xy, c->d_c_ref, c->d_xy_trk, c->d_c_trk, d_ref_xyz, c->d_c_xyz, nullptr, 0));
   c->n_dev = nullptr;
   VO_TRY(enqueue_fmat_fused(c, n, c->p.f_thr_temporal, true));
+  }
   // PnP on d_f_* (count in d_count[1])
   c->n_dev = c->d_count + 1;
   VO_TRY(sample_launch(c, 5, nullptr, nullptr, n, Hp, c->d_samples, c->d_flags + 1));
@@ -990,6 +1138,11 @@ static int stereo_fused_enqueue(vo_ctx* c, int slot_l, int slot_r, int* n_grid_o
   // lk_after: the other chain's LK launch.  Either LK fills every SM; side by side they only slow each
   // other down, back to back this one overlaps the other chain's latency-bound RANSAC solvers instead.
   if (lk_after) VO_CUDA(cudaStreamWaitEvent(c->stream, lk_after, 0));
+  if (c->s_lk_aux) {
+    VO_TRY(on_stream(c, c->s_lk_aux, c->ev_p[0], c->ev_p[1], [&]() {
+      return lk_launch(c, slot_l, slot_r, c->d_xy_in, ng, c->d_xy_trk, c->d_status, nullptr);
+    }));
+  } else
   VO_TRY(lk_launch(c, slot_l, slot_r, c->d_xy_in, ng, c->d_xy_trk, c->d_status, nullptr));
   VO_TRY(compact_launch(c, c->d_status, ng, c->d_xy_in, c->d_c_ref, c->d_xy_trk, c->d_c_trk, nullptr, nullptr, nullptr, 0));
   VO_TRY(enqueue_fmat_fused(c, ng, c->p.f_thr_stereo, false));

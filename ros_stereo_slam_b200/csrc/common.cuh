@@ -126,6 +126,13 @@ struct vo_ctx {
   const uint8_t* pa_left = nullptr;  // identity (the pointer the caller announced / will pass)
   int pa_slot = -1;
   bool opt_no_pyramid_ahead = false; // VO_B200_NO_PYRAMID_AHEAD at vo_create
+  // SM partition (VO_B200_ISLAND=<SMs> at vo_create; CUDA green contexts): an island of a few SMs that no LK launch can
+  // occupy runs the tracking chain's F-RANSAC stage, the LK launches of both chains run on the rest
+  void* g_island = nullptr;          // CUgreenCtx
+  void* g_big = nullptr;
+  cudaStream_t s_island = nullptr, s_lk = nullptr, s_lk_aux = nullptr;
+  cudaEvent_t ev_p[4] = {nullptr, nullptr, nullptr, nullptr};
+  int island_sms = 0;
   bool pf_by_worker = false;         // this call's prefetch copies are issued by the stereo worker thread
   bool opt_host_chains = false;      // VO_B200_SEQ_HOST at vo_create: host-driven chains also when the keyframe is known
   bool opt_lookahead = false;        // VO_B200_LOOKAHEAD at vo_create (needs the host-driven chains)

@@ -789,6 +789,40 @@ def test_pyramid_ahead_changes_the_schedule_not_the_numbers():
         assert np.array_equal(got[1][0], plain[1][0]) and np.array_equal(got[1][1], plain[1][1]), mode
 
 
+def test_sm_partition_changes_the_schedule_not_the_numbers():
+    """VO_B200_ISLAND=8 (CUDA green contexts): the LK launches of both chains run on 140 SMs, the tracking chain's
+    latency-bound F-RANSAC kernels on an 8-SM island no LK launch can occupy.  Every frame result must equal the
+    default schedule's."""
+    import os
+    sc = synth.Scene(4)
+    n = 5
+    Ls = [np.ascontiguousarray(sc.render(i, "L")) for i in range(n)]
+    Rs = [np.ascontiguousarray(sc.render(i, "R")) for i in range(n)]
+
+    def fields(res):
+        return (res.n_lk_in, res.n_tracked, res.n_inliers, res.attempt_used, res.keyframe, res.n_kf_points,
+                res.n_lk_in_stereo, tuple(res.rvec), tuple(res.tvec), tuple(res.pose3x4))
+
+    out = []
+    for island in (None, "8"):
+        if island:
+            os.environ["VO_B200_ISLAND"] = island
+        try:
+            fe = make_frontend(kf_min_inliers=2 ** 31 - 1, grid_step=9)
+        finally:
+            os.environ.pop("VO_B200_ISLAND", None)
+        fe.seq_init(Ls[0], Rs[0])
+        rows = []
+        for i in range(1, n):
+            res, code = fe.seq_track(Ls[i], Rs[i])
+            assert code == 0
+            rows.append(fields(res))
+        out.append((rows, fe.seq_reference()))
+        fe.close()
+    assert out[0][0] == out[1][0]
+    assert np.array_equal(out[0][1][0], out[1][1][0]) and np.array_equal(out[0][1][1], out[1][1][1])
+
+
 def test_small_point_sets_take_opencv_paths(fe, G):
     """SURVEY 8 a-5 / a-7 small-N behaviour (missing items 1-2): findFundamentalMat with 7 and 8..14 points,
     solvePnPRansac with 5 and 4 points, against the live cv2."""
