@@ -74,7 +74,7 @@ def bench_config(world, steps, warmup):
 
 # ----------------------------------------------------------------------------- helpers
 class ClockSampler:
-    """SM clocks and throttle reasons of the given GPUs, sampled every 20 ms by an NVML thread of THIS process while it
+    """SM clocks and throttle reasons of the given GPUs, sampled every ~10 ms by an NVML thread of THIS process while it
     is running (started before the warm-up, so the timed region lies inside the sampled span; mark() brackets it).
     A spawned `nvidia-smi -lms` -- the first version -- starts up inside a 20 ms timed region and takes driver locks
     the frame loop needs; at N > 1 only rank 0 samples (all N GPUs), the other ranks run undisturbed."""
@@ -111,7 +111,7 @@ class ClockSampler:
                                           get_reasons(h)))
                     except Exception:   # noqa: BLE001
                         pass
-                time.sleep(0.02)
+                time.sleep(0.008)
 
         self.thread = threading.Thread(target=loop, daemon=True)
         self.thread.start()
@@ -139,7 +139,7 @@ class ClockSampler:
             per_gpu.setdefault(r[1], []).append(r[2])
         out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max((r[3] for r in used), default=None),
                "samples": len(used), "samples_inside_timed_region": len(inside),
-               "reasons": [n for n, b in self.REASONS if bits & b], "source": "NVML, 20 ms period"}
+               "reasons": [n for n, b in self.REASONS if bits & b], "source": "NVML thread, ~10 ms period"}
         if len(self.devices) > 1:
             out["sm_mhz_per_gpu"] = {str(d): float(np.median(v)) for d, v in sorted(per_gpu.items())}
         return out
