@@ -1883,16 +1883,25 @@ int vo_seq_track(vo_ctx* c, const uint8_t* left, const uint8_t* right, int strid
   int kk = 0, ng = 0;
   int k = 0, ni = 0, att = 1;
   int r;
+  bool stereo_synced = false;
   if (have_la) {
     // this frame's tracks: the F-RANSAC inliers of the keyframe (aux->d_idx, order of d_seq_xy) out of the look-ahead
     // launch over all stereo-LK survivors
     VO_TRY(gather_tracks_launch(c, a->d_idx, c->seq_n, c->la->d_xy_trk, c->la->d_status, c->d_xy_trk, c->d_status));
   }
-  VO_CUDA(cudaEventRecord(c->ev_gather, c->stream));   // the look-ahead buffers and aux->d_idx are free again
-  if (c->xform_pending) {   // previous frame's world transform still reads the stereo chain's outputs
-    VO_CUDA(cudaStreamWaitEvent(a->stream, c->ev_xform, 0));
-    c->xform_pending = false;
-  }
+  // (host calls in front of the tracking chain's LK launch are GPU idle time at the frame boundary: only those the launch
+  // depends on come first)
+  const bool fused_frame = kf_known && c->seq_n > 0 && temporal_fusable(c) && !host_driven;
+  if (!fused_frame || la_enabled)
+    VO_CUDA(cudaEventRecord(c->ev_gather, c->stream));   // the look-ahead buffers and aux->d_idx are free again
+  auto release_aux = [&]() -> int {
+    if (c->xform_pending) {   // previous frame's world transform still reads the stereo chain's outputs
+      VO_CUDA(cudaStreamWaitEvent(a->stream, c->ev_xform, 0));
+      c->xform_pending = false;
+    }
+    return VO_OK;
+  };
+  if (!fused_frame) VO_TRY(release_aux());
   // Two drivers for the dual-chain frame.  Measured on the bench workload (B200, 60 frames, round 2):
   //   fused single-sync chains enqueued by this thread (device-side sampling)                  868 frames/s, e2e 876
   //   host-driven chains, stereo chain on the worker thread (2-3 synchronisations per chain)  883 frames/s, e2e 873
@@ -1900,12 +1909,13 @@ int vo_seq_track(vo_ctx* c, const uint8_t* left, const uint8_t* right, int strid
   // per frame instead of seven, which is what keeps eight ranks on one host from disturbing each other.  (Round 1
   // measured 919 vs 956 the other way round: without the host gaps the tracking chain reaches pnp_solve_kernel
   // while the stereo chain's LK is still running.)  The look-ahead lives in the host-driven form only.
-  if (kf_known && c->seq_n > 0 && temporal_fusable(c) && !host_driven) {
+  if (fused_frame) {
     // both chains are enqueued by this thread, the critical one (tracking + PnP, high-priority
     // stream) first; one synchronisation per chain at the end
     VO_CUDA(cudaEventRecord(c->ev_left, c->stream));           // cur-left pyramid is complete
     int rs = VO_OK;
     if (getenv("VO_B200_STEREO_FIRST")) {
+      VO_TRY(release_aux());
       VO_CUDA(cudaStreamWaitEvent(a->stream, c->ev_left, 0));
       rs = load_image(a, 2, right, stride, is_device, false);
       if (rs == VO_OK) rs = stereo_fused_enqueue(a, cur, 2, &ng);
@@ -1916,6 +1926,7 @@ int vo_seq_track(vo_ctx* c, const uint8_t* left, const uint8_t* right, int strid
       const int rt = track_pnp_fused_enqueue(c, ref, cur, c->d_seq_xy, c->d_seq_xyz, c->seq_n);
       c->ev_lk_done = nullptr;
       VO_TRY(rt);
+      VO_TRY(release_aux());
       VO_CUDA(cudaStreamWaitEvent(a->stream, c->ev_left, 0));
       rs = load_image(a, 2, right, stride, is_device, false);
       if (rs == VO_OK) rs = stereo_fused_enqueue(a, cur, 2, &ng, lk_order ? c->ev_lk : nullptr);
@@ -1926,7 +1937,7 @@ int vo_seq_track(vo_ctx* c, const uint8_t* left, const uint8_t* right, int strid
     r = temporal_finish(c, &k, &ni, &att);
     if (rs == VO_OK) rs = stereo_fused_finish(a, &kk);
     else cudaStreamSynchronize(a->stream);
-    VO_CUDA(cudaEventRecord(c->ev_stereo, a->stream));
+    stereo_synced = true;     // the host has waited for the stereo chain: the epilogue needs no event on it
     if (r == VO_OK) r = rs;
   } else {
     if (kf_known) {
@@ -1992,7 +2003,7 @@ int vo_seq_track(vo_ctx* c, const uint8_t* left, const uint8_t* right, int strid
   pose_from_pnp(out->rvec, out->tvec, out->pose3x4);
   if (kf_known) {
     // insertKeyFrames epilogue: world points = pose * camera points (src/keyFrameManagement.cpp:20-30)
-    VO_CUDA(cudaStreamWaitEvent(c->stream, c->ev_stereo, 0));
+    if (!stereo_synced) VO_CUDA(cudaStreamWaitEvent(c->stream, c->ev_stereo, 0));
     VO_TRY(keyframe_epilogue_launch(c, out->pose3x4, a->d_xyz_tmp, a->d_f_ref, kk, c->d_seq_xyz, c->d_seq_xy));
     c->seq_n = kk;
     out->keyframe = 1;
