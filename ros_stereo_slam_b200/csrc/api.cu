@@ -1058,7 +1058,7 @@ static bool fmat_fused_valid(const vo_ctx* c, int m, int H) {
 // d_n (optional): device-resident number of reference points (n is then only the upper bound the
 // grids are sized with) -- what a CUDA-graph replay needs.
 static int track_pnp_fused_enqueue(vo_ctx* c, int slot_ref, int slot_cur, const float2* d_ref_xy,
-                                   const float3* d_ref_xyz, int n, const int* d_n = nullptr) {
+                                   const float3* d_ref_xyz, int n, const int* d_n = nullptr, bool lk_done = false) {
   const int iters = std::max(c->p.pnp_iters, 1);
   const int Hp = c->p.ransac_exhaustive ? iters : std::min(iters, PNP_CHUNK);
   const float thr2 = (float)(c->p.pnp_thr * c->p.pnp_thr);
@@ -1087,7 +1087,7 @@ static int track_pnp_fused_enqueue(vo_ctx* c, int slot_ref, int slot_cur, const 
     c->n_dev = nullptr;
     c->last_f_h = H;
   } else {
-  VO_TRY(lk_launch(c, slot_ref, slot_cur, d_ref_xy, n, c->d_xy_trk, c->d_status, nullptr));
+  if (!lk_done) VO_TRY(lk_launch(c, slot_ref, slot_cur, d_ref_xy, n, c->d_xy_trk, c->d_status, nullptr));
   if (c->ev_lk_done) VO_CUDA(cudaEventRecord(c->ev_lk_done, c->stream));
   VO_TRY(compact_launch(c, c->d_status, n, d_ref_xy, c->d_c_ref, c->d_xy_trk, c->d_c_trk, d_ref_xyz, c->d_c_xyz, nullptr, 0));
   c->n_dev = nullptr;
@@ -1245,6 +1245,11 @@ static int lookahead_enqueue(vo_ctx* c, int m, int slot_cur, int slot_next, cons
   c->la_left = identity;
   c->la_m = m;
   return VO_OK;
+}
+
+static bool lk_order_env() {
+  static const bool v = getenv("VO_B200_LK_ORDER") != nullptr;
+  return v;
 }
 
 // The announced next frame's left pyramid, built ahead on the `la` stream into the slot the next call will use as its
@@ -1871,11 +1876,14 @@ int vo_seq_track(vo_ctx* c, const uint8_t* left, const uint8_t* right, int strid
     c->la_valid = false;
   }
   bool have_pa = false;     // the previous call built this image's pyramid ahead (pyramid_ahead_enqueue)
+  const bool lk_was_ahead = c->lk_ahead;   // ... and enqueued this frame's tracking LK behind its epilogue
+  c->lk_ahead = false;
   if (c->pa_valid) {
     have_pa = !have_la && c->pa_left == left_id && c->pa_slot == cur;
-    VO_CUDA(cudaStreamWaitEvent(c->stream, c->ev_la, 0));     // either way: it writes a slot this call may use
+    if (!lk_was_ahead) VO_CUDA(cudaStreamWaitEvent(c->stream, c->ev_la, 0));     // either way: it writes a slot this call may use
     c->pa_valid = false;
   }
+  const bool lk_done_ahead = lk_was_ahead && have_pa && c->seq_n == c->lk_ahead_n;
   // with derivatives: this left image is the previous image of this frame's stereo LK and of the
   // next frame's temporal LK (one fused launch builds levels, borders and Scharr planes)
   if (!have_la && !have_pa) VO_TRY(load_image(c, cur, left, stride, is_device, true));
@@ -1912,22 +1920,26 @@ int vo_seq_track(vo_ctx* c, const uint8_t* left, const uint8_t* right, int strid
   if (fused_frame) {
     // both chains are enqueued by this thread, the critical one (tracking + PnP, high-priority
     // stream) first; one synchronisation per chain at the end
-    VO_CUDA(cudaEventRecord(c->ev_left, c->stream));           // cur-left pyramid is complete
+    // cur-left pyramid is complete: the stereo chain waits for this.  With the tracking LK already in the stream (LK-ahead)
+    // an event recorded here would fire after that launch; the pyramid's own completion event stands in
+    cudaEvent_t left_ready = c->ev_left;
+    if (lk_done_ahead) left_ready = c->ev_la;
+    else VO_CUDA(cudaEventRecord(c->ev_left, c->stream));
     int rs = VO_OK;
     if (getenv("VO_B200_STEREO_FIRST")) {
       VO_TRY(release_aux());
-      VO_CUDA(cudaStreamWaitEvent(a->stream, c->ev_left, 0));
+      VO_CUDA(cudaStreamWaitEvent(a->stream, left_ready, 0));
       rs = load_image(a, 2, right, stride, is_device, false);
       if (rs == VO_OK) rs = stereo_fused_enqueue(a, cur, 2, &ng);
       VO_TRY(track_pnp_fused_enqueue(c, ref, cur, c->d_seq_xy, c->d_seq_xyz, c->seq_n));
     } else {
-      static const bool lk_order = getenv("VO_B200_LK_ORDER") != nullptr;   // measured: slower (835 vs 853 frames/s)
+      static const bool lk_order = lk_order_env();   // measured: slower (835 vs 853 frames/s)
       c->ev_lk_done = lk_order ? c->ev_lk : nullptr;
-      const int rt = track_pnp_fused_enqueue(c, ref, cur, c->d_seq_xy, c->d_seq_xyz, c->seq_n);
+      const int rt = track_pnp_fused_enqueue(c, ref, cur, c->d_seq_xy, c->d_seq_xyz, c->seq_n, nullptr, lk_done_ahead);
       c->ev_lk_done = nullptr;
       VO_TRY(rt);
       VO_TRY(release_aux());
-      VO_CUDA(cudaStreamWaitEvent(a->stream, c->ev_left, 0));
+      VO_CUDA(cudaStreamWaitEvent(a->stream, left_ready, 0));
       rs = load_image(a, 2, right, stride, is_device, false);
       if (rs == VO_OK) rs = stereo_fused_enqueue(a, cur, 2, &ng, lk_order ? c->ev_lk : nullptr);
     }
@@ -2015,6 +2027,14 @@ int vo_seq_track(vo_ctx* c, const uint8_t* left, const uint8_t* right, int strid
     VO_CUDA(cudaEventRecord(c->ev_xform, c->stream));
     c->xform_pending = true;
     c->seq_ref_slot = cur;
+    // LK-ahead: the announced next frame's pyramid is (being) built; its tracking LK only needs that pyramid and the
+    // points the epilogue above has just produced.  Enqueued now, it runs while the caller turns around.
+    if (fused_frame && c->pa_valid && c->pa_slot == next_left_slot(cur) && kk > 0 && !c->s_island && !lk_order_env()) {
+      VO_CUDA(cudaStreamWaitEvent(c->stream, c->ev_la, 0));
+      VO_TRY(lk_launch(c, cur, c->pa_slot, c->d_seq_xy, kk, c->d_xy_trk, c->d_status, nullptr));
+      c->lk_ahead = true;
+      c->lk_ahead_n = kk;
+    }
     return VO_OK;
   } else if (ni < c->p.kf_min_inliers || force_keyframe) {
     // keyframe: src/VisualSLAM.cpp:120-137 -> insertKeyFrames (src/keyFrameManagement.cpp:9-31)

@@ -126,6 +126,10 @@ struct vo_ctx {
   const uint8_t* pa_left = nullptr;  // identity (the pointer the caller announced / will pass)
   int pa_slot = -1;
   bool opt_no_pyramid_ahead = false; // VO_B200_NO_PYRAMID_AHEAD at vo_create
+  // ... and when that pyramid exists, the NEXT frame's tracking LK launch is enqueued at the end of this call, behind the
+  // keyframe epilogue that produces its input points: it runs while the caller turns around instead of after it
+  bool lk_ahead = false;
+  int lk_ahead_n = 0;
   // SM partition (VO_B200_ISLAND=<SMs> at vo_create; CUDA green contexts): an island of a few SMs that no LK launch can
   // occupy runs the tracking chain's F-RANSAC stage, the LK launches of both chains run on the rest
   void* g_island = nullptr;          // CUgreenCtx
