@@ -358,7 +358,8 @@ int vo_seq_prefetch(vo_ctx* ctx, const uint8_t* left, const uint8_t* right, int 
 /* The same announcement for either kind of pointer: is_device = 0 is vo_seq_prefetch; is_device != 0 announces a
  * frame that is already resident in device memory (nothing is copied).  When the keyframe policy inserts a keyframe
  * on every frame, an announced frame (of either kind) lets the library build the NEXT frame's left image pyramid -- which
- * depends on nothing but the image -- on a third stream while the current frame is processed (default), or, opt-in
+ * depends on nothing but the image -- on a third stream while the current frame is processed and enqueue that frame's
+ * tracking LK at the end of the current call, behind the epilogue that produces its input points (default), or, opt-in
  * (VO_B200_LOOKAHEAD=1 with VO_B200_SEQ_HOST=1), run the next frame's whole temporal LK there.  The announced image
  * must stay unchanged until the vo_seq_track call that passes it has returned; the next vo_seq_track call must pass
  * the announced pointers to use the work done ahead, any other image simply discards it.
