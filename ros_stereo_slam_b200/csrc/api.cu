@@ -1289,6 +1289,7 @@ static int pyramid_ahead_enqueue(vo_ctx* c, int slot_next, const uint8_t* curren
 static void lookahead_quiesce(vo_ctx* c) {
   if (c->la && (c->la_inflight || c->la_valid || c->pa_valid)) cudaStreamSynchronize(c->la->stream);
   c->pa_valid = false;
+  c->lk_ahead = false;
   c->la_inflight = c->la_valid = false;
   c->ann_left = c->ann_right = nullptr;
 }
