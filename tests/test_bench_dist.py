@@ -49,3 +49,16 @@ def test_dist_env_defaults(monkeypatch):
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
         monkeypatch.delenv(k, raising=False)
     assert bench.dist_env() == (0, 1, 0)
+
+
+def test_clock_sampler_without_nvml():
+    """no GPU driver here: the sampler reports that instead of raising, and a rank that does not sample says so"""
+    import bench
+    s = bench.ClockSampler([0])
+    s.start()
+    s.mark_begin()
+    s.mark_end()
+    out = s.stop()
+    assert out["sm_mhz"] is None and out["reasons"] and "NVML" in out["reasons"][0]
+    idle = bench.ClockSampler([])
+    assert idle.stop()["reasons"] == ["not sampled on this rank"]
